@@ -1,0 +1,139 @@
+/* rt3.h — C ABI of librt3.so: the B200-native (sm_100a) wavefront path tracer that replaces
+ * the OptiX engine underneath rendertoy3o's device-scene operators.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the
+ * rendertoy3C tree).  Conventions:
+ *   - every call returns 0 on success, a negative rt3_status otherwise; rt3_last_error()
+ *     returns the thread-local message (reference: exceptions from src/util/exception.h:11-96).
+ *   - host pointers are borrowed for the duration of the call only; device memory never
+ *     crosses the ABI except through the explicit download calls / rt3_accum_device_ptr.
+ *   - one context per GPU, externally synchronised (one host thread per context).
+ *   - there is NO CPU fallback: without a CUDA device rt3_context_create fails with
+ *     RT3_ERR_NO_DEVICE.
+ */
+#ifndef RT3_H
+#define RT3_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    RT3_OK = 0,
+    RT3_ERR_INVALID = -1,   /* bad argument */
+    RT3_ERR_CUDA = -2,      /* CUDA runtime error (message has file:line) */
+    RT3_ERR_NO_DEVICE = -3, /* no usable CUDA device: there is no CPU fallback */
+    RT3_ERR_STATE = -4,     /* call out of order (e.g. launch before accel build) */
+    RT3_ERR_UNSUPPORTED = -5,
+    RT3_ERR_NCCL = -6
+} rt3_status;
+
+typedef struct rt3_context* rt3_context_t; /* replaces OptixContext + CUDAScene (src/cuda/optix_context.h:231-271, src/cuda/cuda_scene.h:124-183) */
+typedef uint64_t rt3_handle_t;             /* replaces OptixTraversableHandle of a GAS (src/cuda/cuda_mesh.h:165) */
+
+/* Batch ray / hit records of the rt3_trace test hook (no reference equivalent: optixTraverse
+ * is device-only, src/shader/shader_common.h:74-88).  16-byte aligned on purpose. */
+typedef struct { float o[3]; float tmin; float d[3]; float tmax; float time; float pad[3]; } rt3_ray;   /* 48 B */
+typedef struct { float t, u, v; int32_t prim; int32_t inst; int32_t pad[3]; } rt3_hit;                  /* 32 B; prim = inst = -1 on miss */
+
+/* Launch parameters: replaces RenderSettings (src/shader/shader_data.h:71-114).  The accum /
+ * frame buffers and the light array live inside the context instead of being raw pointers. */
+typedef struct {
+    uint32_t width, height;        /* film_settings.width/height */
+    uint32_t samples_per_launch;   /* film_settings.samples_per_launch (reference default 8, src/wavefront.cpp:55) */
+    uint32_t subframe_index;       /* film_settings.subframe_index: seeds tea<4>(pixel, subframe) (src/shader/raygen.cu:25) */
+    float eye[3], U[3], V[3], W[3];/* camera_settings (sutil/Camera.cpp:34-45) */
+    int32_t max_depth;             /* extension: max extension rays per path; <=0 = unbounded like the reference (src/shader/raygen.cu:48) */
+    int32_t mode;                  /* 0 = REFERENCE_FAITHFUL estimator (only mode in round 1) */
+    float miss_color[3];           /* __direct_callable__test returns (0.01,0.01,0.01) (src/shader/test.cu:5) */
+    int32_t accum_mode;            /* 0 = running mean exactly as src/shader/raygen.cu:79-85; 1 = per-pixel SUM of subframe means (for the multi-GPU reduce) */
+} rt3_render_settings;
+
+typedef struct {
+    uint64_t rays_primary, rays_bounce, rays_shadow; /* rays actually traversed, device-counted */
+    uint64_t samples;                                /* pixel-samples completed */
+    uint64_t kernel_launches;                        /* number of librt3 kernels launched so far */
+    float ms_generate, ms_extend, ms_shade, ms_connect, ms_resolve; /* CUDA-event time of the LAST subframe, per stage (0 if timing disabled) */
+    float ms_total;
+    uint32_t max_stack_depth;                        /* traversal stack high-water mark (debug) */
+    uint32_t error_flags;                            /* bit0: traversal stack overflow */
+} rt3_stats;
+
+/* texture enums: identical values to CUDATexture<T>::AddressMode / FilterMode
+ * (src/cuda/cuda_texture.h:16-28).  NOTE the reference casts FilterMode::Linear (=0) to
+ * cudaTextureFilterMode where 0 is POINT; filter_mode 0 therefore means point sampling. */
+enum { RT3_ADDRESS_WRAP = 0, RT3_ADDRESS_CLAMP = 1, RT3_ADDRESS_MIRROR = 2, RT3_ADDRESS_BORDER = 3 };
+enum { RT3_FILTER_REFERENCE_LINEAR_IS_POINT = 0 };
+
+/* ---- context -------------------------------------------------------------------------- */
+int rt3_context_create(int device, rt3_context_t* out);   /* OptixContext() src/cuda/optix_context.h:231-243 */
+void rt3_context_destroy(rt3_context_t ctx);              /* ~CUDAScene src/cuda/cuda_scene.h:161-169 */
+int rt3_sync(rt3_context_t ctx);                          /* CUDA_SYNC_CHECK src/wavefront.cpp:221 */
+const char* rt3_last_error(void);
+int rt3_get_stats(rt3_context_t ctx, rt3_stats* out);
+int rt3_reset_stats(rt3_context_t ctx);
+int rt3_set_option(rt3_context_t ctx, const char* key, int value); /* tuning switches: "timing", "sort_rays", "sort_materials", "persist_ctas_per_sm" */
+
+/* ---- geometry (BLAS) ------------------------------------------------------------------- */
+/* CUDAMesh(ctx, mesh) src/cuda/cuda_mesh.h:33-155: uploads vertex/index/normal/uv arrays and
+ * builds the BLAS (there: optixAccelBuild + compaction; here: GPU LBVH -> compressed BVH8).
+ * verts [num_keys][nv][3] (key 0 is used; vertex-key motion is SURVEY 8f/N2), idx [nt][3],
+ * normals [nv][3], uvs [nv][2] (both required, like the reference, Q11). */
+int rt3_mesh_create(rt3_context_t ctx, const float* verts, int num_keys, int nv, const int32_t* idx, int nt,
+                    const float* normals, const float* uvs, rt3_handle_t* blas);
+/* analytic spheres, center_radius [n][4] (cuda/GeometryData.h:83-87, test per cuda/sphere.cu:37-97) */
+int rt3_spheres_create(rt3_context_t ctx, const float* center_radius, int n, rt3_handle_t* blas);
+/* round curves; degree 1 (linear segments) in round 1.  cp_radius [ncp][4], segment i uses
+ * control points seg_first_cp[i], seg_first_cp[i]+1 (cuda/curve.h:38-80, cuda/GeometryData.h:127-133) */
+int rt3_curves_create(rt3_context_t ctx, int degree, const float* cp_radius, int ncp, const int32_t* seg_first_cp,
+                      int nseg, rt3_handle_t* blas);
+/* CUDATexture<uchar4>(w,h,data,address,filter) src/cuda/cuda_texture.h:46-75 */
+int rt3_texture_create(rt3_context_t ctx, const uint8_t* rgba8, int w, int h, int address_mode, int filter_mode, int* tex_id);
+
+/* ---- instances (TLAS) ------------------------------------------------------------------ */
+/* CUDAAccel::append_instance src/cuda/cuda_accel.h:75-90 (instanceId = sbtOffset = index) */
+int rt3_accel_append_instance(rt3_context_t ctx, rt3_handle_t blas, const float xform[12], int* instance_id);
+/* CUDAAccel::append_animated_instance src/cuda/cuda_accel.h:38-73: keys [nkeys][12] row-major 3x4,
+ * OptixMotionOptions{numKeys,timeBegin,timeEnd}, plus the static instance transform */
+int rt3_accel_append_animated_instance(rt3_context_t ctx, rt3_handle_t blas, const float* keys, int nkeys,
+                                       float t_begin, float t_end, const float static_xform[12], int* instance_id);
+int rt3_accel_build(rt3_context_t ctx);                   /* CUDAAccel::build src/cuda/cuda_accel.h:92-150 */
+
+/* ---- shading records / lights ----------------------------------------------------------- */
+/* one HitGroupRecord per instance: CUDAScene::create_sbt src/cuda/cuda_scene.h:54-88, HitGroupData src/shader/shader_data.h:125-136 */
+int rt3_scene_set_hitgroup(rt3_context_t ctx, int instance_id, const float emission[3], const float diffuse[3], int tex_id);
+/* buildLightSampler src/wavefront.cpp:257-275: array of 68-byte rendertoy3o::Light (src/light.h:13-22) */
+int rt3_scene_set_lights(rt3_context_t ctx, const void* lights68, int n);
+/* Light ctor src/light.h:24-30 (host helper, pure arithmetic) */
+int rt3_light_make(const float emission[3], const float v0[3], const float v1[3], const float v2[3], void* light68_out);
+/* sutil::Camera::UVWFrame sutil/Camera.cpp:34-45 (host helper, pure arithmetic) */
+int rt3_camera_uvw(const float eye[3], const float lookat[3], const float up[3], float fovy_deg, float aspect,
+                   float U[3], float V[3], float W[3]);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+/* launchSubframe src/wavefront.cpp:203-222 = update_cuda_params_async + optixLaunch(w,h,1):
+ * renders samples_per_launch paths per pixel through generate/extend/shade/connect/resolve
+ * and folds them into the context's float4 accumulation buffer.  Asynchronous on the
+ * context's stream. */
+int rt3_launch_subframe(rt3_context_t ctx, const rt3_render_settings* settings);
+/* batch closest-hit (any_hit=0) / occlusion (any_hit=1; hits[i].prim>=0 means occluded) query
+ * through the same traversal kernels, host buffers in and out.  Test hook + e2e bench leg. */
+int rt3_trace(rt3_context_t ctx, const rt3_ray* rays, int n, int any_hit, rt3_hit* hits);
+/* same, with rays/hits already resident in device memory of this context's GPU */
+int rt3_trace_device(rt3_context_t ctx, const void* d_rays, int n, int any_hit, void* d_hits);
+
+/* ---- results ---------------------------------------------------------------------------- */
+int rt3_download_accum(rt3_context_t ctx, float* rgba);   /* float4 accum_buffer [h][w][4]; row 0 = image bottom (Q19) */
+int rt3_download_frame(rt3_context_t ctx, uint8_t* rgba8);/* uchar4 frame_buffer, make_color cuda/helpers.h:57-66 */
+int rt3_accum_device_ptr(rt3_context_t ctx, void** d_ptr, uint64_t* n_floats); /* for an external collective (torch.distributed / NCCL) */
+/* after an external SUM reduce in accum_mode 1: accum = sum / total_subframes, refresh the u8 frame */
+int rt3_finalize_accum(rt3_context_t ctx, uint32_t total_subframes);
+/* single-process multi-GPU: NCCL sum of the accumulation buffers of n contexts (one per GPU), then
+ * finalize on each.  No reference equivalent (the reference is single-GPU). */
+int rt3_allreduce_accum(rt3_context_t* ctxs, int n, uint32_t total_subframes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,760 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see rt3o_math.hpp header).
+//
+// Scalar CPU restatement of rendertoy3o's path (Appendix A of SURVEY.md, draw for draw):
+//   raygen + path loop + RR + accumulate : src/shader/raygen.cu:14-87
+//   ray time draws                       : src/shader/shader_common.h:64,125
+//   closest-hit shading + NEE            : src/shader/closehit_radiance.cu:60-160
+//   miss                                 : src/shader/miss.cu:29-32 + src/shader/test.cu:5
+//   instance / SBT mapping               : src/cuda/cuda_accel.h:75-85, src/cuda/cuda_scene.h:60-82
+//   texture semantics (point, wrap)      : src/cuda/cuda_texture.h:52-74 (Q9)
+// Intersection is brute force over every instance x primitive (accel=0) or a binned-SAH
+// BVH2 with padded boxes (accel=1, validated against accel=0 in tests/); tie-break on equal
+// t: lowest instance id, then lowest primitive id.
+// PARITY NOTE: the reference ships no tests/goldens and cannot be built here (OptiX), so
+// only the KAT-level functions are pinned by reference code (tests/golden/ref_kat.json);
+// hits and images are "parity unpinned" by the reference and pinned by this oracle.
+#include "rt3o.h"
+#include "rt3o_math.hpp"
+#include "rt3o_prims.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace rt3o;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Box {
+    f3 lo{3e38f, 3e38f, 3e38f}, hi{-3e38f, -3e38f, -3e38f};
+    void grow(f3 p) {
+        lo = {fminf(lo.x, p.x), fminf(lo.y, p.y), fminf(lo.z, p.z)};
+        hi = {fmaxf(hi.x, p.x), fmaxf(hi.y, p.y), fmaxf(hi.z, p.z)};
+    }
+    void grow(const Box& b) { grow(b.lo); grow(b.hi); }
+    float area() const {
+        f3 e = hi - lo;
+        return 2.0f * (e.x * e.y + e.y * e.z + e.z * e.x);
+    }
+};
+
+// ------------------------------------------------------------------ BVH2 (oracle-only accelerator)
+struct Bvh2 {
+    struct Node { Box box; int left, right, first, count, axis; };  // leaf when count > 0
+    std::vector<Node> nodes;
+    std::vector<int> order;
+
+    void build(const std::vector<Box>& boxes) {
+        nodes.clear();
+        int n = (int)boxes.size();
+        order.resize(n);
+        for (int i = 0; i < n; i++) order[i] = i;
+        if (n == 0) return;
+        std::vector<f3> cent(n);
+        for (int i = 0; i < n; i++) cent[i] = (boxes[i].lo + boxes[i].hi) * 0.5f;
+        nodes.reserve(2 * n);
+        nodes.push_back({});
+        struct Item { int node, first, count; };
+        std::vector<Item> todo{{0, 0, n}};
+        while (!todo.empty()) {
+            Item it = todo.back();
+            todo.pop_back();
+            Box b, cb;
+            for (int i = it.first; i < it.first + it.count; i++) { b.grow(boxes[order[i]]); cb.grow(cent[order[i]]); }
+            // pad: culling must stay conservative w.r.t. the brute-force primitive tests
+            f3 pad = {1e-5f * (fabsf(b.lo.x) + fabsf(b.hi.x)) + 1e-7f, 1e-5f * (fabsf(b.lo.y) + fabsf(b.hi.y)) + 1e-7f,
+                      1e-5f * (fabsf(b.lo.z) + fabsf(b.hi.z)) + 1e-7f};
+            Node nd;
+            nd.box.lo = b.lo - pad;
+            nd.box.hi = b.hi + pad;
+            nd.left = nd.right = -1;
+            nd.first = it.first;
+            nd.count = it.count;
+            nd.axis = 0;
+            if (it.count > 4) {
+                f3 ext = cb.hi - cb.lo;
+                int axis = ext.x > ext.y ? (ext.x > ext.z ? 0 : 2) : (ext.y > ext.z ? 1 : 2);
+                float lo = get(cb.lo, axis), e = get(ext, axis);
+                int mid = -1;
+                if (e > 0) {
+                    const int NB = 16;
+                    Box bb[NB];
+                    int bc[NB] = {0};
+                    float k = NB * (1.0f - 1e-6f) / e;
+                    for (int i = it.first; i < it.first + it.count; i++) {
+                        int bi = (int)((get(cent[order[i]], axis) - lo) * k);
+                        bi = std::min(std::max(bi, 0), NB - 1);
+                        bb[bi].grow(boxes[order[i]]);
+                        bc[bi]++;
+                    }
+                    float la[NB], ra[NB];
+                    int lc[NB], rc[NB];
+                    Box acc;
+                    int c = 0;
+                    for (int i = 0; i < NB; i++) { if (bc[i]) acc.grow(bb[i]); c += bc[i]; la[i] = c ? acc.area() : 0; lc[i] = c; }
+                    acc = Box();
+                    c = 0;
+                    for (int i = NB - 1; i >= 0; i--) { if (bc[i]) acc.grow(bb[i]); c += bc[i]; ra[i] = c ? acc.area() : 0; rc[i] = c; }
+                    float best = 3e38f;
+                    int bs = -1;
+                    for (int i = 0; i < NB - 1; i++) {
+                        if (lc[i] == 0 || rc[i + 1] == 0) continue;
+                        float cost = la[i] * lc[i] + ra[i + 1] * rc[i + 1];
+                        if (cost < best) { best = cost; bs = i; }
+                    }
+                    if (bs >= 0) {
+                        auto pivot = std::partition(order.begin() + it.first, order.begin() + it.first + it.count, [&](int p) {
+                            int bi = (int)((get(cent[p], axis) - lo) * k);
+                            bi = std::min(std::max(bi, 0), NB - 1);
+                            return bi <= bs;
+                        });
+                        mid = (int)(pivot - order.begin());
+                    }
+                }
+                if (mid <= it.first || mid >= it.first + it.count) mid = it.first + it.count / 2;  // median fallback
+                nd.count = 0;
+                nd.axis = axis;
+                nd.left = (int)nodes.size();
+                nd.right = nd.left + 1;
+                nodes.push_back({});
+                nodes.push_back({});
+                todo.push_back({nd.left, it.first, mid - it.first});
+                todo.push_back({nd.right, mid, it.first + it.count - mid});
+            }
+            nodes[it.node] = nd;
+        }
+    }
+
+    // calls leaf(prim) for every primitive whose padded box the ray may touch within [tmin, *tfar]
+    template <class F>
+    bool traverse(f3 o, f3 d, float tmin, const float* tfar, F&& leaf) const {
+        if (nodes.empty()) return false;
+        f3 inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+        int stack[128];
+        int sp = 0;
+        stack[sp++] = 0;
+        while (sp) {
+            const Node& nd = nodes[stack[--sp]];
+            float t0 = tmin, t1 = *tfar;
+            bool ok = true;
+            for (int a = 0; a < 3 && ok; a++) {
+                float oa = get(o, a), da = get(d, a), lo = get(nd.box.lo, a), hi = get(nd.box.hi, a);
+                if (da == 0.0f) { ok = (oa >= lo && oa <= hi); continue; }
+                float ia = get(inv, a);
+                float ta = (lo - oa) * ia, tb = (hi - oa) * ia;
+                if (ta > tb) std::swap(ta, tb);
+                // widen by a few ulps (robust slab test)
+                ta -= fabsf(ta) * 4e-7f;
+                tb += fabsf(tb) * 4e-7f;
+                t0 = fmaxf(t0, ta);
+                t1 = fminf(t1, tb);
+                ok = t0 <= t1;
+            }
+            if (!ok) continue;
+            if (nd.count > 0) {
+                for (int i = nd.first; i < nd.first + nd.count; i++)
+                    if (leaf(order[i])) return true;
+            } else {
+                if (get(d, nd.axis) > 0.0f) { stack[sp++] = nd.right; stack[sp++] = nd.left; }
+                else { stack[sp++] = nd.left; stack[sp++] = nd.right; }
+            }
+        }
+        return false;
+    }
+};
+
+enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2 };
+
+struct Blas {
+    int type = PRIM_TRI;
+    std::vector<f3> verts, normals;
+    std::vector<f2> uvs;
+    std::vector<int32_t> idx;          // tris: 3 per prim
+    std::vector<float> cr;             // spheres: 4 per prim; curves: control points 4 per cp
+    std::vector<int32_t> seg;          // curves: first cp per segment
+    int nprims = 0;
+    Bvh2 bvh;
+    Box bounds;
+
+    Box prim_box(int p) const {
+        Box b;
+        if (type == PRIM_TRI) {
+            b.grow(verts[idx[3 * p]]); b.grow(verts[idx[3 * p + 1]]); b.grow(verts[idx[3 * p + 2]]);
+        } else if (type == PRIM_SPHERE) {
+            f3 c = {cr[4 * p], cr[4 * p + 1], cr[4 * p + 2]};
+            float r = cr[4 * p + 3];
+            b.grow(c - mk3(r, r, r)); b.grow(c + mk3(r, r, r));
+        } else {
+            int a = seg[p];
+            for (int k = 0; k < 2; k++) {
+                f3 c = {cr[4 * (a + k)], cr[4 * (a + k) + 1], cr[4 * (a + k) + 2]};
+                float r = cr[4 * (a + k) + 3];
+                b.grow(c - mk3(r, r, r)); b.grow(c + mk3(r, r, r));
+            }
+        }
+        return b;
+    }
+};
+
+struct Instance {
+    int blas;
+    Affine stat, stat_inv;
+    int nkeys = 0;
+    std::vector<float> keys;
+    float t0 = 0, t1 = 1;
+    f3 emission{0, 0, 0}, diffuse{0.8f, 0.8f, 0.8f};
+    int tex = -1;
+};
+
+struct Texture { int w, h, addr, filt; std::vector<uint8_t> px; };
+
+struct Hit { float t = 0, u = 0, v = 0; int prim = -1, inst = -1; };
+
+static inline bool better(float t, int inst, int prim, const Hit& h) {
+    if (h.prim < 0) return true;
+    if (t < h.t) return true;
+    if (t > h.t) return false;
+    if (inst != h.inst) return inst < h.inst;
+    return prim < h.prim;
+}
+
+}  // namespace
+
+struct rt3o_scene {
+    std::vector<std::unique_ptr<Blas>> blas;
+    std::vector<Instance> inst;
+    std::vector<Texture> tex;
+    std::vector<Light> lights;
+    Bvh2 tlas;
+    bool built = false;
+    uint32_t w = 0, h = 0;
+    std::vector<float> accum;
+    std::vector<uint8_t> frame;
+    std::atomic<uint64_t> n_primary{0}, n_bounce{0}, n_shadow{0}, n_samples{0};
+
+    // world -> object matrix of instance i at ray time
+    Affine world_to_object(const Instance& in, float time, bool& has_motion, Affine& motion_inv) const {
+        has_motion = in.nkeys > 0;
+        if (has_motion) {
+            Affine m = lerp_keys(in.keys.data(), in.nkeys, in.t0, in.t1, time);
+            motion_inv = invert_affine(m);
+        }
+        return in.stat_inv;
+    }
+    void to_object(const Instance& in, float time, f3 o, f3 d, f3& oo, f3& od) const {
+        oo = xform_point(in.stat_inv, o);
+        od = xform_vector(in.stat_inv, d);
+        if (in.nkeys > 0) {
+            Affine m = lerp_keys(in.keys.data(), in.nkeys, in.t0, in.t1, time);
+            Affine mi = invert_affine(m);
+            oo = xform_point(mi, oo);
+            od = xform_vector(mi, od);
+        }
+    }
+
+    // test one primitive of one BLAS in object space
+    static inline bool test_prim(const Blas& b, int p, f3 oo, f3 od, const RayShear& sh, float tmin, float tmax,
+                                 float& t, float& u, float& v) {
+        if (b.type == PRIM_TRI) {
+            return hit_triangle(oo, sh, b.verts[b.idx[3 * p]], b.verts[b.idx[3 * p + 1]], b.verts[b.idx[3 * p + 2]], tmin, tmax, t, u, v);
+        } else if (b.type == PRIM_SPHERE) {
+            u = v = 0;
+            return hit_sphere(oo, od, {b.cr[4 * p], b.cr[4 * p + 1], b.cr[4 * p + 2]}, b.cr[4 * p + 3], tmin, tmax, t);
+        } else {
+            int a = b.seg[p];
+            v = 0;
+            return hit_curve_linear(oo, od, {b.cr[4 * a], b.cr[4 * a + 1], b.cr[4 * a + 2]}, b.cr[4 * a + 3],
+                                    {b.cr[4 * a + 4], b.cr[4 * a + 5], b.cr[4 * a + 6]}, b.cr[4 * a + 7], tmin, tmax, t, u);
+        }
+    }
+
+    // closest hit (any_hit=false) or occlusion (any_hit=true)
+    Hit trace(f3 o, f3 d, float tmin, float tmax, float time, bool any_hit, int accel) const {
+        Hit best;
+        float tfar = tmax;
+        auto visit_instance = [&](int ii) -> bool {
+            const Instance& in = inst[ii];
+            const Blas& b = *blas[in.blas];
+            f3 oo, od;
+            to_object(in, time, o, d, oo, od);
+            RayShear sh = make_shear(od);
+            auto visit_prim = [&](int p) -> bool {
+                float t, u, v;
+                if (!test_prim(b, p, oo, od, sh, tmin, tmax, t, u, v)) return false;
+                if (better(t, ii, p, best)) {
+                    best.t = t; best.u = u; best.v = v; best.prim = p; best.inst = ii;
+                    tfar = t;
+                }
+                return any_hit;
+            };
+            if (accel == 0) {
+                for (int p = 0; p < b.nprims; p++)
+                    if (visit_prim(p)) return true;
+                return false;
+            }
+            return b.bvh.traverse(oo, od, tmin, &tfar, visit_prim);
+        };
+        if (accel == 0) {
+            for (int ii = 0; ii < (int)inst.size(); ii++)
+                if (visit_instance(ii)) break;
+        } else {
+            tlas.traverse(o, d, tmin, &tfar, visit_instance);
+        }
+        return best;
+    }
+
+    Box instance_world_box(const Instance& in) const {
+        const Blas& b = *blas[in.blas];
+        Box wb;
+        int nk = in.nkeys > 0 ? in.nkeys : 1;
+        for (int k = 0; k < nk; k++) {
+            for (int c = 0; c < 8; c++) {
+                f3 p = {(c & 1) ? b.bounds.hi.x : b.bounds.lo.x, (c & 2) ? b.bounds.hi.y : b.bounds.lo.y,
+                        (c & 4) ? b.bounds.hi.z : b.bounds.lo.z};
+                if (in.nkeys > 0) {
+                    Affine m;
+                    std::memcpy(m.m, in.keys.data() + 12 * k, sizeof(m.m));
+                    p = xform_point(m, p);
+                }
+                wb.grow(xform_point(in.stat, p));
+            }
+        }
+        return wb;
+    }
+
+    // ------------------------------------------------------------------ shading helpers
+    f3 fetch_texture(int id, float u, float v) const {
+        // point sampling, normalised coords, RGBA8 -> [0,1], no sRGB decode (Q9, Q10)
+        const Texture& tx = tex[id];
+        auto addr = [&](float c, int n) -> int {
+            if (tx.addr == RT3_ADDRESS_WRAP) {
+                float f = c - floorf(c);
+                int i = (int)(f * (float)n);
+                return i > n - 1 ? n - 1 : i;
+            }
+            float f = fminf(fmaxf(c, 0.0f), 1.0f);
+            int i = (int)(f * (float)n);
+            return i > n - 1 ? n - 1 : i;
+        };
+        int x = addr(u, tx.w), y = addr(v, tx.h);
+        const uint8_t* p = &tx.px[4 * ((size_t)y * tx.w + x)];
+        return {(float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f};
+    }
+
+    // "LocalGeometry" of the new shade stage: object-space N/uv per closehit_radiance.cu:66-74,
+    // N moved to world space by the inverse-transpose (cuda/LocalGeometry.h:110,119) — exact
+    // identity for the reference's identity instances.
+    void local_geometry(const Hit& h, f3 o, f3 d, float time, f3& N, f2& uv) const {
+        const Instance& in = inst[h.inst];
+        const Blas& b = *blas[in.blas];
+        f3 n_obj;
+        if (b.type == PRIM_TRI) {
+            const int i0 = b.idx[3 * h.prim], i1 = b.idx[3 * h.prim + 1], i2 = b.idx[3 * h.prim + 2];
+            const float w0 = 1.0f - h.u - h.v;
+            n_obj = w0 * b.normals[i0] + h.u * b.normals[i1] + h.v * b.normals[i2];
+            uv.x = w0 * b.uvs[i0].x + h.u * b.uvs[i1].x + h.v * b.uvs[i2].x;
+            uv.y = w0 * b.uvs[i0].y + h.u * b.uvs[i1].y + h.v * b.uvs[i2].y;
+        } else {
+            f3 oo, od;
+            to_object(in, time, o, d, oo, od);
+            f3 ps = oo + h.t * od;
+            if (b.type == PRIM_SPHERE) {
+                f3 c = {b.cr[4 * h.prim], b.cr[4 * h.prim + 1], b.cr[4 * h.prim + 2]};
+                n_obj = (ps - c) / b.cr[4 * h.prim + 3];
+                uv = {0, 0};
+            } else {  // cuda/curve.h:382-425 surfaceNormal<LinearInterpolator>
+                int a = b.seg[h.prim];
+                f3 p0 = {b.cr[4 * a], b.cr[4 * a + 1], b.cr[4 * a + 2]};
+                f3 p1 = {b.cr[4 * a + 4], b.cr[4 * a + 5], b.cr[4 * a + 6]};
+                float r0 = b.cr[4 * a + 3], r1 = b.cr[4 * a + 7];
+                if (h.u == 0.0f) n_obj = ps - p0;
+                else if (h.u >= 1.0f) n_obj = ps - p1;
+                else {
+                    f3 dd3 = p1 - p0;
+                    float dr = r1 - r0;
+                    f3 p = p0 + h.u * dd3;
+                    float r = r0 + h.u * dr;
+                    float dd = dot(dd3, dd3);
+                    f3 o1 = ps - p;
+                    o1 = o1 - (dot(o1, dd3) / dd) * dd3;
+                    o1 = o1 * (r / length(o1));
+                    n_obj = dd * o1 - (dr * r) * dd3;
+                }
+                uv = {h.u, 0};
+            }
+        }
+        // object -> world normal: (M^-1)^T n, M = static o motion(t)
+        f3 n = n_obj;
+        if (in.nkeys > 0) {
+            Affine m = lerp_keys(in.keys.data(), in.nkeys, in.t0, in.t1, time);
+            n = xform_normal_by_inverse(invert_affine(m), n);
+        }
+        n = xform_normal_by_inverse(in.stat_inv, n);
+        N = normalize(n);
+    }
+
+    // one pixel, one launch: returns result/spl (raygen.cu:28-76)
+    f3 render_pixel(const rt3_render_settings& rs, uint32_t x, uint32_t y, int accel, uint64_t cnt[3]) const {
+        const uint32_t w = rs.width, h = rs.height;
+        const f3 eye = {rs.eye[0], rs.eye[1], rs.eye[2]}, U = {rs.U[0], rs.U[1], rs.U[2]}, V = {rs.V[0], rs.V[1], rs.V[2]},
+                 W = {rs.W[0], rs.W[1], rs.W[2]};
+        const f3 miss = {rs.miss_color[0], rs.miss_color[1], rs.miss_color[2]};
+        uint32_t seed = tea4(y * w + x, rs.subframe_index);
+        f3 result = {0, 0, 0};
+        const int max_depth = rs.max_depth > 0 ? rs.max_depth : (1 << 30);
+        const uint32_t nl = (uint32_t)lights.size();
+        int i = (int)rs.samples_per_launch;
+        do {
+            const float jx = rnd(seed);
+            const float jy = rnd(seed);
+            const float dx = 2.0f * (((float)x + jx) / (float)w) - 1.0f;
+            const float dy = 2.0f * (((float)y + jy) / (float)h) - 1.0f;
+            f3 dir = normalize(dx * U + dy * V + W);
+            f3 org = eye;
+            f3 att = {1, 1, 1};
+            uint32_t pseed = seed;
+            int depth = 0;
+            f3 last_att = att;
+            for (;;) {
+                // traceRadiance (shader_common.h:50-106)
+                const float time = rnd(pseed);
+                cnt[depth == 0 ? 0 : 1]++;
+                Hit hit = trace(org, dir, 0.01f, 1e16f, time, false, accel);
+                f3 emitted, radiance, norg = org, ndir = dir;
+                bool done;
+                if (hit.prim < 0) {  // miss.cu:29-32
+                    radiance = miss;
+                    emitted = {0, 0, 0};
+                    done = true;
+                } else {  // closehit_radiance.cu:60-160
+                    const Instance& in = inst[hit.inst];
+                    f3 N;
+                    f2 uv;
+                    local_geometry(hit, org, dir, time, N, uv);
+                    const f3 Ns = faceforward(N, -dir, N);
+                    const f3 P = org + hit.t * dir;
+                    emitted = depth == 0 ? in.emission : mk3(0, 0, 0);
+                    uint32_t s = pseed;
+                    (void)rnd(s);
+                    (void)rnd(s);  // z1, z2 discarded (Q6)
+                    const float u1 = rnd(s);
+                    const float u2 = rnd(s);
+                    f3 w_in = sample_cosine_hemisphere(u1, u2);
+                    const float pdf_prev = (float)((double)w_in.z / 3.14159265358979323846);
+                    Onb onb(Ns);
+                    ndir = onb.inverse_transform(w_in);
+                    norg = P;
+                    const float bsdf = (float)(1.0 / 3.14159265358979323846);
+                    const f3 albedo = in.tex >= 0 ? fetch_texture(in.tex, uv.x, uv.y) : in.diffuse;
+                    att = att * albedo;
+                    att = att * (bsdf / pdf_prev);
+                    // NEE
+                    const Light& lt = lights[(int)(rnd(s) * (float)nl)];
+                    f3 lpos, lem;
+                    float pdf_light;
+                    light_sample(lt, P, s, lpos, lem, pdf_light);
+                    pdf_light = pdf_light / (float)nl;
+                    pseed = s;
+                    const float Ldist = length(lpos - P);
+                    const f3 L = normalize(lpos - P);
+                    const float nDl = dot(Ns, L);
+                    f3 weight = {0, 0, 0};
+                    if (nDl > 0.0f) {
+                        const float tshadow = rnd(s);  // local copy only (Q7)
+                        cnt[2]++;
+                        Hit sh = trace(P, L, 0.001f, Ldist - 0.01f, tshadow, true, accel);
+                        if (sh.prim < 0) {
+                            const float pdf_scat = (float)((double)fabsf(dot(L, Ns)) / 3.14159265358979323846);
+                            weight = albedo * (power_heuristic(pdf_light, pdf_scat) * bsdf);
+                        }
+                    }
+                    radiance = lem * weight;
+                    done = false;
+                }
+                result = result + emitted;
+                result = result + radiance * last_att;
+                last_att = att;
+                const float p = att.x * 0.30f + att.y * 0.59f + att.z * 0.11f;
+                if (done || rnd(pseed) > p) break;
+                att = att / p;
+                org = norg;
+                dir = ndir;
+                ++depth;
+                if (depth >= max_depth) break;  // extension
+            }
+        } while (--i);
+        return result / (float)rs.samples_per_launch;
+    }
+};
+
+template <class F>
+static void parallel_for(int n, int nthreads, int grain, F&& f) {
+    if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            int b = next.fetch_add(grain);
+            if (b >= n) break;
+            int e = std::min(n, b + grain);
+            for (int i = b; i < e; i++) f(i);
+        }
+    };
+    if (nthreads == 1) { worker(); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back(worker);
+    for (auto& t : th) t.join();
+}
+
+// ====================================================================== C API
+#define RT3O_TRY try {
+#define RT3O_CATCH(ret) } catch (const std::exception& e) { g_err = e.what(); return ret; }
+
+extern "C" {
+
+rt3o_scene* rt3o_scene_create(void) { return new rt3o_scene(); }
+void rt3o_scene_destroy(rt3o_scene* s) { delete s; }
+const char* rt3o_last_error(void) { return g_err.c_str(); }
+
+static int finish_blas(rt3o_scene* s, std::unique_ptr<Blas> b) {
+    std::vector<Box> boxes(b->nprims);
+    for (int p = 0; p < b->nprims; p++) { boxes[p] = b->prim_box(p); b->bounds.grow(boxes[p]); }
+    b->bvh.build(boxes);
+    s->blas.push_back(std::move(b));
+    return (int)s->blas.size() - 1;
+}
+
+int rt3o_mesh_create(rt3o_scene* s, const float* verts, int num_keys, int nv, const int32_t* idx, int nt,
+                     const float* normals, const float* uvs) {
+    RT3O_TRY
+    if (!s || !verts || !idx || !normals || !uvs || nv <= 0 || nt <= 0 || num_keys < 1) { g_err = "mesh_create: bad argument"; return -1; }
+    for (int i = 0; i < 3 * nt; i++)
+        if (idx[i] < 0 || idx[i] >= nv) { g_err = "mesh_create: index out of range"; return -1; }
+    auto b = std::make_unique<Blas>();
+    b->type = PRIM_TRI;
+    b->nprims = nt;
+    b->verts.resize(nv); b->normals.resize(nv); b->uvs.resize(nv);
+    std::memcpy(b->verts.data(), verts, sizeof(f3) * nv);  // key 0
+    std::memcpy(b->normals.data(), normals, sizeof(f3) * nv);
+    std::memcpy(b->uvs.data(), uvs, sizeof(f2) * nv);
+    b->idx.assign(idx, idx + 3 * nt);
+    return finish_blas(s, std::move(b));
+    RT3O_CATCH(-1)
+}
+int rt3o_spheres_create(rt3o_scene* s, const float* cr, int n) {
+    RT3O_TRY
+    if (!s || !cr || n <= 0) { g_err = "spheres_create: bad argument"; return -1; }
+    auto b = std::make_unique<Blas>();
+    b->type = PRIM_SPHERE;
+    b->nprims = n;
+    b->cr.assign(cr, cr + 4 * n);
+    return finish_blas(s, std::move(b));
+    RT3O_CATCH(-1)
+}
+int rt3o_curves_create(rt3o_scene* s, int degree, const float* cp, int ncp, const int32_t* seg, int nseg) {
+    RT3O_TRY
+    if (!s || !cp || !seg || ncp < 2 || nseg <= 0) { g_err = "curves_create: bad argument"; return -1; }
+    if (degree != 1) { g_err = "curves_create: only degree 1 (linear) is supported"; return -5; }
+    for (int i = 0; i < nseg; i++)
+        if (seg[i] < 0 || seg[i] + 1 >= ncp) { g_err = "curves_create: segment out of range"; return -1; }
+    auto b = std::make_unique<Blas>();
+    b->type = PRIM_CURVE;
+    b->nprims = nseg;
+    b->cr.assign(cp, cp + 4 * ncp);
+    b->seg.assign(seg, seg + nseg);
+    return finish_blas(s, std::move(b));
+    RT3O_CATCH(-1)
+}
+int rt3o_texture_create(rt3o_scene* s, const uint8_t* rgba8, int w, int h, int address_mode, int filter_mode) {
+    RT3O_TRY
+    if (!s || !rgba8 || w <= 0 || h <= 0) { g_err = "texture_create: bad argument"; return -1; }
+    if (filter_mode != 0) { g_err = "texture_create: only filter_mode 0 (point, Q9) is supported"; return -5; }
+    if (address_mode != RT3_ADDRESS_WRAP && address_mode != RT3_ADDRESS_CLAMP) { g_err = "texture_create: address mode unsupported"; return -5; }
+    Texture t;
+    t.w = w; t.h = h; t.addr = address_mode; t.filt = filter_mode;
+    t.px.assign(rgba8, rgba8 + (size_t)4 * w * h);
+    s->tex.push_back(std::move(t));
+    return (int)s->tex.size() - 1;
+    RT3O_CATCH(-1)
+}
+static int add_instance(rt3o_scene* s, int blas, const float* stat, const float* keys, int nkeys, float t0, float t1) {
+    if (!s || blas < 0 || blas >= (int)s->blas.size() || !stat) { g_err = "append_instance: bad argument"; return -1; }
+    Instance in;
+    in.blas = blas;
+    std::memcpy(in.stat.m, stat, sizeof(float) * 12);
+    in.stat_inv = invert_affine(in.stat);
+    if (keys) {
+        if (nkeys < 2 || !(t1 > t0)) { g_err = "append_animated_instance: need >=2 keys and t_end > t_begin"; return -1; }
+        in.nkeys = nkeys;
+        in.keys.assign(keys, keys + 12 * nkeys);
+        in.t0 = t0; in.t1 = t1;
+    }
+    s->inst.push_back(std::move(in));
+    s->built = false;
+    return (int)s->inst.size() - 1;
+}
+int rt3o_accel_append_instance(rt3o_scene* s, int blas, const float xform[12]) {
+    RT3O_TRY return add_instance(s, blas, xform, nullptr, 0, 0, 1); RT3O_CATCH(-1)
+}
+int rt3o_accel_append_animated_instance(rt3o_scene* s, int blas, const float* keys, int nkeys, float t_begin, float t_end,
+                                        const float static_xform[12]) {
+    RT3O_TRY
+    if (!keys) { g_err = "append_animated_instance: keys null"; return -1; }
+    return add_instance(s, blas, static_xform, keys, nkeys, t_begin, t_end);
+    RT3O_CATCH(-1)
+}
+int rt3o_accel_build(rt3o_scene* s) {
+    RT3O_TRY
+    if (!s || s->inst.empty()) { g_err = "accel_build: no instances"; return -4; }
+    std::vector<Box> boxes(s->inst.size());
+    for (size_t i = 0; i < s->inst.size(); i++) boxes[i] = s->instance_world_box(s->inst[i]);
+    s->tlas.build(boxes);
+    s->built = true;
+    return 0;
+    RT3O_CATCH(-1)
+}
+int rt3o_scene_set_hitgroup(rt3o_scene* s, int id, const float e[3], const float d[3], int tex) {
+    if (!s || id < 0 || id >= (int)s->inst.size() || tex >= (int)s->tex.size()) { g_err = "set_hitgroup: bad argument"; return -1; }
+    s->inst[id].emission = {e[0], e[1], e[2]};
+    s->inst[id].diffuse = {d[0], d[1], d[2]};
+    s->inst[id].tex = tex;
+    return 0;
+}
+int rt3o_scene_set_lights(rt3o_scene* s, const void* lights68, int n) {
+    if (!s || !lights68 || n <= 0) { g_err = "set_lights: need at least one light (Q17)"; return -1; }
+    s->lights.resize(n);
+    std::memcpy(s->lights.data(), lights68, sizeof(Light) * n);
+    return 0;
+}
+
+int rt3o_trace(rt3o_scene* s, const rt3_ray* rays, int n, int any_hit, rt3_hit* hits, int accel, int nthreads) {
+    RT3O_TRY
+    if (!s || !s->built) { g_err = "trace: accel not built"; return -4; }
+    if (n < 0 || (n > 0 && (!rays || !hits))) { g_err = "trace: bad argument"; return -1; }
+    parallel_for(n, nthreads, accel == 0 ? 1 : 256, [&](int i) {
+        const rt3_ray& r = rays[i];
+        Hit h = s->trace({r.o[0], r.o[1], r.o[2]}, {r.d[0], r.d[1], r.d[2]}, r.tmin, r.tmax, r.time, any_hit != 0, accel);
+        rt3_hit& o = hits[i];
+        std::memset(&o, 0, sizeof(o));
+        o.t = h.t; o.u = h.u; o.v = h.v; o.prim = h.prim; o.inst = h.inst;
+    });
+    return 0;
+    RT3O_CATCH(-1)
+}
+
+int rt3o_launch_subframe(rt3o_scene* s, const rt3_render_settings* rs, int nthreads) {
+    RT3O_TRY
+    if (!s || !rs || !s->built) { g_err = "launch_subframe: accel not built"; return -4; }
+    if (s->lights.empty()) { g_err = "launch_subframe: no lights (Q17)"; return -4; }
+    if (rs->width == 0 || rs->height == 0 || rs->samples_per_launch == 0) { g_err = "launch_subframe: bad settings"; return -1; }
+    if (s->w != rs->width || s->h != rs->height) {
+        s->w = rs->width; s->h = rs->height;
+        s->accum.assign((size_t)4 * s->w * s->h, 0.0f);
+        s->frame.assign((size_t)4 * s->w * s->h, 0);
+    }
+    const int W = (int)rs->width, H = (int)rs->height;
+    const int tx = (W + 15) / 16, ty = (H + 15) / 16;
+    std::atomic<uint64_t> c0{0}, c1{0}, c2{0};
+    parallel_for(tx * ty, nthreads, 1, [&](int tile) {
+        uint64_t cnt[3] = {0, 0, 0};
+        int bx = (tile % tx) * 16, by = (tile / tx) * 16;
+        for (int y = by; y < std::min(by + 16, H); y++)
+            for (int x = bx; x < std::min(bx + 16, W); x++) {
+                f3 c = s->render_pixel(*rs, (uint32_t)x, (uint32_t)y, 1, cnt);
+                size_t pi = (size_t)y * W + x;
+                float* a = &s->accum[4 * pi];
+                if (rs->accum_mode == 0) {  // raygen.cu:75-86
+                    if (rs->subframe_index > 0) {
+                        const float k = 1.0f / (float)(rs->subframe_index + 1);
+                        f3 prev = {a[0], a[1], a[2]};
+                        c = prev + k * (c - prev);  // lerp: a + t*(b-a)
+                    }
+                    a[0] = c.x; a[1] = c.y; a[2] = c.z; a[3] = 1.0f;
+                    make_color(c, &s->frame[4 * pi]);
+                } else {
+                    a[0] += c.x; a[1] += c.y; a[2] += c.z; a[3] += 1.0f;
+                }
+            }
+        c0 += cnt[0]; c1 += cnt[1]; c2 += cnt[2];
+    });
+    s->n_primary += c0; s->n_bounce += c1; s->n_shadow += c2;
+    s->n_samples += (uint64_t)W * H * rs->samples_per_launch;
+    return 0;
+    RT3O_CATCH(-1)
+}
+int rt3o_download_accum(rt3o_scene* s, float* rgba) {
+    if (!s || !rgba || s->accum.empty()) { g_err = "download_accum: nothing rendered"; return -4; }
+    std::memcpy(rgba, s->accum.data(), s->accum.size() * sizeof(float));
+    return 0;
+}
+int rt3o_download_frame(rt3o_scene* s, uint8_t* rgba8) {
+    if (!s || !rgba8 || s->frame.empty()) { g_err = "download_frame: nothing rendered"; return -4; }
+    std::memcpy(rgba8, s->frame.data(), s->frame.size());
+    return 0;
+}
+int rt3o_get_stats(rt3o_scene* s, rt3_stats* st) {
+    if (!s || !st) return -1;
+    std::memset(st, 0, sizeof(*st));
+    st->rays_primary = s->n_primary; st->rays_bounce = s->n_bounce; st->rays_shadow = s->n_shadow; st->samples = s->n_samples;
+    return 0;
+}
+int rt3o_reset_stats(rt3o_scene* s) {
+    if (!s) return -1;
+    s->n_primary = 0; s->n_bounce = 0; s->n_shadow = 0; s->n_samples = 0;
+    return 0;
+}
+
+// ---------------------------------------------------------------- KAT hooks
+uint32_t rt3o_kat_tea4(uint32_t a, uint32_t b) { return tea4(a, b); }
+float rt3o_kat_rnd(uint32_t* seed) { return rnd(*seed); }
+void rt3o_kat_cosine_sample(float u1, float u2, float o[4]) {
+    f3 p = sample_cosine_hemisphere(u1, u2);
+    o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = (float)((double)p.z / 3.14159265358979323846);
+}
+void rt3o_kat_onb(const float n[3], const float w[3], float o[9]) {
+    Onb b({n[0], n[1], n[2]});
+    f3 p = b.inverse_transform({w[0], w[1], w[2]});
+    o[0] = b.t.x; o[1] = b.t.y; o[2] = b.t.z; o[3] = b.b.x; o[4] = b.b.y; o[5] = b.b.z; o[6] = p.x; o[7] = p.y; o[8] = p.z;
+}
+void rt3o_kat_light_make(const float e[3], const float v0[3], const float v1[3], const float v2[3], void* out) {
+    Light l = light_make({e[0], e[1], e[2]}, {v0[0], v0[1], v0[2]}, {v1[0], v1[1], v1[2]}, {v2[0], v2[1], v2[2]});
+    std::memcpy(out, &l, sizeof(l));
+}
+void rt3o_kat_light_sample(const void* light68, const float P[3], uint32_t* seed, float o[7]) {
+    Light l;
+    std::memcpy(&l, light68, sizeof(l));
+    f3 pos, em;
+    float pdf;
+    light_sample(l, {P[0], P[1], P[2]}, *seed, pos, em, pdf);
+    o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; o[3] = em.x; o[4] = em.y; o[5] = em.z; o[6] = pdf;
+}
+void rt3o_kat_make_color(const float c[3], uint8_t out[4]) { make_color({c[0], c[1], c[2]}, out); }
+void rt3o_kat_camera_uvw(const float e[3], const float l[3], const float u[3], float fovy, float aspect, float o[9]) {
+    f3 U, V, W;
+    camera_uvw({e[0], e[1], e[2]}, {l[0], l[1], l[2]}, {u[0], u[1], u[2]}, fovy, aspect, U, V, W);
+    o[0] = U.x; o[1] = U.y; o[2] = U.z; o[3] = V.x; o[4] = V.y; o[5] = V.z; o[6] = W.x; o[7] = W.y; o[8] = W.z;
+}
+void rt3o_kat_sincos_2pi(float u, float o[2]) { sincos_2pi(u, o[0], o[1]); }
+void rt3o_kat_invert_affine(const float m[12], float out[12]) {
+    Affine a;
+    std::memcpy(a.m, m, sizeof(a.m));
+    Affine r = invert_affine(a);
+    std::memcpy(out, r.m, sizeof(r.m));
+}
+int rt3o_kat_hit_triangle(const float o[3], const float d[3], const float v[9], float tmin, float tmax, float out[3]) {
+    RayShear s = make_shear({d[0], d[1], d[2]});
+    return hit_triangle({o[0], o[1], o[2]}, s, {v[0], v[1], v[2]}, {v[3], v[4], v[5]}, {v[6], v[7], v[8]}, tmin, tmax, out[0], out[1], out[2]) ? 1 : 0;
+}
+int rt3o_kat_hit_sphere(const float o[3], const float d[3], const float cr[4], float tmin, float tmax, float* t) {
+    return hit_sphere({o[0], o[1], o[2]}, {d[0], d[1], d[2]}, {cr[0], cr[1], cr[2]}, cr[3], tmin, tmax, *t) ? 1 : 0;
+}
+int rt3o_kat_hit_curve(const float o[3], const float d[3], const float a[4], const float b[4], float tmin, float tmax, float out[2]) {
+    return hit_curve_linear({o[0], o[1], o[2]}, {d[0], d[1], d[2]}, {a[0], a[1], a[2]}, a[3], {b[0], b[1], b[2]}, b[3], tmin, tmax, out[0], out[1]) ? 1 : 0;
+}
+
+}  // extern "C"
