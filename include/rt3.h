@@ -127,6 +127,7 @@ int rt3_trace_device(rt3_context_t ctx, const void* d_rays, int n, int any_hit, 
 int rt3_download_accum(rt3_context_t ctx, float* rgba);   /* float4 accum_buffer [h][w][4]; row 0 = image bottom (Q19) */
 int rt3_download_frame(rt3_context_t ctx, uint8_t* rgba8);/* uchar4 frame_buffer, make_color cuda/helpers.h:57-66 */
 int rt3_accum_device_ptr(rt3_context_t ctx, void** d_ptr, uint64_t* n_floats); /* for an external collective (torch.distributed / NCCL) */
+int rt3_clear_accum(rt3_context_t ctx);                  /* restart accumulation (reference: subframe_index = 0 on camera change, src/wavefront.cpp:193-201) */
 /* after an external SUM reduce in accum_mode 1: accum = sum / total_subframes, refresh the u8 frame */
 int rt3_finalize_accum(rt3_context_t ctx, uint32_t total_subframes);
 /* single-process multi-GPU: NCCL sum of the accumulation buffers of n contexts (one per GPU), then

@@ -29,6 +29,7 @@ using namespace rt3o;
 namespace {
 
 thread_local std::string g_err;
+bool g_chain_sum = false;  // see render_pixel
 
 struct Box {
     f3 lo{3e38f, 3e38f, 3e38f}, hi{-3e38f, -3e38f, -3e38f};
@@ -420,6 +421,13 @@ struct rt3o_scene {
             uint32_t pseed = seed;
             int depth = 0;
             f3 last_att = att;
+            // Association of the radiance sum: the reference keeps ONE running `result` across the
+            // samples of a launch (raygen.cu:27,58-59).  The wavefront kernels sum each path on its
+            // own and then the samples of a pixel in order; the oracle follows that association by
+            // default (fp32 reassociation only, quantified in tests/test_oracle.py) and the
+            // reference's single chain when g_chain_sum is set.
+            f3 sres = {0, 0, 0};
+            f3& acc = g_chain_sum ? result : sres;
             for (;;) {
                 // traceRadiance (shader_common.h:50-106)
                 const float time = rnd(pseed);
@@ -476,8 +484,8 @@ struct rt3o_scene {
                     radiance = lem * weight;
                     done = false;
                 }
-                result = result + emitted;
-                result = result + radiance * last_att;
+                acc = acc + emitted;
+                acc = acc + radiance * last_att;
                 last_att = att;
                 const float p = att.x * 0.30f + att.y * 0.59f + att.z * 0.11f;
                 if (done || rnd(pseed) > p) break;
@@ -487,6 +495,7 @@ struct rt3o_scene {
                 ++depth;
                 if (depth >= max_depth) break;  // extension
             }
+            if (!g_chain_sum) result = result + sres;
         } while (--i);
         return result / (float)rs.samples_per_launch;
     }
@@ -708,6 +717,8 @@ int rt3o_reset_stats(rt3o_scene* s) {
     s->n_primary = 0; s->n_bounce = 0; s->n_shadow = 0; s->n_samples = 0;
     return 0;
 }
+
+void rt3o_set_chain_sum(int on) { g_chain_sum = on != 0; }
 
 // ---------------------------------------------------------------- KAT hooks
 uint32_t rt3o_kat_tea4(uint32_t a, uint32_t b) { return tea4(a, b); }

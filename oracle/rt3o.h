@@ -36,6 +36,9 @@ int rt3o_download_frame(rt3o_scene*, uint8_t* rgba8);
 int rt3o_get_stats(rt3o_scene*, rt3_stats*);
 int rt3o_reset_stats(rt3o_scene*);
 const char* rt3o_last_error(void);
+/* 1 = sum radiance in the reference's single running chain across the samples of a launch (raygen.cu:27,58-59);
+ * 0 (default) = per-sample sums added in sample order, the association the wavefront kernels use */
+void rt3o_set_chain_sum(int on);
 
 /* known-answer hooks (each follows the reference line cited in rt3o_math.hpp) */
 uint32_t rt3o_kat_tea4(uint32_t v0, uint32_t v1);

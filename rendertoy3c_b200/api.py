@@ -29,7 +29,8 @@ RT3_SYMBOLS = [
     "rt3_set_option", "rt3_mesh_create", "rt3_spheres_create", "rt3_curves_create", "rt3_texture_create",
     "rt3_accel_append_instance", "rt3_accel_append_animated_instance", "rt3_accel_build", "rt3_scene_set_hitgroup",
     "rt3_scene_set_lights", "rt3_light_make", "rt3_camera_uvw", "rt3_launch_subframe", "rt3_trace", "rt3_trace_device",
-    "rt3_download_accum", "rt3_download_frame", "rt3_accum_device_ptr", "rt3_finalize_accum", "rt3_allreduce_accum",
+    "rt3_download_accum", "rt3_download_frame", "rt3_accum_device_ptr", "rt3_clear_accum", "rt3_finalize_accum",
+    "rt3_allreduce_accum",
 ]
 
 
@@ -39,31 +40,30 @@ class Rt3Error(RuntimeError):
         self.code = code
 
 
-_lib = None
+_libs = {}
 
 
 def load_library(path=None):
     """dlopen librt3.so (built in-tree by __graft_entry__.build()).  Raises if it is missing."""
-    global _lib
-    if _lib is None:
-        p = path or LIB_PATH
+    p = path or LIB_PATH
+    if p not in _libs:
         if not os.path.exists(p):
             raise Rt3Error(-3, "librt3.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
                                "there is no CPU fallback" % p)
         L = C.CDLL(p)
         L.rt3_last_error.restype = C.c_char_p
         L.rt3_context_destroy.restype = None
-        _lib = L
-    return _lib
+        _libs[p] = L
+    return _libs[p]
 
 
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-def camera_uvw(eye, lookat, up, fovy, aspect):
+def camera_uvw(eye, lookat, up, fovy, aspect, L=None):
     """sutil::Camera::UVWFrame (sutil/Camera.cpp:34-45) through the library's host helper."""
-    L = load_library()
+    L = L or load_library()
     e, l, u = _f32(eye), _f32(lookat), _f32(up)
     U, V, W = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32)
     rc = L.rt3_camera_uvw(fptr(e), fptr(l), fptr(u), C.c_float(fovy), C.c_float(aspect), fptr(U), fptr(V), fptr(W))
@@ -93,8 +93,8 @@ def make_settings(desc, uvw, subframe_index=0, samples_per_launch=8, accum_mode=
 class Context:
     """One GPU's device scene + renderer.  Move-only in spirit, like the reference's RAII owners."""
 
-    def __init__(self, device=0):
-        self.L = load_library()
+    def __init__(self, device=0, lib_path=None):
+        self.L = load_library(lib_path)
         self.ctx = C.c_void_p()
         self._chk(self.L.rt3_context_create(C.c_int(device), C.byref(self.ctx)))
         self.width = self.height = 0
@@ -176,7 +176,10 @@ class Context:
         self._chk(self.L.rt3_scene_set_lights(self.ctx, C.c_char_p(blob), C.c_int(n)))
 
     def camera_uvw(self, eye, lookat, up, fovy, aspect):
-        return camera_uvw(eye, lookat, up, fovy, aspect)
+        return camera_uvw(eye, lookat, up, fovy, aspect, L=self.L)
+
+    def clear_accum(self):
+        self._chk(self.L.rt3_clear_accum(self.ctx))
 
     # ---- hot path
     def launch_subframe(self, settings: RenderSettings):

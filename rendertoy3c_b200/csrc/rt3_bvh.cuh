@@ -1,0 +1,414 @@
+// rt3_bvh.cuh — GPU builder for the compressed 8-wide BVH used by both BLAS and TLAS.
+//
+// Replaces optixAccelBuild / optixAccelCompact (reference call sites src/cuda/cuda_mesh.h:92-146,
+// src/cuda/cuda_accel.h:118-146; no reference source exists for the builder itself).
+//
+// Pipeline (all on the GPU, one stream):
+//   1. centroid bounds           (atomic min/max on order-preserving uint keys)
+//   2. 63-bit Morton codes       (21 bits / axis)
+//   3. radix sort (key,prim)     (CUB DeviceRadixSort — library sort, not on the per-ray path)
+//   4. Karras 2012 radix tree    (one thread per internal node)
+//   5. bottom-up refit           (one thread per leaf, atomic arrival counters)
+//   6. top-down collapse BVH2 -> BVH8 by largest-surface-area opening (level-synchronous work
+//      queue), octant-ordered child slots, leaf children of <= 3 primitives, primitives
+//      re-ordered into node-contiguous blocks
+//   7. 80-byte compressed nodes: per-node origin + per-axis power-of-two scale, 8-bit child
+//      boxes rounded outward (verified in double), after Ylitie/Karras/Laine 2017.
+#pragma once
+#include "rt3_common.cuh"
+#include "rt3_rt.h"
+
+#ifndef RT3_EMULATE
+#include <cub/device/device_radix_sort.cuh>
+#else
+#include <algorithm>
+#include <vector>
+#endif
+
+namespace rt3 {
+
+// ------------------------------------------------------------------------------------ node layout (80 B = 5 x 16 B)
+struct alignas(16) Node8 {
+    float px, py, pz;        // quantisation origin = node box lo
+    uint8_t ex, ey, ez;      // biased exponents: scale_k = 2^(e_k - 127)
+    uint8_t imask;           // bit s set: slot s holds an internal child
+    uint32_t child_base;     // index of the first internal child (children stored contiguously in slot order)
+    uint32_t prim_base;      // index of the first primitive of this node's leaf children
+    uint8_t meta[8];         // 0 = empty | internal: 001sssss (sssss = 24+slot) | leaf: (unary count)<<5 | offset
+    uint8_t qlo[3][8];       // [axis][slot]
+    uint8_t qhi[3][8];
+};
+static_assert(sizeof(Node8) == 80, "compressed wide node must be 80 bytes");
+
+struct Bvh8 {            // one acceleration structure (BLAS or TLAS) in device memory
+    Node8* nodes = nullptr;
+    uint32_t* prim_order = nullptr;  // node-contiguous order -> original primitive index
+    uint32_t num_nodes = 0, num_prims = 0;
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};  // root bounds (host copy)
+};
+
+// ------------------------------------------------------------------------------------ helpers
+RT3_HD uint32_t float_to_ordered(float f) { const uint32_t u = rt3_f2u(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+RT3_HD float ordered_to_float(uint32_t u) { return rt3_u2f((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+RT3_HD uint64_t expand21(uint32_t v) {  // spread 21 bits to every third bit
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+struct BuildArrays {  // device pointers of one build
+    const float4* plo;  // primitive boxes
+    const float4* phi;
+    uint32_t n;
+    uint32_t* bounds;   // 6 ordered uints: centroid lo xyz, hi xyz
+    uint64_t* keys;
+    uint32_t* vals;     // after sort: sorted position -> primitive
+    // BVH2: ids [0,n-1) internal, (n-1)+j leaf j
+    float4* nlo;
+    float4* nhi;
+    int* left;
+    int* right;
+    int* parent;
+    int* first;   // internal: first sorted position of the range
+    int* last;
+    uint32_t* flags;
+    // BVH8 output
+    Node8* nodes;
+    uint32_t* prim_order;
+    uint32_t* counters;  // [0] nodes allocated, [1] prims allocated, [2] out-queue size
+    int2* q_in;
+    int2* q_out;
+};
+
+// ------------------------------------------------------------------------------------ kernels
+RT3_GLOBAL(k_bvh_bounds, BuildArrays b) {
+    const uint32_t i = RT3_THREAD_ID();
+    if (i >= rt3_n_) return;
+    const float4 lo = b.plo[i], hi = b.phi[i];
+    const float cx = (lo.x + hi.x) * 0.5f, cy = (lo.y + hi.y) * 0.5f, cz = (lo.z + hi.z) * 0.5f;
+    rt3_atomic_min(&b.bounds[0], float_to_ordered(cx));
+    rt3_atomic_min(&b.bounds[1], float_to_ordered(cy));
+    rt3_atomic_min(&b.bounds[2], float_to_ordered(cz));
+    rt3_atomic_max(&b.bounds[3], float_to_ordered(cx));
+    rt3_atomic_max(&b.bounds[4], float_to_ordered(cy));
+    rt3_atomic_max(&b.bounds[5], float_to_ordered(cz));
+}
+
+RT3_GLOBAL(k_bvh_morton, BuildArrays b) {
+    const uint32_t i = RT3_THREAD_ID();
+    if (i >= rt3_n_) return;
+    const float4 lo = b.plo[i], hi = b.phi[i];
+    const float c[3] = {(lo.x + hi.x) * 0.5f, (lo.y + hi.y) * 0.5f, (lo.z + hi.z) * 0.5f};
+    uint64_t key = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float l = ordered_to_float(b.bounds[k]), h = ordered_to_float(b.bounds[3 + k]);
+        const float ext = h - l;
+        float t = ext > 0.0f ? (c[k] - l) / ext : 0.0f;
+        t = fminf(fmaxf(t * 2097152.0f, 0.0f), 2097151.0f);
+        key |= expand21((uint32_t)t) << k;
+    }
+    b.keys[i] = key;
+    b.vals[i] = i;
+}
+
+// common-prefix length of sorted keys i and j (Karras 2012), ties broken by position
+RT3_HD int bvh_delta(const uint64_t* RT3_RESTRICT keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], c = keys[j];
+    if (a == c) return 64 + rt3_clz((uint32_t)i ^ (uint32_t)j);
+    return rt3_clzll(a ^ c);
+}
+
+RT3_GLOBAL(k_bvh_hierarchy, BuildArrays b) {
+    const int i = (int)RT3_THREAD_ID();
+    const int n = (int)b.n;
+    if (i >= n - 1) return;
+    const uint64_t* keys = b.keys;
+    const int d = (bvh_delta(keys, n, i, i + 1) - bvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = bvh_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (bvh_delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (bvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = bvh_delta(keys, n, i, j);
+    int s = 0;
+    int div = 2;
+    for (;;) {
+        const int t = (l + div - 1) / div;
+        if (bvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t <= 1) break;
+        div *= 2;
+    }
+    const int gamma = i + s * d + (d < 0 ? -1 : 0);
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    const int lc = (lo == gamma) ? (n - 1 + gamma) : gamma;
+    const int rc = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    b.left[i] = lc;
+    b.right[i] = rc;
+    b.first[i] = lo;
+    b.last[i] = hi;
+    b.parent[lc] = i;
+    b.parent[rc] = i;
+    if (i == 0) b.parent[0] = -1;
+}
+
+RT3_GLOBAL(k_bvh_refit, BuildArrays b) {
+    const uint32_t j = RT3_THREAD_ID();
+    if (j >= rt3_n_) return;
+    const int n = (int)b.n;
+    const uint32_t prim = b.vals[j];
+    int id = n - 1 + (int)j;
+    b.nlo[id] = b.plo[prim];
+    b.nhi[id] = b.phi[prim];
+    if (n == 1) return;
+    int cur = b.parent[id];
+    while (cur >= 0) {
+        rt3_threadfence();
+        if (rt3_atomic_add(&b.flags[cur], 1u) == 0u) return;  // first arrival: the sibling finishes this node
+        rt3_threadfence();
+        const int lc = b.left[cur], rc = b.right[cur];
+#ifdef RT3_EMULATE
+        const float4 a0 = b.nlo[lc], a1 = b.nhi[lc], c0 = b.nlo[rc], c1 = b.nhi[rc];
+#else
+        const float4 a0 = __ldcg(&b.nlo[lc]), a1 = __ldcg(&b.nhi[lc]), c0 = __ldcg(&b.nlo[rc]), c1 = __ldcg(&b.nhi[rc]);
+#endif
+        b.nlo[cur] = make_float4(fminf(a0.x, c0.x), fminf(a0.y, c0.y), fminf(a0.z, c0.z), 0.0f);
+        b.nhi[cur] = make_float4(fmaxf(a1.x, c1.x), fmaxf(a1.y, c1.y), fmaxf(a1.z, c1.z), 0.0f);
+        cur = b.parent[cur];
+    }
+}
+
+RT3_HD int bvh2_count(const BuildArrays& b, int id) { return id >= (int)b.n - 1 ? 1 : (b.last[id] - b.first[id] + 1); }
+RT3_HD int bvh2_first(const BuildArrays& b, int id) { return id >= (int)b.n - 1 ? id - ((int)b.n - 1) : b.first[id]; }
+RT3_HD float bvh2_area(const BuildArrays& b, int id) {
+    const float4 lo = b.nlo[id], hi = b.nhi[id];
+    const float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+    return ex * ey + ey * ez + ez * ex;
+}
+
+// smallest biased exponent E with p + 255 * 2^(E-127) >= hi (checked in double)
+RT3_HD uint32_t quant_exponent(float p, float hi) {
+    const float ext = hi - p;
+    uint32_t E = 1;
+    if (ext > 0.0f) {
+        const uint32_t bits = rt3_f2u(ext / 255.0f);
+        E = (bits >> 23) & 0xffu;
+        if (bits & 0x7fffffu) E += 1;
+        if (E < 1) E = 1;
+    }
+    while (E < 254 && (double)p + 255.0 * (double)rt3_u2f(E << 23) < (double)hi) E++;
+    return E;
+}
+
+RT3_GLOBAL(k_bvh_collapse, BuildArrays b) {
+    const uint32_t item = RT3_THREAD_ID();
+    if (item >= rt3_n_) return;
+    const int n = (int)b.n;
+    const int root = b.q_in[item].x;
+    const uint32_t widx = (uint32_t)b.q_in[item].y;
+
+    int ch[8];
+    int nch = 1;
+    ch[0] = root;
+    // phase 1: open the largest-area child holding more than 3 primitives; phase 2: use free slots
+    // to split the remaining multi-primitive leaves (tighter boxes at no extra nodes)
+    for (int phase = 0; phase < 2; phase++) {
+        const int min_count = phase == 0 ? 4 : 2;
+        while (nch < 8) {
+            int best = -1;
+            float best_a = -1.0f;
+            for (int c = 0; c < nch; c++) {
+                if (ch[c] >= n - 1) continue;  // BVH2 leaf
+                if (bvh2_count(b, ch[c]) < min_count) continue;
+                const float a = bvh2_area(b, ch[c]);
+                if (a > best_a) { best_a = a; best = c; }
+            }
+            if (best < 0) break;
+            const int o = ch[best];
+            ch[best] = b.left[o];
+            ch[nch++] = b.right[o];
+        }
+    }
+
+    const float4 rlo = b.nlo[root], rhi = b.nhi[root];
+    const float cen[3] = {(rlo.x + rhi.x) * 0.5f, (rlo.y + rhi.y) * 0.5f, (rlo.z + rhi.z) * 0.5f};
+    // octant-ordered slot assignment (greedy): slot bit k set <=> child lies on the + side of axis k
+    float cd[8][3];
+    for (int c = 0; c < nch; c++) {
+        const float4 lo = b.nlo[ch[c]], hi = b.nhi[ch[c]];
+        cd[c][0] = (lo.x + hi.x) * 0.5f - cen[0];
+        cd[c][1] = (lo.y + hi.y) * 0.5f - cen[1];
+        cd[c][2] = (lo.z + hi.z) * 0.5f - cen[2];
+    }
+    int slot_child[8];
+    for (int s = 0; s < 8; s++) slot_child[s] = -1;
+    uint32_t child_done = 0;
+    for (int round = 0; round < nch; round++) {
+        float best = -3.4e38f;
+        int bc = -1, bs = -1;
+        for (int c = 0; c < nch; c++) {
+            if (child_done & (1u << c)) continue;
+            for (int s = 0; s < 8; s++) {
+                if (slot_child[s] >= 0) continue;
+                const float cost = ((s & 1) ? cd[c][0] : -cd[c][0]) + ((s & 2) ? cd[c][1] : -cd[c][1]) + ((s & 4) ? cd[c][2] : -cd[c][2]);
+                if (cost > best) { best = cost; bc = c; bs = s; }
+            }
+        }
+        slot_child[bs] = bc;
+        child_done |= 1u << bc;
+    }
+
+    uint32_t imask = 0, nprims = 0;
+    for (int s = 0; s < 8; s++) {
+        if (slot_child[s] < 0) continue;
+        const int cnt = bvh2_count(b, ch[slot_child[s]]);
+        if (cnt > 3) imask |= 1u << s;
+        else nprims += (uint32_t)cnt;
+    }
+    const uint32_t nint = (uint32_t)rt3_popc(imask);
+    const uint32_t child_base = nint ? rt3_atomic_add(&b.counters[0], nint) : 0u;
+    const uint32_t prim_base = nprims ? rt3_atomic_add(&b.counters[1], nprims) : 0u;
+
+    Node8 nd;
+    nd.px = rlo.x; nd.py = rlo.y; nd.pz = rlo.z;
+    const uint32_t E[3] = {quant_exponent(rlo.x, rhi.x), quant_exponent(rlo.y, rhi.y), quant_exponent(rlo.z, rhi.z)};
+    nd.ex = (uint8_t)E[0]; nd.ey = (uint8_t)E[1]; nd.ez = (uint8_t)E[2];
+    nd.imask = (uint8_t)imask;
+    nd.child_base = child_base;
+    nd.prim_base = prim_base;
+    const float p[3] = {rlo.x, rlo.y, rlo.z};
+    uint32_t offset = 0;
+    for (int s = 0; s < 8; s++) {
+        const int c = slot_child[s];
+        if (c < 0) {
+            nd.meta[s] = 0;
+            for (int k = 0; k < 3; k++) { nd.qlo[k][s] = 255; nd.qhi[k][s] = 0; }  // inverted box: never hit
+            continue;
+        }
+        const int id = ch[c];
+        const int cnt = bvh2_count(b, id);
+        if (cnt > 3) {
+            nd.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+            const uint32_t cw = child_base + (uint32_t)rt3_popc(imask & ((1u << s) - 1u));
+            const uint32_t q = rt3_atomic_add(&b.counters[2], 1u);
+            b.q_out[q] = make_int2(id, (int)cw);
+        } else {
+            const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
+            nd.meta[s] = (uint8_t)((unary << 5) | offset);
+            const int f = bvh2_first(b, id);
+            for (int k = 0; k < cnt; k++) b.prim_order[prim_base + offset + (uint32_t)k] = b.vals[f + k];
+            offset += (uint32_t)cnt;
+        }
+        const float4 clo4 = b.nlo[id], chi4 = b.nhi[id];
+        const float clo[3] = {clo4.x, clo4.y, clo4.z}, chi[3] = {chi4.x, chi4.y, chi4.z};
+        for (int k = 0; k < 3; k++) {
+            const float scale = rt3_u2f(E[k] << 23);
+            int ql = (int)floorf((clo[k] - p[k]) / scale);
+            ql = ql < 0 ? 0 : (ql > 255 ? 255 : ql);
+            while (ql > 0 && (double)p[k] + (double)ql * (double)scale > (double)clo[k]) ql--;
+            int qh = (int)ceilf((chi[k] - p[k]) / scale);
+            qh = qh < 0 ? 0 : (qh > 255 ? 255 : qh);
+            while (qh < 255 && (double)p[k] + (double)qh * (double)scale < (double)chi[k]) qh++;
+            nd.qlo[k][s] = (uint8_t)ql;
+            nd.qhi[k][s] = (uint8_t)qh;
+        }
+    }
+    b.nodes[widx] = nd;
+}
+
+// ------------------------------------------------------------------------------------ host driver
+inline void sort_pairs(uint64_t* keys, uint32_t* vals, uint32_t n, Stream st) {
+#ifdef RT3_EMULATE
+    std::vector<std::pair<uint64_t, uint32_t>> v(n);
+    for (uint32_t i = 0; i < n; i++) v[i] = {keys[i], vals[i]};
+    std::stable_sort(v.begin(), v.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    for (uint32_t i = 0; i < n; i++) { keys[i] = v[i].first; vals[i] = v[i].second; }
+#else
+    DevBuf<uint64_t> k2(n);
+    DevBuf<uint32_t> v2(n);
+    size_t tmp_bytes = 0;
+    RT3_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, k2.p, vals, v2.p, (int)n, 0, 63, st));
+    DevBuf<uint8_t> tmp(tmp_bytes);
+    RT3_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys, k2.p, vals, v2.p, (int)n, 0, 63, st));
+    count_launch();
+    d2d(keys, k2.p, sizeof(uint64_t) * n, st);
+    d2d(vals, v2.p, sizeof(uint32_t) * n, st);
+    stream_sync(st);
+#endif
+}
+
+// Builds a BVH8 over n primitive boxes (device arrays).  Synchronises the stream (one-off build).
+inline void build_bvh8(const float4* d_plo, const float4* d_phi, uint32_t n, Stream st, DevBuf<Node8>& out_nodes,
+                       DevBuf<uint32_t>& out_order, Bvh8& out) {
+    RT3_REQUIRE(n > 0, -1, "build_bvh8: no primitives");
+    const uint32_t nn = 2 * n;
+    DevBuf<uint32_t> bounds(6), flags(n), counters(4);
+    DevBuf<uint64_t> keys(n);
+    DevBuf<uint32_t> vals(n), order(n);
+    DevBuf<float4> nlo(nn), nhi(nn);
+    DevBuf<int> left(n), right(n), parent(nn), first(n), last(n);
+    DevBuf<Node8> nodes(n);  // worst case; compacted below
+    DevBuf<int2> qa(n), qb(n);
+
+    BuildArrays b;
+    b.plo = d_plo; b.phi = d_phi; b.n = n;
+    b.bounds = bounds.p; b.keys = keys.p; b.vals = vals.p;
+    b.nlo = nlo.p; b.nhi = nhi.p; b.left = left.p; b.right = right.p; b.parent = parent.p;
+    b.first = first.p; b.last = last.p; b.flags = flags.p;
+    b.nodes = nodes.p; b.prim_order = order.p; b.counters = counters.p; b.q_in = qa.p; b.q_out = qb.p;
+
+    const uint32_t init_bounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    h2d(bounds.p, init_bounds, sizeof(init_bounds), st);
+    dev_memset(flags.p, 0, sizeof(uint32_t) * n, st);
+    dev_memset(parent.p, 0xff, sizeof(int) * nn, st);
+    RT3_LAUNCH_1D(k_bvh_bounds, n, st, b);
+    RT3_LAUNCH_1D(k_bvh_morton, n, st, b);
+    sort_pairs(keys.p, vals.p, n, st);
+    if (n > 1) RT3_LAUNCH_1D(k_bvh_hierarchy, n - 1, st, b);
+    RT3_LAUNCH_1D(k_bvh_refit, n, st, b);
+
+    // collapse, level by level
+    const uint32_t init_counters[4] = {1u, 0u, 0u, 0u};  // node 0 = root
+    h2d(counters.p, init_counters, sizeof(init_counters), st);
+    const int2 root_item = make_int2(n == 1 ? 0 : 0, 0);  // BVH2 id 0 is the root (leaf 0 when n == 1)
+    h2d(qa.p, &root_item, sizeof(root_item), st);
+    uint32_t qn = 1;
+    int levels = 0;
+    while (qn > 0) {
+        RT3_LAUNCH_1D(k_bvh_collapse, qn, st, b);
+        uint32_t c[4];
+        d2h(c, counters.p, sizeof(c), st);
+        stream_sync(st);
+        qn = c[2];
+        const uint32_t zero = 0;
+        h2d(&counters.p[2], &zero, sizeof(zero), st);
+        int2* t = b.q_in; b.q_in = b.q_out; b.q_out = t;
+        RT3_REQUIRE(++levels < 256, -2, "build_bvh8: collapse did not converge");
+    }
+    uint32_t c[4];
+    d2h(c, counters.p, sizeof(c), st);
+    float4 rb[2];
+    d2h(&rb[0], &nlo.p[0], sizeof(float4), st);
+    d2h(&rb[1], &nhi.p[0], sizeof(float4), st);
+    stream_sync(st);
+    RT3_REQUIRE(c[1] == n, -2, "build_bvh8: primitive count mismatch after collapse");
+    out_nodes.alloc(c[0]);
+    d2d(out_nodes.p, nodes.p, sizeof(Node8) * c[0], st);  // compaction (reference: optixAccelCompact, cuda_mesh.h:146)
+    out_order = std::move(order);
+    stream_sync(st);
+    out.nodes = out_nodes.p;
+    out.prim_order = out_order.p;
+    out.num_nodes = c[0];
+    out.num_prims = n;
+    out.lo[0] = rb[0].x; out.lo[1] = rb[0].y; out.lo[2] = rb[0].z;
+    out.hi[0] = rb[1].x; out.hi[1] = rb[1].y; out.hi[2] = rb[1].z;
+}
+
+}  // namespace rt3

@@ -1,0 +1,710 @@
+// rt3_lib.cu — the C ABI of include/rt3.h over the sm_100a kernels (single translation unit).
+//
+// Host-side orchestration only: device-scene assembly (geometry upload + BLAS build, instance
+// table + TLAS build, hit-group / light / texture tables) and the per-subframe stage schedule
+//   generate -> { extend -> shade -> connect } x depth -> resolve
+// issued on one CUDA stream with no host synchronisation inside the loop (queue sizes stay in
+// device memory; persistent kernels read them there).
+// Compiled with: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
+#include "../../include/rt3.h"
+#include "rt3_wavefront.cuh"
+
+#include <memory>
+#include <vector>
+#ifndef RT3_EMULATE
+#include <dlfcn.h>
+#endif
+
+namespace rt3 {
+thread_local std::string g_last_error;
+unsigned long long g_launch_count = 0;
+}  // namespace rt3
+
+using namespace rt3;
+
+namespace {
+
+struct Geometry {
+    uint32_t type = PRIM_TRI, nprims = 0;
+    DevBuf<float> verts, normals, uvs;
+    DevBuf<int32_t> idx, seg;
+    DevBuf<float4> cr;
+    DevBuf<Node8> nodes;
+    DevBuf<uint32_t> order;
+    DevBuf<float4> prims;
+    Bvh8 bvh;
+};
+
+struct InstanceHost {
+    uint32_t blas = 0;
+    float xform[12];
+    std::vector<float> keys;
+    uint32_t nkeys = 0;
+    float t0 = 0, t1 = 1;
+    HitGroupDev hg;
+};
+
+struct TextureObj { DevBuf<uchar4> px; int w = 0, h = 0, addr = 0, filt = 0; };
+
+constexpr uint32_t MAX_DEPTH_SLOTS = 1024;
+
+}  // namespace
+
+struct rt3_context {
+    int device = 0;
+    Stream stream = 0;
+    int num_sms = 148;
+    std::vector<std::unique_ptr<Geometry>> geoms;
+    std::vector<InstanceHost> inst;
+    std::vector<std::unique_ptr<TextureObj>> textures;
+    bool built = false;
+    // device scene tables
+    DevBuf<BlasDev> d_blas;
+    DevBuf<InstanceDev> d_inst;
+    DevBuf<HitGroupDev> d_hg;
+    DevBuf<float> d_keys, d_static;
+    DevBuf<TexDev> d_tex;
+    DevBuf<Light> d_lights;
+    uint32_t nlights = 0;
+    DevBuf<Node8> tlas_nodes;
+    DevBuf<uint32_t> tlas_order;
+    Bvh8 tlas;
+    DevBuf<uint32_t> d_flags;  // [0] error flags, [1] max stack
+    // film
+    uint32_t width = 0, height = 0;
+    DevBuf<float4> accum;
+    DevBuf<uchar4> frame;
+    // wavefront pools
+    size_t pool_paths = 0;
+    DevBuf<float4> ray[2][3], st[2][2], hit0, sh[4], result;
+    DevBuf<int32_t> hit_inst;
+    DevBuf<uint32_t> counters;           // 4 x MAX_DEPTH_SLOTS
+    DevBuf<unsigned long long> d_stats;  // primary, bounce, shadow
+    DevBuf<uint32_t> trace_fetch;
+    // options / stats
+    int opt_timing = 0;
+    int opt_ctas_per_sm = 0;
+    uint64_t samples = 0;
+    float ms[6] = {0, 0, 0, 0, 0, 0};
+    bool hitgroups_dirty = true;
+#ifndef RT3_EMULATE
+    void* nccl_comm = nullptr;
+#endif
+
+    TravScene trav_scene() {
+        TravScene s;
+        s.tlas_nodes = tlas_nodes.p;
+        s.tlas_order = tlas_order.p;
+        s.instances = d_inst.p;
+        s.hitgroups = d_hg.p;
+        s.blas = d_blas.p;
+        s.keys = d_keys.p;
+        s.error_flags = d_flags.p;
+        s.max_stack = d_flags.p + 1;
+        return s;
+    }
+    int trav_grid() const {
+#ifdef RT3_EMULATE
+        return 1;
+#else
+        const int per_sm = opt_ctas_per_sm > 0 ? opt_ctas_per_sm : RT3_TRAV_MIN_BLOCKS;
+        return num_sms * per_sm;
+#endif
+    }
+};
+
+namespace {
+
+template <int MODE>
+void launch_traverse(rt3_context* c, const TraverseArgs& a) {
+#ifdef RT3_EMULATE
+    k_traverse<MODE>(a);
+#else
+    k_traverse<MODE><<<c->trav_grid(), RT3_TRAV_THREADS, 0, c->stream>>>(a);
+    RT3_CUDA(cudaGetLastError());
+#endif
+    count_launch();
+}
+
+void upload_hitgroups(rt3_context* c) {
+    if (!c->hitgroups_dirty || c->inst.empty()) return;
+    std::vector<HitGroupDev> hg(c->inst.size());
+    for (size_t i = 0; i < c->inst.size(); i++) hg[i] = c->inst[i].hg;
+    c->d_hg.ensure(hg.size());
+    h2d(c->d_hg.p, hg.data(), sizeof(HitGroupDev) * hg.size(), c->stream);
+    stream_sync(c->stream);
+    c->hitgroups_dirty = false;
+}
+
+uint64_t finish_geometry(rt3_context* c, std::unique_ptr<Geometry> g, DevBuf<float4>& lo, DevBuf<float4>& hi) {
+    build_bvh8(lo.p, hi.p, g->nprims, c->stream, g->nodes, g->order, g->bvh);
+    g->prims.alloc(3 * (size_t)g->nprims);
+    if (g->type == PRIM_TRI) RT3_LAUNCH_1D(k_pack_tris, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, (const uint32_t*)g->order.p, g->prims.p);
+    else if (g->type == PRIM_SPHERE) RT3_LAUNCH_1D(k_pack_spheres, g->nprims, c->stream, (const float4*)g->cr.p, (const uint32_t*)g->order.p, g->prims.p);
+    else RT3_LAUNCH_1D(k_pack_curves, g->nprims, c->stream, (const float4*)g->cr.p, (const int32_t*)g->seg.p, (const uint32_t*)g->order.p, g->prims.p);
+    stream_sync(c->stream);
+    c->geoms.push_back(std::move(g));
+    c->built = false;
+    return (uint64_t)c->geoms.size();  // handle = index + 1
+}
+
+void ensure_pools(rt3_context* c, size_t paths) {
+    if (paths <= c->pool_paths) return;
+    for (int b = 0; b < 2; b++) {
+        for (int k = 0; k < 3; k++) c->ray[b][k].alloc(paths);
+        for (int k = 0; k < 2; k++) c->st[b][k].alloc(paths);
+    }
+    c->hit0.alloc(paths);
+    c->hit_inst.alloc(paths);
+    for (int k = 0; k < 4; k++) c->sh[k].alloc(paths);
+    c->result.alloc(paths);
+    c->pool_paths = paths;
+}
+
+void ensure_film(rt3_context* c, uint32_t w, uint32_t h) {
+    if (c->width == w && c->height == h && c->accum.p) return;
+    c->width = w;
+    c->height = h;
+    c->accum.alloc((size_t)w * h);  // handleResize reallocates the accumulation buffer (src/wavefront.cpp:178-191)
+    c->frame.alloc((size_t)w * h);
+    dev_memset(c->accum.p, 0, c->accum.bytes(), c->stream);
+    dev_memset(c->frame.p, 0, c->frame.bytes(), c->stream);
+}
+
+}  // namespace
+
+#define RT3_API_BEGIN try {
+#define RT3_API_END                                       \
+    }                                                     \
+    catch (const rt3::Error& e) {                         \
+        rt3::g_last_error = e.what();                     \
+        return e.code;                                    \
+    }                                                     \
+    catch (const std::exception& e) {                     \
+        rt3::g_last_error = e.what();                     \
+        return RT3_ERR_INVALID;                           \
+    }                                                     \
+    return RT3_OK;
+
+extern "C" {
+
+const char* rt3_last_error(void) { return rt3::g_last_error.c_str(); }
+
+int rt3_context_create(int device, rt3_context_t* out) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(out, RT3_ERR_INVALID, "context_create: null output");
+    *out = nullptr;
+    auto c = std::make_unique<rt3_context>();
+    c->device = device;
+#ifndef RT3_EMULATE
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+        throw Error(RT3_ERR_NO_DEVICE, std::string("context_create: no usable CUDA device (") + cudaGetErrorString(e) +
+                                           "); librt3 has no CPU fallback");
+    RT3_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RT3_CUDA(cudaGetDeviceProperties(&prop, device));
+    RT3_REQUIRE(prop.major >= 10, RT3_ERR_NO_DEVICE, "context_create: kernels are built for sm_100a only");
+    c->num_sms = prop.multiProcessorCount;
+    RT3_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+#endif
+    c->d_flags.alloc(2);
+    c->counters.alloc(4 * MAX_DEPTH_SLOTS);
+    c->d_stats.alloc(4);
+    c->trace_fetch.alloc(1);
+    dev_memset(c->d_flags.p, 0, c->d_flags.bytes(), c->stream);
+    dev_memset(c->d_stats.p, 0, c->d_stats.bytes(), c->stream);
+    stream_sync(c->stream);
+    *out = c.release();
+    RT3_API_END
+}
+
+void rt3_context_destroy(rt3_context_t c) {
+    if (!c) return;
+#ifndef RT3_EMULATE
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStream_t s = c->stream;
+    delete c;
+    cudaStreamDestroy(s);
+#else
+    delete c;
+#endif
+}
+
+int rt3_sync(rt3_context_t c) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c, RT3_ERR_INVALID, "sync: null context");
+    stream_sync(c->stream);
+    RT3_API_END
+}
+
+int rt3_set_option(rt3_context_t c, const char* key, int value) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && key, RT3_ERR_INVALID, "set_option: null argument");
+    const std::string k(key);
+    if (k == "timing") c->opt_timing = value;
+    else if (k == "persist_ctas_per_sm") c->opt_ctas_per_sm = value;
+    else if (k == "sort_rays" || k == "sort_materials") { RT3_REQUIRE(value == 0, RT3_ERR_UNSUPPORTED, "set_option: sorting stages are not built yet"); }
+    else throw Error(RT3_ERR_INVALID, "set_option: unknown key " + k);
+    RT3_API_END
+}
+
+// ------------------------------------------------------------------------------------ geometry
+int rt3_mesh_create(rt3_context_t c, const float* verts, int num_keys, int nv, const int32_t* idx, int nt, const float* normals,
+                    const float* uvs, rt3_handle_t* blas) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && verts && idx && normals && uvs && blas, RT3_ERR_INVALID, "mesh_create: null argument (normals and uvs are required, Q11)");
+    RT3_REQUIRE(nv > 0 && nt > 0 && num_keys >= 1, RT3_ERR_INVALID, "mesh_create: empty mesh");
+    for (size_t i = 0; i < 3 * (size_t)nt; i++) RT3_REQUIRE(idx[i] >= 0 && idx[i] < nv, RT3_ERR_INVALID, "mesh_create: index out of range");
+    auto g = std::make_unique<Geometry>();
+    g->type = PRIM_TRI;
+    g->nprims = (uint32_t)nt;
+    g->verts.alloc(3 * (size_t)nv);
+    g->normals.alloc(3 * (size_t)nv);
+    g->uvs.alloc(2 * (size_t)nv);
+    g->idx.alloc(3 * (size_t)nt);
+    h2d(g->verts.p, verts, g->verts.bytes(), c->stream);  // key 0 (vertex-key motion: SURVEY 8f/N2)
+    h2d(g->normals.p, normals, g->normals.bytes(), c->stream);
+    h2d(g->uvs.p, uvs, g->uvs.bytes(), c->stream);
+    h2d(g->idx.p, idx, g->idx.bytes(), c->stream);
+    DevBuf<float4> lo(nt), hi(nt);
+    RT3_LAUNCH_1D(k_tri_boxes, nt, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, lo.p, hi.p);
+    *blas = finish_geometry(c, std::move(g), lo, hi);
+    RT3_API_END
+}
+
+int rt3_spheres_create(rt3_context_t c, const float* cr, int n, rt3_handle_t* blas) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && cr && blas && n > 0, RT3_ERR_INVALID, "spheres_create: bad argument");
+    auto g = std::make_unique<Geometry>();
+    g->type = PRIM_SPHERE;
+    g->nprims = (uint32_t)n;
+    g->cr.alloc(n);
+    h2d(g->cr.p, cr, g->cr.bytes(), c->stream);
+    DevBuf<float4> lo(n), hi(n);
+    RT3_LAUNCH_1D(k_sphere_boxes, n, c->stream, (const float4*)g->cr.p, lo.p, hi.p);
+    *blas = finish_geometry(c, std::move(g), lo, hi);
+    RT3_API_END
+}
+
+int rt3_curves_create(rt3_context_t c, int degree, const float* cp, int ncp, const int32_t* seg, int nseg, rt3_handle_t* blas) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && cp && seg && blas && ncp >= 2 && nseg > 0, RT3_ERR_INVALID, "curves_create: bad argument");
+    RT3_REQUIRE(degree == 1, RT3_ERR_UNSUPPORTED, "curves_create: only degree 1 (round linear segments) is supported");
+    for (int i = 0; i < nseg; i++) RT3_REQUIRE(seg[i] >= 0 && seg[i] + 1 < ncp, RT3_ERR_INVALID, "curves_create: segment out of range");
+    auto g = std::make_unique<Geometry>();
+    g->type = PRIM_CURVE;
+    g->nprims = (uint32_t)nseg;
+    g->cr.alloc(ncp);
+    g->seg.alloc(nseg);
+    h2d(g->cr.p, cp, g->cr.bytes(), c->stream);
+    h2d(g->seg.p, seg, g->seg.bytes(), c->stream);
+    DevBuf<float4> lo(nseg), hi(nseg);
+    RT3_LAUNCH_1D(k_curve_boxes, nseg, c->stream, (const float4*)g->cr.p, (const int32_t*)g->seg.p, lo.p, hi.p);
+    *blas = finish_geometry(c, std::move(g), lo, hi);
+    RT3_API_END
+}
+
+int rt3_texture_create(rt3_context_t c, const uint8_t* rgba8, int w, int h, int address_mode, int filter_mode, int* tex_id) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && rgba8 && tex_id && w > 0 && h > 0, RT3_ERR_INVALID, "texture_create: bad argument");
+    RT3_REQUIRE(filter_mode == 0, RT3_ERR_UNSUPPORTED, "texture_create: only filter_mode 0 (= point sampling in the reference, Q9) is supported");
+    RT3_REQUIRE(address_mode == RT3_ADDRESS_WRAP || address_mode == RT3_ADDRESS_CLAMP, RT3_ERR_UNSUPPORTED, "texture_create: address mode unsupported");
+    auto t = std::make_unique<TextureObj>();
+    t->w = w; t->h = h; t->addr = address_mode; t->filt = filter_mode;
+    t->px.alloc((size_t)w * h);
+    h2d(t->px.p, rgba8, t->px.bytes(), c->stream);
+    stream_sync(c->stream);
+    c->textures.push_back(std::move(t));
+    *tex_id = (int)c->textures.size() - 1;
+    std::vector<TexDev> td(c->textures.size());
+    for (size_t i = 0; i < td.size(); i++) td[i] = TexDev{c->textures[i]->px.p, c->textures[i]->w, c->textures[i]->h, c->textures[i]->addr, c->textures[i]->filt};
+    c->d_tex.ensure(td.size());
+    h2d(c->d_tex.p, td.data(), sizeof(TexDev) * td.size(), c->stream);
+    stream_sync(c->stream);
+    RT3_API_END
+}
+
+// ------------------------------------------------------------------------------------ instances
+static int append_instance_impl(rt3_context_t c, rt3_handle_t blas, const float* xform, const float* keys, int nkeys, float t0, float t1, int* iid) {
+    RT3_REQUIRE(c && xform && iid, RT3_ERR_INVALID, "append_instance: null argument");
+    RT3_REQUIRE(blas >= 1 && blas <= c->geoms.size(), RT3_ERR_INVALID, "append_instance: invalid BLAS handle");
+    InstanceHost in;
+    in.blas = (uint32_t)(blas - 1);
+    memcpy(in.xform, xform, sizeof(in.xform));
+    if (keys) {
+        RT3_REQUIRE(nkeys >= 2 && t1 > t0, RT3_ERR_INVALID, "append_animated_instance: need >= 2 keys and t_end > t_begin");
+        in.nkeys = (uint32_t)nkeys;
+        in.keys.assign(keys, keys + 12 * (size_t)nkeys);
+        in.t0 = t0; in.t1 = t1;
+    }
+    in.hg = HitGroupDev{{0, 0, 0}, {0.8f, 0.8f, 0.8f}, -1, in.t1};
+    c->inst.push_back(std::move(in));
+    c->built = false;
+    c->hitgroups_dirty = true;
+    *iid = (int)c->inst.size() - 1;  // instanceId = sbtOffset = index (cuda_accel.h:78-79)
+    return RT3_OK;
+}
+
+int rt3_accel_append_instance(rt3_context_t c, rt3_handle_t blas, const float xform[12], int* instance_id) {
+    RT3_API_BEGIN
+    append_instance_impl(c, blas, xform, nullptr, 0, 0.0f, 1.0f, instance_id);
+    RT3_API_END
+}
+
+int rt3_accel_append_animated_instance(rt3_context_t c, rt3_handle_t blas, const float* keys, int nkeys, float t_begin, float t_end,
+                                       const float static_xform[12], int* instance_id) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(keys, RT3_ERR_INVALID, "append_animated_instance: null keys");
+    append_instance_impl(c, blas, static_xform, keys, nkeys, t_begin, t_end, instance_id);
+    RT3_API_END
+}
+
+int rt3_accel_build(rt3_context_t c) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c, RT3_ERR_INVALID, "accel_build: null context");
+    RT3_REQUIRE(!c->inst.empty(), RT3_ERR_STATE, "accel_build: no instances");
+    const uint32_t ni = (uint32_t)c->inst.size();
+    // BLAS table
+    std::vector<BlasDev> bt(c->geoms.size());
+    std::vector<BlasBounds> bb(c->geoms.size());
+    for (size_t i = 0; i < bt.size(); i++) {
+        const Geometry& g = *c->geoms[i];
+        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p};
+        for (int k = 0; k < 3; k++) { bb[i].lo[k] = g.bvh.lo[k]; bb[i].hi[k] = g.bvh.hi[k]; }
+    }
+    c->d_blas.alloc(bt.size());
+    h2d(c->d_blas.p, bt.data(), sizeof(BlasDev) * bt.size(), c->stream);
+    DevBuf<BlasBounds> d_bb(bb.size());
+    h2d(d_bb.p, bb.data(), sizeof(BlasBounds) * bb.size(), c->stream);
+    // instance table (+ motion keys)
+    std::vector<InstanceDev> it(ni);
+    std::vector<float> keys, stat(12 * (size_t)ni);
+    for (uint32_t i = 0; i < ni; i++) {
+        const InstanceHost& in = c->inst[i];
+        memset(&it[i], 0, sizeof(InstanceDev));
+        it[i].blas = in.blas;
+        it[i].nkeys = in.nkeys;
+        it[i].key_offset = (uint32_t)keys.size();
+        it[i].t0 = in.t0;
+        keys.insert(keys.end(), in.keys.begin(), in.keys.end());
+        memcpy(&stat[12 * (size_t)i], in.xform, sizeof(in.xform));
+    }
+    c->d_inst.alloc(ni);
+    c->d_static.alloc(stat.size());
+    c->d_keys.alloc(keys.size() ? keys.size() : 12);
+    h2d(c->d_inst.p, it.data(), sizeof(InstanceDev) * ni, c->stream);
+    h2d(c->d_static.p, stat.data(), sizeof(float) * stat.size(), c->stream);
+    h2d(c->d_keys.p, keys.data(), sizeof(float) * keys.size(), c->stream);
+    RT3_LAUNCH_1D(k_invert_static, ni, c->stream, (const float*)c->d_static.p, c->d_inst.p);
+    DevBuf<float4> lo(ni), hi(ni);
+    RT3_LAUNCH_1D(k_instance_boxes, ni, c->stream, (const InstanceDev*)c->d_inst.p, (const float*)c->d_static.p, (const BlasBounds*)d_bb.p,
+                  (const float*)c->d_keys.p, lo.p, hi.p);
+    build_bvh8(lo.p, hi.p, ni, c->stream, c->tlas_nodes, c->tlas_order, c->tlas);
+    c->hitgroups_dirty = true;
+    upload_hitgroups(c);
+    c->built = true;
+    RT3_API_END
+}
+
+// ------------------------------------------------------------------------------------ shading records
+int rt3_scene_set_hitgroup(rt3_context_t c, int id, const float e[3], const float d[3], int tex) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && e && d, RT3_ERR_INVALID, "set_hitgroup: null argument");
+    RT3_REQUIRE(id >= 0 && id < (int)c->inst.size(), RT3_ERR_INVALID, "set_hitgroup: instance id out of range");
+    RT3_REQUIRE(tex >= -1 && tex < (int)c->textures.size(), RT3_ERR_INVALID, "set_hitgroup: texture id out of range");
+    HitGroupDev& hg = c->inst[id].hg;
+    for (int k = 0; k < 3; k++) { hg.emission[k] = e[k]; hg.diffuse[k] = d[k]; }
+    hg.tex = tex;
+    c->hitgroups_dirty = true;
+    RT3_API_END
+}
+
+int rt3_scene_set_lights(rt3_context_t c, const void* lights68, int n) {
+    RT3_API_BEGIN
+    static_assert(sizeof(Light) == 68, "rendertoy3o::Light is 68 bytes");
+    RT3_REQUIRE(c && lights68 && n > 0, RT3_ERR_INVALID, "set_lights: at least one light is required (Q17)");
+    c->d_lights.alloc(n);
+    h2d(c->d_lights.p, lights68, sizeof(Light) * (size_t)n, c->stream);
+    stream_sync(c->stream);
+    c->nlights = (uint32_t)n;
+    RT3_API_END
+}
+
+// host helpers: pure fp32 arithmetic, no device work (nvcc passes -ffp-contract=off to the host compiler)
+int rt3_light_make(const float e[3], const float v0[3], const float v1[3], const float v2[3], void* out) {  // Light ctor, src/light.h:24-30
+    RT3_API_BEGIN
+    RT3_REQUIRE(e && v0 && v1 && v2 && out, RT3_ERR_INVALID, "light_make: null argument");
+    Light l;
+    l.type = 0;
+    const float a[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]}, b[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
+    float n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    const float len = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    l.area = 0.5f * len;
+    const float inv = 1.0f / sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    for (int k = 0; k < 3; k++) { l.emission[k] = e[k]; l.v0[k] = v0[k]; l.v1[k] = v1[k]; l.v2[k] = v2[k]; l.normal[k] = n[k] * inv; }
+    memcpy(out, &l, sizeof(l));
+    RT3_API_END
+}
+
+int rt3_camera_uvw(const float eye[3], const float lookat[3], const float up[3], float fovy, float aspect, float U[3], float V[3], float W[3]) {  // sutil/Camera.cpp:34-45
+    RT3_API_BEGIN
+    RT3_REQUIRE(eye && lookat && up && U && V && W, RT3_ERR_INVALID, "camera_uvw: null argument");
+    for (int k = 0; k < 3; k++) W[k] = lookat[k] - eye[k];
+    const float wlen = sqrtf(W[0] * W[0] + W[1] * W[1] + W[2] * W[2]);
+    float u[3] = {W[1] * up[2] - W[2] * up[1], W[2] * up[0] - W[0] * up[2], W[0] * up[1] - W[1] * up[0]};
+    float inv = 1.0f / sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    for (int k = 0; k < 3; k++) u[k] = u[k] * inv;
+    float v[3] = {u[1] * W[2] - u[2] * W[1], u[2] * W[0] - u[0] * W[2], u[0] * W[1] - u[1] * W[0]};
+    inv = 1.0f / sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    for (int k = 0; k < 3; k++) v[k] = v[k] * inv;
+    const float vlen = wlen * tanf(0.5f * fovy * 3.14159265358979323846f / 180.0f);
+    const float ulen = vlen * aspect;
+    for (int k = 0; k < 3; k++) { V[k] = v[k] * vlen; U[k] = u[k] * ulen; }
+    RT3_API_END
+}
+
+// ------------------------------------------------------------------------------------ the hot path
+int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && rs, RT3_ERR_INVALID, "launch_subframe: null argument");
+    RT3_REQUIRE(c->built, RT3_ERR_STATE, "launch_subframe: rt3_accel_build has not been called");
+    RT3_REQUIRE(c->nlights > 0, RT3_ERR_STATE, "launch_subframe: no lights set (Q17)");
+    RT3_REQUIRE(rs->width > 0 && rs->height > 0 && rs->samples_per_launch > 0, RT3_ERR_INVALID, "launch_subframe: bad film settings");
+    RT3_REQUIRE(rs->mode == 0, RT3_ERR_UNSUPPORTED, "launch_subframe: only mode 0 (REFERENCE_FAITHFUL) exists");
+    const uint64_t paths64 = (uint64_t)rs->width * rs->height * rs->samples_per_launch;
+    RT3_REQUIRE(paths64 < 0xfffffff0ull, RT3_ERR_INVALID, "launch_subframe: too many paths per launch");
+    const uint32_t P = (uint32_t)paths64;
+    upload_hitgroups(c);
+    ensure_film(c, rs->width, rs->height);
+    ensure_pools(c, P);
+
+    FrameParams f;
+    f.width = rs->width; f.height = rs->height; f.spl = rs->samples_per_launch; f.subframe = rs->subframe_index;
+    for (int k = 0; k < 3; k++) { f.eye[k] = rs->eye[k]; f.U[k] = rs->U[k]; f.V[k] = rs->V[k]; f.W[k] = rs->W[k]; f.miss[k] = rs->miss_color[k]; }
+    f.max_depth = rs->max_depth; f.accum_mode = rs->accum_mode;
+    f.lights = c->d_lights.p; f.nlights = c->nlights; f.tex = c->d_tex.p;
+    const TravScene sc = c->trav_scene();
+
+    uint32_t* cnt = c->counters.p;  // [0,M): rays per depth  [M,2M): shadow rays per depth  [2M,3M): extend fetch  [3M,4M): connect fetch
+    const uint32_t M = MAX_DEPTH_SLOTS;
+    dev_memset(cnt, 0, c->counters.bytes(), c->stream);
+
+    Event ev[8];
+    const bool timing = c->opt_timing != 0;
+    float acc_ms[4] = {0, 0, 0, 0};
+    if (timing) event_record(ev[0], c->stream);
+
+    int cur = 0;
+    Queues q;
+    auto bind = [&](uint32_t depth) {
+        q.ray0 = c->ray[cur][0].p; q.ray1 = c->ray[cur][1].p; q.ray2 = c->ray[cur][2].p;
+        q.st0 = c->st[cur][0].p; q.st1 = c->st[cur][1].p;
+        q.nray0 = c->ray[cur ^ 1][0].p; q.nray1 = c->ray[cur ^ 1][1].p; q.nray2 = c->ray[cur ^ 1][2].p;
+        q.nst0 = c->st[cur ^ 1][0].p; q.nst1 = c->st[cur ^ 1][1].p;
+        q.hit0 = c->hit0.p; q.hit_inst = c->hit_inst.p;
+        q.sh0 = c->sh[0].p; q.sh1 = c->sh[1].p; q.sh2 = c->sh[2].p; q.sh3 = c->sh[3].p;
+        q.result = c->result.p;
+        q.n_cur = cnt + depth; q.n_next = cnt + depth + 1; q.n_shadow = cnt + M + depth;
+    };
+    bind(0);
+    RT3_LAUNCH_1D(k_generate, P, c->stream, f, q);
+    if (timing) event_record(ev[1], c->stream);
+
+    const bool unbounded = rs->max_depth <= 0;
+    const uint32_t depth_limit = unbounded ? M - 2 : (uint32_t)rs->max_depth;
+    RT3_REQUIRE(depth_limit <= M - 2, RT3_ERR_INVALID, "launch_subframe: max_depth too large");
+    for (uint32_t depth = 0; depth < depth_limit; depth++) {
+        bind(depth);
+        Event e0, e1, e2, e3;
+        if (timing) event_record(e0, c->stream);
+        TraverseArgs a;
+        a.scene = sc;
+        a.rays = RayPlanes{q.ray0, q.ray1, q.ray2, 1u};
+        a.count_ptr = q.n_cur; a.count = 0; a.fetch = cnt + 2 * M + depth;
+        a.hit0 = q.hit0; a.hit_inst = q.hit_inst; a.contrib = nullptr; a.result = nullptr;
+        a.stat = c->d_stats.p + (depth == 0 ? 0 : 1);
+        launch_traverse<TRAV_EXTEND>(c, a);
+        if (timing) event_record(e1, c->stream);
+#ifdef RT3_EMULATE
+        k_shade(f, sc, q);
+#else
+        k_shade<<<c->num_sms * 4, 256, 0, c->stream>>>(f, sc, q);
+        RT3_CUDA(cudaGetLastError());
+#endif
+        count_launch();
+        if (timing) event_record(e2, c->stream);
+        TraverseArgs s;
+        s.scene = sc;
+        s.rays = RayPlanes{q.sh0, q.sh1, q.sh2, 1u};
+        s.count_ptr = q.n_shadow; s.count = 0; s.fetch = cnt + 3 * M + depth;
+        s.hit0 = nullptr; s.hit_inst = nullptr; s.contrib = q.sh3; s.result = q.result;
+        s.stat = c->d_stats.p + 2;
+        launch_traverse<TRAV_CONNECT>(c, s);
+        if (timing) {
+            event_record(e3, c->stream);
+            stream_sync(c->stream);
+            acc_ms[0] += event_ms(e0, e1); acc_ms[1] += event_ms(e1, e2); acc_ms[2] += event_ms(e2, e3);
+        }
+        cur ^= 1;
+        if (unbounded) {  // reference semantics: paths end only by miss / Russian roulette (raygen.cu:48-72)
+            uint32_t nnext = 0;
+            d2h(&nnext, q.n_next, sizeof(nnext), c->stream);
+            stream_sync(c->stream);
+            if (nnext == 0) break;
+        }
+    }
+    if (timing) event_record(ev[2], c->stream);
+    RT3_LAUNCH_1D(k_resolve, rs->width * rs->height, c->stream, f, (const float4*)c->result.p, c->accum.p, c->frame.p);
+    if (timing) {
+        event_record(ev[3], c->stream);
+        stream_sync(c->stream);
+        c->ms[0] = event_ms(ev[0], ev[1]); c->ms[1] = acc_ms[0]; c->ms[2] = acc_ms[1]; c->ms[3] = acc_ms[2];
+        c->ms[4] = event_ms(ev[2], ev[3]); c->ms[5] = event_ms(ev[0], ev[3]);
+    }
+    c->samples += paths64;
+    RT3_API_END
+}
+
+int rt3_trace_device(rt3_context_t c, const void* d_rays, int n, int any_hit, void* d_hits) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && c->built, RT3_ERR_STATE, "trace: rt3_accel_build has not been called");
+    RT3_REQUIRE(n >= 0 && (n == 0 || (d_rays && d_hits)), RT3_ERR_INVALID, "trace: bad argument");
+    if (n == 0) return RT3_OK;
+    upload_hitgroups(c);
+    dev_memset(c->trace_fetch.p, 0, sizeof(uint32_t), c->stream);
+    TraverseArgs a;
+    a.scene = c->trav_scene();
+    const float4* r = (const float4*)d_rays;
+    a.rays = RayPlanes{r, r + 1, r + 2, 3u};
+    a.count_ptr = nullptr; a.count = (uint32_t)n; a.fetch = c->trace_fetch.p;
+    a.hit0 = (float4*)d_hits; a.hit_inst = nullptr; a.contrib = nullptr; a.result = nullptr; a.stat = nullptr;
+    if (any_hit) launch_traverse<TRAV_TRACE_ANY>(c, a);
+    else launch_traverse<TRAV_TRACE_CLOSEST>(c, a);
+    RT3_API_END
+}
+
+int rt3_trace(rt3_context_t c, const rt3_ray* rays, int n, int any_hit, rt3_hit* hits) {
+    RT3_API_BEGIN
+    static_assert(sizeof(rt3_ray) == 48 && sizeof(rt3_hit) == 32, "ABI record sizes");
+    RT3_REQUIRE(c && c->built, RT3_ERR_STATE, "trace: rt3_accel_build has not been called");
+    RT3_REQUIRE(n >= 0 && (n == 0 || (rays && hits)), RT3_ERR_INVALID, "trace: bad argument");
+    if (n == 0) return RT3_OK;
+    DevBuf<float4> d_rays(3 * (size_t)n), d_hits(2 * (size_t)n);
+    h2d(d_rays.p, rays, sizeof(rt3_ray) * (size_t)n, c->stream);
+    const int rc = rt3_trace_device(c, d_rays.p, n, any_hit, d_hits.p);
+    if (rc != RT3_OK) return rc;
+    d2h(hits, d_hits.p, sizeof(rt3_hit) * (size_t)n, c->stream);
+    stream_sync(c->stream);
+    RT3_API_END
+}
+
+// ------------------------------------------------------------------------------------ results
+int rt3_download_accum(rt3_context_t c, float* rgba) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && rgba && c->accum.p, RT3_ERR_STATE, "download_accum: nothing rendered");
+    d2h(rgba, c->accum.p, c->accum.bytes(), c->stream);
+    stream_sync(c->stream);
+    RT3_API_END
+}
+int rt3_download_frame(rt3_context_t c, uint8_t* rgba8) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && rgba8 && c->frame.p, RT3_ERR_STATE, "download_frame: nothing rendered");
+    d2h(rgba8, c->frame.p, c->frame.bytes(), c->stream);
+    stream_sync(c->stream);
+    RT3_API_END
+}
+int rt3_accum_device_ptr(rt3_context_t c, void** p, uint64_t* n) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && p && n && c->accum.p, RT3_ERR_STATE, "accum_device_ptr: nothing rendered");
+    stream_sync(c->stream);
+    *p = c->accum.p;
+    *n = 4ull * c->width * c->height;
+    RT3_API_END
+}
+int rt3_clear_accum(rt3_context_t c) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c, RT3_ERR_INVALID, "clear_accum: null context");
+    if (c->accum.p) dev_memset(c->accum.p, 0, c->accum.bytes(), c->stream);
+    RT3_API_END
+}
+int rt3_finalize_accum(rt3_context_t c, uint32_t total_subframes) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && c->accum.p && total_subframes > 0, RT3_ERR_STATE, "finalize_accum: nothing rendered");
+    RT3_LAUNCH_1D(k_finalize, c->width * c->height, c->stream, c->accum.p, c->frame.p, 1.0f / (float)total_subframes);
+    RT3_API_END
+}
+
+int rt3_get_stats(rt3_context_t c, rt3_stats* st) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && st, RT3_ERR_INVALID, "get_stats: null argument");
+    unsigned long long s[4] = {0, 0, 0, 0};
+    uint32_t fl[2] = {0, 0};
+    d2h(s, c->d_stats.p, sizeof(s), c->stream);
+    d2h(fl, c->d_flags.p, sizeof(fl), c->stream);
+    stream_sync(c->stream);
+    memset(st, 0, sizeof(*st));
+    st->rays_primary = s[0]; st->rays_bounce = s[1]; st->rays_shadow = s[2];
+    st->samples = c->samples;
+    st->kernel_launches = g_launch_count;
+    st->ms_generate = c->ms[0]; st->ms_extend = c->ms[1]; st->ms_shade = c->ms[2]; st->ms_connect = c->ms[3]; st->ms_resolve = c->ms[4]; st->ms_total = c->ms[5];
+    st->error_flags = fl[0]; st->max_stack_depth = fl[1];
+    RT3_API_END
+}
+int rt3_reset_stats(rt3_context_t c) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c, RT3_ERR_INVALID, "reset_stats: null context");
+    dev_memset(c->d_stats.p, 0, c->d_stats.bytes(), c->stream);
+    c->samples = 0;
+    stream_sync(c->stream);
+    RT3_API_END
+}
+
+// ------------------------------------------------------------------------------------ multi-GPU (single process, one context per GPU)
+int rt3_allreduce_accum(rt3_context_t* ctxs, int n, uint32_t total_subframes) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(ctxs && n >= 1, RT3_ERR_INVALID, "allreduce_accum: bad argument");
+#ifdef RT3_EMULATE
+    throw Error(RT3_ERR_UNSUPPORTED, "allreduce_accum: not available in the kernel-logic simulator");
+#else
+    if (n > 1) {
+        // NCCL is resolved at run time so that librt3.so has no link-time dependency on it
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        RT3_REQUIRE(lib, RT3_ERR_NCCL, "allreduce_accum: libnccl.so.2 not found");
+        typedef int (*InitAll)(void**, int, const int*);
+        typedef int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+        typedef int (*Group)(void);
+        typedef int (*Destroy)(void*);
+        InitAll initAll = (InitAll)dlsym(lib, "ncclCommInitAll");
+        AllReduce allReduce = (AllReduce)dlsym(lib, "ncclAllReduce");
+        Group gs = (Group)dlsym(lib, "ncclGroupStart"), ge = (Group)dlsym(lib, "ncclGroupEnd");
+        Destroy destroy = (Destroy)dlsym(lib, "ncclCommDestroy");
+        RT3_REQUIRE(initAll && allReduce && gs && ge && destroy, RT3_ERR_NCCL, "allreduce_accum: NCCL symbols missing");
+        std::vector<void*> comms(n);
+        std::vector<int> devs(n);
+        for (int i = 0; i < n; i++) { RT3_REQUIRE(ctxs[i] && ctxs[i]->accum.p, RT3_ERR_STATE, "allreduce_accum: context has no film"); devs[i] = ctxs[i]->device; }
+        RT3_REQUIRE(initAll(comms.data(), n, devs.data()) == 0, RT3_ERR_NCCL, "ncclCommInitAll failed");
+        RT3_REQUIRE(gs() == 0, RT3_ERR_NCCL, "ncclGroupStart failed");
+        for (int i = 0; i < n; i++) {
+            RT3_CUDA(cudaSetDevice(ctxs[i]->device));
+            const size_t count = 4ull * ctxs[i]->width * ctxs[i]->height;
+            RT3_REQUIRE(allReduce(ctxs[i]->accum.p, ctxs[i]->accum.p, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comms[i], ctxs[i]->stream) == 0, RT3_ERR_NCCL,
+                        "ncclAllReduce failed");
+        }
+        RT3_REQUIRE(ge() == 0, RT3_ERR_NCCL, "ncclGroupEnd failed");
+        for (int i = 0; i < n; i++) { RT3_CUDA(cudaSetDevice(ctxs[i]->device)); stream_sync(ctxs[i]->stream); destroy(comms[i]); }
+    }
+    for (int i = 0; i < n; i++) {
+        RT3_CUDA(cudaSetDevice(ctxs[i]->device));
+        const int rc = rt3_finalize_accum(ctxs[i], total_subframes);
+        if (rc != RT3_OK) return rc;
+        stream_sync(ctxs[i]->stream);
+    }
+#endif
+    RT3_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,399 @@
+// rt3_traverse.cuh — two-level software traversal (replaces optixTraverse on RT cores; reference
+// call sites src/shader/shader_common.h:74-88 closest hit, :119-133 occlusion; no reference source).
+//
+// Per-thread state machine over the compressed BVH8 (rt3_bvh.cuh):
+//   step() does exactly one of { intersect one wide node | test one primitive / enter one
+//   instance | pop }.  The persistent kernels in rt3_kernels.cuh drive 32 of these per warp and
+//   refill finished lanes from the ray queue (dynamic fetch).
+// Primitive tests (same operation order as the CPU oracle, oracle/rt3o_prims.hpp):
+//   triangle: watertight (Woop/Benthin/Wald 2013), barycentrics u->v1, v->v2;
+//   sphere  : cuda/sphere.cu:44-96;  curve: round linear segment, entry hits only.
+// Closest hit keeps the lexicographically smallest (t, instance, primitive) so the result does
+// not depend on traversal order; box culling is padded so it never removes such a candidate.
+#pragma once
+#include "rt3_bvh.cuh"
+
+namespace rt3 {
+
+enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2 };
+#define RT3_STACK_SIZE 48
+
+struct BlasDev {             // per geometry, device-resident table entry
+    const Node8* nodes;
+    const float4* prims;     // 3 x float4 per primitive, node-contiguous order (see k_pack_*)
+    uint32_t type, nprims;
+    // shading attributes, ORIGINAL primitive order (reference HitGroupData arrays, shader_data.h:125-136)
+    const int32_t* idx;      // mesh [nt][3]
+    const float* normals;    // mesh [nv][3]
+    const float* uvs;        // mesh [nv][2]
+    const float4* cr;        // spheres [n] / curve control points [ncp]
+    const int32_t* seg;      // curves [nseg]
+};
+
+struct InstanceDev {         // traversal record (64 B)
+    float inv_static[12];    // world -> object of the static instance transform
+    uint32_t blas;
+    uint32_t nkeys;          // 0 = no motion
+    uint32_t key_offset;     // first float of this instance's keys in TravScene::keys
+    float t0;                // motion begin; end in t1 (kept in the shading record to stay at 64 B)
+};
+
+struct HitGroupDev {         // shading record (reference HitGroupData + motion end time)
+    float emission[3];
+    float diffuse[3];
+    int32_t tex;
+    float t1;
+};
+
+struct TravScene {
+    const Node8* tlas_nodes;
+    const uint32_t* tlas_order;     // TLAS leaf slot -> instance id
+    const InstanceDev* instances;
+    const HitGroupDev* hitgroups;
+    const BlasDev* blas;
+    const float* keys;
+    uint32_t* error_flags;          // bit0 stack overflow
+    uint32_t* max_stack;
+};
+
+struct HitRec { float t, u, v; int prim, inst; };
+
+// object-space ray of an instance at a ray time (shared by traversal and the shade stage)
+RT3_HD void instance_ray(const TravScene& sc, const InstanceDev* in, float t1, float time, float3 wo, float3 wd, float3& oo, float3& od) {
+    Affine si;
+#pragma unroll
+    for (int j = 0; j < 12; j++) si.m[j] = in->inv_static[j];
+    oo = xform_point(si, wo);
+    od = xform_vector(si, wd);
+    if (in->nkeys > 0) {
+        const Affine m = lerp_keys(sc.keys + in->key_offset, (int)in->nkeys, in->t0, t1, time);
+        const Affine mi = invert_affine(m);
+        oo = xform_point(mi, oo);
+        od = xform_vector(mi, od);
+    }
+}
+
+// ------------------------------------------------------------------------------------ primitive tests
+struct Shear { int kx, ky, kz; float Sx, Sy, Sz; };
+
+RT3_HD Shear make_shear(float3 d) {
+    Shear s;
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    s.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+    s.kx = s.kz + 1; if (s.kx == 3) s.kx = 0;
+    s.ky = s.kx + 1; if (s.ky == 3) s.ky = 0;
+    const float dz = comp(d, s.kz);
+    if (dz < 0.0f) { const int t = s.kx; s.kx = s.ky; s.ky = t; }
+    s.Sx = comp(d, s.kx) / dz;
+    s.Sy = comp(d, s.ky) / dz;
+    s.Sz = 1.0f / dz;
+    return s;
+}
+
+RT3_HD bool test_triangle(float3 o, const Shear& s, float3 v0, float3 v1, float3 v2, float& t, float& u, float& v) {
+    const float3 A = sub(v0, o), B = sub(v1, o), C = sub(v2, o);
+    const float Akz = comp(A, s.kz), Bkz = comp(B, s.kz), Ckz = comp(C, s.kz);
+    const float Ax = comp(A, s.kx) - s.Sx * Akz;
+    const float Ay = comp(A, s.ky) - s.Sy * Akz;
+    const float Bx = comp(B, s.kx) - s.Sx * Bkz;
+    const float By = comp(B, s.ky) - s.Sy * Bkz;
+    const float Cx = comp(C, s.kx) - s.Sx * Ckz;
+    const float Cy = comp(C, s.ky) - s.Sy * Ckz;
+    float U = Cx * By - Cy * Bx;
+    float V = Ax * Cy - Ay * Cx;
+    float W = Bx * Ay - By * Ax;
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {  // edge-on: redo the edge functions in double
+        const double CxBy = (double)Cx * (double)By, CyBx = (double)Cy * (double)Bx;
+        U = (float)(CxBy - CyBx);
+        const double AxCy = (double)Ax * (double)Cy, AyCx = (double)Ay * (double)Cx;
+        V = (float)(AxCy - AyCx);
+        const double BxAy = (double)Bx * (double)Ay, ByAx = (double)By * (double)Ax;
+        W = (float)(BxAy - ByAx);
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const float det = U + V + W;
+    if (det == 0.0f) return false;
+    const float Az = s.Sz * Akz, Bz = s.Sz * Bkz, Cz = s.Sz * Ckz;
+    const float T = U * Az + V * Bz + W * Cz;
+    const float rcp = 1.0f / det;
+    t = T * rcp;
+    u = V * rcp;
+    v = W * rcp;
+    return true;
+}
+
+// returns up to two candidate roots in order (cuda/sphere.cu:44-96); caller applies the interval
+RT3_HD int test_sphere(float3 o, float3 d, float3 center, float radius, float& ta, float& tb) {
+    const float3 O = sub(o, center);
+    const float l = 1.0f / length(d);
+    const float3 D = mul(d, l);
+    float b = dot(O, D);
+    float c = dot(O, O) - radius * radius;
+    float disc = b * b - c;
+    if (!(disc > 0.0f)) return 0;
+    float sdisc = sqrtf(disc);
+    const float root1 = (-b - sdisc);
+    float root11 = 0.0f;
+    const bool do_refine = fabsf(root1) > (10.0f * radius);
+    if (do_refine) {
+        const float3 O1 = add(O, mul(D, root1));
+        b = dot(O1, D);
+        c = dot(O1, O1) - radius * radius;
+        disc = b * b - c;
+        if (disc > 0.0f) {
+            sdisc = sqrtf(disc);
+            root11 = (-b - sdisc);
+        }
+    }
+    ta = (root1 + root11) * l;
+    const float root2 = (-b + sdisc) + (do_refine ? root1 : 0.0f);
+    tb = root2 * l;
+    return 2;
+}
+
+RT3_HD bool test_curve_linear(float3 o, float3 d, float3 pa, float ra, float3 pb, float rb, float& t, float& u) {
+    const float l = 1.0f / length(d);
+    const float3 D = mul(d, l);
+    const float t0 = dot(sub(pa, o), D);
+    const float3 ro = add(o, mul(D, t0));
+    const float3 ba = sub(pb, pa);
+    const float3 oa = sub(ro, pa);
+    const float3 ob = sub(ro, pb);
+    const float rr = ra - rb;
+    const float m0 = dot(ba, ba);
+    const float m1 = dot(ba, oa);
+    const float m2 = dot(ba, D);
+    const float m3 = dot(D, oa);
+    const float m5 = dot(oa, oa);
+    const float m6 = dot(ob, D);
+    const float m7 = dot(ob, ob);
+    const float d2 = m0 - rr * rr;
+    bool found = false;
+    float tn = 0.0f, un = 0.0f;
+    if (d2 > 0.0f) {
+        const float k2 = d2 - m2 * m2;
+        const float k1 = d2 * m3 - m1 * m2 + m2 * rr * ra;
+        const float k0 = d2 * m5 - m1 * m1 + m1 * rr * ra * 2.0f - m0 * ra * ra;
+        const float h = k1 * k1 - k0 * k2;
+        if (h > 0.0f && k2 != 0.0f) {
+            const float tb = (-sqrtf(h) - k1) / k2;
+            const float y = m1 - ra * rr + tb * m2;
+            if (y > 0.0f && y < d2) { found = true; tn = tb; un = y / d2; }
+        }
+    }
+    if (!found) {
+        const float h1 = m3 * m3 - m5 + ra * ra;
+        const float h2 = m6 * m6 - m7 + rb * rb;
+        float best = 3.0e38f;
+        if (h1 > 0.0f) { best = -m3 - sqrtf(h1); un = 0.0f; found = true; }
+        if (h2 > 0.0f) {
+            const float tc = -m6 - sqrtf(h2);
+            if (tc < best) { best = tc; un = 1.0f; }
+            found = true;
+        }
+        tn = best;
+    }
+    if (!found) return false;
+    t = (t0 + tn) * l;
+    u = un;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------ traversal state machine
+template <bool ANY_HIT>
+struct Trav {
+    // current-space ray
+    float3 o, d;
+    float3 idir;
+    float tmin, tbest, time;
+    uint32_t inv;  // bit k set <=> d_k >= 0
+    Shear sh;
+    // world-space ray (restored when an instance is left)
+    float3 wo, wd;
+    // closest hit so far
+    float hu, hv;
+    int hprim, hinst;
+    // current level
+    const Node8* nodes;
+    const float4* prims;
+    uint32_t ptype;
+    int cur_inst;
+    bool in_blas;
+    uint2 ng, tg;
+    int sp;
+    uint2 stack[RT3_STACK_SIZE];
+
+    RT3_HD void set_space(float3 oo, float3 dd) {
+        o = oo;
+        d = dd;
+        const float eps = 8.271806e-25f;  // 2^-80: keeps 1/d finite for axis-parallel rays
+        const float dx = fabsf(dd.x) > eps ? dd.x : copysignf(eps, dd.x);
+        const float dy = fabsf(dd.y) > eps ? dd.y : copysignf(eps, dd.y);
+        const float dz = fabsf(dd.z) > eps ? dd.z : copysignf(eps, dd.z);
+        idir = v3(1.0f / dx, 1.0f / dy, 1.0f / dz);
+        inv = (dx >= 0.0f ? 1u : 0u) | (dy >= 0.0f ? 2u : 0u) | (dz >= 0.0f ? 4u : 0u);
+        sh = make_shear(dd);
+    }
+
+    RT3_HD void init(const TravScene& sc, float3 ro, float3 rd, float rtmin, float rtmax, float rtime) {
+        wo = ro; wd = rd;
+        tmin = rtmin; tbest = rtmax; time = rtime;
+        hu = hv = 0.0f; hprim = -1; hinst = -1;
+        nodes = sc.tlas_nodes; prims = nullptr; ptype = 0; cur_inst = -1; in_blas = false;
+        ng = make_uint2(0u, 0x80000000u);
+        tg = make_uint2(0u, 0u);
+        sp = 0;
+        set_space(ro, rd);
+    }
+
+    RT3_HD void push(const TravScene& sc, uint2 e) {
+        if (sp < RT3_STACK_SIZE) stack[sp++] = e;
+        else rt3_atomic_or(sc.error_flags, 1u);
+    }
+
+    RT3_HD bool in_range(float t) const { return t > tmin && (hprim < 0 ? t < tbest : t <= tbest); }
+
+    // returns true if the candidate was accepted
+    RT3_HD bool accept(float t, float u, float v, int prim) {
+        if (!in_range(t)) return false;
+        if (!ANY_HIT && hprim >= 0 && t == tbest) {
+            if (!(cur_inst < hinst || (cur_inst == hinst && prim < hprim))) return false;
+        }
+        tbest = t; hu = u; hv = v; hprim = prim; hinst = cur_inst;
+        return true;
+    }
+
+    RT3_HD void node_step(const TravScene& sc) {
+        const uint32_t hits = ng.y;
+        const int bit = 31 - rt3_clz(hits);
+        ng.y &= ~(1u << bit);
+        if (ng.y & 0xff000000u) push(sc, ng);
+        const uint32_t slot = ((uint32_t)bit - 24u) ^ inv;
+        const uint32_t rel = (uint32_t)rt3_popc(hits & 0xffu & ((1u << slot) - 1u));
+        const uint4* np = reinterpret_cast<const uint4*>(nodes + (ng.x + rel));
+        const uint4 n0 = rt3_ldg(np + 0), n1 = rt3_ldg(np + 1), n2 = rt3_ldg(np + 2), n3 = rt3_ldg(np + 3), n4 = rt3_ldg(np + 4);
+
+        const float adjx = rt3_u2f((n0.w & 0xffu) << 23) * idir.x;
+        const float adjy = rt3_u2f(((n0.w >> 8) & 0xffu) << 23) * idir.y;
+        const float adjz = rt3_u2f(((n0.w >> 16) & 0xffu) << 23) * idir.z;
+        const float orgx = (rt3_u2f(n0.x) - o.x) * idir.x;
+        const float orgy = (rt3_u2f(n0.y) - o.y) * idir.y;
+        const float orgz = (rt3_u2f(n0.z) - o.z) * idir.z;
+        // conservative padding of the slab distances (a few ulps of the largest operand)
+        const float keps = 4.76837158e-7f;  // 2^-21
+        const float padx = keps * (fabsf(orgx) + 255.0f * fabsf(adjx));
+        const float pady = keps * (fabsf(orgy) + 255.0f * fabsf(adjy));
+        const float padz = keps * (fabsf(orgz) + 255.0f * fabsf(adjz));
+        const float nox = orgx - padx, fox = orgx + padx;
+        const float noy = orgy - pady, foy = orgy + pady;
+        const float noz = orgz - padz, foz = orgz + padz;
+
+        uint32_t hitmask = 0;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const uint32_t meta4 = half ? n1.w : n1.z;
+            const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
+            const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
+            const uint32_t nx = (inv & 1u) ? lox : hix, fx = (inv & 1u) ? hix : lox;
+            const uint32_t ny = (inv & 2u) ? loy : hiy, fy = (inv & 2u) ? hiy : loy;
+            const uint32_t nz = (inv & 4u) ? loz : hiz, fz = (inv & 4u) ? hiz : loz;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t m = (meta4 >> (8 * j)) & 0xffu;
+                const float tnx = fmaf((float)((nx >> (8 * j)) & 0xffu), adjx, nox);
+                const float tny = fmaf((float)((ny >> (8 * j)) & 0xffu), adjy, noy);
+                const float tnz = fmaf((float)((nz >> (8 * j)) & 0xffu), adjz, noz);
+                const float tfx = fmaf((float)((fx >> (8 * j)) & 0xffu), adjx, fox);
+                const float tfy = fmaf((float)((fy >> (8 * j)) & 0xffu), adjy, foy);
+                const float tfz = fmaf((float)((fz >> (8 * j)) & 0xffu), adjz, foz);
+                const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+                const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
+                if (m != 0u && tn <= tf) {
+                    const bool internal = (m & 0x18u) == 0x18u;
+                    const uint32_t idx = (m & 31u) ^ (internal ? inv : 0u);
+                    hitmask |= (m >> 5) << idx;
+                }
+            }
+        }
+        ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
+        tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+    }
+
+    // returns true when an any-hit ray is finished
+    RT3_HD bool prim_step(const TravScene& sc) {
+        const int bit = 31 - rt3_clz(tg.y & (0u - tg.y));  // lowest set bit
+        tg.y &= tg.y - 1u;
+        const uint32_t pi = tg.x + (uint32_t)bit;
+        if (!in_blas) {  // TLAS leaf: enter the instance
+            const int inst = (int)rt3_ldg(sc.tlas_order + pi);
+            if (ng.y & 0xff000000u) push(sc, ng);
+            if (tg.y) push(sc, tg);
+            push(sc, make_uint2(0xffffffffu, 0u));  // sentinel: leave instance
+            const InstanceDev* in = sc.instances + inst;
+            float3 oo, od;
+            instance_ray(sc, in, sc.hitgroups[inst].t1, time, wo, wd, oo, od);
+            set_space(oo, od);
+            const BlasDev* bl = sc.blas + in->blas;
+            nodes = bl->nodes; prims = bl->prims; ptype = bl->type;
+            cur_inst = inst; in_blas = true;
+            ng = make_uint2(0u, 0x80000000u);
+            tg = make_uint2(0u, 0u);
+            return false;
+        }
+        const float4* pr = prims + 3u * pi;
+        const float4 a = rt3_ldg(pr), b = rt3_ldg(pr + 1);
+        bool got = false;
+        if (ptype == PRIM_TRI) {
+            const float4 c = rt3_ldg(pr + 2);
+            float t, u, v;
+            if (test_triangle(o, sh, v3(a), v3(b), v3(c), t, u, v)) got = accept(t, u, v, (int)rt3_f2u(a.w));
+        } else if (ptype == PRIM_SPHERE) {
+            float ta, tb;
+            if (test_sphere(o, d, v3(a), a.w, ta, tb)) {
+                const int prim = (int)rt3_f2u(b.x);
+                // first root if it lies in the interval, else the second (cuda/sphere.cu:76-94)
+                if (in_range(ta)) got = accept(ta, 0.0f, 0.0f, prim);
+                else got = accept(tb, 0.0f, 0.0f, prim);
+            }
+        } else {
+            const float4 c = rt3_ldg(pr + 2);
+            float t, u;
+            if (test_curve_linear(o, d, v3(a), a.w, v3(b), b.w, t, u)) got = accept(t, u, 0.0f, (int)rt3_f2u(c.x));
+        }
+        return ANY_HIT && got;
+    }
+
+    // one unit of work; returns false when the ray is finished
+    RT3_HD bool step(const TravScene& sc) {
+        if (tg.y != 0u) {
+            if (prim_step(sc)) return false;
+            return true;
+        }
+        if (ng.y & 0xff000000u) {
+            node_step(sc);
+            return true;
+        }
+        if (sp == 0) return false;
+        const uint2 e = stack[--sp];
+        if (e.x == 0xffffffffu && e.y == 0u) {  // leave instance
+            set_space(wo, wd);
+            nodes = sc.tlas_nodes;
+            in_blas = false;
+            cur_inst = -1;
+        } else if (e.y & 0xff000000u) {
+            ng = e;
+        } else {
+            tg = e;
+        }
+        return true;
+    }
+
+    RT3_HD HitRec result() const {
+        HitRec h;
+        h.t = hprim >= 0 ? tbest : 0.0f;
+        h.u = hu; h.v = hv; h.prim = hprim; h.inst = hinst;
+        return h;
+    }
+};
+
+}  // namespace rt3

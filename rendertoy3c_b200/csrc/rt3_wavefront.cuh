@@ -1,0 +1,525 @@
+// rt3_wavefront.cuh — the wavefront stages of the path tracer (sm_100a).
+//
+// The reference runs the whole path loop inside one OptiX raygen megakernel
+// (src/shader/raygen.cu:14-87, one thread per pixel, traversal on RT cores).  Here the same
+// computation is staged over SoA queues in HBM:
+//   generate (raygen.cu:16-46)  ->  [ extend (optixTraverse, shader_common.h:74-88)
+//                                     shade  (closehit_radiance.cu:60-160 + miss.cu:22-35 + RR raygen.cu:58-71)
+//                                     connect(traceOcclusion, shader_common.h:109-134) ] x depth
+//   -> resolve (raygen.cu:75-86)
+// Queue records are 16-byte float4 planes indexed by queue slot (coalesced 128-bit accesses);
+// surviving paths are compacted into the next queue with one atomic per warp (ballot + popc).
+// A path's radiance is accumulated in bounce order into result[path]; resolve sums the samples
+// of a pixel in sample order, so the image is bit-identical to the CPU oracle.
+#pragma once
+#include "rt3_traverse.cuh"
+
+namespace rt3 {
+
+struct TexDev { const uchar4* px; int32_t w, h, addr, filt; };
+
+struct RayPlanes {           // stride in float4 units: 1 for SoA planes, 3 for the AoS rt3_ray
+    const float4* r0;        // {o.xyz, tmin}
+    const float4* r1;        // {d.xyz, tmax}
+    const float4* r2;        // {time, path id (bits), -, -}
+    uint32_t stride;
+};
+
+struct TraverseArgs {
+    TravScene scene;
+    RayPlanes rays;
+    const uint32_t* count_ptr;   // number of rays (device-resident queue counter) or null
+    uint32_t count;              // used when count_ptr == null
+    uint32_t* fetch;             // persistent-kernel work counter (zeroed by the host)
+    // outputs
+    float4* hit0;                // extend: {t,u,v,prim}; trace: rt3_hit AoS (2 float4 per hit)
+    int32_t* hit_inst;           // extend
+    const float4* contrib;       // connect: {contribution.xyz, -}
+    float4* result;              // connect: per-path radiance
+    unsigned long long* stat;    // ray counter to bump by count
+};
+
+enum { TRAV_EXTEND = 0, TRAV_CONNECT = 1, TRAV_TRACE_CLOSEST = 2, TRAV_TRACE_ANY = 3 };
+
+template <int MODE>
+RT3_HD void trav_begin(const TraverseArgs& a, uint32_t i, Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY)>& tr) {
+    const float4 r0 = a.rays.r0[(size_t)i * a.rays.stride];
+    const float4 r1 = a.rays.r1[(size_t)i * a.rays.stride];
+    const float4 r2 = a.rays.r2[(size_t)i * a.rays.stride];
+    tr.init(a.scene, v3(r0), v3(r1), r0.w, r1.w, r2.x);
+}
+
+template <int MODE>
+RT3_HD void trav_end(const TraverseArgs& a, uint32_t i, const Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY)>& tr) {
+    const HitRec h = tr.result();
+    if (MODE == TRAV_EXTEND) {
+        a.hit0[i] = make_float4(h.t, h.u, h.v, rt3_u2f((uint32_t)h.prim));
+        a.hit_inst[i] = h.inst;
+    } else if (MODE == TRAV_CONNECT) {
+        const uint32_t path = rt3_f2u(a.rays.r2[(size_t)i * a.rays.stride].y);
+        const float4 c = a.contrib[i];
+        if (h.prim < 0) {  // unoccluded: result += radiance * last_attenuation (raygen.cu:59)
+            float4 r = a.result[path];
+            r.x = r.x + c.x; r.y = r.y + c.y; r.z = r.z + c.z;
+            a.result[path] = r;
+        } else {           // occluded: the reference adds (Le*0)*last_att, which is NaN iff the product is not finite
+            const float zx = c.x * 0.0f, zy = c.y * 0.0f, zz = c.z * 0.0f;
+            if (zx != 0.0f || zy != 0.0f || zz != 0.0f) {
+                float4 r = a.result[path];
+                r.x = r.x + zx; r.y = r.y + zy; r.z = r.z + zz;
+                a.result[path] = r;
+            }
+        }
+    } else {
+        a.hit0[2 * (size_t)i] = make_float4(h.t, h.u, h.v, rt3_u2f((uint32_t)h.prim));
+        a.hit0[2 * (size_t)i + 1] = make_float4(rt3_u2f((uint32_t)h.inst), 0.0f, 0.0f, 0.0f);
+    }
+}
+
+#ifdef RT3_EMULATE
+template <int MODE>
+static void k_traverse(TraverseArgs a) {
+    const uint32_t n = a.count_ptr ? *a.count_ptr : a.count;
+    if (a.stat) *a.stat += n;
+    for (uint32_t i = 0; i < n; i++) {
+        Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY)> tr;
+        trav_begin<MODE>(a, i, tr);
+        uint32_t hw = 0;
+        while (tr.step(a.scene)) { if ((uint32_t)tr.sp > hw) hw = (uint32_t)tr.sp; }
+        if (hw > *a.scene.max_stack) *a.scene.max_stack = hw;
+        trav_end<MODE>(a, i, tr);
+    }
+}
+#else
+#ifndef RT3_TRAV_THREADS
+#define RT3_TRAV_THREADS 128
+#endif
+#ifndef RT3_TRAV_MIN_BLOCKS
+#define RT3_TRAV_MIN_BLOCKS 4
+#endif
+#ifndef RT3_REFILL_THRESHOLD
+#define RT3_REFILL_THRESHOLD 20
+#endif
+// Persistent threads with dynamic fetch: a warp keeps traversing until fewer than
+// RT3_REFILL_THRESHOLD lanes are busy, then refills the idle lanes from the queue with a single
+// atomicAdd per warp (warp-aggregated fetch).
+template <int MODE>
+__global__ void __launch_bounds__(RT3_TRAV_THREADS, RT3_TRAV_MIN_BLOCKS) k_traverse(TraverseArgs a) {
+    const uint32_t n = a.count_ptr ? *a.count_ptr : a.count;
+    if (a.stat && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.stat, (unsigned long long)n);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY)> tr;
+    bool active = false;
+    bool exhausted = false;
+    uint32_t my = 0;
+    for (;;) {
+        const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (idle != 0u && !exhausted) {
+            const uint32_t nidle = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(a.fetch, nidle);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!active) {
+                const uint32_t cand = base + __popc(idle & lt_mask);
+                if (cand < n) {
+                    my = cand;
+                    trav_begin<MODE>(a, my, tr);
+                    active = true;
+                }
+            }
+            if (base + nidle >= n) exhausted = true;
+        }
+        uint32_t busy = __ballot_sync(0xffffffffu, active);
+        if (busy == 0u) break;
+        const uint32_t threshold = exhausted ? 1u : RT3_REFILL_THRESHOLD;
+        while (__popc(busy) >= threshold) {
+            if (active) {
+                if (!tr.step(a.scene)) {
+                    trav_end<MODE>(a, my, tr);
+                    active = false;
+                }
+            }
+            busy = __ballot_sync(0xffffffffu, active);
+        }
+    }
+}
+#endif
+
+// ------------------------------------------------------------------------------------ geometry packing / boxes
+RT3_GLOBAL(k_tri_boxes, const float* verts, const int32_t* idx, float4* lo, float4* hi) {
+    const uint32_t p = RT3_THREAD_ID();
+    if (p >= rt3_n_) return;
+    const float3 a = ld3(verts + 3 * (size_t)idx[3 * (size_t)p]), b = ld3(verts + 3 * (size_t)idx[3 * (size_t)p + 1]),
+                 c = ld3(verts + 3 * (size_t)idx[3 * (size_t)p + 2]);
+    lo[p] = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.0f);
+    hi[p] = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.0f);
+}
+RT3_GLOBAL(k_sphere_boxes, const float4* cr, float4* lo, float4* hi) {
+    const uint32_t p = RT3_THREAD_ID();
+    if (p >= rt3_n_) return;
+    const float4 s = cr[p];
+    const float r = fabsf(s.w);
+    lo[p] = make_float4(s.x - r, s.y - r, s.z - r, 0.0f);
+    hi[p] = make_float4(s.x + r, s.y + r, s.z + r, 0.0f);
+}
+RT3_GLOBAL(k_curve_boxes, const float4* cp, const int32_t* seg, float4* lo, float4* hi) {
+    const uint32_t p = RT3_THREAD_ID();
+    if (p >= rt3_n_) return;
+    const float4 a = cp[seg[p]], b = cp[seg[p] + 1];
+    const float ra = fabsf(a.w), rb = fabsf(b.w);
+    lo[p] = make_float4(fminf(a.x - ra, b.x - rb), fminf(a.y - ra, b.y - rb), fminf(a.z - ra, b.z - rb), 0.0f);
+    hi[p] = make_float4(fmaxf(a.x + ra, b.x + rb), fmaxf(a.y + ra, b.y + rb), fmaxf(a.z + ra, b.z + rb), 0.0f);
+}
+// primitive records in node-contiguous order: 3 x float4 each, original id kept for the hit record
+RT3_GLOBAL(k_pack_tris, const float* verts, const int32_t* idx, const uint32_t* order, float4* out) {
+    const uint32_t j = RT3_THREAD_ID();
+    if (j >= rt3_n_) return;
+    const uint32_t p = order[j];
+    const float3 a = ld3(verts + 3 * (size_t)idx[3 * (size_t)p]), b = ld3(verts + 3 * (size_t)idx[3 * (size_t)p + 1]),
+                 c = ld3(verts + 3 * (size_t)idx[3 * (size_t)p + 2]);
+    out[3 * (size_t)j] = make_float4(a.x, a.y, a.z, rt3_u2f(p));
+    out[3 * (size_t)j + 1] = make_float4(b.x, b.y, b.z, 0.0f);
+    out[3 * (size_t)j + 2] = make_float4(c.x, c.y, c.z, 0.0f);
+}
+RT3_GLOBAL(k_pack_spheres, const float4* cr, const uint32_t* order, float4* out) {
+    const uint32_t j = RT3_THREAD_ID();
+    if (j >= rt3_n_) return;
+    const uint32_t p = order[j];
+    out[3 * (size_t)j] = cr[p];
+    out[3 * (size_t)j + 1] = make_float4(rt3_u2f(p), 0.0f, 0.0f, 0.0f);
+    out[3 * (size_t)j + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+RT3_GLOBAL(k_pack_curves, const float4* cp, const int32_t* seg, const uint32_t* order, float4* out) {
+    const uint32_t j = RT3_THREAD_ID();
+    if (j >= rt3_n_) return;
+    const uint32_t p = order[j];
+    out[3 * (size_t)j] = cp[seg[p]];
+    out[3 * (size_t)j + 1] = cp[seg[p] + 1];
+    out[3 * (size_t)j + 2] = make_float4(rt3_u2f(p), 0.0f, 0.0f, 0.0f);
+}
+// world-space box of every instance: union over motion keys of the transformed BLAS root box
+struct BlasBounds { float lo[3], hi[3]; };
+RT3_GLOBAL(k_instance_boxes, const InstanceDev* inst, const float* inst_static, const BlasBounds* bb, const float* keys, float4* lo, float4* hi) {
+    const uint32_t i = RT3_THREAD_ID();
+    if (i >= rt3_n_) return;
+    const InstanceDev in = inst[i];
+    const BlasBounds b = bb[in.blas];
+    Affine st;
+    for (int j = 0; j < 12; j++) st.m[j] = inst_static[12 * (size_t)i + j];
+    float3 mn = v3(3e38f, 3e38f, 3e38f), mx = v3(-3e38f, -3e38f, -3e38f);
+    const int nk = in.nkeys > 0 ? (int)in.nkeys : 1;
+    for (int k = 0; k < nk; k++) {
+        Affine km;
+        if (in.nkeys > 0) for (int j = 0; j < 12; j++) km.m[j] = keys[in.key_offset + 12 * k + j];
+        for (int c = 0; c < 8; c++) {
+            float3 p = v3((c & 1) ? b.hi[0] : b.lo[0], (c & 2) ? b.hi[1] : b.lo[1], (c & 4) ? b.hi[2] : b.lo[2]);
+            if (in.nkeys > 0) p = xform_point(km, p);
+            p = xform_point(st, p);
+            mn = v3(fminf(mn.x, p.x), fminf(mn.y, p.y), fminf(mn.z, p.z));
+            mx = v3(fmaxf(mx.x, p.x), fmaxf(mx.y, p.y), fmaxf(mx.z, p.z));
+        }
+    }
+    // pad by a few ulps: the per-ray inverse transform is not exactly the inverse of these corners
+    const float3 pad = v3(1e-5f * (fabsf(mn.x) + fabsf(mx.x)) + 1e-7f, 1e-5f * (fabsf(mn.y) + fabsf(mx.y)) + 1e-7f,
+                          1e-5f * (fabsf(mn.z) + fabsf(mx.z)) + 1e-7f);
+    lo[i] = make_float4(mn.x - pad.x, mn.y - pad.y, mn.z - pad.z, 0.0f);
+    hi[i] = make_float4(mx.x + pad.x, mx.y + pad.y, mx.z + pad.z, 0.0f);
+}
+RT3_GLOBAL(k_invert_static, const float* xf, InstanceDev* inst) {
+    const uint32_t i = RT3_THREAD_ID();
+    if (i >= rt3_n_) return;
+    Affine a;
+    for (int j = 0; j < 12; j++) a.m[j] = xf[12 * (size_t)i + j];
+    const Affine r = invert_affine(a);
+    for (int j = 0; j < 12; j++) inst[i].inv_static[j] = r.m[j];
+}
+
+// ------------------------------------------------------------------------------------ frame parameters
+struct FrameParams {
+    uint32_t width, height, spl, subframe;
+    float eye[3], U[3], V[3], W[3];
+    float miss[3];
+    int32_t max_depth, accum_mode;
+    const Light* lights;
+    uint32_t nlights;
+    const TexDev* tex;
+};
+
+struct Queues {
+    float4* ray0; float4* ray1; float4* ray2;     // current rays
+    float4* st0; float4* st1;                      // {att, seed}, {last_att, depth}
+    float4* nray0; float4* nray1; float4* nray2;   // next rays
+    float4* nst0; float4* nst1;
+    float4* hit0; int32_t* hit_inst;
+    float4* sh0; float4* sh1; float4* sh2; float4* sh3;  // shadow rays + contribution
+    float4* result;                                // per path
+    uint32_t* n_cur;                               // device counters
+    uint32_t* n_next;
+    uint32_t* n_shadow;
+};
+
+// ------------------------------------------------------------------------------------ generate (raygen.cu:16-46)
+RT3_GLOBAL(k_generate, FrameParams f, Queues q) {
+    const uint32_t p = RT3_THREAD_ID();
+    if (p >= rt3_n_) return;
+    const uint32_t npix = f.width * f.height;
+    const uint32_t pix = p % npix, k = p / npix;
+    const uint32_t x = pix % f.width, y = pix / f.width;
+    uint32_t seed = tea4(pix, f.subframe);
+    for (uint32_t i = 0; i < 2u * k; i++) seed = 1664525u * seed + 1013904223u;  // samples of a launch share one LCG stream (Q8)
+    const float jx = rnd(seed);
+    const float jy = rnd(seed);
+    const float dx = 2.0f * (((float)x + jx) / (float)f.width) - 1.0f;
+    const float dy = 2.0f * (((float)y + jy) / (float)f.height) - 1.0f;
+    const float3 dir = normalize(add(add(mul(ld3(f.U), dx), mul(ld3(f.V), dy)), ld3(f.W)));
+    uint32_t pseed = seed;
+    const float time = rnd(pseed);  // traceRadiance draws the ray time first (shader_common.h:64)
+    q.ray0[p] = make_float4(f.eye[0], f.eye[1], f.eye[2], 0.01f);
+    q.ray1[p] = make_float4(dir.x, dir.y, dir.z, 1e16f);
+    q.ray2[p] = make_float4(time, rt3_u2f(p), 0.0f, 0.0f);
+    q.st0[p] = make_float4(1.0f, 1.0f, 1.0f, rt3_u2f(pseed));
+    q.st1[p] = make_float4(1.0f, 1.0f, 1.0f, rt3_u2f(0u));
+    q.result[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (p == 0) *q.n_cur = rt3_n_;
+}
+
+// ------------------------------------------------------------------------------------ LocalGeometry / LocalShading
+struct LocalGeometry {   // subset of cuda/LocalGeometry.h:40-58 that the Lambert closure consumes
+    float3 P, N;
+    float2 UV;
+};
+
+RT3_HD float3 fetch_texture(const TexDev& tx, float u, float v) {  // tex2D point/wrap/normalised RGBA8 (cuda_texture.h:52-74, Q9/Q10)
+    int x, y;
+    if (tx.addr == 0) {
+        const float fu = u - floorf(u), fv = v - floorf(v);
+        x = (int)(fu * (float)tx.w);
+        y = (int)(fv * (float)tx.h);
+    } else {
+        x = (int)(fminf(fmaxf(u, 0.0f), 1.0f) * (float)tx.w);
+        y = (int)(fminf(fmaxf(v, 0.0f), 1.0f) * (float)tx.h);
+    }
+    x = x > tx.w - 1 ? tx.w - 1 : x;
+    y = y > tx.h - 1 ? tx.h - 1 : y;
+    const uchar4 t = rt3_ldg(tx.px + (size_t)y * tx.w + x);
+    return v3((float)t.x / 255.0f, (float)t.y / 255.0f, (float)t.z / 255.0f);
+}
+
+RT3_HD LocalGeometry local_geometry(const TravScene& sc, const HitRec& h, float3 o, float3 d, float time) {
+    LocalGeometry lg;
+    const InstanceDev* in = sc.instances + h.inst;
+    const BlasDev* b = sc.blas + in->blas;
+    const float t1 = sc.hitgroups[h.inst].t1;
+    float3 n_obj;
+    if (b->type == PRIM_TRI) {  // closehit_radiance.cu:66-73
+        const int i0 = b->idx[3 * (size_t)h.prim], i1 = b->idx[3 * (size_t)h.prim + 1], i2 = b->idx[3 * (size_t)h.prim + 2];
+        const float w0 = 1.0f - h.u - h.v;
+        n_obj = add(add(mul(ld3(b->normals + 3 * (size_t)i0), w0), mul(ld3(b->normals + 3 * (size_t)i1), h.u)), mul(ld3(b->normals + 3 * (size_t)i2), h.v));
+        lg.UV.x = w0 * b->uvs[2 * (size_t)i0] + h.u * b->uvs[2 * (size_t)i1] + h.v * b->uvs[2 * (size_t)i2];
+        lg.UV.y = w0 * b->uvs[2 * (size_t)i0 + 1] + h.u * b->uvs[2 * (size_t)i1 + 1] + h.v * b->uvs[2 * (size_t)i2 + 1];
+    } else {
+        float3 oo, od;
+        instance_ray(sc, in, t1, time, o, d, oo, od);
+        float3 ps = add(oo, mul(od, h.t));
+        if (b->type == PRIM_SPHERE) {  // cuda/sphere.cu:79: normal = (O + t*D) / radius
+            const float4 s = b->cr[h.prim];
+            n_obj = divs(sub(ps, v3(s)), s.w);
+            lg.UV = make_float2(0.0f, 0.0f);
+        } else {  // cuda/curve.h:382-425 surfaceNormal<LinearInterpolator>
+            const float4 c0 = b->cr[b->seg[h.prim]], c1 = b->cr[b->seg[h.prim] + 1];
+            if (h.u == 0.0f) n_obj = sub(ps, v3(c0));
+            else if (h.u >= 1.0f) n_obj = sub(ps, v3(c1));
+            else {
+                const float3 dd3 = sub(v3(c1), v3(c0));
+                const float dr = c1.w - c0.w;
+                const float3 p = add(v3(c0), mul(dd3, h.u));
+                const float r = c0.w + h.u * dr;
+                const float dd = dot(dd3, dd3);
+                float3 o1 = sub(ps, p);
+                o1 = sub(o1, mul(dd3, dot(o1, dd3) / dd));
+                o1 = mul(o1, r / length(o1));
+                n_obj = sub(mul(o1, dd), mul(dd3, dr * r));
+            }
+            lg.UV = make_float2(h.u, 0.0f);
+        }
+    }
+    float3 n = n_obj;
+    if (in->nkeys > 0) {
+        const Affine m = lerp_keys(sc.keys + in->key_offset, (int)in->nkeys, in->t0, t1, time);
+        n = xform_normal_by_inverse(invert_affine(m), n);
+    }
+    Affine si;
+#pragma unroll
+    for (int j = 0; j < 12; j++) si.m[j] = in->inv_static[j];
+    n = xform_normal_by_inverse(si, n);
+    lg.N = normalize(n);
+    lg.P = add(o, mul(d, h.t));
+    return lg;
+}
+
+// one atomic per warp: ballot + popc prefix (device); sequential counter (emulation)
+RT3_HD uint32_t warp_append(uint32_t* counter, bool pred) {
+#ifdef RT3_EMULATE
+    return pred ? rt3_atomic_add(counter, 1u) : 0xffffffffu;
+#else
+    const uint32_t m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0u) return 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs((int)m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return pred ? base + (uint32_t)__popc(m & ((1u << lane) - 1u)) : 0xffffffffu;
+#endif
+}
+
+// ------------------------------------------------------------------------------------ shade
+// closest-hit / miss programs + the tail of the path loop, for queue slot i (valid == false: the
+// lane only takes part in the warp-wide compaction votes)
+RT3_HD void shade_slot(const FrameParams& f, const TravScene& sc, const Queues& q, uint32_t i, bool valid) {
+    bool push_ray = false, push_shadow = false;
+    float3 P = v3(0, 0, 0), ndir = v3(0, 0, 0), L = v3(0, 0, 0), att = v3(0, 0, 0), new_last = v3(0, 0, 0), contrib = v3(0, 0, 0);
+    float shadow_tmax = 0.0f, tshadow = 0.0f, next_time = 0.0f;
+    uint32_t pseed = 0, path = 0, depth = 0;
+    if (valid) {
+        const float4 r0 = q.ray0[i], r1 = q.ray1[i], r2 = q.ray2[i];
+        const float4 h0 = q.hit0[i];
+        const float4 s0 = q.st0[i], s1 = q.st1[i];
+        const float3 org = v3(r0), dir = v3(r1);
+        const float time = r2.x;
+        path = rt3_f2u(r2.y);
+        HitRec h;
+        h.t = h0.x; h.u = h0.y; h.v = h0.z; h.prim = (int)rt3_f2u(h0.w); h.inst = q.hit_inst[i];
+        att = v3(s0);
+        pseed = rt3_f2u(s0.w);
+        const float3 last_att = v3(s1);
+        depth = rt3_f2u(s1.w);
+        if (h.prim < 0) {  // __miss__radiance (miss.cu:29-32): radiance = callable(0.01), done
+            const float3 c = mul(ld3(f.miss), last_att);
+            float4 r = q.result[path];
+            r.x = r.x + c.x; r.y = r.y + c.y; r.z = r.z + c.z;
+            q.result[path] = r;
+        } else {           // __closesthit__radiance
+            const HitGroupDev hg = sc.hitgroups[h.inst];
+            const LocalGeometry lg = local_geometry(sc, h, org, dir, time);
+            const float3 Ns = faceforward(lg.N, neg(dir), lg.N);
+            P = lg.P;
+            if (depth == 0u) {  // emitted only on the camera ray (closehit_radiance.cu:78-83)
+                float4 r = q.result[path];
+                r.x = r.x + hg.emission[0]; r.y = r.y + hg.emission[1]; r.z = r.z + hg.emission[2];
+                q.result[path] = r;
+            }
+            uint32_t s = pseed;
+            (void)rnd(s);
+            (void)rnd(s);  // z1, z2 discarded (Q6)
+            const float u1 = rnd(s);
+            const float u2 = rnd(s);
+            const float3 w_in = sample_cosine_hemisphere(u1, u2);
+            const float pdf_prev = (float)((double)w_in.z / 3.14159265358979323846);
+            ndir = onb_inverse_transform(Ns, w_in);
+            const float bsdf = (float)(1.0 / 3.14159265358979323846);
+            const float3 albedo = hg.tex >= 0 ? fetch_texture(f.tex[hg.tex], lg.UV.x, lg.UV.y) : ld3(hg.diffuse);
+            att = mul(att, albedo);
+            att = mul(att, bsdf / pdf_prev);
+            // next event estimation: uniform light pick (closehit_radiance.cu:10-15,117-156)
+            const Light* lt = f.lights + (int)(rnd(s) * (float)f.nlights);
+            float3 lpos, lem;
+            float pdf_light;
+            light_sample(lt, P, s, lpos, lem, pdf_light);
+            pdf_light = pdf_light / (float)f.nlights;
+            pseed = s;
+            const float3 dl = sub(lpos, P);
+            const float Ldist = length(dl);
+            L = normalize(dl);
+            const float nDl = dot(Ns, L);
+            if (nDl > 0.0f) {
+                tshadow = rnd(s);  // local copy: same value as the RR draw below (Q7)
+                const float pdf_scat = (float)((double)fabsf(dot(L, Ns)) / 3.14159265358979323846);
+                const float3 weight = mul(albedo, power_heuristic(pdf_light, pdf_scat) * bsdf);
+                contrib = mul(mul(lem, weight), last_att);
+                shadow_tmax = Ldist - 0.01f;
+                push_shadow = true;
+            } else {  // weight = 0: the reference still adds (Le*0)*last_att — NaN iff not finite
+                const float3 z = mul(mul(lem, 0.0f), last_att);
+                if (z.x != 0.0f || z.y != 0.0f || z.z != 0.0f) {
+                    float4 r = q.result[path];
+                    r.x = r.x + z.x; r.y = r.y + z.y; r.z = r.z + z.z;
+                    q.result[path] = r;
+                }
+            }
+            new_last = att;
+            // Russian roulette (raygen.cu:62-66) + depth bound (extension)
+            const float p = att.x * 0.30f + att.y * 0.59f + att.z * 0.11f;
+            if (!(rnd(pseed) > p)) {
+                att = divs(att, p);
+                depth += 1u;
+                if (f.max_depth <= 0 || (int)depth < f.max_depth) {
+                    next_time = rnd(pseed);
+                    push_ray = true;
+                }
+            }
+        }
+    }
+    const uint32_t sslot = warp_append(q.n_shadow, push_shadow);
+    if (push_shadow) {
+        q.sh0[sslot] = make_float4(P.x, P.y, P.z, 0.001f);
+        q.sh1[sslot] = make_float4(L.x, L.y, L.z, shadow_tmax);
+        q.sh2[sslot] = make_float4(tshadow, rt3_u2f(path), 0.0f, 0.0f);
+        q.sh3[sslot] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+    }
+    const uint32_t rslot = warp_append(q.n_next, push_ray);
+    if (push_ray) {
+        q.nray0[rslot] = make_float4(P.x, P.y, P.z, 0.01f);
+        q.nray1[rslot] = make_float4(ndir.x, ndir.y, ndir.z, 1e16f);
+        q.nray2[rslot] = make_float4(next_time, rt3_u2f(path), 0.0f, 0.0f);
+        q.nst0[rslot] = make_float4(att.x, att.y, att.z, rt3_u2f(pseed));
+        q.nst1[rslot] = make_float4(new_last.x, new_last.y, new_last.z, rt3_u2f(depth));
+    }
+}
+
+#ifdef RT3_EMULATE
+static void k_shade(FrameParams f, TravScene sc, Queues q) {
+    const uint32_t n = *q.n_cur;
+    for (uint32_t i = 0; i < n; i++) shade_slot(f, sc, q, i, true);
+}
+#else
+__global__ void __launch_bounds__(256) k_shade(FrameParams f, TravScene sc, Queues q) {
+    const uint32_t n = *q.n_cur;
+    const uint32_t n32 = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += gridDim.x * blockDim.x) shade_slot(f, sc, q, i, i < n);
+}
+#endif
+
+// ------------------------------------------------------------------------------------ resolve (raygen.cu:75-86)
+RT3_GLOBAL(k_resolve, FrameParams f, const float4* result, float4* accum, uchar4* frame) {
+    const uint32_t pix = RT3_THREAD_ID();
+    if (pix >= rt3_n_) return;
+    const uint32_t npix = f.width * f.height;
+    float3 res = v3(0.0f, 0.0f, 0.0f);
+    for (uint32_t k = 0; k < f.spl; k++) res = add(res, v3(result[(size_t)k * npix + pix]));
+    float3 c = divs(res, (float)f.spl);
+    if (f.accum_mode == 0) {
+        if (f.subframe > 0u) {
+            const float a = 1.0f / (float)(f.subframe + 1u);
+            const float3 prev = v3(accum[pix]);
+            c = add(prev, mul(sub(c, prev), a));  // lerp(prev, c, a) = prev + a*(c-prev), vec_math.h:515-518
+        }
+        accum[pix] = make_float4(c.x, c.y, c.z, 1.0f);
+        frame[pix] = make_color(c);
+    } else {
+        const float4 a = accum[pix];  // SUM mode: cleared by rt3_clear_accum / film (re)allocation
+        accum[pix] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + 1.0f);
+    }
+}
+// after the multi-GPU SUM reduce: accum = sum / total_subframes, refresh the 8-bit frame
+RT3_GLOBAL(k_finalize, float4* accum, uchar4* frame, float inv_n) {
+    const uint32_t pix = RT3_THREAD_ID();
+    if (pix >= rt3_n_) return;
+    const float4 a = accum[pix];
+    const float3 c = v3(a.x * inv_n, a.y * inv_n, a.z * inv_n);
+    accum[pix] = make_float4(c.x, c.y, c.z, 1.0f);
+    frame[pix] = make_color(c);
+}
+
+}  // namespace rt3

@@ -1,0 +1,90 @@
+"""Shared parity checks: a backend under test (librt3.so on the GPU, or the kernel-logic simulator on
+this box) against the CPU oracle on the same seeded inputs."""
+import numpy as np
+
+from oracle_backend import OracleScene
+from rendertoy3c_b200 import scenes
+from rendertoy3c_b200._abi import RAY_DTYPE
+from rendertoy3c_b200.api import camera_rays, make_settings
+
+SMALL = {
+    "cornell": lambda: scenes.cornell(width=64, height=64),
+    "terrain": lambda: scenes.terrain(n=40, width=80, height=48, tex_size=64),
+    "instanced": lambda: scenes.instanced(n_inst=27, blob_n=10, n_spheres=16, width=80, height=48),
+    "motion": lambda: scenes.motion(n_inst=8, blob_n=8, n_spheres=10, n_curves=50, width=80, height=48),
+}
+
+
+def random_rays(desc, n, seed, extent=None):
+    """half camera-like rays from the eye, half rays between random points around the scene"""
+    rng = np.random.RandomState(seed)
+    eye = np.asarray(desc.camera.eye, dtype=np.float32)
+    look = np.asarray(desc.camera.lookat, dtype=np.float32)
+    ext = extent or float(np.linalg.norm(eye - look))
+    rays = np.zeros(n, dtype=RAY_DTYPE)
+    h = n // 2
+    d = (look - eye)[None, :] + (rng.rand(h, 3).astype(np.float32) - 0.5) * ext
+    rays["o"][:h] = eye
+    rays["d"][:h] = d
+    a = look[None, :] + (rng.rand(n - h, 3).astype(np.float32) - 0.5) * 1.5 * ext
+    b = look[None, :] + (rng.rand(n - h, 3).astype(np.float32) - 0.5) * 1.5 * ext
+    rays["o"][h:] = a
+    rays["d"][h:] = b - a
+    rays["tmin"] = 1e-3
+    rays["tmax"] = 1e16
+    rays["time"] = rng.rand(n).astype(np.float32)
+    return rays
+
+
+def degenerate_mask(oracle, rays, hits):
+    """rays excluded from the bit-exact ID check — edge/vertex grazes and near-ties.  The ID
+    check in these tests is nevertheless applied to ALL rays; this mask is only reported."""
+    u, v = hits["u"], hits["v"]
+    hit = hits["prim"] >= 0
+    w = 1.0 - u - v
+    return hit & (np.minimum(np.minimum(u, v), w) < 1e-6)
+
+
+def check_trace(backend, oracle, rays, accel=1):
+    hb = backend.trace(rays)
+    ho = oracle.trace(rays, accel=accel)
+    assert np.array_equal(hb["prim"], ho["prim"]), "closest-hit primitive ids differ: %d of %d" % ((hb["prim"] != ho["prim"]).sum(), len(rays))
+    assert np.array_equal(hb["inst"], ho["inst"]), "closest-hit instance ids differ"
+    for k in ("t", "u", "v"):
+        assert np.array_equal(hb[k].view(np.uint32), ho[k].view(np.uint32)), "hit %s not bit-identical" % k
+    ab = backend.trace(rays, any_hit=True)
+    ao = oracle.trace(rays, any_hit=True, accel=accel)
+    assert np.array_equal(ab["prim"] >= 0, ao["prim"] >= 0), "occlusion results differ"
+    return ho
+
+
+def check_render(backend, oracle, desc, subframes=2, spl=8, width=None, height=None, max_depth=None):
+    uvw = oracle.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy,
+                            (width or desc.width) / (height or desc.height))
+    uvw_b = backend.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy,
+                               (width or desc.width) / (height or desc.height))
+    for a, b in zip(uvw, uvw_b):
+        assert np.array_equal(a, b), "camera frame differs"
+    oracle.reset_stats()
+    backend.reset_stats()
+    for sf in range(subframes):
+        rs = make_settings(desc, uvw, sf, samples_per_launch=spl, width=width, height=height, max_depth=max_depth)
+        backend.launch_subframe(rs)
+        oracle.launch_subframe(rs)
+    ab, ao = backend.download_accum(), oracle.download_accum()
+    assert np.array_equal(ab.view(np.uint32), ao.view(np.uint32)), \
+        "accumulation buffer not bit-identical to the oracle (%d of %d floats differ)" % ((ab.view(np.uint32) != ao.view(np.uint32)).sum(), ab.size)
+    fb, fo = backend.download_frame(), oracle.download_frame()
+    assert np.abs(fb.astype(int) - fo.astype(int)).max() <= 1, "8-bit frame differs by more than 1 LSB (powf)"
+    sb, so = backend.stats(), oracle.stats()
+    for k in ("rays_primary", "rays_bounce", "rays_shadow", "samples"):
+        assert sb[k] == so[k], "ray counter %s differs: %d vs %d" % (k, sb[k], so[k])
+    assert sb["error_flags"] == 0
+    return ao
+
+
+def build_pair(desc, backend):
+    o = OracleScene()
+    scenes.replay(desc, o)
+    scenes.replay(desc, backend)
+    return o

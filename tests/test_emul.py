@@ -1,0 +1,40 @@
+"""CPU-side coverage of the kernel logic: the kernel bodies of rendertoy3c_b200/csrc run through the
+kernel-logic simulator (conftest.emul_lib) against the oracle.  These are NOT the parity tests proper
+(those are tests/test_gpu_parity.py, on the B200); they keep the host logic, the BVH builder and the
+wavefront schedule covered on a box without a GPU."""
+import numpy as np
+import pytest
+
+from parity_common import SMALL, build_pair, check_render, check_trace, random_rays
+from rendertoy3c_b200.api import Context, camera_rays
+
+
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_trace_and_render_match_oracle(emul_lib, name):
+    desc = SMALL[name]()
+    with Context(0, lib_path=emul_lib) as e:
+        o = build_pair(desc, e)
+        uvw = o.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, desc.width / desc.height)
+        rays = np.concatenate([camera_rays(desc, uvw, 48, 48), random_rays(desc, 1500, 7)])
+        check_trace(e, o, rays, accel=0)
+        check_render(e, o, desc, subframes=2)
+
+
+def test_unbounded_depth_matches_oracle(emul_lib):
+    desc = SMALL["cornell"]()
+    with Context(0, lib_path=emul_lib) as e:
+        o = build_pair(desc, e)
+        check_render(e, o, desc, subframes=1, width=32, height=32, max_depth=0)
+
+
+def test_api_errors(emul_lib):
+    from rendertoy3c_b200.api import Rt3Error
+    with Context(0, lib_path=emul_lib) as e:
+        with pytest.raises(Rt3Error):
+            e.accel_build()  # no instances
+        with pytest.raises(Rt3Error):
+            e.append_instance(5, np.zeros(12, np.float32))  # bad handle
+        with pytest.raises(Rt3Error):
+            e.mesh_create(np.zeros((3, 3)), np.array([[0, 1, 7]]), np.zeros((3, 3)), np.zeros((3, 2)))  # index out of range
+        with pytest.raises(Rt3Error):
+            e.texture_create(np.zeros((4, 4, 4), np.uint8), 0, 1)  # only filter 0
