@@ -88,3 +88,25 @@ def build_pair(desc, backend):
     scenes.replay(desc, o)
     scenes.replay(desc, backend)
     return o
+
+
+def check_golden(backend, name):
+    """backend vs the COMMITTED oracle vectors (tests/golden/oracle_golden.json), no live oracle involved."""
+    import hashlib
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.json")))[name]
+    desc = SMALL[name]()
+    scenes.replay(desc, backend)
+    uvw = backend.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, desc.width / desc.height)
+    rays = np.concatenate([camera_rays(desc, uvw, 32, 32), random_rays(desc, 1000, 31)])
+    h = backend.trace(rays)
+    core = np.stack([h["t"].view(np.uint32), h["u"].view(np.uint32), h["v"].view(np.uint32), h["prim"].view(np.uint32), h["inst"].view(np.uint32)])
+    assert hashlib.sha256(core.tobytes()).hexdigest() == gold["hits_sha256"]
+    assert int((h["prim"] >= 0).sum()) == gold["n_hit"]
+    backend.reset_stats()
+    for sf in range(2):
+        backend.launch_subframe(make_settings(desc, uvw, sf))
+    assert hashlib.sha256(backend.download_accum().tobytes()).hexdigest() == gold["accum_sha256"]
+    st = backend.stats()
+    assert [st[k] for k in ("rays_primary", "rays_bounce", "rays_shadow")] == gold["rays"]

@@ -38,3 +38,10 @@ def test_api_errors(emul_lib):
             e.mesh_create(np.zeros((3, 3)), np.array([[0, 1, 7]]), np.zeros((3, 3)), np.zeros((3, 2)))  # index out of range
         with pytest.raises(Rt3Error):
             e.texture_create(np.zeros((4, 4, 4), np.uint8), 0, 1)  # only filter 0
+
+
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_committed_golden_vectors(emul_lib, name):
+    from parity_common import check_golden
+    with Context(0, lib_path=emul_lib) as e:
+        check_golden(e, name)

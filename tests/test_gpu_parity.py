@@ -61,3 +61,22 @@ def test_unbounded_depth(product_lib):
     with Context(0) as g:
         o = build_pair(desc, g)
         check_render(g, o, desc, subframes=1, width=48, height=48, max_depth=0)
+
+
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_committed_golden_vectors(product_lib, name):
+    """kernels vs tests/golden/oracle_golden.json — committed vectors, no live oracle on the GPU box"""
+    from parity_common import check_golden
+    with Context(0) as g:
+        check_golden(g, name)
+
+
+def test_empty_and_ragged_batches(product_lib):
+    from rendertoy3c_b200._abi import RAY_DTYPE
+    desc = SMALL["cornell"]()
+    with Context(0) as g:
+        o = build_pair(desc, g)
+        assert len(g.trace(np.zeros(0, RAY_DTYPE))) == 0
+        for n in (1, 31, 33, 1000):                     # not multiples of the warp size
+            rays = random_rays(desc, n, 100 + n)
+            check_trace(g, o, rays, accel=0)

@@ -1,0 +1,248 @@
+"""The oracle against (a) known answers produced by the REFERENCE'S OWN headers compiled as host code
+(tests/golden/ref_kat.json, generator oracle/ref_kat/gen_ref_kat.cpp), (b) its own brute force, and
+(c) analytic cases.  The reference ships no tests or goldens, so (a) is everything reference
+code can pin; hits and images are pinned by (b)/(c) and the committed oracle goldens."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_backend as ob
+from parity_common import SMALL, random_rays
+from rendertoy3c_b200 import scenes
+from rendertoy3c_b200._abi import RAY_DTYPE, fptr
+from rendertoy3c_b200.api import camera_rays, make_settings
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+KAT = json.load(open(os.path.join(GOLD, "ref_kat.json")))
+L = ob.lib()
+
+
+def f3(x):
+    return np.asarray(x, dtype=np.float32)
+
+
+def close(a, b, rel=1e-6, abs_=1e-7):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.all(np.abs(a - b) <= abs_ + rel * np.abs(b))
+
+
+def test_rng_kat_exact():
+    for c in KAT["tea4_rnd"]:
+        seed = L.rt3o_kat_tea4(c["v0"], c["v1"])
+        assert seed == c["seed"]
+        s = C.c_uint32(seed)
+        r = [L.rt3o_kat_rnd(C.byref(s)) for _ in range(3)]
+        assert [np.float32(x) for x in r] == [np.float32(x) for x in c["rnd"]]
+        assert s.value == c["state"]
+
+
+def test_cosine_sample_kat():
+    # the oracle replaces libm sinf/cosf by an explicit polynomial (bit-reproducible on the GPU):
+    # agreement with the reference's libm-based values is to ~1e-7 absolute, not bitwise
+    for c in KAT["cosine"]:
+        out = np.zeros(4, np.float32)
+        L.rt3o_kat_cosine_sample(C.c_float(c["u"][0]), C.c_float(c["u"][1]), fptr(out))
+        assert close(out[:3], c["w"], rel=2e-6, abs_=3e-7), (out, c)
+        assert close(out[3], c["pdf"], rel=2e-6, abs_=3e-7)
+
+
+def test_sincos_accuracy():
+    u = np.linspace(0, 1, 20001, dtype=np.float32)[:-1]
+    out = np.zeros(2, np.float32)
+    worst = 0.0
+    for x in u[::7]:
+        L.rt3o_kat_sincos_2pi(C.c_float(x), fptr(out))
+        worst = max(worst, abs(out[0] - np.sin(2 * np.pi * np.float64(x))), abs(out[1] - np.cos(2 * np.pi * np.float64(x))))
+    assert worst < 4e-7
+
+
+def test_onb_kat_exact():
+    for c in KAT["onb"]:
+        out = np.zeros(9, np.float32)
+        n, w = f3(c["n"]), f3([0.3, 0.4, 0.8660254])
+        L.rt3o_kat_onb(fptr(n), fptr(w), fptr(out))
+        assert np.array_equal(out[0:3], f3(c["T"])) and np.array_equal(out[3:6], f3(c["B"])) and np.array_equal(out[6:9], f3(c["p"]))
+
+
+def test_light_kat_exact():
+    k = KAT["light"]
+    buf = C.create_string_buffer(68)
+    e, v0, v1, v2 = f3([17, 12, 4]), f3([343, 548.7, 227]), f3([343, 548.7, 332]), f3([213, 548.7, 332])
+    L.rt3o_kat_light_make(fptr(e), fptr(v0), fptr(v1), fptr(v2), buf)
+    raw = np.frombuffer(buf.raw, dtype=np.float32)
+    assert k["sizeof"] == 68 and raw[16] == np.float32(k["area"]) and np.array_equal(raw[13:16], f3(k["normal"]))
+    for s in k["samples"]:
+        seed = C.c_uint32(s["seed"])
+        out = np.zeros(7, np.float32)
+        P = f3(s["P"])
+        L.rt3o_kat_light_sample(buf, fptr(P), C.byref(seed), fptr(out))
+        assert np.array_equal(out[0:3], f3(s["pos"])) and np.array_equal(out[3:6], f3(s["em"])) and out[6] == np.float32(s["pdf"])
+        assert seed.value == s["state"]
+
+
+def test_make_color_kat_exact():
+    for c in KAT["make_color"]:
+        out = np.zeros(4, np.uint8)
+        v = f3(c["c"])
+        L.rt3o_kat_make_color(fptr(v), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert list(out) == c["rgba"]
+
+
+def test_camera_kat_exact():
+    for c in KAT["camera"]:
+        out = np.zeros(9, np.float32)
+        e, l, u = f3(c["eye"]), f3(c["lookat"]), f3(c["up"])
+        L.rt3o_kat_camera_uvw(fptr(e), fptr(l), fptr(u), C.c_float(c["fovy"]), C.c_float(c["aspect"]), fptr(out))
+        assert np.array_equal(out, f3(c["U"] + c["V"] + c["W"]))
+
+
+def test_power_heuristic_kat():
+    for a, b, r in KAT["power_heuristic"]:
+        a, b = np.float32(a), np.float32(b)
+        assert np.float32(a * a / (a * a + b * b)) == np.float32(r)
+
+
+# ---------------------------------------------------------------- analytic primitive cases
+def tri(o, d, v, tmin=0.0, tmax=1e30):
+    out = np.zeros(3, np.float32)
+    o, d, v = f3(o), f3(d), f3(v).reshape(-1)
+    hit = L.rt3o_kat_hit_triangle(fptr(o), fptr(d), fptr(v), C.c_float(tmin), C.c_float(tmax), fptr(out))
+    return hit, out
+
+
+def test_triangle_analytic():
+    V = [[0, 0, 5], [4, 0, 5], [0, 4, 5]]
+    hit, o = tri([1, 1, 0], [0, 0, 1], V)
+    assert hit and o[0] == 5 and o[1] == 0.25 and o[2] == 0.25           # u -> v1, v -> v2 (OptiX convention)
+    hit, o = tri([1, 1, 0], [0, 0, 2], V)
+    assert hit and o[0] == 2.5                                            # t is in units of |d|
+    assert tri([1, 1, 10], [0, 0, 1], V)[0] == 0                          # behind
+    assert tri([1, 1, 10], [0, 0, -1], V)[0] == 1                         # no back-face culling
+    assert tri([3, 3, 0], [0, 0, 1], V)[0] == 0                           # outside
+    assert tri([1, 1, 0], [0, 0, 1], V, tmin=5.0)[0] == 0                 # open interval
+    assert tri([1, 1, 0], [0, 0, 1], V, tmax=5.0)[0] == 0
+    # watertight: a ray through the shared edge of two triangles hits at least one of them
+    A = [[0, 0, 5], [4, 0, 5], [0, 4, 5]]
+    B = [[4, 0, 5], [4, 4, 5], [0, 4, 5]]
+    rng = np.random.RandomState(3)
+    for _ in range(2000):
+        s = rng.rand()
+        p = np.array([4 * s, 4 * (1 - s), 5.0])
+        o_ = rng.randn(3) * 3 + np.array([2, 2, -4.0])
+        d_ = p - o_
+        assert tri(o_, d_, A)[0] or tri(o_, d_, B)[0]
+
+
+def test_sphere_analytic():
+    def sph(o, d, cr, tmin=0.0, tmax=1e30):
+        t = C.c_float()
+        o, d, cr = f3(o), f3(d), f3(cr)
+        return L.rt3o_kat_hit_sphere(fptr(o), fptr(d), fptr(cr), C.c_float(tmin), C.c_float(tmax), C.byref(t)), t.value
+    assert sph([0, 0, -5], [0, 0, 1], [0, 0, 0, 1]) == (1, 4.0)
+    assert sph([0, 0, 0], [0, 0, 1], [0, 0, 0, 1]) == (1, 1.0)              # inside: far root
+    assert sph([0, 0, -5], [0, 0, 2], [0, 0, 0, 1]) == (1, 2.0)             # unnormalised direction
+    assert sph([0, 2, -5], [0, 0, 1], [0, 0, 0, 1])[0] == 0
+    hit, t = sph([0, 0, -1000], [0, 0, 1], [0, 0, 0, 0.5])                   # refinement path (|root| > 10 r)
+    assert hit and abs(t - 999.5) < 1e-3
+
+
+def curve(o, d, a, b, tmin=0.0, tmax=1e30):
+    out = np.zeros(2, np.float32)
+    o, d, a, b = f3(o), f3(d), f3(a), f3(b)
+    return L.rt3o_kat_hit_curve(fptr(o), fptr(d), fptr(a), fptr(b), C.c_float(tmin), C.c_float(tmax), fptr(out)), out
+
+
+def test_curve_analytic_and_union_of_spheres():
+    hit, o = curve([0.5, 0, -5], [0, 0, 1], [0, 0, 0, 0.2], [1, 0, 0, 0.2])
+    assert hit and abs(o[0] - 4.8) < 1e-5 and abs(o[1] - 0.5) < 1e-5         # cylinder body
+    hit, o = curve([-0.1, 0, -5], [0, 0, 1], [0, 0, 0, 0.2], [1, 0, 0, 0.2])
+    assert hit and o[1] == 0.0                                               # end cap a
+    assert curve([0.5, 0, 0], [0, 0, 1], [0, 0, 0, 0.2], [1, 0, 0, 0.2])[0] == 0  # origin inside: entry hits only
+    # against a dense union of spheres (the definition of the primitive)
+    rng = np.random.RandomState(5)
+    a = np.array([0.1, -0.2, 0.3, 0.25]); b = np.array([0.9, 0.4, -0.1, 0.08])
+    s = np.linspace(0, 1, 4001)
+    cen = a[None, :3] + s[:, None] * (b[:3] - a[:3])[None, :]
+    rad = a[3] + s * (b[3] - a[3])
+    n_hit = 0
+    for _ in range(400):
+        o_ = rng.randn(3); o_ = 3 * o_ / np.linalg.norm(o_)
+        d_ = (a[:3] + rng.rand() * (b[:3] - a[:3]) + 0.3 * rng.randn(3)) - o_
+        d_ /= np.linalg.norm(d_)
+        oc = o_[None, :] - cen
+        bq = oc @ d_
+        disc = bq * bq - (np.sum(oc * oc, axis=1) - rad * rad)
+        ok = disc > 0
+        tref = np.min(-bq[ok] - np.sqrt(disc[ok])) if ok.any() else None
+        hit, o = curve(o_, d_, a, b)
+        if tref is None or not hit:
+            if tref is not None and (ok.sum() > 8):
+                assert hit, "missed a clear hit"
+            continue
+        n_hit += 1
+        assert abs(o[0] - tref) < 2e-3, (o, tref)
+    assert n_hit > 50
+
+
+def test_invert_affine_identity_is_exact():
+    m = scenes.IDENTITY.copy()
+    out = np.zeros(12, np.float32)
+    L.rt3o_kat_invert_affine(fptr(m), fptr(out))
+    assert np.array_equal(np.abs(out), m)
+
+
+# ---------------------------------------------------------------- BVH2 path == brute force, images, goldens
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_oracle_bvh_equals_bruteforce(name):
+    desc = SMALL[name]()
+    o = ob.OracleScene()
+    scenes.replay(desc, o)
+    uvw = o.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, desc.width / desc.height)
+    rays = np.concatenate([camera_rays(desc, uvw, 64, 64), random_rays(desc, 3000, 23)])
+    for any_hit in (False, True):
+        a, b = o.trace(rays, any_hit=any_hit, accel=0), o.trace(rays, any_hit=any_hit, accel=1)
+        if any_hit:
+            assert np.array_equal(a["prim"] >= 0, b["prim"] >= 0)
+        else:
+            assert a.tobytes() == b.tobytes()
+    assert (a["prim"] >= 0).mean() > 0.05
+
+
+def test_edge_cases_empty_and_ragged():
+    desc = SMALL["cornell"]()
+    o = ob.OracleScene()
+    scenes.replay(desc, o)
+    assert len(o.trace(np.zeros(0, RAY_DTYPE))) == 0
+    r = np.zeros(3, RAY_DTYPE)
+    r["o"] = [278, 273, -800]; r["d"] = [[0, 0, 1], [0, 0, -1], [0, 0, 1]]
+    r["tmin"] = [0.01, 0.01, 0.01]; r["tmax"] = [1e16, 1e16, 5.0]      # hit / pointing away / interval too short
+    h = o.trace(r, accel=0)
+    assert h["prim"][0] >= 0 and h["prim"][1] == -1 and h["prim"][2] == -1 and h["inst"][1] == -1
+
+
+def test_chain_sum_association_is_rounding_only():
+    """The reference keeps one running sum over the samples of a launch (raygen.cu:27,58-59); the oracle's
+    default (per-sample sums, the wavefront association) differs by fp32 rounding only."""
+    desc = SMALL["cornell"]()
+    imgs = []
+    for chain in (0, 1):
+        L.rt3o_set_chain_sum(chain)
+        o = ob.OracleScene()
+        scenes.replay(desc, o)
+        uvw = o.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, 1.0)
+        o.launch_subframe(make_settings(desc, uvw, 0))
+        imgs.append(o.download_accum()[..., :3].astype(np.float64))
+    L.rt3o_set_chain_sum(0)
+    rel = np.abs(imgs[0] - imgs[1]) / np.maximum(np.abs(imgs[1]), 1e-3)
+    assert rel.max() < 5e-6
+
+
+def test_oracle_golden_fixture():
+    """tests/golden/oracle_golden.json (made by tests/golden/make_golden.py) pins the oracle itself."""
+    import make_golden
+    gold = json.load(open(os.path.join(GOLD, "oracle_golden.json")))
+    now = make_golden.compute(ob)
+    assert now == gold
