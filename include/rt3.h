@@ -71,6 +71,7 @@ int rt3_context_create(int device, rt3_context_t* out);   /* OptixContext() src/
 void rt3_context_destroy(rt3_context_t ctx);              /* ~CUDAScene src/cuda/cuda_scene.h:161-169 */
 int rt3_sync(rt3_context_t ctx);                          /* CUDA_SYNC_CHECK src/wavefront.cpp:221 */
 const char* rt3_last_error(void);
+int rt3_get_stream(rt3_context_t ctx, void** cuda_stream); /* the cudaStream_t every launch of this context goes to (reference: state.stream, src/wavefront.cpp:302) */
 int rt3_get_stats(rt3_context_t ctx, rt3_stats* out);
 int rt3_reset_stats(rt3_context_t ctx);
 int rt3_set_option(rt3_context_t ctx, const char* key, int value); /* tuning switches: "timing", "sort_rays", "sort_materials", "persist_ctas_per_sm" */

@@ -206,6 +206,7 @@ struct Instance {
     int blas;
     Affine stat, stat_inv;
     int nkeys = 0;
+    bool identity = false;
     std::vector<float> keys;
     float t0 = 0, t1 = 1;
     f3 emission{0, 0, 0}, diffuse{0.8f, 0.8f, 0.8f};
@@ -238,16 +239,10 @@ struct rt3o_scene {
     std::vector<uint8_t> frame;
     std::atomic<uint64_t> n_primary{0}, n_bounce{0}, n_shadow{0}, n_samples{0};
 
-    // world -> object matrix of instance i at ray time
-    Affine world_to_object(const Instance& in, float time, bool& has_motion, Affine& motion_inv) const {
-        has_motion = in.nkeys > 0;
-        if (has_motion) {
-            Affine m = lerp_keys(in.keys.data(), in.nkeys, in.t0, in.t1, time);
-            motion_inv = invert_affine(m);
-        }
-        return in.stat_inv;
-    }
     void to_object(const Instance& in, float time, f3 o, f3 d, f3& oo, f3& od) const {
+        // an instance whose transform is bit-for-bit the identity (and has no motion keys) — every
+        // instance the reference creates, cuda_scene.h:141-146 — sees the world-space ray unchanged
+        if (in.identity) { oo = o; od = d; return; }
         oo = xform_point(in.stat_inv, o);
         od = xform_vector(in.stat_inv, d);
         if (in.nkeys > 0) {
@@ -597,6 +592,8 @@ static int add_instance(rt3o_scene* s, int blas, const float* stat, const float*
     in.blas = blas;
     std::memcpy(in.stat.m, stat, sizeof(float) * 12);
     in.stat_inv = invert_affine(in.stat);
+    static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    in.identity = !keys && std::memcmp(stat, ident, sizeof(ident)) == 0;
     if (keys) {
         if (nkeys < 2 || !(t1 > t0)) { g_err = "append_animated_instance: need >=2 keys and t_end > t_begin"; return -1; }
         in.nkeys = nkeys;

@@ -25,7 +25,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librt3.so")
 
 RT3_SYMBOLS = [
-    "rt3_context_create", "rt3_context_destroy", "rt3_sync", "rt3_last_error", "rt3_get_stats", "rt3_reset_stats",
+    "rt3_context_create", "rt3_context_destroy", "rt3_sync", "rt3_last_error", "rt3_get_stream", "rt3_get_stats", "rt3_reset_stats",
     "rt3_set_option", "rt3_mesh_create", "rt3_spheres_create", "rt3_curves_create", "rt3_texture_create",
     "rt3_accel_append_instance", "rt3_accel_append_animated_instance", "rt3_accel_build", "rt3_scene_set_hitgroup",
     "rt3_scene_set_lights", "rt3_light_make", "rt3_camera_uvw", "rt3_launch_subframe", "rt3_trace", "rt3_trace_device",
@@ -45,7 +45,7 @@ _libs = {}
 
 def load_library(path=None):
     """dlopen librt3.so (built in-tree by __graft_entry__.build()).  Raises if it is missing."""
-    p = path or LIB_PATH
+    p = path or os.environ.get("RT3_LIB") or LIB_PATH  # RT3_LIB: tuning builds of the same sources (tools/)
     if p not in _libs:
         if not os.path.exists(p):
             raise Rt3Error(-3, "librt3.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
@@ -217,6 +217,14 @@ class Context:
 
     def sync(self):
         self._chk(self.L.rt3_sync(self.ctx))
+
+    def stream(self):
+        p = C.c_void_p()
+        self._chk(self.L.rt3_get_stream(self.ctx, C.byref(p)))
+        return p.value or 0
+
+    def download_frame_into(self, host_ptr):
+        self._chk(self.L.rt3_download_frame(self.ctx, C.c_void_p(host_ptr)))
 
     def stats(self):
         st = Stats()

@@ -240,6 +240,17 @@ int rt3_sync(rt3_context_t c) {
     RT3_API_END
 }
 
+int rt3_get_stream(rt3_context_t c, void** stream) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && stream, RT3_ERR_INVALID, "get_stream: null argument");
+#ifdef RT3_EMULATE
+    *stream = nullptr;
+#else
+    *stream = (void*)c->stream;
+#endif
+    RT3_API_END
+}
+
 int rt3_set_option(rt3_context_t c, const char* key, int value) {
     RT3_API_BEGIN
     RT3_REQUIRE(c && key, RT3_ERR_INVALID, "set_option: null argument");
@@ -387,6 +398,8 @@ int rt3_accel_build(rt3_context_t c) {
         memset(&it[i], 0, sizeof(InstanceDev));
         it[i].blas = in.blas;
         it[i].nkeys = in.nkeys;
+        static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        it[i].identity = (in.nkeys == 0 && memcmp(in.xform, ident, sizeof(ident)) == 0) ? 1u : 0u;
         it[i].key_offset = (uint32_t)keys.size();
         it[i].t0 = in.t0;
         keys.insert(keys.end(), in.keys.begin(), in.keys.end());

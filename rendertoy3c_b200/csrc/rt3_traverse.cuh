@@ -2,9 +2,9 @@
 // call sites src/shader/shader_common.h:74-88 closest hit, :119-133 occlusion; no reference source).
 //
 // Per-thread state machine over the compressed BVH8 (rt3_bvh.cuh):
-//   step() does exactly one of { intersect one wide node | test one primitive / enter one
-//   instance | pop }.  The persistent kernels in rt3_kernels.cuh drive 32 of these per warp and
-//   refill finished lanes from the ray queue (dynamic fetch).
+//   step() is one round of a while-while loop: pop -> intersect one wide node -> test all pending
+//   primitives / enter one instance.  The persistent kernels in rt3_wavefront.cuh drive 32 of these
+//   per warp and refill finished lanes from the ray queue (dynamic fetch).
 // Primitive tests (same operation order as the CPU oracle, oracle/rt3o_prims.hpp):
 //   triangle: watertight (Woop/Benthin/Wald 2013), barycentrics u->v1, v->v2;
 //   sphere  : cuda/sphere.cu:44-96;  curve: round linear segment, entry hits only.
@@ -16,7 +16,7 @@
 namespace rt3 {
 
 enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2 };
-#define RT3_STACK_SIZE 48
+#define RT3_STACK_SIZE 64
 
 struct BlasDev {             // per geometry, device-resident table entry
     const Node8* nodes;
@@ -33,10 +33,12 @@ struct BlasDev {             // per geometry, device-resident table entry
 struct InstanceDev {         // traversal record (64 B)
     float inv_static[12];    // world -> object of the static instance transform
     uint32_t blas;
-    uint32_t nkeys;          // 0 = no motion
+    uint32_t nkeys : 16;     // 0 = no motion
+    uint32_t identity : 16;  // static transform is exactly the identity and there is no motion
     uint32_t key_offset;     // first float of this instance's keys in TravScene::keys
     float t0;                // motion begin; end in t1 (kept in the shading record to stay at 64 B)
 };
+static_assert(sizeof(InstanceDev) == 64, "instance record is 64 bytes");
 
 struct HitGroupDev {         // shading record (reference HitGroupData + motion end time)
     float emission[3];
@@ -60,6 +62,7 @@ struct HitRec { float t, u, v; int prim, inst; };
 
 // object-space ray of an instance at a ray time (shared by traversal and the shade stage)
 RT3_HD void instance_ray(const TravScene& sc, const InstanceDev* in, float t1, float time, float3 wo, float3 wd, float3& oo, float3& od) {
+    if (in->identity) { oo = wo; od = wd; return; }
     Affine si;
 #pragma unroll
     for (int j = 0; j < 12; j++) si.m[j] = in->inv_static[j];
@@ -199,51 +202,103 @@ RT3_HD bool test_curve_linear(float3 o, float3 d, float3 pa, float ra, float3 pb
     return true;
 }
 
+// quantised byte j of a packed word as float: exact, PRMT + FADD on the device instead of shift/and/I2F
+RT3_HD float byte_to_float(uint32_t w, int j) {
+#ifdef RT3_EMULATE
+    return (float)((w >> (8 * j)) & 0xffu);
+#else
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (uint32_t)j)) - 8388608.0f;
+#endif
+}
+
 // ------------------------------------------------------------------------------------ traversal state machine
+#ifndef RT3_PREFETCH
+#define RT3_PREFETCH 0
+#endif
+RT3_HD void prefetch_l1(const void* p) {
+#if !defined(RT3_EMULATE) && RT3_PREFETCH
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
+// Register diet: only what every node / triangle test needs lives in registers (origin, 1/d,
+// shear constants, interval, hit, cursors).  The rest — the current-space direction, the ray
+// time and the saved world-space ray — sits in a "frame" behind the traversal stack in local
+// memory (L1-resident) and is touched only by sphere / curve tests and instance entry / exit.
+enum { FR_D_XY = 0, FR_DZ_TIME, FR_WO_XY, FR_WOZ_WDX, FR_WD_YZ, FR_WIDIR_XY, FR_WIDIRZ_INV, FR_WS_XY, FR_WSZ, FR_COUNT };
+
 template <bool ANY_HIT>
 struct Trav {
-    // current-space ray
-    float3 o, d;
-    float3 idir;
-    float tmin, tbest, time;
-    uint32_t inv;  // bit k set <=> d_k >= 0
-    Shear sh;
-    // world-space ray (restored when an instance is left)
-    float3 wo, wd;
-    // closest hit so far
-    float hu, hv;
+    float3 o;          // current-space origin
+    float3 idir;       // 1 / current-space direction (clamped)
+    float tmin, tbest;
+    uint32_t inv;      // bits 0-2: d_k >= 0 per axis; bits 8-9 kx, 10-11 ky, 12-13 kz (watertight shear axes)
+    float Sx, Sy, Sz;  // watertight shear constants
+    float hu, hv;      // closest hit so far
     int hprim, hinst;
-    // current level
     const Node8* nodes;
     const float4* prims;
     uint32_t ptype;
-    int cur_inst;
-    bool in_blas;
+    int cur_inst;      // -1 while in the TLAS
     uint2 ng, tg;
     int sp;
-    uint2 stack[RT3_STACK_SIZE];
+    uint2 stack[RT3_STACK_SIZE + FR_COUNT];
 
-    RT3_HD void set_space(float3 oo, float3 dd) {
+    RT3_HD void fr_set(int k, float a, float b) { stack[RT3_STACK_SIZE + k] = make_uint2(rt3_f2u(a), rt3_f2u(b)); }
+    RT3_HD float2 fr_get(int k) const { const uint2 v = stack[RT3_STACK_SIZE + k]; return make_float2(rt3_u2f(v.x), rt3_u2f(v.y)); }
+    RT3_HD float3 cur_d() const { const float2 a = fr_get(FR_D_XY), b = fr_get(FR_DZ_TIME); return v3(a.x, a.y, b.x); }
+    RT3_HD float ray_time() const { return fr_get(FR_DZ_TIME).y; }
+
+    RT3_HD void set_space(float3 oo, float3 dd, float time) {
         o = oo;
-        d = dd;
+        fr_set(FR_D_XY, dd.x, dd.y);
+        fr_set(FR_DZ_TIME, dd.z, time);
         const float eps = 8.271806e-25f;  // 2^-80: keeps 1/d finite for axis-parallel rays
         const float dx = fabsf(dd.x) > eps ? dd.x : copysignf(eps, dd.x);
         const float dy = fabsf(dd.y) > eps ? dd.y : copysignf(eps, dd.y);
         const float dz = fabsf(dd.z) > eps ? dd.z : copysignf(eps, dd.z);
         idir = v3(1.0f / dx, 1.0f / dy, 1.0f / dz);
-        inv = (dx >= 0.0f ? 1u : 0u) | (dy >= 0.0f ? 2u : 0u) | (dz >= 0.0f ? 4u : 0u);
-        sh = make_shear(dd);
+        const Shear s = make_shear(dd);
+        Sx = s.Sx; Sy = s.Sy; Sz = s.Sz;
+        inv = (dx >= 0.0f ? 1u : 0u) | (dy >= 0.0f ? 2u : 0u) | (dz >= 0.0f ? 4u : 0u) | ((uint32_t)s.kx << 8) | ((uint32_t)s.ky << 10) |
+              ((uint32_t)s.kz << 12);
+    }
+    RT3_HD Shear shear() const {
+        Shear s;
+        s.kx = (int)((inv >> 8) & 3u); s.ky = (int)((inv >> 10) & 3u); s.kz = (int)((inv >> 12) & 3u);
+        s.Sx = Sx; s.Sy = Sy; s.Sz = Sz;
+        return s;
     }
 
     RT3_HD void init(const TravScene& sc, float3 ro, float3 rd, float rtmin, float rtmax, float rtime) {
-        wo = ro; wd = rd;
-        tmin = rtmin; tbest = rtmax; time = rtime;
+        tmin = rtmin; tbest = rtmax;
         hu = hv = 0.0f; hprim = -1; hinst = -1;
-        nodes = sc.tlas_nodes; prims = nullptr; ptype = 0; cur_inst = -1; in_blas = false;
+        nodes = sc.tlas_nodes; prims = nullptr; ptype = 0; cur_inst = -1;
         ng = make_uint2(0u, 0x80000000u);
         tg = make_uint2(0u, 0u);
         sp = 0;
-        set_space(ro, rd);
+        set_space(ro, rd, rtime);
+        // world-space copy for leaving transformed instances
+        fr_set(FR_WO_XY, ro.x, ro.y);
+        fr_set(FR_WOZ_WDX, ro.z, rd.x);
+        fr_set(FR_WD_YZ, rd.y, rd.z);
+        fr_set(FR_WIDIR_XY, idir.x, idir.y);
+        fr_set(FR_WIDIRZ_INV, idir.z, rt3_u2f(inv));
+        fr_set(FR_WS_XY, Sx, Sy);
+        fr_set(FR_WSZ, Sz, 0.0f);
+    }
+    RT3_HD void restore_world() {
+        const float2 a = fr_get(FR_WO_XY), b = fr_get(FR_WOZ_WDX), c = fr_get(FR_WD_YZ), e = fr_get(FR_WIDIR_XY), f = fr_get(FR_WIDIRZ_INV),
+                     g = fr_get(FR_WS_XY), h = fr_get(FR_WSZ);
+        o = v3(a.x, a.y, b.x);
+        const float time = ray_time();
+        fr_set(FR_D_XY, b.y, c.x);
+        fr_set(FR_DZ_TIME, c.y, time);
+        idir = v3(e.x, e.y, f.x);
+        inv = rt3_f2u(f.y);
+        Sx = g.x; Sy = g.y; Sz = h.x;
     }
 
     RT3_HD void push(const TravScene& sc, uint2 e) {
@@ -268,7 +323,8 @@ struct Trav {
         const int bit = 31 - rt3_clz(hits);
         ng.y &= ~(1u << bit);
         if (ng.y & 0xff000000u) push(sc, ng);
-        const uint32_t slot = ((uint32_t)bit - 24u) ^ inv;
+        const uint32_t oct = inv & 7u;
+        const uint32_t slot = ((uint32_t)bit - 24u) ^ oct;
         const uint32_t rel = (uint32_t)rt3_popc(hits & 0xffu & ((1u << slot) - 1u));
         const uint4* np = reinterpret_cast<const uint4*>(nodes + (ng.x + rel));
         const uint4 n0 = rt3_ldg(np + 0), n1 = rt3_ldg(np + 1), n2 = rt3_ldg(np + 2), n3 = rt3_ldg(np + 3), n4 = rt3_ldg(np + 4);
@@ -294,29 +350,35 @@ struct Trav {
             const uint32_t meta4 = half ? n1.w : n1.z;
             const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
             const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
-            const uint32_t nx = (inv & 1u) ? lox : hix, fx = (inv & 1u) ? hix : lox;
-            const uint32_t ny = (inv & 2u) ? loy : hiy, fy = (inv & 2u) ? hiy : loy;
-            const uint32_t nz = (inv & 4u) ? loz : hiz, fz = (inv & 4u) ? hiz : loz;
+            const uint32_t nx = (oct & 1u) ? lox : hix, fx = (oct & 1u) ? hix : lox;
+            const uint32_t ny = (oct & 2u) ? loy : hiy, fy = (oct & 2u) ? hiy : loy;
+            const uint32_t nz = (oct & 4u) ? loz : hiz, fz = (oct & 4u) ? hiz : loz;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const uint32_t m = (meta4 >> (8 * j)) & 0xffu;
-                const float tnx = fmaf((float)((nx >> (8 * j)) & 0xffu), adjx, nox);
-                const float tny = fmaf((float)((ny >> (8 * j)) & 0xffu), adjy, noy);
-                const float tnz = fmaf((float)((nz >> (8 * j)) & 0xffu), adjz, noz);
-                const float tfx = fmaf((float)((fx >> (8 * j)) & 0xffu), adjx, fox);
-                const float tfy = fmaf((float)((fy >> (8 * j)) & 0xffu), adjy, foy);
-                const float tfz = fmaf((float)((fz >> (8 * j)) & 0xffu), adjz, foz);
+                const float tnx = fmaf(byte_to_float(nx, j), adjx, nox);
+                const float tny = fmaf(byte_to_float(ny, j), adjy, noy);
+                const float tnz = fmaf(byte_to_float(nz, j), adjz, noz);
+                const float tfx = fmaf(byte_to_float(fx, j), adjx, fox);
+                const float tfy = fmaf(byte_to_float(fy, j), adjy, foy);
+                const float tfz = fmaf(byte_to_float(fz, j), adjz, foz);
                 const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
                 const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
                 if (m != 0u && tn <= tf) {
                     const bool internal = (m & 0x18u) == 0x18u;
-                    const uint32_t idx = (m & 31u) ^ (internal ? inv : 0u);
+                    const uint32_t idx = (m & 31u) ^ (internal ? oct : 0u);
                     hitmask |= (m >> 5) << idx;
                 }
             }
         }
         ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
         tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+        // warm L1 for what this lane touches next: its first pending primitive and its nearest child
+        if (tg.y != 0u && cur_inst >= 0) prefetch_l1(prims + 3u * (tg.x + (uint32_t)(31 - rt3_clz(tg.y & (0u - tg.y)))));
+        if (ng.y & 0xff000000u) {
+            const uint32_t nslot = ((uint32_t)(31 - rt3_clz(ng.y)) - 24u) ^ oct;
+            prefetch_l1(nodes + (ng.x + (uint32_t)rt3_popc(ng.y & 0xffu & ((1u << nslot) - 1u))));
+        }
     }
 
     // returns true when an any-hit ray is finished
@@ -324,18 +386,24 @@ struct Trav {
         const int bit = 31 - rt3_clz(tg.y & (0u - tg.y));  // lowest set bit
         tg.y &= tg.y - 1u;
         const uint32_t pi = tg.x + (uint32_t)bit;
-        if (!in_blas) {  // TLAS leaf: enter the instance
+        if (cur_inst < 0) {  // TLAS leaf: enter the instance
             const int inst = (int)rt3_ldg(sc.tlas_order + pi);
             if (ng.y & 0xff000000u) push(sc, ng);
             if (tg.y) push(sc, tg);
-            push(sc, make_uint2(0xffffffffu, 0u));  // sentinel: leave instance
             const InstanceDev* in = sc.instances + inst;
-            float3 oo, od;
-            instance_ray(sc, in, sc.hitgroups[inst].t1, time, wo, wd, oo, od);
-            set_space(oo, od);
+            if (in->identity) {  // exact identity, no motion: the object-space ray IS the world-space ray
+                push(sc, make_uint2(0xfffffffeu, 0u));
+            } else {
+                push(sc, make_uint2(0xffffffffu, 0u));  // sentinel: restore the world-space ray on the way out
+                const float2 a = fr_get(FR_WO_XY), b = fr_get(FR_WOZ_WDX), c = fr_get(FR_WD_YZ);
+                const float time = ray_time();
+                float3 oo, od;
+                instance_ray(sc, in, sc.hitgroups[inst].t1, time, v3(a.x, a.y, b.x), v3(b.y, c.x, c.y), oo, od);
+                set_space(oo, od, time);
+            }
             const BlasDev* bl = sc.blas + in->blas;
             nodes = bl->nodes; prims = bl->prims; ptype = bl->type;
-            cur_inst = inst; in_blas = true;
+            cur_inst = inst;
             ng = make_uint2(0u, 0x80000000u);
             tg = make_uint2(0u, 0u);
             return false;
@@ -346,10 +414,10 @@ struct Trav {
         if (ptype == PRIM_TRI) {
             const float4 c = rt3_ldg(pr + 2);
             float t, u, v;
-            if (test_triangle(o, sh, v3(a), v3(b), v3(c), t, u, v)) got = accept(t, u, v, (int)rt3_f2u(a.w));
+            if (test_triangle(o, shear(), v3(a), v3(b), v3(c), t, u, v)) got = accept(t, u, v, (int)rt3_f2u(a.w));
         } else if (ptype == PRIM_SPHERE) {
             float ta, tb;
-            if (test_sphere(o, d, v3(a), a.w, ta, tb)) {
+            if (test_sphere(o, cur_d(), v3(a), a.w, ta, tb)) {
                 const int prim = (int)rt3_f2u(b.x);
                 // first root if it lies in the interval, else the second (cuda/sphere.cu:76-94)
                 if (in_range(ta)) got = accept(ta, 0.0f, 0.0f, prim);
@@ -358,32 +426,31 @@ struct Trav {
         } else {
             const float4 c = rt3_ldg(pr + 2);
             float t, u;
-            if (test_curve_linear(o, d, v3(a), a.w, v3(b), b.w, t, u)) got = accept(t, u, 0.0f, (int)rt3_f2u(c.x));
+            if (test_curve_linear(o, cur_d(), v3(a), a.w, v3(b), b.w, t, u)) got = accept(t, u, 0.0f, (int)rt3_f2u(c.x));
         }
         return ANY_HIT && got;
     }
 
-    // one unit of work; returns false when the ray is finished
+    // One round of the while-while loop; returns false when the ray is finished.  Every lane of a
+    // warp runs the three phases in lock step (pop -> one wide node -> all pending primitives), so
+    // lanes that are in the same phase execute it together instead of serialising per action.
     RT3_HD bool step(const TravScene& sc) {
-        if (tg.y != 0u) {
+        while (tg.y == 0u && !(ng.y & 0xff000000u)) {
+            if (sp == 0) return false;
+            const uint2 e = stack[--sp];
+            if (e.y == 0u) {  // sentinel: leave the instance
+                if (e.x == 0xffffffffu) restore_world();  // the instance had its own ray space
+                nodes = sc.tlas_nodes;
+                cur_inst = -1;
+            } else if (e.y & 0xff000000u) {
+                ng = e;
+            } else {
+                tg = e;
+            }
+        }
+        if (tg.y == 0u) node_step(sc);
+        while (tg.y != 0u) {
             if (prim_step(sc)) return false;
-            return true;
-        }
-        if (ng.y & 0xff000000u) {
-            node_step(sc);
-            return true;
-        }
-        if (sp == 0) return false;
-        const uint2 e = stack[--sp];
-        if (e.x == 0xffffffffu && e.y == 0u) {  // leave instance
-            set_space(wo, wd);
-            nodes = sc.tlas_nodes;
-            in_blas = false;
-            cur_inst = -1;
-        } else if (e.y & 0xff000000u) {
-            ng = e;
-        } else {
-            tg = e;
         }
         return true;
     }
