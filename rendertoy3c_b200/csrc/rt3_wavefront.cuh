@@ -98,7 +98,7 @@ static void k_traverse(TraverseArgs a) {
 #define RT3_TRAV_MIN_BLOCKS 10
 #endif
 #ifndef RT3_REFILL_THRESHOLD
-#define RT3_REFILL_THRESHOLD 20
+#define RT3_REFILL_THRESHOLD 26
 #endif
 // Persistent threads with dynamic fetch: a warp keeps traversing until fewer than
 // RT3_REFILL_THRESHOLD lanes are busy, then refills the idle lanes from the queue with a single

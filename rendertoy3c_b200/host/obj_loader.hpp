@@ -1,0 +1,156 @@
+// obj_loader.hpp — minimal Wavefront .obj/.mtl ingest producing the same Mesh list, primitive order
+// and vertex order as the reference's loadOBJ (src/mesh.cpp:37-210), written from scratch (the
+// reference vendors tinyobj + stb_image; neither is used here).
+//   * one Mesh per (shape x ascending material id), shapes split at every `o` / `g` statement;
+//   * faces in file order; vertices de-duplicated per mesh on the (v, vn, vt) triple, numbered by
+//     first use (mesh.cpp:78-110);
+//   * quads split along the shorter diagonal (tinyobj rule), larger polygons as a fan;
+//   * material fields Kd, Ke, map_Kd; textures: binary PPM (P6) only, RGBA8, rows flipped so that
+//     v = 0 is the image bottom (mesh.cpp:151-159), de-duplicated by file name;
+//   * normals and texcoords are required (the reference reads them unconditionally, Q11).
+#pragma once
+#include <cstdio>
+#include <fstream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <tuple>
+
+#include "rt3_host.hpp"
+
+namespace rt3host {
+
+namespace detail {
+struct ObjIndex { int v, vt, vn; bool operator<(const ObjIndex& o) const { return std::tie(v, vn, vt) < std::tie(o.v, o.vn, o.vt); } };
+struct ObjShape { std::vector<ObjIndex> idx; std::vector<int> mat; };  // 3 indices per triangle
+struct ObjMaterial { std::string name; float3_ Kd{0.8f, 0.8f, 0.8f}, Ke{0, 0, 0}; std::string map_Kd; };
+
+inline int fix_index(int i, int n) { return i > 0 ? i - 1 : n + i; }
+
+inline bool load_ppm(const std::string& path, Texture& t) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    std::string magic;
+    f >> magic;
+    if (magic != "P6") return false;
+    auto next_int = [&]() { int v; while (f >> std::ws && f.peek() == '#') { std::string l; std::getline(f, l); } f >> v; return v; };
+    const int w = next_int(), h = next_int(), maxv = next_int();
+    f.get();
+    if (w <= 0 || h <= 0 || maxv != 255) return false;
+    std::vector<uint8_t> rgb((size_t)3 * w * h);
+    f.read(reinterpret_cast<char*>(rgb.data()), (std::streamsize)rgb.size());
+    if (!f) return false;
+    t.width = w; t.height = h;
+    t.pixel.resize((size_t)4 * w * h);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const uint8_t* s = &rgb[3 * ((size_t)(h - 1 - y) * w + x)];  // vertical flip
+            uint8_t* d = &t.pixel[4 * ((size_t)y * w + x)];
+            d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = 255;
+        }
+    return true;
+}
+}  // namespace detail
+
+inline void loadOBJ(const std::string& path, std::vector<Mesh>& meshes, std::vector<Texture>& textures) {
+    using namespace detail;
+    std::ifstream in(path);
+    if (!in) throw Exception("loadOBJ: cannot open " + path);
+    const std::string dir = path.substr(0, path.rfind('/') + 1);
+    std::vector<float> V, VN, VT;
+    std::vector<ObjShape> shapes(1);
+    std::vector<ObjMaterial> mats;
+    std::map<std::string, int> mat_id;
+    int cur_mat = -1;
+    std::string line;
+    auto load_mtl = [&](const std::string& file) {
+        std::ifstream m(dir + file);
+        std::string l;
+        while (std::getline(m, l)) {
+            std::istringstream ss(l);
+            std::string k;
+            ss >> k;
+            if (k == "newmtl") { ObjMaterial mm; ss >> mm.name; mat_id[mm.name] = (int)mats.size(); mats.push_back(mm); }
+            else if (mats.empty()) continue;
+            else if (k == "Kd") ss >> mats.back().Kd.x >> mats.back().Kd.y >> mats.back().Kd.z;
+            else if (k == "Ke") ss >> mats.back().Ke.x >> mats.back().Ke.y >> mats.back().Ke.z;
+            else if (k == "map_Kd") ss >> mats.back().map_Kd;
+        }
+    };
+    while (std::getline(in, line)) {
+        std::istringstream ss(line);
+        std::string k;
+        ss >> k;
+        if (k == "v") { float x, y, z; ss >> x >> y >> z; V.insert(V.end(), {x, y, z}); }
+        else if (k == "vn") { float x, y, z; ss >> x >> y >> z; VN.insert(VN.end(), {x, y, z}); }
+        else if (k == "vt") { float x, y = 0; ss >> x >> y; VT.insert(VT.end(), {x, y}); }
+        else if (k == "o" || k == "g") { if (!shapes.back().idx.empty()) shapes.emplace_back(); }
+        else if (k == "mtllib") { std::string f; ss >> f; load_mtl(f); }
+        else if (k == "usemtl") { std::string n; ss >> n; auto it = mat_id.find(n); cur_mat = it == mat_id.end() ? -1 : it->second; }
+        else if (k == "f") {
+            std::vector<ObjIndex> poly;
+            std::string tok;
+            while (ss >> tok) {
+                ObjIndex ix{0, -1, -1};
+                int a = 0, b = 0, c = 0;
+                if (std::sscanf(tok.c_str(), "%d/%d/%d", &a, &b, &c) == 3) { ix.v = fix_index(a, (int)V.size() / 3); ix.vt = fix_index(b, (int)VT.size() / 2); ix.vn = fix_index(c, (int)VN.size() / 3); }
+                else if (std::sscanf(tok.c_str(), "%d//%d", &a, &c) == 2) { ix.v = fix_index(a, (int)V.size() / 3); ix.vn = fix_index(c, (int)VN.size() / 3); }
+                else if (std::sscanf(tok.c_str(), "%d/%d", &a, &b) == 2) { ix.v = fix_index(a, (int)V.size() / 3); ix.vt = fix_index(b, (int)VT.size() / 2); }
+                else if (std::sscanf(tok.c_str(), "%d", &a) == 1) { ix.v = fix_index(a, (int)V.size() / 3); }
+                poly.push_back(ix);
+            }
+            auto emit = [&](int a, int b, int c) { shapes.back().idx.insert(shapes.back().idx.end(), {poly[(size_t)a], poly[(size_t)b], poly[(size_t)c]}); shapes.back().mat.push_back(cur_mat); };
+            if (poly.size() == 3) emit(0, 1, 2);
+            else if (poly.size() == 4) {
+                auto d2 = [&](int a, int b) { float s = 0; for (int q = 0; q < 3; ++q) { const float e = V[3 * (size_t)poly[(size_t)a].v + q] - V[3 * (size_t)poly[(size_t)b].v + q]; s += e * e; } return s; };
+                if (d2(0, 2) < d2(1, 3)) { emit(0, 1, 2); emit(0, 2, 3); } else { emit(0, 1, 3); emit(1, 2, 3); }
+            } else for (size_t q = 1; q + 1 < poly.size(); ++q) emit(0, (int)q, (int)q + 1);
+        }
+    }
+    std::map<std::string, int> known_tex;
+    for (const ObjShape& sh : shapes) {
+        std::set<int> ids(sh.mat.begin(), sh.mat.end());
+        for (int mid : ids) {
+            if (mid < 0) throw Exception("loadOBJ: face without material (the reference dereferences materials[-1], Q11)");
+            Mesh mesh;
+            mesh.vertices.resize(1); mesh.normals.resize(1); mesh.texcoords.resize(1);
+            std::map<ObjIndex, int> known;
+            for (size_t f = 0; f < sh.mat.size(); ++f) {
+                if (sh.mat[f] != mid) continue;
+                for (int c = 0; c < 3; ++c) {
+                    const ObjIndex ix = sh.idx[3 * f + (size_t)c];
+                    if (ix.vn < 0 || ix.vt < 0) throw Exception("loadOBJ: vertex without normal or texcoord (required, Q11)");
+                    auto it = known.find(ix);
+                    int id;
+                    if (it != known.end()) id = it->second;
+                    else {
+                        id = (int)mesh.vertices[0].size() / 3;
+                        known[ix] = id;
+                        for (int q = 0; q < 3; ++q) mesh.vertices[0].push_back(V[3 * (size_t)ix.v + q]);
+                        for (int q = 0; q < 3; ++q) mesh.normals[0].push_back(VN[3 * (size_t)ix.vn + q]);
+                        for (int q = 0; q < 2; ++q) mesh.texcoords[0].push_back(VT[2 * (size_t)ix.vt + q]);
+                    }
+                    mesh.indices.push_back(id);
+                }
+            }
+            const ObjMaterial& m = mats[(size_t)mid];
+            mesh.material.m_diffuse = m.Kd;
+            mesh.material.m_emissive = m.Ke;
+            if (!m.map_Kd.empty()) {
+                auto it = known_tex.find(m.map_Kd);
+                if (it != known_tex.end()) mesh.material.m_diffuseTextureID = it->second;
+                else {
+                    Texture t;
+                    std::string fn = m.map_Kd;
+                    for (char& ch : fn) if (ch == '\\') ch = '/';
+                    if (load_ppm(dir + fn, t)) { mesh.material.m_diffuseTextureID = (int)textures.size(); textures.push_back(std::move(t)); }
+                    else std::fprintf(stderr, "Error loading texture %s (only binary PPM is supported).\n", fn.c_str());
+                    known_tex[m.map_Kd] = mesh.material.m_diffuseTextureID;
+                }
+            }
+            if (!mesh.vertices[0].empty()) meshes.push_back(std::move(mesh));
+        }
+    }
+}
+
+}  // namespace rt3host

@@ -1,0 +1,86 @@
+// wavefront.cpp — headless host driver with the shape of the reference's src/wavefront.cpp:
+// loadOBJ -> Context -> CUDAScene (meshes, textures, instances, hit groups, light sampler) ->
+// RenderSettings + camera -> render loop of launchSubframe -> image to disk (the reference
+// displays through GL instead; saveImage in sutil/sutil.cpp:542-700 flips rows the same way).
+//
+//   wavefront --scene scene.obj [--width 768 --height 768 --spp 64 --spl 8 --max-depth 0]
+//             [--eye x y z --lookat x y z --up x y z --fovy 45] [--gpus N] [--out out.ppm]
+// Multi-GPU: scene replicated, GPU g renders subframes g, g+N, ...; one NCCL sum of the float4
+// accumulation buffers (rt3_allreduce_accum).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+
+#include "obj_loader.hpp"
+
+using namespace rt3host;
+
+int main(int argc, char** argv) {
+    std::string scene, out = "out.ppm";
+    int width = 768, height = 768, spp = 64, spl = 8, max_depth = 0, gpus = 1;  // reference defaults (wavefront.cpp:55,300)
+    float eye[3] = {5, 5, 5}, lookat[3] = {0, 1, 0}, up[3] = {0, 1, 0}, fovy = 45.0f;  // initCameraState, wavefront.cpp:238-243
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto f3 = [&](float* v) { for (int k = 0; k < 3; ++k) v[k] = (float)std::atof(argv[++i]); };
+        if (a == "--scene") scene = argv[++i];
+        else if (a == "--out") out = argv[++i];
+        else if (a == "--width") width = std::atoi(argv[++i]);
+        else if (a == "--height") height = std::atoi(argv[++i]);
+        else if (a == "--spp") spp = std::atoi(argv[++i]);
+        else if (a == "--spl") spl = std::atoi(argv[++i]);
+        else if (a == "--max-depth") max_depth = std::atoi(argv[++i]);
+        else if (a == "--gpus") gpus = std::atoi(argv[++i]);
+        else if (a == "--fovy") fovy = (float)std::atof(argv[++i]);
+        else if (a == "--eye") f3(eye);
+        else if (a == "--lookat") f3(lookat);
+        else if (a == "--up") f3(up);
+        else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
+    }
+    if (scene.empty()) { std::fprintf(stderr, "usage: wavefront --scene file.obj [options]\n"); return 2; }
+    try {
+        std::vector<Mesh> meshes;
+        std::vector<Texture> textures;
+        loadOBJ(scene, meshes, textures);
+        std::vector<std::unique_ptr<Context>> ctx;
+        std::vector<std::unique_ptr<CUDAScene>> scenes;
+        for (int g = 0; g < gpus; ++g) {
+            ctx.emplace_back(new Context(g));
+            scenes.emplace_back(new CUDAScene(*ctx.back(), meshes, textures));
+        }
+        RenderSettings params(width, height, (unsigned)spl);
+        params.max_depth = max_depth;
+        params.accum_mode = gpus > 1 ? 1 : 0;
+        for (int k = 0; k < 3; ++k) params.eye[k] = eye[k];
+        RT3HOST_CHECK(rt3_camera_uvw(eye, lookat, up, fovy, (float)width / (float)height, params.U, params.V, params.W));  // handleCameraUpdate
+        const int subframes = (spp + spl - 1) / spl;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int sf = 0; sf < subframes; ++sf) {
+            params.subframe_index = (uint32_t)sf;
+            RT3HOST_CHECK(rt3_launch_subframe(ctx[(size_t)(sf % gpus)]->ctx(), &params));  // asynchronous: GPUs run concurrently
+        }
+        for (auto& c : ctx) RT3HOST_CHECK(rt3_sync(c->ctx()));
+        if (gpus > 1) {
+            std::vector<rt3_context_t> raw;
+            for (auto& c : ctx) raw.push_back(c->ctx());
+            RT3HOST_CHECK(rt3_allreduce_accum(raw.data(), gpus, (uint32_t)subframes));
+        }
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        unsigned long long rays = 0, samples = 0;
+        for (auto& c : ctx) { rt3_stats st; RT3HOST_CHECK(rt3_get_stats(c->ctx(), &st)); rays += st.rays_primary + st.rays_bounce + st.rays_shadow; samples += st.samples; }
+        std::vector<uint8_t> frame((size_t)4 * width * height);
+        RT3HOST_CHECK(rt3_download_frame(ctx[0]->ctx(), frame.data()));
+        FILE* f = std::fopen(out.c_str(), "wb");
+        if (!f) throw Exception("cannot write " + out);
+        std::fprintf(f, "P6\n%d %d\n255\n", width, height);
+        for (int y = height - 1; y >= 0; --y)  // row 0 is the image bottom (Q19)
+            for (int x = 0; x < width; ++x) std::fwrite(&frame[4 * ((size_t)y * width + x)], 1, 3, f);
+        std::fclose(f);
+        std::printf("{\"meshes\": %zu, \"gpus\": %d, \"subframes\": %d, \"seconds\": %.4f, \"Mrays_s\": %.1f, \"Msamples_s\": %.1f, \"out\": \"%s\"}\n", meshes.size(), gpus,
+                    subframes, secs, rays / secs / 1e6, samples / secs / 1e6, out.c_str());
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "wavefront: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -346,3 +346,35 @@ def motion(n_inst=64, blob_n=224, n_spheres=256, n_curves=10000, width=1920, hei
 
 def by_name(name, **kw):
     return {"cornell": cornell, "terrain": terrain, "instanced": instanced, "motion": motion}[name](**kw)
+
+
+def write_obj(desc, path):
+    """Export the mesh instances of a SceneDesc (identity transforms only) as .obj + .mtl (+ binary PPM
+    textures), one `o` shape and one material per instance, for the C++ host (host/wavefront.cpp) and the
+    loader round-trip tests.  Rows of textures are written top-down (the loader flips them back)."""
+    import os
+    base = os.path.splitext(path)[0]
+    with open(path, "w") as f, open(base + ".mtl", "w") as m:
+        f.write("mtllib %s.mtl\n" % os.path.basename(base))
+        vo = 1
+        for i, inst in enumerate(desc.instances):
+            g = desc.geoms[inst.geom]
+            assert g.kind == "mesh" and inst.keys is None and np.array_equal(inst.xform, IDENTITY)
+            m.write("newmtl m%d\nKd %.9g %.9g %.9g\nKe %.9g %.9g %.9g\n" % ((i,) + tuple(np.float32(x) for x in inst.diffuse) + tuple(np.float32(x) for x in inst.emission)))
+            if inst.tex >= 0:
+                tname = "%s_tex%d.ppm" % (os.path.basename(base), inst.tex)
+                m.write("map_Kd %s\n" % tname)
+                rgba = desc.textures[inst.tex].rgba
+                with open(os.path.join(os.path.dirname(path), tname), "wb") as t:
+                    t.write(b"P6\n%d %d\n255\n" % (rgba.shape[1], rgba.shape[0]))
+                    t.write(np.ascontiguousarray(rgba[::-1, :, :3]).tobytes())
+            f.write("o shape%d\nusemtl m%d\n" % (i, i))
+            for v in g.verts:
+                f.write("v %.9g %.9g %.9g\n" % tuple(v))
+            for n in g.normals:
+                f.write("vn %.9g %.9g %.9g\n" % tuple(n))
+            for t in g.uvs:
+                f.write("vt %.9g %.9g\n" % tuple(t))
+            for tri in g.idx:
+                f.write("f %d/%d/%d %d/%d/%d %d/%d/%d\n" % tuple(int(x) + vo for x in np.repeat(tri, 3)))
+            vo += len(g.verts)
