@@ -25,7 +25,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librt3.so")
 
 RT3_SYMBOLS = [
-    "rt3_context_create", "rt3_context_destroy", "rt3_sync", "rt3_last_error", "rt3_get_stream", "rt3_get_stats", "rt3_reset_stats",
+    "rt3_context_create", "rt3_context_destroy", "rt3_sync", "rt3_last_error", "rt3_get_stream", "rt3_get_stats", "rt3_reset_stats", "rt3_get_debug_counters",
     "rt3_set_option", "rt3_mesh_create", "rt3_spheres_create", "rt3_curves_create", "rt3_texture_create",
     "rt3_accel_append_instance", "rt3_accel_append_animated_instance", "rt3_accel_build", "rt3_scene_set_hitgroup",
     "rt3_scene_set_lights", "rt3_light_make", "rt3_camera_uvw", "rt3_launch_subframe", "rt3_trace", "rt3_trace_device",
@@ -233,6 +233,11 @@ class Context:
 
     def reset_stats(self):
         self._chk(self.L.rt3_reset_stats(self.ctx))
+
+    def debug_counters(self):
+        out = (C.c_uint32 * 8)()
+        self._chk(self.L.rt3_get_debug_counters(self.ctx, out))
+        return list(out)
 
     def set_option(self, key, value):
         self._chk(self.L.rt3_set_option(self.ctx, key.encode(), C.c_int(int(value))))

@@ -27,7 +27,34 @@
 
 namespace rt3 {
 
-// ------------------------------------------------------------------------------------ node layout (80 B = 5 x 16 B)
+// ------------------------------------------------------------------------------------ node layout
+// RT3_NODE_FP16 = 1 (default): 128-byte, cache-line-aligned node; child boxes are 11-bit integers
+//   (0..2047, in units of the per-axis power-of-two scale) stored as fp16, so the decode is ONE
+//   full-rate HADD2.F32 per plane on the FMA pipe (the 8-bit layout needs PRMT + FADD, and the ALU
+//   pipe is the busier one in the slab test), the grid is 8x finer, and a node never straddles lines.
+// RT3_NODE_FP16 = 0: the 80-byte layout of Ylitie/Karras/Laine 2017 (8-bit boxes).
+#ifndef RT3_NODE_FP16
+#define RT3_NODE_FP16 0
+#endif
+#if RT3_NODE_FP16
+#define RT3_QMAX 2047
+struct alignas(128) Node8 {
+    float px, py, pz;        // quantisation origin = node box lo
+    uint8_t ex, ey, ez;      // biased exponents: scale_k = 2^(e_k - 127)
+    uint8_t imask;           // bit s set: slot s holds an internal child
+    uint32_t child_base;     // index of the first internal child (children stored contiguously in slot order)
+    uint32_t prim_base;      // index of the first primitive of this node's leaf children
+    uint8_t meta[8];         // 0 = empty | internal: 001sssss (sssss = 24+slot) | leaf: (unary count)<<5 | offset
+    uint16_t q[2][3][2][4];  // [half: slots 0-3 / 4-7][axis][lo,hi][slot in half] fp16 bit patterns
+};
+static_assert(sizeof(Node8) == 128, "wide node must be one 128-byte line");
+RT3_HD uint16_t int_to_half_bits(int n) {  // exact for 0 <= n < 2048
+    if (n <= 0) return 0;
+    const int e = 31 - rt3_clz((uint32_t)n);
+    return (uint16_t)(((uint32_t)(e + 15) << 10) | (((uint32_t)n << (10 - e)) & 0x3ffu));
+}
+#else
+#define RT3_QMAX 255
 struct alignas(16) Node8 {
     float px, py, pz;        // quantisation origin = node box lo
     uint8_t ex, ey, ez;      // biased exponents: scale_k = 2^(e_k - 127)
@@ -39,6 +66,7 @@ struct alignas(16) Node8 {
     uint8_t qhi[3][8];
 };
 static_assert(sizeof(Node8) == 80, "compressed wide node must be 80 bytes");
+#endif
 
 struct Bvh8 {            // one acceleration structure (BLAS or TLAS) in device memory
     Node8* nodes = nullptr;
@@ -193,17 +221,17 @@ RT3_HD float bvh2_area(const BuildArrays& b, int id) {
     return ex * ey + ey * ez + ez * ex;
 }
 
-// smallest biased exponent E with p + 255 * 2^(E-127) >= hi (checked in double)
+// smallest biased exponent E with p + RT3_QMAX * 2^(E-127) >= hi (checked in double)
 RT3_HD uint32_t quant_exponent(float p, float hi) {
     const float ext = hi - p;
     uint32_t E = 1;
     if (ext > 0.0f) {
-        const uint32_t bits = rt3_f2u(ext / 255.0f);
+        const uint32_t bits = rt3_f2u(ext / (float)RT3_QMAX);
         E = (bits >> 23) & 0xffu;
         if (bits & 0x7fffffu) E += 1;
         if (E < 1) E = 1;
     }
-    while (E < 254 && (double)p + 255.0 * (double)rt3_u2f(E << 23) < (double)hi) E++;
+    while (E < 254 && (double)p + (double)RT3_QMAX * (double)rt3_u2f(E << 23) < (double)hi) E++;
     return E;
 }
 
@@ -289,7 +317,14 @@ RT3_GLOBAL(k_bvh_collapse, BuildArrays b) {
         const int c = slot_child[s];
         if (c < 0) {
             nd.meta[s] = 0;
-            for (int k = 0; k < 3; k++) { nd.qlo[k][s] = 255; nd.qhi[k][s] = 0; }  // inverted box: never hit
+            for (int k = 0; k < 3; k++) {  // inverted box; the empty meta byte is what makes it unhittable
+#if RT3_NODE_FP16
+                nd.q[s >> 2][k][0][s & 3] = int_to_half_bits(RT3_QMAX);
+                nd.q[s >> 2][k][1][s & 3] = 0;
+#else
+                nd.qlo[k][s] = 255; nd.qhi[k][s] = 0;
+#endif
+            }
             continue;
         }
         const int id = ch[c];
@@ -311,13 +346,18 @@ RT3_GLOBAL(k_bvh_collapse, BuildArrays b) {
         for (int k = 0; k < 3; k++) {
             const float scale = rt3_u2f(E[k] << 23);
             int ql = (int)floorf((clo[k] - p[k]) / scale);
-            ql = ql < 0 ? 0 : (ql > 255 ? 255 : ql);
+            ql = ql < 0 ? 0 : (ql > RT3_QMAX ? RT3_QMAX : ql);
             while (ql > 0 && (double)p[k] + (double)ql * (double)scale > (double)clo[k]) ql--;
             int qh = (int)ceilf((chi[k] - p[k]) / scale);
-            qh = qh < 0 ? 0 : (qh > 255 ? 255 : qh);
-            while (qh < 255 && (double)p[k] + (double)qh * (double)scale < (double)chi[k]) qh++;
+            qh = qh < 0 ? 0 : (qh > RT3_QMAX ? RT3_QMAX : qh);
+            while (qh < RT3_QMAX && (double)p[k] + (double)qh * (double)scale < (double)chi[k]) qh++;
+#if RT3_NODE_FP16
+            nd.q[s >> 2][k][0][s & 3] = int_to_half_bits(ql);
+            nd.q[s >> 2][k][1][s & 3] = int_to_half_bits(qh);
+#else
             nd.qlo[k][s] = (uint8_t)ql;
             nd.qhi[k][s] = (uint8_t)qh;
+#endif
         }
     }
     b.nodes[widx] = nd;

@@ -209,7 +209,7 @@ int rt3_context_create(int device, rt3_context_t* out) {
     c->num_sms = prop.multiProcessorCount;
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 #endif
-    c->d_flags.alloc(2);
+    c->d_flags.alloc(8);  // [0] error flags, [1] max stack, [2..5] diagnostic counters (RT3_STATS builds)
     c->counters.alloc(4 * MAX_DEPTH_SLOTS);
     c->d_stats.alloc(4);
     c->trace_fetch.alloc(1);
@@ -664,6 +664,14 @@ int rt3_get_stats(rt3_context_t c, rt3_stats* st) {
     st->kernel_launches = g_launch_count;
     st->ms_generate = c->ms[0]; st->ms_extend = c->ms[1]; st->ms_shade = c->ms[2]; st->ms_connect = c->ms[3]; st->ms_resolve = c->ms[4]; st->ms_total = c->ms[5];
     st->error_flags = fl[0]; st->max_stack_depth = fl[1];
+    RT3_API_END
+}
+int rt3_get_debug_counters(rt3_context_t c, uint32_t out[8]) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && out, RT3_ERR_INVALID, "get_debug_counters: null argument");
+    d2h(out, c->d_flags.p, 8 * sizeof(uint32_t), c->stream);
+    stream_sync(c->stream);
+    dev_memset(c->d_flags.p + 2, 0, 6 * sizeof(uint32_t), c->stream);
     RT3_API_END
 }
 int rt3_reset_stats(rt3_context_t c) {

@@ -41,7 +41,13 @@ inline void count_launch() { ++g_launch_count; }
 typedef int Stream;
 struct Event { double t = 0; };
 #define RT3_CUDA(call) (void)0
-inline void* dev_alloc(size_t bytes) { void* p = calloc(bytes ? bytes : 1, 1); if (!p) throw Error(-2, "emul: out of memory"); return p; }
+inline void* dev_alloc(size_t bytes) {  // 256-byte aligned like cudaMalloc
+    const size_t n = ((bytes ? bytes : 1) + 255) & ~(size_t)255;
+    void* p = aligned_alloc(256, n);
+    if (!p) throw Error(-2, "emul: out of memory");
+    memset(p, 0, n);
+    return p;
+}
 inline void dev_free(void* p) { free(p); }
 inline void h2d(void* d, const void* h, size_t n, Stream) { memcpy(d, h, n); }
 inline void d2h(void* h, const void* d, size_t n, Stream) { memcpy(h, d, n); }

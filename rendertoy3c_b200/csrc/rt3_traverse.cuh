@@ -12,11 +12,20 @@
 // not depend on traversal order; box culling is padded so it never removes such a candidate.
 #pragma once
 #include "rt3_bvh.cuh"
+#ifndef RT3_EMULATE
+#include <cuda_fp16.h>
+#endif
 
 namespace rt3 {
 
 enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2 };
 #define RT3_STACK_SIZE 64
+#ifndef RT3_COOP_CAP
+#define RT3_COOP_CAP 32   // (owner, triangle) pairs a warp shares per round
+#endif
+#ifndef RT3_COOP
+#define RT3_COOP 1        // 1: warp-cooperative triangle phase (step_warp), 0: per-lane loop (step)
+#endif
 
 struct BlasDev {             // per geometry, device-resident table entry
     const Node8* nodes;
@@ -211,6 +220,22 @@ RT3_HD float byte_to_float(uint32_t w, int j) {
 #endif
 }
 
+// two fp16 values packed in a word -> float2 (x = low half); exact.  Device: 2 x HADD2.F32
+RT3_HD float2 half2_to_float2(uint32_t w) {
+#ifdef RT3_EMULATE
+    float r[2];
+    for (int i = 0; i < 2; i++) {
+        const uint32_t h = (w >> (16 * i)) & 0xffffu;
+        const uint32_t e = (h >> 10) & 31u, m = h & 0x3ffu;
+        r[i] = e == 0 ? ldexpf((float)m, -24) : ldexpf((float)(m | 0x400u), (int)e - 25);
+        if (h & 0x8000u) r[i] = -r[i];
+    }
+    return make_float2(r[0], r[1]);
+#else
+    return __half22float2(*reinterpret_cast<const __half2*>(&w));
+#endif
+}
+
 // ------------------------------------------------------------------------------------ traversal state machine
 #ifndef RT3_PREFETCH
 #define RT3_PREFETCH 0
@@ -244,6 +269,10 @@ struct Trav {
     int cur_inst;      // -1 while in the TLAS
     uint2 ng, tg;
     int sp;
+#ifdef RT3_STATS
+    uint32_t c_nodes, c_prims, c_rounds;  // diagnostic build only (tools/build_variant.sh -DRT3_STATS)
+    uint32_t* dbg;
+#endif
     uint2 stack[RT3_STACK_SIZE + FR_COUNT];
 
     RT3_HD void fr_set(int k, float a, float b) { stack[RT3_STACK_SIZE + k] = make_uint2(rt3_f2u(a), rt3_f2u(b)); }
@@ -279,6 +308,12 @@ struct Trav {
         ng = make_uint2(0u, 0x80000000u);
         tg = make_uint2(0u, 0u);
         sp = 0;
+#ifdef RT3_STATS
+        dbg = sc.error_flags;
+#endif
+#ifdef RT3_STATS
+        c_nodes = c_prims = c_rounds = 0;
+#endif
         set_space(ro, rd, rtime);
         // world-space copy for leaving transformed instances
         fr_set(FR_WO_XY, ro.x, ro.y);
@@ -319,6 +354,9 @@ struct Trav {
     }
 
     RT3_HD void node_step(const TravScene& sc) {
+#ifdef RT3_STATS
+        c_nodes++;
+#endif
         const uint32_t hits = ng.y;
         const int bit = 31 - rt3_clz(hits);
         ng.y &= ~(1u << bit);
@@ -327,7 +365,7 @@ struct Trav {
         const uint32_t slot = ((uint32_t)bit - 24u) ^ oct;
         const uint32_t rel = (uint32_t)rt3_popc(hits & 0xffu & ((1u << slot) - 1u));
         const uint4* np = reinterpret_cast<const uint4*>(nodes + (ng.x + rel));
-        const uint4 n0 = rt3_ldg(np + 0), n1 = rt3_ldg(np + 1), n2 = rt3_ldg(np + 2), n3 = rt3_ldg(np + 3), n4 = rt3_ldg(np + 4);
+        const uint4 n0 = rt3_ldg(np + 0), n1 = rt3_ldg(np + 1);
 
         const float adjx = rt3_u2f((n0.w & 0xffu) << 23) * idir.x;
         const float adjy = rt3_u2f(((n0.w >> 8) & 0xffu) << 23) * idir.y;
@@ -337,17 +375,51 @@ struct Trav {
         const float orgz = (rt3_u2f(n0.z) - o.z) * idir.z;
         // conservative padding of the slab distances (a few ulps of the largest operand)
         const float keps = 4.76837158e-7f;  // 2^-21
-        const float padx = keps * (fabsf(orgx) + 255.0f * fabsf(adjx));
-        const float pady = keps * (fabsf(orgy) + 255.0f * fabsf(adjy));
-        const float padz = keps * (fabsf(orgz) + 255.0f * fabsf(adjz));
+        const float padx = keps * (fabsf(orgx) + (float)RT3_QMAX * fabsf(adjx));
+        const float pady = keps * (fabsf(orgy) + (float)RT3_QMAX * fabsf(adjy));
+        const float padz = keps * (fabsf(orgz) + (float)RT3_QMAX * fabsf(adjz));
         const float nox = orgx - padx, fox = orgx + padx;
         const float noy = orgy - pady, foy = orgy + pady;
         const float noz = orgz - padz, foz = orgz + padz;
+        const uint32_t oct4 = oct * 0x01010101u;
 
         uint32_t hitmask = 0;
 #pragma unroll
         for (int half = 0; half < 2; half++) {
+            // meta bytes of 4 children at once (after Ylitie et al.): internal children land on bit
+            // 24 + (slot ^ oct) so that the nearest child is the highest set bit; leaf children put
+            // their unary primitive count at their primitive offset; empty slots contribute 0 bits
             const uint32_t meta4 = half ? n1.w : n1.z;
+            const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;  // 0xff in the bytes of internal children
+            const uint32_t bit_index4 = (meta4 ^ (oct4 & inner_mask4)) & 0x1f1f1f1fu;
+            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+#if RT3_NODE_FP16
+            const uint4 qx = rt3_ldg(np + 2 + 3 * half), qy = rt3_ldg(np + 3 + 3 * half), qz = rt3_ldg(np + 4 + 3 * half);
+            // {lo01, lo23, hi01, hi23} per axis; near plane = lo when d >= 0
+            const uint32_t nx[2] = {(oct & 1u) ? qx.x : qx.z, (oct & 1u) ? qx.y : qx.w}, fx[2] = {(oct & 1u) ? qx.z : qx.x, (oct & 1u) ? qx.w : qx.y};
+            const uint32_t ny[2] = {(oct & 2u) ? qy.x : qy.z, (oct & 2u) ? qy.y : qy.w}, fy[2] = {(oct & 2u) ? qy.z : qy.x, (oct & 2u) ? qy.w : qy.y};
+            const uint32_t nz[2] = {(oct & 4u) ? qz.x : qz.z, (oct & 4u) ? qz.y : qz.w}, fz[2] = {(oct & 4u) ? qz.z : qz.x, (oct & 4u) ? qz.w : qz.y};
+#pragma unroll
+            for (int pr = 0; pr < 2; pr++) {
+                const float2 anx = half2_to_float2(nx[pr]), any_ = half2_to_float2(ny[pr]), anz = half2_to_float2(nz[pr]);
+                const float2 afx = half2_to_float2(fx[pr]), afy = half2_to_float2(fy[pr]), afz = half2_to_float2(fz[pr]);
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int j = 2 * pr + e;
+                    const float tnx = fmaf(e ? anx.y : anx.x, adjx, nox);
+                    const float tny = fmaf(e ? any_.y : any_.x, adjy, noy);
+                    const float tnz = fmaf(e ? anz.y : anz.x, adjz, noz);
+                    const float tfx = fmaf(e ? afx.y : afx.x, adjx, fox);
+                    const float tfy = fmaf(e ? afy.y : afy.x, adjy, foy);
+                    const float tfz = fmaf(e ? afz.y : afz.x, adjz, foz);
+                    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+                    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
+                    if (tn <= tf) hitmask |= ((child_bits4 >> (8 * j)) & 0xffu) << ((bit_index4 >> (8 * j)) & 0xffu);
+                }
+            }
+#else
+            const uint4 n2 = rt3_ldg(np + 2), n3 = rt3_ldg(np + 3), n4 = rt3_ldg(np + 4);
             const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
             const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
             const uint32_t nx = (oct & 1u) ? lox : hix, fx = (oct & 1u) ? hix : lox;
@@ -355,7 +427,6 @@ struct Trav {
             const uint32_t nz = (oct & 4u) ? loz : hiz, fz = (oct & 4u) ? hiz : loz;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint32_t m = (meta4 >> (8 * j)) & 0xffu;
                 const float tnx = fmaf(byte_to_float(nx, j), adjx, nox);
                 const float tny = fmaf(byte_to_float(ny, j), adjy, noy);
                 const float tnz = fmaf(byte_to_float(nz, j), adjz, noz);
@@ -364,12 +435,9 @@ struct Trav {
                 const float tfz = fmaf(byte_to_float(fz, j), adjz, foz);
                 const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
                 const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
-                if (m != 0u && tn <= tf) {
-                    const bool internal = (m & 0x18u) == 0x18u;
-                    const uint32_t idx = (m & 31u) ^ (internal ? oct : 0u);
-                    hitmask |= (m >> 5) << idx;
-                }
+                if (tn <= tf) hitmask |= ((child_bits4 >> (8 * j)) & 0xffu) << ((bit_index4 >> (8 * j)) & 0xffu);
             }
+#endif
         }
         ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
         tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
@@ -408,6 +476,9 @@ struct Trav {
             tg = make_uint2(0u, 0u);
             return false;
         }
+#ifdef RT3_STATS
+        c_prims++;
+#endif
         const float4* pr = prims + 3u * pi;
         const float4 a = rt3_ldg(pr), b = rt3_ldg(pr + 1);
         bool got = false;
@@ -435,6 +506,9 @@ struct Trav {
     // warp runs the three phases in lock step (pop -> one wide node -> all pending primitives), so
     // lanes that are in the same phase execute it together instead of serialising per action.
     RT3_HD bool step(const TravScene& sc) {
+#ifdef RT3_STATS
+        c_rounds++;
+#endif
         while (tg.y == 0u && !(ng.y & 0xff000000u)) {
             if (sp == 0) return false;
             const uint2 e = stack[--sp];
@@ -455,7 +529,130 @@ struct Trav {
         return true;
     }
 
+#ifndef RT3_EMULATE
+    // ---------------------------------------------------------------------------------- warp-cooperative round
+    // Same round as step(), but executed by ALL 32 lanes of the warp (finished lanes pass active =
+    // false) so that the triangle phase can be shared: ncu showed that after a wide-node step only
+    // ~2.7 lanes have triangles pending, some of them several, and the per-lane loop ran 3.5 passes
+    // of a ~270-instruction test at <10 % lane utilisation — more issue slots than the node phase.
+    // Here every lane posts its pending (owner lane, triangle) pairs to a shared-memory work list,
+    // the pairs are dealt out one per lane, each lane tests its pair against the OWNER's ray
+    // (fetched with shuffles), and the owners then fold the results of their own pairs through the
+    // usual accept() rule — so the outcome is identical to the per-lane loop, pass for pass.
+    // Spheres, curves and TLAS leaves (instance entry) keep the per-lane path.
+    __device__ __forceinline__ bool step_warp(const TravScene& sc, bool active, uint32_t* s_items, float4* s_res) {
+        const uint32_t lane = threadIdx.x & 31u;
+        if (active) {
+#ifdef RT3_STATS
+            c_rounds++;
+#endif
+            while (tg.y == 0u && !(ng.y & 0xff000000u)) {
+                if (sp == 0) { active = false; break; }
+                const uint2 e = stack[--sp];
+                if (e.y == 0u) {  // sentinel: leave the instance
+                    if (e.x == 0xffffffffu) restore_world();
+                    nodes = sc.tlas_nodes;
+                    cur_inst = -1;
+                } else if (e.y & 0xff000000u) {
+                    ng = e;
+                } else {
+                    tg = e;
+                }
+            }
+            if (active && tg.y == 0u) node_step(sc);
+        }
+        // ---- cooperative triangle phase (warp-uniform control flow from here)
+        const bool tri_lane = active && tg.y != 0u && cur_inst >= 0 && ptype == PRIM_TRI;
+        const uint32_t cnt = tri_lane ? (uint32_t)__popc(tg.y) : 0u;
+        const uint32_t maxc = __reduce_max_sync(0xffffffffu, cnt);
+        if (maxc == 1u) {  // one triangle per lane at most: nothing to redistribute, test in place
+            if (tri_lane) {
+#ifdef RT3_STATS
+                c_prims++;
+#endif
+                const float4* pr = prims + 3u * (tg.x + (uint32_t)(__ffs((int)tg.y) - 1));
+                tg.y = 0u;
+                const float4 a = __ldg(pr), b = __ldg(pr + 1), c = __ldg(pr + 2);
+                float t, u, v;
+                if (test_triangle(o, shear(), v3(a), v3(b), v3(c), t, u, v) && accept(t, u, v, (int)__float_as_uint(a.w)) && ANY_HIT) active = false;
+            }
+        } else if (maxc > 1u) {
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total != 0u) {
+            const uint32_t excl = incl - cnt;
+            uint32_t posted = 0;
+            if (tri_lane) {  // post (owner, triangle) pairs; what does not fit stays in tg for the next round
+                uint32_t m = tg.y, pos = excl;
+                while (m != 0u && pos < RT3_COOP_CAP) {
+                    const uint32_t b = (uint32_t)(__ffs((int)m) - 1);
+                    m &= m - 1u;
+                    s_items[pos++] = (lane << 27) | (tg.x + b);
+                    posted++;
+                }
+                tg.y = m;
+            }
+            __syncwarp();
+            const uint32_t n_items = total < RT3_COOP_CAP ? total : RT3_COOP_CAP;
+            const uint32_t kpack = inv >> 8;
+            const uint64_t pbase = (uint64_t)prims;
+            for (uint32_t base = 0; base < n_items; base += 32u) {
+                const uint32_t g = base + lane;
+                const bool have = g < n_items;
+                const uint32_t item = have ? s_items[g] : 0u;
+                const int owner = (int)(item >> 27);
+                const float ox = __shfl_sync(0xffffffffu, o.x, owner), oy = __shfl_sync(0xffffffffu, o.y, owner), oz = __shfl_sync(0xffffffffu, o.z, owner);
+                Shear s;
+                s.Sx = __shfl_sync(0xffffffffu, Sx, owner); s.Sy = __shfl_sync(0xffffffffu, Sy, owner); s.Sz = __shfl_sync(0xffffffffu, Sz, owner);
+                const uint32_t kp = __shfl_sync(0xffffffffu, kpack, owner);
+                const float otmin = __shfl_sync(0xffffffffu, tmin, owner), otbest = __shfl_sync(0xffffffffu, tbest, owner);
+                const uint64_t op = __shfl_sync(0xffffffffu, pbase, owner);
+                if (have) {
+                    s.kx = (int)(kp & 3u); s.ky = (int)((kp >> 2) & 3u); s.kz = (int)((kp >> 4) & 3u);
+                    const float4* pr = reinterpret_cast<const float4*>(op) + 3u * (item & 0x07ffffffu);
+                    const float4 a = __ldg(pr), b = __ldg(pr + 1), c = __ldg(pr + 2);
+                    float t, u, v;
+                    const bool hit = test_triangle(v3(ox, oy, oz), s, v3(a), v3(b), v3(c), t, u, v) && t > otmin && t <= otbest;
+                    s_res[g] = make_float4(hit ? t : __int_as_float(0x7fc00000), u, v, a.w);  // NaN marks a miss
+                }
+            }
+            __syncwarp();
+            if (tri_lane) {  // owners fold their own results, in posting order
+                for (uint32_t k = 0; k < posted; k++) {
+#ifdef RT3_STATS
+                    c_prims++;
+#endif
+                    const float4 r = s_res[excl + k];
+                    if (r.x == r.x) {
+                        if (accept(r.x, r.y, r.z, (int)__float_as_uint(r.w)) && ANY_HIT) { active = false; break; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        }
+        // ---- everything else that is pending: instance entry, spheres, curves (per lane)
+        if (active && tg.y != 0u && !(cur_inst >= 0 && ptype == PRIM_TRI)) {
+            while (tg.y != 0u) {
+                if (prim_step(sc)) { active = false; break; }
+            }
+        }
+        return active;
+    }
+#endif
+
     RT3_HD HitRec result() const {
+#ifdef RT3_STATS
+        rt3_atomic_add(const_cast<uint32_t*>(dbg) + 2, c_nodes);
+        rt3_atomic_add(const_cast<uint32_t*>(dbg) + 3, c_prims);
+        rt3_atomic_add(const_cast<uint32_t*>(dbg) + 4, c_rounds);
+        rt3_atomic_add(const_cast<uint32_t*>(dbg) + 5, 1u);
+#endif
         HitRec h;
         h.t = hprim >= 0 ? tbest : 0.0f;
         h.u = hu; h.v = hv; h.prim = hprim; h.inst = hinst;

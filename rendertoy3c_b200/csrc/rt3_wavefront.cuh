@@ -95,7 +95,7 @@ static void k_traverse(TraverseArgs a) {
 #define RT3_TRAV_THREADS 128
 #endif
 #ifndef RT3_TRAV_MIN_BLOCKS
-#define RT3_TRAV_MIN_BLOCKS 10
+#define RT3_TRAV_MIN_BLOCKS 8
 #endif
 #ifndef RT3_REFILL_THRESHOLD
 #define RT3_REFILL_THRESHOLD 26
@@ -109,6 +109,10 @@ __global__ void __launch_bounds__(RT3_TRAV_THREADS, RT3_TRAV_MIN_BLOCKS) k_trave
     if (a.stat && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.stat, (unsigned long long)n);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
+#if RT3_COOP
+    __shared__ uint32_t s_items[RT3_TRAV_THREADS / 32][RT3_COOP_CAP];
+    __shared__ float4 s_res[RT3_TRAV_THREADS / 32][RT3_COOP_CAP];
+#endif
     Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY)> tr;
     bool active = false;
     bool exhausted = false;
@@ -134,12 +138,18 @@ __global__ void __launch_bounds__(RT3_TRAV_THREADS, RT3_TRAV_MIN_BLOCKS) k_trave
         if (busy == 0u) break;
         const uint32_t threshold = exhausted ? 1u : RT3_REFILL_THRESHOLD;
         while (__popc(busy) >= threshold) {
+#if RT3_COOP
+            const bool was = active;
+            active = tr.step_warp(a.scene, active, s_items[threadIdx.x >> 5], s_res[threadIdx.x >> 5]);
+            if (was && !active) trav_end<MODE>(a, my, tr);
+#else
             if (active) {
                 if (!tr.step(a.scene)) {
                     trav_end<MODE>(a, my, tr);
                     active = false;
                 }
             }
+#endif
             busy = __ballot_sync(0xffffffffu, active);
         }
     }

@@ -45,6 +45,9 @@ def run(rays, any_hit, reps=3):
         ev[1].record(st)
         g.sync()
         best = min(best, ev[0].elapsed_time(ev[1]))
+    dc = g.debug_counters()
+    if dc[5]:
+        print("   per ray: %.1f wide nodes, %.1f prim tests, %.1f rounds" % (dc[2] / dc[5], dc[3] / dc[5], dc[4] / dc[5]))
     return len(rays) / best / 1e3
 
 
