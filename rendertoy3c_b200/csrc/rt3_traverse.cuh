@@ -216,7 +216,16 @@ RT3_HD float byte_to_float(uint32_t w, int j) {
 #ifdef RT3_EMULATE
     return (float)((w >> (8 * j)) & 0xffu);
 #else
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (uint32_t)j)) - 8388608.0f;
+    // selector as an immediate, the 2^23 bias in a register (PRMT takes one immediate): PRMT + FADD
+    uint32_t r;
+    uint32_t magic = 0x4B000000u;
+    switch (j) {
+        case 0: asm("prmt.b32 %0, %1, %2, 0x7650;" : "=r"(r) : "r"(w), "r"(magic)); break;
+        case 1: asm("prmt.b32 %0, %1, %2, 0x7651;" : "=r"(r) : "r"(w), "r"(magic)); break;
+        case 2: asm("prmt.b32 %0, %1, %2, 0x7652;" : "=r"(r) : "r"(w), "r"(magic)); break;
+        default: asm("prmt.b32 %0, %1, %2, 0x7653;" : "=r"(r) : "r"(w), "r"(magic)); break;
+    }
+    return __uint_as_float(r) - 8388608.0f;
 #endif
 }
 

@@ -95,7 +95,7 @@ static void k_traverse(TraverseArgs a) {
 #define RT3_TRAV_THREADS 128
 #endif
 #ifndef RT3_TRAV_MIN_BLOCKS
-#define RT3_TRAV_MIN_BLOCKS 8
+#define RT3_TRAV_MIN_BLOCKS 10
 #endif
 #ifndef RT3_REFILL_THRESHOLD
 #define RT3_REFILL_THRESHOLD 26
