@@ -75,6 +75,10 @@ struct Bvh8 {            // one acceleration structure (BLAS or TLAS) in device 
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};  // root bounds (host copy)
 };
 
+#ifndef RT3_ADAPTIVE_MORTON
+#define RT3_ADAPTIVE_MORTON 1
+#endif
+
 // ------------------------------------------------------------------------------------ helpers
 RT3_HD uint32_t float_to_ordered(float f) { const uint32_t u = rt3_f2u(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 RT3_HD float ordered_to_float(uint32_t u) { return rt3_u2f((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
@@ -132,14 +136,36 @@ RT3_GLOBAL(k_bvh_morton, BuildArrays b) {
     const float4 lo = b.plo[i], hi = b.phi[i];
     const float c[3] = {(lo.x + hi.x) * 0.5f, (lo.y + hi.y) * 0.5f, (lo.z + hi.z) * 0.5f};
     uint64_t key = 0;
+    uint32_t q[3];
+    float ext[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const float l = ordered_to_float(b.bounds[k]), h = ordered_to_float(b.bounds[3 + k]);
-        const float ext = h - l;
-        float t = ext > 0.0f ? (c[k] - l) / ext : 0.0f;
+        ext[k] = h - l;
+        float t = ext[k] > 0.0f ? (c[k] - l) / ext[k] : 0.0f;
         t = fminf(fmaxf(t * 2097152.0f, 0.0f), 2097151.0f);
-        key |= expand21((uint32_t)t) << k;
+        q[k] = (uint32_t)t;
     }
+#if RT3_ADAPTIVE_MORTON
+    // Extent-adaptive bit order (after Vinkler et al. 2017, "Extended Morton codes"): instead of the
+    // fixed xyz interleave, each key bit halves the axis whose CELL is currently longest, so a flat
+    // scene (terrain: 20 x 8 x 20) is not split in y as often as in x and z.  The axis sequence
+    // depends only on the scene bounds, so a common key prefix is still one spatial cell.
+    int used[3] = {0, 0, 0};
+    for (int bit = 0; bit < 63; bit++) {
+        int a = -1;
+        float best = -1.0f;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (used[k] < 21 && ext[k] > best) { best = ext[k]; a = k; }
+        key = (key << 1) | ((q[a] >> (20 - used[a])) & 1u);
+        used[a]++;
+        ext[a] *= 0.5f;
+    }
+#else
+#pragma unroll
+    for (int k = 0; k < 3; k++) key |= expand21(q[k]) << k;
+#endif
     b.keys[i] = key;
     b.vals[i] = i;
 }

@@ -33,6 +33,7 @@ struct Geometry {
     DevBuf<uint32_t> order;
     DevBuf<float4> prims;
     Bvh8 bvh;
+    bool has_blas = false;  // built lazily: meshes that are only used by merged (identity) instances never need one
 };
 
 struct InstanceHost {
@@ -69,6 +70,14 @@ struct rt3_context {
     DevBuf<Node8> tlas_nodes;
     DevBuf<uint32_t> tlas_order;
     Bvh8 tlas;
+    // merged world BLAS of the identity static mesh instances (single-level fast path)
+    DevBuf<Node8> m_nodes;
+    DevBuf<uint32_t> m_order;
+    DevBuf<float4> m_prims;
+    DevBuf<uint2> m_map;
+    Bvh8 m_bvh;
+    bool has_merged = false, single_level = false;
+    int opt_merge = 1;
     DevBuf<uint32_t> d_flags;  // [0] error flags, [1] max stack
     // film
     uint32_t width = 0, height = 0;
@@ -93,8 +102,11 @@ struct rt3_context {
 
     TravScene trav_scene() {
         TravScene s;
-        s.tlas_nodes = tlas_nodes.p;
+        s.tlas_nodes = single_level ? m_nodes.p : tlas_nodes.p;
         s.tlas_order = tlas_order.p;
+        s.merged_map = m_map.p;
+        s.root_prims = single_level ? m_prims.p : nullptr;
+        s.root_is_blas = single_level ? 1u : 0u;
         s.instances = d_inst.p;
         s.hitgroups = d_hg.p;
         s.blas = d_blas.p;
@@ -128,24 +140,35 @@ void launch_traverse(rt3_context* c, const TraverseArgs& a) {
 
 void upload_hitgroups(rt3_context* c) {
     if (!c->hitgroups_dirty || c->inst.empty()) return;
-    std::vector<HitGroupDev> hg(c->inst.size());
+    std::vector<HitGroupDev> hg(c->inst.size() + 1);  // + the merged pseudo-instance (never shaded)
     for (size_t i = 0; i < c->inst.size(); i++) hg[i] = c->inst[i].hg;
+    hg[c->inst.size()] = HitGroupDev{{0, 0, 0}, {0, 0, 0}, -1, 1.0f};
     c->d_hg.ensure(hg.size());
     h2d(c->d_hg.p, hg.data(), sizeof(HitGroupDev) * hg.size(), c->stream);
     stream_sync(c->stream);
     c->hitgroups_dirty = false;
 }
 
-uint64_t finish_geometry(rt3_context* c, std::unique_ptr<Geometry> g, DevBuf<float4>& lo, DevBuf<float4>& hi) {
+uint64_t finish_geometry(rt3_context* c, std::unique_ptr<Geometry> g) {
+    c->geoms.push_back(std::move(g));
+    c->built = false;
+    return (uint64_t)c->geoms.size();  // handle = index + 1
+}
+
+// BLAS of one geometry (reference: the GAS build inside the CUDAMesh ctor, cuda_mesh.h:92-146), on first need
+void ensure_blas(rt3_context* c, Geometry* g) {
+    if (g->has_blas) return;
+    DevBuf<float4> lo(g->nprims), hi(g->nprims);
+    if (g->type == PRIM_TRI) RT3_LAUNCH_1D(k_tri_boxes, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, lo.p, hi.p);
+    else if (g->type == PRIM_SPHERE) RT3_LAUNCH_1D(k_sphere_boxes, g->nprims, c->stream, (const float4*)g->cr.p, lo.p, hi.p);
+    else RT3_LAUNCH_1D(k_curve_boxes, g->nprims, c->stream, (const float4*)g->cr.p, (const int32_t*)g->seg.p, lo.p, hi.p);
     build_bvh8(lo.p, hi.p, g->nprims, c->stream, g->nodes, g->order, g->bvh);
     g->prims.alloc(3 * (size_t)g->nprims);
     if (g->type == PRIM_TRI) RT3_LAUNCH_1D(k_pack_tris, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, (const uint32_t*)g->order.p, g->prims.p);
     else if (g->type == PRIM_SPHERE) RT3_LAUNCH_1D(k_pack_spheres, g->nprims, c->stream, (const float4*)g->cr.p, (const uint32_t*)g->order.p, g->prims.p);
     else RT3_LAUNCH_1D(k_pack_curves, g->nprims, c->stream, (const float4*)g->cr.p, (const int32_t*)g->seg.p, (const uint32_t*)g->order.p, g->prims.p);
     stream_sync(c->stream);
-    c->geoms.push_back(std::move(g));
-    c->built = false;
-    return (uint64_t)c->geoms.size();  // handle = index + 1
+    g->has_blas = true;
 }
 
 void ensure_pools(rt3_context* c, size_t paths) {
@@ -257,6 +280,7 @@ int rt3_set_option(rt3_context_t c, const char* key, int value) {
     const std::string k(key);
     if (k == "timing") c->opt_timing = value;
     else if (k == "persist_ctas_per_sm") c->opt_ctas_per_sm = value;
+    else if (k == "merge_identity") { c->opt_merge = value; c->built = false; }
     else if (k == "sort_rays" || k == "sort_materials") { RT3_REQUIRE(value == 0, RT3_ERR_UNSUPPORTED, "set_option: sorting stages are not built yet"); }
     else throw Error(RT3_ERR_INVALID, "set_option: unknown key " + k);
     RT3_API_END
@@ -280,9 +304,8 @@ int rt3_mesh_create(rt3_context_t c, const float* verts, int num_keys, int nv, c
     h2d(g->normals.p, normals, g->normals.bytes(), c->stream);
     h2d(g->uvs.p, uvs, g->uvs.bytes(), c->stream);
     h2d(g->idx.p, idx, g->idx.bytes(), c->stream);
-    DevBuf<float4> lo(nt), hi(nt);
-    RT3_LAUNCH_1D(k_tri_boxes, nt, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, lo.p, hi.p);
-    *blas = finish_geometry(c, std::move(g), lo, hi);
+    stream_sync(c->stream);  // host arrays are borrowed for the duration of the call only
+    *blas = finish_geometry(c, std::move(g));
     RT3_API_END
 }
 
@@ -294,9 +317,8 @@ int rt3_spheres_create(rt3_context_t c, const float* cr, int n, rt3_handle_t* bl
     g->nprims = (uint32_t)n;
     g->cr.alloc(n);
     h2d(g->cr.p, cr, g->cr.bytes(), c->stream);
-    DevBuf<float4> lo(n), hi(n);
-    RT3_LAUNCH_1D(k_sphere_boxes, n, c->stream, (const float4*)g->cr.p, lo.p, hi.p);
-    *blas = finish_geometry(c, std::move(g), lo, hi);
+    stream_sync(c->stream);
+    *blas = finish_geometry(c, std::move(g));
     RT3_API_END
 }
 
@@ -312,9 +334,8 @@ int rt3_curves_create(rt3_context_t c, int degree, const float* cp, int ncp, con
     g->seg.alloc(nseg);
     h2d(g->cr.p, cp, g->cr.bytes(), c->stream);
     h2d(g->seg.p, seg, g->seg.bytes(), c->stream);
-    DevBuf<float4> lo(nseg), hi(nseg);
-    RT3_LAUNCH_1D(k_curve_boxes, nseg, c->stream, (const float4*)g->cr.p, (const int32_t*)g->seg.p, lo.p, hi.p);
-    *blas = finish_geometry(c, std::move(g), lo, hi);
+    stream_sync(c->stream);
+    *blas = finish_geometry(c, std::move(g));
     RT3_API_END
 }
 
@@ -378,44 +399,105 @@ int rt3_accel_build(rt3_context_t c) {
     RT3_REQUIRE(c, RT3_ERR_INVALID, "accel_build: null context");
     RT3_REQUIRE(!c->inst.empty(), RT3_ERR_STATE, "accel_build: no instances");
     const uint32_t ni = (uint32_t)c->inst.size();
-    // BLAS table
-    std::vector<BlasDev> bt(c->geoms.size());
-    std::vector<BlasBounds> bb(c->geoms.size());
-    for (size_t i = 0; i < bt.size(); i++) {
+    static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    // ---- which instances go into the merged world BLAS, which stay in the TLAS
+    std::vector<uint32_t> merged, tl;
+    for (uint32_t i = 0; i < ni; i++) {
+        const InstanceHost& in = c->inst[i];
+        const bool identity = in.nkeys == 0 && memcmp(in.xform, ident, sizeof(ident)) == 0;
+        if (c->opt_merge && identity && c->geoms[in.blas]->type == PRIM_TRI) merged.push_back(i);
+        else tl.push_back(i);
+    }
+    c->has_merged = !merged.empty();
+    c->single_level = c->has_merged && tl.empty();
+    for (uint32_t i : tl) ensure_blas(c, c->geoms[c->inst[i].blas].get());
+    BlasBounds merged_bounds{};
+    if (c->has_merged) {
+        std::vector<MergedRange> ranges;
+        uint32_t total = 0;
+        for (uint32_t i : merged) {
+            const Geometry& g = *c->geoms[c->inst[i].blas];
+            ranges.push_back(MergedRange{total, i, g.verts.p, g.idx.p});
+            total += g.nprims;
+        }
+        DevBuf<float4> lo(total), hi(total);
+        for (const MergedRange& r : ranges) {
+            const Geometry& g = *c->geoms[c->inst[r.inst].blas];
+            RT3_LAUNCH_1D(k_tri_boxes, g.nprims, c->stream, (const float*)g.verts.p, (const int32_t*)g.idx.p, lo.p + r.first, hi.p + r.first);
+        }
+        build_bvh8(lo.p, hi.p, total, c->stream, c->m_nodes, c->m_order, c->m_bvh);
+        DevBuf<MergedRange> d_ranges(ranges.size());
+        h2d(d_ranges.p, ranges.data(), sizeof(MergedRange) * ranges.size(), c->stream);
+        c->m_prims.alloc(3 * (size_t)total);
+        c->m_map.alloc(total);
+        RT3_LAUNCH_1D(k_pack_merged, total, c->stream, (const MergedRange*)d_ranges.p, (uint32_t)ranges.size(), (const uint32_t*)c->m_order.p, c->m_prims.p, c->m_map.p);
+        stream_sync(c->stream);
+        for (int k = 0; k < 3; k++) { merged_bounds.lo[k] = c->m_bvh.lo[k]; merged_bounds.hi[k] = c->m_bvh.hi[k]; }
+    } else {
+        c->m_map.alloc(1);
+    }
+    // ---- BLAS table: one entry per geometry (+ one for the merged BLAS)
+    const size_t ng = c->geoms.size();
+    std::vector<BlasDev> bt(ng + 1);
+    std::vector<BlasBounds> bb(ng + 1);
+    for (size_t i = 0; i < ng; i++) {
         const Geometry& g = *c->geoms[i];
         bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p};
         for (int k = 0; k < 3; k++) { bb[i].lo[k] = g.bvh.lo[k]; bb[i].hi[k] = g.bvh.hi[k]; }
     }
+    bt[ng] = BlasDev{c->m_nodes.p, c->m_prims.p, PRIM_TRI, c->m_bvh.num_prims, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bb[ng] = merged_bounds;
     c->d_blas.alloc(bt.size());
     h2d(c->d_blas.p, bt.data(), sizeof(BlasDev) * bt.size(), c->stream);
     DevBuf<BlasBounds> d_bb(bb.size());
     h2d(d_bb.p, bb.data(), sizeof(BlasBounds) * bb.size(), c->stream);
-    // instance table (+ motion keys)
-    std::vector<InstanceDev> it(ni);
-    std::vector<float> keys, stat(12 * (size_t)ni);
+    // ---- instance table: the real instances (shading reads them by hit id) + one pseudo-instance for the merged BLAS
+    std::vector<InstanceDev> it(ni + 1);
+    std::vector<float> keys, stat(12 * (size_t)(ni + 1));
     for (uint32_t i = 0; i < ni; i++) {
         const InstanceHost& in = c->inst[i];
         memset(&it[i], 0, sizeof(InstanceDev));
         it[i].blas = in.blas;
         it[i].nkeys = in.nkeys;
-        static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
         it[i].identity = (in.nkeys == 0 && memcmp(in.xform, ident, sizeof(ident)) == 0) ? 1u : 0u;
         it[i].key_offset = (uint32_t)keys.size();
         it[i].t0 = in.t0;
         keys.insert(keys.end(), in.keys.begin(), in.keys.end());
         memcpy(&stat[12 * (size_t)i], in.xform, sizeof(in.xform));
     }
-    c->d_inst.alloc(ni);
+    memset(&it[ni], 0, sizeof(InstanceDev));
+    it[ni].blas = (uint32_t)ng;
+    it[ni].identity = 2u;
+    memcpy(&stat[12 * (size_t)ni], ident, sizeof(ident));
+    c->d_inst.alloc(ni + 1);
     c->d_static.alloc(stat.size());
     c->d_keys.alloc(keys.size() ? keys.size() : 12);
-    h2d(c->d_inst.p, it.data(), sizeof(InstanceDev) * ni, c->stream);
+    h2d(c->d_inst.p, it.data(), sizeof(InstanceDev) * (ni + 1), c->stream);
     h2d(c->d_static.p, stat.data(), sizeof(float) * stat.size(), c->stream);
     h2d(c->d_keys.p, keys.data(), sizeof(float) * keys.size(), c->stream);
-    RT3_LAUNCH_1D(k_invert_static, ni, c->stream, (const float*)c->d_static.p, c->d_inst.p);
-    DevBuf<float4> lo(ni), hi(ni);
-    RT3_LAUNCH_1D(k_instance_boxes, ni, c->stream, (const InstanceDev*)c->d_inst.p, (const float*)c->d_static.p, (const BlasBounds*)d_bb.p,
-                  (const float*)c->d_keys.p, lo.p, hi.p);
-    build_bvh8(lo.p, hi.p, ni, c->stream, c->tlas_nodes, c->tlas_order, c->tlas);
+    RT3_LAUNCH_1D(k_invert_static, ni + 1, c->stream, (const float*)c->d_static.p, c->d_inst.p);
+    // ---- TLAS over the remaining instances (+ the merged pseudo-instance), unless the scene is single-level
+    if (!c->single_level) {
+        DevBuf<float4> lo(ni + 1), hi(ni + 1);
+        RT3_LAUNCH_1D(k_instance_boxes, ni + 1, c->stream, (const InstanceDev*)c->d_inst.p, (const float*)c->d_static.p, (const BlasBounds*)d_bb.p,
+                      (const float*)c->d_keys.p, lo.p, hi.p);
+        std::vector<uint32_t> sel(tl);
+        if (c->has_merged) sel.push_back(ni);
+        // gather the selected boxes, build, then translate the TLAS leaf order back to instance ids
+        const uint32_t ns = (uint32_t)sel.size();
+        DevBuf<float4> slo(ns), shi(ns);
+        for (uint32_t k = 0; k < ns; k++) {
+            d2d(slo.p + k, lo.p + sel[k], sizeof(float4), c->stream);
+            d2d(shi.p + k, hi.p + sel[k], sizeof(float4), c->stream);
+        }
+        build_bvh8(slo.p, shi.p, ns, c->stream, c->tlas_nodes, c->tlas_order, c->tlas);
+        std::vector<uint32_t> order(ns);
+        d2h(order.data(), c->tlas_order.p, sizeof(uint32_t) * ns, c->stream);
+        stream_sync(c->stream);
+        for (uint32_t k = 0; k < ns; k++) order[k] = sel[order[k]];
+        h2d(c->tlas_order.p, order.data(), sizeof(uint32_t) * ns, c->stream);
+        stream_sync(c->stream);
+    }
     c->hitgroups_dirty = true;
     upload_hitgroups(c);
     c->built = true;

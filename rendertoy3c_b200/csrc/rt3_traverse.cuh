@@ -43,7 +43,7 @@ struct InstanceDev {         // traversal record (64 B)
     float inv_static[12];    // world -> object of the static instance transform
     uint32_t blas;
     uint32_t nkeys : 16;     // 0 = no motion
-    uint32_t identity : 16;  // static transform is exactly the identity and there is no motion
+    uint32_t identity : 16;  // 1: static transform is exactly the identity and there is no motion; 2: merged world BLAS
     uint32_t key_offset;     // first float of this instance's keys in TravScene::keys
     float t0;                // motion begin; end in t1 (kept in the shading record to stay at 64 B)
 };
@@ -65,7 +65,15 @@ struct TravScene {
     const float* keys;
     uint32_t* error_flags;          // bit0 stack overflow
     uint32_t* max_stack;
+    // single-level fast path: all identity, static triangle-mesh instances (every instance the
+    // reference creates, cuda_scene.h:141-146) are merged into ONE world-space BLAS whose primitive
+    // ids index merged_map -> (instance, primitive).  If nothing else is in the scene the TLAS is
+    // skipped altogether (root_is_blas) and tlas_nodes points at the merged BLAS.
+    const uint2* merged_map;
+    const float4* root_prims;
+    uint32_t root_is_blas;
 };
+#define RT3_MERGED_INST 0x7fffffff
 
 struct HitRec { float t, u, v; int prim, inst; };
 
@@ -313,7 +321,7 @@ struct Trav {
     RT3_HD void init(const TravScene& sc, float3 ro, float3 rd, float rtmin, float rtmax, float rtime) {
         tmin = rtmin; tbest = rtmax;
         hu = hv = 0.0f; hprim = -1; hinst = -1;
-        nodes = sc.tlas_nodes; prims = nullptr; ptype = 0; cur_inst = -1;
+        nodes = sc.tlas_nodes; prims = sc.root_prims; ptype = PRIM_TRI; cur_inst = sc.root_is_blas ? RT3_MERGED_INST : -1;
         ng = make_uint2(0u, 0x80000000u);
         tg = make_uint2(0u, 0u);
         sp = 0;
@@ -353,10 +361,13 @@ struct Trav {
     RT3_HD bool in_range(float t) const { return t > tmin && (hprim < 0 ? t < tbest : t <= tbest); }
 
     // returns true if the candidate was accepted
-    RT3_HD bool accept(float t, float u, float v, int prim) {
+    RT3_HD bool accept(const TravScene& sc, float t, float u, float v, int prim) {
         if (!in_range(t)) return false;
-        if (!ANY_HIT && hprim >= 0 && t == tbest) {
-            if (!(cur_inst < hinst || (cur_inst == hinst && prim < hprim))) return false;
+        if (!ANY_HIT && hprim >= 0 && t == tbest) {  // exact tie: lowest (instance, primitive) wins
+            int ci = cur_inst, cp = prim, bi = hinst, bp = hprim;
+            if (ci == RT3_MERGED_INST) { const uint2 m = sc.merged_map[cp]; ci = (int)m.x; cp = (int)m.y; }
+            if (bi == RT3_MERGED_INST) { const uint2 m = sc.merged_map[bp]; bi = (int)m.x; bp = (int)m.y; }
+            if (!(ci < bi || (ci == bi && cp < bp))) return false;
         }
         tbest = t; hu = u; hv = v; hprim = prim; hinst = cur_inst;
         return true;
@@ -480,7 +491,7 @@ struct Trav {
             }
             const BlasDev* bl = sc.blas + in->blas;
             nodes = bl->nodes; prims = bl->prims; ptype = bl->type;
-            cur_inst = inst;
+            cur_inst = in->identity == 2u ? RT3_MERGED_INST : inst;  // 2 = the merged world BLAS pseudo-instance
             ng = make_uint2(0u, 0x80000000u);
             tg = make_uint2(0u, 0u);
             return false;
@@ -494,19 +505,19 @@ struct Trav {
         if (ptype == PRIM_TRI) {
             const float4 c = rt3_ldg(pr + 2);
             float t, u, v;
-            if (test_triangle(o, shear(), v3(a), v3(b), v3(c), t, u, v)) got = accept(t, u, v, (int)rt3_f2u(a.w));
+            if (test_triangle(o, shear(), v3(a), v3(b), v3(c), t, u, v)) got = accept(sc, t, u, v, (int)rt3_f2u(a.w));
         } else if (ptype == PRIM_SPHERE) {
             float ta, tb;
             if (test_sphere(o, cur_d(), v3(a), a.w, ta, tb)) {
                 const int prim = (int)rt3_f2u(b.x);
                 // first root if it lies in the interval, else the second (cuda/sphere.cu:76-94)
-                if (in_range(ta)) got = accept(ta, 0.0f, 0.0f, prim);
-                else got = accept(tb, 0.0f, 0.0f, prim);
+                if (in_range(ta)) got = accept(sc, ta, 0.0f, 0.0f, prim);
+                else got = accept(sc, tb, 0.0f, 0.0f, prim);
             }
         } else {
             const float4 c = rt3_ldg(pr + 2);
             float t, u;
-            if (test_curve_linear(o, cur_d(), v3(a), a.w, v3(b), b.w, t, u)) got = accept(t, u, 0.0f, (int)rt3_f2u(c.x));
+            if (test_curve_linear(o, cur_d(), v3(a), a.w, v3(b), b.w, t, u)) got = accept(sc, t, u, 0.0f, (int)rt3_f2u(c.x));
         }
         return ANY_HIT && got;
     }
@@ -583,7 +594,7 @@ struct Trav {
                 tg.y = 0u;
                 const float4 a = __ldg(pr), b = __ldg(pr + 1), c = __ldg(pr + 2);
                 float t, u, v;
-                if (test_triangle(o, shear(), v3(a), v3(b), v3(c), t, u, v) && accept(t, u, v, (int)__float_as_uint(a.w)) && ANY_HIT) active = false;
+                if (test_triangle(o, shear(), v3(a), v3(b), v3(c), t, u, v) && accept(sc, t, u, v, (int)__float_as_uint(a.w)) && ANY_HIT) active = false;
             }
         } else if (maxc > 1u) {
         uint32_t incl = cnt;
@@ -638,7 +649,7 @@ struct Trav {
 #endif
                     const float4 r = s_res[excl + k];
                     if (r.x == r.x) {
-                        if (accept(r.x, r.y, r.z, (int)__float_as_uint(r.w)) && ANY_HIT) { active = false; break; }
+                        if (accept(sc, r.x, r.y, r.z, (int)__float_as_uint(r.w)) && ANY_HIT) { active = false; break; }
                     }
                 }
             }
@@ -655,7 +666,7 @@ struct Trav {
     }
 #endif
 
-    RT3_HD HitRec result() const {
+    RT3_HD HitRec result(const TravScene& sc) const {
 #ifdef RT3_STATS
         rt3_atomic_add(const_cast<uint32_t*>(dbg) + 2, c_nodes);
         rt3_atomic_add(const_cast<uint32_t*>(dbg) + 3, c_prims);
@@ -665,6 +676,7 @@ struct Trav {
         HitRec h;
         h.t = hprim >= 0 ? tbest : 0.0f;
         h.u = hu; h.v = hv; h.prim = hprim; h.inst = hinst;
+        if (hprim >= 0 && hinst == RT3_MERGED_INST) { const uint2 m = sc.merged_map[hprim]; h.inst = (int)m.x; h.prim = (int)m.y; }
         return h;
     }
 };

@@ -51,7 +51,7 @@ RT3_HD void trav_begin(const TraverseArgs& a, uint32_t i, Trav<(MODE == TRAV_CON
 
 template <int MODE>
 RT3_HD void trav_end(const TraverseArgs& a, uint32_t i, const Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY)>& tr) {
-    const HitRec h = tr.result();
+    const HitRec h = tr.result(a.scene);
     if (MODE == TRAV_EXTEND) {
         a.hit0[i] = make_float4(h.t, h.u, h.v, rt3_u2f((uint32_t)h.prim));
         a.hit_inst[i] = h.inst;
@@ -207,6 +207,23 @@ RT3_GLOBAL(k_pack_curves, const float4* cp, const int32_t* seg, const uint32_t* 
     out[3 * (size_t)j] = cp[seg[p]];
     out[3 * (size_t)j + 1] = cp[seg[p] + 1];
     out[3 * (size_t)j + 2] = make_float4(rt3_u2f(p), 0.0f, 0.0f, 0.0f);
+}
+// merged world BLAS: records of all identity static mesh instances, primitive id = merged index
+struct MergedRange { uint32_t first, inst; const float* verts; const int32_t* idx; };
+RT3_GLOBAL(k_pack_merged, const MergedRange* ranges, uint32_t nranges, const uint32_t* order, float4* out, uint2* map) {
+    const uint32_t j = RT3_THREAD_ID();
+    if (j >= rt3_n_) return;
+    const uint32_t g = order[j];
+    uint32_t lo = 0, hi = nranges;  // last range with first <= g
+    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (ranges[mid].first <= g) lo = mid; else hi = mid; }
+    const MergedRange r = ranges[lo];
+    const uint32_t p = g - r.first;
+    const float3 a = ld3(r.verts + 3 * (size_t)r.idx[3 * (size_t)p]), b = ld3(r.verts + 3 * (size_t)r.idx[3 * (size_t)p + 1]),
+                 c = ld3(r.verts + 3 * (size_t)r.idx[3 * (size_t)p + 2]);
+    out[3 * (size_t)j] = make_float4(a.x, a.y, a.z, rt3_u2f(g));
+    out[3 * (size_t)j + 1] = make_float4(b.x, b.y, b.z, 0.0f);
+    out[3 * (size_t)j + 2] = make_float4(c.x, c.y, c.z, 0.0f);
+    map[g] = make_uint2(r.inst, p);
 }
 // world-space box of every instance: union over motion keys of the transformed BLAS root box
 struct BlasBounds { float lo[3], hi[3]; };
