@@ -23,6 +23,12 @@ enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2 };
 #ifndef RT3_COOP_CAP
 #define RT3_COOP_CAP 32   // (owner, triangle) pairs a warp shares per round
 #endif
+#ifndef RT3_TRAV_THREADS
+#define RT3_TRAV_THREADS 128
+#endif
+#ifndef RT3_SMEM_STACK
+#define RT3_SMEM_STACK 0   // >0: keep that many bottom stack entries per lane in shared memory (measured slower: ptxas spills)
+#endif
 #ifndef RT3_COOP
 #define RT3_COOP 1        // 1: warp-cooperative triangle phase (step_warp), 0: per-lane loop (step)
 #endif
@@ -271,6 +277,10 @@ RT3_HD void prefetch_l1(const void* p) {
 // memory (L1-resident) and is touched only by sphere / curve tests and instance entry / exit.
 enum { FR_D_XY = 0, FR_DZ_TIME, FR_WO_XY, FR_WOZ_WDX, FR_WD_YZ, FR_WIDIR_XY, FR_WIDIRZ_INV, FR_WS_XY, FR_WSZ, FR_COUNT };
 
+#if !defined(RT3_EMULATE) && RT3_SMEM_STACK > 0
+static __shared__ uint2 rt3_s_stack[RT3_SMEM_STACK][RT3_TRAV_THREADS];  // [entry][thread of the CTA]
+#endif
+
 template <bool ANY_HIT>
 struct Trav {
     float3 o;          // current-space origin
@@ -291,16 +301,28 @@ struct Trav {
     uint32_t* dbg;
 #endif
     uint2 stack[RT3_STACK_SIZE + FR_COUNT];
+    // ncu: the per-thread stack in local memory (1280 threads/SM) competes with nodes and triangles for
+    // L1 and spilled to DRAM (99 B written per ray for a 20 B hit record); the hot bottom of the stack
+    // therefore sits in shared memory, column per thread (bank-conflict free), the rest stays local.
+#if !defined(RT3_EMULATE) && RT3_SMEM_STACK > 0
+    RT3_HD void st_put(int i, uint2 e) { if (i < RT3_SMEM_STACK) rt3_s_stack[i][threadIdx.x] = e; else stack[i - RT3_SMEM_STACK] = e; }
+    RT3_HD uint2 st_get(int i) const { return i < RT3_SMEM_STACK ? rt3_s_stack[i][threadIdx.x] : stack[i - RT3_SMEM_STACK]; }
+#else
+    RT3_HD void st_put(int i, uint2 e) { stack[i] = e; }
+    RT3_HD uint2 st_get(int i) const { return stack[i]; }
+#endif
 
     RT3_HD void fr_set(int k, float a, float b) { stack[RT3_STACK_SIZE + k] = make_uint2(rt3_f2u(a), rt3_f2u(b)); }
     RT3_HD float2 fr_get(int k) const { const uint2 v = stack[RT3_STACK_SIZE + k]; return make_float2(rt3_u2f(v.x), rt3_u2f(v.y)); }
     RT3_HD float3 cur_d() const { const float2 a = fr_get(FR_D_XY), b = fr_get(FR_DZ_TIME); return v3(a.x, a.y, b.x); }
     RT3_HD float ray_time() const { return fr_get(FR_DZ_TIME).y; }
 
-    RT3_HD void set_space(float3 oo, float3 dd, float time) {
+    RT3_HD void set_space(float3 oo, float3 dd, float time, bool keep_frame = true) {
         o = oo;
-        fr_set(FR_D_XY, dd.x, dd.y);
-        fr_set(FR_DZ_TIME, dd.z, time);
+        if (keep_frame) {
+            fr_set(FR_D_XY, dd.x, dd.y);
+            fr_set(FR_DZ_TIME, dd.z, time);
+        }
         const float eps = 8.271806e-25f;  // 2^-80: keeps 1/d finite for axis-parallel rays
         const float dx = fabsf(dd.x) > eps ? dd.x : copysignf(eps, dd.x);
         const float dy = fabsf(dd.y) > eps ? dd.y : copysignf(eps, dd.y);
@@ -331,15 +353,17 @@ struct Trav {
 #ifdef RT3_STATS
         c_nodes = c_prims = c_rounds = 0;
 #endif
-        set_space(ro, rd, rtime);
-        // world-space copy for leaving transformed instances
-        fr_set(FR_WO_XY, ro.x, ro.y);
-        fr_set(FR_WOZ_WDX, ro.z, rd.x);
-        fr_set(FR_WD_YZ, rd.y, rd.z);
-        fr_set(FR_WIDIR_XY, idir.x, idir.y);
-        fr_set(FR_WIDIRZ_INV, idir.z, rt3_u2f(inv));
-        fr_set(FR_WS_XY, Sx, Sy);
-        fr_set(FR_WSZ, Sz, 0.0f);
+        // single-level scenes (merged world BLAS only) never read the frame: skip its local-memory stores
+        set_space(ro, rd, rtime, sc.root_is_blas == 0u);
+        if (sc.root_is_blas == 0u) {  // world-space copy for leaving transformed instances
+            fr_set(FR_WO_XY, ro.x, ro.y);
+            fr_set(FR_WOZ_WDX, ro.z, rd.x);
+            fr_set(FR_WD_YZ, rd.y, rd.z);
+            fr_set(FR_WIDIR_XY, idir.x, idir.y);
+            fr_set(FR_WIDIRZ_INV, idir.z, rt3_u2f(inv));
+            fr_set(FR_WS_XY, Sx, Sy);
+            fr_set(FR_WSZ, Sz, 0.0f);
+        }
     }
     RT3_HD void restore_world() {
         const float2 a = fr_get(FR_WO_XY), b = fr_get(FR_WOZ_WDX), c = fr_get(FR_WD_YZ), e = fr_get(FR_WIDIR_XY), f = fr_get(FR_WIDIRZ_INV),
@@ -354,7 +378,7 @@ struct Trav {
     }
 
     RT3_HD void push(const TravScene& sc, uint2 e) {
-        if (sp < RT3_STACK_SIZE) stack[sp++] = e;
+        if (sp < RT3_STACK_SIZE) st_put(sp++, e);
         else rt3_atomic_or(sc.error_flags, 1u);
     }
 
@@ -531,7 +555,7 @@ struct Trav {
 #endif
         while (tg.y == 0u && !(ng.y & 0xff000000u)) {
             if (sp == 0) return false;
-            const uint2 e = stack[--sp];
+            const uint2 e = st_get(--sp);
             if (e.y == 0u) {  // sentinel: leave the instance
                 if (e.x == 0xffffffffu) restore_world();  // the instance had its own ray space
                 nodes = sc.tlas_nodes;
@@ -568,7 +592,7 @@ struct Trav {
 #endif
             while (tg.y == 0u && !(ng.y & 0xff000000u)) {
                 if (sp == 0) { active = false; break; }
-                const uint2 e = stack[--sp];
+                const uint2 e = st_get(--sp);
                 if (e.y == 0u) {  // sentinel: leave the instance
                     if (e.x == 0xffffffffu) restore_world();
                     nodes = sc.tlas_nodes;

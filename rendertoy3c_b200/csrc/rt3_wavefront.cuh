@@ -91,9 +91,6 @@ static void k_traverse(TraverseArgs a) {
     }
 }
 #else
-#ifndef RT3_TRAV_THREADS
-#define RT3_TRAV_THREADS 128
-#endif
 #ifndef RT3_TRAV_MIN_BLOCKS
 #define RT3_TRAV_MIN_BLOCKS 10
 #endif
