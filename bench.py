@@ -308,6 +308,14 @@ def run_rt3(args):
         BYTES_PER_RAY_EXTEND = 68.0   # 48 B ray record read + 20 B hit record written
         BYTES_PER_RAY_PATH = 240.0    # whole wavefront segment, all stages (SURVEY 8d's figure restated for this layout)
         achieved = BYTES_PER_RAY_EXTEND * ext_rays / (ext_ms * 1e-3) / 1e9
+        # DRAM bytes of the extend launches of one step, from the committed ncu capture of this command
+        traffic = None
+        shares = os.path.join(ROOT, "profiles", "r01g_launch_shares.json")
+        if os.path.exists(shares) and (args.grid, args.width, args.height) == (708, 1920, 1080):
+            k = json.load(open(shares))["kernels"].get("k_traverse<0>")
+            if k:
+                traffic = {"bytes_per_step": (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6, "launches_per_step": k["launches"],
+                           "algorithmic_bytes_per_step": BYTES_PER_RAY_EXTEND * ext_rays / 2, "source": "profiles/r01g_launches.csv (ncu dram__bytes_read/write.sum)"}
         out = {
             "metric": METRIC, "value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -320,7 +328,7 @@ def run_rt3(args):
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "rt3::k_traverse<0> (extend, closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_ray": BYTES_PER_RAY_EXTEND,
                          "kernel_ms_per_step": ext_ms / 2, "kernel_Mrays_s": ext_rays / (ext_ms * 1e-3) / 1e6,
                          "kernel_share_of_step": ext_ms / tot_ms,
