@@ -50,6 +50,19 @@ RT3_HD void rt3_atomic_add64(unsigned long long* p, unsigned long long v) { atom
 RT3_HD void rt3_threadfence() { __threadfence(); }
 #endif
 
+// Queue records are touched once per stage: stream them through L2 (evict-first) so that the BVH
+// nodes and primitive records, which every ray re-reads, keep the L2 to themselves.
+#ifndef RT3_STREAM_HINTS
+#define RT3_STREAM_HINTS 1
+#endif
+#if defined(RT3_EMULATE) || !RT3_STREAM_HINTS
+template <class T> RT3_HD T rt3_ldcs(const T* p) { return *p; }
+template <class T> RT3_HD void rt3_stcs(T* p, T v) { *p = v; }
+#else
+template <class T> RT3_HD T rt3_ldcs(const T* p) { return __ldcs(p); }
+template <class T> RT3_HD void rt3_stcs(T* p, T v) { __stcs(p, v); }
+#endif
+
 namespace rt3 {
 
 // ------------------------------------------------------------------------------------ float3 ops

@@ -43,9 +43,9 @@ enum { TRAV_EXTEND = 0, TRAV_CONNECT = 1, TRAV_TRACE_CLOSEST = 2, TRAV_TRACE_ANY
 
 template <int MODE>
 RT3_HD void trav_begin(const TraverseArgs& a, uint32_t i, Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY)>& tr) {
-    const float4 r0 = a.rays.r0[(size_t)i * a.rays.stride];
-    const float4 r1 = a.rays.r1[(size_t)i * a.rays.stride];
-    const float4 r2 = a.rays.r2[(size_t)i * a.rays.stride];
+    const float4 r0 = rt3_ldcs(&a.rays.r0[(size_t)i * a.rays.stride]);
+    const float4 r1 = rt3_ldcs(&a.rays.r1[(size_t)i * a.rays.stride]);
+    const float4 r2 = rt3_ldcs(&a.rays.r2[(size_t)i * a.rays.stride]);
     tr.init(a.scene, v3(r0), v3(r1), r0.w, r1.w, r2.x);
 }
 
@@ -53,11 +53,11 @@ template <int MODE>
 RT3_HD void trav_end(const TraverseArgs& a, uint32_t i, const Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY)>& tr) {
     const HitRec h = tr.result(a.scene);
     if (MODE == TRAV_EXTEND) {
-        a.hit0[i] = make_float4(h.t, h.u, h.v, rt3_u2f((uint32_t)h.prim));
-        a.hit_inst[i] = h.inst;
+        rt3_stcs(&a.hit0[i], make_float4(h.t, h.u, h.v, rt3_u2f((uint32_t)h.prim)));
+        rt3_stcs(&a.hit_inst[i], h.inst);
     } else if (MODE == TRAV_CONNECT) {
         const uint32_t path = rt3_f2u(a.rays.r2[(size_t)i * a.rays.stride].y);
-        const float4 c = a.contrib[i];
+        const float4 c = rt3_ldcs(&a.contrib[i]);
         if (h.prim < 0) {  // unoccluded: result += radiance * last_attenuation (raygen.cu:59)
             float4 r = a.result[path];
             r.x = r.x + c.x; r.y = r.y + c.y; r.z = r.z + c.z;
@@ -71,8 +71,8 @@ RT3_HD void trav_end(const TraverseArgs& a, uint32_t i, const Trav<(MODE == TRAV
             }
         }
     } else {
-        a.hit0[2 * (size_t)i] = make_float4(h.t, h.u, h.v, rt3_u2f((uint32_t)h.prim));
-        a.hit0[2 * (size_t)i + 1] = make_float4(rt3_u2f((uint32_t)h.inst), 0.0f, 0.0f, 0.0f);
+        rt3_stcs(&a.hit0[2 * (size_t)i], make_float4(h.t, h.u, h.v, rt3_u2f((uint32_t)h.prim)));
+        rt3_stcs(&a.hit0[2 * (size_t)i + 1], make_float4(rt3_u2f((uint32_t)h.inst), 0.0f, 0.0f, 0.0f));
     }
 }
 
@@ -299,12 +299,12 @@ RT3_GLOBAL(k_generate, FrameParams f, Queues q) {
     const float3 dir = normalize(add(add(mul(ld3(f.U), dx), mul(ld3(f.V), dy)), ld3(f.W)));
     uint32_t pseed = seed;
     const float time = rnd(pseed);  // traceRadiance draws the ray time first (shader_common.h:64)
-    q.ray0[p] = make_float4(f.eye[0], f.eye[1], f.eye[2], 0.01f);
-    q.ray1[p] = make_float4(dir.x, dir.y, dir.z, 1e16f);
-    q.ray2[p] = make_float4(time, rt3_u2f(p), 0.0f, 0.0f);
-    q.st0[p] = make_float4(1.0f, 1.0f, 1.0f, rt3_u2f(pseed));
-    q.st1[p] = make_float4(1.0f, 1.0f, 1.0f, rt3_u2f(0u));
-    q.result[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    rt3_stcs(&q.ray0[p], make_float4(f.eye[0], f.eye[1], f.eye[2], 0.01f));
+    rt3_stcs(&q.ray1[p], make_float4(dir.x, dir.y, dir.z, 1e16f));
+    rt3_stcs(&q.ray2[p], make_float4(time, rt3_u2f(p), 0.0f, 0.0f));
+    rt3_stcs(&q.st0[p], make_float4(1.0f, 1.0f, 1.0f, rt3_u2f(pseed)));
+    rt3_stcs(&q.st1[p], make_float4(1.0f, 1.0f, 1.0f, rt3_u2f(0u)));
+    rt3_stcs(&q.result[p], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
     if (p == 0) *q.n_cur = rt3_n_;
 }
 
@@ -407,14 +407,14 @@ RT3_HD void shade_slot(const FrameParams& f, const TravScene& sc, const Queues& 
     float shadow_tmax = 0.0f, tshadow = 0.0f, next_time = 0.0f;
     uint32_t pseed = 0, path = 0, depth = 0;
     if (valid) {
-        const float4 r0 = q.ray0[i], r1 = q.ray1[i], r2 = q.ray2[i];
-        const float4 h0 = q.hit0[i];
-        const float4 s0 = q.st0[i], s1 = q.st1[i];
+        const float4 r0 = rt3_ldcs(&q.ray0[i]), r1 = rt3_ldcs(&q.ray1[i]), r2 = rt3_ldcs(&q.ray2[i]);
+        const float4 h0 = rt3_ldcs(&q.hit0[i]);
+        const float4 s0 = rt3_ldcs(&q.st0[i]), s1 = rt3_ldcs(&q.st1[i]);
         const float3 org = v3(r0), dir = v3(r1);
         const float time = r2.x;
         path = rt3_f2u(r2.y);
         HitRec h;
-        h.t = h0.x; h.u = h0.y; h.v = h0.z; h.prim = (int)rt3_f2u(h0.w); h.inst = q.hit_inst[i];
+        h.t = h0.x; h.u = h0.y; h.v = h0.z; h.prim = (int)rt3_f2u(h0.w); h.inst = rt3_ldcs(&q.hit_inst[i]);
         att = v3(s0);
         pseed = rt3_f2u(s0.w);
         const float3 last_att = v3(s1);
@@ -487,18 +487,18 @@ RT3_HD void shade_slot(const FrameParams& f, const TravScene& sc, const Queues& 
     }
     const uint32_t sslot = warp_append(q.n_shadow, push_shadow);
     if (push_shadow) {
-        q.sh0[sslot] = make_float4(P.x, P.y, P.z, 0.001f);
-        q.sh1[sslot] = make_float4(L.x, L.y, L.z, shadow_tmax);
-        q.sh2[sslot] = make_float4(tshadow, rt3_u2f(path), 0.0f, 0.0f);
-        q.sh3[sslot] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+        rt3_stcs(&q.sh0[sslot], make_float4(P.x, P.y, P.z, 0.001f));
+        rt3_stcs(&q.sh1[sslot], make_float4(L.x, L.y, L.z, shadow_tmax));
+        rt3_stcs(&q.sh2[sslot], make_float4(tshadow, rt3_u2f(path), 0.0f, 0.0f));
+        rt3_stcs(&q.sh3[sslot], make_float4(contrib.x, contrib.y, contrib.z, 0.0f));
     }
     const uint32_t rslot = warp_append(q.n_next, push_ray);
     if (push_ray) {
-        q.nray0[rslot] = make_float4(P.x, P.y, P.z, 0.01f);
-        q.nray1[rslot] = make_float4(ndir.x, ndir.y, ndir.z, 1e16f);
-        q.nray2[rslot] = make_float4(next_time, rt3_u2f(path), 0.0f, 0.0f);
-        q.nst0[rslot] = make_float4(att.x, att.y, att.z, rt3_u2f(pseed));
-        q.nst1[rslot] = make_float4(new_last.x, new_last.y, new_last.z, rt3_u2f(depth));
+        rt3_stcs(&q.nray0[rslot], make_float4(P.x, P.y, P.z, 0.01f));
+        rt3_stcs(&q.nray1[rslot], make_float4(ndir.x, ndir.y, ndir.z, 1e16f));
+        rt3_stcs(&q.nray2[rslot], make_float4(next_time, rt3_u2f(path), 0.0f, 0.0f));
+        rt3_stcs(&q.nst0[rslot], make_float4(att.x, att.y, att.z, rt3_u2f(pseed)));
+        rt3_stcs(&q.nst1[rslot], make_float4(new_last.x, new_last.y, new_last.z, rt3_u2f(depth)));
     }
 }
 
