@@ -80,7 +80,8 @@ int rt3_set_option(rt3_context_t ctx, const char* key, int value); /* tuning swi
 /* ---- geometry (BLAS) ------------------------------------------------------------------- */
 /* CUDAMesh(ctx, mesh) src/cuda/cuda_mesh.h:33-155: uploads vertex/index/normal/uv arrays and
  * builds the BLAS (there: optixAccelBuild + compaction; here: GPU LBVH -> compressed BVH8).
- * verts [num_keys][nv][3] (key 0 is used; vertex-key motion is SURVEY 8f/N2), idx [nt][3],
+ * verts [num_keys][nv][3]: num_keys > 1 = vertex-key (deformation) motion blur, keys spread evenly over ray
+ * time [0,1] like the reference's motionOptions (cuda_mesh.h:82-88), per-vertex linear interpolation; idx [nt][3],
  * normals [nv][3], uvs [nv][2] (both required, like the reference, Q11). */
 int rt3_mesh_create(rt3_context_t ctx, const float* verts, int num_keys, int nv, const int32_t* idx, int nt,
                     const float* normals, const float* uvs, rt3_handle_t* blas);

@@ -173,7 +173,8 @@ enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2 };
 
 struct Blas {
     int type = PRIM_TRI;
-    std::vector<f3> verts, normals;
+    std::vector<f3> verts, normals;    // verts: [vkeys][nv] (vertex-key motion, cuda_mesh.h:85-88: keys spread over time [0,1])
+    int vkeys = 1, nv = 0;
     std::vector<f2> uvs;
     std::vector<int32_t> idx;          // tris: 3 per prim
     std::vector<float> cr;             // spheres: 4 per prim; curves: control points 4 per cp
@@ -185,7 +186,8 @@ struct Blas {
     Box prim_box(int p) const {
         Box b;
         if (type == PRIM_TRI) {
-            b.grow(verts[idx[3 * p]]); b.grow(verts[idx[3 * p + 1]]); b.grow(verts[idx[3 * p + 2]]);
+            for (int k = 0; k < vkeys; k++)  // vertices move on straight segments between keys: the key boxes bound the motion
+                for (int c = 0; c < 3; c++) b.grow(verts[(size_t)k * nv + idx[3 * p + c]]);
         } else if (type == PRIM_SPHERE) {
             f3 c = {cr[4 * p], cr[4 * p + 1], cr[4 * p + 2]};
             float r = cr[4 * p + 3];
@@ -254,10 +256,24 @@ struct rt3o_scene {
     }
 
     // test one primitive of one BLAS in object space
-    static inline bool test_prim(const Blas& b, int p, f3 oo, f3 od, const RayShear& sh, float tmin, float tmax,
+    static inline bool test_prim(const Blas& b, int p, f3 oo, f3 od, const RayShear& sh, float tmin, float tmax, float time,
                                  float& t, float& u, float& v) {
         if (b.type == PRIM_TRI) {
-            return hit_triangle(oo, sh, b.verts[b.idx[3 * p]], b.verts[b.idx[3 * p + 1]], b.verts[b.idx[3 * p + 2]], tmin, tmax, t, u, v);
+            if (b.vkeys == 1)
+                return hit_triangle(oo, sh, b.verts[b.idx[3 * p]], b.verts[b.idx[3 * p + 1]], b.verts[b.idx[3 * p + 2]], tmin, tmax, t, u, v);
+            // vertex-key motion: per-vertex linear interpolation of the bracketing keys at the ray time
+            // (OptiX motion GAS semantics, timeBegin 0 / timeEnd 1, clamped; cuda_mesh.h:82-88)
+            const float tc = fminf(fmaxf(time, 0.0f), 1.0f);
+            const float f = tc * (float)(b.vkeys - 1);
+            int ki = (int)floorf(f);
+            if (ki > b.vkeys - 2) ki = b.vkeys - 2;
+            const float a = f - (float)ki, w = 1.0f - a;
+            f3 q[3];
+            for (int c = 0; c < 3; c++) {
+                const f3 v0 = b.verts[(size_t)ki * b.nv + b.idx[3 * p + c]], v1 = b.verts[(size_t)(ki + 1) * b.nv + b.idx[3 * p + c]];
+                q[c] = {w * v0.x + a * v1.x, w * v0.y + a * v1.y, w * v0.z + a * v1.z};
+            }
+            return hit_triangle(oo, sh, q[0], q[1], q[2], tmin, tmax, t, u, v);
         } else if (b.type == PRIM_SPHERE) {
             u = v = 0;
             return hit_sphere(oo, od, {b.cr[4 * p], b.cr[4 * p + 1], b.cr[4 * p + 2]}, b.cr[4 * p + 3], tmin, tmax, t);
@@ -281,7 +297,7 @@ struct rt3o_scene {
             RayShear sh = make_shear(od);
             auto visit_prim = [&](int p) -> bool {
                 float t, u, v;
-                if (!test_prim(b, p, oo, od, sh, tmin, tmax, t, u, v)) return false;
+                if (!test_prim(b, p, oo, od, sh, tmin, tmax, time, t, u, v)) return false;
                 if (better(t, ii, p, best)) {
                     best.t = t; best.u = u; best.v = v; best.prim = p; best.inst = ii;
                     tfar = t;
@@ -542,8 +558,9 @@ int rt3o_mesh_create(rt3o_scene* s, const float* verts, int num_keys, int nv, co
     auto b = std::make_unique<Blas>();
     b->type = PRIM_TRI;
     b->nprims = nt;
-    b->verts.resize(nv); b->normals.resize(nv); b->uvs.resize(nv);
-    std::memcpy(b->verts.data(), verts, sizeof(f3) * nv);  // key 0
+    b->vkeys = num_keys; b->nv = nv;
+    b->verts.resize((size_t)nv * num_keys); b->normals.resize(nv); b->uvs.resize(nv);
+    std::memcpy(b->verts.data(), verts, sizeof(f3) * (size_t)nv * num_keys);  // [key][vertex]; normals / uvs: key 0 (create_sbt binds the buffer start)
     std::memcpy(b->normals.data(), normals, sizeof(f3) * nv);
     std::memcpy(b->uvs.data(), uvs, sizeof(f2) * nv);
     b->idx.assign(idx, idx + 3 * nt);

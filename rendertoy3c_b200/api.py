@@ -119,10 +119,11 @@ class Context:
 
     # ---- geometry
     def mesh_create(self, verts, idx, normals, uvs):
-        v, n, t = _f32(verts), _f32(normals), _f32(uvs)
+        v, n, t = _f32(verts), _f32(normals), _f32(uvs)  # verts [nv,3] or [keys,nv,3] (vertex-key motion)
         i = np.ascontiguousarray(idx, dtype=np.int32)
         h = C.c_uint64()
-        self._chk(self.L.rt3_mesh_create(self.ctx, fptr(v), C.c_int(1), C.c_int(len(v)), iptr(i), C.c_int(len(i)), fptr(n), fptr(t), C.byref(h)))
+        keys, nv = (v.shape[0], v.shape[1]) if v.ndim == 3 else (1, len(v))
+        self._chk(self.L.rt3_mesh_create(self.ctx, fptr(v), C.c_int(keys), C.c_int(nv), iptr(i), C.c_int(len(i)), fptr(n), fptr(t), C.byref(h)))
         return h.value
 
     def spheres_create(self, cr):

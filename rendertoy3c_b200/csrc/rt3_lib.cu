@@ -25,7 +25,7 @@ using namespace rt3;
 namespace {
 
 struct Geometry {
-    uint32_t type = PRIM_TRI, nprims = 0;
+    uint32_t type = PRIM_TRI, nprims = 0, vkeys = 1, nv = 0;
     DevBuf<float> verts, normals, uvs;
     DevBuf<int32_t> idx, seg;
     DevBuf<float4> cr;
@@ -164,11 +164,13 @@ void ensure_blas(rt3_context* c, Geometry* g) {
     if (g->has_blas) return;
     DevBuf<float4> lo(g->nprims), hi(g->nprims);
     if (g->type == PRIM_TRI) RT3_LAUNCH_1D(k_tri_boxes, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, lo.p, hi.p);
+    else if (g->type == PRIM_TRI_MOTION) RT3_LAUNCH_1D(k_tri_boxes_motion, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, g->vkeys, g->nv, lo.p, hi.p);
     else if (g->type == PRIM_SPHERE) RT3_LAUNCH_1D(k_sphere_boxes, g->nprims, c->stream, (const float4*)g->cr.p, lo.p, hi.p);
     else RT3_LAUNCH_1D(k_curve_boxes, g->nprims, c->stream, (const float4*)g->cr.p, (const int32_t*)g->seg.p, lo.p, hi.p);
     build_bvh8(lo.p, hi.p, g->nprims, c->stream, g->nodes, g->order, g->bvh);
-    g->prims.alloc(3 * (size_t)g->nprims);
-    if (g->type == PRIM_TRI) RT3_LAUNCH_1D(k_pack_tris, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, (const uint32_t*)g->order.p, g->prims.p);
+    g->prims.alloc(3 * (size_t)g->nprims * g->vkeys);
+    if (g->type == PRIM_TRI_MOTION) RT3_LAUNCH_1D(k_pack_tris_motion, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, g->vkeys, g->nv, (const uint32_t*)g->order.p, g->prims.p);
+    else if (g->type == PRIM_TRI) RT3_LAUNCH_1D(k_pack_tris, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, (const uint32_t*)g->order.p, g->prims.p);
     else if (g->type == PRIM_SPHERE) RT3_LAUNCH_1D(k_pack_spheres, g->nprims, c->stream, (const float4*)g->cr.p, (const uint32_t*)g->order.p, g->prims.p);
     else RT3_LAUNCH_1D(k_pack_curves, g->nprims, c->stream, (const float4*)g->cr.p, (const int32_t*)g->seg.p, (const uint32_t*)g->order.p, g->prims.p);
     stream_sync(c->stream);
@@ -323,13 +325,15 @@ int rt3_mesh_create(rt3_context_t c, const float* verts, int num_keys, int nv, c
     RT3_REQUIRE(nv > 0 && nt > 0 && num_keys >= 1, RT3_ERR_INVALID, "mesh_create: empty mesh");
     for (size_t i = 0; i < 3 * (size_t)nt; i++) RT3_REQUIRE(idx[i] >= 0 && idx[i] < nv, RT3_ERR_INVALID, "mesh_create: index out of range");
     auto g = std::make_unique<Geometry>();
-    g->type = PRIM_TRI;
+    g->type = num_keys > 1 ? PRIM_TRI_MOTION : PRIM_TRI;  // motionOptions.numKeys = mesh.num_keys, cuda_mesh.h:85
+    g->vkeys = (uint32_t)num_keys;
+    g->nv = (uint32_t)nv;
     g->nprims = (uint32_t)nt;
-    g->verts.alloc(3 * (size_t)nv);
+    g->verts.alloc(3 * (size_t)nv * (size_t)num_keys);
     g->normals.alloc(3 * (size_t)nv);
     g->uvs.alloc(2 * (size_t)nv);
     g->idx.alloc(3 * (size_t)nt);
-    h2d(g->verts.p, verts, g->verts.bytes(), c->stream);  // key 0 (vertex-key motion: SURVEY 8f/N2)
+    h2d(g->verts.p, verts, g->verts.bytes(), c->stream);  // [key][vertex][3]
     h2d(g->normals.p, normals, g->normals.bytes(), c->stream);
     h2d(g->uvs.p, uvs, g->uvs.bytes(), c->stream);
     h2d(g->idx.p, idx, g->idx.bytes(), c->stream);
@@ -484,10 +488,10 @@ int rt3_accel_build(rt3_context_t c) {
     std::vector<BlasBounds> bb(ng + 1);
     for (size_t i = 0; i < ng; i++) {
         const Geometry& g = *c->geoms[i];
-        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p};
+        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p, g.vkeys};
         for (int k = 0; k < 3; k++) { bb[i].lo[k] = g.bvh.lo[k]; bb[i].hi[k] = g.bvh.hi[k]; }
     }
-    bt[ng] = BlasDev{c->m_nodes_p, c->m_prims_p, PRIM_TRI, c->m_bvh.num_prims, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bt[ng] = BlasDev{c->m_nodes_p, c->m_prims_p, PRIM_TRI, c->m_bvh.num_prims, nullptr, nullptr, nullptr, nullptr, nullptr, 1u};
     bb[ng] = merged_bounds;
     c->d_blas.alloc(bt.size());
     h2d(c->d_blas.p, bt.data(), sizeof(BlasDev) * bt.size(), c->stream);

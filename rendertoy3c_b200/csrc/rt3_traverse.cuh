@@ -18,7 +18,7 @@
 
 namespace rt3 {
 
-enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2 };
+enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2, PRIM_TRI_MOTION = 3 };  // 3: triangles with vertex keys (deformation blur)
 #define RT3_STACK_SIZE 64
 #ifndef RT3_COOP_CAP
 #define RT3_COOP_CAP 32   // (owner, triangle) pairs a warp shares per round
@@ -43,6 +43,7 @@ struct BlasDev {             // per geometry, device-resident table entry
     const float* uvs;        // mesh [nv][2]
     const float4* cr;        // spheres [n] / curve control points [ncp]
     const int32_t* seg;      // curves [nseg]
+    uint32_t vkeys;          // PRIM_TRI_MOTION: vertex keys per triangle record (record = vkeys x 3 float4)
 };
 
 struct InstanceDev {         // traversal record (64 B)
@@ -514,7 +515,7 @@ struct Trav {
                 set_space(oo, od, time);
             }
             const BlasDev* bl = sc.blas + in->blas;
-            nodes = bl->nodes; prims = bl->prims; ptype = bl->type;
+            nodes = bl->nodes; prims = bl->prims; ptype = bl->type == PRIM_TRI_MOTION ? (PRIM_TRI_MOTION | (bl->vkeys << 8)) : bl->type;
             cur_inst = in->identity == 2u ? RT3_MERGED_INST : inst;  // 2 = the merged world BLAS pseudo-instance
             ng = make_uint2(0u, 0x80000000u);
             tg = make_uint2(0u, 0u);
@@ -523,13 +524,31 @@ struct Trav {
 #ifdef RT3_STATS
         c_prims++;
 #endif
-        const float4* pr = prims + 3u * pi;
+        const float4* pr = prims + 3u * ((ptype & 0xffu) == PRIM_TRI_MOTION ? (ptype >> 8) * pi : pi);
         const float4 a = rt3_ldg(pr), b = rt3_ldg(pr + 1);
         bool got = false;
         if (ptype == PRIM_TRI) {
             const float4 c = rt3_ldg(pr + 2);
             float t, u, v;
             if (test_triangle(o, shear(), v3(a), v3(b), v3(c), t, u, v)) got = accept(sc, t, u, v, (int)rt3_f2u(a.w));
+        } else if ((ptype & 0xffu) == PRIM_TRI_MOTION) {
+            // vertex-key motion (the reference's num_keys GAS, cuda_mesh.h:82-88): lerp the bracketing keys at the ray time
+            const uint32_t vk = ptype >> 8;
+            const float tc = fminf(fmaxf(ray_time(), 0.0f), 1.0f);
+            const float f = tc * (float)(vk - 1u);
+            int ki = (int)floorf(f);
+            if (ki > (int)vk - 2) ki = (int)vk - 2;
+            const float al = f - (float)ki, w = 1.0f - al;
+            const float4* k0 = prims + 3u * (vk * pi + (uint32_t)ki);
+            const float4 id4 = rt3_ldg(prims + 3u * vk * pi);
+            float3 q[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float4 p0 = rt3_ldg(k0 + c), p1 = rt3_ldg(k0 + 3 + c);
+                q[c] = v3(w * p0.x + al * p1.x, w * p0.y + al * p1.y, w * p0.z + al * p1.z);
+            }
+            float t, u, v;
+            if (test_triangle(o, shear(), q[0], q[1], q[2], t, u, v)) got = accept(sc, t, u, v, (int)rt3_f2u(id4.w));
         } else if (ptype == PRIM_SPHERE) {
             float ta, tb;
             if (test_sphere(o, cur_d(), v3(a), a.w, ta, tb)) {

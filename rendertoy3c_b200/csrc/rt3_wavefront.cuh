@@ -162,6 +162,31 @@ RT3_GLOBAL(k_tri_boxes, const float* verts, const int32_t* idx, float4* lo, floa
     lo[p] = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.0f);
     hi[p] = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.0f);
 }
+// vertex-key meshes: verts [vkeys][nv][3]; a vertex moves on straight segments between keys, so the
+// union of the key boxes bounds the triangle at every time
+RT3_GLOBAL(k_tri_boxes_motion, const float* verts, const int32_t* idx, uint32_t vkeys, uint32_t nv, float4* lo, float4* hi) {
+    const uint32_t p = RT3_THREAD_ID();
+    if (p >= rt3_n_) return;
+    float3 mn = v3(3e38f, 3e38f, 3e38f), mx = v3(-3e38f, -3e38f, -3e38f);
+    for (uint32_t k = 0; k < vkeys; k++)
+        for (int c = 0; c < 3; c++) {
+            const float3 a = ld3(verts + 3 * ((size_t)k * nv + (size_t)idx[3 * (size_t)p + c]));
+            mn = v3(fminf(mn.x, a.x), fminf(mn.y, a.y), fminf(mn.z, a.z));
+            mx = v3(fmaxf(mx.x, a.x), fmaxf(mx.y, a.y), fmaxf(mx.z, a.z));
+        }
+    lo[p] = make_float4(mn.x, mn.y, mn.z, 0.0f);
+    hi[p] = make_float4(mx.x, mx.y, mx.z, 0.0f);
+}
+RT3_GLOBAL(k_pack_tris_motion, const float* verts, const int32_t* idx, uint32_t vkeys, uint32_t nv, const uint32_t* order, float4* out) {
+    const uint32_t j = RT3_THREAD_ID();
+    if (j >= rt3_n_) return;
+    const uint32_t p = order[j];
+    for (uint32_t k = 0; k < vkeys; k++)
+        for (int c = 0; c < 3; c++) {
+            const float3 a = ld3(verts + 3 * ((size_t)k * nv + (size_t)idx[3 * (size_t)p + c]));
+            out[3 * ((size_t)vkeys * j + k) + c] = make_float4(a.x, a.y, a.z, (k == 0 && c == 0) ? rt3_u2f(p) : 0.0f);
+        }
+}
 RT3_GLOBAL(k_sphere_boxes, const float4* cr, float4* lo, float4* hi) {
     const uint32_t p = RT3_THREAD_ID();
     if (p >= rt3_n_) return;
@@ -336,7 +361,7 @@ RT3_HD LocalGeometry local_geometry(const TravScene& sc, const HitRec& h, float3
     const BlasDev* b = sc.blas + in->blas;
     const float t1 = sc.hitgroups[h.inst].t1;
     float3 n_obj;
-    if (b->type == PRIM_TRI) {  // closehit_radiance.cu:66-73
+    if (b->type == PRIM_TRI || b->type == PRIM_TRI_MOTION) {  // closehit_radiance.cu:66-73 (key-0 normals / uvs: create_sbt binds the buffer start)
         const int i0 = b->idx[3 * (size_t)h.prim], i1 = b->idx[3 * (size_t)h.prim + 1], i2 = b->idx[3 * (size_t)h.prim + 2];
         const float w0 = 1.0f - h.u - h.v;
         n_obj = add(add(mul(ld3(b->normals + 3 * (size_t)i0), w0), mul(ld3(b->normals + 3 * (size_t)i1), h.u)), mul(ld3(b->normals + 3 * (size_t)i2), h.v));

@@ -24,6 +24,7 @@ class Geometry:
     uvs: np.ndarray = None        # mesh [nv,2]
     cr: np.ndarray = None         # spheres [n,4] / curves control points [ncp,4]
     seg: np.ndarray = None        # curves [nseg] i32 first control point
+    vert_keys: np.ndarray = None  # mesh, optional [keys,nv,3]: vertex-key (deformation) motion; verts = key 0
 
     @property
     def nprims(self):
@@ -79,7 +80,7 @@ def replay(desc, be):
     handles = []
     for g in desc.geoms:
         if g.kind == "mesh":
-            handles.append(be.mesh_create(g.verts, g.idx, g.normals, g.uvs))
+            handles.append(be.mesh_create(g.verts if g.vert_keys is None else g.vert_keys, g.idx, g.normals, g.uvs))
         elif g.kind == "spheres":
             handles.append(be.spheres_create(g.cr))
         else:
@@ -344,8 +345,26 @@ def motion(n_inst=64, blob_n=224, n_spheres=256, n_curves=10000, width=1920, hei
     return SceneDesc("C4_motion", geoms, inst, [], cam, width, height, spp, max_depth)
 
 
+def deforming(blob_n=24, width=160, height=90, spp=16, max_depth=6, keys=3):
+    """vertex-key motion: a blob whose vertices move through `keys` key-frames over the
+    shutter, next to a static copy (transformed instance), above an emissive-lit floor."""
+    blob = grid_mesh(blob_n, blob_n, _blob_pos)
+    vk = np.stack([blob.verts * np.float32(1.0 + 0.25 * k) + np.array([0.15 * k, 0.1 * k * k, 0.0], np.float32) for k in range(keys)]).astype(np.float32)
+    moving = Geometry("mesh", verts=np.ascontiguousarray(vk[0]), idx=blob.idx, normals=blob.normals, uvs=blob.uvs, vert_keys=vk)
+    geoms = [moving, blob]
+    stat = IDENTITY.copy()
+    stat[[3, 7, 11]] = (1.4, 0.0, 0.0)
+    inst = [Instance(0, diffuse=(0.8, 0.4, 0.3)), Instance(1, xform=stat, diffuse=(0.3, 0.5, 0.8))]
+    geoms.append(_quad_mesh([[[-2, 2.5, -2], [2, 2.5, -2], [2, 2.5, 2], [-2, 2.5, 2]]]))
+    inst.append(Instance(2, diffuse=(0.8, 0.8, 0.8), emission=(8.0, 8.0, 7.0)))
+    geoms.append(_quad_mesh([[[-4, -0.8, -4], [-4, -0.8, 4], [4, -0.8, 4], [4, -0.8, -4]]]))
+    inst.append(Instance(3, diffuse=(0.6, 0.6, 0.6)))
+    cam = Camera(eye=(0.7, 0.8, 3.6), lookat=(0.7, 0.1, 0.0), fovy=45.0)
+    return SceneDesc("N2_deforming", geoms, inst, [], cam, width, height, spp, max_depth)
+
+
 def by_name(name, **kw):
-    return {"cornell": cornell, "terrain": terrain, "instanced": instanced, "motion": motion}[name](**kw)
+    return {"cornell": cornell, "terrain": terrain, "instanced": instanced, "motion": motion, "deforming": deforming}[name](**kw)
 
 
 def write_obj(desc, path):

@@ -77,7 +77,8 @@ class OracleScene:
     def mesh_create(self, verts, idx, normals, uvs):
         v, n, t = _f32(verts), _f32(normals), _f32(uvs)
         i = np.ascontiguousarray(idx, dtype=np.int32)
-        return self._chk(self.L.rt3o_mesh_create(self.s, fptr(v), 1, C.c_int(len(v)), iptr(i), C.c_int(len(i)), fptr(n), fptr(t)))
+        keys, nv = (v.shape[0], v.shape[1]) if v.ndim == 3 else (1, len(v))
+        return self._chk(self.L.rt3o_mesh_create(self.s, fptr(v), C.c_int(keys), C.c_int(nv), iptr(i), C.c_int(len(i)), fptr(n), fptr(t)))
 
     def spheres_create(self, cr):
         c = _f32(cr)

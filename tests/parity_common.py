@@ -12,6 +12,7 @@ SMALL = {
     "terrain": lambda: scenes.terrain(n=40, width=80, height=48, tex_size=64),
     "instanced": lambda: scenes.instanced(n_inst=27, blob_n=10, n_spheres=16, width=80, height=48),
     "motion": lambda: scenes.motion(n_inst=8, blob_n=8, n_spheres=10, n_curves=50, width=80, height=48),
+    "deforming": lambda: scenes.deforming(blob_n=10, width=80, height=48),
 }
 
 

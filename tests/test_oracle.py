@@ -246,3 +246,23 @@ def test_oracle_golden_fixture():
     gold = json.load(open(os.path.join(GOLD, "oracle_golden.json")))
     now = make_golden.compute(ob)
     assert now == gold
+
+
+def test_vertex_key_motion_analytic():
+    """N2: a unit triangle sliding +2 in x over the shutter (2 keys); a fixed ray at x = 1.5 only hits it
+    while the interpolated triangle covers that x, and 3 keys interpolate piecewise."""
+    from rendertoy3c_b200.scenes import IDENTITY
+    tri0 = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    keys = np.stack([tri0, tri0 + np.array([2, 0, 0], np.float32)])
+    o = ob.OracleScene()
+    h = o.mesh_create(keys, np.array([[0, 1, 2]], np.int32), np.tile([[0, 0, 1]], (3, 1)), np.zeros((3, 2)))
+    o.append_instance(h, IDENTITY)
+    o.accel_build()
+    r = np.zeros(5, RAY_DTYPE)
+    r["o"] = [1.6, 0.2, -1]; r["d"] = [0, 0, 1]; r["tmin"] = 0; r["tmax"] = 10
+    r["time"] = [0.0, 0.3, 0.5, 0.75, 1.0]          # triangle spans x in [2t, 2t+1-y]: covers 1.6 (y=0.2) for t in (0.4, 0.8)
+    hits = o.trace(r, accel=0)
+    assert list(hits["prim"] >= 0) == [False, False, True, True, False]
+    assert np.allclose(hits["t"][2:4], 1.0)
+    assert np.allclose(hits["u"][2], 1.6 - 1.0) and np.allclose(hits["u"][3], 1.6 - 1.5)   # u = weight of v1 = x offset in the moved triangle
+    assert o.trace(r, accel=1).tobytes() == hits.tobytes()

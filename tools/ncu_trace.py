@@ -14,7 +14,8 @@ from rendertoy3c_b200.api import Context, camera_rays  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 708
 w, h = 1920, 1080
-d = scenes.terrain(n=n, width=w, height=h, tex_size=64)
+scene = os.environ.get("SCENE", "terrain")
+d = scenes.terrain(n=n, width=w, height=h, tex_size=64) if scene == "terrain" else (scenes.instanced(width=w, height=h) if scene == "instanced" else scenes.motion(width=w, height=h))
 g = Context(0)
 scenes.replay(d, g)
 uvw = g.camera_uvw(d.camera.eye, d.camera.lookat, d.camera.up, d.camera.fovy, w / h)
@@ -30,6 +31,8 @@ dirs[:, 1] = np.abs(dirs[:, 1]) * 0.7
 dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
 inc["d"] = dirs
 inc["tmin"] = 0.01
+inc["time"] = rng.rand(len(inc)).astype(np.float32)
+prim["time"] = rng.rand(len(prim)).astype(np.float32)
 
 
 def run(rays, any_hit, reps=3):
