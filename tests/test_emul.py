@@ -45,3 +45,14 @@ def test_committed_golden_vectors(emul_lib, name):
     from parity_common import check_golden
     with Context(0, lib_path=emul_lib) as e:
         check_golden(e, name)
+
+
+@pytest.mark.parametrize("offset", [0.0, 4096.0])
+def test_adversarial_geometry_bit_exact(emul_lib, offset):
+    import adversarial
+    desc, off = adversarial.make_scene(offset)
+    with Context(0, lib_path=emul_lib) as e:
+        o = build_pair(desc, e)
+        ho = check_trace(e, o, adversarial.make_rays(off), accel=0)
+        assert (ho["prim"] >= 0).mean() > 0.1
+        check_render(e, o, desc, subframes=1)

@@ -80,3 +80,15 @@ def test_empty_and_ragged_batches(product_lib):
         for n in (1, 31, 33, 1000):                     # not multiples of the warp size
             rays = random_rays(desc, n, 100 + n)
             check_trace(g, o, rays, accel=0)
+
+
+@pytest.mark.parametrize("offset", [0.0, 4096.0])
+def test_adversarial_geometry_bit_exact(product_lib, offset):
+    """ties, degenerate triangles, flat boxes, far-from-origin scene, axis-parallel and in-plane rays"""
+    import adversarial
+    desc, off = adversarial.make_scene(offset)
+    with Context(0) as g:
+        o = build_pair(desc, g)
+        ho = check_trace(g, o, adversarial.make_rays(off, n=20000), accel=0)
+        assert (ho["prim"] >= 0).mean() > 0.1
+        check_render(g, o, desc, subframes=2)
