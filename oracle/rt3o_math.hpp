@@ -43,7 +43,9 @@ static inline float length(f3 v) { return sqrtf(dot(v, v)); }
 static inline f3 normalize(f3 v) { float invLen = 1.0f / sqrtf(dot(v, v)); return v * invLen; }
 // sutil/vec_math.h:582-585
 static inline f3 faceforward(f3 n, f3 i, f3 nref) { return n * copysignf(1.0f, dot(i, nref)); }
-static inline float clampf(float x, float a, float b) { return fmaxf(a, fminf(x, b)); }
+// clamp(NaN, 0, 1) = 0: nvcc compiles the reference's fmaxf(0, fminf(x, 1)) (cuda/helpers.h:50,59) to a
+// saturating move, which maps NaN to +0, so NaN pixels of the reference come out black, not white
+static inline float clampf(float x, float a, float b) { return x != x ? a : fmaxf(a, fminf(x, b)); }
 static inline float get(f3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
 
 // ---------------------------------------------------------------- RNG (cuda/random.h)

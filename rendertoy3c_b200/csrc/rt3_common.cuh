@@ -167,16 +167,17 @@ RT3_HD float to_srgb1(float c) {
     const float powed = powf(c, invGamma);
     return c < 0.0031308f ? 12.92f * c : 1.055f * powed - 0.055f;
 }
+RT3_HD float clamp01(float x) { return x != x ? 0.0f : fmaxf(0.0f, fminf(x, 1.0f)); }  // NaN -> 0, as the saturating move nvcc emits for the reference
 RT3_HD uint32_t quantize_u8(float x) {
-    x = fmaxf(0.0f, fminf(x, 1.0f));
+    x = clamp01(x);
     const uint32_t v = (uint32_t)(x * 256.0f);
     return v < 255u ? v : 255u;
 }
 RT3_HD uchar4 make_color(float3 c) {
     uchar4 o;
-    o.x = (unsigned char)quantize_u8(to_srgb1(fmaxf(0.0f, fminf(c.x, 1.0f))));
-    o.y = (unsigned char)quantize_u8(to_srgb1(fmaxf(0.0f, fminf(c.y, 1.0f))));
-    o.z = (unsigned char)quantize_u8(to_srgb1(fmaxf(0.0f, fminf(c.z, 1.0f))));
+    o.x = (unsigned char)quantize_u8(to_srgb1(clamp01(c.x)));
+    o.y = (unsigned char)quantize_u8(to_srgb1(clamp01(c.y)));
+    o.z = (unsigned char)quantize_u8(to_srgb1(clamp01(c.z)));
     o.w = 255;
     return o;
 }

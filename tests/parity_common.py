@@ -73,8 +73,10 @@ def check_render(backend, oracle, desc, subframes=2, spl=8, width=None, height=N
         backend.launch_subframe(rs)
         oracle.launch_subframe(rs)
     ab, ao = backend.download_accum(), oracle.download_accum()
-    assert np.array_equal(ab.view(np.uint32), ao.view(np.uint32)), \
-        "accumulation buffer not bit-identical to the oracle (%d of %d floats differ)" % ((ab.view(np.uint32) != ao.view(np.uint32)).sum(), ab.size)
+    # bit-identical, except that a NaN is a NaN: x86 and the GPU canonicalise NaN payloads differently
+    # (the faithful estimator does produce NaNs: zero-area lights, cos = 0 in the Q2 weight)
+    diff = (ab.view(np.uint32) != ao.view(np.uint32)) & ~(np.isnan(ab) & np.isnan(ao))
+    assert not diff.any(), "accumulation buffer not bit-identical to the oracle (%d of %d floats differ)" % (diff.sum(), ab.size)
     fb, fo = backend.download_frame(), oracle.download_frame()
     assert np.abs(fb.astype(int) - fo.astype(int)).max() <= 1, "8-bit frame differs by more than 1 LSB (powf)"
     sb, so = backend.stats(), oracle.stats()
