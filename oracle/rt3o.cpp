@@ -410,6 +410,110 @@ struct rt3o_scene {
         N = normalize(n);
     }
 
+
+    // ---------------------------------------------------------------------------------- CORRECTED mode (mode = 1)
+    // the same stages with the estimator errors Q2-Q5, Q7, Q8 fixed — unbiased
+    // Lambertian path tracing with uniform-light NEE and two-strategy MIS (power heuristic):
+    //   * per-sample independent stream: seed = tea<4>(pixel, subframe * spl + k)            (Q8)
+    //   * one ray time per path, drawn after the jitter                                        (Q7)
+    //   * throughput *= albedo (f * cos / pdf of the cosine-sampled Lambert lobe)              (Q2)
+    //   * NEE: Le * (albedo/pi) * cos_s * w / pdf_light, pdf_light = dist^2 / (N * area * cos_l),
+    //     weighted by the throughput BEFORE this bounce's BSDF factor                          (Q3, Q4)
+    //   * BSDF-sampled emitter hits count at every depth with the complementary MIS weight     (Q3)
+    //   * Russian roulette with p = min(lum(throughput), 1)                                    (Q5)
+    // Emissive meshes must be identity instances (the light list holds object-space vertices, Q15).
+    f3 render_pixel_corrected(const rt3_render_settings& rs, uint32_t x, uint32_t y, int accel, uint64_t cnt[3]) const {
+        const uint32_t w = rs.width, h = rs.height;
+        const f3 eye = {rs.eye[0], rs.eye[1], rs.eye[2]}, U = {rs.U[0], rs.U[1], rs.U[2]}, V = {rs.V[0], rs.V[1], rs.V[2]},
+                 W = {rs.W[0], rs.W[1], rs.W[2]};
+        const f3 miss = {rs.miss_color[0], rs.miss_color[1], rs.miss_color[2]};
+        const int max_depth = rs.max_depth > 0 ? rs.max_depth : (1 << 30);
+        const uint32_t nl = (uint32_t)lights.size();
+        const float inv_pi = (float)(1.0 / 3.14159265358979323846);
+        f3 result = {0, 0, 0};
+        for (uint32_t k = 0; k < rs.samples_per_launch; k++) {
+            uint32_t seed = tea4(y * w + x, rs.subframe_index * rs.samples_per_launch + k);
+            const float jx = rnd(seed);
+            const float jy = rnd(seed);
+            const float time = rnd(seed);
+            const float dx = 2.0f * (((float)x + jx) / (float)w) - 1.0f;
+            const float dy = 2.0f * (((float)y + jy) / (float)h) - 1.0f;
+            f3 dir = normalize(dx * U + dy * V + W);
+            f3 org = eye;
+            f3 beta = {1, 1, 1};
+            f3 L = {0, 0, 0};
+            float pdf_prev = 0.0f;
+            int depth = 0;
+            for (;;) {
+                cnt[depth == 0 ? 0 : 1]++;
+                Hit hit = trace(org, dir, 0.01f, 1e16f, time, false, accel);
+                if (hit.prim < 0) { L = L + beta * miss; break; }
+                const Instance& in = inst[hit.inst];
+                f3 N;
+                f2 uv;
+                local_geometry(hit, org, dir, time, N, uv);
+                const f3 Ns = faceforward(N, -dir, N);
+                const f3 P = org + hit.t * dir;
+                if (in.emission.x != 0.0f || in.emission.y != 0.0f || in.emission.z != 0.0f) {
+                    float wgt = 1.0f;
+                    if (depth > 0) {  // BSDF-sampled emitter hit: weight against the NEE strategy
+                        const Blas& b = *blas[in.blas];
+                        const f3 v0 = b.verts[b.idx[3 * hit.prim]], v1 = b.verts[b.idx[3 * hit.prim + 1]], v2 = b.verts[b.idx[3 * hit.prim + 2]];
+                        const f3 nrm = cross(v1 - v0, v2 - v0);
+                        const float area = 0.5f * length(nrm);
+                        const float cos_l = fabsf(dot(normalize(nrm), dir));
+                        const float dist2 = hit.t * hit.t * dot(dir, dir);
+                        const float pdf_light = dist2 / ((float)nl * area * cos_l);
+                        wgt = power_heuristic(pdf_prev, pdf_light);
+                    }
+                    L = L + beta * in.emission * wgt;
+                }
+                const f3 albedo = in.tex >= 0 ? fetch_texture(in.tex, uv.x, uv.y) : in.diffuse;
+                // next event estimation
+                const Light& lt = lights[(int)(rnd(seed) * (float)nl)];
+                const float u = rnd(seed);
+                const float v = rnd(seed);
+                const float su0 = sqrtf(u);
+                const float b0 = 1.0f - su0, b1 = v * su0;
+                const f3 lpos = b0 * lt.v0 + b1 * lt.v1 + (1.0f - b0 - b1) * lt.v2;
+                const f3 dl = lpos - P;
+                const float dist2 = dot(dl, dl);
+                if (dist2 > 1e-10f) {
+                    const float dist = sqrtf(dist2);
+                    const f3 Ld = dl / dist;
+                    const float cos_s = dot(Ns, Ld);
+                    const float cos_l = fabsf(dot(Ld, lt.normal));
+                    if (cos_s > 0.0f && cos_l > 0.0f && lt.area > 0.0f) {
+                        const float pdf_light = dist2 / ((float)nl * lt.area * cos_l);
+                        const float pdf_bsdf = cos_s * inv_pi;
+                        const float wgt = power_heuristic(pdf_light, pdf_bsdf);
+                        const f3 contrib = beta * albedo * lt.emission * (inv_pi * cos_s * wgt / pdf_light);
+                        cnt[2]++;
+                        Hit sh = trace(P, Ld, 0.001f, dist - 0.01f, time, true, accel);
+                        if (sh.prim < 0) L = L + contrib;
+                    }
+                }
+                // BSDF sample
+                const float u1 = rnd(seed);
+                const float u2 = rnd(seed);
+                const f3 w_in = sample_cosine_hemisphere(u1, u2);
+                if (!(w_in.z > 0.0f)) break;
+                pdf_prev = w_in.z * inv_pi;
+                Onb onb(Ns);
+                dir = onb.inverse_transform(w_in);
+                org = P;
+                beta = beta * albedo;
+                const float p = fminf(beta.x * 0.30f + beta.y * 0.59f + beta.z * 0.11f, 1.0f);
+                if (rnd(seed) > p) break;
+                beta = beta / p;
+                ++depth;
+                if (depth >= max_depth) break;
+            }
+            result = result + L;
+        }
+        return result / (float)rs.samples_per_launch;
+    }
+
     // one pixel, one launch: returns result/spl (raygen.cu:28-76)
     f3 render_pixel(const rt3_render_settings& rs, uint32_t x, uint32_t y, int accel, uint64_t cnt[3]) const {
         const uint32_t w = rs.width, h = rs.height;
@@ -688,7 +792,7 @@ int rt3o_launch_subframe(rt3o_scene* s, const rt3_render_settings* rs, int nthre
         int bx = (tile % tx) * 16, by = (tile / tx) * 16;
         for (int y = by; y < std::min(by + 16, H); y++)
             for (int x = bx; x < std::min(bx + 16, W); x++) {
-                f3 c = s->render_pixel(*rs, (uint32_t)x, (uint32_t)y, 1, cnt);
+                f3 c = rs->mode == 1 ? s->render_pixel_corrected(*rs, (uint32_t)x, (uint32_t)y, 1, cnt) : s->render_pixel(*rs, (uint32_t)x, (uint32_t)y, 1, cnt);
                 size_t pi = (size_t)y * W + x;
                 float* a = &s->accum[4 * pi];
                 if (rs->accum_mode == 0) {  // raygen.cu:75-86

@@ -72,7 +72,7 @@ def camera_uvw(eye, lookat, up, fovy, aspect, L=None):
     return U, V, W
 
 
-def make_settings(desc, uvw, subframe_index=0, samples_per_launch=8, accum_mode=0, max_depth=None, width=None, height=None):
+def make_settings(desc, uvw, subframe_index=0, samples_per_launch=8, accum_mode=0, max_depth=None, width=None, height=None, mode=0, miss=0.01):
     """RenderSettings for a SceneDesc (src/shader/shader_data.h:100-112 + handleCameraUpdate src/wavefront.cpp:167-176)."""
     rs = RenderSettings()
     rs.width = width or desc.width
@@ -83,9 +83,9 @@ def make_settings(desc, uvw, subframe_index=0, samples_per_launch=8, accum_mode=
     for i in range(3):
         rs.eye[i] = float(np.float32(desc.camera.eye[i]))
         rs.U[i], rs.V[i], rs.W[i] = float(U[i]), float(V[i]), float(W[i])
-        rs.miss_color[i] = 0.01
+        rs.miss_color[i] = miss
     rs.max_depth = desc.max_depth if max_depth is None else max_depth
-    rs.mode = 0
+    rs.mode = mode  # 0 = REFERENCE_FAITHFUL, 1 = CORRECTED
     rs.accum_mode = accum_mode
     return rs
 

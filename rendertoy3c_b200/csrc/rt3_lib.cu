@@ -488,10 +488,10 @@ int rt3_accel_build(rt3_context_t c) {
     std::vector<BlasBounds> bb(ng + 1);
     for (size_t i = 0; i < ng; i++) {
         const Geometry& g = *c->geoms[i];
-        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p, g.vkeys};
+        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p, g.vkeys, g.verts.p};
         for (int k = 0; k < 3; k++) { bb[i].lo[k] = g.bvh.lo[k]; bb[i].hi[k] = g.bvh.hi[k]; }
     }
-    bt[ng] = BlasDev{c->m_nodes_p, c->m_prims_p, PRIM_TRI, c->m_bvh.num_prims, nullptr, nullptr, nullptr, nullptr, nullptr, 1u};
+    bt[ng] = BlasDev{c->m_nodes_p, c->m_prims_p, PRIM_TRI, c->m_bvh.num_prims, nullptr, nullptr, nullptr, nullptr, nullptr, 1u, nullptr};
     bb[ng] = merged_bounds;
     c->d_blas.alloc(bt.size());
     h2d(c->d_blas.p, bt.data(), sizeof(BlasDev) * bt.size(), c->stream);
@@ -614,7 +614,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
     RT3_REQUIRE(c->built, RT3_ERR_STATE, "launch_subframe: rt3_accel_build has not been called");
     RT3_REQUIRE(c->nlights > 0, RT3_ERR_STATE, "launch_subframe: no lights set (Q17)");
     RT3_REQUIRE(rs->width > 0 && rs->height > 0 && rs->samples_per_launch > 0, RT3_ERR_INVALID, "launch_subframe: bad film settings");
-    RT3_REQUIRE(rs->mode == 0, RT3_ERR_UNSUPPORTED, "launch_subframe: only mode 0 (REFERENCE_FAITHFUL) exists");
+    RT3_REQUIRE(rs->mode == 0 || rs->mode == 1, RT3_ERR_UNSUPPORTED, "launch_subframe: mode must be 0 (REFERENCE_FAITHFUL) or 1 (CORRECTED)");
     const uint64_t paths64 = (uint64_t)rs->width * rs->height * rs->samples_per_launch;
     RT3_REQUIRE(paths64 < 0xfffffff0ull, RT3_ERR_INVALID, "launch_subframe: too many paths per launch");
     const uint32_t P = (uint32_t)paths64;
@@ -625,7 +625,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
     FrameParams f;
     f.width = rs->width; f.height = rs->height; f.spl = rs->samples_per_launch; f.subframe = rs->subframe_index;
     for (int k = 0; k < 3; k++) { f.eye[k] = rs->eye[k]; f.U[k] = rs->U[k]; f.V[k] = rs->V[k]; f.W[k] = rs->W[k]; f.miss[k] = rs->miss_color[k]; }
-    f.max_depth = rs->max_depth; f.accum_mode = rs->accum_mode;
+    f.max_depth = rs->max_depth; f.accum_mode = rs->accum_mode; f.mode = rs->mode;
     f.lights = c->d_lights.p; f.nlights = c->nlights; f.tex = c->d_tex.p;
     const TravScene sc = c->trav_scene();
 
@@ -667,6 +667,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
         a.count_ptr = q.n_cur; a.count = 0; a.fetch = cnt + 2 * M + depth;
         a.hit0 = q.hit0; a.hit_inst = q.hit_inst; a.contrib = nullptr; a.result = nullptr;
         a.stat = c->d_stats.p + (depth == 0 ? 0 : 1);
+        a.faithful = 0;
         launch_traverse<TRAV_EXTEND>(c, a);
         if (timing) event_record(e1, c->stream);
 #ifdef RT3_EMULATE
@@ -683,6 +684,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
         s.count_ptr = q.n_shadow; s.count = 0; s.fetch = cnt + 3 * M + depth;
         s.hit0 = nullptr; s.hit_inst = nullptr; s.contrib = q.sh3; s.result = q.result;
         s.stat = c->d_stats.p + 2;
+        s.faithful = rs->mode == 0 ? 1u : 0u;
         launch_traverse<TRAV_CONNECT>(c, s);
         if (timing) {
             event_record(e3, c->stream);
@@ -721,7 +723,7 @@ int rt3_trace_device(rt3_context_t c, const void* d_rays, int n, int any_hit, vo
     const float4* r = (const float4*)d_rays;
     a.rays = RayPlanes{r, r + 1, r + 2, 3u};
     a.count_ptr = nullptr; a.count = (uint32_t)n; a.fetch = c->trace_fetch.p;
-    a.hit0 = (float4*)d_hits; a.hit_inst = nullptr; a.contrib = nullptr; a.result = nullptr; a.stat = nullptr;
+    a.hit0 = (float4*)d_hits; a.hit_inst = nullptr; a.contrib = nullptr; a.result = nullptr; a.stat = nullptr; a.faithful = 0;
     if (any_hit) launch_traverse<TRAV_TRACE_ANY>(c, a);
     else launch_traverse<TRAV_TRACE_CLOSEST>(c, a);
     RT3_API_END

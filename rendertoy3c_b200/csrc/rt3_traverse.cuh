@@ -44,6 +44,7 @@ struct BlasDev {             // per geometry, device-resident table entry
     const float4* cr;        // spheres [n] / curve control points [ncp]
     const int32_t* seg;      // curves [nseg]
     uint32_t vkeys;          // PRIM_TRI_MOTION: vertex keys per triangle record (record = vkeys x 3 float4)
+    const float* verts;      // mesh [nv][3], key 0 (corrected mode: area of BSDF-sampled emitter hits)
 };
 
 struct InstanceDev {         // traversal record (64 B)

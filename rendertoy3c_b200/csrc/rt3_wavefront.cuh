@@ -37,6 +37,7 @@ struct TraverseArgs {
     const float4* contrib;       // connect: {contribution.xyz, -}
     float4* result;              // connect: per-path radiance
     unsigned long long* stat;    // ray counter to bump by count
+    uint32_t faithful;           // connect: reproduce the reference's (Le*0)*last_att NaN propagation on occluded rays (mode 0)
 };
 
 enum { TRAV_EXTEND = 0, TRAV_CONNECT = 1, TRAV_TRACE_CLOSEST = 2, TRAV_TRACE_ANY = 3 };
@@ -62,7 +63,7 @@ RT3_HD void trav_end(const TraverseArgs& a, uint32_t i, const Trav<(MODE == TRAV
             float4 r = a.result[path];
             r.x = r.x + c.x; r.y = r.y + c.y; r.z = r.z + c.z;
             a.result[path] = r;
-        } else {           // occluded: the reference adds (Le*0)*last_att, which is NaN iff the product is not finite
+        } else if (a.faithful) {  // occluded: the reference adds (Le*0)*last_att, which is NaN iff the product is not finite
             const float zx = c.x * 0.0f, zy = c.y * 0.0f, zz = c.z * 0.0f;
             if (zx != 0.0f || zy != 0.0f || zz != 0.0f) {
                 float4 r = a.result[path];
@@ -289,7 +290,7 @@ struct FrameParams {
     uint32_t width, height, spl, subframe;
     float eye[3], U[3], V[3], W[3];
     float miss[3];
-    int32_t max_depth, accum_mode;
+    int32_t max_depth, accum_mode, mode;  // mode 0 = REFERENCE_FAITHFUL, 1 = CORRECTED (unbiased)
     const Light* lights;
     uint32_t nlights;
     const TexDev* tex;
@@ -315,15 +316,21 @@ RT3_GLOBAL(k_generate, FrameParams f, Queues q) {
     const uint32_t npix = f.width * f.height;
     const uint32_t pix = p % npix, k = p / npix;
     const uint32_t x = pix % f.width, y = pix / f.width;
-    uint32_t seed = tea4(pix, f.subframe);
-    for (uint32_t i = 0; i < 2u * k; i++) seed = 1664525u * seed + 1013904223u;  // samples of a launch share one LCG stream (Q8)
+    uint32_t seed;
+    if (f.mode == 0) {
+        seed = tea4(pix, f.subframe);
+        for (uint32_t i = 0; i < 2u * k; i++) seed = 1664525u * seed + 1013904223u;  // samples of a launch share one LCG stream (Q8)
+    } else {
+        seed = tea4(pix, f.subframe * f.spl + k);  // corrected: an independent stream per sample
+    }
     const float jx = rnd(seed);
     const float jy = rnd(seed);
+    const float path_time = f.mode == 0 ? 0.0f : rnd(seed);  // corrected: one ray time per path
     const float dx = 2.0f * (((float)x + jx) / (float)f.width) - 1.0f;
     const float dy = 2.0f * (((float)y + jy) / (float)f.height) - 1.0f;
     const float3 dir = normalize(add(add(mul(ld3(f.U), dx), mul(ld3(f.V), dy)), ld3(f.W)));
     uint32_t pseed = seed;
-    const float time = rnd(pseed);  // traceRadiance draws the ray time first (shader_common.h:64)
+    const float time = f.mode == 0 ? rnd(pseed) : path_time;  // faithful: traceRadiance draws the ray time first (shader_common.h:64)
     rt3_stcs(&q.ray0[p], make_float4(f.eye[0], f.eye[1], f.eye[2], 0.01f));
     rt3_stcs(&q.ray1[p], make_float4(dir.x, dir.y, dir.z, 1e16f));
     rt3_stcs(&q.ray2[p], make_float4(time, rt3_u2f(p), 0.0f, 0.0f));
@@ -527,16 +534,127 @@ RT3_HD void shade_slot(const FrameParams& f, const TravScene& sc, const Queues& 
     }
 }
 
+// ------------------------------------------------------------------------------------ shade, CORRECTED mode
+// Same stage, unbiased estimator (draw order identical to oracle/rt3o.cpp
+// render_pixel_corrected): throughput *= albedo, NEE with solid-angle light pdf and power-heuristic
+// MIS against the cosine lobe, BSDF-sampled emitter hits weighted by the complementary heuristic,
+// Russian roulette with p = min(luminance, 1), one ray time per path.
+RT3_HD void shade_slot_corrected(const FrameParams& f, const TravScene& sc, const Queues& q, uint32_t i, bool valid) {
+    bool push_ray = false, push_shadow = false;
+    float3 P = v3(0, 0, 0), ndir = v3(0, 0, 0), Ld = v3(0, 0, 0), beta = v3(0, 0, 0), contrib = v3(0, 0, 0);
+    float shadow_tmax = 0.0f, time = 0.0f, pdf_prev = 0.0f;
+    uint32_t seed = 0, path = 0, depth = 0;
+    if (valid) {
+        const float4 r0 = rt3_ldcs(&q.ray0[i]), r1 = rt3_ldcs(&q.ray1[i]), r2 = rt3_ldcs(&q.ray2[i]);
+        const float4 h0 = rt3_ldcs(&q.hit0[i]);
+        const float4 s0 = rt3_ldcs(&q.st0[i]), s1 = rt3_ldcs(&q.st1[i]);
+        const float3 org = v3(r0), dir = v3(r1);
+        time = r2.x;
+        path = rt3_f2u(r2.y);
+        pdf_prev = r2.z;
+        HitRec h;
+        h.t = h0.x; h.u = h0.y; h.v = h0.z; h.prim = (int)rt3_f2u(h0.w); h.inst = rt3_ldcs(&q.hit_inst[i]);
+        beta = v3(s0);
+        seed = rt3_f2u(s0.w);
+        depth = rt3_f2u(s1.w);
+        const float inv_pi = (float)(1.0 / 3.14159265358979323846);
+        if (h.prim < 0) {
+            const float3 c = mul(beta, ld3(f.miss));
+            float4 r = q.result[path];
+            r.x = r.x + c.x; r.y = r.y + c.y; r.z = r.z + c.z;
+            q.result[path] = r;
+        } else {
+            const HitGroupDev hg = sc.hitgroups[h.inst];
+            const LocalGeometry lg = local_geometry(sc, h, org, dir, time);
+            const float3 Ns = faceforward(lg.N, neg(dir), lg.N);
+            P = lg.P;
+            if (hg.emission[0] != 0.0f || hg.emission[1] != 0.0f || hg.emission[2] != 0.0f) {
+                float wgt = 1.0f;
+                if (depth > 0u) {  // BSDF-sampled emitter hit: weight against the NEE strategy
+                    const BlasDev* b = sc.blas + sc.instances[h.inst].blas;
+                    const float3 v0 = ld3(b->verts + 3 * (size_t)b->idx[3 * (size_t)h.prim]), v1 = ld3(b->verts + 3 * (size_t)b->idx[3 * (size_t)h.prim + 1]),
+                                 v2 = ld3(b->verts + 3 * (size_t)b->idx[3 * (size_t)h.prim + 2]);
+                    const float3 nrm = cross(sub(v1, v0), sub(v2, v0));
+                    const float area = 0.5f * length(nrm);
+                    const float cos_l = fabsf(dot(normalize(nrm), dir));
+                    const float dist2 = h.t * h.t * dot(dir, dir);
+                    const float pdf_light = dist2 / ((float)f.nlights * area * cos_l);
+                    wgt = power_heuristic(pdf_prev, pdf_light);
+                }
+                const float3 c = mul(mul(beta, ld3(hg.emission)), wgt);
+                float4 r = q.result[path];
+                r.x = r.x + c.x; r.y = r.y + c.y; r.z = r.z + c.z;
+                q.result[path] = r;
+            }
+            const float3 albedo = hg.tex >= 0 ? fetch_texture(f.tex[hg.tex], lg.UV.x, lg.UV.y) : ld3(hg.diffuse);
+            // next event estimation
+            const Light* lt = f.lights + (int)(rnd(seed) * (float)f.nlights);
+            const float u = rnd(seed);
+            const float v = rnd(seed);
+            const float su0 = sqrtf(u);
+            const float b0 = 1.0f - su0, b1 = v * su0;
+            const float3 lpos = add(add(mul(ld3(lt->v0), b0), mul(ld3(lt->v1), b1)), mul(ld3(lt->v2), 1.0f - b0 - b1));
+            const float3 dl = sub(lpos, P);
+            const float dist2 = dot(dl, dl);
+            if (dist2 > 1e-10f) {
+                const float dist = sqrtf(dist2);
+                Ld = divs(dl, dist);
+                const float cos_s = dot(Ns, Ld);
+                const float cos_l = fabsf(dot(Ld, ld3(lt->normal)));
+                if (cos_s > 0.0f && cos_l > 0.0f && lt->area > 0.0f) {
+                    const float pdf_light = dist2 / ((float)f.nlights * lt->area * cos_l);
+                    const float pdf_bsdf = cos_s * inv_pi;
+                    const float wgt = power_heuristic(pdf_light, pdf_bsdf);
+                    contrib = mul(mul(mul(beta, albedo), ld3(lt->emission)), inv_pi * cos_s * wgt / pdf_light);
+                    shadow_tmax = dist - 0.01f;
+                    push_shadow = true;
+                }
+            }
+            // BSDF sample + Russian roulette + depth bound
+            const float u1 = rnd(seed);
+            const float u2 = rnd(seed);
+            const float3 w_in = sample_cosine_hemisphere(u1, u2);
+            if (w_in.z > 0.0f) {
+                pdf_prev = w_in.z * inv_pi;
+                ndir = onb_inverse_transform(Ns, w_in);
+                beta = mul(beta, albedo);
+                const float p = fminf(beta.x * 0.30f + beta.y * 0.59f + beta.z * 0.11f, 1.0f);
+                if (!(rnd(seed) > p)) {
+                    beta = divs(beta, p);
+                    depth += 1u;
+                    if (f.max_depth <= 0 || (int)depth < f.max_depth) push_ray = true;
+                }
+            }
+        }
+    }
+    const uint32_t sslot = warp_append(q.n_shadow, push_shadow);
+    if (push_shadow) {
+        rt3_stcs(&q.sh0[sslot], make_float4(P.x, P.y, P.z, 0.001f));
+        rt3_stcs(&q.sh1[sslot], make_float4(Ld.x, Ld.y, Ld.z, shadow_tmax));
+        rt3_stcs(&q.sh2[sslot], make_float4(time, rt3_u2f(path), 0.0f, 0.0f));
+        rt3_stcs(&q.sh3[sslot], make_float4(contrib.x, contrib.y, contrib.z, 0.0f));
+    }
+    const uint32_t rslot = warp_append(q.n_next, push_ray);
+    if (push_ray) {
+        rt3_stcs(&q.nray0[rslot], make_float4(P.x, P.y, P.z, 0.01f));
+        rt3_stcs(&q.nray1[rslot], make_float4(ndir.x, ndir.y, ndir.z, 1e16f));
+        rt3_stcs(&q.nray2[rslot], make_float4(time, rt3_u2f(path), pdf_prev, 0.0f));
+        rt3_stcs(&q.nst0[rslot], make_float4(beta.x, beta.y, beta.z, rt3_u2f(seed)));
+        rt3_stcs(&q.nst1[rslot], make_float4(0.0f, 0.0f, 0.0f, rt3_u2f(depth)));
+    }
+}
+
 #ifdef RT3_EMULATE
 static void k_shade(FrameParams f, TravScene sc, Queues q) {
     const uint32_t n = *q.n_cur;
-    for (uint32_t i = 0; i < n; i++) shade_slot(f, sc, q, i, true);
+    for (uint32_t i = 0; i < n; i++) { if (f.mode == 0) shade_slot(f, sc, q, i, true); else shade_slot_corrected(f, sc, q, i, true); }
 }
 #else
 __global__ void __launch_bounds__(256) k_shade(FrameParams f, TravScene sc, Queues q) {
     const uint32_t n = *q.n_cur;
     const uint32_t n32 = (n + 31u) & ~31u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += gridDim.x * blockDim.x) shade_slot(f, sc, q, i, i < n);
+    if (f.mode == 0) { for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += gridDim.x * blockDim.x) shade_slot(f, sc, q, i, i < n); }
+    else { for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += gridDim.x * blockDim.x) shade_slot_corrected(f, sc, q, i, i < n); }
 }
 #endif
 

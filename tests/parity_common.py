@@ -59,7 +59,7 @@ def check_trace(backend, oracle, rays, accel=1):
     return ho
 
 
-def check_render(backend, oracle, desc, subframes=2, spl=8, width=None, height=None, max_depth=None):
+def check_render(backend, oracle, desc, subframes=2, spl=8, width=None, height=None, max_depth=None, mode=0):
     uvw = oracle.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy,
                             (width or desc.width) / (height or desc.height))
     uvw_b = backend.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy,
@@ -69,7 +69,7 @@ def check_render(backend, oracle, desc, subframes=2, spl=8, width=None, height=N
     oracle.reset_stats()
     backend.reset_stats()
     for sf in range(subframes):
-        rs = make_settings(desc, uvw, sf, samples_per_launch=spl, width=width, height=height, max_depth=max_depth)
+        rs = make_settings(desc, uvw, sf, samples_per_launch=spl, width=width, height=height, max_depth=max_depth, mode=mode)
         backend.launch_subframe(rs)
         oracle.launch_subframe(rs)
     ab, ao = backend.download_accum(), oracle.download_accum()

@@ -56,3 +56,11 @@ def test_adversarial_geometry_bit_exact(emul_lib, offset):
         ho = check_trace(e, o, adversarial.make_rays(off), accel=0)
         assert (ho["prim"] >= 0).mean() > 0.1
         check_render(e, o, desc, subframes=1)
+
+
+@pytest.mark.parametrize("name", ["cornell", "terrain", "motion"])
+def test_corrected_mode_matches_oracle(emul_lib, name):
+    desc = SMALL[name]()
+    with Context(0, lib_path=emul_lib) as e:
+        o = build_pair(desc, e)
+        check_render(e, o, desc, subframes=2, mode=1)

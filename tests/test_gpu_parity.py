@@ -92,3 +92,22 @@ def test_adversarial_geometry_bit_exact(product_lib, offset):
         ho = check_trace(g, o, adversarial.make_rays(off, n=20000), accel=0)
         assert (ho["prim"] >= 0).mean() > 0.1
         check_render(g, o, desc, subframes=2)
+
+
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_corrected_mode_matches_oracle(product_lib, name):
+    """mode 1 (unbiased Lambert + NEE + MIS): bit-identical to the oracle's corrected integrator"""
+    desc = SMALL[name]()
+    with Context(0) as g:
+        o = build_pair(desc, g)
+        check_render(g, o, desc, subframes=2, mode=1)
+
+
+def test_corrected_mode_analytic_direct_lighting(product_lib):
+    import corrected_cases as cc
+    desc = cc.furnace_scene(width=64, height=64)
+    with Context(0) as g:
+        scenes.replay(desc, g)
+        got = cc.render_mean(g, desc, subframes=32, mode=1, max_depth=2)   # 64*64 px * 256 spp
+    want = cc.analytic_radiance()
+    assert abs(got - want) / want < 0.02, (got, want)
