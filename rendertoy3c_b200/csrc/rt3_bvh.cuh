@@ -6,7 +6,7 @@
 // Pipeline (all on the GPU, one stream):
 //   1. centroid bounds           (atomic min/max on order-preserving uint keys)
 //   2. 63-bit Morton codes       (21 bits / axis)
-//   3. radix sort (key,prim)     (CUB DeviceRadixSort — library sort, not on the per-ray path)
+//   3. sort (key,prim)           (hand-written bitonic sort, k_bitonic_stage)
 //   4. Karras 2012 radix tree    (one thread per internal node)
 //   5. bottom-up refit           (one thread per leaf, atomic arrival counters)
 //   6. top-down collapse BVH2 -> BVH8 by largest-surface-area opening (level-synchronous work
@@ -18,9 +18,7 @@
 #include "rt3_common.cuh"
 #include "rt3_rt.h"
 
-#ifndef RT3_EMULATE
-#include <cub/device/device_radix_sort.cuh>
-#else
+#ifdef RT3_EMULATE
 #include <algorithm>
 #include <vector>
 #endif
@@ -390,6 +388,25 @@ RT3_GLOBAL(k_bvh_collapse, BuildArrays b) {
 }
 
 // ------------------------------------------------------------------------------------ host driver
+// Hand-written bitonic sort of (Morton key, primitive) pairs, ascending by (key, primitive) so that
+// equal keys keep primitive order (= a stable sort by key; the simulator's std::stable_sort agrees).
+// One compare-exchange stage per launch on a power-of-two padded copy: O(n log^2 n), a few
+// milliseconds for 1 M primitives — a one-off inside the build, kept simple on purpose.
+RT3_GLOBAL(k_bitonic_stage, uint64_t* keys, uint32_t* vals, uint32_t j, uint32_t k) {
+    const uint32_t i = RT3_THREAD_ID();
+    if (i >= rt3_n_) return;
+    const uint32_t l = i ^ j;
+    if (l <= i) return;
+    const uint64_t ka = keys[i], kb = keys[l];
+    const uint32_t va = vals[i], vb = vals[l];
+    const bool a_gt_b = ka > kb || (ka == kb && va > vb);
+    const bool ascending = (i & k) == 0u;
+    if (a_gt_b == ascending) {
+        keys[i] = kb; keys[l] = ka;
+        vals[i] = vb; vals[l] = va;
+    }
+}
+
 inline void sort_pairs(uint64_t* keys, uint32_t* vals, uint32_t n, Stream st) {
 #ifdef RT3_EMULATE
     std::vector<std::pair<uint64_t, uint32_t>> v(n);
@@ -397,13 +414,17 @@ inline void sort_pairs(uint64_t* keys, uint32_t* vals, uint32_t n, Stream st) {
     std::stable_sort(v.begin(), v.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
     for (uint32_t i = 0; i < n; i++) { keys[i] = v[i].first; vals[i] = v[i].second; }
 #else
-    DevBuf<uint64_t> k2(n);
-    DevBuf<uint32_t> v2(n);
-    size_t tmp_bytes = 0;
-    RT3_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, k2.p, vals, v2.p, (int)n, 0, 63, st));
-    DevBuf<uint8_t> tmp(tmp_bytes);
-    RT3_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys, k2.p, vals, v2.p, (int)n, 0, 63, st));
-    count_launch();
+    if (n < 2) return;
+    uint32_t m = 1;
+    while (m < n) m <<= 1;
+    DevBuf<uint64_t> k2(m);
+    DevBuf<uint32_t> v2(m);
+    dev_memset(k2.p, 0xff, sizeof(uint64_t) * m, st);  // padding sorts to the end
+    dev_memset(v2.p, 0xff, sizeof(uint32_t) * m, st);
+    d2d(k2.p, keys, sizeof(uint64_t) * n, st);
+    d2d(v2.p, vals, sizeof(uint32_t) * n, st);
+    for (uint32_t k = 2; k <= m; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) RT3_LAUNCH_1D(k_bitonic_stage, m, st, k2.p, v2.p, j, k);
     d2d(keys, k2.p, sizeof(uint64_t) * n, st);
     d2d(vals, v2.p, sizeof(uint32_t) * n, st);
     stream_sync(st);
