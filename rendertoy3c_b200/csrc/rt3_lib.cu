@@ -82,6 +82,7 @@ struct rt3_context {
     Bvh8 m_bvh;
     bool has_merged = false, single_level = false;
     int opt_merge = 1;
+    int opt_tlas_refine = 1;  // instance boxes from the BLAS root's grandchild boxes instead of its root box
     DevBuf<uint32_t> d_flags;  // [0] error flags, [1] max stack
     // film
     uint32_t width = 0, height = 0;
@@ -123,7 +124,7 @@ struct rt3_context {
 #ifdef RT3_EMULATE
         return 1;
 #else
-        const int per_sm = opt_ctas_per_sm > 0 ? opt_ctas_per_sm : RT3_TRAV_MIN_BLOCKS;
+        const int per_sm = opt_ctas_per_sm > 0 ? opt_ctas_per_sm : (single_level ? RT3_TRAV_MIN_BLOCKS_SINGLE : RT3_TRAV_MIN_BLOCKS);
         return num_sms * per_sm;
 #endif
     }
@@ -133,10 +134,13 @@ namespace {
 
 template <int MODE>
 void launch_traverse(rt3_context* c, const TraverseArgs& a) {
+    // single-level scenes (merged world BLAS only) run the lean instantiation
 #ifdef RT3_EMULATE
-    k_traverse<MODE>(a);
+    if (c->single_level) k_traverse<MODE, true>(a);
+    else k_traverse<MODE, false>(a);
 #else
-    k_traverse<MODE><<<c->trav_grid(), RT3_TRAV_THREADS, 0, c->stream>>>(a);
+    if (c->single_level) k_traverse<MODE, true><<<c->trav_grid(), RT3_TRAV_THREADS, 0, c->stream>>>(a);
+    else k_traverse<MODE, false><<<c->trav_grid(), RT3_TRAV_THREADS, 0, c->stream>>>(a);
     RT3_CUDA(cudaGetLastError());
 #endif
     count_launch();
@@ -312,6 +316,7 @@ int rt3_set_option(rt3_context_t c, const char* key, int value) {
     else if (k == "persist_ctas_per_sm") c->opt_ctas_per_sm = value;
     else if (k == "merge_identity") { c->opt_merge = value; c->built = false; }
     else if (k == "l2_persist") { c->opt_l2_persist = value; c->built = false; }
+    else if (k == "tlas_refine") { c->opt_tlas_refine = value; c->built = false; }
     else if (k == "sort_rays" || k == "sort_materials") { RT3_REQUIRE(value == 0, RT3_ERR_UNSUPPORTED, "set_option: sorting stages are not built yet"); }
     else throw Error(RT3_ERR_INVALID, "set_option: unknown key " + k);
     RT3_API_END
@@ -526,7 +531,7 @@ int rt3_accel_build(rt3_context_t c) {
     if (!c->single_level) {
         DevBuf<float4> lo(ni + 1), hi(ni + 1);
         RT3_LAUNCH_1D(k_instance_boxes, ni + 1, c->stream, (const InstanceDev*)c->d_inst.p, (const float*)c->d_static.p, (const BlasBounds*)d_bb.p,
-                      (const float*)c->d_keys.p, lo.p, hi.p);
+                      (const BlasDev*)c->d_blas.p, (const float*)c->d_keys.p, c->opt_tlas_refine, lo.p, hi.p);
         std::vector<uint32_t> sel(tl);
         if (c->has_merged) sel.push_back(ni);
         // gather the selected boxes, build, then translate the TLAS leaf order back to instance ids

@@ -283,7 +283,10 @@ enum { FR_D_XY = 0, FR_DZ_TIME, FR_WO_XY, FR_WOZ_WDX, FR_WD_YZ, FR_WIDIR_XY, FR_
 static __shared__ uint2 rt3_s_stack[RT3_SMEM_STACK][RT3_TRAV_THREADS];  // [entry][thread of the CTA]
 #endif
 
-template <bool ANY_HIT>
+// SINGLE = the scene is the merged world BLAS only (sc.root_is_blas): no TLAS, no instance entry /
+// exit, static triangles only.  The kernel instantiated with SINGLE = true drops every other path
+// (their code costs the hot loop registers even when it never runs).
+template <bool ANY_HIT, bool SINGLE>
 struct Trav {
     float3 o;          // current-space origin
     float3 idir;       // 1 / current-space direction (clamped)
@@ -344,8 +347,9 @@ struct Trav {
 
     RT3_HD void init(const TravScene& sc, float3 ro, float3 rd, float rtmin, float rtmax, float rtime) {
         tmin = rtmin; tbest = rtmax;
-        hu = hv = 0.0f; hprim = -1; hinst = -1;
-        nodes = sc.tlas_nodes; prims = sc.root_prims; ptype = PRIM_TRI; cur_inst = sc.root_is_blas ? RT3_MERGED_INST : -1;
+        hu = hv = 0.0f; hprim = -1;
+        if (!SINGLE) hinst = -1;
+        if (!SINGLE) { nodes = sc.tlas_nodes; prims = sc.root_prims; ptype = PRIM_TRI; cur_inst = sc.root_is_blas ? RT3_MERGED_INST : -1; }
         ng = make_uint2(0u, 0x80000000u);
         tg = make_uint2(0u, 0u);
         sp = 0;
@@ -356,8 +360,8 @@ struct Trav {
         c_nodes = c_prims = c_rounds = 0;
 #endif
         // single-level scenes (merged world BLAS only) never read the frame: skip its local-memory stores
-        set_space(ro, rd, rtime, sc.root_is_blas == 0u);
-        if (sc.root_is_blas == 0u) {  // world-space copy for leaving transformed instances
+        set_space(ro, rd, rtime, !SINGLE);
+        if (!SINGLE) {  // world-space copy for leaving transformed instances
             fr_set(FR_WO_XY, ro.x, ro.y);
             fr_set(FR_WOZ_WDX, ro.z, rd.x);
             fr_set(FR_WD_YZ, rd.y, rd.z);
@@ -390,12 +394,12 @@ struct Trav {
     RT3_HD bool accept(const TravScene& sc, float t, float u, float v, int prim) {
         if (!in_range(t)) return false;
         if (!ANY_HIT && hprim >= 0 && t == tbest) {  // exact tie: lowest (instance, primitive) wins
-            int ci = cur_inst, cp = prim, bi = hinst, bp = hprim;
-            if (ci == RT3_MERGED_INST) { const uint2 m = sc.merged_map[cp]; ci = (int)m.x; cp = (int)m.y; }
-            if (bi == RT3_MERGED_INST) { const uint2 m = sc.merged_map[bp]; bi = (int)m.x; bp = (int)m.y; }
+            int ci = SINGLE ? RT3_MERGED_INST : cur_inst, cp = prim, bi = SINGLE ? RT3_MERGED_INST : hinst, bp = hprim;
+            if (!SINGLE && ci == RT3_MERGED_INST) { const uint2 m = sc.merged_map[cp]; ci = (int)m.x; cp = (int)m.y; }
+            if (!SINGLE && bi == RT3_MERGED_INST) { const uint2 m = sc.merged_map[bp]; bi = (int)m.x; bp = (int)m.y; }  // SINGLE: merged ids already order like (instance, primitive)
             if (!(ci < bi || (ci == bi && cp < bp))) return false;
         }
-        tbest = t; hu = u; hv = v; hprim = prim; hinst = cur_inst;
+        tbest = t; hu = u; hv = v; hprim = prim; hinst = SINGLE ? RT3_MERGED_INST : cur_inst;
         return true;
     }
 
@@ -410,7 +414,7 @@ struct Trav {
         const uint32_t oct = inv & 7u;
         const uint32_t slot = ((uint32_t)bit - 24u) ^ oct;
         const uint32_t rel = (uint32_t)rt3_popc(hits & 0xffu & ((1u << slot) - 1u));
-        const uint4* np = reinterpret_cast<const uint4*>(nodes + (ng.x + rel));
+        const uint4* np = reinterpret_cast<const uint4*>((SINGLE ? sc.tlas_nodes : nodes) + (ng.x + rel));
         const uint4 n0 = rt3_ldg(np + 0), n1 = rt3_ldg(np + 1);
 
         const float adjx = rt3_u2f((n0.w & 0xffu) << 23) * idir.x;
@@ -488,10 +492,10 @@ struct Trav {
         ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
         tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
         // warm L1 for what this lane touches next: its first pending primitive and its nearest child
-        if (tg.y != 0u && cur_inst >= 0) prefetch_l1(prims + 3u * (tg.x + (uint32_t)(31 - rt3_clz(tg.y & (0u - tg.y)))));
+        if (!SINGLE && tg.y != 0u && cur_inst >= 0) prefetch_l1(prims + 3u * (tg.x + (uint32_t)(31 - rt3_clz(tg.y & (0u - tg.y)))));
         if (ng.y & 0xff000000u) {
             const uint32_t nslot = ((uint32_t)(31 - rt3_clz(ng.y)) - 24u) ^ oct;
-            prefetch_l1(nodes + (ng.x + (uint32_t)rt3_popc(ng.y & 0xffu & ((1u << nslot) - 1u))));
+            prefetch_l1((SINGLE ? sc.tlas_nodes : nodes) + (ng.x + (uint32_t)rt3_popc(ng.y & 0xffu & ((1u << nslot) - 1u))));
         }
     }
 
@@ -500,7 +504,7 @@ struct Trav {
         const int bit = 31 - rt3_clz(tg.y & (0u - tg.y));  // lowest set bit
         tg.y &= tg.y - 1u;
         const uint32_t pi = tg.x + (uint32_t)bit;
-        if (cur_inst < 0) {  // TLAS leaf: enter the instance
+        if (!SINGLE && cur_inst < 0) {  // TLAS leaf: enter the instance
             const int inst = (int)rt3_ldg(sc.tlas_order + pi);
             if (ng.y & 0xff000000u) push(sc, ng);
             if (tg.y) push(sc, tg);
@@ -525,31 +529,33 @@ struct Trav {
 #ifdef RT3_STATS
         c_prims++;
 #endif
-        const float4* pr = prims + 3u * ((ptype & 0xffu) == PRIM_TRI_MOTION ? (ptype >> 8) * pi : pi);
+        const float4* pr = (SINGLE ? sc.root_prims : prims) + 3u * ((!SINGLE && (ptype & 0xffu) == PRIM_TRI_MOTION) ? (ptype >> 8) * pi : pi);
         const float4 a = rt3_ldg(pr), b = rt3_ldg(pr + 1);
         bool got = false;
-        if (ptype == PRIM_TRI) {
-            const float4 c = rt3_ldg(pr + 2);
-            float t, u, v;
-            if (test_triangle(o, shear(), v3(a), v3(b), v3(c), t, u, v)) got = accept(sc, t, u, v, (int)rt3_f2u(a.w));
-        } else if ((ptype & 0xffu) == PRIM_TRI_MOTION) {
-            // vertex-key motion (the reference's num_keys GAS, cuda_mesh.h:82-88): lerp the bracketing keys at the ray time
-            const uint32_t vk = ptype >> 8;
-            const float tc = fminf(fmaxf(ray_time(), 0.0f), 1.0f);
-            const float f = tc * (float)(vk - 1u);
-            int ki = (int)floorf(f);
-            if (ki > (int)vk - 2) ki = (int)vk - 2;
-            const float al = f - (float)ki, w = 1.0f - al;
-            const float4* k0 = prims + 3u * (vk * pi + (uint32_t)ki);
-            const float4 id4 = rt3_ldg(prims + 3u * vk * pi);
-            float3 q[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const float4 p0 = rt3_ldg(k0 + c), p1 = rt3_ldg(k0 + 3 + c);
-                q[c] = v3(w * p0.x + al * p1.x, w * p0.y + al * p1.y, w * p0.z + al * p1.z);
+        if (SINGLE || ptype == PRIM_TRI || (ptype & 0xffu) == PRIM_TRI_MOTION) {
+            float3 q0, q1, q2;
+            int id;
+            if (SINGLE || ptype == PRIM_TRI) {
+                const float4 c = rt3_ldg(pr + 2);
+                q0 = v3(a); q1 = v3(b); q2 = v3(c);
+                id = (int)rt3_f2u(a.w);
+            } else {
+                // vertex-key motion (the reference's num_keys GAS, cuda_mesh.h:82-88): lerp the bracketing keys at the ray time
+                const uint32_t vk = ptype >> 8;
+                const float tc = fminf(fmaxf(ray_time(), 0.0f), 1.0f);
+                const float f = tc * (float)(vk - 1u);
+                int ki = (int)floorf(f);
+                if (ki > (int)vk - 2) ki = (int)vk - 2;
+                const float al = f - (float)ki, w = 1.0f - al;
+                const float4* k0 = pr + 3 * ki;
+                const float4 p0 = rt3_ldg(k0), p1 = rt3_ldg(k0 + 1), p2 = rt3_ldg(k0 + 2), r0 = rt3_ldg(k0 + 3), r1 = rt3_ldg(k0 + 4), r2 = rt3_ldg(k0 + 5);
+                q0 = v3(w * p0.x + al * r0.x, w * p0.y + al * r0.y, w * p0.z + al * r0.z);
+                q1 = v3(w * p1.x + al * r1.x, w * p1.y + al * r1.y, w * p1.z + al * r1.z);
+                q2 = v3(w * p2.x + al * r2.x, w * p2.y + al * r2.y, w * p2.z + al * r2.z);
+                id = (int)rt3_f2u(a.w);
             }
             float t, u, v;
-            if (test_triangle(o, shear(), q[0], q[1], q[2], t, u, v)) got = accept(sc, t, u, v, (int)rt3_f2u(id4.w));
+            if (test_triangle(o, shear(), q0, q1, q2, t, u, v)) got = accept(sc, t, u, v, id);
         } else if (ptype == PRIM_SPHERE) {
             float ta, tb;
             if (test_sphere(o, cur_d(), v3(a), a.w, ta, tb)) {
@@ -576,7 +582,7 @@ struct Trav {
         while (tg.y == 0u && !(ng.y & 0xff000000u)) {
             if (sp == 0) return false;
             const uint2 e = st_get(--sp);
-            if (e.y == 0u) {  // sentinel: leave the instance
+            if (!SINGLE && e.y == 0u) {  // sentinel: leave the instance
                 if (e.x == 0xffffffffu) restore_world();  // the instance had its own ray space
                 nodes = sc.tlas_nodes;
                 cur_inst = -1;
@@ -613,7 +619,7 @@ struct Trav {
             while (tg.y == 0u && !(ng.y & 0xff000000u)) {
                 if (sp == 0) { active = false; break; }
                 const uint2 e = st_get(--sp);
-                if (e.y == 0u) {  // sentinel: leave the instance
+                if (!SINGLE && e.y == 0u) {  // sentinel: leave the instance
                     if (e.x == 0xffffffffu) restore_world();
                     nodes = sc.tlas_nodes;
                     cur_inst = -1;
@@ -626,7 +632,7 @@ struct Trav {
             if (active && tg.y == 0u) node_step(sc);
         }
         // ---- cooperative triangle phase (warp-uniform control flow from here)
-        const bool tri_lane = active && tg.y != 0u && cur_inst >= 0 && ptype == PRIM_TRI;
+        const bool tri_lane = active && tg.y != 0u && (SINGLE || (cur_inst >= 0 && ptype == PRIM_TRI));
         const uint32_t cnt = tri_lane ? (uint32_t)__popc(tg.y) : 0u;
         const uint32_t maxc = __reduce_max_sync(0xffffffffu, cnt);
         if (maxc == 1u) {  // one triangle per lane at most: nothing to redistribute, test in place
@@ -634,7 +640,7 @@ struct Trav {
 #ifdef RT3_STATS
                 c_prims++;
 #endif
-                const float4* pr = prims + 3u * (tg.x + (uint32_t)(__ffs((int)tg.y) - 1));
+                const float4* pr = (SINGLE ? sc.root_prims : prims) + 3u * (tg.x + (uint32_t)(__ffs((int)tg.y) - 1));
                 tg.y = 0u;
                 const float4 a = __ldg(pr), b = __ldg(pr + 1), c = __ldg(pr + 2);
                 float t, u, v;
@@ -664,7 +670,7 @@ struct Trav {
             __syncwarp();
             const uint32_t n_items = total < RT3_COOP_CAP ? total : RT3_COOP_CAP;
             const uint32_t kpack = inv >> 8;
-            const uint64_t pbase = (uint64_t)prims;
+            const uint64_t pbase = SINGLE ? (uint64_t)sc.root_prims : (uint64_t)prims;  // finished lanes help too: never use their stale members
             for (uint32_t base = 0; base < n_items; base += 32u) {
                 const uint32_t g = base + lane;
                 const bool have = g < n_items;
@@ -675,7 +681,7 @@ struct Trav {
                 s.Sx = __shfl_sync(0xffffffffu, Sx, owner); s.Sy = __shfl_sync(0xffffffffu, Sy, owner); s.Sz = __shfl_sync(0xffffffffu, Sz, owner);
                 const uint32_t kp = __shfl_sync(0xffffffffu, kpack, owner);
                 const float otmin = __shfl_sync(0xffffffffu, tmin, owner), otbest = __shfl_sync(0xffffffffu, tbest, owner);
-                const uint64_t op = __shfl_sync(0xffffffffu, pbase, owner);
+                const uint64_t op = SINGLE ? pbase : __shfl_sync(0xffffffffu, pbase, owner);
                 if (have) {
                     s.kx = (int)(kp & 3u); s.ky = (int)((kp >> 2) & 3u); s.kz = (int)((kp >> 4) & 3u);
                     const float4* pr = reinterpret_cast<const float4*>(op) + 3u * (item & 0x07ffffffu);
@@ -701,7 +707,7 @@ struct Trav {
         }
         }
         // ---- everything else that is pending: instance entry, spheres, curves (per lane)
-        if (active && tg.y != 0u && !(cur_inst >= 0 && ptype == PRIM_TRI)) {
+        if (!SINGLE && active && tg.y != 0u && !(cur_inst >= 0 && ptype == PRIM_TRI)) {
             while (tg.y != 0u) {
                 if (prim_step(sc)) { active = false; break; }
             }
@@ -719,8 +725,8 @@ struct Trav {
 #endif
         HitRec h;
         h.t = hprim >= 0 ? tbest : 0.0f;
-        h.u = hu; h.v = hv; h.prim = hprim; h.inst = hinst;
-        if (hprim >= 0 && hinst == RT3_MERGED_INST) { const uint2 m = sc.merged_map[hprim]; h.inst = (int)m.x; h.prim = (int)m.y; }
+        h.u = hu; h.v = hv; h.prim = hprim; h.inst = hprim < 0 ? -1 : (SINGLE ? RT3_MERGED_INST : hinst);
+        if (hprim >= 0 && h.inst == RT3_MERGED_INST) { const uint2 m = sc.merged_map[hprim]; h.inst = (int)m.x; h.prim = (int)m.y; }
         return h;
     }
 };

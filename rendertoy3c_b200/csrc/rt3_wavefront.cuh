@@ -42,16 +42,16 @@ struct TraverseArgs {
 
 enum { TRAV_EXTEND = 0, TRAV_CONNECT = 1, TRAV_TRACE_CLOSEST = 2, TRAV_TRACE_ANY = 3 };
 
-template <int MODE>
-RT3_HD void trav_begin(const TraverseArgs& a, uint32_t i, Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY)>& tr) {
+template <int MODE, bool SINGLE>
+RT3_HD void trav_begin(const TraverseArgs& a, uint32_t i, Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY), SINGLE>& tr) {
     const float4 r0 = rt3_ldcs(&a.rays.r0[(size_t)i * a.rays.stride]);
     const float4 r1 = rt3_ldcs(&a.rays.r1[(size_t)i * a.rays.stride]);
     const float4 r2 = rt3_ldcs(&a.rays.r2[(size_t)i * a.rays.stride]);
     tr.init(a.scene, v3(r0), v3(r1), r0.w, r1.w, r2.x);
 }
 
-template <int MODE>
-RT3_HD void trav_end(const TraverseArgs& a, uint32_t i, const Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY)>& tr) {
+template <int MODE, bool SINGLE>
+RT3_HD void trav_end(const TraverseArgs& a, uint32_t i, const Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY), SINGLE>& tr) {
     const HitRec h = tr.result(a.scene);
     if (MODE == TRAV_EXTEND) {
         rt3_stcs(&a.hit0[i], make_float4(h.t, h.u, h.v, rt3_u2f((uint32_t)h.prim)));
@@ -78,22 +78,25 @@ RT3_HD void trav_end(const TraverseArgs& a, uint32_t i, const Trav<(MODE == TRAV
 }
 
 #ifdef RT3_EMULATE
-template <int MODE>
+template <int MODE, bool SINGLE>
 static void k_traverse(TraverseArgs a) {
     const uint32_t n = a.count_ptr ? *a.count_ptr : a.count;
     if (a.stat) *a.stat += n;
     for (uint32_t i = 0; i < n; i++) {
-        Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY)> tr;
-        trav_begin<MODE>(a, i, tr);
+        Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY), SINGLE> tr;
+        trav_begin<MODE, SINGLE>(a, i, tr);
         uint32_t hw = 0;
         while (tr.step(a.scene)) { if ((uint32_t)tr.sp > hw) hw = (uint32_t)tr.sp; }
         if (hw > *a.scene.max_stack) *a.scene.max_stack = hw;
-        trav_end<MODE>(a, i, tr);
+        trav_end<MODE, SINGLE>(a, i, tr);
     }
 }
 #else
 #ifndef RT3_TRAV_MIN_BLOCKS
-#define RT3_TRAV_MIN_BLOCKS 10
+#define RT3_TRAV_MIN_BLOCKS 9          // general kernel (TLAS, instances, all primitive types): 56 regs, no spills
+#endif
+#ifndef RT3_TRAV_MIN_BLOCKS_SINGLE
+#define RT3_TRAV_MIN_BLOCKS_SINGLE 9   // single-level kernel (merged world BLAS only): 56 regs
 #endif
 #ifndef RT3_REFILL_THRESHOLD
 #define RT3_REFILL_THRESHOLD 26
@@ -101,8 +104,8 @@ static void k_traverse(TraverseArgs a) {
 // Persistent threads with dynamic fetch: a warp keeps traversing until fewer than
 // RT3_REFILL_THRESHOLD lanes are busy, then refills the idle lanes from the queue with a single
 // atomicAdd per warp (warp-aggregated fetch).
-template <int MODE>
-__global__ void __launch_bounds__(RT3_TRAV_THREADS, RT3_TRAV_MIN_BLOCKS) k_traverse(TraverseArgs a) {
+template <int MODE, bool SINGLE>
+__global__ void __launch_bounds__(RT3_TRAV_THREADS, SINGLE ? RT3_TRAV_MIN_BLOCKS_SINGLE : RT3_TRAV_MIN_BLOCKS) k_traverse(TraverseArgs a) {
     const uint32_t n = a.count_ptr ? *a.count_ptr : a.count;
     if (a.stat && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.stat, (unsigned long long)n);
     const uint32_t lane = threadIdx.x & 31u;
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(RT3_TRAV_THREADS, RT3_TRAV_MIN_BLOCKS) k_trave
     __shared__ uint32_t s_items[RT3_TRAV_THREADS / 32][RT3_COOP_CAP];
     __shared__ float4 s_res[RT3_TRAV_THREADS / 32][RT3_COOP_CAP];
 #endif
-    Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY)> tr;
+    Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY), SINGLE> tr;
     bool active = false;
     bool exhausted = false;
     uint32_t my = 0;
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(RT3_TRAV_THREADS, RT3_TRAV_MIN_BLOCKS) k_trave
                 const uint32_t cand = base + __popc(idle & lt_mask);
                 if (cand < n) {
                     my = cand;
-                    trav_begin<MODE>(a, my, tr);
+                    trav_begin<MODE, SINGLE>(a, my, tr);
                     active = true;
                 }
             }
@@ -139,11 +142,11 @@ __global__ void __launch_bounds__(RT3_TRAV_THREADS, RT3_TRAV_MIN_BLOCKS) k_trave
 #if RT3_COOP
             const bool was = active;
             active = tr.step_warp(a.scene, active, s_items[threadIdx.x >> 5], s_res[threadIdx.x >> 5]);
-            if (was && !active) trav_end<MODE>(a, my, tr);
+            if (was && !active) trav_end<MODE, SINGLE>(a, my, tr);
 #else
             if (active) {
                 if (!tr.step(a.scene)) {
-                    trav_end<MODE>(a, my, tr);
+                    trav_end<MODE, SINGLE>(a, my, tr);
                     active = false;
                 }
             }
@@ -248,28 +251,89 @@ RT3_GLOBAL(k_pack_merged, const MergedRange* ranges, uint32_t nranges, const uin
     out[3 * (size_t)j + 2] = make_float4(c.x, c.y, c.z, 0.0f);
     map[g] = make_uint2(r.inst, p);
 }
-// world-space box of every instance: union over motion keys of the transformed BLAS root box
+// decoded (conservative) box of child slot s of a wide node
+RT3_HD void node_child_box(const Node8& n, int s, float3& lo, float3& hi) {
+    const float sx = rt3_u2f((uint32_t)n.ex << 23), sy = rt3_u2f((uint32_t)n.ey << 23), sz = rt3_u2f((uint32_t)n.ez << 23);
+#if RT3_NODE_FP16
+    const float2 xl = half2_to_float2(n.q[s >> 2][0][0][s & 3]), xh = half2_to_float2(n.q[s >> 2][0][1][s & 3]);
+    const float2 yl = half2_to_float2(n.q[s >> 2][1][0][s & 3]), yh = half2_to_float2(n.q[s >> 2][1][1][s & 3]);
+    const float2 zl = half2_to_float2(n.q[s >> 2][2][0][s & 3]), zh = half2_to_float2(n.q[s >> 2][2][1][s & 3]);
+    lo = v3(n.px + xl.x * sx, n.py + yl.x * sy, n.pz + zl.x * sz);
+    hi = v3(n.px + xh.x * sx, n.py + yh.x * sy, n.pz + zh.x * sz);
+#else
+    lo = v3(n.px + (float)n.qlo[0][s] * sx, n.py + (float)n.qlo[1][s] * sy, n.pz + (float)n.qlo[2][s] * sz);
+    hi = v3(n.px + (float)n.qhi[0][s] * sx, n.py + (float)n.qhi[1][s] * sy, n.pz + (float)n.qhi[2][s] * sz);
+#endif
+    // one ulp-scale step outward: p + q*scale is rounded here, the traversal evaluates it exactly in t-space
+    const float3 e = v3(1e-6f * (fabsf(lo.x) + fabsf(hi.x)), 1e-6f * (fabsf(lo.y) + fabsf(hi.y)), 1e-6f * (fabsf(lo.z) + fabsf(hi.z)));
+    lo = sub(lo, e);
+    hi = add(hi, e);
+}
+
+// world-space box of every instance: union over motion keys of the transformed BLAS boxes.  Instead of
+// the 8 corners of the BLAS root box, the (up to 64) grandchild boxes of the BLAS root are transformed:
+// for a rotated, roughly round object that is close to its true world-space extent, whereas the box of a
+// rotated box is up to sqrt(3) larger per side — and every false TLAS hit costs a ray transform, three
+// reciprocals, the shear constants and a wide-node step.
 struct BlasBounds { float lo[3], hi[3]; };
-RT3_GLOBAL(k_instance_boxes, const InstanceDev* inst, const float* inst_static, const BlasBounds* bb, const float* keys, float4* lo, float4* hi) {
+struct InstBoxAcc {
+    float3 mn, mx;
+    Affine st;
+    const float* keys;
+    int nk;
+    bool moving;
+    RT3_HD void grow(float3 blo, float3 bhi) {
+        for (int k = 0; k < nk; k++) {
+            Affine km;
+            if (moving) for (int j = 0; j < 12; j++) km.m[j] = keys[12 * k + j];
+            for (int c = 0; c < 8; c++) {
+                float3 p = v3((c & 1) ? bhi.x : blo.x, (c & 2) ? bhi.y : blo.y, (c & 4) ? bhi.z : blo.z);
+                if (moving) p = xform_point(km, p);
+                p = xform_point(st, p);
+                mn = v3(fminf(mn.x, p.x), fminf(mn.y, p.y), fminf(mn.z, p.z));
+                mx = v3(fmaxf(mx.x, p.x), fmaxf(mx.y, p.y), fmaxf(mx.z, p.z));
+            }
+        }
+    }
+};
+RT3_GLOBAL(k_instance_boxes, const InstanceDev* inst, const float* inst_static, const BlasBounds* bb, const BlasDev* blas, const float* keys, int refine, float4* lo, float4* hi) {
     const uint32_t i = RT3_THREAD_ID();
     if (i >= rt3_n_) return;
     const InstanceDev in = inst[i];
     const BlasBounds b = bb[in.blas];
-    Affine st;
-    for (int j = 0; j < 12; j++) st.m[j] = inst_static[12 * (size_t)i + j];
-    float3 mn = v3(3e38f, 3e38f, 3e38f), mx = v3(-3e38f, -3e38f, -3e38f);
-    const int nk = in.nkeys > 0 ? (int)in.nkeys : 1;
-    for (int k = 0; k < nk; k++) {
-        Affine km;
-        if (in.nkeys > 0) for (int j = 0; j < 12; j++) km.m[j] = keys[in.key_offset + 12 * k + j];
-        for (int c = 0; c < 8; c++) {
-            float3 p = v3((c & 1) ? b.hi[0] : b.lo[0], (c & 2) ? b.hi[1] : b.lo[1], (c & 4) ? b.hi[2] : b.lo[2]);
-            if (in.nkeys > 0) p = xform_point(km, p);
-            p = xform_point(st, p);
-            mn = v3(fminf(mn.x, p.x), fminf(mn.y, p.y), fminf(mn.z, p.z));
-            mx = v3(fmaxf(mx.x, p.x), fmaxf(mx.y, p.y), fmaxf(mx.z, p.z));
+    InstBoxAcc acc;
+    for (int j = 0; j < 12; j++) acc.st.m[j] = inst_static[12 * (size_t)i + j];
+    acc.mn = v3(3e38f, 3e38f, 3e38f);
+    acc.mx = v3(-3e38f, -3e38f, -3e38f);
+    acc.moving = in.nkeys > 0;
+    acc.nk = in.nkeys > 0 ? (int)in.nkeys : 1;
+    acc.keys = keys + in.key_offset;
+    const Node8* nodes = blas[in.blas].nodes;
+    if (in.identity || nodes == nullptr || !refine) {
+        acc.grow(v3(b.lo[0], b.lo[1], b.lo[2]), v3(b.hi[0], b.hi[1], b.hi[2]));
+    } else {
+        const Node8 root = nodes[0];
+        for (int s = 0; s < 8; s++) {
+            if (root.meta[s] == 0) continue;
+            float3 clo, chi;
+            node_child_box(root, s, clo, chi);
+            if ((root.meta[s] & 0x18) == 0x18) {  // internal child: descend one more level
+                const Node8 ch = nodes[root.child_base + (uint32_t)rt3_popc((uint32_t)root.imask & ((1u << s) - 1u))];
+                for (int s2 = 0; s2 < 8; s2++) {
+                    if (ch.meta[s2] == 0) continue;
+                    float3 glo, ghi;
+                    node_child_box(ch, s2, glo, ghi);
+                    // a grandchild box may stick out of its (tighter, exact) parent box by quantisation: clip to it
+                    glo = v3(fmaxf(glo.x, clo.x), fmaxf(glo.y, clo.y), fmaxf(glo.z, clo.z));
+                    ghi = v3(fminf(ghi.x, chi.x), fminf(ghi.y, chi.y), fminf(ghi.z, chi.z));
+                    acc.grow(glo, ghi);
+                }
+            } else {
+                acc.grow(clo, chi);
+            }
         }
     }
+    const float3 mn = acc.mn, mx = acc.mx;
     // pad by a few ulps: the per-ray inverse transform is not exactly the inverse of these corners
     const float3 pad = v3(1e-5f * (fabsf(mn.x) + fabsf(mx.x)) + 1e-7f, 1e-5f * (fabsf(mn.y) + fabsf(mx.y)) + 1e-7f,
                           1e-5f * (fabsf(mn.z) + fabsf(mx.z)) + 1e-7f);

@@ -17,6 +17,9 @@ w, h = 1920, 1080
 scene = os.environ.get("SCENE", "terrain")
 d = scenes.terrain(n=n, width=w, height=h, tex_size=64) if scene == "terrain" else (scenes.instanced(width=w, height=h) if scene == "instanced" else scenes.motion(width=w, height=h))
 g = Context(0)
+for kv in os.environ.get("OPTS", "").split(","):
+    if kv:
+        g.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 scenes.replay(d, g)
 uvw = g.camera_uvw(d.camera.eye, d.camera.lookat, d.camera.up, d.camera.fovy, w / h)
 prim = camera_rays(d, uvw, w, h)
