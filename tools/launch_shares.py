@@ -1,0 +1,34 @@
+"""Per-kernel time shares and DRAM bytes of the last complete subframe in an ncu launch list CSV
+(ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv).
+usage: python tools/launch_shares.py launches.csv out.json"""
+import csv
+import json
+import sys
+
+rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 8]
+hdr = rows[0]
+ki, mi, vi, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+byid = {}
+for r in rows[1:]:
+    d = byid.setdefault(int(r[ii]), {"k": r[ki]})
+    d[r[mi]] = float(r[vi].replace(",", ""))
+ids = sorted(byid)
+gen = [i for i in ids if "k_generate" in byid[i]["k"]]
+res = [i for i in ids if "k_resolve" in byid[i]["k"]]
+last_res = res[-1]
+last_gen = max(i for i in gen if i < last_res)
+sub = [byid[i] for i in ids if last_gen <= i <= last_res]
+tot = sum(d["gpu__time_duration.sum"] for d in sub)
+agg = {}
+for d in sub:
+    name = d["k"].split("(")[0].replace("void ", "").replace("rt3::", "")
+    a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
+    a[0] += 1
+    a[1] += d["gpu__time_duration.sum"]
+    a[2] += d.get("dram__bytes_read.sum", 0)
+    a[3] += d.get("dram__bytes_write.sum", 0)
+out = {"source": sys.argv[1], "total_ms_under_ncu": tot / 1e6, "kernels": {}}
+for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
+    print("%-28s launches %2d  %8.3f ms  share %5.1f%%  dram read %7.1f MB write %7.1f MB" % (k, a[0], a[1] / 1e6, 100 * a[1] / tot, a[2] / 1e6, a[3] / 1e6))
+    out["kernels"][k] = {"launches": a[0], "ms": a[1] / 1e6, "share": a[1] / tot, "dram_read_MB": a[2] / 1e6, "dram_write_MB": a[3] / 1e6}
+json.dump(out, open(sys.argv[2], "w"), indent=1)
