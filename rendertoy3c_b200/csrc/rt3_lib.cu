@@ -678,7 +678,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
 #ifdef RT3_EMULATE
         k_shade(f, sc, q);
 #else
-        k_shade<<<c->num_sms * 4, 256, 0, c->stream>>>(f, sc, q);
+        k_shade<<<c->num_sms * RT3_SHADE_MIN_BLOCKS, 256, 0, c->stream>>>(f, sc, q);
         RT3_CUDA(cudaGetLastError());
 #endif
         count_launch();

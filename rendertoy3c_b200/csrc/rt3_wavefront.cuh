@@ -708,13 +708,16 @@ RT3_HD void shade_slot_corrected(const FrameParams& f, const TravScene& sc, cons
     }
 }
 
+#ifndef RT3_SHADE_MIN_BLOCKS
+#define RT3_SHADE_MIN_BLOCKS 4   // grid = SMs x this, all CTAs resident (one wave): 64 regs
+#endif
 #ifdef RT3_EMULATE
 static void k_shade(FrameParams f, TravScene sc, Queues q) {
     const uint32_t n = *q.n_cur;
     for (uint32_t i = 0; i < n; i++) { if (f.mode == 0) shade_slot(f, sc, q, i, true); else shade_slot_corrected(f, sc, q, i, true); }
 }
 #else
-__global__ void __launch_bounds__(256) k_shade(FrameParams f, TravScene sc, Queues q) {
+__global__ void __launch_bounds__(256, RT3_SHADE_MIN_BLOCKS) k_shade(FrameParams f, TravScene sc, Queues q) {
     const uint32_t n = *q.n_cur;
     const uint32_t n32 = (n + 31u) & ~31u;
     if (f.mode == 0) { for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += gridDim.x * blockDim.x) shade_slot(f, sc, q, i, i < n); }
