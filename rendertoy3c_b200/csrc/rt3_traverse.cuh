@@ -77,6 +77,7 @@ struct TravScene {
     // reference creates, cuda_scene.h:141-146) are merged into ONE world-space BLAS whose primitive
     // ids index merged_map -> (instance, primitive).  If nothing else is in the scene the TLAS is
     // skipped altogether (root_is_blas) and tlas_nodes points at the merged BLAS.
+    const uint32_t* consts;         // [0] = 0x4B000000 (kept opaque to the compiler on purpose)
     const uint2* merged_map;
     const float4* root_prims;
     uint32_t root_is_blas;
@@ -228,13 +229,16 @@ RT3_HD bool test_curve_linear(float3 o, float3 d, float3 pa, float ra, float3 pb
 }
 
 // quantised byte j of a packed word as float: exact, PRMT + FADD on the device instead of shift/and/I2F
-RT3_HD float byte_to_float(uint32_t w, int j) {
+// `magic` must hold 0x4B000000 in a per-thread register that ptxas cannot treat as a constant (it is
+// loaded from device memory once per kernel): PRMT encodes ONE immediate, and with both operands
+// constant ptxas keeps the bias as the immediate and the selector in a uniform register, which costs
+// a UR->R move in front of every one of the 48 PRMTs of a node step (205 of 1584 SASS instructions).
+RT3_HD float byte_to_float(uint32_t w, int j, uint32_t magic) {
 #ifdef RT3_EMULATE
+    (void)magic;
     return (float)((w >> (8 * j)) & 0xffu);
 #else
-    // selector as an immediate, the 2^23 bias in a register (PRMT takes one immediate): PRMT + FADD
     uint32_t r;
-    uint32_t magic = 0x4B000000u;
     switch (j) {
         case 0: asm("prmt.b32 %0, %1, %2, 0x7650;" : "=r"(r) : "r"(w), "r"(magic)); break;
         case 1: asm("prmt.b32 %0, %1, %2, 0x7651;" : "=r"(r) : "r"(w), "r"(magic)); break;
@@ -301,6 +305,7 @@ struct Trav {
     int cur_inst;      // -1 while in the TLAS
     uint2 ng, tg;
     int sp;
+    uint32_t magic;    // 0x4B000000 from device memory (see byte_to_float)
 #ifdef RT3_STATS
     uint32_t c_nodes, c_prims, c_rounds;  // diagnostic build only (tools/build_variant.sh -DRT3_STATS)
     uint32_t* dbg;
@@ -347,6 +352,7 @@ struct Trav {
 
     RT3_HD void init(const TravScene& sc, float3 ro, float3 rd, float rtmin, float rtmax, float rtime) {
         tmin = rtmin; tbest = rtmax;
+        magic = rt3_ldg(sc.consts);
         hu = hv = 0.0f; hprim = -1;
         if (!SINGLE) hinst = -1;
         if (!SINGLE) { nodes = sc.tlas_nodes; prims = sc.root_prims; ptype = PRIM_TRI; cur_inst = sc.root_is_blas ? RT3_MERGED_INST : -1; }
@@ -477,12 +483,12 @@ struct Trav {
             const uint32_t nz = (oct & 4u) ? loz : hiz, fz = (oct & 4u) ? hiz : loz;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float tnx = fmaf(byte_to_float(nx, j), adjx, nox);
-                const float tny = fmaf(byte_to_float(ny, j), adjy, noy);
-                const float tnz = fmaf(byte_to_float(nz, j), adjz, noz);
-                const float tfx = fmaf(byte_to_float(fx, j), adjx, fox);
-                const float tfy = fmaf(byte_to_float(fy, j), adjy, foy);
-                const float tfz = fmaf(byte_to_float(fz, j), adjz, foz);
+                const float tnx = fmaf(byte_to_float(nx, j, magic), adjx, nox);
+                const float tny = fmaf(byte_to_float(ny, j, magic), adjy, noy);
+                const float tnz = fmaf(byte_to_float(nz, j, magic), adjz, noz);
+                const float tfx = fmaf(byte_to_float(fx, j, magic), adjx, fox);
+                const float tfy = fmaf(byte_to_float(fy, j, magic), adjy, foy);
+                const float tfz = fmaf(byte_to_float(fz, j, magic), adjz, foz);
                 const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
                 const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
                 if (tn <= tf) hitmask |= ((child_bits4 >> (8 * j)) & 0xffu) << ((bit_index4 >> (8 * j)) & 0xffu);
