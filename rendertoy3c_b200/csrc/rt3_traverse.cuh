@@ -228,6 +228,15 @@ RT3_HD bool test_curve_linear(float3 o, float3 d, float3 pa, float ra, float3 pb
     return true;
 }
 
+// hit word of child j: its child bits (1 for an internal child, the unary primitive count for a leaf) at its bit index
+RT3_HD uint32_t child_word(uint32_t child_bits4, uint32_t bit_index4, int j) {
+#ifdef RT3_EMULATE
+    return ((child_bits4 >> (8 * j)) & 0xffu) << ((bit_index4 >> (8 * j)) & 31u);
+#else
+    return __byte_perm(child_bits4, 0u, 0x4440u + (uint32_t)j) << ((bit_index4 >> (8 * j)) & 31u);  // PRMT, SHF.R, SHF.L.W
+#endif
+}
+
 // quantised byte j of a packed word as float: exact, PRMT + FADD on the device instead of shift/and/I2F
 // `magic` must hold 0x4B000000 in a per-thread register that ptxas cannot treat as a constant (it is
 // loaded from device memory once per kernel): PRMT encodes ONE immediate, and with both operands
@@ -310,7 +319,10 @@ struct Trav {
     uint32_t c_nodes, c_prims, c_rounds;  // diagnostic build only (tools/build_variant.sh -DRT3_STATS)
     uint32_t* dbg;
 #endif
-    uint2 stack[RT3_STACK_SIZE + FR_COUNT];
+    // the traversal stack (+ frame) is a separate per-thread array owned by the kernel: as a member its
+    // dynamically indexed stores forced the WHOLE state into local memory (every push was followed by a
+    // reload of origin, 1/d, ... and every node step stored the cursors back)
+    uint2* stack;
     // ncu: the per-thread stack in local memory (1280 threads/SM) competes with nodes and triangles for
     // L1 and spilled to DRAM (99 B written per ray for a 20 B hit record); the hot bottom of the stack
     // therefore sits in shared memory, column per thread (bank-conflict free), the rest stays local.
@@ -437,7 +449,6 @@ struct Trav {
         const float nox = orgx - padx, fox = orgx + padx;
         const float noy = orgy - pady, foy = orgy + pady;
         const float noz = orgz - padz, foz = orgz + padz;
-        const uint32_t oct4 = oct * 0x01010101u;
 
         uint32_t hitmask = 0;
 #pragma unroll
@@ -447,9 +458,14 @@ struct Trav {
             // their unary primitive count at their primitive offset; empty slots contribute 0 bits
             const uint32_t meta4 = half ? n1.w : n1.z;
             const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-            const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;  // 0xff in the bytes of internal children
-            const uint32_t bit_index4 = (meta4 ^ (oct4 & inner_mask4)) & 0x1f1f1f1fu;
-            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+            const uint32_t oct_inner4 = (is_inner4 >> 4) * oct;  // the ray octant in the bytes of internal children
+            uint32_t bit_index4 = (meta4 ^ oct_inner4) & 0x1f1f1f1fu;
+            uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+#ifndef RT3_EMULATE
+            // pin the 4-wide decode: ptxas otherwise sinks it into the predicated per-child code and
+            // redoes it for every child (87 instead of ~50 instructions for the eight hit words)
+            asm volatile("" : "+r"(bit_index4), "+r"(child_bits4));
+#endif
 #if RT3_NODE_FP16
             const uint4 qx = rt3_ldg(np + 2 + 3 * half), qy = rt3_ldg(np + 3 + 3 * half), qz = rt3_ldg(np + 4 + 3 * half);
             // {lo01, lo23, hi01, hi23} per axis; near plane = lo when d >= 0
@@ -491,7 +507,7 @@ struct Trav {
                 const float tfz = fmaf(byte_to_float(fz, j, magic), adjz, foz);
                 const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
                 const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
-                if (tn <= tf) hitmask |= ((child_bits4 >> (8 * j)) & 0xffu) << ((bit_index4 >> (8 * j)) & 0xffu);
+                hitmask |= (tn <= tf) ? child_word(child_bits4, bit_index4, j) : 0u;
             }
 #endif
         }

@@ -84,6 +84,8 @@ static void k_traverse(TraverseArgs a) {
     if (a.stat) *a.stat += n;
     for (uint32_t i = 0; i < n; i++) {
         Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY), SINGLE> tr;
+        uint2 stack_mem[RT3_STACK_SIZE + FR_COUNT];
+        tr.stack = stack_mem;
         trav_begin<MODE, SINGLE>(a, i, tr);
         uint32_t hw = 0;
         while (tr.step(a.scene)) { if ((uint32_t)tr.sp > hw) hw = (uint32_t)tr.sp; }
@@ -115,6 +117,8 @@ __global__ void __launch_bounds__(RT3_TRAV_THREADS, SINGLE ? RT3_TRAV_MIN_BLOCKS
     __shared__ float4 s_res[RT3_TRAV_THREADS / 32][RT3_COOP_CAP];
 #endif
     Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY), SINGLE> tr;
+    uint2 stack_mem[RT3_STACK_SIZE + FR_COUNT];
+    tr.stack = stack_mem;
     bool active = false;
     bool exhausted = false;
     uint32_t my = 0;
