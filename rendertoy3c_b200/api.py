@@ -236,7 +236,7 @@ class Context:
         self._chk(self.L.rt3_reset_stats(self.ctx))
 
     def debug_counters(self):
-        out = (C.c_uint32 * 8)()
+        out = (C.c_uint32 * 16)()
         self._chk(self.L.rt3_get_debug_counters(self.ctx, out))
         return list(out)
 

@@ -270,7 +270,7 @@ int rt3_context_create(int device, rt3_context_t* out) {
 #endif
     c->d_consts.alloc(4);
     { const uint32_t k[4] = {0x4B000000u, 0u, 0u, 0u}; h2d(c->d_consts.p, k, sizeof(k), c->stream); }
-    c->d_flags.alloc(8);  // [0] error flags, [1] max stack, [2..5] diagnostic counters (RT3_STATS builds)
+    c->d_flags.alloc(16);  // [0] error flags, [1] max stack, [2..15] diagnostic counters (RT3_STATS builds)
     c->counters.alloc(4 * MAX_DEPTH_SLOTS);
     c->d_stats.alloc(4);
     c->trace_fetch.alloc(1);
@@ -805,12 +805,12 @@ int rt3_get_stats(rt3_context_t c, rt3_stats* st) {
     st->error_flags = fl[0]; st->max_stack_depth = fl[1];
     RT3_API_END
 }
-int rt3_get_debug_counters(rt3_context_t c, uint32_t out[8]) {
+int rt3_get_debug_counters(rt3_context_t c, uint32_t out[16]) {
     RT3_API_BEGIN
     RT3_REQUIRE(c && out, RT3_ERR_INVALID, "get_debug_counters: null argument");
-    d2h(out, c->d_flags.p, 8 * sizeof(uint32_t), c->stream);
+    d2h(out, c->d_flags.p, 16 * sizeof(uint32_t), c->stream);
     stream_sync(c->stream);
-    dev_memset(c->d_flags.p + 2, 0, 6 * sizeof(uint32_t), c->stream);
+    dev_memset(c->d_flags.p + 2, 0, 14 * sizeof(uint32_t), c->stream);
     RT3_API_END
 }
 int rt3_reset_stats(rt3_context_t c) {

@@ -29,6 +29,18 @@ enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2, PRIM_TRI_MOTION = 3 };  //
 #ifndef RT3_SMEM_STACK
 #define RT3_SMEM_STACK 0   // >0: keep that many bottom stack entries per lane in shared memory (measured slower: ptxas spills)
 #endif
+#ifndef RT3_DEFER
+#define RT3_DEFER 1       // single-level kernel: triangles wait in a per-warp queue until a pass is worth it (step_warp_deferred)
+#endif
+#ifndef RT3_QCAP
+#define RT3_QCAP 64       // capacity of that queue
+#endif
+#ifndef RT3_DEFER_ITEMS
+#define RT3_DEFER_ITEMS 20    // run the triangle pass once this many pairs are queued ...
+#endif
+#ifndef RT3_DEFER_BLOCKED
+#define RT3_DEFER_BLOCKED 2   // ... or more than this many lanes have nothing else left to do
+#endif
 #ifndef RT3_COOP
 #define RT3_COOP 1        // 1: warp-cooperative triangle phase (step_warp), 0: per-lane loop (step)
 #endif
@@ -315,6 +327,7 @@ struct Trav {
     uint2 ng, tg;
     int sp;
     uint32_t magic;    // 0x4B000000 from device memory (see byte_to_float)
+    uint32_t pend;     // triangles of this lane waiting in the warp's queue (step_warp_deferred)
 #ifdef RT3_STATS
     uint32_t c_nodes, c_prims, c_rounds;  // diagnostic build only (tools/build_variant.sh -DRT3_STATS)
     uint32_t* dbg;
@@ -365,6 +378,7 @@ struct Trav {
     RT3_HD void init(const TravScene& sc, float3 ro, float3 rd, float rtmin, float rtmax, float rtime) {
         tmin = rtmin; tbest = rtmax;
         magic = rt3_ldg(sc.consts);
+        pend = 0u;
         hu = hv = 0.0f; hprim = -1;
         if (!SINGLE) hinst = -1;
         if (!SINGLE) { nodes = sc.tlas_nodes; prims = sc.root_prims; ptype = PRIM_TRI; cur_inst = sc.root_is_blas ? RT3_MERGED_INST : -1; }
@@ -657,6 +671,16 @@ struct Trav {
         const bool tri_lane = active && tg.y != 0u && (SINGLE || (cur_inst >= 0 && ptype == PRIM_TRI));
         const uint32_t cnt = tri_lane ? (uint32_t)__popc(tg.y) : 0u;
         const uint32_t maxc = __reduce_max_sync(0xffffffffu, cnt);
+#ifdef RT3_STATS
+        {   // warp-round histogram: [6] rounds, [7] rounds without triangles, [8] rounds with <= 1 per lane, [9] lanes with triangles, [10] triangles, [11] busy lanes
+            const uint32_t tl = __popc(__ballot_sync(0xffffffffu, tri_lane)), tt = __reduce_add_sync(0xffffffffu, cnt), bl = __popc(__ballot_sync(0xffffffffu, active));
+            if (lane == 0) {
+                uint32_t* d = const_cast<uint32_t*>(sc.error_flags);
+                atomicAdd(d + 6, 1u); atomicAdd(d + 7, maxc == 0u ? 1u : 0u); atomicAdd(d + 8, maxc == 1u ? 1u : 0u);
+                atomicAdd(d + 9, tl); atomicAdd(d + 10, tt); atomicAdd(d + 11, bl);
+            }
+        }
+#endif
         if (maxc == 1u) {  // one triangle per lane at most: nothing to redistribute, test in place
             if (tri_lane) {
 #ifdef RT3_STATS
@@ -734,6 +758,120 @@ struct Trav {
                 if (prim_step(sc)) { active = false; break; }
             }
         }
+        return active;
+    }
+#endif
+
+#ifndef RT3_EMULATE
+    // ---------------------------------------------------------------------------------- deferred triangle queue
+    // Single-level scenes.  Counters (RT3_STATS build, C2 bounce rays): a round leaves triangles on only 4
+    // of 25 busy lanes, 10.7 in total, in 9 rounds out of 10 — so a triangle pass per round runs its ~300
+    // instructions at a third of the lanes and costs as many issue slots as the wide-node step.  Here the
+    // (owner lane, triangle) pairs stay in a per-warp shared-memory queue ACROSS rounds while their
+    // owners go on with node work, and one pass tests them when RT3_DEFER_ITEMS have gathered (or when
+    // more than RT3_DEFER_BLOCKED lanes have nothing else left, or a lane could not queue everything).
+    // The fold is order-free: a candidate is valid under the owner's accept() rule, the owner's new hit
+    // is the valid candidate with the smallest (t, primitive id) — which is what accept() yields for any
+    // order of the same candidates — found with shared-memory atomicMin in two steps (t, then id among
+    // equal t).  A late tbest only means a few more nodes are visited; the result is the same.
+    __device__ __forceinline__ bool step_warp_deferred(const TravScene& sc, bool active, uint32_t* s_items, float4* s_res, uint32_t* s_best, uint32_t& qn) {
+        static_assert(SINGLE, "deferred queue: single-level kernel only");
+        const uint32_t lane = threadIdx.x & 31u;
+        if (active && tg.y == 0u) {  // (triangles that did not fit the queue last round are queued first)
+#ifdef RT3_STATS
+            c_rounds++;
+#endif
+            while (!(ng.y & 0xff000000u) && sp != 0) ng = st_get(--sp);  // the stack holds node groups only here
+            if (ng.y & 0xff000000u) node_step(sc);
+        }
+        // ---- queue this round's triangles (warp-uniform control flow from here)
+        const uint32_t cnt = (active && tg.y != 0u) ? (uint32_t)__popc(tg.y) : 0u;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total != 0u) {
+            if (cnt != 0u) {
+                uint32_t m = tg.y, pos = qn + incl - cnt;
+                while (m != 0u && pos < RT3_QCAP) {
+                    const uint32_t b = (uint32_t)(__ffs((int)m) - 1);
+                    m &= m - 1u;
+                    s_items[pos++] = (lane << 27) | (tg.x + b);
+                    pend++;
+                }
+                tg.y = m;
+            }
+            qn = qn + total < RT3_QCAP ? qn + total : RT3_QCAP;
+        }
+        const bool ready = active && tg.y == 0u && ((ng.y & 0xff000000u) != 0u || sp != 0);
+        const uint32_t act_mask = __ballot_sync(0xffffffffu, active), ready_mask = __ballot_sync(0xffffffffu, ready);
+        const uint32_t waiting = (uint32_t)(__popc(act_mask) - __popc(ready_mask));  // lanes that wait for the pass (or could not queue)
+#ifdef RT3_STATS
+        if (lane == 0) {
+            uint32_t* d = const_cast<uint32_t*>(sc.error_flags);
+            atomicAdd(d + 6, 1u); atomicAdd(d + 10, total); atomicAdd(d + 11, (uint32_t)__popc(act_mask));
+        }
+#endif
+        if (qn != 0u && (qn >= RT3_DEFER_ITEMS || waiting > RT3_DEFER_BLOCKED || ready_mask == 0u)) {
+#ifdef RT3_STATS
+            if (lane == 0) { uint32_t* d = const_cast<uint32_t*>(sc.error_flags); atomicAdd(d + 7, 1u); atomicAdd(d + 9, qn); }
+#endif
+            __syncwarp();
+            const uint32_t kpack = inv >> 8;
+            for (uint32_t base = 0; base < qn; base += 32u) {
+                s_best[lane] = 0xffffffffu;       // smallest ordered t per owner
+                s_best[32u + lane] = 0xffffffffu; // smallest primitive id among those
+                __syncwarp();
+                const uint32_t g = base + lane;
+                const bool have = g < qn;
+                const uint32_t item = have ? s_items[g] : 0u;
+                const int owner = (int)(item >> 27);
+                const float ox = __shfl_sync(0xffffffffu, o.x, owner), oy = __shfl_sync(0xffffffffu, o.y, owner), oz = __shfl_sync(0xffffffffu, o.z, owner);
+                Shear s;
+                s.Sx = __shfl_sync(0xffffffffu, Sx, owner); s.Sy = __shfl_sync(0xffffffffu, Sy, owner); s.Sz = __shfl_sync(0xffffffffu, Sz, owner);
+                const uint32_t kp = __shfl_sync(0xffffffffu, kpack, owner);
+                const float otmin = __shfl_sync(0xffffffffu, tmin, owner), otbest = __shfl_sync(0xffffffffu, tbest, owner);
+                const int ohprim = __shfl_sync(0xffffffffu, hprim, owner);
+                bool valid = false;
+                float t = 0.0f, u = 0.0f, v = 0.0f;
+                uint32_t id = 0u, key = 0u;
+                if (have) {
+#ifdef RT3_STATS
+                    c_prims++;
+#endif
+                    s.kx = (int)(kp & 3u); s.ky = (int)((kp >> 2) & 3u); s.kz = (int)((kp >> 4) & 3u);
+                    const float4* pr = sc.root_prims + 3u * (item & 0x07ffffffu);
+                    const float4 a = __ldg(pr), b = __ldg(pr + 1), c = __ldg(pr + 2);
+                    id = __float_as_uint(a.w);
+                    // the owner's accept() rule
+                    valid = test_triangle(v3(ox, oy, oz), s, v3(a), v3(b), v3(c), t, u, v) && t > otmin &&
+                            (ohprim < 0 ? t < otbest : (t < otbest || (t == otbest && (int)id < ohprim)));
+                    if (valid) {
+                        const uint32_t tb = __float_as_uint(t);
+                        key = tb ^ ((uint32_t)((int)tb >> 31) | 0x80000000u);  // unsigned order == float order
+                        atomicMin(&s_best[owner], key);
+                    }
+                }
+                __syncwarp();
+                const bool first = valid && s_best[owner] == key;
+                if (first) atomicMin(&s_best[32 + owner], id);
+                __syncwarp();
+                if (first && s_best[32 + owner] == id) s_res[owner] = make_float4(t, u, v, __uint_as_float(id));
+                __syncwarp();
+                if (s_best[lane] != 0xffffffffu) {
+                    const float4 r = s_res[lane];
+                    tbest = r.x; hu = r.y; hv = r.z; hprim = (int)__float_as_uint(r.w);
+                    if (ANY_HIT) { active = false; tg.y = 0u; }
+                }
+                __syncwarp();
+            }
+            qn = 0u;
+            pend = 0u;
+        }
+        if (active && pend == 0u && tg.y == 0u && !(ng.y & 0xff000000u) && sp == 0) active = false;  // nothing left anywhere
         return active;
     }
 #endif

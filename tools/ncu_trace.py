@@ -54,6 +54,9 @@ def run(rays, any_hit, reps=3):
     dc = g.debug_counters()
     if dc[5]:
         print("   per ray: %.1f wide nodes, %.1f prim tests, %.1f rounds" % (dc[2] / dc[5], dc[3] / dc[5], dc[4] / dc[5]))
+        if dc[6]:
+            print("   per warp round: no-triangle %.2f, <=1 per lane %.2f, lanes with triangles %.1f, triangles %.1f, busy lanes %.1f" %
+                  (dc[7] / dc[6], dc[8] / dc[6], dc[9] / dc[6], dc[10] / dc[6], dc[11] / dc[6]))
     return len(rays) / best / 1e3
 
 
