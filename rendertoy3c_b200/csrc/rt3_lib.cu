@@ -83,7 +83,6 @@ struct rt3_context {
     bool has_merged = false, single_level = false;
     int opt_merge = 1;
     int opt_tlas_refine = 1;  // instance boxes from the BLAS root's grandchild boxes instead of its root box
-    DevBuf<uint32_t> d_consts; // [0] = 0x4B000000
     DevBuf<uint32_t> d_flags;  // [0] error flags, [1] max stack
     // film
     uint32_t width = 0, height = 0;
@@ -111,7 +110,8 @@ struct rt3_context {
         s.tlas_nodes = single_level ? m_nodes_p : tlas_nodes.p;
         s.tlas_order = tlas_order.p;
         s.merged_map = m_map.p;
-        s.consts = d_consts.p;
+        s.magic_h2 = 0x64646464u;
+        s.bias_h = -1024.0f;
         s.root_prims = single_level ? m_prims_p : nullptr;
         s.root_is_blas = single_level ? 1u : 0u;
         s.instances = d_inst.p;
@@ -268,8 +268,6 @@ int rt3_context_create(int device, rt3_context_t* out) {
     c->num_sms = prop.multiProcessorCount;
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 #endif
-    c->d_consts.alloc(4);
-    { const uint32_t k[4] = {0x4B000000u, 0u, 0u, 0u}; h2d(c->d_consts.p, k, sizeof(k), c->stream); }
     c->d_flags.alloc(16);  // [0] error flags, [1] max stack, [2..15] diagnostic counters (RT3_STATS builds)
     c->counters.alloc(4 * MAX_DEPTH_SLOTS);
     c->d_stats.alloc(4);

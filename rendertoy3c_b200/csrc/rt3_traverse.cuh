@@ -89,7 +89,8 @@ struct TravScene {
     // reference creates, cuda_scene.h:141-146) are merged into ONE world-space BLAS whose primitive
     // ids index merged_map -> (instance, primitive).  If nothing else is in the scene the TLAS is
     // skipped altogether (root_is_blas) and tlas_nodes points at the merged BLAS.
-    const uint32_t* consts;         // [0] = 0x4B000000 (kept opaque to the compiler on purpose)
+    uint32_t magic_h2;              // 0x64646464 and
+    float bias_h;                   // -1024.0f: see widen_bytes / byte_to_float (kept opaque to the compiler on purpose)
     const uint2* merged_map;
     const float4* root_prims;
     uint32_t root_is_blas;
@@ -249,24 +250,35 @@ RT3_HD uint32_t child_word(uint32_t child_bits4, uint32_t bit_index4, int j) {
 #endif
 }
 
-// quantised byte j of a packed word as float: exact, PRMT + FADD on the device instead of shift/and/I2F
-// `magic` must hold 0x4B000000 in a per-thread register that ptxas cannot treat as a constant (it is
-// loaded from device memory once per kernel): PRMT encodes ONE immediate, and with both operands
-// constant ptxas keeps the bias as the immediate and the selector in a uniform register, which costs
-// a UR->R move in front of every one of the 48 PRMTs of a node step (205 of 1584 SASS instructions).
-RT3_HD float byte_to_float(uint32_t w, int j, uint32_t magic) {
+// The four quantised bytes of a packed word as floats, exact.  Device: bytes (0,1) and (2,3) are widened to
+// fp16 pairs {0x64 b} = 1024 + b with ONE PRMT per pair, and the mixed-precision add of sm_100
+// (add.f32.f16 -> FHADD, half operand selected in place) removes the 1024 and widens to fp32: 24 PRMT +
+// 48 FHADD per wide node instead of 48 PRMT + 48 FADD.  `magic` (0x64646464) and `bias` (-1024.0f) are
+// kernel parameters so that ptxas cannot treat them as constants: PRMT encodes ONE immediate, and with
+// both operands constant ptxas keeps the magic as the immediate and parks the selectors in uniform
+// registers, which costs a UR->R move in front of every PRMT (205 of 1584 SASS instructions, r01k).
+struct Bytes4 { uint32_t h01, h23; };
+RT3_HD Bytes4 widen_bytes(uint32_t w, uint32_t magic) {
+    Bytes4 r;
 #ifdef RT3_EMULATE
     (void)magic;
-    return (float)((w >> (8 * j)) & 0xffu);
+    r.h01 = w; r.h23 = w;
 #else
-    uint32_t r;
-    switch (j) {
-        case 0: asm("prmt.b32 %0, %1, %2, 0x7650;" : "=r"(r) : "r"(w), "r"(magic)); break;
-        case 1: asm("prmt.b32 %0, %1, %2, 0x7651;" : "=r"(r) : "r"(w), "r"(magic)); break;
-        case 2: asm("prmt.b32 %0, %1, %2, 0x7652;" : "=r"(r) : "r"(w), "r"(magic)); break;
-        default: asm("prmt.b32 %0, %1, %2, 0x7653;" : "=r"(r) : "r"(w), "r"(magic)); break;
-    }
-    return __uint_as_float(r) - 8388608.0f;
+    asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(r.h01) : "r"(w), "r"(magic));
+    asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(r.h23) : "r"(w), "r"(magic));
+#endif
+    return r;
+}
+RT3_HD float byte_to_float(const Bytes4& b, int j, float bias) {
+#ifdef RT3_EMULATE
+    (void)bias;
+    return (float)((b.h01 >> (8 * j)) & 0xffu);
+#else
+    float f;
+    const uint32_t h2 = j < 2 ? b.h01 : b.h23;
+    if (j & 1) asm("{\n .reg .b16 lo, hi;\n mov.b32 {lo, hi}, %1;\n add.f32.f16 %0, hi, %2;\n}" : "=f"(f) : "r"(h2), "f"(bias));
+    else asm("{\n .reg .b16 lo, hi;\n mov.b32 {lo, hi}, %1;\n add.f32.f16 %0, lo, %2;\n}" : "=f"(f) : "r"(h2), "f"(bias));
+    return f;
 #endif
 }
 
@@ -326,7 +338,6 @@ struct Trav {
     int cur_inst;      // -1 while in the TLAS
     uint2 ng, tg;
     int sp;
-    uint32_t magic;    // 0x4B000000 from device memory (see byte_to_float)
     uint32_t pend;     // triangles of this lane waiting in the warp's queue (step_warp_deferred)
 #ifdef RT3_STATS
     uint32_t c_nodes, c_prims, c_rounds;  // diagnostic build only (tools/build_variant.sh -DRT3_STATS)
@@ -377,7 +388,6 @@ struct Trav {
 
     RT3_HD void init(const TravScene& sc, float3 ro, float3 rd, float rtmin, float rtmax, float rtime) {
         tmin = rtmin; tbest = rtmax;
-        magic = rt3_ldg(sc.consts);
         pend = 0u;
         hu = hv = 0.0f; hprim = -1;
         if (!SINGLE) hinst = -1;
@@ -511,14 +521,16 @@ struct Trav {
             const uint32_t nx = (oct & 1u) ? lox : hix, fx = (oct & 1u) ? hix : lox;
             const uint32_t ny = (oct & 2u) ? loy : hiy, fy = (oct & 2u) ? hiy : loy;
             const uint32_t nz = (oct & 4u) ? loz : hiz, fz = (oct & 4u) ? hiz : loz;
+            const Bytes4 bnx = widen_bytes(nx, sc.magic_h2), bny = widen_bytes(ny, sc.magic_h2), bnz = widen_bytes(nz, sc.magic_h2);
+            const Bytes4 bfx = widen_bytes(fx, sc.magic_h2), bfy = widen_bytes(fy, sc.magic_h2), bfz = widen_bytes(fz, sc.magic_h2);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float tnx = fmaf(byte_to_float(nx, j, magic), adjx, nox);
-                const float tny = fmaf(byte_to_float(ny, j, magic), adjy, noy);
-                const float tnz = fmaf(byte_to_float(nz, j, magic), adjz, noz);
-                const float tfx = fmaf(byte_to_float(fx, j, magic), adjx, fox);
-                const float tfy = fmaf(byte_to_float(fy, j, magic), adjy, foy);
-                const float tfz = fmaf(byte_to_float(fz, j, magic), adjz, foz);
+                const float tnx = fmaf(byte_to_float(bnx, j, sc.bias_h), adjx, nox);
+                const float tny = fmaf(byte_to_float(bny, j, sc.bias_h), adjy, noy);
+                const float tnz = fmaf(byte_to_float(bnz, j, sc.bias_h), adjz, noz);
+                const float tfx = fmaf(byte_to_float(bfx, j, sc.bias_h), adjx, fox);
+                const float tfy = fmaf(byte_to_float(bfy, j, sc.bias_h), adjy, foy);
+                const float tfz = fmaf(byte_to_float(bfz, j, sc.bias_h), adjz, foz);
                 const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
                 const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
                 hitmask |= (tn <= tf) ? child_word(child_bits4, bit_index4, j) : 0u;
