@@ -259,6 +259,9 @@ RT3_HD uint32_t quant_exponent(float p, float hi) {
     return E;
 }
 
+#ifndef RT3_LEAF_MAX
+#define RT3_LEAF_MAX 3  // primitives per leaf child (the meta byte holds a unary count of up to 3)
+#endif
 RT3_GLOBAL(k_bvh_collapse, BuildArrays b) {
     const uint32_t item = RT3_THREAD_ID();
     if (item >= rt3_n_) return;
@@ -272,7 +275,7 @@ RT3_GLOBAL(k_bvh_collapse, BuildArrays b) {
     // phase 1: open the largest-area child holding more than 3 primitives; phase 2: use free slots
     // to split the remaining multi-primitive leaves (tighter boxes at no extra nodes)
     for (int phase = 0; phase < 2; phase++) {
-        const int min_count = phase == 0 ? 4 : 2;
+        const int min_count = phase == 0 ? RT3_LEAF_MAX + 1 : 2;
         while (nch < 8) {
             int best = -1;
             float best_a = -1.0f;
@@ -321,7 +324,7 @@ RT3_GLOBAL(k_bvh_collapse, BuildArrays b) {
     for (int s = 0; s < 8; s++) {
         if (slot_child[s] < 0) continue;
         const int cnt = bvh2_count(b, ch[slot_child[s]]);
-        if (cnt > 3) imask |= 1u << s;
+        if (cnt > RT3_LEAF_MAX) imask |= 1u << s;
         else nprims += (uint32_t)cnt;
     }
     const uint32_t nint = (uint32_t)rt3_popc(imask);
@@ -353,7 +356,7 @@ RT3_GLOBAL(k_bvh_collapse, BuildArrays b) {
         }
         const int id = ch[c];
         const int cnt = bvh2_count(b, id);
-        if (cnt > 3) {
+        if (cnt > RT3_LEAF_MAX) {
             nd.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
             const uint32_t cw = child_base + (uint32_t)rt3_popc(imask & ((1u << s) - 1u));
             const uint32_t q = rt3_atomic_add(&b.counters[2], 1u);

@@ -282,6 +282,18 @@ RT3_HD float byte_to_float(const Bytes4& b, int j, float bias) {
 #endif
 }
 
+// (a.x * m + c, a.y * m + c), each one IEEE fma like fmaf(): ONE packed FFMA2 on sm_100 (the scalars are broadcast operands)
+RT3_HD float2 fma2(float ax, float ay, float m, float c) {
+#ifdef RT3_EMULATE
+    return make_float2(fmaf(ax, m, c), fmaf(ay, m, c));
+#else
+    float2 r;
+    asm("{\n .reg .b64 a, m, c, d;\n mov.b64 a, {%2, %3};\n mov.b64 m, {%4, %4};\n mov.b64 c, {%5, %5};\n fma.rn.f32x2 d, a, m, c;\n mov.b64 {%0, %1}, d;\n}"
+        : "=f"(r.x), "=f"(r.y) : "f"(ax), "f"(ay), "f"(m), "f"(c));
+    return r;
+#endif
+}
+
 // two fp16 values packed in a word -> float2 (x = low half); exact.  Device: 2 x HADD2.F32
 RT3_HD float2 half2_to_float2(uint32_t w) {
 #ifdef RT3_EMULATE
@@ -524,16 +536,18 @@ struct Trav {
             const Bytes4 bnx = widen_bytes(nx, sc.magic_h2), bny = widen_bytes(ny, sc.magic_h2), bnz = widen_bytes(nz, sc.magic_h2);
             const Bytes4 bfx = widen_bytes(fx, sc.magic_h2), bfy = widen_bytes(fy, sc.magic_h2), bfz = widen_bytes(fz, sc.magic_h2);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float tnx = fmaf(byte_to_float(bnx, j, sc.bias_h), adjx, nox);
-                const float tny = fmaf(byte_to_float(bny, j, sc.bias_h), adjy, noy);
-                const float tnz = fmaf(byte_to_float(bnz, j, sc.bias_h), adjz, noz);
-                const float tfx = fmaf(byte_to_float(bfx, j, sc.bias_h), adjx, fox);
-                const float tfy = fmaf(byte_to_float(bfy, j, sc.bias_h), adjy, foy);
-                const float tfz = fmaf(byte_to_float(bfz, j, sc.bias_h), adjz, foz);
-                const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-                const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
-                hitmask |= (tn <= tf) ? child_word(child_bits4, bit_index4, j) : 0u;
+            for (int pr = 0; pr < 2; pr++) {  // two children per packed fma
+                const int j = 2 * pr;
+                const float2 tnx = fma2(byte_to_float(bnx, j, sc.bias_h), byte_to_float(bnx, j + 1, sc.bias_h), adjx, nox);
+                const float2 tny = fma2(byte_to_float(bny, j, sc.bias_h), byte_to_float(bny, j + 1, sc.bias_h), adjy, noy);
+                const float2 tnz = fma2(byte_to_float(bnz, j, sc.bias_h), byte_to_float(bnz, j + 1, sc.bias_h), adjz, noz);
+                const float2 tfx = fma2(byte_to_float(bfx, j, sc.bias_h), byte_to_float(bfx, j + 1, sc.bias_h), adjx, fox);
+                const float2 tfy = fma2(byte_to_float(bfy, j, sc.bias_h), byte_to_float(bfy, j + 1, sc.bias_h), adjy, foy);
+                const float2 tfz = fma2(byte_to_float(bfz, j, sc.bias_h), byte_to_float(bfz, j + 1, sc.bias_h), adjz, foz);
+                const float tn0 = fmaxf(fmaxf(tnx.x, tny.x), fmaxf(tnz.x, tmin)), tf0 = fminf(fminf(tfx.x, tfy.x), fminf(tfz.x, tbest));
+                const float tn1 = fmaxf(fmaxf(tnx.y, tny.y), fmaxf(tnz.y, tmin)), tf1 = fminf(fminf(tfx.y, tfy.y), fminf(tfz.y, tbest));
+                hitmask |= (tn0 <= tf0) ? child_word(child_bits4, bit_index4, j) : 0u;
+                hitmask |= (tn1 <= tf1) ? child_word(child_bits4, bit_index4, j + 1) : 0u;
             }
 #endif
         }
@@ -786,7 +800,7 @@ struct Trav {
     // is the valid candidate with the smallest (t, primitive id) — which is what accept() yields for any
     // order of the same candidates — found with shared-memory atomicMin in two steps (t, then id among
     // equal t).  A late tbest only means a few more nodes are visited; the result is the same.
-    __device__ __forceinline__ bool step_warp_deferred(const TravScene& sc, bool active, uint32_t* s_items, float4* s_res, uint32_t* s_best, uint32_t& qn) {
+    __device__ __forceinline__ bool step_warp_deferred(const TravScene& sc, bool active, uint32_t* s_items, float4* s_res, uint32_t* s_best) {
         static_assert(SINGLE, "deferred queue: single-level kernel only");
         const uint32_t lane = threadIdx.x & 31u;
         if (active && tg.y == 0u) {  // (triangles that did not fit the queue last round are queued first)
@@ -796,35 +810,27 @@ struct Trav {
             while (!(ng.y & 0xff000000u) && sp != 0) ng = st_get(--sp);  // the stack holds node groups only here
             if (ng.y & 0xff000000u) node_step(sc);
         }
-        // ---- queue this round's triangles (warp-uniform control flow from here)
-        const uint32_t cnt = (active && tg.y != 0u) ? (uint32_t)__popc(tg.y) : 0u;
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if ((int)lane >= d) incl += v;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total != 0u) {
-            if (cnt != 0u) {
-                uint32_t m = tg.y, pos = qn + incl - cnt;
-                while (m != 0u && pos < RT3_QCAP) {
-                    const uint32_t b = (uint32_t)(__ffs((int)m) - 1);
-                    m &= m - 1u;
-                    s_items[pos++] = (lane << 27) | (tg.x + b);
-                    pend++;
-                }
-                tg.y = m;
+        // ---- queue this round's triangles: the few lanes that have some reserve their slots with one shared-
+        // memory atomicAdd each (the order of the pairs does not matter to the fold)
+        if (active && tg.y != 0u) {
+            uint32_t m = tg.y, pos = atomicAdd(&s_items[RT3_QCAP], (uint32_t)__popc(m));
+            while (m != 0u && pos < RT3_QCAP) {
+                const uint32_t b = (uint32_t)(__ffs((int)m) - 1);
+                m &= m - 1u;
+                s_items[pos++] = (lane << 27) | (tg.x + b);
+                pend++;
             }
-            qn = qn + total < RT3_QCAP ? qn + total : RT3_QCAP;
+            tg.y = m;  // what did not fit waits in the lane (and forces the pass below)
         }
+        __syncwarp();
+        const uint32_t qn = s_items[RT3_QCAP] < RT3_QCAP ? s_items[RT3_QCAP] : RT3_QCAP;  // warp-uniform from here
         const bool ready = active && tg.y == 0u && ((ng.y & 0xff000000u) != 0u || sp != 0);
         const uint32_t act_mask = __ballot_sync(0xffffffffu, active), ready_mask = __ballot_sync(0xffffffffu, ready);
         const uint32_t waiting = (uint32_t)(__popc(act_mask) - __popc(ready_mask));  // lanes that wait for the pass (or could not queue)
 #ifdef RT3_STATS
         if (lane == 0) {
             uint32_t* d = const_cast<uint32_t*>(sc.error_flags);
-            atomicAdd(d + 6, 1u); atomicAdd(d + 10, total); atomicAdd(d + 11, (uint32_t)__popc(act_mask));
+            atomicAdd(d + 6, 1u); atomicAdd(d + 11, (uint32_t)__popc(act_mask));
         }
 #endif
         if (qn != 0u && (qn >= RT3_DEFER_ITEMS || waiting > RT3_DEFER_BLOCKED || ready_mask == 0u)) {
@@ -880,8 +886,9 @@ struct Trav {
                 }
                 __syncwarp();
             }
-            qn = 0u;
+            if (lane == 0) s_items[RT3_QCAP] = 0u;
             pend = 0u;
+            __syncwarp();
         }
         if (active && pend == 0u && tg.y == 0u && !(ng.y & 0xff000000u) && sp == 0) active = false;  // nothing left anywhere
         return active;

@@ -114,10 +114,11 @@ __global__ void __launch_bounds__(RT3_TRAV_THREADS, SINGLE ? RT3_TRAV_MIN_BLOCKS
     const uint32_t lt_mask = (1u << lane) - 1u;
 #if RT3_COOP
     constexpr bool DEFER = SINGLE && RT3_DEFER;
-    __shared__ uint32_t s_items[RT3_TRAV_THREADS / 32][DEFER ? RT3_QCAP : RT3_COOP_CAP];
+    __shared__ uint32_t s_items[RT3_TRAV_THREADS / 32][DEFER ? RT3_QCAP + 1 : RT3_COOP_CAP];  // deferred queue: [RT3_QCAP] = its fill count
     __shared__ float4 s_res[RT3_TRAV_THREADS / 32][32];
     __shared__ uint32_t s_best[DEFER ? RT3_TRAV_THREADS / 32 : 1][64];
-    uint32_t qn = 0;  // pairs in this warp's triangle queue (warp-uniform)
+    if (DEFER && (threadIdx.x & 31u) == 0u) s_items[threadIdx.x >> 5][DEFER ? RT3_QCAP : 0] = 0u;
+    __syncwarp();
 #endif
     Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY), SINGLE> tr;
     uint2 stack_mem[RT3_STACK_SIZE + FR_COUNT];
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(RT3_TRAV_THREADS, SINGLE ? RT3_TRAV_MIN_BLOCKS
         while (__popc(busy) >= threshold) {
 #if RT3_COOP
             const bool was = active;
-            if constexpr (DEFER) active = tr.step_warp_deferred(a.scene, active, s_items[threadIdx.x >> 5], s_res[threadIdx.x >> 5], s_best[threadIdx.x >> 5], qn);
+            if constexpr (DEFER) active = tr.step_warp_deferred(a.scene, active, s_items[threadIdx.x >> 5], s_res[threadIdx.x >> 5], s_best[threadIdx.x >> 5]);
             else active = tr.step_warp(a.scene, active, s_items[threadIdx.x >> 5], s_res[threadIdx.x >> 5]);
             if (was && !active) trav_end<MODE, SINGLE>(a, my, tr);
 #else
