@@ -310,12 +310,14 @@ def run_rt3(args):
         achieved = BYTES_PER_RAY_EXTEND * ext_rays / (ext_ms * 1e-3) / 1e9
         # DRAM bytes of the extend launches of one step, from the committed ncu capture of this command
         traffic = None
-        shares = os.path.join(ROOT, "profiles", "r01j_launch_shares.json")
-        if os.path.exists(shares) and (args.grid, args.width, args.height) == (708, 1920, 1080):
+        import glob
+        cand = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_launch_shares.json")))  # newest committed capture
+        shares = cand[-1] if cand else ""
+        if shares and (args.grid, args.width, args.height) == (708, 1920, 1080):
             k = json.load(open(shares))["kernels"].get("k_traverse<0, 1>")
             if k:
                 traffic = {"bytes_per_step": (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6, "launches_per_step": k["launches"],
-                           "algorithmic_bytes_per_step": BYTES_PER_RAY_EXTEND * ext_rays / 2, "source": "profiles/r01j_launches.csv (ncu dram__bytes_read/write.sum)"}
+                           "algorithmic_bytes_per_step": BYTES_PER_RAY_EXTEND * ext_rays / 2, "source": "profiles/%s (ncu dram__bytes_read/write.sum of this command)" % os.path.basename(shares)}
         out = {
             "metric": METRIC, "value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
