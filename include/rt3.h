@@ -45,7 +45,7 @@ typedef struct {
     uint32_t subframe_index;       /* film_settings.subframe_index: seeds tea<4>(pixel, subframe) (src/shader/raygen.cu:25) */
     float eye[3], U[3], V[3], W[3];/* camera_settings (sutil/Camera.cpp:34-45) */
     int32_t max_depth;             /* extension: max extension rays per path; <=0 = unbounded like the reference (src/shader/raygen.cu:48) */
-    int32_t mode;                  /* 0 = REFERENCE_FAITHFUL estimator (quirks Q2-Q8 reproduced); 1 = CORRECTED: unbiased Lambert + NEE + MIS */
+    int32_t mode;                  /* 0 = REFERENCE_FAITHFUL estimator (quirks Q2-Q8 reproduced); 1 = CORRECTED: unbiased Lambert + NEE + MIS; 2 = CORRECTED with lights chosen in proportion to luminance(emission) x area (the reference README's unchecked "power light sampler") */
     float miss_color[3];           /* __direct_callable__test returns (0.01,0.01,0.01) (src/shader/test.cu:5) */
     int32_t accum_mode;            /* 0 = running mean exactly as src/shader/raygen.cu:79-85; 1 = per-pixel SUM of subframe means (for the multi-GPU reduce) */
 } rt3_render_settings;

@@ -234,6 +234,7 @@ struct rt3o_scene {
     std::vector<Instance> inst;
     std::vector<Texture> tex;
     std::vector<Light> lights;
+    std::vector<float> light_cdf;  // running sum of luminance(emission) * area (mode 2, power light sampler)
     Bvh2 tlas;
     bool built = false;
     uint32_t w = 0, h = 0;
@@ -422,7 +423,23 @@ struct rt3o_scene {
     //   * BSDF-sampled emitter hits count at every depth with the complementary MIS weight     (Q3)
     //   * Russian roulette with p = min(lum(throughput), 1)                                    (Q5)
     // Emissive meshes must be identity instances (the light list holds object-space vertices, Q15).
+    // mode 2 (the reference README's unchecked "power light sampler"): light k is chosen with
+    // probability power_k / total, power = luminance(emission) * area; cdf = sequential fp32 running sum
+    uint32_t pick_light_by_power(float xi01, float& p_sel) const {
+        const uint32_t nl = (uint32_t)lights.size();
+        const float total = light_cdf[nl - 1];
+        const float xi = xi01 * total;
+        uint32_t lo = 0, hi = nl - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (xi < light_cdf[mid]) hi = mid; else lo = mid + 1;
+        }
+        p_sel = light_power(lights[lo].emission, lights[lo].area) / total;
+        return lo;
+    }
+
     f3 render_pixel_corrected(const rt3_render_settings& rs, uint32_t x, uint32_t y, int accel, uint64_t cnt[3]) const {
+        const bool by_power = rs.mode == 2 && light_cdf.back() > 0.0f;
         const uint32_t w = rs.width, h = rs.height;
         const f3 eye = {rs.eye[0], rs.eye[1], rs.eye[2]}, U = {rs.U[0], rs.U[1], rs.U[2]}, V = {rs.V[0], rs.V[1], rs.V[2]},
                  W = {rs.W[0], rs.W[1], rs.W[2]};
@@ -463,14 +480,17 @@ struct rt3o_scene {
                         const float area = 0.5f * length(nrm);
                         const float cos_l = fabsf(dot(normalize(nrm), dir));
                         const float dist2 = hit.t * hit.t * dot(dir, dir);
-                        const float pdf_light = dist2 / ((float)nl * area * cos_l);
+                        const float pdf_light = by_power ? (dist2 / (area * cos_l)) * (light_power(in.emission, area) / light_cdf.back())
+                                                         : dist2 / ((float)nl * area * cos_l);
                         wgt = power_heuristic(pdf_prev, pdf_light);
                     }
                     L = L + beta * in.emission * wgt;
                 }
                 const f3 albedo = in.tex >= 0 ? fetch_texture(in.tex, uv.x, uv.y) : in.diffuse;
                 // next event estimation
-                const Light& lt = lights[(int)(rnd(seed) * (float)nl)];
+                float p_sel = 0.0f;
+                const float xi_l = rnd(seed);
+                const Light& lt = lights[by_power ? pick_light_by_power(xi_l, p_sel) : (uint32_t)(int)(xi_l * (float)nl)];
                 const float u = rnd(seed);
                 const float v = rnd(seed);
                 const float su0 = sqrtf(u);
@@ -484,7 +504,7 @@ struct rt3o_scene {
                     const float cos_s = dot(Ns, Ld);
                     const float cos_l = fabsf(dot(Ld, lt.normal));
                     if (cos_s > 0.0f && cos_l > 0.0f && lt.area > 0.0f) {
-                        const float pdf_light = dist2 / ((float)nl * lt.area * cos_l);
+                        const float pdf_light = by_power ? (dist2 / (lt.area * cos_l)) * p_sel : dist2 / ((float)nl * lt.area * cos_l);
                         const float pdf_bsdf = cos_s * inv_pi;
                         const float wgt = power_heuristic(pdf_light, pdf_bsdf);
                         const f3 contrib = beta * albedo * lt.emission * (inv_pi * cos_s * wgt / pdf_light);
@@ -756,6 +776,12 @@ int rt3o_scene_set_lights(rt3o_scene* s, const void* lights68, int n) {
     if (!s || !lights68 || n <= 0) { g_err = "set_lights: need at least one light (Q17)"; return -1; }
     s->lights.resize(n);
     std::memcpy(s->lights.data(), lights68, sizeof(Light) * n);
+    s->light_cdf.resize(n);
+    float run = 0.0f;
+    for (int k = 0; k < n; k++) {
+        run = run + light_power(s->lights[k].emission, s->lights[k].area);
+        s->light_cdf[k] = run;
+    }
     return 0;
 }
 
@@ -792,7 +818,7 @@ int rt3o_launch_subframe(rt3o_scene* s, const rt3_render_settings* rs, int nthre
         int bx = (tile % tx) * 16, by = (tile / tx) * 16;
         for (int y = by; y < std::min(by + 16, H); y++)
             for (int x = bx; x < std::min(bx + 16, W); x++) {
-                f3 c = rs->mode == 1 ? s->render_pixel_corrected(*rs, (uint32_t)x, (uint32_t)y, 1, cnt) : s->render_pixel(*rs, (uint32_t)x, (uint32_t)y, 1, cnt);
+                f3 c = rs->mode != 0 ? s->render_pixel_corrected(*rs, (uint32_t)x, (uint32_t)y, 1, cnt) : s->render_pixel(*rs, (uint32_t)x, (uint32_t)y, 1, cnt);
                 size_t pi = (size_t)y * W + x;
                 float* a = &s->accum[4 * pi];
                 if (rs->accum_mode == 0) {  // raygen.cu:75-86

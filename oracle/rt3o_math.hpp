@@ -126,6 +126,9 @@ struct Light {
 };
 static_assert(sizeof(Light) == 68, "rendertoy Light layout is 68 bytes");
 
+// selection weight of the power light sampler (mode 2): luminance with the Russian-roulette weights of raygen.cu:66, times area
+static inline float light_power(f3 emission, float area) { return (emission.x * 0.30f + emission.y * 0.59f + emission.z * 0.11f) * area; }
+
 static inline Light light_make(f3 emission, f3 v0, f3 v1, f3 v2) {  // light.h:24-30
     Light l;
     l.type = 0; l.emission = emission; l.v0 = v0; l.v1 = v1; l.v2 = v2;

@@ -85,7 +85,7 @@ def make_settings(desc, uvw, subframe_index=0, samples_per_launch=8, accum_mode=
         rs.U[i], rs.V[i], rs.W[i] = float(U[i]), float(V[i]), float(W[i])
         rs.miss_color[i] = miss
     rs.max_depth = desc.max_depth if max_depth is None else max_depth
-    rs.mode = mode  # 0 = REFERENCE_FAITHFUL, 1 = CORRECTED
+    rs.mode = mode  # 0 = REFERENCE_FAITHFUL, 1 = CORRECTED, 2 = CORRECTED + power light sampler
     rs.accum_mode = accum_mode
     return rs
 

@@ -66,6 +66,7 @@ struct rt3_context {
     DevBuf<float> d_keys, d_static;
     DevBuf<TexDev> d_tex;
     DevBuf<Light> d_lights;
+    DevBuf<float> d_light_cdf;  // running sum of the power-sampler weights (mode 2)
     uint32_t nlights = 0;
     DevBuf<Node8> tlas_nodes;
     DevBuf<uint32_t> tlas_order;
@@ -576,6 +577,18 @@ int rt3_scene_set_lights(rt3_context_t c, const void* lights68, int n) {
     RT3_REQUIRE(c && lights68 && n > 0, RT3_ERR_INVALID, "set_lights: at least one light is required (Q17)");
     c->d_lights.alloc(n);
     h2d(c->d_lights.p, lights68, sizeof(Light) * (size_t)n, c->stream);
+    // running sum of the power-sampler weights (mode 2); sequential fp32, same recipe as the kernels' light_power()
+    std::vector<float> cdf((size_t)n);
+    const Light* L = static_cast<const Light*>(lights68);
+    float run = 0.0f;
+    for (int k = 0; k < n; k++) {
+        Light l;
+        memcpy(&l, reinterpret_cast<const char*>(L) + sizeof(Light) * (size_t)k, sizeof(l));
+        run = run + (l.emission[0] * 0.30f + l.emission[1] * 0.59f + l.emission[2] * 0.11f) * l.area;
+        cdf[(size_t)k] = run;
+    }
+    c->d_light_cdf.alloc(n);
+    h2d(c->d_light_cdf.p, cdf.data(), sizeof(float) * (size_t)n, c->stream);
     stream_sync(c->stream);
     c->nlights = (uint32_t)n;
     RT3_API_END
@@ -621,7 +634,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
     RT3_REQUIRE(c->built, RT3_ERR_STATE, "launch_subframe: rt3_accel_build has not been called");
     RT3_REQUIRE(c->nlights > 0, RT3_ERR_STATE, "launch_subframe: no lights set (Q17)");
     RT3_REQUIRE(rs->width > 0 && rs->height > 0 && rs->samples_per_launch > 0, RT3_ERR_INVALID, "launch_subframe: bad film settings");
-    RT3_REQUIRE(rs->mode == 0 || rs->mode == 1, RT3_ERR_UNSUPPORTED, "launch_subframe: mode must be 0 (REFERENCE_FAITHFUL) or 1 (CORRECTED)");
+    RT3_REQUIRE(rs->mode >= 0 && rs->mode <= 2, RT3_ERR_UNSUPPORTED, "launch_subframe: mode must be 0 (REFERENCE_FAITHFUL), 1 (CORRECTED) or 2 (CORRECTED + power light sampler)");
     const uint64_t paths64 = (uint64_t)rs->width * rs->height * rs->samples_per_launch;
     RT3_REQUIRE(paths64 < 0xfffffff0ull, RT3_ERR_INVALID, "launch_subframe: too many paths per launch");
     const uint32_t P = (uint32_t)paths64;
@@ -633,7 +646,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
     f.width = rs->width; f.height = rs->height; f.spl = rs->samples_per_launch; f.subframe = rs->subframe_index;
     for (int k = 0; k < 3; k++) { f.eye[k] = rs->eye[k]; f.U[k] = rs->U[k]; f.V[k] = rs->V[k]; f.W[k] = rs->W[k]; f.miss[k] = rs->miss_color[k]; }
     f.max_depth = rs->max_depth; f.accum_mode = rs->accum_mode; f.mode = rs->mode;
-    f.lights = c->d_lights.p; f.nlights = c->nlights; f.tex = c->d_tex.p;
+    f.lights = c->d_lights.p; f.nlights = c->nlights; f.light_cdf = c->d_light_cdf.p; f.tex = c->d_tex.p;
     const TravScene sc = c->trav_scene();
 
     uint32_t* cnt = c->counters.p;  // [0,M): rays per depth  [M,2M): shadow rays per depth  [2M,3M): extend fetch  [3M,4M): connect fetch

@@ -363,9 +363,10 @@ struct FrameParams {
     uint32_t width, height, spl, subframe;
     float eye[3], U[3], V[3], W[3];
     float miss[3];
-    int32_t max_depth, accum_mode, mode;  // mode 0 = REFERENCE_FAITHFUL, 1 = CORRECTED (unbiased)
+    int32_t max_depth, accum_mode, mode;  // mode 0 = REFERENCE_FAITHFUL, 1 = CORRECTED (unbiased), 2 = CORRECTED + power light sampler
     const Light* lights;
     uint32_t nlights;
+    const float* light_cdf;               // running sum of light_power() over the lights (mode 2)
     const TexDev* tex;
 };
 
@@ -612,6 +613,9 @@ RT3_HD void shade_slot(const FrameParams& f, const TravScene& sc, const Queues& 
 // render_pixel_corrected): throughput *= albedo, NEE with solid-angle light pdf and power-heuristic
 // MIS against the cosine lobe, BSDF-sampled emitter hits weighted by the complementary heuristic,
 // Russian roulette with p = min(luminance, 1), one ray time per path.
+// selection weight of the power light sampler (mode 2): luminance (the Russian-roulette weights of raygen.cu:66) x area
+RT3_HD float light_power(float3 e, float area) { return (e.x * 0.30f + e.y * 0.59f + e.z * 0.11f) * area; }
+
 RT3_HD void shade_slot_corrected(const FrameParams& f, const TravScene& sc, const Queues& q, uint32_t i, bool valid) {
     bool push_ray = false, push_shadow = false;
     float3 P = v3(0, 0, 0), ndir = v3(0, 0, 0), Ld = v3(0, 0, 0), beta = v3(0, 0, 0), contrib = v3(0, 0, 0);
@@ -631,6 +635,8 @@ RT3_HD void shade_slot_corrected(const FrameParams& f, const TravScene& sc, cons
         seed = rt3_f2u(s0.w);
         depth = rt3_f2u(s1.w);
         const float inv_pi = (float)(1.0 / 3.14159265358979323846);
+        const float light_total = f.mode == 2 ? f.light_cdf[f.nlights - 1u] : 0.0f;
+        const bool by_power = light_total > 0.0f;
         if (h.prim < 0) {
             const float3 c = mul(beta, ld3(f.miss));
             float4 r = q.result[path];
@@ -651,7 +657,8 @@ RT3_HD void shade_slot_corrected(const FrameParams& f, const TravScene& sc, cons
                     const float area = 0.5f * length(nrm);
                     const float cos_l = fabsf(dot(normalize(nrm), dir));
                     const float dist2 = h.t * h.t * dot(dir, dir);
-                    const float pdf_light = dist2 / ((float)f.nlights * area * cos_l);
+                    const float pdf_light = by_power ? (dist2 / (area * cos_l)) * (light_power(ld3(hg.emission), area) / light_total)
+                                                     : dist2 / ((float)f.nlights * area * cos_l);
                     wgt = power_heuristic(pdf_prev, pdf_light);
                 }
                 const float3 c = mul(mul(beta, ld3(hg.emission)), wgt);
@@ -661,7 +668,22 @@ RT3_HD void shade_slot_corrected(const FrameParams& f, const TravScene& sc, cons
             }
             const float3 albedo = hg.tex >= 0 ? fetch_texture(f.tex[hg.tex], lg.UV.x, lg.UV.y) : ld3(hg.diffuse);
             // next event estimation
-            const Light* lt = f.lights + (int)(rnd(seed) * (float)f.nlights);
+            const float xi_l = rnd(seed);
+            float p_sel = 0.0f;
+            uint32_t lk;
+            if (by_power) {  // smallest k with xi < cdf[k]
+                const float xi = xi_l * light_total;
+                uint32_t lo = 0, hi = f.nlights - 1u;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (xi < f.light_cdf[mid]) hi = mid; else lo = mid + 1u;
+                }
+                lk = lo;
+                p_sel = light_power(ld3(f.lights[lk].emission), f.lights[lk].area) / light_total;
+            } else {
+                lk = (uint32_t)(int)(xi_l * (float)f.nlights);
+            }
+            const Light* lt = f.lights + lk;
             const float u = rnd(seed);
             const float v = rnd(seed);
             const float su0 = sqrtf(u);
@@ -675,7 +697,7 @@ RT3_HD void shade_slot_corrected(const FrameParams& f, const TravScene& sc, cons
                 const float cos_s = dot(Ns, Ld);
                 const float cos_l = fabsf(dot(Ld, ld3(lt->normal)));
                 if (cos_s > 0.0f && cos_l > 0.0f && lt->area > 0.0f) {
-                    const float pdf_light = dist2 / ((float)f.nlights * lt->area * cos_l);
+                    const float pdf_light = by_power ? (dist2 / (lt->area * cos_l)) * p_sel : dist2 / ((float)f.nlights * lt->area * cos_l);
                     const float pdf_bsdf = cos_s * inv_pi;
                     const float wgt = power_heuristic(pdf_light, pdf_bsdf);
                     contrib = mul(mul(mul(beta, albedo), ld3(lt->emission)), inv_pi * cos_s * wgt / pdf_light);

@@ -23,6 +23,26 @@ def analytic_radiance(albedo=0.5, le=10.0, a=1.0, b=1.0, h=1.0):
     return albedo * le * 4 * corner
 
 
+def _corner(X, Y):
+    """configuration factor from a surface point to a rectangle X x Y (in units of its height) with one corner on the point's normal"""
+    return (X / np.sqrt(1 + X * X) * np.arctan(Y / np.sqrt(1 + X * X)) + Y / np.sqrt(1 + Y * Y) * np.arctan(X / np.sqrt(1 + Y * Y))) / (2 * np.pi)
+
+
+def two_light_scene(width=24, height=24):
+    """furnace_scene plus a second, dim emitter (Le=1) of the same size next to the first (x in [1,3]): the power
+    sampler (mode 2) picks it 1 time in 11, the uniform sampler every other time; both must converge to the same value"""
+    d = furnace_scene(width, height)
+    dim = _quad_mesh([[[1, 1, -1], [3, 1, -1], [3, 1, 1], [1, 1, 1]]])
+    d.geoms.append(dim)
+    d.camera.fovy = 0.5  # the dim emitter is off-centre: its factor varies linearly across the footprint, keep the footprint small
+    d.instances.append(Instance(2, diffuse=(0.0, 0.0, 0.0), emission=(1.0, 1.0, 1.0)))
+    return d
+
+
+def analytic_two_lights(albedo=0.5, le_a=10.0, le_b=1.0):
+    return albedo * (le_a * 4 * _corner(1.0, 1.0) + le_b * 2 * (_corner(3.0, 1.0) - _corner(1.0, 1.0)))
+
+
 def render_mean(backend, desc, subframes, mode, max_depth):
     uvw = backend.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, desc.width / desc.height)
     backend.clear_accum() if hasattr(backend, "clear_accum") else None

@@ -58,9 +58,10 @@ def test_adversarial_geometry_bit_exact(emul_lib, offset):
         check_render(e, o, desc, subframes=1)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name", ["cornell", "terrain", "motion"])
-def test_corrected_mode_matches_oracle(emul_lib, name):
+def test_corrected_mode_matches_oracle(emul_lib, name, mode):
     desc = SMALL[name]()
     with Context(0, lib_path=emul_lib) as e:
         o = build_pair(desc, e)
-        check_render(e, o, desc, subframes=2, mode=1)
+        check_render(e, o, desc, subframes=2, mode=mode)

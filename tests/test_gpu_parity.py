@@ -94,13 +94,25 @@ def test_adversarial_geometry_bit_exact(product_lib, offset):
         check_render(g, o, desc, subframes=2)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name", sorted(SMALL))
-def test_corrected_mode_matches_oracle(product_lib, name):
-    """mode 1 (unbiased Lambert + NEE + MIS): bit-identical to the oracle's corrected integrator"""
+def test_corrected_mode_matches_oracle(product_lib, name, mode):
+    """mode 1 (unbiased Lambert + NEE + MIS) and mode 2 (the same with the power light sampler):
+    bit-identical to the oracle's corrected integrator"""
     desc = SMALL[name]()
     with Context(0) as g:
         o = build_pair(desc, g)
-        check_render(g, o, desc, subframes=2, mode=1)
+        check_render(g, o, desc, subframes=2, mode=mode)
+
+
+def test_power_light_sampler_analytic_two_lights(product_lib):
+    import corrected_cases as cc
+    desc = cc.two_light_scene(width=64, height=64)
+    want = cc.analytic_two_lights()
+    with Context(0) as g:
+        scenes.replay(desc, g)
+        got = cc.render_mean(g, desc, subframes=32, mode=2, max_depth=2)
+    assert abs(got - want) / want < 0.02, (got, want)
 
 
 def test_corrected_mode_analytic_direct_lighting(product_lib):

@@ -282,3 +282,18 @@ def test_corrected_mode_matches_analytic_direct_lighting():
     scenes.replay(desc, o2)
     faithful = cc.render_mean(o2, desc, subframes=24, mode=0, max_depth=2)
     assert abs(faithful - want) / want > 0.1                               # documents that mode 0 is not physically correct (F6)
+
+
+def test_power_light_sampler_matches_analytic_two_lights():
+    """N4 / reference README "power light sampler": mode 2 chooses lights in proportion to luminance x area; with a
+    bright and a dim emitter it converges to the same closed form as the uniform sampler (mode 1), from different samples"""
+    import corrected_cases as cc
+    desc = cc.two_light_scene()
+    want = cc.analytic_two_lights()
+    got = {}
+    for mode in (1, 2):
+        o = ob.OracleScene()
+        scenes.replay(desc, o)
+        got[mode] = cc.render_mean(o, desc, subframes=24, mode=mode, max_depth=2)
+        assert abs(got[mode] - want) / want < 0.02, (mode, got[mode], want)
+    assert got[1] != got[2]
