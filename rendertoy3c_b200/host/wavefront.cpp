@@ -18,7 +18,7 @@ using namespace rt3host;
 
 int main(int argc, char** argv) {
     std::string scene, out = "out.ppm";
-    int width = 768, height = 768, spp = 64, spl = 8, max_depth = 0, gpus = 1;  // reference defaults (wavefront.cpp:55,300)
+    int width = 768, height = 768, spp = 64, spl = 8, max_depth = 0, gpus = 1, mode = 0;  // reference defaults (wavefront.cpp:55,300)
     float eye[3] = {5, 5, 5}, lookat[3] = {0, 1, 0}, up[3] = {0, 1, 0}, fovy = 45.0f;  // initCameraState, wavefront.cpp:238-243
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
@@ -31,6 +31,7 @@ int main(int argc, char** argv) {
         else if (a == "--spl") spl = std::atoi(argv[++i]);
         else if (a == "--max-depth") max_depth = std::atoi(argv[++i]);
         else if (a == "--gpus") gpus = std::atoi(argv[++i]);
+        else if (a == "--mode") mode = std::atoi(argv[++i]);  // 0 reference-faithful, 1 corrected, 2 corrected + power light sampler
         else if (a == "--fovy") fovy = (float)std::atof(argv[++i]);
         else if (a == "--eye") f3(eye);
         else if (a == "--lookat") f3(lookat);
@@ -50,6 +51,7 @@ int main(int argc, char** argv) {
         }
         RenderSettings params(width, height, (unsigned)spl);
         params.max_depth = max_depth;
+        params.mode = mode;
         params.accum_mode = gpus > 1 ? 1 : 0;
         for (int k = 0; k < 3; ++k) params.eye[k] = eye[k];
         RT3HOST_CHECK(rt3_camera_uvw(eye, lookat, up, fovy, (float)width / (float)height, params.U, params.V, params.W));  // handleCameraUpdate
