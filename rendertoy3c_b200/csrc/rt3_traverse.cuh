@@ -821,6 +821,9 @@ struct Trav {
                 pend++;
             }
             tg.y = m;  // what did not fit waits in the lane (and forces the pass below)
+#ifdef RT3_STATS
+            if (m != 0u) atomicAdd(const_cast<uint32_t*>(sc.error_flags) + 12, 1u);  // queue-full events
+#endif
         }
         __syncwarp();
         const uint32_t qn = s_items[RT3_QCAP] < RT3_QCAP ? s_items[RT3_QCAP] : RT3_QCAP;  // warp-uniform from here

@@ -55,3 +55,43 @@ def make_rays(off, n=4000, seed=9):
     rays["tmax"] = 1e16
     rays["time"] = rng.rand(n).astype(np.float32)
     return rays
+
+
+def make_stacked_scene(layers=48, n=6):
+    """ONE static identity mesh (-> the single-level kernel and its deferred triangle queue): an n x n flat grid,
+    `layers` copies, half of them exactly coincident (exact-t ties between many primitives: the lowest id must win)
+    and half a hair apart.  A ray down the stack has dozens of triangles pending per round, far more than the
+    per-warp queue holds, so the partial-queue / forced-pass path and the order-free fold are exercised."""
+    g = scenes.grid_mesh(n, n, lambda U, V: np.stack([U * 2 - 1, 0 * U, V * 2 - 1], axis=-1))
+    verts, idx = [], []
+    for k in range(layers):
+        v = g.verts.copy()
+        if k % 2:
+            v[:, 1] += np.float32(1e-4 * k)
+        idx.append(g.idx + len(g.verts) * k)
+        verts.append(v)
+    verts = np.concatenate(verts).astype(np.float32)
+    idx = np.concatenate(idx).astype(np.int32)
+    normals = np.tile(np.array([[0, 1, 0]], np.float32), (len(verts), 1))
+    uvs = np.zeros((len(verts), 2), np.float32)
+    mesh = Geometry("mesh", verts=verts, idx=idx, normals=normals, uvs=uvs)
+    light = scenes.grid_mesh(1, 1, lambda U, V: np.stack([U - 0.5, 0 * U + 2.0, V - 0.5], axis=-1))
+    inst = [Instance(0, diffuse=(0.7, 0.6, 0.5)), Instance(1, emission=(5.0, 5.0, 5.0))]
+    cam = scenes.Camera(eye=(0.3, 2.5, 1.5), lookat=(0.0, 0.0, 0.0))
+    return scenes.SceneDesc("stacked", [mesh, light], inst, [], cam, 40, 30, 8, 3)
+
+
+def make_stacked_rays(n=6000, seed=5):
+    rng = np.random.RandomState(seed)
+    rays = np.zeros(n, RAY_DTYPE)
+    o = rng.rand(n, 3).astype(np.float32) * np.array([2.4, 0, 2.4], np.float32) - np.array([1.2, 0, 1.2], np.float32)
+    o[:, 1] = rng.choice([-1.0, 1.5], n).astype(np.float32)          # from below and from above
+    d = rng.randn(n, 3).astype(np.float32) * np.float32(0.3)
+    d[:, 1] = -np.sign(o[:, 1])
+    d[: n // 4, 0] = 0.0
+    d[: n // 4, 2] = 0.0                                             # straight through every layer
+    rays["o"] = o
+    rays["d"] = d
+    rays["tmin"] = 0.0
+    rays["tmax"] = 1e16
+    return rays

@@ -65,3 +65,13 @@ def test_corrected_mode_matches_oracle(emul_lib, name, mode):
     with Context(0, lib_path=emul_lib) as e:
         o = build_pair(desc, e)
         check_render(e, o, desc, subframes=2, mode=mode)
+
+
+def test_stacked_layers_ties(emul_lib):
+    """the simulator's per-lane loop on the stacked-layer scene (the GPU suite runs it through the deferred queue)"""
+    import adversarial
+    desc = adversarial.make_stacked_scene(layers=16)
+    with Context(0, lib_path=emul_lib) as e:
+        o = build_pair(desc, e)
+        ho = check_trace(e, o, adversarial.make_stacked_rays(n=1500), accel=0)
+        assert (ho["prim"] >= 0).mean() > 0.5

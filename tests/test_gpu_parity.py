@@ -94,6 +94,17 @@ def test_adversarial_geometry_bit_exact(product_lib, offset):
         check_render(g, o, desc, subframes=2)
 
 
+def test_stacked_layers_queue_overflow_and_ties(product_lib):
+    """single-level kernel: dozens of coincident / near-coincident triangles pending per ray and round"""
+    import adversarial
+    desc = adversarial.make_stacked_scene()
+    with Context(0) as g:
+        o = build_pair(desc, g)
+        ho = check_trace(g, o, adversarial.make_stacked_rays(), accel=0)
+        assert (ho["prim"] >= 0).mean() > 0.5
+        check_render(g, o, desc, subframes=2)
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name", sorted(SMALL))
 def test_corrected_mode_matches_oracle(product_lib, name, mode):
