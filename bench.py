@@ -183,6 +183,25 @@ class _CudaArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
+def issue_evidence():
+    """Issue-slot utilisation of the extend launches from the newest committed full ncu capture of this command
+    (profiles/r*_ncu_bench_traverse_full.txt): static evidence, not measured in this run."""
+    import glob
+    import re
+    cand = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_bench_traverse_full.txt")))
+    if not cand:
+        return None
+    txt = open(cand[-1]).read()
+    blocks = [b for b in txt.split("=" * 100) if "k_traverse<0" in b]
+    vals = {}
+    for key in ("smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
+                "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"):
+        v = [float(m.group(1)) for b in blocks for m in [re.search(re.escape(key) + r"\s+([0-9.]+)", b)] if m]
+        if v:
+            vals[key] = round(sum(v) / len(v), 2)
+    return {"source": "profiles/" + os.path.basename(cand[-1]), "extend_launches_averaged": len(blocks), **vals}
+
+
 def run_rt3(args):
     import numpy as np
     import torch
@@ -337,7 +356,8 @@ def run_rt3(args):
                          "connect_kernel_Mrays_s": con_rays / (con_ms * 1e-3) / 1e6 if con_ms > 0 else None,
                          "whole_path_achieved_GBs": BYTES_PER_RAY_PATH * rays / (ms * 1e-3) / 1e9,
                          "note": "software BVH traversal is latency/issue bound, not HBM bound (SURVEY 8d): frac is expected to be small; "
-                                 "see profiles/ for issue-slot and L2 counters"},
+                                 "see profiles/ for issue-slot and L2 counters",
+                         "issue_bound_evidence": issue_evidence()},
             "stage_ms_last_step": stage,
         }
         if world == 1 and not args.no_cpu_baseline:
