@@ -36,10 +36,13 @@ enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2, PRIM_TRI_MOTION = 3 };  //
 #define RT3_QCAP 64       // capacity of that queue
 #endif
 #ifndef RT3_DEFER_ITEMS
-#define RT3_DEFER_ITEMS 20    // run the triangle pass once this many pairs are queued ...
+#define RT3_DEFER_ITEMS 32    // run the triangle pass once this many pairs are queued (a full-width pass) ...
 #endif
 #ifndef RT3_DEFER_BLOCKED
-#define RT3_DEFER_BLOCKED 2   // ... or more than this many lanes have nothing else left to do
+#define RT3_DEFER_BLOCKED 4   // ... or more than this many lanes have nothing else left to do
+#endif
+#ifndef RT3_DEFER_PARTIAL
+#define RT3_DEFER_PARTIAL 1   // 1: a pass takes 32 pairs at most and leaves the rest queued (no near-empty second pass: +3-5 %)
 #endif
 #ifndef RT3_COOP
 #define RT3_COOP 1        // 1: warp-cooperative triangle phase (step_warp), 0: per-lane loop (step)
@@ -794,8 +797,9 @@ struct Trav {
     // of 25 busy lanes, 10.7 in total, in 9 rounds out of 10 — so a triangle pass per round runs its ~300
     // instructions at a third of the lanes and costs as many issue slots as the wide-node step.  Here the
     // (owner lane, triangle) pairs stay in a per-warp shared-memory queue ACROSS rounds while their
-    // owners go on with node work, and one pass tests them when RT3_DEFER_ITEMS have gathered (or when
-    // more than RT3_DEFER_BLOCKED lanes have nothing else left, or a lane could not queue everything).
+    // owners go on with node work, and one full-width pass tests 32 of them when RT3_DEFER_ITEMS have gathered
+    // (or fewer when more than RT3_DEFER_BLOCKED lanes have nothing else left, or a lane could not queue
+    // everything); pairs beyond 32 stay queued, per-owner counts in shared memory tell when a lane is drained.
     // The fold is order-free: a candidate is valid under the owner's accept() rule, the owner's new hit
     // is the valid candidate with the smallest (t, primitive id) — which is what accept() yields for any
     // order of the same candidates — found with shared-memory atomicMin in two steps (t, then id among
@@ -821,6 +825,9 @@ struct Trav {
                 pend++;
             }
             tg.y = m;  // what did not fit waits in the lane (and forces the pass below)
+#if RT3_DEFER_PARTIAL
+            s_best[64u + lane] = pend;  // pairs of this lane in the queue (the pass counts them down)
+#endif
 #ifdef RT3_STATS
             if (m != 0u) atomicAdd(const_cast<uint32_t*>(sc.error_flags) + 12, 1u);  // queue-full events
 #endif
@@ -842,7 +849,12 @@ struct Trav {
 #endif
             __syncwarp();
             const uint32_t kpack = inv >> 8;
-            for (uint32_t base = 0; base < qn; base += 32u) {
+#if RT3_DEFER_PARTIAL
+            const uint32_t qpass = qn < 32u ? qn : 32u;  // ONE full-width pass; the rest stays queued
+#else
+            const uint32_t qpass = qn;
+#endif
+            for (uint32_t base = 0; base < qpass; base += 32u) {
                 s_best[lane] = 0xffffffffu;       // smallest ordered t per owner
                 s_best[32u + lane] = 0xffffffffu; // smallest primitive id among those
                 __syncwarp();
@@ -867,6 +879,9 @@ struct Trav {
                     const float4* pr = sc.root_prims + 3u * (item & 0x07ffffffu);
                     const float4 a = __ldg(pr), b = __ldg(pr + 1), c = __ldg(pr + 2);
                     id = __float_as_uint(a.w);
+#if RT3_DEFER_PARTIAL
+                    atomicSub(&s_best[64 + owner], 1u);
+#endif
                     // the owner's accept() rule
                     valid = test_triangle(v3(ox, oy, oz), s, v3(a), v3(b), v3(c), t, u, v) && t > otmin &&
                             (ohprim < 0 ? t < otbest : (t < otbest || (t == otbest && (int)id < ohprim)));
@@ -885,12 +900,25 @@ struct Trav {
                 if (s_best[lane] != 0xffffffffu) {
                     const float4 r = s_res[lane];
                     tbest = r.x; hu = r.y; hv = r.z; hprim = (int)__float_as_uint(r.w);
+#if RT3_DEFER_PARTIAL
+                    if (ANY_HIT) { tg.y = 0u; ng.y = 0u; sp = 0; }  // done; goes inactive below once none of its pairs is left in the queue
+#else
                     if (ANY_HIT) { active = false; tg.y = 0u; }
+#endif
                 }
                 __syncwarp();
             }
+#if RT3_DEFER_PARTIAL
+            const uint32_t rest = qn - qpass;  // <= 32: move it to the front
+            const uint32_t moved = lane < rest ? s_items[32u + lane] : 0u;
+            pend = s_best[64u + lane];
+            __syncwarp();
+            if (lane < rest) s_items[lane] = moved;
+            if (lane == 0) s_items[RT3_QCAP] = rest;
+#else
             if (lane == 0) s_items[RT3_QCAP] = 0u;
             pend = 0u;
+#endif
             __syncwarp();
         }
         if (active && pend == 0u && tg.y == 0u && !(ng.y & 0xff000000u) && sp == 0) active = false;  // nothing left anywhere

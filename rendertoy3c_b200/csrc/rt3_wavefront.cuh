@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(RT3_TRAV_THREADS, SINGLE ? RT3_TRAV_MIN_BLOCKS
     constexpr bool DEFER = SINGLE && RT3_DEFER;
     __shared__ uint32_t s_items[RT3_TRAV_THREADS / 32][DEFER ? RT3_QCAP + 1 : RT3_COOP_CAP];  // deferred queue: [RT3_QCAP] = its fill count
     __shared__ float4 s_res[RT3_TRAV_THREADS / 32][32];
-    __shared__ uint32_t s_best[DEFER ? RT3_TRAV_THREADS / 32 : 1][64];
+    __shared__ uint32_t s_best[DEFER ? RT3_TRAV_THREADS / 32 : 1][96];  // [0,32) t, [32,64) id, [64,96) queued pairs per owner
+    if (DEFER) s_best[DEFER ? threadIdx.x >> 5 : 0][64u + (threadIdx.x & 31u)] = 0u;
     if (DEFER && (threadIdx.x & 31u) == 0u) s_items[threadIdx.x >> 5][DEFER ? RT3_QCAP : 0] = 0u;
     __syncwarp();
 #endif
