@@ -438,6 +438,8 @@ inline void sort_pairs(uint64_t* keys, uint32_t* vals, uint32_t n, Stream st) {
 inline void build_bvh8(const float4* d_plo, const float4* d_phi, uint32_t n, Stream st, DevBuf<Node8>& out_nodes,
                        DevBuf<uint32_t>& out_order, Bvh8& out) {
     RT3_REQUIRE(n > 0, -1, "build_bvh8: no primitives");
+    // the traversal kernels tag queued triangles as (lane << 27 | index): 2^27 primitives per acceleration structure
+    RT3_REQUIRE(n < (1u << 27), -1, "build_bvh8: more than 134,217,727 primitives in one acceleration structure");
     const uint32_t nn = 2 * n;
     DevBuf<uint32_t> bounds(6), flags(n), counters(4);
     DevBuf<uint64_t> keys(n);

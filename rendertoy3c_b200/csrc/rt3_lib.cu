@@ -449,6 +449,15 @@ int rt3_accel_build(rt3_context_t c) {
         if (c->opt_merge && identity && c->geoms[in.blas]->type == PRIM_TRI) merged.push_back(i);
         else tl.push_back(i);
     }
+    {   // the merged BLAS is one acceleration structure: keep it below the 2^27-primitive limit of build_bvh8
+        uint64_t sum = 0;
+        for (uint32_t i : merged) sum += c->geoms[c->inst[i].blas]->nprims;
+        if (sum >= (1ull << 27)) {
+            merged.clear();
+            tl.clear();
+            for (uint32_t i = 0; i < ni; i++) tl.push_back(i);
+        }
+    }
     c->has_merged = !merged.empty();
     c->single_level = c->has_merged && tl.empty();
     for (uint32_t i : tl) ensure_blas(c, c->geoms[c->inst[i].blas].get());
