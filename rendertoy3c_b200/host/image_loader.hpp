@@ -1,0 +1,345 @@
+// image_loader.hpp — texture file ingest for the .obj/.mtl loader, written from scratch (the reference
+// calls stbi_load(..., STBI_rgb_alpha), src/mesh.cpp:137; stb_image is not used here).
+// Decodes to RGBA8, rows flipped so that v = 0 is the image bottom (mesh.cpp:151-159):
+//   * PNG  — 8/16-bit, grey / grey+alpha / RGB / RGBA / palette (+ tRNS), non-interlaced; own inflate
+//   * BMP  — uncompressed 24 / 32 bit, bottom-up or top-down
+//   * TGA  — true-colour 24 / 32 bit and 8-bit grey, raw or RLE, either origin
+//   * PPM / PGM — binary P6 / P5, maxval 255
+// JPEG and interlaced PNG are not supported (load_image returns false and says why).
+#pragma once
+#include <cctype>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "rt3_host.hpp"
+
+namespace rt3host {
+namespace detail {
+
+inline bool read_file(const std::string& path, std::vector<uint8_t>& out) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    f.seekg(0, std::ios::end);
+    const std::streamoff n = f.tellg();
+    if (n < 0) return false;
+    f.seekg(0);
+    out.resize((size_t)n);
+    f.read(reinterpret_cast<char*>(out.data()), n);
+    return (bool)f;
+}
+
+// rows top-down RGBA in `top`, stored bottom row first in the texture
+inline void store_flipped(const std::vector<uint8_t>& top, int w, int h, Texture& t) {
+    t.width = w; t.height = h;
+    t.pixel.resize((size_t)4 * w * h);
+    for (int y = 0; y < h; ++y) std::memcpy(&t.pixel[(size_t)4 * w * y], &top[(size_t)4 * w * (h - 1 - y)], (size_t)4 * w);
+}
+
+// ------------------------------------------------------------------------------------ inflate (RFC 1951)
+struct BitSrc {
+    const uint8_t* p; size_t n, pos = 0; uint32_t acc = 0; int cnt = 0; bool bad = false;
+    BitSrc(const uint8_t* d, size_t len) : p(d), n(len) {}
+    uint32_t bits(int k) {  // k <= 16, LSB first
+        while (cnt < k) {
+            if (pos >= n) { bad = true; return 0; }
+            acc |= (uint32_t)p[pos++] << cnt;
+            cnt += 8;
+        }
+        const uint32_t v = acc & ((1u << k) - 1u);
+        acc >>= k; cnt -= k;
+        return v;
+    }
+    void align() { acc = 0; cnt = 0; }
+};
+struct HuffTable {  // canonical code: symbols sorted by (length, value)
+    uint16_t count[16] = {0};
+    std::vector<uint16_t> sym;
+    void build(const uint8_t* len, int n) {
+        for (int i = 0; i < 16; ++i) count[i] = 0;
+        for (int i = 0; i < n; ++i) count[len[i]]++;
+        count[0] = 0;
+        uint16_t offs[16];
+        offs[1] = 0;
+        for (int i = 1; i < 15; ++i) offs[i + 1] = (uint16_t)(offs[i] + count[i]);
+        sym.assign((size_t)n, 0);
+        for (int i = 0; i < n; ++i) if (len[i]) sym[offs[len[i]]++] = (uint16_t)i;
+    }
+    int decode(BitSrc& b) const {
+        int code = 0, first = 0, index = 0;
+        for (int l = 1; l < 16; ++l) {
+            code |= (int)b.bits(1);
+            if (b.bad) return -1;
+            const int c = count[l];
+            if (code - c < first) return sym[(size_t)(index + (code - first))];
+            index += c; first += c; first <<= 1; code <<= 1;
+        }
+        return -1;
+    }
+};
+inline bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
+    static const uint16_t len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const uint8_t len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static const uint16_t dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const uint8_t dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    BitSrc b(src, n);
+    for (;;) {
+        const uint32_t final = b.bits(1), type = b.bits(2);
+        if (b.bad) return false;
+        if (type == 0) {
+            b.align();
+            if (b.pos + 4 > n) return false;
+            const uint32_t len = b.p[b.pos] | (b.p[b.pos + 1] << 8), nlen = b.p[b.pos + 2] | (b.p[b.pos + 3] << 8);
+            b.pos += 4;
+            if ((len ^ 0xffffu) != nlen || b.pos + len > n) return false;
+            out.insert(out.end(), b.p + b.pos, b.p + b.pos + len);
+            b.pos += len;
+        } else if (type == 1 || type == 2) {
+            HuffTable lit, dist;
+            uint8_t lens[320];
+            if (type == 1) {
+                for (int i = 0; i < 144; ++i) lens[i] = 8;
+                for (int i = 144; i < 256; ++i) lens[i] = 9;
+                for (int i = 256; i < 280; ++i) lens[i] = 7;
+                for (int i = 280; i < 288; ++i) lens[i] = 8;
+                lit.build(lens, 288);
+                for (int i = 0; i < 30; ++i) lens[i] = 5;
+                dist.build(lens, 30);
+            } else {
+                const int nlit = (int)b.bits(5) + 257, ndist = (int)b.bits(5) + 1, ncode = (int)b.bits(4) + 4;
+                if (b.bad || nlit > 286 || ndist > 30) return false;
+                uint8_t cl[19] = {0};
+                for (int i = 0; i < ncode; ++i) cl[order[i]] = (uint8_t)b.bits(3);
+                HuffTable clt;
+                clt.build(cl, 19);
+                int i = 0;
+                while (i < nlit + ndist) {
+                    const int s = clt.decode(b);
+                    if (s < 0) return false;
+                    if (s < 16) { lens[i++] = (uint8_t)s; continue; }
+                    int rep; uint8_t val = 0;
+                    if (s == 16) { if (i == 0) return false; val = lens[i - 1]; rep = 3 + (int)b.bits(2); }
+                    else if (s == 17) rep = 3 + (int)b.bits(3);
+                    else rep = 11 + (int)b.bits(7);
+                    if (b.bad || i + rep > nlit + ndist) return false;
+                    while (rep--) lens[i++] = val;
+                }
+                lit.build(lens, nlit);
+                dist.build(lens + nlit, ndist);
+            }
+            for (;;) {
+                const int s = lit.decode(b);
+                if (s < 0) return false;
+                if (s < 256) { out.push_back((uint8_t)s); continue; }
+                if (s == 256) break;
+                if (s > 285) return false;
+                const int len = len_base[s - 257] + (int)b.bits(len_extra[s - 257]);
+                const int ds = dist.decode(b);
+                if (ds < 0 || ds > 29) return false;
+                const size_t d = (size_t)dist_base[ds] + b.bits(dist_extra[ds]);
+                if (b.bad || d > out.size()) return false;
+                const size_t from = out.size() - d;
+                for (int k = 0; k < len; ++k) out.push_back(out[from + (size_t)k]);  // may overlap: byte by byte
+            }
+        } else {
+            return false;
+        }
+        if (final) return true;
+    }
+}
+
+// ------------------------------------------------------------------------------------ PNG
+inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+inline bool load_png(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (f.size() < 8 || std::memcmp(f.data(), sig, 8) != 0) return false;
+    uint32_t w = 0, h = 0;
+    int depth = 0, ctype = -1, interlace = 0;
+    std::vector<uint8_t> idat, plte, trns;
+    size_t pos = 8;
+    while (pos + 12 <= f.size()) {
+        const uint32_t len = be32(&f[pos]);
+        const uint8_t* type = &f[pos + 4];
+        const uint8_t* data = &f[pos + 8];
+        if (pos + 12 + (size_t)len > f.size()) { why = "truncated PNG chunk"; return false; }
+        if (!std::memcmp(type, "IHDR", 4) && len >= 13) { w = be32(data); h = be32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12]; }
+        else if (!std::memcmp(type, "PLTE", 4)) plte.assign(data, data + len);
+        else if (!std::memcmp(type, "tRNS", 4)) trns.assign(data, data + len);
+        else if (!std::memcmp(type, "IDAT", 4)) idat.insert(idat.end(), data, data + len);
+        else if (!std::memcmp(type, "IEND", 4)) break;
+        pos += 12 + (size_t)len;
+    }
+    if (w == 0 || h == 0 || w > 65535u || h > 65535u) { why = "bad PNG header"; return false; }
+    if (interlace) { why = "interlaced PNG is not supported"; return false; }
+    const int chan = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    if (!chan || !(depth == 8 || depth == 16 || (depth < 8 && (ctype == 0 || ctype == 3))) || (ctype == 3 && depth == 16)) { why = "unsupported PNG colour type / bit depth"; return false; }
+    if (idat.size() < 6) { why = "PNG without image data"; return false; }
+    std::vector<uint8_t> raw;
+    raw.reserve(((size_t)w * chan * depth / 8 + 2) * h);
+    if (!inflate_raw(idat.data() + 2, idat.size() - 2, raw)) { why = "corrupt PNG data stream"; return false; }  // 2-byte zlib header; Adler-32 not checked
+    const size_t stride = ((size_t)w * chan * depth + 7) / 8, bpp = (size_t)((chan * depth + 7) / 8);
+    if (raw.size() < (stride + 1) * h) { why = "short PNG data stream"; return false; }
+    std::vector<uint8_t> prev(stride, 0), top((size_t)4 * w * h);
+    for (uint32_t y = 0; y < h; ++y) {
+        uint8_t* row = &raw[(stride + 1) * y + 1];
+        const int ft = raw[(stride + 1) * y];
+        for (size_t i = 0; i < stride; ++i) {  // un-filter in place (PNG spec 9.2)
+            const int a = i >= bpp ? row[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+            int pred = 0;
+            if (ft == 1) pred = a;
+            else if (ft == 2) pred = b;
+            else if (ft == 3) pred = (a + b) >> 1;
+            else if (ft == 4) { const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+            else if (ft != 0) { why = "bad PNG filter type"; return false; }
+            row[i] = (uint8_t)(row[i] + pred);
+        }
+        std::memcpy(prev.data(), row, stride);
+        for (uint32_t x = 0; x < w; ++x) {
+            uint8_t* d = &top[4 * ((size_t)y * w + x)];
+            auto sample = [&](int c) -> int {  // channel c of pixel x as 8 bit (16 bit: high byte)
+                if (depth == 8) return row[(size_t)x * chan + c];
+                if (depth == 16) return row[((size_t)x * chan + c) * 2];
+                const int per = 8 / depth, v = (row[x / per] >> ((per - 1 - (int)(x % per)) * depth)) & ((1 << depth) - 1);
+                return ctype == 3 ? v : v * 255 / ((1 << depth) - 1);
+            };
+            if (ctype == 0) { const int g = sample(0); d[0] = d[1] = d[2] = (uint8_t)g; d[3] = 255; }
+            else if (ctype == 2) { d[0] = (uint8_t)sample(0); d[1] = (uint8_t)sample(1); d[2] = (uint8_t)sample(2); d[3] = 255; }
+            else if (ctype == 4) { const int g = sample(0); d[0] = d[1] = d[2] = (uint8_t)g; d[3] = (uint8_t)sample(1); }
+            else if (ctype == 6) { d[0] = (uint8_t)sample(0); d[1] = (uint8_t)sample(1); d[2] = (uint8_t)sample(2); d[3] = (uint8_t)sample(3); }
+            else {
+                const size_t k = (size_t)sample(0);
+                if (3 * k + 2 >= plte.size()) { why = "PNG palette index out of range"; return false; }
+                d[0] = plte[3 * k]; d[1] = plte[3 * k + 1]; d[2] = plte[3 * k + 2];
+                d[3] = k < trns.size() ? trns[k] : 255;
+            }
+        }
+    }
+    store_flipped(top, (int)w, (int)h, t);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------ BMP
+inline bool load_bmp(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
+    if (f.size() < 54 || f[0] != 'B' || f[1] != 'M') return false;
+    auto le32 = [&](size_t o) { return (uint32_t)f[o] | ((uint32_t)f[o + 1] << 8) | ((uint32_t)f[o + 2] << 16) | ((uint32_t)f[o + 3] << 24); };
+    const uint32_t off = le32(10), hdr = le32(14);
+    const int32_t w = (int32_t)le32(18), hs = (int32_t)le32(22);
+    const int bpp = f[28] | (f[29] << 8);
+    const uint32_t comp = le32(30);
+    if (hdr < 40 || w <= 0 || hs == 0 || (bpp != 24 && bpp != 32) || (comp != 0 && !(comp == 3 && bpp == 32))) { why = "unsupported BMP (need uncompressed 24 / 32 bit)"; return false; }
+    const int h = hs < 0 ? -hs : hs;
+    const size_t stride = (((size_t)w * bpp / 8) + 3) & ~(size_t)3;
+    if ((size_t)off + stride * h > f.size()) { why = "truncated BMP"; return false; }
+    std::vector<uint8_t> top((size_t)4 * w * h);
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* row = &f[off + stride * (size_t)(hs < 0 ? y : h - 1 - y)];
+        for (int x = 0; x < w; ++x) {
+            const uint8_t* s = row + (size_t)x * bpp / 8;
+            uint8_t* d = &top[4 * ((size_t)y * w + x)];
+            d[0] = s[2]; d[1] = s[1]; d[2] = s[0]; d[3] = bpp == 32 ? s[3] : 255;
+        }
+    }
+    store_flipped(top, w, h, t);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------ TGA
+inline bool load_tga(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
+    if (f.size() < 18) return false;
+    const int idlen = f[0], cmap = f[1], type = f[2], w = f[12] | (f[13] << 8), h = f[14] | (f[15] << 8), bpp = f[16], desc = f[17];
+    const bool rle = type == 10 || type == 11, grey = type == 3 || type == 11;
+    if (cmap != 0 || !(type == 2 || type == 3 || rle) || w <= 0 || h <= 0 || !((grey && bpp == 8) || (!grey && (bpp == 24 || bpp == 32)))) { why = "unsupported TGA (need true-colour 24 / 32 bit or 8-bit grey)"; return false; }
+    const size_t px = (size_t)bpp / 8;
+    std::vector<uint8_t> data((size_t)w * h * px);
+    size_t pos = 18 + (size_t)idlen, o = 0;
+    if (!rle) {
+        if (pos + data.size() > f.size()) { why = "truncated TGA"; return false; }
+        std::memcpy(data.data(), &f[pos], data.size());
+    } else {
+        while (o < data.size()) {
+            if (pos >= f.size()) { why = "truncated TGA"; return false; }
+            const int hd = f[pos++], cnt = (hd & 127) + 1;
+            if (hd & 128) {
+                if (pos + px > f.size()) { why = "truncated TGA"; return false; }
+                for (int k = 0; k < cnt && o < data.size(); ++k, o += px) std::memcpy(&data[o], &f[pos], px);
+                pos += px;
+            } else {
+                const size_t nb = (size_t)cnt * px;
+                if (pos + nb > f.size() || o + nb > data.size()) { why = "truncated TGA"; return false; }
+                std::memcpy(&data[o], &f[pos], nb);
+                pos += nb; o += nb;
+            }
+        }
+    }
+    const bool top_origin = (desc & 0x20) != 0, right_origin = (desc & 0x10) != 0;
+    std::vector<uint8_t> top((size_t)4 * w * h);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const uint8_t* s = &data[((size_t)(top_origin ? y : h - 1 - y) * w + (size_t)(right_origin ? w - 1 - x : x)) * px];
+            uint8_t* d = &top[4 * ((size_t)y * w + x)];
+            if (grey) { d[0] = d[1] = d[2] = s[0]; d[3] = 255; }
+            else { d[0] = s[2]; d[1] = s[1]; d[2] = s[0]; d[3] = bpp == 32 ? s[3] : 255; }
+        }
+    store_flipped(top, w, h, t);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------ PPM / PGM
+inline bool load_pnm(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
+    if (f.size() < 7 || f[0] != 'P' || (f[1] != '6' && f[1] != '5')) return false;
+    const int chan = f[1] == '6' ? 3 : 1;
+    size_t pos = 2;
+    auto next_int = [&]() {
+        for (;;) {
+            while (pos < f.size() && (f[pos] == ' ' || f[pos] == '\t' || f[pos] == '\r' || f[pos] == '\n')) ++pos;
+            if (pos < f.size() && f[pos] == '#') { while (pos < f.size() && f[pos] != '\n') ++pos; continue; }
+            break;
+        }
+        int v = -1;
+        while (pos < f.size() && f[pos] >= '0' && f[pos] <= '9') { v = (v < 0 ? 0 : v * 10) + (f[pos] - '0'); ++pos; }
+        return v;
+    };
+    const int w = next_int(), h = next_int(), maxv = next_int();
+    ++pos;  // the single whitespace byte after maxval
+    if (w <= 0 || h <= 0 || maxv != 255) { why = "unsupported PNM (need binary P5 / P6 with maxval 255)"; return false; }
+    if (pos + (size_t)w * h * chan > f.size()) { why = "truncated PNM"; return false; }
+    std::vector<uint8_t> top((size_t)4 * w * h);
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+        const uint8_t* s = &f[pos + i * chan];
+        uint8_t* d = &top[4 * i];
+        d[0] = s[0]; d[1] = s[chan == 3 ? 1 : 0]; d[2] = s[chan == 3 ? 2 : 0]; d[3] = 255;
+    }
+    store_flipped(top, w, h, t);
+    return true;
+}
+
+}  // namespace detail
+
+// Decodes an image file by content (PNG, BMP, PNM) or extension (TGA has no magic).  false + `why` if it cannot.
+inline bool load_image(const std::string& path, Texture& t, std::string* why_out = nullptr) {
+    std::vector<uint8_t> f;
+    std::string why;
+    bool ok = false;
+    if (!detail::read_file(path, f)) why = "cannot read file";
+    else if (f.size() >= 8 && f[0] == 0x89 && f[1] == 'P') ok = detail::load_png(f, t, why);
+    else if (f.size() >= 2 && f[0] == 'B' && f[1] == 'M') ok = detail::load_bmp(f, t, why);
+    else if (f.size() >= 2 && f[0] == 'P' && (f[1] == '5' || f[1] == '6')) ok = detail::load_pnm(f, t, why);
+    else if (f.size() >= 3 && f[0] == 0xff && f[1] == 0xd8) why = "JPEG is not supported (convert to PNG)";
+    else {
+        const size_t dot = path.rfind('.');
+        std::string ext = dot == std::string::npos ? "" : path.substr(dot + 1);
+        for (char& c : ext) c = (char)std::tolower((unsigned char)c);
+        if (ext == "tga") ok = detail::load_tga(f, t, why);
+        else why = "unknown image format";
+    }
+    if (!ok && why.empty()) why = "not a valid image of its kind";
+    if (why_out) *why_out = why;
+    return ok;
+}
+
+}  // namespace rt3host

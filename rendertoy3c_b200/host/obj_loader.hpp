@@ -5,8 +5,8 @@
 //   * faces in file order; vertices de-duplicated per mesh on the (v, vn, vt) triple, numbered by
 //     first use (mesh.cpp:78-110);
 //   * quads split along the shorter diagonal (tinyobj rule), larger polygons as a fan;
-//   * material fields Kd, Ke, map_Kd; textures: binary PPM (P6) only, RGBA8, rows flipped so that
-//     v = 0 is the image bottom (mesh.cpp:151-159), de-duplicated by file name;
+//   * material fields Kd, Ke, map_Kd; textures through image_loader.hpp (PNG, BMP, TGA, PPM/PGM -> RGBA8,
+//     rows flipped so that v = 0 is the image bottom, mesh.cpp:151-159), de-duplicated by file name;
 //   * normals and texcoords are required (the reference reads them unconditionally, Q11).
 #pragma once
 #include <cstdio>
@@ -16,6 +16,7 @@
 #include <sstream>
 #include <tuple>
 
+#include "image_loader.hpp"
 #include "rt3_host.hpp"
 
 namespace rt3host {
@@ -27,29 +28,6 @@ struct ObjMaterial { std::string name; float3_ Kd{0.8f, 0.8f, 0.8f}, Ke{0, 0, 0}
 
 inline int fix_index(int i, int n) { return i > 0 ? i - 1 : n + i; }
 
-inline bool load_ppm(const std::string& path, Texture& t) {
-    std::ifstream f(path, std::ios::binary);
-    if (!f) return false;
-    std::string magic;
-    f >> magic;
-    if (magic != "P6") return false;
-    auto next_int = [&]() { int v; while (f >> std::ws && f.peek() == '#') { std::string l; std::getline(f, l); } f >> v; return v; };
-    const int w = next_int(), h = next_int(), maxv = next_int();
-    f.get();
-    if (w <= 0 || h <= 0 || maxv != 255) return false;
-    std::vector<uint8_t> rgb((size_t)3 * w * h);
-    f.read(reinterpret_cast<char*>(rgb.data()), (std::streamsize)rgb.size());
-    if (!f) return false;
-    t.width = w; t.height = h;
-    t.pixel.resize((size_t)4 * w * h);
-    for (int y = 0; y < h; ++y)
-        for (int x = 0; x < w; ++x) {
-            const uint8_t* s = &rgb[3 * ((size_t)(h - 1 - y) * w + x)];  // vertical flip
-            uint8_t* d = &t.pixel[4 * ((size_t)y * w + x)];
-            d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = 255;
-        }
-    return true;
-}
 }  // namespace detail
 
 inline void loadOBJ(const std::string& path, std::vector<Mesh>& meshes, std::vector<Texture>& textures) {
@@ -143,8 +121,9 @@ inline void loadOBJ(const std::string& path, std::vector<Mesh>& meshes, std::vec
                     Texture t;
                     std::string fn = m.map_Kd;
                     for (char& ch : fn) if (ch == '\\') ch = '/';
-                    if (load_ppm(dir + fn, t)) { mesh.material.m_diffuseTextureID = (int)textures.size(); textures.push_back(std::move(t)); }
-                    else std::fprintf(stderr, "Error loading texture %s (only binary PPM is supported).\n", fn.c_str());
+                    std::string why;
+                    if (load_image(dir + fn, t, &why)) { mesh.material.m_diffuseTextureID = (int)textures.size(); textures.push_back(std::move(t)); }
+                    else std::fprintf(stderr, "Error loading texture %s (%s).\n", fn.c_str(), why.c_str());
                     known_tex[m.map_Kd] = mesh.material.m_diffuseTextureID;
                 }
             }

@@ -31,6 +31,18 @@ int main(int argc, char** argv) {
         else if (a == "--spl") spl = std::atoi(argv[++i]);
         else if (a == "--max-depth") max_depth = std::atoi(argv[++i]);
         else if (a == "--gpus") gpus = std::atoi(argv[++i]);
+        else if (a == "--decode-image" && i + 2 < argc) {  // utility: decode a texture file as loadOBJ would, dump w, h + RGBA8 (bottom row first)
+            Texture t;
+            std::string why;
+            if (!load_image(argv[i + 1], t, &why)) { std::fprintf(stderr, "%s: %s\n", argv[i + 1], why.c_str()); return 1; }
+            FILE* f = std::fopen(argv[i + 2], "wb");
+            if (!f) return 1;
+            const int32_t wh[2] = {t.width, t.height};
+            std::fwrite(wh, sizeof(wh), 1, f);
+            std::fwrite(t.pixel.data(), 1, t.pixel.size(), f);
+            std::fclose(f);
+            return 0;
+        }
         else if (a == "--mode") mode = std::atoi(argv[++i]);  // 0 reference-faithful, 1 corrected, 2 corrected + power light sampler
         else if (a == "--fovy") fovy = (float)std::atof(argv[++i]);
         else if (a == "--eye") f3(eye);

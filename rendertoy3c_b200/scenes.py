@@ -367,9 +367,24 @@ def by_name(name, **kw):
     return {"cornell": cornell, "terrain": terrain, "instanced": instanced, "motion": motion, "deforming": deforming}[name](**kw)
 
 
-def write_obj(desc, path):
-    """Export the mesh instances of a SceneDesc (identity transforms only) as .obj + .mtl (+ binary PPM
-    textures), one `o` shape and one material per instance, for the C++ host (host/wavefront.cpp) and the
+def _png_bytes(rgb_top_down):
+    """8-bit RGB PNG (sub filter, zlib) of an [h,w,3] array, standard library only"""
+    import struct
+    import zlib
+    a = np.ascontiguousarray(rgb_top_down, dtype=np.uint8)
+    h, w = a.shape[:2]
+    d = a.astype(np.int16)
+    d[:, 1:] -= a[:, :-1].astype(np.int16)                        # filter type 1 (sub)
+    raw = np.concatenate([np.ones((h, 1), np.uint8), (d & 255).astype(np.uint8).reshape(h, w * 3)], axis=1).tobytes()
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+    return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b"")
+
+
+def write_obj(desc, path, tex_format="ppm"):
+    """Export the mesh instances of a SceneDesc (identity transforms only) as .obj + .mtl (+ binary PPM or
+    PNG textures), one `o` shape and one material per instance, for the C++ host (host/wavefront.cpp) and the
     loader round-trip tests.  Rows of textures are written top-down (the loader flips them back)."""
     import os
     base = os.path.splitext(path)[0]
@@ -381,12 +396,15 @@ def write_obj(desc, path):
             assert g.kind == "mesh" and inst.keys is None and np.array_equal(inst.xform, IDENTITY)
             m.write("newmtl m%d\nKd %.9g %.9g %.9g\nKe %.9g %.9g %.9g\n" % ((i,) + tuple(np.float32(x) for x in inst.diffuse) + tuple(np.float32(x) for x in inst.emission)))
             if inst.tex >= 0:
-                tname = "%s_tex%d.ppm" % (os.path.basename(base), inst.tex)
+                tname = "%s_tex%d.%s" % (os.path.basename(base), inst.tex, tex_format)
                 m.write("map_Kd %s\n" % tname)
                 rgba = desc.textures[inst.tex].rgba
                 with open(os.path.join(os.path.dirname(path), tname), "wb") as t:
-                    t.write(b"P6\n%d %d\n255\n" % (rgba.shape[1], rgba.shape[0]))
-                    t.write(np.ascontiguousarray(rgba[::-1, :, :3]).tobytes())
+                    if tex_format == "png":
+                        t.write(_png_bytes(rgba[::-1, :, :3]))
+                    else:
+                        t.write(b"P6\n%d %d\n255\n" % (rgba.shape[1], rgba.shape[0]))
+                        t.write(np.ascontiguousarray(rgba[::-1, :, :3]).tobytes())
             f.write("o shape%d\nusemtl m%d\n" % (i, i))
             for v in g.verts:
                 f.write("v %.9g %.9g %.9g\n" % tuple(v))

@@ -28,9 +28,9 @@ def read_ppm(path):
         return np.frombuffer(f.read(), dtype=np.uint8).reshape(h, w, 3)
 
 
-def run_case(tmp_path, exe, lib_path, desc, spp=16):
+def run_case(tmp_path, exe, lib_path, desc, spp=16, tex_format="ppm"):
     obj = str(tmp_path / "scene.obj")
-    scenes.write_obj(desc, obj)
+    scenes.write_obj(desc, obj, tex_format=tex_format)
     out = str(tmp_path / "out.ppm")
     c = desc.camera
     cmd = [exe, "--scene", obj, "--width", str(desc.width), "--height", str(desc.height), "--spp", str(spp), "--max-depth", str(desc.max_depth),
@@ -51,6 +51,7 @@ def test_cpp_host_cornell_and_textured_terrain_simulator(tmp_path, emul_lib):
     exe = build_host(os.path.dirname(emul_lib), os.path.basename(emul_lib), str(tmp_path / "wavefront_emul"))
     run_case(tmp_path, exe, emul_lib, scenes.cornell(width=48, height=48))
     run_case(tmp_path, exe, emul_lib, scenes.terrain(n=12, width=48, height=32, tex_size=16))
+    run_case(tmp_path, exe, emul_lib, scenes.terrain(n=12, width=48, height=32, tex_size=32), tex_format="png")   # map_Kd .png through the own PNG decoder
 
 
 @pytest.mark.gpu
