@@ -4,7 +4,8 @@
 // displays through GL instead; saveImage in sutil/sutil.cpp:542-700 flips rows the same way).
 //
 //   wavefront --scene scene.obj [--width 768 --height 768 --spp 64 --spl 8 --max-depth 0]
-//             [--eye x y z --lookat x y z --up x y z --fovy 45] [--gpus N] [--out out.ppm]
+//             [--eye x y z --lookat x y z --up x y z --fovy 45] [--gpus N] [--mode 0|1|2]
+//             [--out out.ppm|.png|.exr] [--tonemap none|aces]
 // Multi-GPU: scene replicated, GPU g renders subframes g, g+N, ...; one NCCL sum of the float4
 // accumulation buffers (rt3_allreduce_accum).
 #include <chrono>
@@ -12,12 +13,13 @@
 #include <cstdlib>
 #include <memory>
 
+#include "image_writer.hpp"
 #include "obj_loader.hpp"
 
 using namespace rt3host;
 
 int main(int argc, char** argv) {
-    std::string scene, out = "out.ppm";
+    std::string scene, out = "out.ppm", tonemap = "none";
     int width = 768, height = 768, spp = 64, spl = 8, max_depth = 0, gpus = 1, mode = 0;  // reference defaults (wavefront.cpp:55,300)
     float eye[3] = {5, 5, 5}, lookat[3] = {0, 1, 0}, up[3] = {0, 1, 0}, fovy = 45.0f;  // initCameraState, wavefront.cpp:238-243
     for (int i = 1; i < argc; ++i) {
@@ -43,7 +45,8 @@ int main(int argc, char** argv) {
             std::fclose(f);
             return 0;
         }
-        else if (a == "--mode") mode = std::atoi(argv[++i]);  // 0 reference-faithful, 1 corrected, 2 corrected + power light sampler
+        else if (a == "--mode") mode = std::atoi(argv[++i]);
+        else if (a == "--tonemap") tonemap = argv[++i];  // none | aces (the reference viewer's display curve; 8-bit outputs only)  // 0 reference-faithful, 1 corrected, 2 corrected + power light sampler
         else if (a == "--fovy") fovy = (float)std::atof(argv[++i]);
         else if (a == "--eye") f3(eye);
         else if (a == "--lookat") f3(lookat);
@@ -84,12 +87,14 @@ int main(int argc, char** argv) {
         for (auto& c : ctx) { rt3_stats st; RT3HOST_CHECK(rt3_get_stats(c->ctx(), &st)); rays += st.rays_primary + st.rays_bounce + st.rays_shadow; samples += st.samples; }
         std::vector<uint8_t> frame((size_t)4 * width * height);
         RT3HOST_CHECK(rt3_download_frame(ctx[0]->ctx(), frame.data()));
-        FILE* f = std::fopen(out.c_str(), "wb");
-        if (!f) throw Exception("cannot write " + out);
-        std::fprintf(f, "P6\n%d %d\n255\n", width, height);
-        for (int y = height - 1; y >= 0; --y)  // row 0 is the image bottom (Q19)
-            for (int x = 0; x < width; ++x) std::fwrite(&frame[4 * ((size_t)y * width + x)], 1, 3, f);
-        std::fclose(f);
+        if (tonemap == "aces") tonemap_frame_aces(frame);
+        else if (tonemap != "none") throw Exception("unknown --tonemap " + tonemap);
+        std::vector<float> accum;
+        if (out.size() >= 4 && (out.substr(out.size() - 4) == ".exr" || out.substr(out.size() - 4) == ".EXR")) {
+            accum.resize((size_t)4 * width * height);
+            RT3HOST_CHECK(rt3_download_accum(ctx[0]->ctx(), accum.data()));
+        }
+        saveImage(out, width, height, frame.data(), accum.empty() ? nullptr : accum.data());  // .ppm / .png / .exr by extension
         std::printf("{\"meshes\": %zu, \"gpus\": %d, \"subframes\": %d, \"seconds\": %.4f, \"Mrays_s\": %.1f, \"Msamples_s\": %.1f, \"out\": \"%s\"}\n", meshes.size(), gpus,
                     subframes, secs, rays / secs / 1e6, samples / secs / 1e6, out.c_str());
     } catch (const std::exception& e) {

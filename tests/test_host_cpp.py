@@ -59,3 +59,86 @@ def test_cpp_host_on_gpu(tmp_path, product_lib):
     exe = build_host(os.path.dirname(product_lib), os.path.basename(product_lib), str(tmp_path / "wavefront"))
     run_case(tmp_path, exe, None, scenes.cornell(width=128, height=128))
     run_case(tmp_path, exe, None, scenes.terrain(n=32, width=128, height=72, tex_size=64))
+
+
+def _read_png_rgba(path):
+    import struct
+    import zlib
+    d = open(path, "rb").read()
+    assert d[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, w, h = 8, b"", 0, 0
+    while pos < len(d):
+        n, tag = struct.unpack(">I4s", d[pos:pos + 8])
+        body = d[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", d[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body) & 0xFFFFFFFF, "chunk CRC"
+        if tag == b"IHDR":
+            w, h, depth, ctype, _, _, il = struct.unpack(">IIBBBBB", body)
+            assert (depth, ctype, il) == (8, 6, 0)
+        elif tag == b"IDAT":
+            idat += body
+        pos += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 4 * w)   # zlib verifies the Adler-32
+    assert (raw[:, 0] == 0).all()
+    return raw[:, 1:].reshape(h, w, 4)
+
+
+def _read_exr_rgba(path):
+    import struct
+    d = open(path, "rb").read()
+    assert d[:8] == bytes([0x76, 0x2f, 0x31, 0x01, 2, 0, 0, 0])
+    pos, attrs = 8, {}
+    while d[pos] != 0:
+        e = d.index(b"\0", pos); name = d[pos:e].decode(); pos = e + 1
+        e = d.index(b"\0", pos); typ = d[pos:e].decode(); pos = e + 1
+        n = struct.unpack("<i", d[pos:pos + 4])[0]; pos += 4
+        attrs[name] = (typ, d[pos:pos + n]); pos += n
+    pos += 1
+    assert attrs["compression"][1] == b"\0" and attrs["lineOrder"][1] == b"\0"
+    x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"][1])
+    w, h = x1 - x0 + 1, y1 - y0 + 1
+    names = [c.split(b"\0")[0].decode() for c in [attrs["channels"][1][i * 18:(i + 1) * 18] for i in range(4)]]
+    assert names == ["A", "B", "G", "R"]
+    offs = struct.unpack("<%dQ" % h, d[pos:pos + 8 * h])
+    img = np.empty((h, w, 4), np.float32)
+    for y in range(h):
+        yy, nb = struct.unpack("<ii", d[offs[y]:offs[y] + 8])
+        assert yy == y and nb == 16 * w
+        line = np.frombuffer(d[offs[y] + 8:offs[y] + 8 + nb], dtype="<f4").reshape(4, w)
+        img[y] = line[[3, 2, 1, 0]].T
+    return img
+
+
+def test_cpp_host_output_formats(tmp_path, emul_lib):
+    """N3 (image output): .png and .exr written by host/image_writer.hpp parse with the standard library and hold the
+    frame / the float accumulation buffer exactly; --tonemap aces applies the reference viewer's display curve"""
+    exe = build_host(os.path.dirname(emul_lib), os.path.basename(emul_lib), str(tmp_path / "wavefront_emul"))
+    desc = scenes.cornell(width=40, height=28)
+    obj = str(tmp_path / "scene.obj")
+    scenes.write_obj(desc, obj)
+    c = desc.camera
+    base = [exe, "--scene", obj, "--width", str(desc.width), "--height", str(desc.height), "--spp", "16", "--max-depth", str(desc.max_depth),
+            "--fovy", repr(c.fovy), "--eye", *map(repr, c.eye), "--lookat", *map(repr, c.lookat), "--up", *map(repr, c.up)]
+    with Context(0, lib_path=emul_lib) as g:
+        scenes.replay(desc, g)
+        uvw = g.camera_uvw(c.eye, c.lookat, c.up, c.fovy, desc.width / desc.height)
+        for sf in range(2):
+            g.launch_subframe(make_settings(desc, uvw, sf))
+        frame, accum = g.download_frame()[::-1], g.download_accum()[::-1]
+    for ext in ("png", "exr", "ppm"):
+        out = str(tmp_path / ("o." + ext))
+        r = subprocess.run(base + ["--out", out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        if ext == "png":
+            assert np.array_equal(_read_png_rgba(out), frame)
+        elif ext == "exr":
+            assert np.array_equal(_read_exr_rgba(out).view(np.uint32), np.ascontiguousarray(accum).view(np.uint32))
+        else:
+            assert np.array_equal(read_ppm(out), frame[..., :3])
+    out = str(tmp_path / "aces.ppm")
+    r = subprocess.run(base + ["--out", out, "--tonemap", "aces"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    x = frame[..., :3].astype(np.float32) / np.float32(255)
+    want = np.clip((x * (2.51 * x + 0.03)) / (x * (2.43 * x + 0.59) + 0.14), 0, 1)
+    assert np.abs(read_ppm(out).astype(np.int32) - np.rint(want * 255).astype(np.int32)).max() <= 1
+    r = subprocess.run(base + ["--out", str(tmp_path / "o.gif")], capture_output=True, text=True)
+    assert r.returncode != 0 and "unsupported extension" in r.stderr
