@@ -30,12 +30,31 @@ inline int fix_index(int i, int n) { return i > 0 ? i - 1 : n + i; }
 
 }  // namespace detail
 
-inline void loadOBJ(const std::string& path, std::vector<Mesh>& meshes, std::vector<Texture>& textures) {
+// paths[0] is the scene; paths[1..] are key-frames of the SAME topology: only their v / vn / vt arrays are read and
+// indexed with the first file's faces (src/mesh.cpp:39-110) -> Mesh::num_keys = paths.size(), vertex-key motion blur
+inline void loadOBJ(const std::vector<std::string>& paths, std::vector<Mesh>& meshes, std::vector<Texture>& textures) {
     using namespace detail;
+    if (paths.empty()) throw Exception("loadOBJ: no file given");
+    const std::string& path = paths[0];
     std::ifstream in(path);
     if (!in) throw Exception("loadOBJ: cannot open " + path);
     const std::string dir = path.substr(0, path.rfind('/') + 1);
-    std::vector<float> V, VN, VT;
+    const size_t nkeys = paths.size();
+    std::vector<std::vector<float>> KV(nkeys), KVN(nkeys), KVT(nkeys);
+    for (size_t k = 1; k < nkeys; ++k) {
+        std::ifstream kf(paths[k]);
+        if (!kf) throw Exception("loadOBJ: cannot open " + paths[k]);
+        std::string l;
+        while (std::getline(kf, l)) {
+            std::istringstream ss(l);
+            std::string t;
+            ss >> t;
+            if (t == "v") { float x, y, z; ss >> x >> y >> z; KV[k].insert(KV[k].end(), {x, y, z}); }
+            else if (t == "vn") { float x, y, z; ss >> x >> y >> z; KVN[k].insert(KVN[k].end(), {x, y, z}); }
+            else if (t == "vt") { float x, y = 0; ss >> x >> y; KVT[k].insert(KVT[k].end(), {x, y}); }
+        }
+    }
+    std::vector<float>&V = KV[0], &VN = KVN[0], &VT = KVT[0];
     std::vector<ObjShape> shapes(1);
     std::vector<ObjMaterial> mats;
     std::map<std::string, int> mat_id;
@@ -91,7 +110,8 @@ inline void loadOBJ(const std::string& path, std::vector<Mesh>& meshes, std::vec
         for (int mid : ids) {
             if (mid < 0) throw Exception("loadOBJ: face without material (the reference dereferences materials[-1], Q11)");
             Mesh mesh;
-            mesh.vertices.resize(1); mesh.normals.resize(1); mesh.texcoords.resize(1);
+            mesh.num_keys = (unsigned)nkeys;
+            mesh.vertices.resize(nkeys); mesh.normals.resize(nkeys); mesh.texcoords.resize(nkeys);
             std::map<ObjIndex, int> known;
             for (size_t f = 0; f < sh.mat.size(); ++f) {
                 if (sh.mat[f] != mid) continue;
@@ -104,9 +124,13 @@ inline void loadOBJ(const std::string& path, std::vector<Mesh>& meshes, std::vec
                     else {
                         id = (int)mesh.vertices[0].size() / 3;
                         known[ix] = id;
-                        for (int q = 0; q < 3; ++q) mesh.vertices[0].push_back(V[3 * (size_t)ix.v + q]);
-                        for (int q = 0; q < 3; ++q) mesh.normals[0].push_back(VN[3 * (size_t)ix.vn + q]);
-                        for (int q = 0; q < 2; ++q) mesh.texcoords[0].push_back(VT[2 * (size_t)ix.vt + q]);
+                        for (size_t k = 0; k < nkeys; ++k) {
+                            if (3 * (size_t)ix.v + 2 >= KV[k].size() || 3 * (size_t)ix.vn + 2 >= KVN[k].size() || 2 * (size_t)ix.vt + 1 >= KVT[k].size())
+                                throw Exception("loadOBJ: key-frame " + paths[k] + " has fewer v / vn / vt entries than the faces of " + path + " use");
+                            for (int q = 0; q < 3; ++q) mesh.vertices[k].push_back(KV[k][3 * (size_t)ix.v + q]);
+                            for (int q = 0; q < 3; ++q) mesh.normals[k].push_back(KVN[k][3 * (size_t)ix.vn + q]);
+                            for (int q = 0; q < 2; ++q) mesh.texcoords[k].push_back(KVT[k][2 * (size_t)ix.vt + q]);
+                        }
                     }
                     mesh.indices.push_back(id);
                 }
@@ -130,6 +154,10 @@ inline void loadOBJ(const std::string& path, std::vector<Mesh>& meshes, std::vec
             if (!mesh.vertices[0].empty()) meshes.push_back(std::move(mesh));
         }
     }
+}
+
+inline void loadOBJ(const std::string& path, std::vector<Mesh>& meshes, std::vector<Texture>& textures) {
+    loadOBJ(std::vector<std::string>{path}, meshes, textures);
 }
 
 }  // namespace rt3host

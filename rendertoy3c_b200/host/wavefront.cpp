@@ -3,7 +3,7 @@
 // RenderSettings + camera -> render loop of launchSubframe -> image to disk (the reference
 // displays through GL instead; saveImage in sutil/sutil.cpp:542-700 flips rows the same way).
 //
-//   wavefront --scene scene.obj [--width 768 --height 768 --spp 64 --spl 8 --max-depth 0]
+//   wavefront --scene scene.obj [--key frame1.obj ...] [--width 768 --height 768 --spp 64 --spl 8 --max-depth 0]
 //             [--eye x y z --lookat x y z --up x y z --fovy 45] [--gpus N] [--mode 0|1|2]
 //             [--out out.ppm|.png|.exr] [--tonemap none|aces]
 // Multi-GPU: scene replicated, GPU g renders subframes g, g+N, ...; one NCCL sum of the float4
@@ -20,12 +20,14 @@ using namespace rt3host;
 
 int main(int argc, char** argv) {
     std::string scene, out = "out.ppm", tonemap = "none";
+    std::vector<std::string> key_files;  // further .obj files of the same topology = vertex key-frames (src/mesh.cpp:39)
     int width = 768, height = 768, spp = 64, spl = 8, max_depth = 0, gpus = 1, mode = 0;  // reference defaults (wavefront.cpp:55,300)
     float eye[3] = {5, 5, 5}, lookat[3] = {0, 1, 0}, up[3] = {0, 1, 0}, fovy = 45.0f;  // initCameraState, wavefront.cpp:238-243
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto f3 = [&](float* v) { for (int k = 0; k < 3; ++k) v[k] = (float)std::atof(argv[++i]); };
         if (a == "--scene") scene = argv[++i];
+        else if (a == "--key") key_files.push_back(argv[++i]);
         else if (a == "--out") out = argv[++i];
         else if (a == "--width") width = std::atoi(argv[++i]);
         else if (a == "--height") height = std::atoi(argv[++i]);
@@ -57,7 +59,9 @@ int main(int argc, char** argv) {
     try {
         std::vector<Mesh> meshes;
         std::vector<Texture> textures;
-        loadOBJ(scene, meshes, textures);
+        std::vector<std::string> paths = {scene};
+        paths.insert(paths.end(), key_files.begin(), key_files.end());
+        loadOBJ(paths, meshes, textures);
         std::vector<std::unique_ptr<Context>> ctx;
         std::vector<std::unique_ptr<CUDAScene>> scenes;
         for (int g = 0; g < gpus; ++g) {

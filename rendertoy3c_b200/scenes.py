@@ -382,7 +382,7 @@ def _png_bytes(rgb_top_down):
     return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b"")
 
 
-def write_obj(desc, path, tex_format="ppm"):
+def write_obj(desc, path, tex_format="ppm", key=0):
     """Export the mesh instances of a SceneDesc (identity transforms only) as .obj + .mtl (+ binary PPM or
     PNG textures), one `o` shape and one material per instance, for the C++ host (host/wavefront.cpp) and the
     loader round-trip tests.  Rows of textures are written top-down (the loader flips them back)."""
@@ -406,7 +406,7 @@ def write_obj(desc, path, tex_format="ppm"):
                         t.write(b"P6\n%d %d\n255\n" % (rgba.shape[1], rgba.shape[0]))
                         t.write(np.ascontiguousarray(rgba[::-1, :, :3]).tobytes())
             f.write("o shape%d\nusemtl m%d\n" % (i, i))
-            for v in g.verts:
+            for v in (g.verts if g.vert_keys is None else g.vert_keys[key]):  # key-frame files: same topology, other positions
                 f.write("v %.9g %.9g %.9g\n" % tuple(v))
             for n in g.normals:
                 f.write("vn %.9g %.9g %.9g\n" % tuple(n))

@@ -142,3 +142,51 @@ def test_cpp_host_output_formats(tmp_path, emul_lib):
     assert np.abs(read_ppm(out).astype(np.int32) - np.rint(want * 255).astype(np.int32)).max() <= 1
     r = subprocess.run(base + ["--out", str(tmp_path / "o.gif")], capture_output=True, text=True)
     assert r.returncode != 0 and "unsupported extension" in r.stderr
+
+
+def test_cpp_host_vertex_keyframes_from_obj_files(tmp_path, emul_lib):
+    """N1 + N2: several .obj files of one topology are key-frames (src/mesh.cpp:39-110): `--scene k0.obj --key k1.obj
+    --key k2.obj` renders the same frame as the Python host fed with the [keys, nv, 3] vertex arrays"""
+    from rendertoy3c_b200.scenes import Camera, Geometry, Instance, SceneDesc, _blob_pos, _quad_mesh, grid_mesh
+    exe = build_host(os.path.dirname(emul_lib), os.path.basename(emul_lib), str(tmp_path / "wavefront_emul"))
+    blob = grid_mesh(10, 10, _blob_pos)
+    nk = 3
+    vk = np.stack([blob.verts * np.float32(1.0 + 0.25 * k) + np.array([0.15 * k, 0.1 * k * k, 0.0], np.float32) for k in range(nk)]).astype(np.float32)
+    geoms = [Geometry("mesh", verts=np.ascontiguousarray(vk[0]), idx=blob.idx, normals=blob.normals, uvs=blob.uvs, vert_keys=vk)]
+    for quad in ([[-2, 2.5, -2], [2, 2.5, -2], [2, 2.5, 2], [-2, 2.5, 2]], [[-4, -0.8, -4], [-4, -0.8, 4], [4, -0.8, 4], [4, -0.8, -4]]):
+        q = _quad_mesh([quad])
+        q.vert_keys = np.stack([q.verts] * nk)                       # every mesh of a key-framed scene carries all keys, like the reference's
+        geoms.append(q)
+    inst = [Instance(0, diffuse=(0.8, 0.4, 0.3)), Instance(1, diffuse=(0.8, 0.8, 0.8), emission=(8.0, 8.0, 7.0)), Instance(2, diffuse=(0.6, 0.6, 0.6))]
+    desc = SceneDesc("keyframes", geoms, inst, [], Camera(eye=(0.7, 0.8, 3.6), lookat=(0.4, 0.1, 0.0), fovy=45.0), 48, 32, 16, 4)
+    files = []
+    for k in range(nk):
+        files.append(str(tmp_path / ("key%d.obj" % k)))
+        scenes.write_obj(desc, files[-1], key=k)
+    out = str(tmp_path / "out.ppm")
+    c = desc.camera
+    cmd = [exe, "--scene", files[0], "--key", files[1], "--key", files[2], "--width", str(desc.width), "--height", str(desc.height), "--spp", "16",
+           "--max-depth", str(desc.max_depth), "--fovy", repr(c.fovy), "--out", out, "--eye", *map(repr, c.eye), "--lookat", *map(repr, c.lookat), "--up", *map(repr, c.up)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    with Context(0, lib_path=emul_lib) as g:
+        scenes.replay(desc, g)
+        uvw = g.camera_uvw(c.eye, c.lookat, c.up, c.fovy, desc.width / desc.height)
+        for sf in range(2):
+            g.launch_subframe(make_settings(desc, uvw, sf))
+        ref = g.download_frame()[::-1, :, :3]
+        static = None
+    assert np.array_equal(read_ppm(out), ref), "key-framed C++ host frame differs from the Python host frame"
+    with Context(0, lib_path=emul_lib) as g:                         # and the motion is really there: key 0 alone renders something else
+        for gm in desc.geoms:
+            gm.vert_keys = None
+        scenes.replay(desc, g)
+        for sf in range(2):
+            g.launch_subframe(make_settings(desc, uvw, sf))
+        static = g.download_frame()[::-1, :, :3]
+    assert not np.array_equal(static, ref)
+    # a key-frame file of another topology is refused
+    bad = str(tmp_path / "bad.obj")
+    open(bad, "w").write("v 0 0 0\nvn 0 1 0\nvt 0 0\n")
+    r = subprocess.run([exe, "--scene", files[0], "--key", bad, "--out", out], capture_output=True, text=True)
+    assert r.returncode != 0 and "fewer v / vn / vt" in r.stderr
