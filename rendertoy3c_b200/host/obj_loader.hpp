@@ -5,7 +5,8 @@
 //   * faces in file order; vertices de-duplicated per mesh on the (v, vn, vt) triple, numbered by
 //     first use (mesh.cpp:78-110);
 //   * quads split along the shorter diagonal (tinyobj rule), larger polygons as a fan;
-//   * material fields Kd, Ke, map_Kd; textures through image_loader.hpp (PNG, BMP, TGA, PPM/PGM -> RGBA8,
+//   * material fields Kd, Ke, map_Kd (+ map_Ke, Pr, map_Pr, aniso, Ni, Tf, norm: carried, unused by shading, as in the
+//     reference); textures through image_loader.hpp (PNG, BMP, TGA, PPM/PGM -> RGBA8,
 //     rows flipped so that v = 0 is the image bottom, mesh.cpp:151-159), de-duplicated by file name;
 //   * normals and texcoords are required (the reference reads them unconditionally, Q11).
 #pragma once
@@ -24,7 +25,12 @@ namespace rt3host {
 namespace detail {
 struct ObjIndex { int v, vt, vn; bool operator<(const ObjIndex& o) const { return std::tie(v, vn, vt) < std::tie(o.v, o.vn, o.vt); } };
 struct ObjShape { std::vector<ObjIndex> idx; std::vector<int> mat; };  // 3 indices per triangle
-struct ObjMaterial { std::string name; float3_ Kd{0.8f, 0.8f, 0.8f}, Ke{0, 0, 0}; std::string map_Kd; };
+struct ObjMaterial {
+    std::string name;
+    float3_ Kd{0.8f, 0.8f, 0.8f}, Ke{0, 0, 0};
+    float Pr = 0.0f, aniso = 0.0f, Ni = 1.0f, Tf = 0.0f;  // PBR extension: roughness, anisotropy; ior; transmittance (first component)
+    std::string map_Kd, map_Ke, map_Pr, norm;
+};
 
 inline int fix_index(int i, int n) { return i > 0 ? i - 1 : n + i; }
 
@@ -72,6 +78,13 @@ inline void loadOBJ(const std::vector<std::string>& paths, std::vector<Mesh>& me
             else if (k == "Kd") ss >> mats.back().Kd.x >> mats.back().Kd.y >> mats.back().Kd.z;
             else if (k == "Ke") ss >> mats.back().Ke.x >> mats.back().Ke.y >> mats.back().Ke.z;
             else if (k == "map_Kd") ss >> mats.back().map_Kd;
+            else if (k == "map_Ke") ss >> mats.back().map_Ke;
+            else if (k == "Pr") ss >> mats.back().Pr;
+            else if (k == "map_Pr") ss >> mats.back().map_Pr;
+            else if (k == "aniso") ss >> mats.back().aniso;
+            else if (k == "Ni") ss >> mats.back().Ni;
+            else if (k == "Tf") ss >> mats.back().Tf;
+            else if (k == "norm") ss >> mats.back().norm;
         }
     };
     while (std::getline(in, line)) {
@@ -138,19 +151,28 @@ inline void loadOBJ(const std::vector<std::string>& paths, std::vector<Mesh>& me
             const ObjMaterial& m = mats[(size_t)mid];
             mesh.material.m_diffuse = m.Kd;
             mesh.material.m_emissive = m.Ke;
-            if (!m.map_Kd.empty()) {
-                auto it = known_tex.find(m.map_Kd);
-                if (it != known_tex.end()) mesh.material.m_diffuseTextureID = it->second;
-                else {
-                    Texture t;
-                    std::string fn = m.map_Kd;
-                    for (char& ch : fn) if (ch == '\\') ch = '/';
-                    std::string why;
-                    if (load_image(dir + fn, t, &why)) { mesh.material.m_diffuseTextureID = (int)textures.size(); textures.push_back(std::move(t)); }
-                    else std::fprintf(stderr, "Error loading texture %s (%s).\n", fn.c_str(), why.c_str());
-                    known_tex[m.map_Kd] = mesh.material.m_diffuseTextureID;
-                }
-            }
+            auto texture_id = [&](const std::string& name) -> int {  // addTextureAndGetTextureId, mesh.cpp:112-168
+                if (name.empty()) return -1;
+                auto it = known_tex.find(name);
+                if (it != known_tex.end()) return it->second;
+                int id = -1;
+                Texture t;
+                std::string fn = name;
+                for (char& ch : fn) if (ch == '\\') ch = '/';
+                std::string why;
+                if (load_image(dir + fn, t, &why)) { id = (int)textures.size(); textures.push_back(std::move(t)); }
+                else std::fprintf(stderr, "Error loading texture %s (%s).\n", fn.c_str(), why.c_str());
+                known_tex[name] = id;
+                return id;
+            };
+            mesh.material.m_diffuseTextureID = texture_id(m.map_Kd);    // same order as the reference: diffuse, emissive, roughness, normal
+            mesh.material.m_emissiveTextureID = texture_id(m.map_Ke);
+            mesh.material.m_roughness = m.Pr;
+            mesh.material.m_roughnessTextureID = texture_id(m.map_Pr);
+            mesh.material.m_anisotropy = m.aniso;
+            mesh.material.m_ior = m.Ni;
+            mesh.material.m_transmittance = m.Tf;
+            mesh.material.m_normalTextureID = texture_id(m.norm);
             if (!mesh.vertices[0].empty()) meshes.push_back(std::move(mesh));
         }
     }

@@ -38,6 +38,14 @@ struct Material {
     float3_ m_diffuse{0.8f, 0.8f, 0.8f};
     float3_ m_emissive{0, 0, 0};
     int m_diffuseTextureID = -1;
+    // carried like the reference does (src/mesh.cpp:186-197) and, like there, not read by any closure (src/material.h:33-36)
+    int m_emissiveTextureID = -1;
+    float m_roughness = 0.0f;
+    int m_roughnessTextureID = -1;
+    float m_anisotropy = 0.0f;
+    float m_ior = 1.0f;
+    float m_transmittance = 0.0f;
+    int m_normalTextureID = -1;
 };
 struct Mesh {
     unsigned int num_keys = 1;
