@@ -5,9 +5,11 @@
 //   * BMP  — uncompressed 24 / 32 bit, bottom-up or top-down
 //   * TGA  — true-colour 24 / 32 bit and 8-bit grey, raw or RLE, either origin
 //   * PPM / PGM — binary P6 / P5, maxval 255
-// JPEG and interlaced PNG are not supported (load_image returns false and says why).
+//   * JPEG — baseline sequential (Huffman, 8 bit), grey or YCbCr with any sampling factors, restart intervals
+// Progressive / arithmetic / CMYK JPEG and interlaced PNG are not supported (load_image returns false and says why).
 #pragma once
 #include <cctype>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -318,6 +320,203 @@ inline bool load_pnm(const std::vector<uint8_t>& f, Texture& t, std::string& why
     return true;
 }
 
+// ------------------------------------------------------------------------------------ JPEG (baseline sequential, ITU T.81)
+// 8-bit, Huffman, one interleaved scan, 1 or 3 components (grey / YCbCr, any sampling factors up to 4, chroma
+// replicated on upsampling), restart intervals.  Progressive, arithmetic-coded and 4-component files are refused.
+struct JpegHuff {
+    uint8_t vals[256];
+    int mincode[17], maxcode[17], valptr[17];  // per code length 1..16 (T.81 F.2.2.3); maxcode = -1: no code of that length
+    bool set = false;
+    void build(const uint8_t counts[16], const uint8_t* v, int nv) {
+        std::memcpy(vals, v, (size_t)nv);
+        int code = 0, k = 0;
+        for (int l = 1; l <= 16; ++l) {
+            valptr[l] = k;
+            mincode[l] = code;
+            code += counts[l - 1];
+            k += counts[l - 1];
+            maxcode[l] = counts[l - 1] ? code - 1 : -1;
+            code <<= 1;
+        }
+        set = true;
+    }
+};
+struct JpegBits {
+    const uint8_t* p; size_t n, pos; uint32_t acc = 0; int cnt = 0; bool bad = false;
+    JpegBits(const uint8_t* d, size_t len, size_t at) : p(d), n(len), pos(at) {}
+    int bit() {
+        if (cnt == 0) {
+            if (pos >= n) { bad = true; return 0; }
+            uint8_t b = p[pos++];
+            if (b == 0xff) {
+                if (pos < n && p[pos] == 0x00) ++pos;  // stuffed zero
+                else { bad = true; --pos; return 0; }  // a marker inside the data: the scan ended early
+            }
+            acc = b; cnt = 8;
+        }
+        --cnt;
+        return (int)((acc >> cnt) & 1u);
+    }
+    int receive(int k) { int v = 0; while (k--) v = (v << 1) | bit(); return v; }
+    int decode(const JpegHuff& h) {
+        int code = 0;
+        for (int l = 1; l <= 16; ++l) {
+            code = (code << 1) | bit();
+            if (bad) return -1;
+            if (h.maxcode[l] >= 0 && code <= h.maxcode[l] && code >= h.mincode[l]) return h.vals[h.valptr[l] + code - h.mincode[l]];
+        }
+        bad = true;
+        return -1;
+    }
+    bool restart(int expect) {  // byte-align, then RSTn
+        cnt = 0;
+        if (pos + 2 > n || p[pos] != 0xff || p[pos + 1] != (uint8_t)(0xd0 + (expect & 7))) return false;
+        pos += 2;
+        return true;
+    }
+};
+
+inline bool load_jpeg(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
+    static const uint8_t zz[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                                   35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    if (f.size() < 4 || f[0] != 0xff || f[1] != 0xd8) return false;
+    struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0, pw = 0, ph = 0; std::vector<uint8_t> plane; };
+    uint16_t quant[4][64] = {};
+    JpegHuff dc[4], ac[4];
+    std::vector<Comp> comps;
+    int W = 0, H = 0, ri = 0;
+    size_t pos = 2;
+    auto be16 = [&](size_t o) { return (int)((f[o] << 8) | f[o + 1]); };
+    for (;;) {
+        while (pos < f.size() && f[pos] != 0xff) ++pos;
+        while (pos < f.size() && f[pos] == 0xff) ++pos;
+        if (pos >= f.size()) { why = "JPEG without image data"; return false; }
+        const int m = f[pos++];
+        if (m == 0xd9) { why = "JPEG without image data"; return false; }
+        if (m == 0x01 || (m >= 0xd0 && m <= 0xd7)) continue;
+        if (pos + 2 > f.size()) { why = "truncated JPEG"; return false; }
+        const int len = be16(pos);
+        if (len < 2 || pos + (size_t)len > f.size()) { why = "truncated JPEG"; return false; }
+        const size_t seg = pos + 2, end = pos + (size_t)len;
+        if (m == 0xc2 || m == 0xc6 || m == 0xca || m == 0xce) { why = "progressive JPEG is not supported (save it as baseline, or as PNG)"; return false; }
+        if (m == 0xc3 || m == 0xc5 || m == 0xc7 || (m >= 0xc9 && m <= 0xcf && m != 0xcc)) { why = "lossless / arithmetic-coded JPEG is not supported"; return false; }
+        if (m == 0xc0 || m == 0xc1) {
+            if (len < 8 || f[seg] != 8) { why = "JPEG sample precision other than 8 bit"; return false; }
+            H = be16(seg + 1); W = be16(seg + 3);
+            const int nf = f[seg + 5];
+            if (W <= 0 || H <= 0 || !(nf == 1 || nf == 3) || len < 8 + 3 * nf) { why = nf == 4 ? "4-component (CMYK) JPEG is not supported" : "bad JPEG frame header"; return false; }
+            comps.assign((size_t)nf, Comp());
+            for (int i = 0; i < nf; ++i) {
+                Comp& c = comps[(size_t)i];
+                c.id = f[seg + 6 + 3 * (size_t)i]; c.h = f[seg + 7 + 3 * (size_t)i] >> 4; c.v = f[seg + 7 + 3 * (size_t)i] & 15; c.tq = f[seg + 8 + 3 * (size_t)i] & 3;
+                if (c.h < 1 || c.h > 4 || c.v < 1 || c.v > 4) { why = "bad JPEG sampling factors"; return false; }
+            }
+        } else if (m == 0xdb) {
+            size_t q = seg;
+            while (q < end) {
+                const int pq = f[q] >> 4, tq = f[q] & 15;
+                ++q;
+                if (tq > 3 || q + (size_t)(pq ? 128 : 64) > end) { why = "bad JPEG quantisation table"; return false; }
+                for (int i = 0; i < 64; ++i) { quant[tq][zz[i]] = (uint16_t)(pq ? be16(q + 2 * (size_t)i) : f[q + (size_t)i]); }
+                q += pq ? 128 : 64;
+            }
+        } else if (m == 0xc4) {
+            size_t q = seg;
+            while (q < end) {
+                const int tc = f[q] >> 4, th = f[q] & 15;
+                if (tc > 1 || th > 3 || q + 17 > end) { why = "bad JPEG Huffman table"; return false; }
+                int nv = 0;
+                for (int i = 0; i < 16; ++i) nv += f[q + 1 + (size_t)i];
+                if (nv > 256 || q + 17 + (size_t)nv > end) { why = "bad JPEG Huffman table"; return false; }
+                (tc ? ac[th] : dc[th]).build(&f[q + 1], &f[q + 17], nv);
+                q += 17 + (size_t)nv;
+            }
+        } else if (m == 0xdd) {
+            ri = be16(seg);
+        } else if (m == 0xda) {
+            const int ns = f[seg];
+            if (comps.empty() || ns != (int)comps.size() || len < 6 + 2 * ns) { why = "JPEG with several scans is not supported"; return false; }
+            for (int i = 0; i < ns; ++i) {
+                const int cs = f[seg + 1 + 2 * (size_t)i], tdta = f[seg + 2 + 2 * (size_t)i];
+                bool found = false;
+                for (Comp& c : comps) if (c.id == cs) { c.td = tdta >> 4; c.ta = tdta & 15; found = true; }
+                if (!found || (tdta >> 4) > 3 || (tdta & 15) > 3) { why = "bad JPEG scan header"; return false; }
+            }
+            pos = end;
+            break;
+        }
+        pos = end;
+    }
+    int hmax = 1, vmax = 1;
+    for (const Comp& c : comps) { hmax = c.h > hmax ? c.h : hmax; vmax = c.v > vmax ? c.v : vmax; if (!dc[c.td].set || !ac[c.ta].set) { why = "JPEG scan refers to a missing Huffman table"; return false; } }
+    const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+    for (Comp& c : comps) { c.pw = mcux * c.h * 8; c.ph = mcuy * c.v * 8; c.plane.assign((size_t)c.pw * c.ph, 0); }
+    float cosm[8][8];
+    for (int x = 0; x < 8; ++x)
+        for (int u = 0; u < 8; ++u) cosm[x][u] = (u == 0 ? 0.70710678118654752f : 1.0f) * std::cos((float)((2 * x + 1) * u) * 3.14159265358979323846f / 16.0f);
+    JpegBits b(f.data(), f.size(), pos);
+    int until_restart = ri, next_rst = 0;
+    for (int my = 0; my < mcuy; ++my)
+        for (int mx = 0; mx < mcux; ++mx) {
+            if (ri && until_restart == 0) {
+                if (!b.restart(next_rst)) { why = "JPEG restart marker missing"; return false; }
+                next_rst = (next_rst + 1) & 7; until_restart = ri;
+                for (Comp& c : comps) c.pred = 0;
+            }
+            for (Comp& c : comps)
+                for (int by = 0; by < c.v; ++by)
+                    for (int bx = 0; bx < c.h; ++bx) {
+                        float co[64] = {0};
+                        const int s = b.decode(dc[c.td]);
+                        if (s < 0 || s > 11) { why = "corrupt JPEG data"; return false; }
+                        int diff = s ? b.receive(s) : 0;
+                        if (s && diff < (1 << (s - 1))) diff -= (1 << s) - 1;  // EXTEND
+                        c.pred += diff;
+                        co[0] = (float)(c.pred * (int)quant[c.tq][0]);
+                        for (int k = 1; k < 64;) {
+                            const int rs = b.decode(ac[c.ta]);
+                            if (rs < 0) { why = "corrupt JPEG data"; return false; }
+                            const int r = rs >> 4, sz = rs & 15;
+                            if (sz == 0) { if (r == 15) { k += 16; continue; } break; }  // ZRL / EOB
+                            k += r;
+                            if (k > 63) { why = "corrupt JPEG data"; return false; }
+                            int v = b.receive(sz);
+                            if (v < (1 << (sz - 1))) v -= (1 << sz) - 1;
+                            co[zz[k]] = (float)(v * (int)quant[c.tq][zz[k]]);
+                            ++k;
+                        }
+                        if (b.bad) { why = "truncated JPEG data"; return false; }
+                        float tmp[64];
+                        for (int y = 0; y < 8; ++y)       // rows: tmp[y][x] = sum_u cos[x][u] co[y][u]
+                            for (int x = 0; x < 8; ++x) { float a = 0; for (int u = 0; u < 8; ++u) a += cosm[x][u] * co[8 * y + u]; tmp[8 * y + x] = a; }
+                        const int ox = (mx * c.h + bx) * 8, oy = (my * c.v + by) * 8;
+                        for (int x = 0; x < 8; ++x)       // columns
+                            for (int y = 0; y < 8; ++y) {
+                                float a = 0;
+                                for (int v = 0; v < 8; ++v) a += cosm[y][v] * tmp[8 * v + x];
+                                const long q = std::lround(a * 0.25f + 128.0f);
+                                c.plane[(size_t)(oy + y) * c.pw + (size_t)(ox + x)] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+                            }
+                    }
+            if (ri) --until_restart;
+        }
+    std::vector<uint8_t> top((size_t)4 * W * H);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            uint8_t* d = &top[4 * ((size_t)y * W + x)];
+            auto at = [&](const Comp& c) { return (float)c.plane[(size_t)(y * c.v / vmax) * c.pw + (size_t)(x * c.h / hmax)]; };
+            if (comps.size() == 1) { d[0] = d[1] = d[2] = (uint8_t)at(comps[0]); }
+            else {
+                const float Y = at(comps[0]), cb = at(comps[1]) - 128.0f, cr = at(comps[2]) - 128.0f;
+                const float rgb[3] = {Y + 1.402f * cr, Y - 0.344136f * cb - 0.714136f * cr, Y + 1.772f * cb};
+                for (int k = 0; k < 3; ++k) { const long q = std::lround(rgb[k]); d[k] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q)); }
+            }
+            d[3] = 255;
+        }
+    store_flipped(top, W, H, t);
+    return true;
+}
+
 }  // namespace detail
 
 // Decodes an image file by content (PNG, BMP, PNM) or extension (TGA has no magic).  false + `why` if it cannot.
@@ -329,7 +528,7 @@ inline bool load_image(const std::string& path, Texture& t, std::string* why_out
     else if (f.size() >= 8 && f[0] == 0x89 && f[1] == 'P') ok = detail::load_png(f, t, why);
     else if (f.size() >= 2 && f[0] == 'B' && f[1] == 'M') ok = detail::load_bmp(f, t, why);
     else if (f.size() >= 2 && f[0] == 'P' && (f[1] == '5' || f[1] == '6')) ok = detail::load_pnm(f, t, why);
-    else if (f.size() >= 3 && f[0] == 0xff && f[1] == 0xd8) why = "JPEG is not supported (convert to PNG)";
+    else if (f.size() >= 3 && f[0] == 0xff && f[1] == 0xd8) ok = detail::load_jpeg(f, t, why);
     else {
         const size_t dot = path.rfind('.');
         std::string ext = dot == std::string::npos ? "" : path.substr(dot + 1);

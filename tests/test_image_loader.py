@@ -198,10 +198,186 @@ def test_bmp_tga_pnm(exe, tmp_path):
     assert np.array_equal(got[..., :3], img[..., :3])
 
 
+ZIGZAG = [0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+          35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63]
+
+
+def _dct_matrix():
+    m = np.zeros((8, 8))
+    for u in range(8):
+        for x in range(8):
+            m[u, x] = (np.sqrt(0.5) if u == 0 else 1.0) * np.cos((2 * x + 1) * u * np.pi / 16) / 2
+    return m
+
+
+def write_baseline_jpeg(path, rgb, sampling=(1, 1), restart=0, grey=False, q=3, optimal=True):
+    """A small baseline JPEG encoder for the tests (Huffman tables built from the symbols that occur: optimal lengths
+    with the reserved all-ones code, or equal-length codes).  Returns the image a straightforward decoder must produce (float IDCT, replicated chroma, JFIF colour)."""
+    h, w = rgb.shape[:2]
+    f = rgb.astype(np.float64)
+    if grey:
+        planes, samp = [np.rint(0.299 * f[..., 0] + 0.587 * f[..., 1] + 0.114 * f[..., 2])], [(1, 1)]
+    else:
+        y = 0.299 * f[..., 0] + 0.587 * f[..., 1] + 0.114 * f[..., 2]
+        cb = 128 - 0.168736 * f[..., 0] - 0.331264 * f[..., 1] + 0.5 * f[..., 2]
+        cr = 128 + 0.5 * f[..., 0] - 0.418688 * f[..., 1] - 0.081312 * f[..., 2]
+        planes, samp = [np.rint(y), np.rint(cb), np.rint(cr)], [sampling, (1, 1), (1, 1)]
+    hmax, vmax = max(s[0] for s in samp), max(s[1] for s in samp)
+    mcux, mcuy = -(-w // (8 * hmax)), -(-h // (8 * vmax))
+    qt = [np.clip(np.add.outer(np.arange(8), np.arange(8)) * q + 2, 1, 255).astype(np.int64), np.full((8, 8), 4 * q + 3, np.int64)]
+    D = _dct_matrix()
+    coefs, recon = [], []
+    for ci, (pl, (sh, sv)) in enumerate(zip(planes, samp)):
+        fx, fy = hmax // sh, vmax // sv
+        ph, pw = mcuy * sv * 8, mcux * sh * 8
+        full = np.pad(pl, ((0, mcuy * vmax * 8 - h), (0, mcux * hmax * 8 - w)), mode="edge")
+        sub = full.reshape(ph, fy, pw, fx).mean(axis=(1, 3))        # box-filtered chroma
+        qq = qt[0 if ci == 0 else 1]
+        blocks = sub.reshape(ph // 8, 8, pw // 8, 8).transpose(0, 2, 1, 3) - 128.0
+        co = np.rint(np.einsum("ux,abxy,vy->abuv", D, blocks, D) / qq).astype(np.int64)   # co[by, bx, v(row freq), u]
+        coefs.append(co)
+        rec = np.einsum("ux,abuv,vy->abxy", D, (co * qq).astype(np.float64), D) + 128.0
+        recon.append(np.clip(np.rint(rec), 0, 255).transpose(0, 2, 1, 3).reshape(ph, pw))
+    # symbol stream
+    def cat(v):
+        return 0 if v == 0 else int(abs(int(v))).bit_length()
+
+    def bits_of(v, s):
+        return (v if v >= 0 else v + (1 << s) - 1, s)
+    stream = []                                                     # items: ("dc"|"ac", table, symbol) or ("raw", value, nbits) or ("rst", n)
+    pred = [0] * len(planes)
+    n_mcu, rst = 0, 0
+    for my in range(mcuy):
+        for mx in range(mcux):
+            if restart and n_mcu and n_mcu % restart == 0:
+                stream.append(("rst", rst)); rst = (rst + 1) & 7; pred = [0] * len(planes)
+            for ci, (sh, sv) in enumerate(samp):
+                tb = 0 if ci == 0 else 1
+                for by in range(sv):
+                    for bx in range(sh):
+                        zzv = coefs[ci][my * sv + by, mx * sh + bx].reshape(64)[ZIGZAG]
+                        d = int(zzv[0]) - pred[ci]; pred[ci] = int(zzv[0])
+                        s = cat(d)
+                        stream.append(("dc", tb, s))
+                        if s:
+                            stream.append(("raw",) + bits_of(d, s))
+                        run = 0
+                        last = max([k for k in range(1, 64) if zzv[k] != 0], default=0)
+                        for k in range(1, last + 1):
+                            v = int(zzv[k])
+                            if v == 0:
+                                run += 1
+                                continue
+                            while run > 15:
+                                stream.append(("ac", tb, 0xF0)); run -= 16
+                            s = cat(v)
+                            stream.append(("ac", tb, (run << 4) | s))
+                            stream.append(("raw",) + bits_of(v, s))
+                            run = 0
+                        if last < 63:
+                            stream.append(("ac", tb, 0x00))
+            n_mcu += 1
+    tables = {}
+    for kind in ("dc", "ac"):
+        for tb in range(2 if not grey else 1):
+            occ = [it[2] for it in stream if it[0] == kind and it[1] == tb] or [0]
+            syms = sorted(set(occ))
+            if not optimal:
+                L = max(1, int(len(syms)).bit_length())             # 2**L > len(syms): the all-ones code stays unused
+                tables[(kind, tb)] = ({sy: (i, L) for i, sy in enumerate(syms)}, [0] * (L - 1) + [len(syms)] + [0] * (16 - L), syms)
+                continue
+            # Huffman code lengths with a reserved (never used) symbol that takes the all-ones code, T.81 K.2
+            import heapq
+            heap = [(occ.count(sy), i, [sy]) for i, sy in enumerate(syms)] + [(0.5, len(syms), [None])]
+            length = {sy: 0 for sy in syms}; length[None] = 0
+            heapq.heapify(heap)
+            tick = len(heap)
+            while len(heap) > 1:
+                a, b = heapq.heappop(heap), heapq.heappop(heap)
+                for sy in a[2] + b[2]:
+                    length[sy] += 1
+                heapq.heappush(heap, (a[0] + b[0], tick, a[2] + b[2])); tick += 1
+            assert max(length.values()) <= 16
+            order = sorted(syms, key=lambda sy: (length[sy], sy)) + [None]   # the reserved symbol last among the longest
+            assert length[None] == max(length.values())
+            codes, code, prev = {}, 0, 0
+            for sy in order:
+                code <<= length[sy] - prev; prev = length[sy]
+                codes[sy] = (code, length[sy]); code += 1
+            assert codes[None][0] == (1 << length[None]) - 1
+            counts = [sum(1 for sy in syms if length[sy] == l) for l in range(1, 17)]
+            tables[(kind, tb)] = ({sy: codes[sy] for sy in syms}, counts, order[:-1])
+    out, acc, nacc = bytearray(), 0, 0
+
+    def put(v, n):
+        nonlocal acc, nacc
+        acc = (acc << n) | v; nacc += n
+        while nacc >= 8:
+            b = (acc >> (nacc - 8)) & 255
+            out.append(b)
+            if b == 0xFF:
+                out.append(0)
+            nacc -= 8
+        acc &= (1 << nacc) - 1
+    for it in stream:
+        if it[0] == "raw":
+            put(it[1], it[2])
+        elif it[0] == "rst":
+            if nacc:
+                put((1 << (8 - nacc)) - 1, 8 - nacc)
+            out += bytes([0xFF, 0xD0 + it[1]])
+        else:
+            put(*tables[(it[0], it[1])][0][it[2]])
+    if nacc:
+        put((1 << (8 - nacc)) - 1, 8 - nacc)
+    seg = lambda m, body: bytes([0xFF, m]) + struct.pack(">H", len(body) + 2) + body
+    jf = b"\xff\xd8" + seg(0xE0, b"JFIF\0\1\1\0\0\1\0\1\0\0")
+    for i in range(1 if grey else 2):
+        jf += seg(0xDB, bytes([i]) + bytes(int(qt[i].reshape(64)[ZIGZAG[k]]) for k in range(64)))
+    jf += seg(0xC0, struct.pack(">BHHB", 8, h, w, len(planes)) + b"".join(bytes([ci + 1, (sh << 4) | sv, 0 if ci == 0 else 1]) for ci, (sh, sv) in enumerate(samp)))
+    for (kind, tb), (_, counts, syms) in tables.items():
+        jf += seg(0xC4, bytes([(16 if kind == "ac" else 0) | tb]) + bytes(counts) + bytes(syms))
+    if restart:
+        jf += seg(0xDD, struct.pack(">H", restart))
+    jf += seg(0xDA, bytes([len(planes)]) + b"".join(bytes([ci + 1, 0x00 if ci == 0 else 0x11]) for ci in range(len(planes))) + bytes([0, 63, 0]))
+    open(path, "wb").write(jf + bytes(out) + b"\xff\xd9")
+    # what a decoder must deliver
+    up = []
+    for ci, (sh, sv) in enumerate(samp):
+        up.append(np.repeat(np.repeat(recon[ci], vmax // sv, axis=0), hmax // sh, axis=1)[:h, :w])
+    if grey:
+        return np.stack([up[0]] * 3, axis=-1)
+    yy, cb, cr = up[0], up[1] - 128.0, up[2] - 128.0
+    return np.clip(np.rint(np.stack([yy + 1.402 * cr, yy - 0.344136 * cb - 0.714136 * cr, yy + 1.772 * cb], axis=-1)), 0, 255)
+
+
+def test_baseline_jpeg(exe, tmp_path):
+    rng = np.random.RandomState(8)
+    h, w = 37, 53                                                   # not multiples of the MCU size
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([128 + 100 * np.sin(xx / 7.0), 128 + 100 * np.cos(yy / 5.0), (xx * 3 + yy * 5) % 256], axis=-1) + rng.randint(-12, 13, size=(h, w, 3))
+    img = np.clip(img, 0, 255).astype(np.uint8)
+    for tag, kw in (("444", {}), ("420", {"sampling": (2, 2)}), ("422_rst", {"sampling": (2, 1), "restart": 3}), ("grey_rst", {"grey": True, "restart": 2}), ("fine", {"q": 1}), ("flatcodes", {"optimal": False, "sampling": (1, 2)})):
+        p = str(tmp_path / (tag + ".jpg"))
+        want = write_baseline_jpeg(p, img, **kw)
+        got, err = decode(exe, p, tmp_path)
+        assert got is not None, (tag, err)
+        diff = np.abs(got[..., :3].astype(np.int32) - want.astype(np.int32))
+        assert diff.max() <= 1 and diff.mean() < 0.02, (tag, diff.max(), diff.mean())   # float32 vs float64 IDCT: isolated +-1
+        assert (got[..., 3] == 255).all()
+        orig = img.astype(np.float64)
+        if kw.get("grey"):
+            orig = np.repeat((0.299 * orig[..., 0] + 0.587 * orig[..., 1] + 0.114 * orig[..., 2])[..., None], 3, axis=-1)
+        assert np.abs(got[..., :3].astype(np.float64) - orig).mean() < (12 if tag != "fine" else 6)   # and it is the picture, not noise
+
+
 def test_rejects_what_it_cannot_decode(exe, tmp_path):
-    p = str(tmp_path / "x.jpg"); open(p, "wb").write(b"\xff\xd8\xff\xe0" + bytes(64))
+    p = str(tmp_path / "x.jpg"); open(p, "wb").write(b"\xff\xd8\xff\xc2" + struct.pack(">H", 17) + bytes(15) + b"\xff\xd9")
     got, err = decode(exe, p, tmp_path)
-    assert got is None and "JPEG" in err
+    assert got is None and "progressive" in err
+    p = str(tmp_path / "y.jpg"); open(p, "wb").write(b"\xff\xd8\xff\xe0" + bytes(64))
+    got, err = decode(exe, p, tmp_path)
+    assert got is None
     rows = [bytes(12)] * 4
     p = str(tmp_path / "i.png"); write_png(p, rows, 2, 8, [0], interlace=1)
     got, err = decode(exe, p, tmp_path)
