@@ -126,7 +126,9 @@ def cpu_sample(o, desc, width, height, subframe, seconds_hint=None):
     return rays, dt, st["samples"]
 
 
-def cpu_baseline(desc, target_s=12.0):
+def cpu_baseline(desc, target_s=12.0, gpu=None):
+    """Times the oracle port on a bounded sample; with `gpu` (the product context, after its timed region) the same
+    subframe is also rendered on the GPU and compared: the checker use of the oracle (same-seed relMSE)."""
     o = oracle_scene(desc)
     cores = os.cpu_count() or 1
     rays, dt, _ = cpu_sample(o, desc, 96, 54, 0)  # probe
@@ -135,10 +137,21 @@ def cpu_baseline(desc, target_s=12.0):
     scale = max(1.0, min(20.0, (target_s * rate / rays) ** 0.5))
     w, h = int(96 * scale) // 8 * 8, int(54 * scale) // 2 * 2
     rays, dt, samples = cpu_sample(o, desc, w, h, 0)
+    out = {"value": rays / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "%dx%d px x %d spl subframe of the same scene and camera (%d rays, %.1f s, BVH2 build excluded)" % (w, h, SPL, rays, dt),
+           "samples_per_s": samples / dt}
+    if gpu is not None:
+        import numpy as np
+        from rendertoy3c_b200.api import make_settings
+        a = o.download_accum()[..., :3].astype(np.float64)
+        uvw = gpu.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, w / h)
+        gpu.launch_subframe(make_settings(desc, uvw, 0, samples_per_launch=SPL, width=w, height=h, max_depth=8))
+        b = gpu.download_accum()[..., :3].astype(np.float64)
+        out["same_seed_check"] = {"relMSE_gpu_vs_cpu": float(np.mean((b - a) ** 2 / (a ** 2 + 1e-2))), "max_abs_diff": float(np.abs(b - a).max()),
+                                  "bit_identical": bool(np.array_equal(o.download_accum().view(np.uint32), gpu.download_accum().view(np.uint32))),
+                                  "what": "float accumulation buffer of that subframe, GPU (librt3.so) vs CPU oracle"}
     o.close()
-    return {"value": rays / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%dx%d px x %d spl subframe of the same scene and camera (%d rays, %.1f s, BVH2 build excluded)" % (w, h, SPL, rays, dt),
-            "samples_per_s": samples / dt}
+    return out
 
 
 def run_reference(args):
@@ -361,7 +374,7 @@ def run_rt3(args):
             "stage_ms_last_step": stage,
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(desc)
+            out["cpu_baseline"] = cpu_baseline(desc, gpu=g)
         print(json.dumps(out))
     g.close()
     if world > 1:
