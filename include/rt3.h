@@ -127,6 +127,18 @@ int rt3_trace(rt3_context_t ctx, const rt3_ray* rays, int n, int any_hit, rt3_hi
 int rt3_trace_device(rt3_context_t ctx, const void* d_rays, int n, int any_hit, void* d_hits);
 
 /* ---- results ---------------------------------------------------------------------------- */
+/* The SDK's stage record (cuda/LocalGeometry.h:40-58, one texcoord set) for hits returned by rt3_trace: world-space P
+ * (interpolated vertices, object -> world at the ray time), shading normal N and geometric normal Ng (world space,
+ * unit length), UV, the object-space derivatives dndu/dndv/dpdu/dpdv as getLocalGeometry forms them
+ * (LocalGeometry.h:126-160) and color = 1.  Spheres and curves (empty in the SDK): P = o + t d, N = Ng = surface
+ * normal, UV = (0,0) / (u,0), zero derivatives.  Misses give an all-zero record. */
+typedef struct rt3_local_geometry {
+    float P[3], N[3], Ng[3];
+    float UV[2], dndu[3], dndv[3], dpdu[3], dpdv[3];
+    float color[4];
+} rt3_local_geometry;
+int rt3_get_local_geometry(rt3_context_t ctx, const rt3_ray* rays, const rt3_hit* hits, int n, rt3_local_geometry* out);
+
 int rt3_download_accum(rt3_context_t ctx, float* rgba);   /* float4 accum_buffer [h][w][4]; row 0 = image bottom (Q19) */
 int rt3_download_frame(rt3_context_t ctx, uint8_t* rgba8);/* uchar4 frame_buffer, make_color cuda/helpers.h:57-66 */
 int rt3_accum_device_ptr(rt3_context_t ctx, void** d_ptr, uint64_t* n_floats); /* for an external collective (torch.distributed / NCCL) */

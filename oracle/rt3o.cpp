@@ -412,6 +412,66 @@ struct rt3o_scene {
     }
 
 
+    // The SDK's complete stage record (cuda/LocalGeometry.h:40-175, one texcoord set): world P from the interpolated
+    // object-space vertices, Ng, N, UV and the object-space derivatives exactly as getLocalGeometry forms them
+    // (LocalGeometry.h:126-160).  Spheres / curves (empty in the SDK): P = o + t d, N = Ng = surface normal, zero derivatives.
+    void local_geometry_full(const Hit& h, f3 o, f3 d, float time, float out[27]) const {
+        for (int k = 0; k < 27; k++) out[k] = 0.0f;
+        const Instance& in = inst[h.inst];
+        const Blas& b = *blas[in.blas];
+        f3 P, N, Ng, dndu{0, 0, 0}, dndv{0, 0, 0}, dpdu{0, 0, 0}, dpdv{0, 0, 0};
+        f2 uv{0, 0};
+        if (b.type == PRIM_TRI) {
+            const bool moving = in.nkeys > 0;
+            Affine m{}, mi{};
+            if (moving) { m = lerp_keys(in.keys.data(), in.nkeys, in.t0, in.t1, time); mi = invert_affine(m); }
+            const int i0 = b.idx[3 * h.prim], i1 = b.idx[3 * h.prim + 1], i2 = b.idx[3 * h.prim + 2];
+            f3 P0, P1, P2;
+            if (b.vkeys <= 1) {
+                P0 = b.verts[i0]; P1 = b.verts[i1]; P2 = b.verts[i2];
+            } else {
+                const float tc = fminf(fmaxf(time, 0.0f), 1.0f);
+                const float f = tc * (float)(b.vkeys - 1);
+                int ki = (int)floorf(f);
+                if (ki > b.vkeys - 2) ki = b.vkeys - 2;
+                const float al = f - (float)ki, w = 1.0f - al;
+                const f3* k0 = &b.verts[(size_t)ki * b.nv];
+                const f3* k1 = k0 + b.nv;
+                P0 = {w * k0[i0].x + al * k1[i0].x, w * k0[i0].y + al * k1[i0].y, w * k0[i0].z + al * k1[i0].z};
+                P1 = {w * k0[i1].x + al * k1[i1].x, w * k0[i1].y + al * k1[i1].y, w * k0[i1].z + al * k1[i1].z};
+                P2 = {w * k0[i2].x + al * k1[i2].x, w * k0[i2].y + al * k1[i2].y, w * k0[i2].z + al * k1[i2].z};
+            }
+            const float w0 = 1.0f - h.u - h.v;
+            f3 p = w0 * P0 + h.u * P1 + h.v * P2;
+            if (moving) p = xform_point(m, p);
+            P = xform_point(in.stat, p);
+            f3 ng = cross(P1 - P0, P2 - P0);
+            const f3 N0 = b.normals[i0], N1 = b.normals[i1], N2 = b.normals[i2];
+            f3 n = w0 * N0 + h.u * N1 + h.v * N2;
+            if (moving) { ng = xform_normal_by_inverse(mi, ng); n = xform_normal_by_inverse(mi, n); }
+            Ng = normalize(xform_normal_by_inverse(in.stat_inv, ng));
+            N = normalize(xform_normal_by_inverse(in.stat_inv, n));
+            const f3 dp1 = P0 - P2, dp2 = P1 - P2, dn1 = N0 - N2, dn2 = N1 - N2;
+            const f2 U0 = b.uvs[i0], U1 = b.uvs[i1], U2 = b.uvs[i2];
+            uv.x = w0 * U0.x + h.u * U1.x + h.v * U2.x;
+            uv.y = w0 * U0.y + h.u * U1.y + h.v * U2.y;
+            const float du1 = U0.x - U2.x, du2 = U1.x - U2.x, dv1 = U0.y - U2.y, dv2 = U1.y - U2.y;
+            const float det = du1 * dv2 - dv1 * du2;
+            const float invdet = 1.0f / det;
+            dpdu = (dv2 * dp1 - dv1 * dp2) * invdet;
+            dpdv = ((-du2) * dp1 + du1 * dp2) * invdet;
+            dndu = (dv2 * dn1 - dv1 * dn2) * invdet;
+            dndv = ((-du2) * dn1 + du1 * dn2) * invdet;
+        } else {
+            local_geometry(h, o, d, time, N, uv);
+            Ng = N;
+            P = o + h.t * d;
+        }
+        const float v[27] = {P.x, P.y, P.z, N.x, N.y, N.z, Ng.x, Ng.y, Ng.z, uv.x, uv.y, dndu.x, dndu.y, dndu.z, dndv.x, dndv.y, dndv.z,
+                             dpdu.x, dpdu.y, dpdu.z, dpdv.x, dpdv.y, dpdv.z, 1.0f, 1.0f, 1.0f, 1.0f};
+        for (int k = 0; k < 27; k++) out[k] = v[k];
+    }
+
     // ---------------------------------------------------------------------------------- CORRECTED mode (mode = 1)
     // the same stages with the estimator errors Q2-Q5, Q7, Q8 fixed — unbiased
     // Lambertian path tracing with uniform-light NEE and two-strategy MIS (power heuristic):
@@ -796,6 +856,22 @@ int rt3o_trace(rt3o_scene* s, const rt3_ray* rays, int n, int any_hit, rt3_hit* 
         std::memset(&o, 0, sizeof(o));
         o.t = h.t; o.u = h.u; o.v = h.v; o.prim = h.prim; o.inst = h.inst;
     });
+    return 0;
+    RT3O_CATCH(-1)
+}
+
+int rt3o_get_local_geometry(rt3o_scene* s, const rt3_ray* rays, const rt3_hit* hits, int n, rt3_local_geometry* out) {
+    RT3O_TRY
+    if (!s || !s->built) { g_err = "get_local_geometry: accel not built"; return -4; }
+    if (n < 0 || (n > 0 && (!rays || !hits || !out))) { g_err = "get_local_geometry: bad argument"; return -1; }
+    static_assert(sizeof(rt3_local_geometry) == 27 * sizeof(float), "record = 27 floats");
+    for (int i = 0; i < n; i++) {
+        float* o = reinterpret_cast<float*>(out + i);
+        if (hits[i].prim < 0) { for (int k = 0; k < 27; k++) o[k] = 0.0f; continue; }
+        Hit h; h.t = hits[i].t; h.u = hits[i].u; h.v = hits[i].v; h.prim = hits[i].prim; h.inst = hits[i].inst;
+        const rt3_ray& r = rays[i];
+        s->local_geometry_full(h, {r.o[0], r.o[1], r.o[2]}, {r.d[0], r.d[1], r.d[2]}, r.time, o);
+    }
     return 0;
     RT3O_CATCH(-1)
 }

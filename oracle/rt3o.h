@@ -30,6 +30,7 @@ int rt3o_scene_set_hitgroup(rt3o_scene*, int instance_id, const float emission[3
 int rt3o_scene_set_lights(rt3o_scene*, const void* lights68, int n);
 /* accel: 0 = brute force over every instance x primitive, 1 = BVH2 (validated against 0) */
 int rt3o_trace(rt3o_scene*, const rt3_ray* rays, int n, int any_hit, rt3_hit* hits, int accel, int nthreads);
+int rt3o_get_local_geometry(rt3o_scene*, const rt3_ray* rays, const rt3_hit* hits, int n, rt3_local_geometry* out);  /* cuda/LocalGeometry.h:61-175 */
 int rt3o_launch_subframe(rt3o_scene*, const rt3_render_settings*, int nthreads);
 int rt3o_download_accum(rt3o_scene*, float* rgba);
 int rt3o_download_frame(rt3o_scene*, uint8_t* rgba8);

@@ -38,7 +38,9 @@ class Stats(C.Structure):
 # rt3_ray (48 B) / rt3_hit (32 B)
 RAY_DTYPE = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4"), ("time", "<f4"), ("pad", "<f4", 3)])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<i4"), ("inst", "<i4"), ("pad", "<i4", 3)])
-assert RAY_DTYPE.itemsize == 48 and HIT_DTYPE.itemsize == 32
+LOCAL_GEOMETRY_DTYPE = np.dtype([("P", "<f4", 3), ("N", "<f4", 3), ("Ng", "<f4", 3), ("UV", "<f4", 2), ("dndu", "<f4", 3), ("dndv", "<f4", 3),
+                                 ("dpdu", "<f4", 3), ("dpdv", "<f4", 3), ("color", "<f4", 4)])   # rt3_local_geometry, cuda/LocalGeometry.h:40-58
+assert RAY_DTYPE.itemsize == 48 and HIT_DTYPE.itemsize == 32 and LOCAL_GEOMETRY_DTYPE.itemsize == 108
 LIGHT_BYTES = 68  # rendertoy3o::Light (reference src/light.h:13-22)
 
 

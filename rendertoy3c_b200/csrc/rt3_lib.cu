@@ -119,6 +119,7 @@ struct rt3_context {
         s.hitgroups = d_hg.p;
         s.blas = d_blas.p;
         s.keys = d_keys.p;
+        s.inst_fwd = d_static.p;
         s.error_flags = d_flags.p;
         s.max_stack = d_flags.p + 1;
         return s;
@@ -505,7 +506,7 @@ int rt3_accel_build(rt3_context_t c) {
     std::vector<BlasBounds> bb(ng + 1);
     for (size_t i = 0; i < ng; i++) {
         const Geometry& g = *c->geoms[i];
-        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p, g.vkeys, g.verts.p};
+        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p, g.vkeys, g.verts.p, g.nv};
         for (int k = 0; k < 3; k++) { bb[i].lo[k] = g.bvh.lo[k]; bb[i].hi[k] = g.bvh.hi[k]; }
     }
     bt[ng] = BlasDev{c->m_nodes_p, c->m_prims_p, PRIM_TRI, c->m_bvh.num_prims, nullptr, nullptr, nullptr, nullptr, nullptr, 1u, nullptr};
@@ -769,6 +770,27 @@ int rt3_trace(rt3_context_t c, const rt3_ray* rays, int n, int any_hit, rt3_hit*
     const int rc = rt3_trace_device(c, d_rays.p, n, any_hit, d_hits.p);
     if (rc != RT3_OK) return rc;
     d2h(hits, d_hits.p, sizeof(rt3_hit) * (size_t)n, c->stream);
+    stream_sync(c->stream);
+    RT3_API_END
+}
+
+// getLocalGeometry (cuda/LocalGeometry.h:61-175) for a batch of rays and the hit records rt3_trace returned for them
+int rt3_get_local_geometry(rt3_context_t c, const rt3_ray* rays, const rt3_hit* hits, int n, rt3_local_geometry* out) {
+    RT3_API_BEGIN
+    static_assert(sizeof(rt3_local_geometry) == 108, "ABI record size");
+    RT3_REQUIRE(c && c->built, RT3_ERR_STATE, "get_local_geometry: rt3_accel_build has not been called");
+    RT3_REQUIRE(n >= 0 && (n == 0 || (rays && hits && out)), RT3_ERR_INVALID, "get_local_geometry: bad argument");
+    for (int i = 0; i < n; i++)
+        RT3_REQUIRE(hits[i].prim < 0 || (hits[i].inst >= 0 && (size_t)hits[i].inst < c->inst.size() && (uint32_t)hits[i].prim < c->geoms[c->inst[(size_t)hits[i].inst].blas]->nprims),
+                    RT3_ERR_INVALID, "get_local_geometry: hit record does not belong to this scene");
+    if (n == 0) return RT3_OK;
+    upload_hitgroups(c);
+    DevBuf<float4> d_rays(3 * (size_t)n), d_hits(2 * (size_t)n);
+    DevBuf<float> d_out(27 * (size_t)n);
+    h2d(d_rays.p, rays, sizeof(rt3_ray) * (size_t)n, c->stream);
+    h2d(d_hits.p, hits, sizeof(rt3_hit) * (size_t)n, c->stream);
+    RT3_LAUNCH_1D(k_local_geometry, (uint32_t)n, c->stream, c->trav_scene(), (const float4*)d_rays.p, (const float4*)d_hits.p, d_out.p);
+    d2h(out, d_out.p, sizeof(rt3_local_geometry) * (size_t)n, c->stream);
     stream_sync(c->stream);
     RT3_API_END
 }

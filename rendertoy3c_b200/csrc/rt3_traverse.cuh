@@ -59,7 +59,8 @@ struct BlasDev {             // per geometry, device-resident table entry
     const float4* cr;        // spheres [n] / curve control points [ncp]
     const int32_t* seg;      // curves [nseg]
     uint32_t vkeys;          // PRIM_TRI_MOTION: vertex keys per triangle record (record = vkeys x 3 float4)
-    const float* verts;      // mesh [nv][3], key 0 (corrected mode: area of BSDF-sampled emitter hits)
+    const float* verts;      // mesh [vkeys][nv][3] (corrected mode: area of BSDF-sampled emitter hits; rt3_get_local_geometry)
+    uint32_t nv;             // vertices per key
 };
 
 struct InstanceDev {         // traversal record (64 B)
@@ -86,6 +87,7 @@ struct TravScene {
     const HitGroupDev* hitgroups;
     const BlasDev* blas;
     const float* keys;
+    const float* inst_fwd;          // [instance][12] object -> world of the static instance transform (rt3_get_local_geometry)
     uint32_t* error_flags;          // bit0 stack overflow
     uint32_t* max_stack;
     // single-level fast path: all identity, static triangle-mesh instances (every instance the

@@ -489,6 +489,91 @@ RT3_HD LocalGeometry local_geometry(const TravScene& sc, const HitRec& h, float3
     return lg;
 }
 
+// The complete stage record of the SDK (cuda/LocalGeometry.h:40-175, one texcoord set), for rt3_get_local_geometry:
+// world-space P from the interpolated object-space vertices, geometric normal Ng, shading normal N, UV and the
+// object-space derivatives dpdu, dpdv, dndu, dndv exactly as the SDK forms them (not transformed, LocalGeometry.h:126-160).
+// Spheres and curves (left empty by the SDK, LocalGeometry.h:164-167) get P = o + t d, N = Ng = their D7 normal,
+// UV as in the shade stage and zero derivatives.
+struct LocalGeometryFull { float3 P, N, Ng; float2 UV; float3 dndu, dndv, dpdu, dpdv; };
+
+RT3_HD LocalGeometryFull local_geometry_full(const TravScene& sc, const HitRec& h, float3 o, float3 d, float time) {
+    LocalGeometryFull lg;
+    const float3 z = v3(0.0f, 0.0f, 0.0f);
+    lg.P = z; lg.N = z; lg.Ng = z; lg.UV = make_float2(0.0f, 0.0f); lg.dndu = z; lg.dndv = z; lg.dpdu = z; lg.dpdv = z;
+    const InstanceDev* in = sc.instances + h.inst;
+    const BlasDev* b = sc.blas + in->blas;
+    const float t1 = sc.hitgroups[h.inst].t1;
+    Affine si, fs, m, mi;
+#pragma unroll
+    for (int j = 0; j < 12; j++) { si.m[j] = in->inv_static[j]; fs.m[j] = sc.inst_fwd[12 * (size_t)h.inst + j]; }
+    const bool moving = in->nkeys > 0;
+    if (moving) { m = lerp_keys(sc.keys + in->key_offset, (int)in->nkeys, in->t0, t1, time); mi = invert_affine(m); }
+    if (b->type == PRIM_TRI || b->type == PRIM_TRI_MOTION) {
+        const int i0 = b->idx[3 * (size_t)h.prim], i1 = b->idx[3 * (size_t)h.prim + 1], i2 = b->idx[3 * (size_t)h.prim + 2];
+        float3 P0, P1, P2;
+        if (b->vkeys <= 1u) {
+            P0 = ld3(b->verts + 3 * (size_t)i0); P1 = ld3(b->verts + 3 * (size_t)i1); P2 = ld3(b->verts + 3 * (size_t)i2);
+        } else {  // vertex keys at the ray time, as in the traversal
+            const float tc = fminf(fmaxf(time, 0.0f), 1.0f);
+            const float f = tc * (float)(b->vkeys - 1u);
+            int ki = (int)floorf(f);
+            if (ki > (int)b->vkeys - 2) ki = (int)b->vkeys - 2;
+            const float al = f - (float)ki, w = 1.0f - al;
+            const float* k0 = b->verts + 3 * (size_t)ki * b->nv;
+            const float* k1 = k0 + 3 * (size_t)b->nv;
+            const float3 a0 = ld3(k0 + 3 * (size_t)i0), a1 = ld3(k0 + 3 * (size_t)i1), a2 = ld3(k0 + 3 * (size_t)i2);
+            const float3 c0 = ld3(k1 + 3 * (size_t)i0), c1 = ld3(k1 + 3 * (size_t)i1), c2 = ld3(k1 + 3 * (size_t)i2);
+            P0 = v3(w * a0.x + al * c0.x, w * a0.y + al * c0.y, w * a0.z + al * c0.z);
+            P1 = v3(w * a1.x + al * c1.x, w * a1.y + al * c1.y, w * a1.z + al * c1.z);
+            P2 = v3(w * a2.x + al * c2.x, w * a2.y + al * c2.y, w * a2.z + al * c2.z);
+        }
+        const float w0 = 1.0f - h.u - h.v;
+        float3 p = add(add(mul(P0, w0), mul(P1, h.u)), mul(P2, h.v));
+        if (moving) p = xform_point(m, p);
+        lg.P = xform_point(fs, p);
+        float3 ng = cross(sub(P1, P0), sub(P2, P0));
+        const float3 N0 = ld3(b->normals + 3 * (size_t)i0), N1 = ld3(b->normals + 3 * (size_t)i1), N2 = ld3(b->normals + 3 * (size_t)i2);
+        float3 n = add(add(mul(N0, w0), mul(N1, h.u)), mul(N2, h.v));
+        if (moving) { ng = xform_normal_by_inverse(mi, ng); n = xform_normal_by_inverse(mi, n); }
+        lg.Ng = normalize(xform_normal_by_inverse(si, ng));
+        lg.N = normalize(xform_normal_by_inverse(si, n));
+        const float3 dp1 = sub(P0, P2), dp2 = sub(P1, P2), dn1 = sub(N0, N2), dn2 = sub(N1, N2);
+        const float u0x = b->uvs[2 * (size_t)i0], u0y = b->uvs[2 * (size_t)i0 + 1], u1x = b->uvs[2 * (size_t)i1], u1y = b->uvs[2 * (size_t)i1 + 1],
+                    u2x = b->uvs[2 * (size_t)i2], u2y = b->uvs[2 * (size_t)i2 + 1];
+        lg.UV.x = w0 * u0x + h.u * u1x + h.v * u2x;
+        lg.UV.y = w0 * u0y + h.u * u1y + h.v * u2y;
+        const float du1 = u0x - u2x, du2 = u1x - u2x, dv1 = u0y - u2y, dv2 = u1y - u2y;
+        const float det = du1 * dv2 - dv1 * du2;
+        const float invdet = 1.0f / det;
+        lg.dpdu = mul(sub(mul(dp1, dv2), mul(dp2, dv1)), invdet);
+        lg.dpdv = mul(add(mul(dp1, -du2), mul(dp2, du1)), invdet);
+        lg.dndu = mul(sub(mul(dn1, dv2), mul(dn2, dv1)), invdet);
+        lg.dndv = mul(add(mul(dn1, -du2), mul(dn2, du1)), invdet);
+    } else {
+        const LocalGeometry g = local_geometry(sc, h, o, d, time);
+        lg.P = g.P; lg.N = g.N; lg.Ng = g.N; lg.UV = g.UV;
+    }
+    return lg;
+}
+
+// rays [n] x {o,tmin | d,tmax | time,...}, hits [n] x {t,u,v,prim | inst,...} -> 27 floats per record (rt3_local_geometry); misses: zeros
+RT3_GLOBAL(k_local_geometry, TravScene sc, const float4* rays, const float4* hits, float* out) {
+    const uint32_t i = RT3_THREAD_ID();
+    if (i >= rt3_n_) return;
+    float* r = out + 27 * (size_t)i;
+    const float4 h0 = hits[2 * (size_t)i], h1 = hits[2 * (size_t)i + 1];
+    HitRec h;
+    h.t = h0.x; h.u = h0.y; h.v = h0.z; h.prim = (int)rt3_f2u(h0.w); h.inst = (int)rt3_f2u(h1.x);
+    if (h.prim < 0) { for (int k = 0; k < 27; k++) r[k] = 0.0f; return; }
+    const float4 r0 = rays[3 * (size_t)i], r1 = rays[3 * (size_t)i + 1], r2 = rays[3 * (size_t)i + 2];
+    const LocalGeometryFull g = local_geometry_full(sc, h, v3(r0), v3(r1), r2.x);
+    r[0] = g.P.x; r[1] = g.P.y; r[2] = g.P.z; r[3] = g.N.x; r[4] = g.N.y; r[5] = g.N.z; r[6] = g.Ng.x; r[7] = g.Ng.y; r[8] = g.Ng.z;
+    r[9] = g.UV.x; r[10] = g.UV.y;
+    r[11] = g.dndu.x; r[12] = g.dndu.y; r[13] = g.dndu.z; r[14] = g.dndv.x; r[15] = g.dndv.y; r[16] = g.dndv.z;
+    r[17] = g.dpdu.x; r[18] = g.dpdu.y; r[19] = g.dpdu.z; r[20] = g.dpdv.x; r[21] = g.dpdv.y; r[22] = g.dpdv.z;
+    r[23] = 1.0f; r[24] = 1.0f; r[25] = 1.0f; r[26] = 1.0f;
+}
+
 // one atomic per warp: ballot + popc prefix (device); sequential counter (emulation)
 RT3_HD uint32_t warp_append(uint32_t* counter, bool pred) {
 #ifdef RT3_EMULATE

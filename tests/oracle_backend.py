@@ -38,7 +38,7 @@ def lib():
         L.rt3o_kat_tea4.argtypes = [C.c_uint32, C.c_uint32]
         for name in ("rt3o_scene_destroy", "rt3o_mesh_create", "rt3o_spheres_create", "rt3o_curves_create", "rt3o_texture_create",
                      "rt3o_accel_append_instance", "rt3o_accel_append_animated_instance", "rt3o_accel_build",
-                     "rt3o_scene_set_hitgroup", "rt3o_scene_set_lights", "rt3o_trace", "rt3o_launch_subframe",
+                     "rt3o_scene_set_hitgroup", "rt3o_scene_set_lights", "rt3o_trace", "rt3o_get_local_geometry", "rt3o_launch_subframe",
                      "rt3o_download_accum", "rt3o_download_frame", "rt3o_get_stats", "rt3o_reset_stats"):
             getattr(L, name).argtypes = None
     return _lib
@@ -129,6 +129,15 @@ class OracleScene:
         self._chk(self.L.rt3o_trace(self.s, rays.ctypes.data_as(C.c_void_p), C.c_int(len(rays)), C.c_int(1 if any_hit else 0),
                                     hits.ctypes.data_as(C.c_void_p), C.c_int(accel), C.c_int(self.nthreads)))
         return hits
+
+    def get_local_geometry(self, rays, hits):
+        from rendertoy3c_b200._abi import LOCAL_GEOMETRY_DTYPE
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.ascontiguousarray(hits, dtype=HIT_DTYPE)
+        out = np.zeros(len(rays), dtype=LOCAL_GEOMETRY_DTYPE)
+        self._chk(self.L.rt3o_get_local_geometry(self.s, rays.ctypes.data_as(C.c_void_p), hits.ctypes.data_as(C.c_void_p), C.c_int(len(rays)),
+                                                 out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def launch_subframe(self, settings: RenderSettings):
         self.width, self.height = settings.width, settings.height

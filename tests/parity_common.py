@@ -56,6 +56,11 @@ def check_trace(backend, oracle, rays, accel=1):
     ab = backend.trace(rays, any_hit=True)
     ao = oracle.trace(rays, any_hit=True, accel=accel)
     assert np.array_equal(ab["prim"] >= 0, ao["prim"] >= 0), "occlusion results differ"
+    # LocalGeometry stage record (cuda/LocalGeometry.h) of those hits: bit-identical, NaN-aware (degenerate uv maps give inf/nan derivatives on both sides)
+    lb = backend.get_local_geometry(rays, hb).view(np.float32).reshape(len(rays), 27)
+    lo = oracle.get_local_geometry(rays, ho).view(np.float32).reshape(len(rays), 27)
+    same = (lb.view(np.uint32) == lo.view(np.uint32)) | (np.isnan(lb) & np.isnan(lo))
+    assert same.all(), "LocalGeometry records differ in %d of %d floats" % ((~same).sum(), same.size)
     return ho
 
 

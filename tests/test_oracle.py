@@ -297,3 +297,39 @@ def test_power_light_sampler_matches_analytic_two_lights():
         got[mode] = cc.render_mean(o, desc, subframes=24, mode=mode, max_depth=2)
         assert abs(got[mode] - want) / want < 0.02, (mode, got[mode], want)
     assert got[1] != got[2]
+
+
+def test_local_geometry_record_analytic():
+    """A9 (cuda/LocalGeometry.h:61-175): world P from interpolated vertices, unit N / Ng in world space, UV, and the
+    object-space derivatives of a triangle whose uv map is the identity on its edges"""
+    from rendertoy3c_b200._abi import RAY_DTYPE
+    from rendertoy3c_b200.scenes import IDENTITY
+    o = ob.OracleScene()
+    verts = np.array([[0, 0, 0], [2, 0, 0], [0, 3, 0]], np.float32)
+    normals = np.array([[0, 0, 1], [0, 0, 1], [0, 0, 1]], np.float32)
+    uvs = np.array([[0, 0], [1, 0], [0, 1]], np.float32)
+    m = o.mesh_create(verts, np.array([[0, 1, 2]], np.int32), normals, uvs)
+    xf = IDENTITY.copy()                                            # rotate 90 degrees about x (z -> -y), then translate by (5, 6, 7)
+    xf[:] = [1, 0, 0, 5, 0, 0, -1, 6, 0, 1, 0, 7]
+    i0 = o.append_instance(m, IDENTITY)
+    i1 = o.append_instance(m, xf)
+    for i in (i0, i1):
+        o.set_hitgroup(i, (0, 0, 0), (0.5, 0.5, 0.5), -1)
+    o.accel_build()
+    rays = np.zeros(3, RAY_DTYPE)
+    rays["o"] = [[0.5, 0.75, 4.0], [5.5, 10.0, 7.75], [50, 50, 50]]
+    rays["d"] = [[0, 0, -1], [0, -1, 0], [0, 0, 1]]
+    rays["tmax"] = 1e16
+    hits = o.trace(rays, accel=0)
+    assert list(hits["inst"]) == [i0, i1, -1] and list(hits["prim"][:2]) == [0, 0]
+    lg = o.get_local_geometry(rays, hits)
+    assert np.allclose(lg["P"][0], [0.5, 0.75, 0.0], atol=1e-6) and np.allclose(lg["P"][1], [5.5, 6.0, 7.75], atol=1e-5)
+    assert np.allclose(lg["P"][:2], rays["o"][:2] + hits["t"][:2, None] * rays["d"][:2], atol=1e-5)
+    assert np.allclose(lg["Ng"][0], [0, 0, 1]) and np.allclose(lg["N"][0], [0, 0, 1])
+    assert np.allclose(lg["Ng"][1], [0, -1, 0], atol=1e-6) and np.allclose(lg["N"][1], [0, -1, 0], atol=1e-6)   # normals follow the rotation
+    assert np.allclose(lg["UV"][0], [0.25, 0.25], atol=1e-6) and np.allclose(lg["UV"][1], [0.25, 0.25], atol=1e-5)
+    for k in range(2):                                              # derivatives stay in object space, like the SDK's
+        assert np.allclose(lg["dpdu"][k], [2, 0, 0]) and np.allclose(lg["dpdv"][k], [0, 3, 0])
+        assert np.allclose(lg["dndu"][k], 0) and np.allclose(lg["dndv"][k], 0)
+        assert np.allclose(lg["color"][k], 1)
+    assert not lg[2].tobytes().strip(b"\0")                         # miss: all-zero record
