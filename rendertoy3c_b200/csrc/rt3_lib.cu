@@ -98,6 +98,11 @@ struct rt3_context {
     DevBuf<uint32_t> trace_fetch;
     // options / stats
     int opt_timing = 0;
+    // connect(d) (shadow rays) and extend(d+1) (next bounce) are independent: connect runs on a second stream so that
+    // the next extend fills the tail of its persistent CTAs; shade(d+1) waits for it (shadow queue + radiance RMW)
+    int opt_overlap = 1;
+    Stream stream2 = 0;
+    Event ev_shade[2], ev_connect[2];
     int opt_ctas_per_sm = 0;
     uint64_t samples = 0;
     float ms[6] = {0, 0, 0, 0, 0, 0};
@@ -137,14 +142,15 @@ struct rt3_context {
 namespace {
 
 template <int MODE>
-void launch_traverse(rt3_context* c, const TraverseArgs& a) {
+void launch_traverse(rt3_context* c, const TraverseArgs& a, Stream st) {
     // single-level scenes (merged world BLAS only) run the lean instantiation
 #ifdef RT3_EMULATE
+    (void)st;
     if (c->single_level) k_traverse<MODE, true>(a);
     else k_traverse<MODE, false>(a);
 #else
-    if (c->single_level) k_traverse<MODE, true><<<c->trav_grid(), RT3_TRAV_THREADS, 0, c->stream>>>(a);
-    else k_traverse<MODE, false><<<c->trav_grid(), RT3_TRAV_THREADS, 0, c->stream>>>(a);
+    if (c->single_level) k_traverse<MODE, true><<<c->trav_grid(), RT3_TRAV_THREADS, 0, st>>>(a);
+    else k_traverse<MODE, false><<<c->trav_grid(), RT3_TRAV_THREADS, 0, st>>>(a);
     RT3_CUDA(cudaGetLastError());
 #endif
     count_launch();
@@ -269,6 +275,8 @@ int rt3_context_create(int device, rt3_context_t* out) {
     RT3_REQUIRE(prop.major >= 10, RT3_ERR_NO_DEVICE, "context_create: kernels are built for sm_100a only");
     c->num_sms = prop.multiProcessorCount;
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    RT3_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    if (const char* e = getenv("RT3_OVERLAP")) c->opt_overlap = atoi(e);  // A/B switch for measurements; rt3_set_option("overlap", v) is the API
 #endif
     c->d_flags.alloc(16);  // [0] error flags, [1] max stack, [2..15] diagnostic counters (RT3_STATS builds)
     c->counters.alloc(4 * MAX_DEPTH_SLOTS);
@@ -286,9 +294,11 @@ void rt3_context_destroy(rt3_context_t c) {
 #ifndef RT3_EMULATE
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaStream_t s = c->stream;
+    cudaStreamSynchronize(c->stream2);
+    cudaStream_t s = c->stream, s2 = c->stream2;
     delete c;
     cudaStreamDestroy(s);
+    cudaStreamDestroy(s2);
 #else
     delete c;
 #endif
@@ -317,6 +327,7 @@ int rt3_set_option(rt3_context_t c, const char* key, int value) {
     RT3_REQUIRE(c && key, RT3_ERR_INVALID, "set_option: null argument");
     const std::string k(key);
     if (k == "timing") c->opt_timing = value;
+    else if (k == "overlap") c->opt_overlap = value;
     else if (k == "persist_ctas_per_sm") c->opt_ctas_per_sm = value;
     else if (k == "merge_identity") { c->opt_merge = value; c->built = false; }
     else if (k == "l2_persist") { c->opt_l2_persist = value; c->built = false; }
@@ -685,6 +696,12 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
     if (timing) event_record(ev[1], c->stream);
 
     const bool unbounded = rs->max_depth <= 0;
+#ifdef RT3_EMULATE
+    const bool overlap = false;
+#else
+    const bool overlap = c->opt_overlap != 0 && !timing && !unbounded;
+#endif
+    int connect_pending = -1;  // index of the ev_connect event the main stream still has to wait for
     const uint32_t depth_limit = unbounded ? M - 2 : (uint32_t)rs->max_depth;
     RT3_REQUIRE(depth_limit <= M - 2, RT3_ERR_INVALID, "launch_subframe: max_depth too large");
     for (uint32_t depth = 0; depth < depth_limit; depth++) {
@@ -698,8 +715,9 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
         a.hit0 = q.hit0; a.hit_inst = q.hit_inst; a.contrib = nullptr; a.result = nullptr;
         a.stat = c->d_stats.p + (depth == 0 ? 0 : 1);
         a.faithful = 0;
-        launch_traverse<TRAV_EXTEND>(c, a);
+        launch_traverse<TRAV_EXTEND>(c, a, c->stream);
         if (timing) event_record(e1, c->stream);
+        if (overlap && connect_pending >= 0) { stream_wait(c->stream, c->ev_connect[connect_pending]); connect_pending = -1; }  // shade reuses the shadow queue and adds to the same radiance slots
 #ifdef RT3_EMULATE
         k_shade(f, sc, q);
 #else
@@ -708,6 +726,10 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
 #endif
         count_launch();
         if (timing) event_record(e2, c->stream);
+        if (overlap) {  // shadow rays of this bounce on the second stream, behind shade(depth)
+            event_record(c->ev_shade[depth & 1u], c->stream);
+            stream_wait(c->stream2, c->ev_shade[depth & 1u]);
+        }
         TraverseArgs s;
         s.scene = sc;
         s.rays = RayPlanes{q.sh0, q.sh1, q.sh2, 1u};
@@ -715,7 +737,8 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
         s.hit0 = nullptr; s.hit_inst = nullptr; s.contrib = q.sh3; s.result = q.result;
         s.stat = c->d_stats.p + 2;
         s.faithful = rs->mode == 0 ? 1u : 0u;
-        launch_traverse<TRAV_CONNECT>(c, s);
+        launch_traverse<TRAV_CONNECT>(c, s, overlap ? c->stream2 : c->stream);
+        if (overlap) { event_record(c->ev_connect[depth & 1u], c->stream2); connect_pending = (int)(depth & 1u); }
         if (timing) {
             event_record(e3, c->stream);
             stream_sync(c->stream);
@@ -729,6 +752,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
             if (nnext == 0) break;
         }
     }
+    if (overlap && connect_pending >= 0) stream_wait(c->stream, c->ev_connect[connect_pending]);
     if (timing) event_record(ev[2], c->stream);
     RT3_LAUNCH_1D(k_resolve, rs->width * rs->height, c->stream, f, (const float4*)c->result.p, c->accum.p, c->frame.p);
     if (timing) {
@@ -754,8 +778,8 @@ int rt3_trace_device(rt3_context_t c, const void* d_rays, int n, int any_hit, vo
     a.rays = RayPlanes{r, r + 1, r + 2, 3u};
     a.count_ptr = nullptr; a.count = (uint32_t)n; a.fetch = c->trace_fetch.p;
     a.hit0 = (float4*)d_hits; a.hit_inst = nullptr; a.contrib = nullptr; a.result = nullptr; a.stat = nullptr; a.faithful = 0;
-    if (any_hit) launch_traverse<TRAV_TRACE_ANY>(c, a);
-    else launch_traverse<TRAV_TRACE_CLOSEST>(c, a);
+    if (any_hit) launch_traverse<TRAV_TRACE_ANY>(c, a, c->stream);
+    else launch_traverse<TRAV_TRACE_CLOSEST>(c, a, c->stream);
     RT3_API_END
 }
 
