@@ -369,6 +369,7 @@ struct FrameParams {
     uint32_t nlights;
     const float* light_cdf;               // running sum of light_power() over the lights (mode 2)
     const TexDev* tex;
+    uint32_t path_base;                   // first path of this chain (a subframe may be issued as two independent halves)
 };
 
 struct Queues {
@@ -386,8 +387,9 @@ struct Queues {
 
 // ------------------------------------------------------------------------------------ generate (raygen.cu:16-46)
 RT3_GLOBAL(k_generate, FrameParams f, Queues q) {
-    const uint32_t p = RT3_THREAD_ID();
-    if (p >= rt3_n_) return;
+    const uint32_t slot = RT3_THREAD_ID();  // queue slot of this chain; path id = path_base + slot
+    if (slot >= rt3_n_) return;
+    const uint32_t p = f.path_base + slot;
     const uint32_t npix = f.width * f.height;
     const uint32_t pix = p % npix, k = p / npix;
     const uint32_t x = pix % f.width, y = pix / f.width;
@@ -406,13 +408,13 @@ RT3_GLOBAL(k_generate, FrameParams f, Queues q) {
     const float3 dir = normalize(add(add(mul(ld3(f.U), dx), mul(ld3(f.V), dy)), ld3(f.W)));
     uint32_t pseed = seed;
     const float time = f.mode == 0 ? rnd(pseed) : path_time;  // faithful: traceRadiance draws the ray time first (shader_common.h:64)
-    rt3_stcs(&q.ray0[p], make_float4(f.eye[0], f.eye[1], f.eye[2], 0.01f));
-    rt3_stcs(&q.ray1[p], make_float4(dir.x, dir.y, dir.z, 1e16f));
-    rt3_stcs(&q.ray2[p], make_float4(time, rt3_u2f(p), 0.0f, 0.0f));
-    rt3_stcs(&q.st0[p], make_float4(1.0f, 1.0f, 1.0f, rt3_u2f(pseed)));
-    rt3_stcs(&q.st1[p], make_float4(1.0f, 1.0f, 1.0f, rt3_u2f(0u)));
-    rt3_stcs(&q.result[p], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-    if (p == 0) *q.n_cur = rt3_n_;
+    rt3_stcs(&q.ray0[slot], make_float4(f.eye[0], f.eye[1], f.eye[2], 0.01f));
+    rt3_stcs(&q.ray1[slot], make_float4(dir.x, dir.y, dir.z, 1e16f));
+    rt3_stcs(&q.ray2[slot], make_float4(time, rt3_u2f(p), 0.0f, 0.0f));
+    rt3_stcs(&q.st0[slot], make_float4(1.0f, 1.0f, 1.0f, rt3_u2f(pseed)));
+    rt3_stcs(&q.st1[slot], make_float4(1.0f, 1.0f, 1.0f, rt3_u2f(0u)));
+    rt3_stcs(&q.result[p], make_float4(0.0f, 0.0f, 0.0f, 0.0f));  // result is indexed by path id (all chains share it)
+    if (slot == 0) *q.n_cur = rt3_n_;
 }
 
 // ------------------------------------------------------------------------------------ LocalGeometry / LocalShading
