@@ -64,7 +64,7 @@ typedef struct {
  * (src/cuda/cuda_texture.h:16-28).  NOTE the reference casts FilterMode::Linear (=0) to
  * cudaTextureFilterMode where 0 is POINT; filter_mode 0 therefore means point sampling. */
 enum { RT3_ADDRESS_WRAP = 0, RT3_ADDRESS_CLAMP = 1, RT3_ADDRESS_MIRROR = 2, RT3_ADDRESS_BORDER = 3 };
-enum { RT3_FILTER_REFERENCE_LINEAR_IS_POINT = 0 };
+enum { RT3_FILTER_REFERENCE_LINEAR_IS_POINT = 0, RT3_FILTER_REFERENCE_POINT_IS_BILINEAR = 1 };  /* the reference's FilterMode values, by what the hardware does with them */
 
 /* ---- context -------------------------------------------------------------------------- */
 int rt3_context_create(int device, rt3_context_t* out);   /* OptixContext() src/cuda/optix_context.h:231-243 */

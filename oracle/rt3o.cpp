@@ -341,22 +341,48 @@ struct rt3o_scene {
     }
 
     // ------------------------------------------------------------------ shading helpers
+    // Texel index of an integer texel coordinate under an address mode (CUDA programming guide, texture fetching):
+    // wrap = modulo, clamp = nearest edge texel, mirror = reflected every N texels, border = -1 (reads as 0).
+    static int resolve_texel(int i, int n, int mode) {
+        if (mode == RT3_ADDRESS_WRAP) { int m = i % n; return m < 0 ? m + n : m; }
+        if (mode == RT3_ADDRESS_CLAMP) return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+        if (mode == RT3_ADDRESS_MIRROR) { int m = i % (2 * n); if (m < 0) m += 2 * n; return m < n ? m : 2 * n - 1 - m; }
+        return (i >= 0 && i < n) ? i : -1;
+    }
     f3 fetch_texture(int id, float u, float v) const {
-        // point sampling, normalised coords, RGBA8 -> [0,1], no sRGB decode (Q9, Q10)
+        // normalised coords, RGBA8 -> [0,1], no sRGB decode (Q10).  filter 0 = point sampling (what the reference's
+        // `FilterMode::Linear = 0` really selects, Q9); filter 1 = the hardware's bilinear filter (what its
+        // `FilterMode::Point = 1` selects): texel centres at i + 0.5, weights rounded to 8 fractional bits.
         const Texture& tx = tex[id];
-        auto addr = [&](float c, int n) -> int {
-            if (tx.addr == RT3_ADDRESS_WRAP) {
-                float f = c - floorf(c);
+        auto texel = [&](int x, int y) -> f3 {
+            if (x < 0 || y < 0) return {0.0f, 0.0f, 0.0f};  // border
+            const uint8_t* p = &tx.px[4 * ((size_t)y * tx.w + x)];
+            return {(float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f};
+        };
+        if (tx.filt == 0 && (tx.addr == RT3_ADDRESS_WRAP || tx.addr == RT3_ADDRESS_CLAMP)) {
+            auto addr = [&](float c, int n) -> int {
+                if (tx.addr == RT3_ADDRESS_WRAP) {
+                    float f = c - floorf(c);
+                    int i = (int)(f * (float)n);
+                    return i > n - 1 ? n - 1 : i;
+                }
+                float f = fminf(fmaxf(c, 0.0f), 1.0f);
                 int i = (int)(f * (float)n);
                 return i > n - 1 ? n - 1 : i;
-            }
-            float f = fminf(fmaxf(c, 0.0f), 1.0f);
-            int i = (int)(f * (float)n);
-            return i > n - 1 ? n - 1 : i;
-        };
-        int x = addr(u, tx.w), y = addr(v, tx.h);
-        const uint8_t* p = &tx.px[4 * ((size_t)y * tx.w + x)];
-        return {(float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f};
+            };
+            return texel(addr(u, tx.w), addr(v, tx.h));
+        }
+        const float fx = u * (float)tx.w, fy = v * (float)tx.h;
+        if (tx.filt == 0) return texel(resolve_texel((int)floorf(fx), tx.w, tx.addr), resolve_texel((int)floorf(fy), tx.h, tx.addr));
+        const float bx = fx - 0.5f, by = fy - 0.5f;
+        const float ix = floorf(bx), iy = floorf(by);
+        const float al = floorf((bx - ix) * 256.0f + 0.5f) / 256.0f, be = floorf((by - iy) * 256.0f + 0.5f) / 256.0f;
+        const int x0 = resolve_texel((int)ix, tx.w, tx.addr), x1 = resolve_texel((int)ix + 1, tx.w, tx.addr);
+        const int y0 = resolve_texel((int)iy, tx.h, tx.addr), y1 = resolve_texel((int)iy + 1, tx.h, tx.addr);
+        const f3 t00 = texel(x0, y0), t10 = texel(x1, y0), t01 = texel(x0, y1), t11 = texel(x1, y1);
+        const float w00 = (1.0f - al) * (1.0f - be), w10 = al * (1.0f - be), w01 = (1.0f - al) * be, w11 = al * be;
+        return {((w00 * t00.x + w10 * t10.x) + w01 * t01.x) + w11 * t11.x, ((w00 * t00.y + w10 * t10.y) + w01 * t01.y) + w11 * t11.y,
+                ((w00 * t00.z + w10 * t10.z) + w01 * t01.z) + w11 * t11.z};
     }
 
     // "LocalGeometry" of the new shade stage: object-space N/uv per closehit_radiance.cu:66-74,
@@ -778,8 +804,8 @@ int rt3o_curves_create(rt3o_scene* s, int degree, const float* cp, int ncp, cons
 int rt3o_texture_create(rt3o_scene* s, const uint8_t* rgba8, int w, int h, int address_mode, int filter_mode) {
     RT3O_TRY
     if (!s || !rgba8 || w <= 0 || h <= 0) { g_err = "texture_create: bad argument"; return -1; }
-    if (filter_mode != 0) { g_err = "texture_create: only filter_mode 0 (point, Q9) is supported"; return -5; }
-    if (address_mode != RT3_ADDRESS_WRAP && address_mode != RT3_ADDRESS_CLAMP) { g_err = "texture_create: address mode unsupported"; return -5; }
+    if (filter_mode != 0 && filter_mode != 1) { g_err = "texture_create: filter_mode must be 0 (point) or 1 (bilinear)"; return -5; }
+    if (address_mode < RT3_ADDRESS_WRAP || address_mode > RT3_ADDRESS_BORDER) { g_err = "texture_create: address mode unsupported"; return -5; }
     Texture t;
     t.w = w; t.h = h; t.addr = address_mode; t.filt = filter_mode;
     t.px.assign(rgba8, rgba8 + (size_t)4 * w * h);
@@ -951,6 +977,12 @@ void rt3o_kat_onb(const float n[3], const float w[3], float o[9]) {
     Onb b({n[0], n[1], n[2]});
     f3 p = b.inverse_transform({w[0], w[1], w[2]});
     o[0] = b.t.x; o[1] = b.t.y; o[2] = b.t.z; o[3] = b.b.x; o[4] = b.b.y; o[5] = b.b.z; o[6] = p.x; o[7] = p.y; o[8] = p.z;
+}
+int rt3o_kat_fetch_texture(rt3o_scene* s, int t, float u, float v, float out[3]) {
+    if (!s || t < 0 || (size_t)t >= s->tex.size()) return -1;
+    const f3 c = s->fetch_texture(t, u, v);
+    out[0] = c.x; out[1] = c.y; out[2] = c.z;
+    return 0;
 }
 void rt3o_kat_light_make(const float e[3], const float v0[3], const float v1[3], const float v2[3], void* out) {
     Light l = light_make({e[0], e[1], e[2]}, {v0[0], v0[1], v0[2]}, {v1[0], v1[1], v1[2]}, {v2[0], v2[1], v2[2]});

@@ -52,6 +52,7 @@ void rt3o_kat_make_color(const float c[3], uint8_t out[4]);
 void rt3o_kat_camera_uvw(const float eye[3], const float lookat[3], const float up[3], float fovy, float aspect, float out_uvw[9]);
 void rt3o_kat_sincos_2pi(float u, float out_sc[2]);
 void rt3o_kat_invert_affine(const float m[12], float out[12]);
+int rt3o_kat_fetch_texture(rt3o_scene*, int tex, float u, float v, float out_rgb[3]);  /* the shade stage's tex2D restatement */
 int rt3o_kat_hit_triangle(const float o[3], const float d[3], const float v[9], float tmin, float tmax, float out_tuv[3]);
 int rt3o_kat_hit_sphere(const float o[3], const float d[3], const float cr[4], float tmin, float tmax, float* t);
 int rt3o_kat_hit_curve(const float o[3], const float d[3], const float a[4], const float b[4], float tmin, float tmax, float out_tu[2]);

@@ -396,8 +396,8 @@ int rt3_curves_create(rt3_context_t c, int degree, const float* cp, int ncp, con
 int rt3_texture_create(rt3_context_t c, const uint8_t* rgba8, int w, int h, int address_mode, int filter_mode, int* tex_id) {
     RT3_API_BEGIN
     RT3_REQUIRE(c && rgba8 && tex_id && w > 0 && h > 0, RT3_ERR_INVALID, "texture_create: bad argument");
-    RT3_REQUIRE(filter_mode == 0, RT3_ERR_UNSUPPORTED, "texture_create: only filter_mode 0 (= point sampling in the reference, Q9) is supported");
-    RT3_REQUIRE(address_mode == RT3_ADDRESS_WRAP || address_mode == RT3_ADDRESS_CLAMP, RT3_ERR_UNSUPPORTED, "texture_create: address mode unsupported");
+    RT3_REQUIRE(filter_mode == 0 || filter_mode == 1, RT3_ERR_UNSUPPORTED, "texture_create: filter_mode must be 0 (point) or 1 (bilinear)");
+    RT3_REQUIRE(address_mode >= RT3_ADDRESS_WRAP && address_mode <= RT3_ADDRESS_BORDER, RT3_ERR_UNSUPPORTED, "texture_create: address mode unsupported");
     auto t = std::make_unique<TextureObj>();
     t->w = w; t->h = h; t->addr = address_mode; t->filt = filter_mode;
     t->px.alloc((size_t)w * h);

@@ -427,20 +427,48 @@ struct LocalGeometry {   // subset of cuda/LocalGeometry.h:40-58 that the Lamber
     float2 UV;
 };
 
-RT3_HD float3 fetch_texture(const TexDev& tx, float u, float v) {  // tex2D point/wrap/normalised RGBA8 (cuda_texture.h:52-74, Q9/Q10)
-    int x, y;
-    if (tx.addr == 0) {
-        const float fu = u - floorf(u), fv = v - floorf(v);
-        x = (int)(fu * (float)tx.w);
-        y = (int)(fv * (float)tx.h);
-    } else {
-        x = (int)(fminf(fmaxf(u, 0.0f), 1.0f) * (float)tx.w);
-        y = (int)(fminf(fmaxf(v, 0.0f), 1.0f) * (float)tx.h);
-    }
-    x = x > tx.w - 1 ? tx.w - 1 : x;
-    y = y > tx.h - 1 ? tx.h - 1 : y;
+// Texel index of an integer texel coordinate under an address mode (CUDA programming guide, texture fetching):
+// wrap = modulo, clamp = nearest edge texel, mirror = reflected every N texels, border = -1 (reads as 0).
+RT3_HD int resolve_texel(int i, int n, int mode) {
+    if (mode == 0) { int m = i % n; return m < 0 ? m + n : m; }
+    if (mode == 1) return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+    if (mode == 2) { int m = i % (2 * n); if (m < 0) m += 2 * n; return m < n ? m : 2 * n - 1 - m; }
+    return (i >= 0 && i < n) ? i : -1;
+}
+RT3_HD float3 load_texel(const TexDev& tx, int x, int y) {
+    if (x < 0 || y < 0) return v3(0.0f, 0.0f, 0.0f);  // border
     const uchar4 t = rt3_ldg(tx.px + (size_t)y * tx.w + x);
     return v3((float)t.x / 255.0f, (float)t.y / 255.0f, (float)t.z / 255.0f);
+}
+// tex2D on normalised coordinates, RGBA8 -> [0,1], no sRGB decode (cuda_texture.h:52-74, Q10).  filter 0 = point sampling
+// (what the reference's `FilterMode::Linear = 0` really selects, Q9); filter 1 = the hardware's bilinear filter (what
+// its `FilterMode::Point = 1` selects): texel centres at i + 0.5, weights rounded to 8 fractional bits.
+RT3_HD float3 fetch_texture(const TexDev& tx, float u, float v) {
+    if (tx.filt == 0 && tx.addr <= 1) {
+        int x, y;
+        if (tx.addr == 0) {
+            const float fu = u - floorf(u), fv = v - floorf(v);
+            x = (int)(fu * (float)tx.w);
+            y = (int)(fv * (float)tx.h);
+        } else {
+            x = (int)(fminf(fmaxf(u, 0.0f), 1.0f) * (float)tx.w);
+            y = (int)(fminf(fmaxf(v, 0.0f), 1.0f) * (float)tx.h);
+        }
+        x = x > tx.w - 1 ? tx.w - 1 : x;
+        y = y > tx.h - 1 ? tx.h - 1 : y;
+        return load_texel(tx, x, y);
+    }
+    const float fx = u * (float)tx.w, fy = v * (float)tx.h;
+    if (tx.filt == 0) return load_texel(tx, resolve_texel((int)floorf(fx), tx.w, tx.addr), resolve_texel((int)floorf(fy), tx.h, tx.addr));
+    const float bx = fx - 0.5f, by = fy - 0.5f;
+    const float ix = floorf(bx), iy = floorf(by);
+    const float al = floorf((bx - ix) * 256.0f + 0.5f) / 256.0f, be = floorf((by - iy) * 256.0f + 0.5f) / 256.0f;
+    const int x0 = resolve_texel((int)ix, tx.w, tx.addr), x1 = resolve_texel((int)ix + 1, tx.w, tx.addr);
+    const int y0 = resolve_texel((int)iy, tx.h, tx.addr), y1 = resolve_texel((int)iy + 1, tx.h, tx.addr);
+    const float3 t00 = load_texel(tx, x0, y0), t10 = load_texel(tx, x1, y0), t01 = load_texel(tx, x0, y1), t11 = load_texel(tx, x1, y1);
+    const float w00 = (1.0f - al) * (1.0f - be), w10 = al * (1.0f - be), w01 = (1.0f - al) * be, w11 = al * be;
+    return v3(((w00 * t00.x + w10 * t10.x) + w01 * t01.x) + w11 * t11.x, ((w00 * t00.y + w10 * t10.y) + w01 * t01.y) + w11 * t11.y,
+              ((w00 * t00.z + w10 * t10.z) + w01 * t01.z) + w11 * t11.z);
 }
 
 RT3_HD LocalGeometry local_geometry(const TravScene& sc, const HitRec& h, float3 o, float3 d, float time) {

@@ -39,7 +39,7 @@ def lib():
         for name in ("rt3o_scene_destroy", "rt3o_mesh_create", "rt3o_spheres_create", "rt3o_curves_create", "rt3o_texture_create",
                      "rt3o_accel_append_instance", "rt3o_accel_append_animated_instance", "rt3o_accel_build",
                      "rt3o_scene_set_hitgroup", "rt3o_scene_set_lights", "rt3o_trace", "rt3o_get_local_geometry", "rt3o_launch_subframe",
-                     "rt3o_download_accum", "rt3o_download_frame", "rt3o_get_stats", "rt3o_reset_stats"):
+                     "rt3o_download_accum", "rt3o_download_frame", "rt3o_get_stats", "rt3o_reset_stats", "rt3o_kat_fetch_texture"):
             getattr(L, name).argtypes = None
     return _lib
 
@@ -92,6 +92,11 @@ class OracleScene:
     def texture_create(self, rgba, address=0, filt=0):
         r = np.ascontiguousarray(rgba, dtype=np.uint8)
         return self._chk(self.L.rt3o_texture_create(self.s, bptr(r), C.c_int(r.shape[1]), C.c_int(r.shape[0]), C.c_int(address), C.c_int(filt)))
+
+    def fetch_texture(self, tex, u, v):
+        out = np.zeros(3, dtype=np.float32)
+        self._chk(self.L.rt3o_kat_fetch_texture(self.s, C.c_int(tex), C.c_float(u), C.c_float(v), fptr(out)))
+        return out
 
     def append_instance(self, blas, xform):
         x = _f32(xform)

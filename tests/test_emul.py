@@ -37,7 +37,9 @@ def test_api_errors(emul_lib):
         with pytest.raises(Rt3Error):
             e.mesh_create(np.zeros((3, 3)), np.array([[0, 1, 7]]), np.zeros((3, 3)), np.zeros((3, 2)))  # index out of range
         with pytest.raises(Rt3Error):
-            e.texture_create(np.zeros((4, 4, 4), np.uint8), 0, 1)  # only filter 0
+            e.texture_create(np.zeros((4, 4, 4), np.uint8), 0, 2)  # filter 0 (point) or 1 (bilinear)
+        with pytest.raises(Rt3Error):
+            e.texture_create(np.zeros((4, 4, 4), np.uint8), 4, 0)  # address modes 0..3
 
 
 @pytest.mark.parametrize("name", sorted(SMALL))
@@ -75,3 +77,14 @@ def test_stacked_layers_ties(emul_lib):
         o = build_pair(desc, e)
         ho = check_trace(e, o, adversarial.make_stacked_rays(n=1500), accel=0)
         assert (ho["prim"] >= 0).mean() > 0.5
+
+
+@pytest.mark.parametrize("address,filt", [(2, 0), (3, 0), (0, 1), (1, 1), (2, 1), (3, 1)])
+def test_texture_modes_match_oracle(emul_lib, address, filt):
+    """every CUDATexture address / filter mode: the textured terrain (uv in [0,8]: wraps, mirrors, runs into the border) renders bit-identically"""
+    desc = SMALL["terrain"]()
+    for t in desc.textures:
+        t.address, t.filter = address, filt
+    with Context(0, lib_path=emul_lib) as e:
+        o = build_pair(desc, e)
+        check_render(e, o, desc, subframes=1)

@@ -134,3 +134,14 @@ def test_corrected_mode_analytic_direct_lighting(product_lib):
         got = cc.render_mean(g, desc, subframes=32, mode=1, max_depth=2)   # 64*64 px * 256 spp
     want = cc.analytic_radiance()
     assert abs(got - want) / want < 0.02, (got, want)
+
+
+@pytest.mark.parametrize("address,filt", [(2, 0), (3, 0), (0, 1), (1, 1), (2, 1), (3, 1)])
+def test_texture_modes_match_oracle(product_lib, address, filt):
+    """CUDATexture's other address modes (mirror, border) and the hardware-bilinear filter (the reference's FilterMode::Point = 1)"""
+    desc = SMALL["terrain"]()
+    for t in desc.textures:
+        t.address, t.filter = address, filt
+    with Context(0) as g:
+        o = build_pair(desc, g)
+        check_render(g, o, desc, subframes=2)

@@ -333,3 +333,29 @@ def test_local_geometry_record_analytic():
         assert np.allclose(lg["dndu"][k], 0) and np.allclose(lg["dndv"][k], 0)
         assert np.allclose(lg["color"][k], 1)
     assert not lg[2].tobytes().strip(b"\0")                         # miss: all-zero record
+
+
+def test_texture_address_and_filter_modes():
+    """tex2D restatement: point / bilinear x wrap / clamp / mirror / border on a 4x2 texture with known texels"""
+    o = ob.OracleScene()
+    img = np.zeros((2, 4, 4), np.uint8)
+    img[0, :, 0] = [0, 51, 102, 153]                                 # row 0: red ramp 0, .2, .4, .6
+    img[1, :, 0] = [255, 204, 153, 102]                              # row 1: 1, .8, .6, .4
+    img[..., 3] = 255
+    ids = {(a, f): o.texture_create(img, a, f) for a in range(4) for f in range(2)}
+    r = lambda a, f, u, v: float(o.fetch_texture(ids[(a, f)], u, v)[0])
+    for a in range(4):                                               # inside the image every address mode agrees
+        assert abs(r(a, 0, 0.375, 0.25) - 0.2) < 1e-6                # point: texel (1, 0)
+        assert abs(r(a, 1, 0.375, 0.25) - 0.2) < 1e-6                # bilinear at a texel centre = that texel
+        assert abs(r(a, 1, 0.5, 0.25) - 0.3) < 1e-6                  # half way between texels 1 and 2 of row 0
+        assert abs(r(a, 1, 0.375, 0.5) - 0.5) < 1e-6                 # half way between rows: (0.2 + 0.8) / 2
+    # outside: u = 1.125 is texel centre 4 (one past the edge), u = -0.125 is texel centre -1
+    assert abs(r(0, 0, 1.125, 0.25) - 0.0) < 1e-6 and abs(r(0, 0, -0.125, 0.25) - 0.6) < 1e-6     # wrap
+    assert abs(r(1, 0, 1.125, 0.25) - 0.6) < 1e-6 and abs(r(1, 0, -0.125, 0.25) - 0.0) < 1e-6     # clamp
+    assert abs(r(2, 0, 1.125, 0.25) - 0.6) < 1e-6 and abs(r(2, 0, 1.375, 0.25) - 0.4) < 1e-6      # mirror: 4 -> 3, 5 -> 2
+    assert abs(r(2, 0, -0.125, 0.25) - 0.0) < 1e-6 and abs(r(2, 0, -0.375, 0.25) - 0.2) < 1e-6    # mirror: -1 -> 0, -2 -> 1
+    assert r(3, 0, 1.125, 0.25) == 0.0 and r(3, 0, -0.125, 0.25) == 0.0                           # border
+    assert abs(r(3, 1, 1.0, 0.25) - 0.3) < 1e-6                      # bilinear on the edge: half texel 3 (0.6), half border (0)
+    assert abs(r(0, 1, 1.0, 0.25) - 0.3) < 1e-6                      # wrap: half texel 3 (0.6), half texel 0 (0.0)
+    assert abs(r(1, 1, 1.0, 0.25) - 0.6) < 1e-6                      # clamp: both neighbours are texel 3
+    assert abs(r(0, 1, 0.375 + 1.0 / 1024, 0.25) - (0.2 + 0.2 / 256)) < 1e-6                      # weights have 8 fractional bits: 1/256 steps
