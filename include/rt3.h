@@ -106,6 +106,10 @@ int rt3_accel_build(rt3_context_t ctx);                   /* CUDAAccel::build sr
 /* ---- shading records / lights ----------------------------------------------------------- */
 /* one HitGroupRecord per instance: CUDAScene::create_sbt src/cuda/cuda_scene.h:54-88, HitGroupData src/shader/shader_data.h:125-136 */
 int rt3_scene_set_hitgroup(rt3_context_t ctx, int instance_id, const float emission[3], const float diffuse[3], int tex_id);
+/* texcoord transform of the SDK's sampleTexture (cuda/LocalShading.h:37-54): UV' = R(UV * scale) + offset with
+ * rotation = (sin, cos); optional, per instance; without it the texture is fetched at the interpolated UV as in
+ * the reference's closest-hit program (closehit_radiance.cu:105) */
+int rt3_scene_set_texture_transform(rt3_context_t ctx, int instance_id, const float scale[2], const float rotation[2], const float offset[2]);
 /* buildLightSampler src/wavefront.cpp:257-275: array of 68-byte rendertoy3o::Light (src/light.h:13-22) */
 int rt3_scene_set_lights(rt3_context_t ctx, const void* lights68, int n);
 /* Light ctor src/light.h:24-30 (host helper, pure arithmetic) */

@@ -213,6 +213,8 @@ struct Instance {
     float t0 = 0, t1 = 1;
     f3 emission{0, 0, 0}, diffuse{0.8f, 0.8f, 0.8f};
     int tex = -1;
+    bool has_xf = false;  // texcoord transform of the SDK's sampleTexture (cuda/LocalShading.h:37-54)
+    f2 tex_scale{1, 1}, tex_rot{0, 1}, tex_off{0, 0};
 };
 
 struct Texture { int w, h, addr, filt; std::vector<uint8_t> px; };
@@ -383,6 +385,15 @@ struct rt3o_scene {
         const float w00 = (1.0f - al) * (1.0f - be), w10 = al * (1.0f - be), w01 = (1.0f - al) * be, w11 = al * be;
         return {((w00 * t00.x + w10 * t10.x) + w01 * t01.x) + w11 * t11.x, ((w00 * t00.y + w10 * t10.y) + w01 * t01.y) + w11 * t11.y,
                 ((w00 * t00.z + w10 * t10.z) + w01 * t01.z) + w11 * t11.z};
+    }
+
+    // sampleTexture (cuda/LocalShading.h:37-54): the instance's texcoord transform, then tex2D
+    f3 sample_texture(const Instance& in, f2 uv) const {
+        if (!in.has_xf) return fetch_texture(in.tex, uv.x, uv.y);
+        const float sx = uv.x * in.tex_scale.x, sy = uv.y * in.tex_scale.y;
+        const float tu = (sx * in.tex_rot.y + sy * in.tex_rot.x) + in.tex_off.x;
+        const float tv = (sx * (-in.tex_rot.x) + sy * in.tex_rot.y) + in.tex_off.y;
+        return fetch_texture(in.tex, tu, tv);
     }
 
     // "LocalGeometry" of the new shade stage: object-space N/uv per closehit_radiance.cu:66-74,
@@ -572,7 +583,7 @@ struct rt3o_scene {
                     }
                     L = L + beta * in.emission * wgt;
                 }
-                const f3 albedo = in.tex >= 0 ? fetch_texture(in.tex, uv.x, uv.y) : in.diffuse;
+                const f3 albedo = in.tex >= 0 ? sample_texture(in, uv) : in.diffuse;
                 // next event estimation
                 float p_sel = 0.0f;
                 const float xi_l = rnd(seed);
@@ -679,7 +690,7 @@ struct rt3o_scene {
                     ndir = onb.inverse_transform(w_in);
                     norg = P;
                     const float bsdf = (float)(1.0 / 3.14159265358979323846);
-                    const f3 albedo = in.tex >= 0 ? fetch_texture(in.tex, uv.x, uv.y) : in.diffuse;
+                    const f3 albedo = in.tex >= 0 ? sample_texture(in, uv) : in.diffuse;
                     att = att * albedo;
                     att = att * (bsdf / pdf_prev);
                     // NEE
@@ -858,6 +869,13 @@ int rt3o_scene_set_hitgroup(rt3o_scene* s, int id, const float e[3], const float
     s->inst[id].tex = tex;
     return 0;
 }
+int rt3o_scene_set_texture_transform(rt3o_scene* s, int id, const float scale[2], const float rotation[2], const float offset[2]) {
+    if (!s || id < 0 || id >= (int)s->inst.size() || !scale || !rotation || !offset) { g_err = "set_texture_transform: bad argument"; return -1; }
+    Instance& in = s->inst[id];
+    in.tex_scale = {scale[0], scale[1]}; in.tex_rot = {rotation[0], rotation[1]}; in.tex_off = {offset[0], offset[1]};
+    in.has_xf = true;
+    return 0;
+}
 int rt3o_scene_set_lights(rt3o_scene* s, const void* lights68, int n) {
     if (!s || !lights68 || n <= 0) { g_err = "set_lights: need at least one light (Q17)"; return -1; }
     s->lights.resize(n);
@@ -981,6 +999,12 @@ void rt3o_kat_onb(const float n[3], const float w[3], float o[9]) {
 int rt3o_kat_fetch_texture(rt3o_scene* s, int t, float u, float v, float out[3]) {
     if (!s || t < 0 || (size_t)t >= s->tex.size()) return -1;
     const f3 c = s->fetch_texture(t, u, v);
+    out[0] = c.x; out[1] = c.y; out[2] = c.z;
+    return 0;
+}
+int rt3o_kat_sample_texture(rt3o_scene* s, int id, float u, float v, float out[3]) {
+    if (!s || id < 0 || (size_t)id >= s->inst.size() || s->inst[id].tex < 0) return -1;
+    const f3 c = s->sample_texture(s->inst[id], {u, v});
     out[0] = c.x; out[1] = c.y; out[2] = c.z;
     return 0;
 }

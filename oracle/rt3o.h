@@ -27,6 +27,7 @@ int rt3o_accel_append_animated_instance(rt3o_scene*, int blas, const float* keys
                                         float t_end, const float static_xform[12]);
 int rt3o_accel_build(rt3o_scene*);
 int rt3o_scene_set_hitgroup(rt3o_scene*, int instance_id, const float emission[3], const float diffuse[3], int tex_id);
+int rt3o_scene_set_texture_transform(rt3o_scene*, int instance_id, const float scale[2], const float rotation[2], const float offset[2]);  /* cuda/LocalShading.h:37-54 */
 int rt3o_scene_set_lights(rt3o_scene*, const void* lights68, int n);
 /* accel: 0 = brute force over every instance x primitive, 1 = BVH2 (validated against 0) */
 int rt3o_trace(rt3o_scene*, const rt3_ray* rays, int n, int any_hit, rt3_hit* hits, int accel, int nthreads);
@@ -52,7 +53,8 @@ void rt3o_kat_make_color(const float c[3], uint8_t out[4]);
 void rt3o_kat_camera_uvw(const float eye[3], const float lookat[3], const float up[3], float fovy, float aspect, float out_uvw[9]);
 void rt3o_kat_sincos_2pi(float u, float out_sc[2]);
 void rt3o_kat_invert_affine(const float m[12], float out[12]);
-int rt3o_kat_fetch_texture(rt3o_scene*, int tex, float u, float v, float out_rgb[3]);  /* the shade stage's tex2D restatement */
+int rt3o_kat_fetch_texture(rt3o_scene*, int tex, float u, float v, float out_rgb[3]);
+int rt3o_kat_sample_texture(rt3o_scene*, int instance_id, float u, float v, float out_rgb[3]);  /* with the instance's texcoord transform */  /* the shade stage's tex2D restatement */
 int rt3o_kat_hit_triangle(const float o[3], const float d[3], const float v[9], float tmin, float tmax, float out_tuv[3]);
 int rt3o_kat_hit_sphere(const float o[3], const float d[3], const float cr[4], float tmin, float tmax, float* t);
 int rt3o_kat_hit_curve(const float o[3], const float d[3], const float a[4], const float b[4], float tmin, float tmax, float out_tu[2]);

@@ -28,7 +28,7 @@ RT3_SYMBOLS = [
     "rt3_context_create", "rt3_context_destroy", "rt3_sync", "rt3_last_error", "rt3_get_stream", "rt3_get_stats", "rt3_reset_stats", "rt3_get_debug_counters",
     "rt3_set_option", "rt3_mesh_create", "rt3_spheres_create", "rt3_curves_create", "rt3_texture_create",
     "rt3_accel_append_instance", "rt3_accel_append_animated_instance", "rt3_accel_build", "rt3_scene_set_hitgroup",
-    "rt3_scene_set_lights", "rt3_light_make", "rt3_camera_uvw", "rt3_launch_subframe", "rt3_trace", "rt3_trace_device", "rt3_get_local_geometry",
+    "rt3_scene_set_lights", "rt3_light_make", "rt3_camera_uvw", "rt3_launch_subframe", "rt3_trace", "rt3_trace_device", "rt3_get_local_geometry", "rt3_scene_set_texture_transform",
     "rt3_download_accum", "rt3_download_frame", "rt3_accum_device_ptr", "rt3_clear_accum", "rt3_finalize_accum",
     "rt3_allreduce_accum",
 ]
@@ -193,6 +193,11 @@ class Context:
         self._chk(self.L.rt3_trace(self.ctx, rays.ctypes.data_as(C.c_void_p), C.c_int(len(rays)), C.c_int(1 if any_hit else 0),
                                    hits.ctypes.data_as(C.c_void_p)))
         return hits
+
+    def set_texture_transform(self, iid, scale, rotation, offset):
+        """texcoord transform of the SDK's sampleTexture (cuda/LocalShading.h:37-54); rotation = (sin, cos)"""
+        s, r, o = (np.ascontiguousarray(x, dtype=np.float32) for x in (scale, rotation, offset))
+        self._chk(self.L.rt3_scene_set_texture_transform(self.ctx, C.c_int(iid), fptr(s), fptr(r), fptr(o)))
 
     def get_local_geometry(self, rays, hits):
         """getLocalGeometry (cuda/LocalGeometry.h:61-175) for rays and the hit records trace() returned for them"""

@@ -160,7 +160,7 @@ void upload_hitgroups(rt3_context* c) {
     if (!c->hitgroups_dirty || c->inst.empty()) return;
     std::vector<HitGroupDev> hg(c->inst.size() + 1);  // + the merged pseudo-instance (never shaded)
     for (size_t i = 0; i < c->inst.size(); i++) hg[i] = c->inst[i].hg;
-    hg[c->inst.size()] = HitGroupDev{{0, 0, 0}, {0, 0, 0}, -1, 1.0f};
+    hg[c->inst.size()] = HitGroupDev{{0, 0, 0}, {0, 0, 0}, -1, 1.0f, {1, 1}, {0, 1}, {0, 0}, 0u, 0u};
     c->d_hg.ensure(hg.size());
     h2d(c->d_hg.p, hg.data(), sizeof(HitGroupDev) * hg.size(), c->stream);
     stream_sync(c->stream);
@@ -426,7 +426,7 @@ static int append_instance_impl(rt3_context_t c, rt3_handle_t blas, const float*
         in.keys.assign(keys, keys + 12 * (size_t)nkeys);
         in.t0 = t0; in.t1 = t1;
     }
-    in.hg = HitGroupDev{{0, 0, 0}, {0.8f, 0.8f, 0.8f}, -1, in.t1};
+    in.hg = HitGroupDev{{0, 0, 0}, {0.8f, 0.8f, 0.8f}, -1, in.t1, {1, 1}, {0, 1}, {0, 0}, 0u, 0u};
     c->inst.push_back(std::move(in));
     c->built = false;
     c->hitgroups_dirty = true;
@@ -589,6 +589,18 @@ int rt3_scene_set_hitgroup(rt3_context_t c, int id, const float e[3], const floa
     HitGroupDev& hg = c->inst[id].hg;
     for (int k = 0; k < 3; k++) { hg.emission[k] = e[k]; hg.diffuse[k] = d[k]; }
     hg.tex = tex;
+    c->hitgroups_dirty = true;
+    RT3_API_END
+}
+
+// MaterialData::Texture::texcoord_scale / _rotation (sin, cos) / _offset of the SDK's sampleTexture (cuda/LocalShading.h:37-54)
+int rt3_scene_set_texture_transform(rt3_context_t c, int id, const float scale[2], const float rotation[2], const float offset[2]) {
+    RT3_API_BEGIN
+    RT3_REQUIRE(c && scale && rotation && offset, RT3_ERR_INVALID, "set_texture_transform: null argument");
+    RT3_REQUIRE(id >= 0 && id < (int)c->inst.size(), RT3_ERR_INVALID, "set_texture_transform: instance id out of range");
+    HitGroupDev& hg = c->inst[id].hg;
+    for (int k = 0; k < 2; k++) { hg.tex_scale[k] = scale[k]; hg.tex_rot[k] = rotation[k]; hg.tex_off[k] = offset[k]; }
+    hg.has_xf = 1u;
     c->hitgroups_dirty = true;
     RT3_API_END
 }

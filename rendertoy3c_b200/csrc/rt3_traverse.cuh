@@ -78,7 +78,12 @@ struct HitGroupDev {         // shading record (reference HitGroupData + motion 
     float diffuse[3];
     int32_t tex;
     float t1;
+    // MaterialData::Texture of the SDK's sampleTexture (cuda/LocalShading.h:37-54): UV * scale, rotated by (sin, cos), + offset;
+    // has_xf = 0 (the default, and all the reference's src/ path ever does) fetches at the plain UV
+    float tex_scale[2], tex_rot[2], tex_off[2];
+    uint32_t has_xf, pad_;
 };
+static_assert(sizeof(HitGroupDev) == 64, "shading record is 64 bytes");
 
 struct TravScene {
     const Node8* tlas_nodes;

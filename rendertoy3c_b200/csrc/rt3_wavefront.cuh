@@ -471,6 +471,15 @@ RT3_HD float3 fetch_texture(const TexDev& tx, float u, float v) {
               ((w00 * t00.z + w10 * t10.z) + w01 * t01.z) + w11 * t11.z);
 }
 
+// sampleTexture (cuda/LocalShading.h:37-54): the hit group's texcoord transform, then tex2D
+RT3_HD float3 sample_texture(const TexDev& tx, const HitGroupDev& hg, float2 uv) {
+    if (hg.has_xf == 0u) return fetch_texture(tx, uv.x, uv.y);
+    const float sx = uv.x * hg.tex_scale[0], sy = uv.y * hg.tex_scale[1];
+    const float tu = (sx * hg.tex_rot[1] + sy * hg.tex_rot[0]) + hg.tex_off[0];       // dot(UV, (rot.y,  rot.x)) + offset.x
+    const float tv = (sx * (-hg.tex_rot[0]) + sy * hg.tex_rot[1]) + hg.tex_off[1];    // dot(UV, (-rot.x, rot.y)) + offset.y
+    return fetch_texture(tx, tu, tv);
+}
+
 RT3_HD LocalGeometry local_geometry(const TravScene& sc, const HitRec& h, float3 o, float3 d, float time) {
     LocalGeometry lg;
     const InstanceDev* in = sc.instances + h.inst;
@@ -669,7 +678,7 @@ RT3_HD void shade_slot(const FrameParams& f, const TravScene& sc, const Queues& 
             const float pdf_prev = (float)((double)w_in.z / 3.14159265358979323846);
             ndir = onb_inverse_transform(Ns, w_in);
             const float bsdf = (float)(1.0 / 3.14159265358979323846);
-            const float3 albedo = hg.tex >= 0 ? fetch_texture(f.tex[hg.tex], lg.UV.x, lg.UV.y) : ld3(hg.diffuse);
+            const float3 albedo = hg.tex >= 0 ? sample_texture(f.tex[hg.tex], hg, lg.UV) : ld3(hg.diffuse);
             att = mul(att, albedo);
             att = mul(att, bsdf / pdf_prev);
             // next event estimation: uniform light pick (closehit_radiance.cu:10-15,117-156)
@@ -786,7 +795,7 @@ RT3_HD void shade_slot_corrected(const FrameParams& f, const TravScene& sc, cons
                 r.x = r.x + c.x; r.y = r.y + c.y; r.z = r.z + c.z;
                 q.result[path] = r;
             }
-            const float3 albedo = hg.tex >= 0 ? fetch_texture(f.tex[hg.tex], lg.UV.x, lg.UV.y) : ld3(hg.diffuse);
+            const float3 albedo = hg.tex >= 0 ? sample_texture(f.tex[hg.tex], hg, lg.UV) : ld3(hg.diffuse);
             // next event estimation
             const float xi_l = rnd(seed);
             float p_sel = 0.0f;

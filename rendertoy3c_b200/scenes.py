@@ -41,6 +41,7 @@ class Instance:
     emission: tuple = (0.0, 0.0, 0.0)
     diffuse: tuple = (0.8, 0.8, 0.8)
     tex: int = -1
+    tex_xform: tuple = None        # optional (scale[2], rotation (sin, cos), offset[2]) of the SDK's sampleTexture (cuda/LocalShading.h:37-54)
 
 
 @dataclass
@@ -93,6 +94,8 @@ def replay(desc, be):
         else:
             iid = be.append_instance(handles[inst.geom], inst.xform)
         be.set_hitgroup(iid, inst.emission, inst.diffuse, tex_ids[inst.tex] if inst.tex >= 0 else -1)
+        if inst.tex_xform is not None:
+            be.set_texture_transform(iid, *inst.tex_xform)
         g = desc.geoms[inst.geom]
         e = np.asarray(inst.emission, dtype=np.float32)
         if g.kind == "mesh" and float(np.sqrt(np.float32(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]))) >= 1e-5:

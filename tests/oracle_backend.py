@@ -38,8 +38,8 @@ def lib():
         L.rt3o_kat_tea4.argtypes = [C.c_uint32, C.c_uint32]
         for name in ("rt3o_scene_destroy", "rt3o_mesh_create", "rt3o_spheres_create", "rt3o_curves_create", "rt3o_texture_create",
                      "rt3o_accel_append_instance", "rt3o_accel_append_animated_instance", "rt3o_accel_build",
-                     "rt3o_scene_set_hitgroup", "rt3o_scene_set_lights", "rt3o_trace", "rt3o_get_local_geometry", "rt3o_launch_subframe",
-                     "rt3o_download_accum", "rt3o_download_frame", "rt3o_get_stats", "rt3o_reset_stats", "rt3o_kat_fetch_texture"):
+                     "rt3o_scene_set_hitgroup", "rt3o_scene_set_texture_transform", "rt3o_scene_set_lights", "rt3o_trace", "rt3o_get_local_geometry", "rt3o_launch_subframe",
+                     "rt3o_download_accum", "rt3o_download_frame", "rt3o_get_stats", "rt3o_reset_stats", "rt3o_kat_fetch_texture", "rt3o_kat_sample_texture"):
             getattr(L, name).argtypes = None
     return _lib
 
@@ -98,6 +98,11 @@ class OracleScene:
         self._chk(self.L.rt3o_kat_fetch_texture(self.s, C.c_int(tex), C.c_float(u), C.c_float(v), fptr(out)))
         return out
 
+    def sample_texture(self, iid, u, v):
+        out = np.zeros(3, dtype=np.float32)
+        self._chk(self.L.rt3o_kat_sample_texture(self.s, C.c_int(iid), C.c_float(u), C.c_float(v), fptr(out)))
+        return out
+
     def append_instance(self, blas, xform):
         x = _f32(xform)
         return self._chk(self.L.rt3o_accel_append_instance(self.s, C.c_int(blas), fptr(x)))
@@ -112,6 +117,10 @@ class OracleScene:
     def set_hitgroup(self, iid, emission, diffuse, tex):
         e, d = _f32(emission), _f32(diffuse)
         self._chk(self.L.rt3o_scene_set_hitgroup(self.s, C.c_int(iid), fptr(e), fptr(d), C.c_int(tex)))
+
+    def set_texture_transform(self, iid, scale, rotation, offset):
+        s, r, o = _f32(scale), _f32(rotation), _f32(offset)
+        self._chk(self.L.rt3o_scene_set_texture_transform(self.s, C.c_int(iid), fptr(s), fptr(r), fptr(o)))
 
     def light_make(self, e, v0, v1, v2):
         buf = C.create_string_buffer(LIGHT_BYTES)

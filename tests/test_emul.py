@@ -88,3 +88,14 @@ def test_texture_modes_match_oracle(emul_lib, address, filt):
     with Context(0, lib_path=emul_lib) as e:
         o = build_pair(desc, e)
         check_render(e, o, desc, subframes=1)
+
+
+def test_texcoord_transform_matches_oracle(emul_lib):
+    """sampleTexture's scale / rotation / offset (cuda/LocalShading.h:37-54) on the textured terrain"""
+    desc = SMALL["terrain"]()
+    for inst in desc.instances:
+        if inst.tex >= 0:
+            inst.tex_xform = ((1.5, 0.75), (float(np.sin(0.6)), float(np.cos(0.6))), (0.125, -0.3))
+    with Context(0, lib_path=emul_lib) as e:
+        o = build_pair(desc, e)
+        check_render(e, o, desc, subframes=1)

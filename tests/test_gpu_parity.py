@@ -145,3 +145,14 @@ def test_texture_modes_match_oracle(product_lib, address, filt):
     with Context(0) as g:
         o = build_pair(desc, g)
         check_render(g, o, desc, subframes=2)
+
+
+def test_texcoord_transform_matches_oracle(product_lib):
+    """sampleTexture's scale / rotation / offset (cuda/LocalShading.h:37-54) on the textured terrain"""
+    desc = SMALL["terrain"]()
+    for inst in desc.instances:
+        if inst.tex >= 0:
+            inst.tex_xform = ((1.5, 0.75), (float(np.sin(0.6)), float(np.cos(0.6))), (0.125, -0.3))
+    with Context(0) as g:
+        o = build_pair(desc, g)
+        check_render(g, o, desc, subframes=1)

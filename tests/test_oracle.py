@@ -359,3 +359,24 @@ def test_texture_address_and_filter_modes():
     assert abs(r(0, 1, 1.0, 0.25) - 0.3) < 1e-6                      # wrap: half texel 3 (0.6), half texel 0 (0.0)
     assert abs(r(1, 1, 1.0, 0.25) - 0.6) < 1e-6                      # clamp: both neighbours are texel 3
     assert abs(r(0, 1, 0.375 + 1.0 / 1024, 0.25) - (0.2 + 0.2 / 256)) < 1e-6                      # weights have 8 fractional bits: 1/256 steps
+
+
+def test_sample_texture_texcoord_transform():
+    """cuda/LocalShading.h:37-54: UV' = (dot(UV*scale, (cos, sin)), dot(UV*scale, (-sin, cos))) + offset, then tex2D"""
+    from rendertoy3c_b200.scenes import IDENTITY
+    o = ob.OracleScene()
+    img = np.zeros((4, 4, 4), np.uint8)
+    img[..., 0] = np.arange(16).reshape(4, 4) * 16                  # red = 16 * (4 * row + column)
+    t = o.texture_create(img, 0, 0)
+    m = o.mesh_create(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.int32),
+                      np.array([[0, 0, 1]] * 3, np.float32), np.array([[0, 0], [1, 0], [0, 1]], np.float32))
+    plain, moved = o.append_instance(m, IDENTITY), o.append_instance(m, IDENTITY)
+    for i in (plain, moved):
+        o.set_hitgroup(i, (0, 0, 0), (1, 1, 1), t)
+    o.set_texture_transform(moved, (2.0, 0.5), (1.0, 0.0), (0.25, 0.75))   # 90 degrees: (u, v) -> (v', -u') with u' = 2u, v' = v/2
+    texel = lambda u, v: float(o.fetch_texture(t, u, v)[0])
+    assert float(o.sample_texture(plain, 0.3, 0.6)[0]) == texel(0.3, 0.6)
+    for u, v in ((0.1, 0.2), (0.3, 0.6), (0.45, 0.9)):
+        su, sv = np.float32(u) * np.float32(2.0), np.float32(v) * np.float32(0.5)
+        want = texel(float(sv) + 0.25, float(-su) + 0.75)
+        assert float(o.sample_texture(moved, u, v)[0]) == want
