@@ -87,8 +87,10 @@ int rt3_mesh_create(rt3_context_t ctx, const float* verts, int num_keys, int nv,
                     const float* normals, const float* uvs, rt3_handle_t* blas);
 /* analytic spheres, center_radius [n][4] (cuda/GeometryData.h:83-87, test per cuda/sphere.cu:37-97) */
 int rt3_spheres_create(rt3_context_t ctx, const float* center_radius, int n, rt3_handle_t* blas);
-/* round curves; degree 1 (linear segments) in round 1.  cp_radius [ncp][4], segment i uses
- * control points seg_first_cp[i], seg_first_cp[i]+1 (cuda/curve.h:38-80, cuda/GeometryData.h:127-133) */
+/* round curves.  cp_radius [ncp][4]; segment i uses control points seg_first_cp[i] .. seg_first_cp[i] + degree.
+ * degree 1: linear segments (cuda/curve.h:38-80, cuda/GeometryData.h:127-133).  degree 2 / 3: uniform quadratic / cubic
+ * B-spline segments, evaluated with the SDK's Quadratic / CubicInterpolator (cuda/curve.h:98-230) and realised as 8
+ * round linear sub-segments each; hits report the segment and u in [0,1] along it. */
 int rt3_curves_create(rt3_context_t ctx, int degree, const float* cp_radius, int ncp, const int32_t* seg_first_cp,
                       int nseg, rt3_handle_t* blas);
 /* CUDATexture<uchar4>(w,h,data,address,filter) src/cuda/cuda_texture.h:46-75 */

@@ -175,6 +175,7 @@ struct Blas {
     int type = PRIM_TRI;
     std::vector<f3> verts, normals;    // verts: [vkeys][nv] (vertex-key motion, cuda_mesh.h:85-88: keys spread over time [0,1])
     int vkeys = 1, nv = 0;
+    int subdiv = 1;                    // curves of degree 2 / 3: linear sub-segments per user segment (hits translated at the API boundary)
     std::vector<f2> uvs;
     std::vector<int32_t> idx;          // tris: 3 per prim
     std::vector<float> cr;             // spheres: 4 per prim; curves: control points 4 per cp
@@ -798,14 +799,68 @@ int rt3o_spheres_create(rt3o_scene* s, const float* cr, int n) {
     return finish_blas(s, std::move(b));
     RT3O_CATCH(-1)
 }
+// Degree-2 / -3 round curves: each segment (uniform B-spline over control points [a, a + degree], the SDK's
+// Quadratic / CubicInterpolator::initializeFromBSpline + position4, cuda/curve.h:98-140,172-230) is realised as
+// RT3_CURVE_SUBDIV round linear sub-segments between the points P(k / RT3_CURVE_SUBDIV).  Inside the library the
+// sub-segments are ordinary linear-curve primitives; hit records are translated at the API boundary:
+// prim = sub / SUBDIV, u = (sub % SUBDIV + u_sub) / SUBDIV.
+#ifndef RT3_CURVE_SUBDIV
+#define RT3_CURVE_SUBDIV 8
+#endif
+static void tessellate_bspline(int degree, const float* cp, const int32_t* seg, int nseg, std::vector<float>& out_cp, std::vector<int32_t>& out_seg) {
+    const int K = RT3_CURVE_SUBDIV;
+    out_cp.resize((size_t)4 * nseg * (K + 1));
+    out_seg.resize((size_t)nseg * K);
+    for (int s = 0; s < nseg; s++) {
+        const float* q = cp + 4 * (size_t)seg[s];
+        for (int k = 0; k <= K; k++) {
+            const float u = (float)k / (float)K;
+            float* o = &out_cp[4 * ((size_t)s * (K + 1) + (size_t)k)];
+            for (int c = 0; c < 4; c++) {
+                const float q0 = q[c], q1 = q[4 + c], q2 = q[8 + c];
+                if (degree == 2) {
+                    const float p0 = ((q0 - 2.0f * q1) + q2) / 2.0f, p1 = (-2.0f * q0 + 2.0f * q1) / 2.0f, p2 = (q0 + q1) / 2.0f;
+                    o[c] = (p0 * u + p1) * u + p2;
+                } else {
+                    const float q3 = q[12 + c];
+                    const float p0 = (((q0 * -1.0f + q1 * 3.0f) + q2 * -3.0f) + q3) / 6.0f, p1 = ((q0 * 3.0f + q1 * -6.0f) + q2 * 3.0f) / 6.0f,
+                                p2 = (q0 * -3.0f + q2 * 3.0f) / 6.0f, p3 = ((q0 * 1.0f + q1 * 4.0f) + q2 * 1.0f) / 6.0f;
+                    o[c] = ((p0 * u + p1) * u + p2) * u + p3;
+                }
+            }
+            if (k < K) out_seg[(size_t)s * K + (size_t)k] = s * (K + 1) + k;
+        }
+    }
+}
+static inline void curve_hit_to_internal(int K, int32_t& prim, float& u) {
+    const float f = u * (float)K;
+    int k = (int)f;
+    k = k > K - 1 ? K - 1 : (k < 0 ? 0 : k);
+    u = f - (float)k;
+    prim = prim * K + k;
+}
+
+static inline void curve_hit_to_user(int K, int32_t& prim, float& u) {
+    const int k = prim % K;
+    prim = prim / K;
+    u = ((float)k + u) / (float)K;
+}
+
 int rt3o_curves_create(rt3o_scene* s, int degree, const float* cp, int ncp, const int32_t* seg, int nseg) {
     RT3O_TRY
     if (!s || !cp || !seg || ncp < 2 || nseg <= 0) { g_err = "curves_create: bad argument"; return -1; }
-    if (degree != 1) { g_err = "curves_create: only degree 1 (linear) is supported"; return -5; }
+    if (degree < 1 || degree > 3) { g_err = "curves_create: degree must be 1, 2 or 3"; return -5; }
     for (int i = 0; i < nseg; i++)
-        if (seg[i] < 0 || seg[i] + 1 >= ncp) { g_err = "curves_create: segment out of range"; return -1; }
+        if (seg[i] < 0 || seg[i] + degree >= ncp) { g_err = "curves_create: segment out of range"; return -1; }
     auto b = std::make_unique<Blas>();
     b->type = PRIM_CURVE;
+    std::vector<float> tcp;
+    std::vector<int32_t> tseg;
+    if (degree > 1) {
+        tessellate_bspline(degree, cp, seg, nseg, tcp, tseg);
+        cp = tcp.data(); ncp = (int)(tcp.size() / 4); seg = tseg.data(); nseg = (int)tseg.size();
+        b->subdiv = RT3_CURVE_SUBDIV;
+    }
     b->nprims = nseg;
     b->cr.assign(cp, cp + 4 * ncp);
     b->seg.assign(seg, seg + nseg);
@@ -899,6 +954,10 @@ int rt3o_trace(rt3o_scene* s, const rt3_ray* rays, int n, int any_hit, rt3_hit* 
         rt3_hit& o = hits[i];
         std::memset(&o, 0, sizeof(o));
         o.t = h.t; o.u = h.u; o.v = h.v; o.prim = h.prim; o.inst = h.inst;
+        if (h.prim >= 0) {
+            const int K = s->blas[s->inst[h.inst].blas]->subdiv;
+            if (K > 1) curve_hit_to_user(K, o.prim, o.u);
+        }
     });
     return 0;
     RT3O_CATCH(-1)
@@ -913,8 +972,11 @@ int rt3o_get_local_geometry(rt3o_scene* s, const rt3_ray* rays, const rt3_hit* h
         float* o = reinterpret_cast<float*>(out + i);
         if (hits[i].prim < 0) { for (int k = 0; k < 27; k++) o[k] = 0.0f; continue; }
         Hit h; h.t = hits[i].t; h.u = hits[i].u; h.v = hits[i].v; h.prim = hits[i].prim; h.inst = hits[i].inst;
+        const int K = s->blas[s->inst[h.inst].blas]->subdiv;
+        if (K > 1) curve_hit_to_internal(K, h.prim, h.u);
         const rt3_ray& r = rays[i];
         s->local_geometry_full(h, {r.o[0], r.o[1], r.o[2]}, {r.d[0], r.d[1], r.d[2]}, r.time, o);
+        if (K > 1) o[9] = hits[i].u;  // UV.x is the u along the user's segment, not along the sub-segment
     }
     return 0;
     RT3O_CATCH(-1)

@@ -26,6 +26,7 @@ namespace {
 
 struct Geometry {
     uint32_t type = PRIM_TRI, nprims = 0, vkeys = 1, nv = 0;
+    uint32_t subdiv = 1;  // curves of degree 2 / 3: linear sub-segments per user segment (hit records are translated at the API boundary)
     DevBuf<float> verts, normals, uvs;
     DevBuf<int32_t> idx, seg;
     DevBuf<float4> cr;
@@ -82,6 +83,7 @@ struct rt3_context {
     int opt_l2_persist = 0;  // measured: -5 % on C2 (the carve-out starves the streaming queue traffic), off by default
     Bvh8 m_bvh;
     bool has_merged = false, single_level = false;
+    bool has_subdiv_curves = false;  // some instance refers to a degree-2 / -3 curve geometry (set in rt3_accel_build)
     int opt_merge = 1;
     int opt_tlas_refine = 1;  // instance boxes from the BLAS root's grandchild boxes instead of its root box
     DevBuf<uint32_t> d_flags;  // [0] error flags, [1] max stack
@@ -376,13 +378,63 @@ int rt3_spheres_create(rt3_context_t c, const float* cr, int n, rt3_handle_t* bl
     RT3_API_END
 }
 
+
+// Degree-2 / -3 round curves: each segment (uniform B-spline over control points [a, a + degree], the SDK's
+// Quadratic / CubicInterpolator::initializeFromBSpline + position4, cuda/curve.h:98-140,172-230) is realised as
+// RT3_CURVE_SUBDIV round linear sub-segments between the points P(k / RT3_CURVE_SUBDIV).  Inside the library the
+// sub-segments are ordinary linear-curve primitives; hit records are translated at the API boundary:
+// prim = sub / SUBDIV, u = (sub % SUBDIV + u_sub) / SUBDIV.
+#ifndef RT3_CURVE_SUBDIV
+#define RT3_CURVE_SUBDIV 8
+#endif
+static void tessellate_bspline(int degree, const float* cp, const int32_t* seg, int nseg, std::vector<float>& out_cp, std::vector<int32_t>& out_seg) {
+    const int K = RT3_CURVE_SUBDIV;
+    out_cp.resize((size_t)4 * nseg * (K + 1));
+    out_seg.resize((size_t)nseg * K);
+    for (int s = 0; s < nseg; s++) {
+        const float* q = cp + 4 * (size_t)seg[s];
+        for (int k = 0; k <= K; k++) {
+            const float u = (float)k / (float)K;
+            float* o = &out_cp[4 * ((size_t)s * (K + 1) + (size_t)k)];
+            for (int c = 0; c < 4; c++) {
+                const float q0 = q[c], q1 = q[4 + c], q2 = q[8 + c];
+                if (degree == 2) {
+                    const float p0 = ((q0 - 2.0f * q1) + q2) / 2.0f, p1 = (-2.0f * q0 + 2.0f * q1) / 2.0f, p2 = (q0 + q1) / 2.0f;
+                    o[c] = (p0 * u + p1) * u + p2;
+                } else {
+                    const float q3 = q[12 + c];
+                    const float p0 = (((q0 * -1.0f + q1 * 3.0f) + q2 * -3.0f) + q3) / 6.0f, p1 = ((q0 * 3.0f + q1 * -6.0f) + q2 * 3.0f) / 6.0f,
+                                p2 = (q0 * -3.0f + q2 * 3.0f) / 6.0f, p3 = ((q0 * 1.0f + q1 * 4.0f) + q2 * 1.0f) / 6.0f;
+                    o[c] = ((p0 * u + p1) * u + p2) * u + p3;
+                }
+            }
+            if (k < K) out_seg[(size_t)s * K + (size_t)k] = s * (K + 1) + k;
+        }
+    }
+}
+static inline void curve_hit_to_internal(int K, int32_t& prim, float& u) {
+    const float f = u * (float)K;
+    int k = (int)f;
+    k = k > K - 1 ? K - 1 : (k < 0 ? 0 : k);
+    u = f - (float)k;
+    prim = prim * K + k;
+}
+
 int rt3_curves_create(rt3_context_t c, int degree, const float* cp, int ncp, const int32_t* seg, int nseg, rt3_handle_t* blas) {
     RT3_API_BEGIN
     RT3_REQUIRE(c && cp && seg && blas && ncp >= 2 && nseg > 0, RT3_ERR_INVALID, "curves_create: bad argument");
-    RT3_REQUIRE(degree == 1, RT3_ERR_UNSUPPORTED, "curves_create: only degree 1 (round linear segments) is supported");
-    for (int i = 0; i < nseg; i++) RT3_REQUIRE(seg[i] >= 0 && seg[i] + 1 < ncp, RT3_ERR_INVALID, "curves_create: segment out of range");
+    RT3_REQUIRE(degree >= 1 && degree <= 3, RT3_ERR_UNSUPPORTED, "curves_create: degree must be 1 (linear), 2 or 3 (uniform B-spline)");
+    for (int i = 0; i < nseg; i++) RT3_REQUIRE(seg[i] >= 0 && seg[i] + degree < ncp, RT3_ERR_INVALID, "curves_create: segment out of range");
     auto g = std::make_unique<Geometry>();
     g->type = PRIM_CURVE;
+    std::vector<float> tcp;
+    std::vector<int32_t> tseg;
+    if (degree > 1) {
+        RT3_REQUIRE((uint64_t)nseg * RT3_CURVE_SUBDIV < (1u << 27), RT3_ERR_INVALID, "curves_create: too many segments");
+        tessellate_bspline(degree, cp, seg, nseg, tcp, tseg);
+        cp = tcp.data(); ncp = (int)(tcp.size() / 4); seg = tseg.data(); nseg = (int)tseg.size();
+        g->subdiv = RT3_CURVE_SUBDIV;
+    }
     g->nprims = (uint32_t)nseg;
     g->cr.alloc(ncp);
     g->seg.alloc(nseg);
@@ -518,7 +570,7 @@ int rt3_accel_build(rt3_context_t c) {
     std::vector<BlasBounds> bb(ng + 1);
     for (size_t i = 0; i < ng; i++) {
         const Geometry& g = *c->geoms[i];
-        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p, g.vkeys, g.verts.p, g.nv};
+        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p, g.vkeys, g.verts.p, g.nv, g.subdiv};
         for (int k = 0; k < 3; k++) { bb[i].lo[k] = g.bvh.lo[k]; bb[i].hi[k] = g.bvh.hi[k]; }
     }
     bt[ng] = BlasDev{c->m_nodes_p, c->m_prims_p, PRIM_TRI, c->m_bvh.num_prims, nullptr, nullptr, nullptr, nullptr, nullptr, 1u, nullptr};
@@ -576,6 +628,8 @@ int rt3_accel_build(rt3_context_t c) {
     }
     c->hitgroups_dirty = true;
     upload_hitgroups(c);
+    c->has_subdiv_curves = false;
+    for (const InstanceHost& in : c->inst) c->has_subdiv_curves = c->has_subdiv_curves || c->geoms[in.blas]->subdiv > 1;
     c->built = true;
     RT3_API_END
 }
@@ -838,6 +892,8 @@ int rt3_trace_device(rt3_context_t c, const void* d_rays, int n, int any_hit, vo
     a.hit0 = (float4*)d_hits; a.hit_inst = nullptr; a.contrib = nullptr; a.result = nullptr; a.stat = nullptr; a.faithful = 0;
     if (any_hit) launch_traverse<TRAV_TRACE_ANY>(c, a, c->stream);
     else launch_traverse<TRAV_TRACE_CLOSEST>(c, a, c->stream);
+    // degree-2 / -3 curves: internal sub-segment hits -> (segment, u along the segment)
+    if (c->has_subdiv_curves) RT3_LAUNCH_1D(k_curve_hits_to_user, (uint32_t)n, c->stream, a.scene, (float4*)d_hits);
     RT3_API_END
 }
 
@@ -863,10 +919,22 @@ int rt3_get_local_geometry(rt3_context_t c, const rt3_ray* rays, const rt3_hit* 
     RT3_REQUIRE(c && c->built, RT3_ERR_STATE, "get_local_geometry: rt3_accel_build has not been called");
     RT3_REQUIRE(n >= 0 && (n == 0 || (rays && hits && out)), RT3_ERR_INVALID, "get_local_geometry: bad argument");
     for (int i = 0; i < n; i++)
-        RT3_REQUIRE(hits[i].prim < 0 || (hits[i].inst >= 0 && (size_t)hits[i].inst < c->inst.size() && (uint32_t)hits[i].prim < c->geoms[c->inst[(size_t)hits[i].inst].blas]->nprims),
+        RT3_REQUIRE(hits[i].prim < 0 || (hits[i].inst >= 0 && (size_t)hits[i].inst < c->inst.size() &&
+                                        (uint32_t)hits[i].prim < c->geoms[c->inst[(size_t)hits[i].inst].blas]->nprims / c->geoms[c->inst[(size_t)hits[i].inst].blas]->subdiv),
                     RT3_ERR_INVALID, "get_local_geometry: hit record does not belong to this scene");
     if (n == 0) return RT3_OK;
     upload_hitgroups(c);
+    std::vector<rt3_hit> internal;
+    const rt3_hit* user_hits = hits;
+    if (c->has_subdiv_curves) {  // (segment, u) of a degree-2 / -3 curve -> its linear sub-segment
+        internal.assign(hits, hits + n);
+        for (int i = 0; i < n; i++)
+            if (internal[(size_t)i].prim >= 0) {
+                const uint32_t K = c->geoms[c->inst[(size_t)internal[(size_t)i].inst].blas]->subdiv;
+                if (K > 1) curve_hit_to_internal((int)K, internal[(size_t)i].prim, internal[(size_t)i].u);
+            }
+        hits = internal.data();
+    }
     DevBuf<float4> d_rays(3 * (size_t)n), d_hits(2 * (size_t)n);
     DevBuf<float> d_out(27 * (size_t)n);
     h2d(d_rays.p, rays, sizeof(rt3_ray) * (size_t)n, c->stream);
@@ -874,6 +942,9 @@ int rt3_get_local_geometry(rt3_context_t c, const rt3_ray* rays, const rt3_hit* 
     RT3_LAUNCH_1D(k_local_geometry, (uint32_t)n, c->stream, c->trav_scene(), (const float4*)d_rays.p, (const float4*)d_hits.p, d_out.p);
     d2h(out, d_out.p, sizeof(rt3_local_geometry) * (size_t)n, c->stream);
     stream_sync(c->stream);
+    if (c->has_subdiv_curves)  // UV.x is the u along the user's segment, not along the sub-segment
+        for (int i = 0; i < n; i++)
+            if (user_hits[i].prim >= 0 && c->geoms[c->inst[(size_t)user_hits[i].inst].blas]->subdiv > 1) out[i].UV[0] = user_hits[i].u;
     RT3_API_END
 }
 

@@ -61,6 +61,7 @@ struct BlasDev {             // per geometry, device-resident table entry
     uint32_t vkeys;          // PRIM_TRI_MOTION: vertex keys per triangle record (record = vkeys x 3 float4)
     const float* verts;      // mesh [vkeys][nv][3] (corrected mode: area of BSDF-sampled emitter hits; rt3_get_local_geometry)
     uint32_t nv;             // vertices per key
+    uint32_t subdiv;         // curves of degree 2 / 3: linear sub-segments per user segment (1 otherwise)
 };
 
 struct InstanceDev {         // traversal record (64 B)

@@ -617,6 +617,23 @@ RT3_GLOBAL(k_local_geometry, TravScene sc, const float4* rays, const float4* hit
     r[23] = 1.0f; r[24] = 1.0f; r[25] = 1.0f; r[26] = 1.0f;
 }
 
+// rt3_trace output for degree-2 / -3 curves: the traversal reports linear sub-segments; the caller sees
+// prim = segment, u = (sub-segment + u_sub) / subdiv
+RT3_GLOBAL(k_curve_hits_to_user, TravScene sc, float4* hits) {
+    const uint32_t i = RT3_THREAD_ID();
+    if (i >= rt3_n_) return;
+    float4 h0 = hits[2 * (size_t)i];
+    const int prim = (int)rt3_f2u(h0.w);
+    if (prim < 0) return;
+    const int inst = (int)rt3_f2u(hits[2 * (size_t)i + 1].x);
+    const int K = (int)sc.blas[sc.instances[inst].blas].subdiv;
+    if (K <= 1) return;
+    const int k = prim % K;
+    h0.y = ((float)k + h0.y) / (float)K;
+    h0.w = rt3_u2f((uint32_t)(prim / K));
+    hits[2 * (size_t)i] = h0;
+}
+
 // one atomic per warp: ballot + popc prefix (device); sequential counter (emulation)
 RT3_HD uint32_t warp_append(uint32_t* counter, bool pred) {
 #ifdef RT3_EMULATE

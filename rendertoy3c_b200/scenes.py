@@ -24,6 +24,7 @@ class Geometry:
     uvs: np.ndarray = None        # mesh [nv,2]
     cr: np.ndarray = None         # spheres [n,4] / curves control points [ncp,4]
     seg: np.ndarray = None        # curves [nseg] i32 first control point
+    degree: int = 1               # curves: 1 linear, 2 / 3 uniform B-spline (segment i uses control points seg[i] .. seg[i] + degree)
     vert_keys: np.ndarray = None  # mesh, optional [keys,nv,3]: vertex-key (deformation) motion; verts = key 0
 
     @property
@@ -85,7 +86,7 @@ def replay(desc, be):
         elif g.kind == "spheres":
             handles.append(be.spheres_create(g.cr))
         else:
-            handles.append(be.curves_create(1, g.cr, g.seg))
+            handles.append(be.curves_create(g.degree, g.cr, g.seg))
     tex_ids = [be.texture_create(t.rgba, t.address, t.filter) for t in desc.textures]
     lights = []
     for inst in desc.instances:
@@ -364,6 +365,30 @@ def deforming(blob_n=24, width=160, height=90, spp=16, max_depth=6, keys=3):
     inst.append(Instance(3, diffuse=(0.6, 0.6, 0.6)))
     cam = Camera(eye=(0.7, 0.8, 3.6), lookat=(0.7, 0.1, 0.0), fovy=45.0)
     return SceneDesc("N2_deforming", geoms, inst, [], cam, width, height, spp, max_depth)
+
+
+def splines(n_strands=40, width=80, height=48, spp=16, max_depth=4, seed=11):
+    """degree-2 and degree-3 B-spline curve strands (random walks of control points, varying radius) over a lit floor"""
+    rng = np.random.RandomState(seed)
+    geoms, inst = [], []
+    for degree in (2, 3):
+        cps, segs = [], []
+        for _ in range(n_strands):
+            n = rng.randint(degree + 2, degree + 7)
+            p = np.cumsum(rng.randn(n, 3).astype(np.float32) * np.float32(0.35), axis=0) + (rng.rand(3).astype(np.float32) * 3 - 1.5) * np.array([1, 0.3, 1], np.float32)
+            p[:, 1] = np.abs(p[:, 1]) + 0.2
+            r = (0.03 + 0.05 * rng.rand(n)).astype(np.float32)
+            base = sum(len(c) for c in cps)
+            cps.append(np.concatenate([p, r[:, None]], axis=1))
+            segs.extend(range(base, base + n - degree))
+        geoms.append(Geometry("curves", cr=np.concatenate(cps).astype(np.float32), seg=np.array(segs, np.int32), degree=degree))
+        inst.append(Instance(len(geoms) - 1, diffuse=(0.7, 0.5, 0.3) if degree == 2 else (0.3, 0.6, 0.7)))
+    geoms.append(_quad_mesh([[[-3, 3.0, -3], [3, 3.0, -3], [3, 3.0, 3], [-3, 3.0, 3]]]))
+    inst.append(Instance(len(geoms) - 1, diffuse=(0.8, 0.8, 0.8), emission=(7.0, 7.0, 6.5)))
+    geoms.append(_quad_mesh([[[-5, 0, -5], [-5, 0, 5], [5, 0, 5], [5, 0, -5]]]))
+    inst.append(Instance(len(geoms) - 1, diffuse=(0.6, 0.6, 0.6)))
+    cam = Camera(eye=(0.0, 2.2, 5.0), lookat=(0.0, 0.6, 0.0), fovy=45.0)
+    return SceneDesc("splines", geoms, inst, [], cam, width, height, spp, max_depth)
 
 
 def by_name(name, **kw):

@@ -13,6 +13,7 @@ SMALL = {
     "instanced": lambda: scenes.instanced(n_inst=27, blob_n=10, n_spheres=16, width=80, height=48),
     "motion": lambda: scenes.motion(n_inst=8, blob_n=8, n_spheres=10, n_curves=50, width=80, height=48),
     "deforming": lambda: scenes.deforming(blob_n=10, width=80, height=48),
+    "splines": lambda: scenes.splines(),
 }
 
 

@@ -380,3 +380,32 @@ def test_sample_texture_texcoord_transform():
         su, sv = np.float32(u) * np.float32(2.0), np.float32(v) * np.float32(0.5)
         want = texel(float(sv) + 0.25, float(-su) + 0.75)
         assert float(o.sample_texture(moved, u, v)[0]) == want
+
+
+def test_bspline_curves_analytic():
+    """degree 2 / 3 curves (SDK Quadratic / CubicInterpolator from uniform B-spline control points, cuda/curve.h:98-230): with collinear,
+    equally spaced control points of one radius the segment is a straight tube between P(0) and P(1); hits report (segment, u)"""
+    from rendertoy3c_b200._abi import RAY_DTYPE
+    from rendertoy3c_b200.scenes import IDENTITY
+    o = ob.OracleScene()
+    cp = np.array([[x, 0, 0, 0.1] for x in range(6)], np.float32)
+    quad = o.curves_create(2, cp, np.array([0, 1, 2, 3], np.int32))      # segment s spans x in [s + 0.5, s + 1.5]
+    cubic = o.curves_create(3, cp, np.array([0, 1, 2], np.int32))         # segment s spans x in [s + 1, s + 2]
+    shift = IDENTITY.copy(); shift[7] = 10.0                                # the cubic strand 10 higher
+    iq, ic = o.append_instance(quad, IDENTITY), o.append_instance(cubic, shift)
+    for i in (iq, ic):
+        o.set_hitgroup(i, (0, 0, 0), (0.5, 0.5, 0.5), -1)
+    o.accel_build()
+    rays = np.zeros(4, RAY_DTYPE)
+    rays["o"] = [[1.0, 5.0, 0.0], [2.75, 5.0, 0.0], [1.25, 15.0, 0.0], [0.2, 5.0, 0.0]]
+    rays["d"] = [[0, -1, 0]] * 4
+    rays["tmax"] = 1e16
+    h = o.trace(rays, accel=0)
+    assert list(h["inst"]) == [iq, iq, ic, -1]                            # x = 0.2 is before the first quadratic segment starts (0.5 - r)
+    assert list(h["prim"][:3]) == [0, 2, 0]
+    assert np.allclose(h["t"][:3], 4.9, atol=1e-5)
+    assert np.allclose(h["u"][:3], [0.5, 0.25, 0.25], atol=1e-5)
+    assert o.trace(rays, accel=1).tobytes() == h.tobytes()
+    lg = o.get_local_geometry(rays, h)
+    assert np.allclose(lg["N"][:3], [0, 1, 0], atol=1e-5) and np.allclose(lg["UV"][:3, 0], [0.5, 0.25, 0.25], atol=1e-5)
+    assert np.allclose(lg["P"][:3, 1], [0.1, 0.1, 10.1], atol=1e-5)
