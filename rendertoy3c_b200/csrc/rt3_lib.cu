@@ -242,6 +242,14 @@ void ensure_film(rt3_context* c, uint32_t w, uint32_t h) {
 
 }  // namespace
 
+// several contexts (one per GPU) may live in one process: every entry point makes its context's device current
+static inline void use_device(rt3_context* c) {
+#ifndef RT3_EMULATE
+    if (c) cudaSetDevice(c->device);
+#else
+    (void)c;
+#endif
+}
 #define RT3_API_BEGIN try {
 #define RT3_API_END                                       \
     }                                                     \
@@ -309,6 +317,7 @@ void rt3_context_destroy(rt3_context_t c) {
 
 int rt3_sync(rt3_context_t c) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c, RT3_ERR_INVALID, "sync: null context");
     stream_sync(c->stream);
     RT3_API_END
@@ -316,6 +325,7 @@ int rt3_sync(rt3_context_t c) {
 
 int rt3_get_stream(rt3_context_t c, void** stream) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && stream, RT3_ERR_INVALID, "get_stream: null argument");
 #ifdef RT3_EMULATE
     *stream = nullptr;
@@ -327,6 +337,7 @@ int rt3_get_stream(rt3_context_t c, void** stream) {
 
 int rt3_set_option(rt3_context_t c, const char* key, int value) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && key, RT3_ERR_INVALID, "set_option: null argument");
     const std::string k(key);
     if (k == "timing") c->opt_timing = value;
@@ -344,6 +355,7 @@ int rt3_set_option(rt3_context_t c, const char* key, int value) {
 int rt3_mesh_create(rt3_context_t c, const float* verts, int num_keys, int nv, const int32_t* idx, int nt, const float* normals,
                     const float* uvs, rt3_handle_t* blas) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && verts && idx && normals && uvs && blas, RT3_ERR_INVALID, "mesh_create: null argument (normals and uvs are required, Q11)");
     RT3_REQUIRE(nv > 0 && nt > 0 && num_keys >= 1, RT3_ERR_INVALID, "mesh_create: empty mesh");
     for (size_t i = 0; i < 3 * (size_t)nt; i++) RT3_REQUIRE(idx[i] >= 0 && idx[i] < nv, RT3_ERR_INVALID, "mesh_create: index out of range");
@@ -367,6 +379,7 @@ int rt3_mesh_create(rt3_context_t c, const float* verts, int num_keys, int nv, c
 
 int rt3_spheres_create(rt3_context_t c, const float* cr, int n, rt3_handle_t* blas) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && cr && blas && n > 0, RT3_ERR_INVALID, "spheres_create: bad argument");
     auto g = std::make_unique<Geometry>();
     g->type = PRIM_SPHERE;
@@ -422,6 +435,7 @@ static inline void curve_hit_to_internal(int K, int32_t& prim, float& u) {
 
 int rt3_curves_create(rt3_context_t c, int degree, const float* cp, int ncp, const int32_t* seg, int nseg, rt3_handle_t* blas) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && cp && seg && blas && ncp >= 2 && nseg > 0, RT3_ERR_INVALID, "curves_create: bad argument");
     RT3_REQUIRE(degree >= 1 && degree <= 3, RT3_ERR_UNSUPPORTED, "curves_create: degree must be 1 (linear), 2 or 3 (uniform B-spline)");
     for (int i = 0; i < nseg; i++) RT3_REQUIRE(seg[i] >= 0 && seg[i] + degree < ncp, RT3_ERR_INVALID, "curves_create: segment out of range");
@@ -447,6 +461,7 @@ int rt3_curves_create(rt3_context_t c, int degree, const float* cp, int ncp, con
 
 int rt3_texture_create(rt3_context_t c, const uint8_t* rgba8, int w, int h, int address_mode, int filter_mode, int* tex_id) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && rgba8 && tex_id && w > 0 && h > 0, RT3_ERR_INVALID, "texture_create: bad argument");
     RT3_REQUIRE(filter_mode == 0 || filter_mode == 1, RT3_ERR_UNSUPPORTED, "texture_create: filter_mode must be 0 (point) or 1 (bilinear)");
     RT3_REQUIRE(address_mode >= RT3_ADDRESS_WRAP && address_mode <= RT3_ADDRESS_BORDER, RT3_ERR_UNSUPPORTED, "texture_create: address mode unsupported");
@@ -488,6 +503,7 @@ static int append_instance_impl(rt3_context_t c, rt3_handle_t blas, const float*
 
 int rt3_accel_append_instance(rt3_context_t c, rt3_handle_t blas, const float xform[12], int* instance_id) {
     RT3_API_BEGIN
+    use_device(c);
     append_instance_impl(c, blas, xform, nullptr, 0, 0.0f, 1.0f, instance_id);
     RT3_API_END
 }
@@ -495,6 +511,7 @@ int rt3_accel_append_instance(rt3_context_t c, rt3_handle_t blas, const float xf
 int rt3_accel_append_animated_instance(rt3_context_t c, rt3_handle_t blas, const float* keys, int nkeys, float t_begin, float t_end,
                                        const float static_xform[12], int* instance_id) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(keys, RT3_ERR_INVALID, "append_animated_instance: null keys");
     append_instance_impl(c, blas, static_xform, keys, nkeys, t_begin, t_end, instance_id);
     RT3_API_END
@@ -502,6 +519,7 @@ int rt3_accel_append_animated_instance(rt3_context_t c, rt3_handle_t blas, const
 
 int rt3_accel_build(rt3_context_t c) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c, RT3_ERR_INVALID, "accel_build: null context");
     RT3_REQUIRE(!c->inst.empty(), RT3_ERR_STATE, "accel_build: no instances");
     const uint32_t ni = (uint32_t)c->inst.size();
@@ -637,6 +655,7 @@ int rt3_accel_build(rt3_context_t c) {
 // ------------------------------------------------------------------------------------ shading records
 int rt3_scene_set_hitgroup(rt3_context_t c, int id, const float e[3], const float d[3], int tex) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && e && d, RT3_ERR_INVALID, "set_hitgroup: null argument");
     RT3_REQUIRE(id >= 0 && id < (int)c->inst.size(), RT3_ERR_INVALID, "set_hitgroup: instance id out of range");
     RT3_REQUIRE(tex >= -1 && tex < (int)c->textures.size(), RT3_ERR_INVALID, "set_hitgroup: texture id out of range");
@@ -650,6 +669,7 @@ int rt3_scene_set_hitgroup(rt3_context_t c, int id, const float e[3], const floa
 // MaterialData::Texture::texcoord_scale / _rotation (sin, cos) / _offset of the SDK's sampleTexture (cuda/LocalShading.h:37-54)
 int rt3_scene_set_texture_transform(rt3_context_t c, int id, const float scale[2], const float rotation[2], const float offset[2]) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && scale && rotation && offset, RT3_ERR_INVALID, "set_texture_transform: null argument");
     RT3_REQUIRE(id >= 0 && id < (int)c->inst.size(), RT3_ERR_INVALID, "set_texture_transform: instance id out of range");
     HitGroupDev& hg = c->inst[id].hg;
@@ -661,6 +681,7 @@ int rt3_scene_set_texture_transform(rt3_context_t c, int id, const float scale[2
 
 int rt3_scene_set_lights(rt3_context_t c, const void* lights68, int n) {
     RT3_API_BEGIN
+    use_device(c);
     static_assert(sizeof(Light) == 68, "rendertoy3o::Light is 68 bytes");
     RT3_REQUIRE(c && lights68 && n > 0, RT3_ERR_INVALID, "set_lights: at least one light is required (Q17)");
     c->d_lights.alloc(n);
@@ -718,6 +739,7 @@ int rt3_camera_uvw(const float eye[3], const float lookat[3], const float up[3],
 // ------------------------------------------------------------------------------------ the hot path
 int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && rs, RT3_ERR_INVALID, "launch_subframe: null argument");
     RT3_REQUIRE(c->built, RT3_ERR_STATE, "launch_subframe: rt3_accel_build has not been called");
     RT3_REQUIRE(c->nlights > 0, RT3_ERR_STATE, "launch_subframe: no lights set (Q17)");
@@ -879,6 +901,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
 
 int rt3_trace_device(rt3_context_t c, const void* d_rays, int n, int any_hit, void* d_hits) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && c->built, RT3_ERR_STATE, "trace: rt3_accel_build has not been called");
     RT3_REQUIRE(n >= 0 && (n == 0 || (d_rays && d_hits)), RT3_ERR_INVALID, "trace: bad argument");
     if (n == 0) return RT3_OK;
@@ -899,6 +922,7 @@ int rt3_trace_device(rt3_context_t c, const void* d_rays, int n, int any_hit, vo
 
 int rt3_trace(rt3_context_t c, const rt3_ray* rays, int n, int any_hit, rt3_hit* hits) {
     RT3_API_BEGIN
+    use_device(c);
     static_assert(sizeof(rt3_ray) == 48 && sizeof(rt3_hit) == 32, "ABI record sizes");
     RT3_REQUIRE(c && c->built, RT3_ERR_STATE, "trace: rt3_accel_build has not been called");
     RT3_REQUIRE(n >= 0 && (n == 0 || (rays && hits)), RT3_ERR_INVALID, "trace: bad argument");
@@ -915,6 +939,7 @@ int rt3_trace(rt3_context_t c, const rt3_ray* rays, int n, int any_hit, rt3_hit*
 // getLocalGeometry (cuda/LocalGeometry.h:61-175) for a batch of rays and the hit records rt3_trace returned for them
 int rt3_get_local_geometry(rt3_context_t c, const rt3_ray* rays, const rt3_hit* hits, int n, rt3_local_geometry* out) {
     RT3_API_BEGIN
+    use_device(c);
     static_assert(sizeof(rt3_local_geometry) == 108, "ABI record size");
     RT3_REQUIRE(c && c->built, RT3_ERR_STATE, "get_local_geometry: rt3_accel_build has not been called");
     RT3_REQUIRE(n >= 0 && (n == 0 || (rays && hits && out)), RT3_ERR_INVALID, "get_local_geometry: bad argument");
@@ -951,6 +976,7 @@ int rt3_get_local_geometry(rt3_context_t c, const rt3_ray* rays, const rt3_hit* 
 // ------------------------------------------------------------------------------------ results
 int rt3_download_accum(rt3_context_t c, float* rgba) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && rgba && c->accum.p, RT3_ERR_STATE, "download_accum: nothing rendered");
     d2h(rgba, c->accum.p, c->accum.bytes(), c->stream);
     stream_sync(c->stream);
@@ -958,6 +984,7 @@ int rt3_download_accum(rt3_context_t c, float* rgba) {
 }
 int rt3_download_frame(rt3_context_t c, uint8_t* rgba8) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && rgba8 && c->frame.p, RT3_ERR_STATE, "download_frame: nothing rendered");
     d2h(rgba8, c->frame.p, c->frame.bytes(), c->stream);
     stream_sync(c->stream);
@@ -965,6 +992,7 @@ int rt3_download_frame(rt3_context_t c, uint8_t* rgba8) {
 }
 int rt3_accum_device_ptr(rt3_context_t c, void** p, uint64_t* n) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && p && n && c->accum.p, RT3_ERR_STATE, "accum_device_ptr: nothing rendered");
     stream_sync(c->stream);
     *p = c->accum.p;
@@ -973,12 +1001,14 @@ int rt3_accum_device_ptr(rt3_context_t c, void** p, uint64_t* n) {
 }
 int rt3_clear_accum(rt3_context_t c) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c, RT3_ERR_INVALID, "clear_accum: null context");
     if (c->accum.p) dev_memset(c->accum.p, 0, c->accum.bytes(), c->stream);
     RT3_API_END
 }
 int rt3_finalize_accum(rt3_context_t c, uint32_t total_subframes) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && c->accum.p && total_subframes > 0, RT3_ERR_STATE, "finalize_accum: nothing rendered");
     RT3_LAUNCH_1D(k_finalize, c->width * c->height, c->stream, c->accum.p, c->frame.p, 1.0f / (float)total_subframes);
     RT3_API_END
@@ -986,6 +1016,7 @@ int rt3_finalize_accum(rt3_context_t c, uint32_t total_subframes) {
 
 int rt3_get_stats(rt3_context_t c, rt3_stats* st) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && st, RT3_ERR_INVALID, "get_stats: null argument");
     unsigned long long s[4] = {0, 0, 0, 0};
     uint32_t fl[2] = {0, 0};
@@ -1002,6 +1033,7 @@ int rt3_get_stats(rt3_context_t c, rt3_stats* st) {
 }
 int rt3_get_debug_counters(rt3_context_t c, uint32_t out[16]) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c && out, RT3_ERR_INVALID, "get_debug_counters: null argument");
     d2h(out, c->d_flags.p, 16 * sizeof(uint32_t), c->stream);
     stream_sync(c->stream);
@@ -1010,6 +1042,7 @@ int rt3_get_debug_counters(rt3_context_t c, uint32_t out[16]) {
 }
 int rt3_reset_stats(rt3_context_t c) {
     RT3_API_BEGIN
+    use_device(c);
     RT3_REQUIRE(c, RT3_ERR_INVALID, "reset_stats: null context");
     dev_memset(c->d_stats.p, 0, c->d_stats.bytes(), c->stream);
     c->samples = 0;

@@ -190,3 +190,25 @@ def test_cpp_host_vertex_keyframes_from_obj_files(tmp_path, emul_lib):
     open(bad, "w").write("v 0 0 0\nvn 0 1 0\nvt 0 0\n")
     r = subprocess.run([exe, "--scene", files[0], "--key", bad, "--out", out], capture_output=True, text=True)
     assert r.returncode != 0 and "fewer v / vn / vt" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_host_two_gpus_one_process(tmp_path, product_lib):
+    """two contexts in one process (every entry point selects its context's device), sample-partitioned subframes and the
+    NCCL sum of rt3_allreduce_accum: same image as one GPU.  Needs a 2-GPU box (skipped otherwise)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    exe = build_host(os.path.dirname(product_lib), os.path.basename(product_lib), str(tmp_path / "wavefront"))
+    desc = scenes.cornell(width=128, height=128)
+    obj = str(tmp_path / "scene.obj")
+    scenes.write_obj(desc, obj)
+    c = desc.camera
+    imgs = []
+    for n in (1, 2):
+        out = str(tmp_path / ("o%d.ppm" % n))
+        r = subprocess.run([exe, "--scene", obj, "--gpus", str(n), "--width", "128", "--height", "128", "--spp", "64", "--max-depth", "4", "--fovy", repr(c.fovy),
+                            "--out", out, "--eye", *map(repr, c.eye), "--lookat", *map(repr, c.lookat), "--up", *map(repr, c.up)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        imgs.append(read_ppm(out).astype(np.int32))
+    assert np.abs(imgs[0] - imgs[1]).max() <= 1   # same samples, another summation order
