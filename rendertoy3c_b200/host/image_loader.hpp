@@ -1,12 +1,12 @@
 // image_loader.hpp — texture file ingest for the .obj/.mtl loader, written from scratch (the reference
 // calls stbi_load(..., STBI_rgb_alpha), src/mesh.cpp:137; stb_image is not used here).
 // Decodes to RGBA8, rows flipped so that v = 0 is the image bottom (mesh.cpp:151-159):
-//   * PNG  — 8/16-bit, grey / grey+alpha / RGB / RGBA / palette (+ tRNS), non-interlaced; own inflate
+//   * PNG  — 1-16 bit, grey / grey+alpha / RGB / RGBA / palette (+ tRNS), plain or Adam7-interlaced; own inflate
 //   * BMP  — uncompressed 24 / 32 bit, bottom-up or top-down
 //   * TGA  — true-colour 24 / 32 bit and 8-bit grey, raw or RLE, either origin
 //   * PPM / PGM — binary P6 / P5, maxval 255
 //   * JPEG — baseline sequential (Huffman, 8 bit), grey or YCbCr with any sampling factors, restart intervals
-// Progressive / arithmetic / CMYK JPEG and interlaced PNG are not supported (load_image returns false and says why).
+// Progressive / arithmetic / CMYK JPEG are not supported (load_image returns false and says why).
 #pragma once
 #include <cctype>
 #include <cmath>
@@ -177,49 +177,63 @@ inline bool load_png(const std::vector<uint8_t>& f, Texture& t, std::string& why
         pos += 12 + (size_t)len;
     }
     if (w == 0 || h == 0 || w > 65535u || h > 65535u) { why = "bad PNG header"; return false; }
-    if (interlace) { why = "interlaced PNG is not supported"; return false; }
+    if (interlace > 1) { why = "unknown PNG interlace method"; return false; }
     const int chan = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!chan || !(depth == 8 || depth == 16 || (depth < 8 && (ctype == 0 || ctype == 3))) || (ctype == 3 && depth == 16)) { why = "unsupported PNG colour type / bit depth"; return false; }
     if (idat.size() < 6) { why = "PNG without image data"; return false; }
     std::vector<uint8_t> raw;
     raw.reserve(((size_t)w * chan * depth / 8 + 2) * h);
     if (!inflate_raw(idat.data() + 2, idat.size() - 2, raw)) { why = "corrupt PNG data stream"; return false; }  // 2-byte zlib header; Adler-32 not checked
-    const size_t stride = ((size_t)w * chan * depth + 7) / 8, bpp = (size_t)((chan * depth + 7) / 8);
-    if (raw.size() < (stride + 1) * h) { why = "short PNG data stream"; return false; }
-    std::vector<uint8_t> prev(stride, 0), top((size_t)4 * w * h);
-    for (uint32_t y = 0; y < h; ++y) {
-        uint8_t* row = &raw[(stride + 1) * y + 1];
-        const int ft = raw[(stride + 1) * y];
-        for (size_t i = 0; i < stride; ++i) {  // un-filter in place (PNG spec 9.2)
-            const int a = i >= bpp ? row[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
-            int pred = 0;
-            if (ft == 1) pred = a;
-            else if (ft == 2) pred = b;
-            else if (ft == 3) pred = (a + b) >> 1;
-            else if (ft == 4) { const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
-            else if (ft != 0) { why = "bad PNG filter type"; return false; }
-            row[i] = (uint8_t)(row[i] + pred);
-        }
-        std::memcpy(prev.data(), row, stride);
-        for (uint32_t x = 0; x < w; ++x) {
-            uint8_t* d = &top[4 * ((size_t)y * w + x)];
-            auto sample = [&](int c) -> int {  // channel c of pixel x as 8 bit (16 bit: high byte)
-                if (depth == 8) return row[(size_t)x * chan + c];
-                if (depth == 16) return row[((size_t)x * chan + c) * 2];
-                const int per = 8 / depth, v = (row[x / per] >> ((per - 1 - (int)(x % per)) * depth)) & ((1 << depth) - 1);
-                return ctype == 3 ? v : v * 255 / ((1 << depth) - 1);
-            };
-            if (ctype == 0) { const int g = sample(0); d[0] = d[1] = d[2] = (uint8_t)g; d[3] = 255; }
-            else if (ctype == 2) { d[0] = (uint8_t)sample(0); d[1] = (uint8_t)sample(1); d[2] = (uint8_t)sample(2); d[3] = 255; }
-            else if (ctype == 4) { const int g = sample(0); d[0] = d[1] = d[2] = (uint8_t)g; d[3] = (uint8_t)sample(1); }
-            else if (ctype == 6) { d[0] = (uint8_t)sample(0); d[1] = (uint8_t)sample(1); d[2] = (uint8_t)sample(2); d[3] = (uint8_t)sample(3); }
-            else {
-                const size_t k = (size_t)sample(0);
-                if (3 * k + 2 >= plte.size()) { why = "PNG palette index out of range"; return false; }
-                d[0] = plte[3 * k]; d[1] = plte[3 * k + 1]; d[2] = plte[3 * k + 2];
-                d[3] = k < trns.size() ? trns[k] : 255;
+    const size_t bpp = (size_t)((chan * depth + 7) / 8);
+    std::vector<uint8_t> top((size_t)4 * w * h), prev;
+    // one pass = a sub-image with its own scanlines: the whole image, or the seven Adam7 passes {x0, y0, dx, dy}
+    static const int adam7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    static const int whole[1][4] = {{0, 0, 1, 1}};
+    const int (*passes)[4] = interlace ? adam7 : whole;
+    size_t pos_raw = 0;
+    for (int pass = 0; pass < (interlace ? 7 : 1); ++pass) {
+        const uint32_t x0 = (uint32_t)passes[pass][0], y0 = (uint32_t)passes[pass][1], dx = (uint32_t)passes[pass][2], dy = (uint32_t)passes[pass][3];
+        if (x0 >= w || y0 >= h) continue;
+        const uint32_t pw = (w - x0 + dx - 1) / dx, ph = (h - y0 + dy - 1) / dy;
+        const size_t stride = ((size_t)pw * chan * depth + 7) / 8;
+        if (raw.size() < pos_raw + (stride + 1) * ph) { why = "short PNG data stream"; return false; }
+        prev.assign(stride, 0);
+        for (uint32_t j = 0; j < ph; ++j) {
+            uint8_t* row = &raw[pos_raw + (stride + 1) * j + 1];
+            const int ft = raw[pos_raw + (stride + 1) * j];
+            for (size_t i = 0; i < stride; ++i) {  // un-filter in place (PNG spec 9.2)
+                const int a = i >= bpp ? row[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+                int pred = 0;
+                if (ft == 1) pred = a;
+                else if (ft == 2) pred = b;
+                else if (ft == 3) pred = (a + b) >> 1;
+                else if (ft == 4) { const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+                else if (ft != 0) { why = "bad PNG filter type"; return false; }
+                row[i] = (uint8_t)(row[i] + pred);
+            }
+            std::memcpy(prev.data(), row, stride);
+            const uint32_t y = y0 + j * dy;
+            for (uint32_t x = 0; x < pw; ++x) {
+                uint8_t* d = &top[4 * ((size_t)y * w + (x0 + x * dx))];
+                auto sample = [&](int c) -> int {  // channel c of pixel x of this pass as 8 bit (16 bit: high byte)
+                    if (depth == 8) return row[(size_t)x * chan + c];
+                    if (depth == 16) return row[((size_t)x * chan + c) * 2];
+                    const int per = 8 / depth, v = (row[x / per] >> ((per - 1 - (int)(x % per)) * depth)) & ((1 << depth) - 1);
+                    return ctype == 3 ? v : v * 255 / ((1 << depth) - 1);
+                };
+                if (ctype == 0) { const int g = sample(0); d[0] = d[1] = d[2] = (uint8_t)g; d[3] = 255; }
+                else if (ctype == 2) { d[0] = (uint8_t)sample(0); d[1] = (uint8_t)sample(1); d[2] = (uint8_t)sample(2); d[3] = 255; }
+                else if (ctype == 4) { const int g = sample(0); d[0] = d[1] = d[2] = (uint8_t)g; d[3] = (uint8_t)sample(1); }
+                else if (ctype == 6) { d[0] = (uint8_t)sample(0); d[1] = (uint8_t)sample(1); d[2] = (uint8_t)sample(2); d[3] = (uint8_t)sample(3); }
+                else {
+                    const size_t k = (size_t)sample(0);
+                    if (3 * k + 2 >= plte.size()) { why = "PNG palette index out of range"; return false; }
+                    d[0] = plte[3 * k]; d[1] = plte[3 * k + 1]; d[2] = plte[3 * k + 2];
+                    d[3] = k < trns.size() ? trns[k] : 255;
+                }
             }
         }
+        pos_raw += (stride + 1) * ph;
     }
     store_flipped(top, (int)w, (int)h, t);
     return true;

@@ -1,5 +1,5 @@
 """N1 (texture ingest): rendertoy3c_b200/host/image_loader.hpp decodes PNG (own inflate: stored, fixed and dynamic
-Huffman blocks; all five scanline filters; grey, grey+alpha, RGB, RGBA, palette + tRNS, 16-bit, sub-byte depths),
+Huffman blocks; all five scanline filters; grey, grey+alpha, RGB, RGBA, palette + tRNS, 16-bit, sub-byte depths, Adam7 interlacing),
 BMP, TGA and PNM files to the RGBA8, bottom-row-first layout the reference's loadOBJ produces (src/mesh.cpp:137-159).
 The files are written here with the standard library only (struct + zlib)."""
 import os
@@ -67,6 +67,46 @@ def write_png(path, rows, ctype, depth, filters, level=6, strategy=zlib.Z_DEFAUL
         f += png_chunk(b"IDAT", z[k:k + step])
     f += png_chunk(b"IEND", b"")
     open(path, "wb").write(f)
+
+
+def write_png_adam7(path, px, ctype, filters, level=6):
+    """8-bit Adam7-interlaced PNG of px [h, w, chan]: seven sub-images, each with its own filtered scanlines"""
+    h, w, chan = px.shape
+    out = bytearray()
+    n = 0
+    for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+        sub = px[y0::dy, x0::dx]
+        if sub.shape[0] == 0 or sub.shape[1] == 0:
+            continue
+        prev = bytes(sub.shape[1] * chan)
+        for y in range(sub.shape[0]):
+            row = sub[y].tobytes()
+            ft = filters[n % len(filters)]; n += 1
+            enc = bytearray()
+            for i, v in enumerate(row):
+                a = row[i - chan] if i >= chan else 0
+                b = prev[i]
+                c = prev[i - chan] if i >= chan else 0
+                enc.append((v - [0, a, b, (a + b) >> 1, paeth(a, b, c)][ft]) & 255)
+            out += bytes([ft]) + enc
+            prev = row
+    f = b"\x89PNG\r\n\x1a\n" + png_chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 1))
+    f += png_chunk(b"IDAT", zlib.compress(bytes(out), level)) + png_chunk(b"IEND", b"")
+    open(path, "wb").write(f)
+
+
+def test_png_adam7_interlaced(exe, tmp_path):
+    rng = np.random.RandomState(9)
+    for (h, w) in ((23, 37), (1, 1), (3, 2), (8, 8), (9, 17)):          # small sizes leave some passes empty
+        img = rng.randint(0, 256, size=(h, w, 4)).astype(np.uint8)
+        for tag, ctype, px in (("rgba", 6, img), ("rgb", 2, img[..., :3]), ("grey", 0, img[..., :1])):
+            p = str(tmp_path / ("adam7_%s_%dx%d.png" % (tag, w, h)))
+            write_png_adam7(p, np.ascontiguousarray(px), ctype, [0, 1, 2, 3, 4])
+            got, err = decode(exe, p, tmp_path)
+            assert got is not None, (tag, w, h, err)
+            want = np.full((h, w, 4), 255, np.uint8)
+            want[..., :px.shape[2] if ctype != 0 else 3] = px if ctype != 0 else np.repeat(px, 3, axis=2)
+            assert np.array_equal(got, want), (tag, w, h)
 
 
 def test_png_variants(exe, tmp_path):
@@ -379,9 +419,9 @@ def test_rejects_what_it_cannot_decode(exe, tmp_path):
     got, err = decode(exe, p, tmp_path)
     assert got is None
     rows = [bytes(12)] * 4
-    p = str(tmp_path / "i.png"); write_png(p, rows, 2, 8, [0], interlace=1)
+    p = str(tmp_path / "i.png"); write_png(p, rows, 2, 8, [0], interlace=2)
     got, err = decode(exe, p, tmp_path)
-    assert got is None and "interlaced" in err
+    assert got is None and "interlace" in err
     p = str(tmp_path / "t.png"); write_png(p, rows, 2, 8, [0])
     data = open(p, "rb").read()
     open(p, "wb").write(data[:len(data) // 2])
