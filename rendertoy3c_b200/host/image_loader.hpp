@@ -2,11 +2,12 @@
 // calls stbi_load(..., STBI_rgb_alpha), src/mesh.cpp:137; stb_image is not used here).
 // Decodes to RGBA8, rows flipped so that v = 0 is the image bottom (mesh.cpp:151-159):
 //   * PNG  — 1-16 bit, grey / grey+alpha / RGB / RGBA / palette (+ tRNS), plain or Adam7-interlaced; own inflate
-//   * BMP  — uncompressed 24 / 32 bit, bottom-up or top-down
-//   * TGA  — true-colour 24 / 32 bit and 8-bit grey, raw or RLE, either origin
-//   * PPM / PGM — binary P6 / P5, maxval 255
-//   * JPEG — baseline sequential (Huffman, 8 bit), grey or YCbCr with any sampling factors, restart intervals
-// Progressive / arithmetic / CMYK JPEG are not supported (load_image returns false and says why).
+//   * BMP  — uncompressed: 1 / 4 / 8-bit palettised, 16 / 32-bit with masks, 24-bit; core, info and V4 / V5 headers
+//   * TGA  — true-colour 15 / 16 / 24 / 32 bit, grey, grey + alpha, colour-mapped; raw or RLE; either vertical origin
+//   * PPM / PGM — binary P6 / P5, 8 or 16 bits per sample
+//   * JPEG — baseline, extended-sequential and progressive (Huffman, 8 bit); grey, YCbCr, RGB, CMYK / YCCK; integer
+//            sampling ratios; restart intervals; decoded with stb_image's arithmetic so that the bytes are the reference's
+// Arithmetic-coded / lossless JPEG are not supported (load_image returns false and says why), as in stb_image.
 #pragma once
 #include <cctype>
 #include <cmath>
@@ -179,12 +180,24 @@ inline bool load_png(const std::vector<uint8_t>& f, Texture& t, std::string& why
     if (w == 0 || h == 0 || w > 65535u || h > 65535u) { why = "bad PNG header"; return false; }
     if (interlace > 1) { why = "unknown PNG interlace method"; return false; }
     const int chan = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-    if (!chan || !(depth == 8 || depth == 16 || (depth < 8 && (ctype == 0 || ctype == 3))) || (ctype == 3 && depth == 16)) { why = "unsupported PNG colour type / bit depth"; return false; }
+    const bool depth_ok = depth == 8 || (depth == 16 && ctype != 3) || ((depth == 1 || depth == 2 || depth == 4) && (ctype == 0 || ctype == 3));
+    if (!chan || !depth_ok) { why = "unsupported PNG colour type / bit depth"; return false; }
+    if ((uint64_t)w * (uint64_t)h > (1ull << 28)) { why = "PNG too large"; return false; }
     if (idat.size() < 6) { why = "PNG without image data"; return false; }
-    std::vector<uint8_t> raw;
-    raw.reserve(((size_t)w * chan * depth / 8 + 2) * h);
+    std::vector<uint8_t> raw;   // grows with the data actually present: the header alone never sizes an allocation
     if (!inflate_raw(idat.data() + 2, idat.size() - 2, raw)) { why = "corrupt PNG data stream"; return false; }  // 2-byte zlib header; Adler-32 not checked
     const size_t bpp = (size_t)((chan * depth + 7) / 8);
+    // colour-key transparency of grey / RGB images (tRNS holds ONE colour, 16 bits per channel): compared at the full
+    // 16 bits for 16-bit images, else on the low byte scaled like the samples (stb_image.h:5155-5166,5218-5226)
+    const bool keyed = (ctype == 0 || ctype == 2) && !trns.empty();
+    uint32_t key[3] = {0, 0, 0};
+    if (keyed) {
+        if (trns.size() != (size_t)2 * chan) { why = "bad PNG tRNS chunk"; return false; }
+        for (int c = 0; c < chan; ++c) {
+            const uint32_t v = ((uint32_t)trns[2 * (size_t)c] << 8) | trns[2 * (size_t)c + 1];
+            key[c] = depth == 16 ? v : (uint8_t)((v & 255u) * (depth == 8 ? 1u : 255u / ((1u << depth) - 1u)));
+        }
+    }
     std::vector<uint8_t> top((size_t)4 * w * h), prev;
     // one pass = a sub-image with its own scanlines: the whole image, or the seven Adam7 passes {x0, y0, dx, dy}
     static const int adam7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
@@ -221,8 +234,15 @@ inline bool load_png(const std::vector<uint8_t>& f, Texture& t, std::string& why
                     const int per = 8 / depth, v = (row[x / per] >> ((per - 1 - (int)(x % per)) * depth)) & ((1 << depth) - 1);
                     return ctype == 3 ? v : v * 255 / ((1 << depth) - 1);
                 };
-                if (ctype == 0) { const int g = sample(0); d[0] = d[1] = d[2] = (uint8_t)g; d[3] = 255; }
-                else if (ctype == 2) { d[0] = (uint8_t)sample(0); d[1] = (uint8_t)sample(1); d[2] = (uint8_t)sample(2); d[3] = 255; }
+                auto full = [&](int c) -> uint32_t {  // the value the colour key is compared with
+                    if (depth == 16) return ((uint32_t)row[((size_t)x * chan + c) * 2] << 8) | row[((size_t)x * chan + c) * 2 + 1];
+                    return (uint32_t)sample(c);
+                };
+                if (ctype == 0) { const int g = sample(0); d[0] = d[1] = d[2] = (uint8_t)g; d[3] = (keyed && full(0) == key[0]) ? 0 : 255; }
+                else if (ctype == 2) {
+                    d[0] = (uint8_t)sample(0); d[1] = (uint8_t)sample(1); d[2] = (uint8_t)sample(2);
+                    d[3] = (keyed && full(0) == key[0] && full(1) == key[1] && full(2) == key[2]) ? 0 : 255;
+                }
                 else if (ctype == 4) { const int g = sample(0); d[0] = d[1] = d[2] = (uint8_t)g; d[3] = (uint8_t)sample(1); }
                 else if (ctype == 6) { d[0] = (uint8_t)sample(0); d[1] = (uint8_t)sample(1); d[2] = (uint8_t)sample(2); d[3] = (uint8_t)sample(3); }
                 else {
@@ -240,300 +260,889 @@ inline bool load_png(const std::vector<uint8_t>& f, Texture& t, std::string& why
 }
 
 // ------------------------------------------------------------------------------------ BMP
+// Uncompressed Windows / OS2 bitmaps the way stb_image reads them (support/stb/stb_image.h:5445-5720): core (12), info
+// (40 / 56) and V4 / V5 (108 / 124) headers; 1 / 4 / 8-bit palettised, 16-bit (5-5-5 or BI_BITFIELDS), 24-bit, 32-bit
+// (BGRA or BI_BITFIELDS); masked channels widened to 8 bits by bit replication; an alpha channel that is zero everywhere
+// is taken as opaque; positive height = bottom-up.  RLE-compressed bitmaps are refused (stb refuses them too).
 inline bool load_bmp(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
-    if (f.size() < 54 || f[0] != 'B' || f[1] != 'M') return false;
-    auto le32 = [&](size_t o) { return (uint32_t)f[o] | ((uint32_t)f[o + 1] << 8) | ((uint32_t)f[o + 2] << 16) | ((uint32_t)f[o + 3] << 24); };
-    const uint32_t off = le32(10), hdr = le32(14);
-    const int32_t w = (int32_t)le32(18), hs = (int32_t)le32(22);
-    const int bpp = f[28] | (f[29] << 8);
-    const uint32_t comp = le32(30);
-    if (hdr < 40 || w <= 0 || hs == 0 || (bpp != 24 && bpp != 32) || (comp != 0 && !(comp == 3 && bpp == 32))) { why = "unsupported BMP (need uncompressed 24 / 32 bit)"; return false; }
-    const int h = hs < 0 ? -hs : hs;
-    const size_t stride = (((size_t)w * bpp / 8) + 3) & ~(size_t)3;
-    if ((size_t)off + stride * h > f.size()) { why = "truncated BMP"; return false; }
-    std::vector<uint8_t> top((size_t)4 * w * h);
-    for (int y = 0; y < h; ++y) {
-        const uint8_t* row = &f[off + stride * (size_t)(hs < 0 ? y : h - 1 - y)];
-        for (int x = 0; x < w; ++x) {
-            const uint8_t* s = row + (size_t)x * bpp / 8;
-            uint8_t* d = &top[4 * ((size_t)y * w + x)];
-            d[0] = s[2]; d[1] = s[1]; d[2] = s[0]; d[3] = bpp == 32 ? s[3] : 255;
+    if (f.size() < 2 || f[0] != 'B' || f[1] != 'M') return false;
+    size_t pos = 2;
+    auto g8 = [&]() -> uint32_t { return pos < f.size() ? f[pos++] : 0u; };
+    auto g16 = [&]() -> uint32_t { const uint32_t a = g8(); return a | (g8() << 8); };
+    auto g32 = [&]() -> uint32_t { const uint32_t a = g16(); return a | (g16() << 16); };
+    auto skip = [&](int k) { if (k < 0) pos = f.size(); else pos = pos + (size_t)k > f.size() ? f.size() : pos + (size_t)k; };
+    g32(); g16(); g16();
+    const int offset = (int)g32(), hsz = (int)g32();
+    uint32_t mr = 0, mg = 0, mb = 0, ma = 0, all_a = 255;
+    int extra_read = 14, W, Hs;
+    if (offset < 0) { why = "bad BMP"; return false; }
+    if (hsz != 12 && hsz != 40 && hsz != 56 && hsz != 108 && hsz != 124) { why = "unknown BMP header"; return false; }
+    if (hsz == 12) { W = (int)g16(); Hs = (int)g16(); } else { W = (int)g32(); Hs = (int)g32(); }
+    if (g16() != 1) { why = "bad BMP"; return false; }
+    const int bpp = (int)g16();
+    auto default_masks = [&](int compress) {
+        if (compress != 0) return;
+        if (bpp == 16) { mr = 31u << 10; mg = 31u << 5; mb = 31u; }
+        else if (bpp == 32) { mr = 0xffu << 16; mg = 0xffu << 8; mb = 0xffu; ma = 0xffu << 24; all_a = 0; }
+        else mr = mg = mb = ma = 0;
+    };
+    if (hsz != 12) {
+        const int compress = (int)g32();
+        if (compress == 1 || compress == 2) { why = "RLE-compressed BMP is not supported"; return false; }
+        if (compress >= 4 || compress < 0) { why = "BMP with embedded JPEG / PNG is not supported"; return false; }
+        if (compress == 3 && bpp != 16 && bpp != 32) { why = "bad BMP"; return false; }
+        g32(); g32(); g32(); g32(); g32();
+        if (hsz == 40 || hsz == 56) {
+            if (hsz == 56) { g32(); g32(); g32(); g32(); }
+            if (bpp == 16 || bpp == 32) {
+                if (compress == 0) default_masks(0);
+                else {
+                    mr = g32(); mg = g32(); mb = g32();
+                    extra_read += 12;
+                    if (mr == mg && mg == mb) { why = "bad BMP"; return false; }
+                }
+            }
+        } else {
+            mr = g32(); mg = g32(); mb = g32(); ma = g32();
+            if (compress != 3) default_masks(compress);
+            for (int i = 0; i < 13; ++i) g32();
+            if (hsz == 124) { g32(); g32(); g32(); g32(); }
         }
     }
-    store_flipped(top, w, h, t);
+    const bool bottom_up = Hs > 0;
+    const int H = Hs < 0 ? -Hs : Hs;
+    if (W <= 0 || H <= 0 || W > (1 << 24) || H > (1 << 24) || (uint64_t)W * (uint64_t)H > (1ull << 28)) { why = "bad BMP size"; return false; }
+    int psize = 0;
+    if (hsz == 12) { if (bpp < 24) psize = (offset - extra_read - 24) / 3; }
+    else if (bpp < 16) psize = (offset - extra_read - hsz) >> 2;
+    if (psize == 0) {
+        const int so_far = (int)pos;
+        if (so_far <= 0 || so_far > 1024 || offset < so_far || offset - so_far > 1024) { why = "corrupt BMP (data offset)"; return false; }
+        skip(offset - so_far);
+    }
+    std::vector<uint8_t> rows((size_t)4 * W * H);   // in file order
+    size_t z = 0;
+    if (bpp < 16) {
+        if (psize == 0 || psize > 256) { why = "corrupt BMP (palette)"; return false; }
+        uint8_t pal[256][3];
+        std::memset(pal, 0, sizeof(pal));
+        for (int i = 0; i < psize; ++i) { pal[i][2] = (uint8_t)g8(); pal[i][1] = (uint8_t)g8(); pal[i][0] = (uint8_t)g8(); if (hsz != 12) g8(); }
+        skip(offset - extra_read - hsz - psize * (hsz == 12 ? 3 : 4));
+        int width;
+        if (bpp == 1) width = (W + 7) >> 3; else if (bpp == 4) width = (W + 1) >> 1; else if (bpp == 8) width = W; else { why = "corrupt BMP (bits per pixel)"; return false; }
+        const int pad = (-width) & 3;
+        for (int j = 0; j < H; ++j) {
+            uint32_t v = 0;
+            for (int i = 0; i < W; ++i) {
+                uint32_t c;
+                if (bpp == 1) { if ((i & 7) == 0) v = g8(); c = (v >> (7 - (i & 7))) & 1u; }
+                else if (bpp == 4) { if ((i & 1) == 0) { v = g8(); c = v >> 4; } else c = v & 15u; }
+                else c = g8();
+                rows[z++] = pal[c][0]; rows[z++] = pal[c][1]; rows[z++] = pal[c][2]; rows[z++] = 255;
+            }
+            skip(pad);
+        }
+    } else {
+        skip(offset - extra_read - hsz);
+        const int pad = bpp == 24 ? (-(3 * W)) & 3 : (bpp == 16 ? (-(2 * W)) & 3 : 0);
+        const int easy = bpp == 24 ? 1 : ((bpp == 32 && mb == 0xffu && mg == 0xff00u && mr == 0x00ff0000u && ma == 0xff000000u) ? 2 : 0);
+        if (bpp != 16 && bpp != 24 && bpp != 32) { why = "corrupt BMP (bits per pixel)"; return false; }
+        auto high_bit = [](uint32_t m) { int n = -1; while (m) { ++n; m >>= 1; } return n; };
+        auto bit_count = [](uint32_t m) { int n = 0; while (m) { n += (int)(m & 1u); m >>= 1; } return n; };
+        // the masked field, top-aligned to 8 bits and filled up by repeating its bit pattern
+        auto widen = [](uint32_t v, int shift, int bits) -> uint32_t {
+            static const uint32_t mul[9] = {0, 0xff, 0x55, 0x49, 0x11, 0x21, 0x41, 0x81, 0x01};
+            static const uint32_t shr[9] = {0, 0, 0, 1, 0, 2, 4, 6, 0};
+            if (shift < 0) v <<= -shift; else v >>= shift;
+            v >>= (8 - bits);
+            return (v * mul[bits]) >> shr[bits];
+        };
+        int rs = 0, gs = 0, bs = 0, as = 0, rc = 0, gc = 0, bc = 0, ac = 0;
+        if (!easy) {
+            if (!mr || !mg || !mb) { why = "corrupt BMP (masks)"; return false; }
+            rs = high_bit(mr) - 7; rc = bit_count(mr); gs = high_bit(mg) - 7; gc = bit_count(mg);
+            bs = high_bit(mb) - 7; bc = bit_count(mb); as = high_bit(ma) - 7; ac = bit_count(ma);
+            if (rc > 8 || gc > 8 || bc > 8 || ac > 8) { why = "corrupt BMP (masks)"; return false; }
+        }
+        for (int j = 0; j < H; ++j) {
+            for (int i = 0; i < W; ++i) {
+                uint32_t a;
+                if (easy) {
+                    rows[z + 2] = (uint8_t)g8(); rows[z + 1] = (uint8_t)g8(); rows[z] = (uint8_t)g8();
+                    a = easy == 2 ? g8() : 255u;
+                } else {
+                    const uint32_t v = bpp == 16 ? g16() : g32();
+                    rows[z] = (uint8_t)widen(v & mr, rs, rc); rows[z + 1] = (uint8_t)widen(v & mg, gs, gc); rows[z + 2] = (uint8_t)widen(v & mb, bs, bc);
+                    a = ma ? widen(v & ma, as, ac) : 255u;
+                }
+                all_a |= a;
+                rows[z + 3] = (uint8_t)a;
+                z += 4;
+            }
+            skip(pad);
+        }
+    }
+    if (all_a == 0) for (size_t i = 3; i < rows.size(); i += 4) rows[i] = 255;
+    t.width = W; t.height = H;
+    t.pixel.resize(rows.size());   // the texture wants the bottom row first, which is the file order of a bottom-up bitmap
+    for (int y = 0; y < H; ++y) std::memcpy(&t.pixel[(size_t)4 * W * y], &rows[(size_t)4 * W * (size_t)(bottom_up ? y : H - 1 - y)], (size_t)4 * W);
     return true;
 }
 
 // ------------------------------------------------------------------------------------ TGA
-inline bool load_tga(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
+// Truevision files as stb_image reads them (support/stb/stb_image.h:5733-6060): true-colour 15 / 16 / 24 / 32 bit, grey 8
+// bit and grey + alpha 16 bit, colour-mapped with 8 / 16-bit indices into a 15 / 16 / 24 / 32-bit palette, raw or RLE;
+// 5-bit channels scale as c * 255 / 31; rows bottom-up unless descriptor bit 5 is set; the right-to-left bit is ignored
+// (stb ignores it).  TGA has no magic number: tga_plausible() is the header check that stands in for one.
+inline bool tga_plausible(const std::vector<uint8_t>& f) {
     if (f.size() < 18) return false;
-    const int idlen = f[0], cmap = f[1], type = f[2], w = f[12] | (f[13] << 8), h = f[14] | (f[15] << 8), bpp = f[16], desc = f[17];
-    const bool rle = type == 10 || type == 11, grey = type == 3 || type == 11;
-    if (cmap != 0 || !(type == 2 || type == 3 || rle) || w <= 0 || h <= 0 || !((grey && bpp == 8) || (!grey && (bpp == 24 || bpp == 32)))) { why = "unsupported TGA (need true-colour 24 / 32 bit or 8-bit grey)"; return false; }
-    const size_t px = (size_t)bpp / 8;
-    std::vector<uint8_t> data((size_t)w * h * px);
-    size_t pos = 18 + (size_t)idlen, o = 0;
-    if (!rle) {
-        if (pos + data.size() > f.size()) { why = "truncated TGA"; return false; }
-        std::memcpy(data.data(), &f[pos], data.size());
-    } else {
-        while (o < data.size()) {
-            if (pos >= f.size()) { why = "truncated TGA"; return false; }
-            const int hd = f[pos++], cnt = (hd & 127) + 1;
-            if (hd & 128) {
-                if (pos + px > f.size()) { why = "truncated TGA"; return false; }
-                for (int k = 0; k < cnt && o < data.size(); ++k, o += px) std::memcpy(&data[o], &f[pos], px);
-                pos += px;
-            } else {
-                const size_t nb = (size_t)cnt * px;
-                if (pos + nb > f.size() || o + nb > data.size()) { why = "truncated TGA"; return false; }
-                std::memcpy(&data[o], &f[pos], nb);
-                pos += nb; o += nb;
-            }
+    const int cmap = f[1], type = f[2], bpp = f[16];
+    if (cmap > 1) return false;
+    if (cmap == 1) {
+        if (type != 1 && type != 9) return false;
+        const int pb = f[7];
+        if (pb != 8 && pb != 15 && pb != 16 && pb != 24 && pb != 32) return false;
+    } else if (type != 2 && type != 3 && type != 10 && type != 11) return false;
+    if ((f[12] | (f[13] << 8)) < 1 || (f[14] | (f[15] << 8)) < 1) return false;
+    if (cmap == 1 && bpp != 8 && bpp != 16) return false;
+    return bpp == 8 || bpp == 15 || bpp == 16 || bpp == 24 || bpp == 32;
+}
+inline bool load_tga(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
+    if (!tga_plausible(f)) return false;
+    size_t pos = 0;
+    auto g8 = [&]() -> int { return pos < f.size() ? f[pos++] : 0; };
+    auto g16 = [&]() -> int { const int a = g8(); return a | (g8() << 8); };
+    const int idlen = g8(), indexed = g8();
+    int type = g8();
+    const int pal_start = g16(), pal_len = g16(), pal_bits = g8();
+    g16(); g16();
+    const int w = g16(), h = g16(), bpp = g8(), desc = g8();
+    const bool rle = type >= 8;
+    if (rle) type -= 8;
+    const bool bottom_up = ((desc >> 5) & 1) == 0;
+    // components of a pixel as stored / looked up: 1 grey, 2 grey + alpha, 3 or 4 colour; 15 / 16-bit colour expands to 3
+    auto comps = [](int bits, bool grey, bool& rgb16) { rgb16 = false; if (bits == 8) return 1; if (bits == 16 && grey) return 2; if (bits == 15 || bits == 16) { rgb16 = true; return 3; } return (bits == 24 || bits == 32) ? bits / 8 : 0; };
+    bool rgb16 = false;
+    const int nc = indexed ? comps(pal_bits, false, rgb16) : comps(bpp, type == 3, rgb16);
+    if (!nc) { why = "unsupported TGA pixel format"; return false; }
+    if ((uint64_t)w * (uint64_t)h > (1ull << 28)) { why = "TGA too large"; return false; }
+    pos += (size_t)idlen;
+    auto read16 = [&](uint8_t* o) { const int px = g16(); o[0] = (uint8_t)((((px >> 10) & 31) * 255) / 31); o[1] = (uint8_t)((((px >> 5) & 31) * 255) / 31); o[2] = (uint8_t)(((px & 31) * 255) / 31); };
+    std::vector<uint8_t> pal;
+    if (indexed) {
+        if (pal_len == 0) { why = "corrupt TGA (empty palette)"; return false; }
+        pos += (size_t)pal_start;
+        pal.assign((size_t)pal_len * nc, 0);
+        if (rgb16) for (int i = 0; i < pal_len; ++i) read16(&pal[(size_t)i * 3]);
+        else {
+            if (pos + pal.size() > f.size()) { why = "truncated TGA"; return false; }
+            std::memcpy(pal.data(), &f[pos], pal.size());
+            pos += pal.size();
         }
     }
-    const bool top_origin = (desc & 0x20) != 0, right_origin = (desc & 0x10) != 0;
-    std::vector<uint8_t> top((size_t)4 * w * h);
-    for (int y = 0; y < h; ++y)
-        for (int x = 0; x < w; ++x) {
-            const uint8_t* s = &data[((size_t)(top_origin ? y : h - 1 - y) * w + (size_t)(right_origin ? w - 1 - x : x)) * px];
-            uint8_t* d = &top[4 * ((size_t)y * w + x)];
-            if (grey) { d[0] = d[1] = d[2] = s[0]; d[3] = 255; }
-            else { d[0] = s[2]; d[1] = s[1]; d[2] = s[0]; d[3] = bpp == 32 ? s[3] : 255; }
+    std::vector<uint8_t> data((size_t)w * h * nc);   // pixels in file order
+    uint8_t px[4] = {0, 0, 0, 0};
+    int run = 0;
+    bool repeating = false;
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+        bool fetch = true;
+        if (rle) {
+            if (run == 0) { const int c = g8(); run = 1 + (c & 127); repeating = (c >> 7) != 0; }
+            else if (repeating) fetch = false;
         }
-    store_flipped(top, w, h, t);
+        if (fetch) {
+            if (indexed) {
+                int k = bpp == 8 ? g8() : g16();
+                if (k >= pal_len) k = 0;
+                std::memcpy(px, &pal[(size_t)k * nc], (size_t)nc);
+            } else if (rgb16) read16(px);
+            else for (int j = 0; j < nc; ++j) px[j] = (uint8_t)g8();
+        }
+        std::memcpy(&data[i * nc], px, (size_t)nc);
+        --run;
+    }
+    t.width = w; t.height = h;
+    t.pixel.resize((size_t)4 * w * h);
+    for (int y = 0; y < h; ++y)   // texture row 0 = image bottom = the first row of a bottom-up file
+        for (int x = 0; x < w; ++x) {
+            const uint8_t* s = &data[((size_t)(bottom_up ? y : h - 1 - y) * w + (size_t)x) * nc];
+            uint8_t* d = &t.pixel[4 * ((size_t)y * w + x)];
+            if (nc == 1) { d[0] = d[1] = d[2] = s[0]; d[3] = 255; }
+            else if (nc == 2) { d[0] = d[1] = d[2] = s[0]; d[3] = s[1]; }
+            else if (rgb16) { d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = 255; }
+            else { d[0] = s[2]; d[1] = s[1]; d[2] = s[0]; d[3] = nc == 4 ? s[3] : 255; }
+        }
     return true;
 }
 
 // ------------------------------------------------------------------------------------ PPM / PGM
+// Binary P5 / P6 as stb_image reads them (support/stb/stb_image.h:7503-7621): samples are taken as they are, whatever
+// maxval says (no rescaling); with maxval > 255 a sample is two bytes and the texture gets the SECOND one — stb reads the
+// big-endian pairs as host-order 16-bit words and keeps their upper half, which on the little-endian hosts the reference
+// runs on is the low-order byte of the sample.
 inline bool load_pnm(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
-    if (f.size() < 7 || f[0] != 'P' || (f[1] != '6' && f[1] != '5')) return false;
+    if (f.size() < 3 || f[0] != 'P' || (f[1] != '6' && f[1] != '5')) return false;
     const int chan = f[1] == '6' ? 3 : 1;
     size_t pos = 2;
-    auto next_int = [&]() {
+    auto eof = [&]() { return pos >= f.size(); };
+    auto g8 = [&]() -> char { return (char)(pos < f.size() ? f[pos++] : 0); };
+    char c = g8();
+    auto is_space = [](char ch) { return ch == ' ' || ch == '\t' || ch == '\n' || ch == '\v' || ch == '\f' || ch == '\r'; };
+    auto skip_space = [&]() {
         for (;;) {
-            while (pos < f.size() && (f[pos] == ' ' || f[pos] == '\t' || f[pos] == '\r' || f[pos] == '\n')) ++pos;
-            if (pos < f.size() && f[pos] == '#') { while (pos < f.size() && f[pos] != '\n') ++pos; continue; }
-            break;
+            while (!eof() && is_space(c)) c = g8();
+            if (eof() || c != '#') break;
+            while (!eof() && c != '\n' && c != '\r') c = g8();
         }
-        int v = -1;
-        while (pos < f.size() && f[pos] >= '0' && f[pos] <= '9') { v = (v < 0 ? 0 : v * 10) + (f[pos] - '0'); ++pos; }
+    };
+    auto integer = [&]() -> long {
+        long v = 0;
+        while (!eof() && c >= '0' && c <= '9') { v = v * 10 + (c - '0'); c = g8(); if (v > 214748364L) return -1; }
         return v;
     };
-    const int w = next_int(), h = next_int(), maxv = next_int();
-    ++pos;  // the single whitespace byte after maxval
-    if (w <= 0 || h <= 0 || maxv != 255) { why = "unsupported PNM (need binary P5 / P6 with maxval 255)"; return false; }
-    if (pos + (size_t)w * h * chan > f.size()) { why = "truncated PNM"; return false; }
+    skip_space();
+    const long w = integer();
+    skip_space();
+    const long h = integer();
+    skip_space();
+    const long maxv = integer();
+    if (w <= 0 || h <= 0 || maxv < 0 || maxv > 65535) { why = "bad PNM header"; return false; }
+    const size_t bytes = maxv > 255 ? 2 : 1;
+    if ((uint64_t)w * (uint64_t)h > (1ull << 28)) { why = "PNM too large"; return false; }
+    if (pos + (size_t)w * h * chan * bytes > f.size()) { why = "truncated PNM"; return false; }
     std::vector<uint8_t> top((size_t)4 * w * h);
     for (size_t i = 0; i < (size_t)w * h; ++i) {
-        const uint8_t* s = &f[pos + i * chan];
+        const uint8_t* s = &f[pos + i * chan * bytes + (bytes - 1)];
         uint8_t* d = &top[4 * i];
-        d[0] = s[0]; d[1] = s[chan == 3 ? 1 : 0]; d[2] = s[chan == 3 ? 2 : 0]; d[3] = 255;
+        d[0] = s[0]; d[1] = s[chan == 3 ? bytes : 0]; d[2] = s[chan == 3 ? 2 * bytes : 0]; d[3] = 255;
     }
-    store_flipped(top, w, h, t);
+    store_flipped(top, (int)w, (int)h, t);
     return true;
 }
 
-// ------------------------------------------------------------------------------------ JPEG (baseline sequential, ITU T.81)
-// 8-bit, Huffman, one interleaved scan, 1 or 3 components (grey / YCbCr, any sampling factors up to 4, chroma
-// replicated on upsampling), restart intervals.  Progressive, arithmetic-coded and 4-component files are refused.
+// ------------------------------------------------------------------------------------ JPEG (ITU T.81), stb_image's arithmetic
+// The reference decodes map_Kd files with stbi_load (src/mesh.cpp:137); a JPEG decoder is not specified to the bit
+// by T.81, so "the same texture bytes" means stb_image's choices (support/stb/stb_image.h), restated here and pinned
+// against the reference's own loader (tests/test_loader_parity.py):
+//   * coefficients dequantised into 16-bit integers while decoding (:2209-2262), progressive scans refined in place
+//     and dequantised at the end (:2264-2412, :3072-3096);
+//   * the 8x8 inverse DCT in integers: the "islow" factorisation with 12-bit constants, a column pass that keeps
+//     2 extra bits (+512 >> 10), a row pass that removes 17 bits with the +128 level shift folded in (:2431-2517);
+//   * chroma planes brought to full resolution row by row with jfif-centred filters: 3:1 taps vertically / horizontally
+//     for factor 2, the 9:3:3:1 tent for 2x2, replication for every other ratio (:3453-3657, :3897-3945);
+//   * YCbCr -> RGB in 20-bit fixed point with the 16 fractional bits of the Cb term of green masked off
+//     (:3659-3688); RGB-tagged ('R','G','B' ids, or Adobe transform 0 without JFIF) and CMYK / YCCK files as stb
+//     treats them (:3947-3981);
+//   * an entropy segment that ends early yields zero bits, a missing restart marker ends the scan quietly (:2075-2092,
+//     :2962-2969) — lenient like stb, so that the same damaged files load to the same bytes.
+// 8-bit baseline, extended-sequential and progressive Huffman files with 1, 3 or 4 components; arithmetic coding and
+// lossless / hierarchical frames are refused, as stb refuses them.
 struct JpegHuff {
-    uint8_t vals[256];
-    int mincode[17], maxcode[17], valptr[17];  // per code length 1..16 (T.81 F.2.2.3); maxcode = -1: no code of that length
-    bool set = false;
-    void build(const uint8_t counts[16], const uint8_t* v, int nv) {
-        std::memcpy(vals, v, (size_t)nv);
-        int code = 0, k = 0;
+    uint8_t size[257], values[256];
+    uint16_t code[256];
+    uint32_t maxcode[18];   // per length: (largest code + 1) aligned to 16 bits
+    int delta[17];          // per length: symbol index of the first code minus that code
+    int16_t fast_ac[512];   // AC tables: (value << 8 | run << 4 | total length) for short codes with short magnitudes, else 0
+    bool build(const int count[16]) {
+        int k = 0;
+        for (int l = 0; l < 16; ++l)
+            for (int j = 0; j < count[l]; ++j) { size[k++] = (uint8_t)(l + 1); if (k >= 257) return false; }
+        size[k] = 0;
+        uint32_t c = 0;
+        k = 0;
         for (int l = 1; l <= 16; ++l) {
-            valptr[l] = k;
-            mincode[l] = code;
-            code += counts[l - 1];
-            k += counts[l - 1];
-            maxcode[l] = counts[l - 1] ? code - 1 : -1;
-            code <<= 1;
-        }
-        set = true;
-    }
-};
-struct JpegBits {
-    const uint8_t* p; size_t n, pos; uint32_t acc = 0; int cnt = 0; bool bad = false;
-    JpegBits(const uint8_t* d, size_t len, size_t at) : p(d), n(len), pos(at) {}
-    int bit() {
-        if (cnt == 0) {
-            if (pos >= n) { bad = true; return 0; }
-            uint8_t b = p[pos++];
-            if (b == 0xff) {
-                if (pos < n && p[pos] == 0x00) ++pos;  // stuffed zero
-                else { bad = true; --pos; return 0; }  // a marker inside the data: the scan ended early
+            delta[l] = k - (int)c;
+            if (size[k] == l) {
+                while (size[k] == l) code[k++] = (uint16_t)(c++);
+                if (c - 1 >= (1u << l)) return false;
             }
-            acc = b; cnt = 8;
+            maxcode[l] = c << (16 - l);
+            c <<= 1;
         }
-        --cnt;
-        return (int)((acc >> cnt) & 1u);
+        maxcode[17] = 0xffffffffu;
+        return true;
     }
-    int receive(int k) { int v = 0; while (k--) v = (v << 1) | bit(); return v; }
-    int decode(const JpegHuff& h) {
-        int code = 0;
-        for (int l = 1; l <= 16; ++l) {
-            code = (code << 1) | bit();
-            if (bad) return -1;
-            if (h.maxcode[l] >= 0 && code <= h.maxcode[l] && code >= h.mincode[l]) return h.vals[h.valptr[l] + code - h.mincode[l]];
-        }
-        bad = true;
+    // symbol index + length of the code at the top of a 9-bit window, or -1 when the code is longer
+    int peek9(uint32_t window9, int& len) const {
+        const uint32_t top16 = window9 << 7;
+        for (int l = 1; l <= 9; ++l)
+            if (top16 < maxcode[l]) { len = l; const int sym = (int)(top16 >> (16 - l)) + delta[l]; return (sym >= 0 && sym < 256 && size[sym] == l) ? sym : -1; }
         return -1;
     }
-    bool restart(int expect) {  // byte-align, then RSTn
-        cnt = 0;
-        if (pos + 2 > n || p[pos] != 0xff || p[pos + 1] != (uint8_t)(0xd0 + (expect & 7))) return false;
-        pos += 2;
+    void build_fast_ac() {
+        for (uint32_t i = 0; i < 512; ++i) {
+            fast_ac[i] = 0;
+            int len = 0;
+            const int sym = peek9(i, len);
+            if (sym < 0) continue;
+            const int rs = values[sym], run = rs >> 4, mag = rs & 15;
+            if (mag && len + mag <= 9) {
+                int k = (int)(((i << len) & 511u) >> (9 - mag));
+                if (k < (1 << (mag - 1))) k -= (1 << mag) - 1;
+                if (k >= -128 && k <= 127) fast_ac[i] = (int16_t)(k * 256 + run * 16 + len + mag);
+            }
+        }
+    }
+};
+
+struct JpegComp {
+    int id = 0, h = 1, v = 1, tq = 0, hd = 0, ha = 0, dc_pred = 0;
+    int x = 0, y = 0, w2 = 0, h2 = 0, coeff_w = 0;
+    std::vector<uint8_t> data;     // w2 x h2 samples
+    std::vector<int16_t> coeff;    // progressive: 64 per block
+};
+
+struct JpegDec {
+    const uint8_t* p; size_t n, pos = 0;
+    uint32_t buf = 0; int bits = 0; int marker = 0xff; bool nomore = false;   // entropy reader; marker 0xff = none
+    JpegHuff hdc[4], hac[4];
+    uint16_t dequant[4][64];
+    JpegComp comp[4];
+    int ncomp = 0, W = 0, H = 0, hmax = 1, vmax = 1, mcu_x = 0, mcu_y = 0;
+    bool progressive = false, jfif = false;
+    int adobe_transform = -1, rgb_ids = 0;
+    int scan_n = 0, order[4] = {0, 0, 0, 0}, spec_start = 0, spec_end = 0, succ_high = 0, succ_low = 0, eob_run = 0;
+    int restart_interval = 0, todo = 0;
+    std::string why;
+
+    int get8() { return pos < n ? p[pos++] : 0; }
+    int get16() { const int a = get8(); return (a << 8) | get8(); }
+    bool fail(const char* m) { if (why.empty()) why = m; return false; }
+
+    void grow() {
+        do {
+            const uint32_t b = nomore ? 0u : (uint32_t)get8();
+            if (b == 0xff) {
+                int c = get8();
+                while (c == 0xff) c = get8();
+                if (c != 0) { marker = c; nomore = true; return; }
+            }
+            buf |= b << (24 - bits);
+            bits += 8;
+        } while (bits <= 24);
+    }
+    int huff(const JpegHuff& h) {
+        if (bits < 16) grow();
+        const uint32_t top = buf >> 16;
+        int k = 1;
+        while (k <= 16 && top >= h.maxcode[k]) ++k;
+        if (k == 17 || k > bits) return -1;
+        const int sym = (int)(buf >> (32 - k)) + h.delta[k];
+        if (sym < 0 || sym >= 256) return -1;
+        bits -= k;
+        buf <<= k;
+        return h.values[sym];
+    }
+    int take(int k) {   // k unsigned bits, 0 once the stream has run dry
+        if (bits < k) grow();
+        if (bits < k || k == 0) return 0;
+        const uint32_t v = buf >> (32 - k);
+        buf <<= k;
+        bits -= k;
+        return (int)v;
+    }
+    int extend(int k) {  // T.81 F.2.2.1 RECEIVE + EXTEND
+        if (bits < k) grow();
+        if (bits < k) return 0;
+        const int v = take(k);
+        return v < (1 << (k - 1)) ? v - (1 << k) + 1 : v;
+    }
+    int get_marker() {
+        if (marker != 0xff) { const int m = marker; marker = 0xff; return m; }
+        int x = get8();
+        if (x != 0xff) return 0xff;
+        while (x == 0xff) x = get8();
+        return x;
+    }
+    void reset() {
+        bits = 0; buf = 0; nomore = false; marker = 0xff; eob_run = 0;
+        for (JpegComp& c : comp) c.dc_pred = 0;
+        todo = restart_interval ? restart_interval : 0x7fffffff;
+    }
+
+    bool table_marker(int m) {   // DRI, DQT, DHT, APPn, COM
+        static const uint8_t zz[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                                       35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+        if (m == 0xff) return fail("corrupt JPEG (marker expected)");
+        if (m == 0xdd) { if (get16() != 4) return fail("corrupt JPEG (DRI)"); restart_interval = get16(); return true; }
+        if (m == 0xdb) {
+            int L = get16() - 2;
+            while (L > 0) {
+                const int q = get8(), prec = q >> 4, t = q & 15;
+                if (prec > 1 || t > 3) return fail("corrupt JPEG (DQT)");
+                for (int i = 0; i < 64; ++i) dequant[t][zz[i]] = (uint16_t)(prec ? get16() : get8());
+                L -= prec ? 129 : 65;
+            }
+            return L == 0 ? true : fail("corrupt JPEG (DQT)");
+        }
+        if (m == 0xc4) {
+            int L = get16() - 2;
+            while (L > 0) {
+                const int q = get8(), tc = q >> 4, th = q & 15;
+                if (tc > 1 || th > 3) return fail("corrupt JPEG (DHT)");
+                int count[16], total = 0;
+                for (int& c : count) { c = get8(); total += c; }
+                if (total > 256) return fail("corrupt JPEG (DHT)");
+                JpegHuff& h = tc ? hac[th] : hdc[th];
+                if (!h.build(count)) return fail("corrupt JPEG (DHT)");
+                for (int i = 0; i < total; ++i) h.values[i] = (uint8_t)get8();
+                if (tc) h.build_fast_ac();
+                L -= 17 + total;
+            }
+            return L == 0 ? true : fail("corrupt JPEG (DHT)");
+        }
+        if ((m >= 0xe0 && m <= 0xef) || m == 0xfe) {
+            int L = get16();
+            if (L < 2) return fail("corrupt JPEG (APP / COM)");
+            L -= 2;
+            if (m == 0xe0 && L >= 5) {
+                static const char tag[5] = {'J', 'F', 'I', 'F', 0};
+                bool ok = true;
+                for (char t : tag) if (get8() != (uint8_t)t) ok = false;
+                L -= 5;
+                if (ok) jfif = true;
+            } else if (m == 0xee && L >= 12) {
+                static const char tag[6] = {'A', 'd', 'o', 'b', 'e', 0};
+                bool ok = true;
+                for (char t : tag) if (get8() != (uint8_t)t) ok = false;
+                L -= 6;
+                if (ok) { get8(); get16(); get16(); adobe_transform = get8(); L -= 6; }
+            }
+            pos = L < 0 ? n : (pos + (size_t)L > n ? n : pos + (size_t)L);
+            return true;
+        }
+        return fail("unsupported JPEG (lossless, hierarchical or arithmetic-coded frame, or an unknown marker)");
+    }
+
+    bool frame_header() {
+        const int Lf = get16();
+        if (Lf < 11) return fail("corrupt JPEG (SOF)");
+        if (get8() != 8) return fail("JPEG sample precision other than 8 bit");
+        H = get16(); W = get16();
+        if (H == 0) return fail("JPEG with delayed height is not supported");
+        if (W == 0) return fail("corrupt JPEG (width 0)");
+        ncomp = get8();
+        if (ncomp != 1 && ncomp != 3 && ncomp != 4) return fail("corrupt JPEG (component count)");
+        if (Lf != 8 + 3 * ncomp) return fail("corrupt JPEG (SOF)");
+        rgb_ids = 0;
+        for (int i = 0; i < ncomp; ++i) {
+            JpegComp& c = comp[i];
+            c.id = get8();
+            if (ncomp == 3 && c.id == "RGB"[i]) ++rgb_ids;
+            const int q = get8();
+            c.h = q >> 4; c.v = q & 15; c.tq = get8();
+            if (c.h < 1 || c.h > 4 || c.v < 1 || c.v > 4 || c.tq > 3) return fail("corrupt JPEG (sampling factors)");
+        }
+        if ((uint64_t)W * (uint64_t)H * (uint64_t)ncomp > 0x7fffffffull) return fail("JPEG too large");
+        hmax = vmax = 1;
+        for (int i = 0; i < ncomp; ++i) { hmax = comp[i].h > hmax ? comp[i].h : hmax; vmax = comp[i].v > vmax ? comp[i].v : vmax; }
+        for (int i = 0; i < ncomp; ++i) if (hmax % comp[i].h || vmax % comp[i].v) return fail("JPEG with fractional sampling ratios is not supported");
+        mcu_x = (W + 8 * hmax - 1) / (8 * hmax);
+        mcu_y = (H + 8 * vmax - 1) / (8 * vmax);
+        for (int i = 0; i < ncomp; ++i) {
+            JpegComp& c = comp[i];
+            c.x = (W * c.h + hmax - 1) / hmax;
+            c.y = (H * c.v + vmax - 1) / vmax;
+            c.w2 = mcu_x * c.h * 8;
+            c.h2 = mcu_y * c.v * 8;
+            c.data.assign((size_t)c.w2 * c.h2, 0);
+            if (progressive) { c.coeff_w = c.w2 / 8; c.coeff.assign((size_t)c.w2 * c.h2, 0); }
+        }
+        return true;
+    }
+
+    bool scan_header() {
+        const int Ls = get16();
+        scan_n = get8();
+        if (scan_n < 1 || scan_n > 4 || scan_n > ncomp) return fail("corrupt JPEG (SOS)");
+        if (Ls != 6 + 2 * scan_n) return fail("corrupt JPEG (SOS)");
+        for (int i = 0; i < scan_n; ++i) {
+            const int id = get8(), q = get8();
+            int which = 0;
+            while (which < ncomp && comp[which].id != id) ++which;
+            if (which == ncomp) return fail("corrupt JPEG (SOS component)");
+            comp[which].hd = q >> 4; comp[which].ha = q & 15;
+            if (comp[which].hd > 3 || comp[which].ha > 3) return fail("corrupt JPEG (SOS table)");
+            order[i] = which;
+        }
+        spec_start = get8(); spec_end = get8();
+        const int aa = get8();
+        succ_high = aa >> 4; succ_low = aa & 15;
+        if (progressive) {
+            if (spec_start > 63 || spec_end > 63 || spec_start > spec_end || succ_high > 13 || succ_low > 13) return fail("corrupt JPEG (SOS)");
+        } else {
+            if (spec_start != 0 || succ_high != 0 || succ_low != 0) return fail("corrupt JPEG (SOS)");
+            spec_end = 63;
+        }
+        return true;
+    }
+
+    static const uint8_t* zigzag() {   // 15 more entries so that a corrupt run cannot index past the block
+        static const uint8_t zz[79] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                                       35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63,
+                                       63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
+        return zz;
+    }
+
+    bool block_sequential(int16_t d[64], JpegComp& c) {
+        const uint8_t* zz = zigzag();
+        const JpegHuff& ac = hac[c.ha];
+        const uint16_t* dq = dequant[c.tq];
+        if (bits < 16) grow();
+        const int t = huff(hdc[c.hd]);
+        if (t < 0 || t > 15) return fail("corrupt JPEG data");
+        std::memset(d, 0, 64 * sizeof(int16_t));
+        const int diff = t ? extend(t) : 0;
+        c.dc_pred += diff;
+        d[0] = (int16_t)(c.dc_pred * dq[0]);
+        int k = 1;
+        do {
+            if (bits < 16) grow();
+            const int r = ac.fast_ac[buf >> 23];
+            if (r) {
+                k += (r >> 4) & 15;
+                const int s = r & 15;
+                if (s > bits) return fail("corrupt JPEG data");
+                buf <<= s; bits -= s;
+                const int z = zz[k++];
+                d[z] = (int16_t)((r >> 8) * dq[z]);
+            } else {
+                const int rs = huff(ac);
+                if (rs < 0) return fail("corrupt JPEG data");
+                const int s = rs & 15, run = rs >> 4;
+                if (s == 0) { if (rs != 0xf0) break; k += 16; }
+                else { k += run; const int z = zz[k++]; d[z] = (int16_t)(extend(s) * dq[z]); }
+            }
+        } while (k < 64);
+        return true;
+    }
+    bool block_prog_dc(int16_t d[64], JpegComp& c) {
+        if (spec_end != 0) return fail("corrupt JPEG (DC scan with AC band)");
+        if (bits < 16) grow();
+        if (succ_high == 0) {
+            std::memset(d, 0, 64 * sizeof(int16_t));
+            const int t = huff(hdc[c.hd]);
+            if (t < 0 || t > 15) return fail("corrupt JPEG data");
+            const int diff = t ? extend(t) : 0;
+            c.dc_pred += diff;
+            d[0] = (int16_t)(c.dc_pred * (1 << succ_low));
+        } else if (take(1)) d[0] = (int16_t)(d[0] + (int16_t)(1 << succ_low));
+        return true;
+    }
+    bool block_prog_ac(int16_t d[64], JpegComp& c) {
+        const uint8_t* zz = zigzag();
+        const JpegHuff& ac = hac[c.ha];
+        if (spec_start == 0) return fail("corrupt JPEG (AC scan with DC)");
+        if (succ_high == 0) {
+            if (eob_run) { --eob_run; return true; }
+            int k = spec_start;
+            do {
+                if (bits < 16) grow();
+                const int r = ac.fast_ac[buf >> 23];
+                if (r) {
+                    k += (r >> 4) & 15;
+                    const int s = r & 15;
+                    if (s > bits) return fail("corrupt JPEG data");
+                    buf <<= s; bits -= s;
+                    d[zz[k++]] = (int16_t)((r >> 8) * (1 << succ_low));
+                } else {
+                    const int rs = huff(ac);
+                    if (rs < 0) return fail("corrupt JPEG data");
+                    const int s = rs & 15, run = rs >> 4;
+                    if (s == 0) {
+                        if (run < 15) { eob_run = 1 << run; if (run) eob_run += take(run); --eob_run; break; }
+                        k += 16;
+                    } else { k += run; d[zz[k++]] = (int16_t)(extend(s) * (1 << succ_low)); }
+                }
+            } while (k <= spec_end);
+            return true;
+        }
+        const int16_t bit = (int16_t)(1 << succ_low);
+        auto refine = [&](int16_t& v) { if (take(1) && (v & bit) == 0) v = (int16_t)(v > 0 ? v + bit : v - bit); };
+        if (eob_run) {
+            --eob_run;
+            for (int k = spec_start; k <= spec_end; ++k) { int16_t& v = d[zz[k]]; if (v != 0) refine(v); }
+            return true;
+        }
+        int k = spec_start;
+        do {
+            const int rs = huff(ac);
+            if (rs < 0) return fail("corrupt JPEG data");
+            int s = rs & 15, run = rs >> 4;
+            if (s == 0) {
+                if (run < 15) { eob_run = (1 << run) - 1; if (run) eob_run += take(run); run = 64; }
+            } else {
+                if (s != 1) return fail("corrupt JPEG data");
+                s = take(1) ? bit : -bit;
+            }
+            while (k <= spec_end) {   // skip `run` zero coefficients, refining the non-zero ones on the way
+                int16_t& v = d[zz[k++]];
+                if (v != 0) refine(v);
+                else { if (run == 0) { v = (int16_t)s; break; } --run; }
+            }
+        } while (k <= spec_end);
+        return true;
+    }
+
+    // 1-D pass of the integer inverse DCT on s[0..7]; returns the even part in x[] and the odd part in t[]
+    static void idct_1d(const int s[8], int x[4], int t[4]) {
+        int p2 = s[2], p3 = s[6];
+        int p1 = (p2 + p3) * 2217;
+        const int t2 = p1 + p3 * -7567, t3 = p1 + p2 * 3135;
+        p2 = s[0]; p3 = s[4];
+        const int t0 = (p2 + p3) * 4096, t1 = (p2 - p3) * 4096;
+        x[0] = t0 + t3; x[3] = t0 - t3; x[1] = t1 + t2; x[2] = t1 - t2;
+        int o0 = s[7], o1 = s[5], o2 = s[3], o3 = s[1];
+        p3 = o0 + o2;
+        int p4 = o1 + o3;
+        p1 = o0 + o3; p2 = o1 + o2;
+        const int p5 = (p3 + p4) * 4816;
+        o0 *= 1223; o1 *= 8410; o2 *= 12586; o3 *= 6149;
+        p1 = p5 + p1 * -3685; p2 = p5 + p2 * -10497;
+        p3 *= -8034; p4 *= -1597;
+        t[3] = o3 + p1 + p4; t[2] = o2 + p2 + p3; t[1] = o1 + p2 + p4; t[0] = o0 + p1 + p3;
+    }
+    static uint8_t clamp8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+    static void idct_block(uint8_t* out, int stride, const int16_t d[64]) {
+        int val[64];
+        for (int i = 0; i < 8; ++i) {   // columns
+            const int16_t* c = d + i;
+            int* v = val + i;
+            if (!(c[8] | c[16] | c[24] | c[32] | c[40] | c[48] | c[56])) {
+                const int dc = c[0] * 4;
+                for (int r = 0; r < 8; ++r) v[8 * r] = dc;
+                continue;
+            }
+            const int s[8] = {c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56]};
+            int x[4], t[4];
+            idct_1d(s, x, t);
+            for (int q = 0; q < 4; ++q) x[q] += 512;
+            v[0] = (x[0] + t[3]) >> 10; v[56] = (x[0] - t[3]) >> 10;
+            v[8] = (x[1] + t[2]) >> 10; v[48] = (x[1] - t[2]) >> 10;
+            v[16] = (x[2] + t[1]) >> 10; v[40] = (x[2] - t[1]) >> 10;
+            v[24] = (x[3] + t[0]) >> 10; v[32] = (x[3] - t[0]) >> 10;
+        }
+        for (int i = 0; i < 8; ++i) {   // rows
+            int x[4], t[4];
+            idct_1d(val + 8 * i, x, t);
+            for (int q = 0; q < 4; ++q) x[q] += 65536 + (128 << 17);
+            uint8_t* o = out + (size_t)stride * i;
+            o[0] = clamp8((x[0] + t[3]) >> 17); o[7] = clamp8((x[0] - t[3]) >> 17);
+            o[1] = clamp8((x[1] + t[2]) >> 17); o[6] = clamp8((x[1] - t[2]) >> 17);
+            o[2] = clamp8((x[2] + t[1]) >> 17); o[5] = clamp8((x[2] - t[1]) >> 17);
+            o[3] = clamp8((x[3] + t[0]) >> 17); o[4] = clamp8((x[3] - t[0]) >> 17);
+        }
+    }
+
+    // true = go on with the scan; false = the scan ends here (without being an error)
+    bool mcu_done() {
+        if (--todo > 0) return true;
+        if (bits < 24) grow();
+        if (!(marker >= 0xd0 && marker <= 0xd7)) return false;
+        reset();
+        return true;
+    }
+    bool entropy_scan() {
+        reset();
+        int16_t blk[64];
+        if (scan_n == 1) {   // non-interleaved: the component's own blocks in raster order
+            JpegComp& c = comp[order[0]];
+            const int bw = (c.x + 7) >> 3, bh = (c.y + 7) >> 3;
+            for (int j = 0; j < bh; ++j)
+                for (int i = 0; i < bw; ++i) {
+                    if (!progressive) {
+                        if (!block_sequential(blk, c)) return false;
+                        idct_block(&c.data[(size_t)c.w2 * j * 8 + (size_t)i * 8], c.w2, blk);
+                    } else {
+                        int16_t* d = &c.coeff[64 * ((size_t)i + (size_t)j * c.coeff_w)];
+                        if (!(spec_start == 0 ? block_prog_dc(d, c) : block_prog_ac(d, c))) return false;
+                    }
+                    if (!mcu_done()) return true;
+                }
+            return true;
+        }
+        for (int j = 0; j < mcu_y; ++j)
+            for (int i = 0; i < mcu_x; ++i) {
+                for (int k = 0; k < scan_n; ++k) {
+                    JpegComp& c = comp[order[k]];
+                    for (int y = 0; y < c.v; ++y)
+                        for (int x = 0; x < c.h; ++x) {
+                            const int bx = i * c.h + x, by = j * c.v + y;
+                            if (!progressive) {
+                                if (!block_sequential(blk, c)) return false;
+                                idct_block(&c.data[(size_t)c.w2 * by * 8 + (size_t)bx * 8], c.w2, blk);
+                            } else if (!block_prog_dc(&c.coeff[64 * ((size_t)bx + (size_t)by * c.coeff_w)], c)) return false;
+                        }
+                }
+                if (!mcu_done()) return true;
+            }
+        return true;
+    }
+    void finish_progressive() {
+        for (int ci = 0; ci < ncomp; ++ci) {
+            JpegComp& c = comp[ci];
+            const int bw = (c.x + 7) >> 3, bh = (c.y + 7) >> 3;
+            for (int j = 0; j < bh; ++j)
+                for (int i = 0; i < bw; ++i) {
+                    int16_t* d = &c.coeff[64 * ((size_t)i + (size_t)j * c.coeff_w)];
+                    for (int q = 0; q < 64; ++q) d[q] = (int16_t)(d[q] * dequant[c.tq][q]);
+                    idct_block(&c.data[(size_t)c.w2 * j * 8 + (size_t)i * 8], c.w2, d);
+                }
+        }
+    }
+
+    bool decode_planes() {
+        if (get_marker() != 0xd8) return fail("not a JPEG");
+        int m = get_marker();
+        while (!(m == 0xc0 || m == 0xc1 || m == 0xc2)) {
+            if (!table_marker(m)) return false;
+            m = get_marker();
+            while (m == 0xff) {   // padding between segments
+                if (pos >= n) return fail("JPEG without a frame header");
+                m = get_marker();
+            }
+        }
+        progressive = m == 0xc2;
+        if (!frame_header()) return false;
+        m = get_marker();
+        while (m != 0xd9) {
+            if (m == 0xda) {
+                if (!scan_header() || !entropy_scan()) return false;
+                if (marker == 0xff) {   // skip whatever follows the scan up to the next thing that looks like a marker
+                    while (pos < n) {
+                        int x = get8();
+                        while (x == 0xff) {
+                            if (pos >= n) break;
+                            x = get8();
+                            if (x != 0x00 && x != 0xff) { marker = x; break; }
+                        }
+                        if (marker != 0xff) break;
+                    }
+                }
+                m = get_marker();
+                if (m >= 0xd0 && m <= 0xd7) m = get_marker();
+            } else if (m == 0xdc) {
+                const int Ld = get16(), NL = get16();
+                if (Ld != 4 || NL != H) return fail("corrupt JPEG (DNL)");
+                m = get_marker();
+            } else {
+                if (!table_marker(m)) { why.clear(); break; }   // whatever was decoded so far is the image
+                m = get_marker();
+            }
+        }
+        if (progressive) finish_progressive();
         return true;
     }
 };
 
+inline uint8_t jpeg_mul255(uint8_t a, uint8_t b) { const unsigned t = (unsigned)a * b + 128u; return (uint8_t)((t + (t >> 8)) >> 8); }
+
 inline bool load_jpeg(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
-    static const uint8_t zz[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
-                                   35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
     if (f.size() < 4 || f[0] != 0xff || f[1] != 0xd8) return false;
-    struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0, pw = 0, ph = 0; std::vector<uint8_t> plane; };
-    uint16_t quant[4][64] = {};
-    JpegHuff dc[4], ac[4];
-    std::vector<Comp> comps;
-    int W = 0, H = 0, ri = 0;
-    size_t pos = 2;
-    auto be16 = [&](size_t o) { return (int)((f[o] << 8) | f[o + 1]); };
-    for (;;) {
-        while (pos < f.size() && f[pos] != 0xff) ++pos;
-        while (pos < f.size() && f[pos] == 0xff) ++pos;
-        if (pos >= f.size()) { why = "JPEG without image data"; return false; }
-        const int m = f[pos++];
-        if (m == 0xd9) { why = "JPEG without image data"; return false; }
-        if (m == 0x01 || (m >= 0xd0 && m <= 0xd7)) continue;
-        if (pos + 2 > f.size()) { why = "truncated JPEG"; return false; }
-        const int len = be16(pos);
-        if (len < 2 || pos + (size_t)len > f.size()) { why = "truncated JPEG"; return false; }
-        const size_t seg = pos + 2, end = pos + (size_t)len;
-        if (m == 0xc2 || m == 0xc6 || m == 0xca || m == 0xce) { why = "progressive JPEG is not supported (save it as baseline, or as PNG)"; return false; }
-        if (m == 0xc3 || m == 0xc5 || m == 0xc7 || (m >= 0xc9 && m <= 0xcf && m != 0xcc)) { why = "lossless / arithmetic-coded JPEG is not supported"; return false; }
-        if (m == 0xc0 || m == 0xc1) {
-            if (len < 8 || f[seg] != 8) { why = "JPEG sample precision other than 8 bit"; return false; }
-            H = be16(seg + 1); W = be16(seg + 3);
-            const int nf = f[seg + 5];
-            if (W <= 0 || H <= 0 || !(nf == 1 || nf == 3) || len < 8 + 3 * nf) { why = nf == 4 ? "4-component (CMYK) JPEG is not supported" : "bad JPEG frame header"; return false; }
-            comps.assign((size_t)nf, Comp());
-            for (int i = 0; i < nf; ++i) {
-                Comp& c = comps[(size_t)i];
-                c.id = f[seg + 6 + 3 * (size_t)i]; c.h = f[seg + 7 + 3 * (size_t)i] >> 4; c.v = f[seg + 7 + 3 * (size_t)i] & 15; c.tq = f[seg + 8 + 3 * (size_t)i] & 3;
-                if (c.h < 1 || c.h > 4 || c.v < 1 || c.v > 4) { why = "bad JPEG sampling factors"; return false; }
-            }
-        } else if (m == 0xdb) {
-            size_t q = seg;
-            while (q < end) {
-                const int pq = f[q] >> 4, tq = f[q] & 15;
-                ++q;
-                if (tq > 3 || q + (size_t)(pq ? 128 : 64) > end) { why = "bad JPEG quantisation table"; return false; }
-                for (int i = 0; i < 64; ++i) { quant[tq][zz[i]] = (uint16_t)(pq ? be16(q + 2 * (size_t)i) : f[q + (size_t)i]); }
-                q += pq ? 128 : 64;
-            }
-        } else if (m == 0xc4) {
-            size_t q = seg;
-            while (q < end) {
-                const int tc = f[q] >> 4, th = f[q] & 15;
-                if (tc > 1 || th > 3 || q + 17 > end) { why = "bad JPEG Huffman table"; return false; }
-                int nv = 0;
-                for (int i = 0; i < 16; ++i) nv += f[q + 1 + (size_t)i];
-                if (nv > 256 || q + 17 + (size_t)nv > end) { why = "bad JPEG Huffman table"; return false; }
-                (tc ? ac[th] : dc[th]).build(&f[q + 1], &f[q + 17], nv);
-                q += 17 + (size_t)nv;
-            }
-        } else if (m == 0xdd) {
-            ri = be16(seg);
-        } else if (m == 0xda) {
-            const int ns = f[seg];
-            if (comps.empty() || ns != (int)comps.size() || len < 6 + 2 * ns) { why = "JPEG with several scans is not supported"; return false; }
-            for (int i = 0; i < ns; ++i) {
-                const int cs = f[seg + 1 + 2 * (size_t)i], tdta = f[seg + 2 + 2 * (size_t)i];
-                bool found = false;
-                for (Comp& c : comps) if (c.id == cs) { c.td = tdta >> 4; c.ta = tdta & 15; found = true; }
-                if (!found || (tdta >> 4) > 3 || (tdta & 15) > 3) { why = "bad JPEG scan header"; return false; }
-            }
-            pos = end;
-            break;
-        }
-        pos = end;
+    JpegDec z{f.data(), f.size()};
+    std::memset(z.dequant, 0, sizeof(z.dequant));
+    for (JpegHuff& h : z.hdc) { std::memset(&h, 0, sizeof(h)); }
+    for (JpegHuff& h : z.hac) { std::memset(&h, 0, sizeof(h)); }
+    if (!z.decode_planes()) { why = z.why.empty() ? "corrupt JPEG" : z.why; return false; }
+    const int W = z.W, H = z.H, nc = z.ncomp;
+    const bool is_rgb = nc == 3 && (z.rgb_ids == 3 || (z.adobe_transform == 0 && !z.jfif));
+    // per component: the two source rows an output row is blended from, advanced as in a streaming decoder
+    struct Up { int hs, vs, ystep, w_lores, ypos; const uint8_t* line0; const uint8_t* line1; std::vector<uint8_t> buf; };
+    Up up[4];
+    for (int k = 0; k < nc; ++k) {
+        const JpegComp& c = z.comp[k];
+        up[k].hs = z.hmax / c.h; up[k].vs = z.vmax / c.v;
+        up[k].ystep = up[k].vs >> 1;
+        up[k].w_lores = (W + up[k].hs - 1) / up[k].hs;
+        up[k].ypos = 0;
+        up[k].line0 = up[k].line1 = c.data.data();
+        up[k].buf.assign((size_t)W + 3 + 8, 0);
     }
-    int hmax = 1, vmax = 1;
-    for (const Comp& c : comps) { hmax = c.h > hmax ? c.h : hmax; vmax = c.v > vmax ? c.v : vmax; if (!dc[c.td].set || !ac[c.ta].set) { why = "JPEG scan refers to a missing Huffman table"; return false; } }
-    const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
-    for (Comp& c : comps) { c.pw = mcux * c.h * 8; c.ph = mcuy * c.v * 8; c.plane.assign((size_t)c.pw * c.ph, 0); }
-    float cosm[8][8];
-    for (int x = 0; x < 8; ++x)
-        for (int u = 0; u < 8; ++u) cosm[x][u] = (u == 0 ? 0.70710678118654752f : 1.0f) * std::cos((float)((2 * x + 1) * u) * 3.14159265358979323846f / 16.0f);
-    JpegBits b(f.data(), f.size(), pos);
-    int until_restart = ri, next_rst = 0;
-    for (int my = 0; my < mcuy; ++my)
-        for (int mx = 0; mx < mcux; ++mx) {
-            if (ri && until_restart == 0) {
-                if (!b.restart(next_rst)) { why = "JPEG restart marker missing"; return false; }
-                next_rst = (next_rst + 1) & 7; until_restart = ri;
-                for (Comp& c : comps) c.pred = 0;
-            }
-            for (Comp& c : comps)
-                for (int by = 0; by < c.v; ++by)
-                    for (int bx = 0; bx < c.h; ++bx) {
-                        float co[64] = {0};
-                        const int s = b.decode(dc[c.td]);
-                        if (s < 0 || s > 11) { why = "corrupt JPEG data"; return false; }
-                        int diff = s ? b.receive(s) : 0;
-                        if (s && diff < (1 << (s - 1))) diff -= (1 << s) - 1;  // EXTEND
-                        c.pred += diff;
-                        co[0] = (float)(c.pred * (int)quant[c.tq][0]);
-                        for (int k = 1; k < 64;) {
-                            const int rs = b.decode(ac[c.ta]);
-                            if (rs < 0) { why = "corrupt JPEG data"; return false; }
-                            const int r = rs >> 4, sz = rs & 15;
-                            if (sz == 0) { if (r == 15) { k += 16; continue; } break; }  // ZRL / EOB
-                            k += r;
-                            if (k > 63) { why = "corrupt JPEG data"; return false; }
-                            int v = b.receive(sz);
-                            if (v < (1 << (sz - 1))) v -= (1 << sz) - 1;
-                            co[zz[k]] = (float)(v * (int)quant[c.tq][zz[k]]);
-                            ++k;
-                        }
-                        if (b.bad) { why = "truncated JPEG data"; return false; }
-                        float tmp[64];
-                        for (int y = 0; y < 8; ++y)       // rows: tmp[y][x] = sum_u cos[x][u] co[y][u]
-                            for (int x = 0; x < 8; ++x) { float a = 0; for (int u = 0; u < 8; ++u) a += cosm[x][u] * co[8 * y + u]; tmp[8 * y + x] = a; }
-                        const int ox = (mx * c.h + bx) * 8, oy = (my * c.v + by) * 8;
-                        for (int x = 0; x < 8; ++x)       // columns
-                            for (int y = 0; y < 8; ++y) {
-                                float a = 0;
-                                for (int v = 0; v < 8; ++v) a += cosm[y][v] * tmp[8 * v + x];
-                                const long q = std::lround(a * 0.25f + 128.0f);
-                                c.plane[(size_t)(oy + y) * c.pw + (size_t)(ox + x)] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
-                            }
-                    }
-            if (ri) --until_restart;
-        }
+    auto div4 = [](int v) { return (uint8_t)(v >> 2); };
+    auto div16 = [](int v) { return (uint8_t)(v >> 4); };
     std::vector<uint8_t> top((size_t)4 * W * H);
-    for (int y = 0; y < H; ++y)
-        for (int x = 0; x < W; ++x) {
-            uint8_t* d = &top[4 * ((size_t)y * W + x)];
-            auto at = [&](const Comp& c) { return (float)c.plane[(size_t)(y * c.v / vmax) * c.pw + (size_t)(x * c.h / hmax)]; };
-            if (comps.size() == 1) { d[0] = d[1] = d[2] = (uint8_t)at(comps[0]); }
-            else {
-                const float Y = at(comps[0]), cb = at(comps[1]) - 128.0f, cr = at(comps[2]) - 128.0f;
-                const float rgb[3] = {Y + 1.402f * cr, Y - 0.344136f * cb - 0.714136f * cr, Y + 1.772f * cb};
-                for (int k = 0; k < 3; ++k) { const long q = std::lround(rgb[k]); d[k] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q)); }
+    const uint8_t* row[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int j = 0; j < H; ++j) {
+        for (int k = 0; k < nc; ++k) {
+            Up& r = up[k];
+            const bool bot = r.ystep >= (r.vs >> 1);
+            const uint8_t* nr = bot ? r.line1 : r.line0;   // the nearer source row
+            const uint8_t* fr = bot ? r.line0 : r.line1;
+            uint8_t* o = r.buf.data();
+            const int w = r.w_lores;
+            if (r.hs == 1 && r.vs == 1) row[k] = nr;
+            else if (r.hs == 1 && r.vs == 2) { for (int i = 0; i < w; ++i) o[i] = div4(3 * nr[i] + fr[i] + 2); row[k] = o; }
+            else if (r.hs == 2 && r.vs == 1) {
+                if (w == 1) o[0] = o[1] = nr[0];
+                else {
+                    o[0] = nr[0];
+                    o[1] = div4(nr[0] * 3 + nr[1] + 2);
+                    int i = 1;
+                    for (; i < w - 1; ++i) { const int c3 = 3 * nr[i] + 2; o[2 * i] = div4(c3 + nr[i - 1]); o[2 * i + 1] = div4(c3 + nr[i + 1]); }
+                    o[2 * i] = div4(nr[w - 2] * 3 + nr[w - 1] + 2);
+                    o[2 * i + 1] = nr[w - 1];
+                }
+                row[k] = o;
+            } else if (r.hs == 2 && r.vs == 2) {
+                if (w == 1) o[0] = o[1] = div4(3 * nr[0] + fr[0] + 2);
+                else {
+                    int t1 = 3 * nr[0] + fr[0];
+                    o[0] = div4(t1 + 2);
+                    for (int i = 1; i < w; ++i) {
+                        const int t0 = t1;
+                        t1 = 3 * nr[i] + fr[i];
+                        o[2 * i - 1] = div16(3 * t0 + t1 + 8);
+                        o[2 * i] = div16(3 * t1 + t0 + 8);
+                    }
+                    o[2 * w - 1] = div4(t1 + 2);
+                }
+                row[k] = o;
+            } else {
+                if (r.buf.size() < (size_t)w * r.hs) r.buf.resize((size_t)w * r.hs), o = r.buf.data();
+                for (int i = 0; i < w; ++i) for (int q = 0; q < r.hs; ++q) o[i * r.hs + q] = nr[i];
+                row[k] = o;
             }
-            d[3] = 255;
+            if (++r.ystep >= r.vs) {
+                r.ystep = 0;
+                r.line0 = r.line1;
+                if (++r.ypos < z.comp[k].y) r.line1 += z.comp[k].w2;
+            }
         }
+        uint8_t* out = &top[(size_t)4 * W * j];
+        auto ycc = [&](uint8_t* d, int Y, int cb, int cr) {
+            const int yf = (Y << 20) + (1 << 19);
+            cr -= 128; cb -= 128;
+            int r = yf + cr * 1470208;
+            int g = yf + cr * -748800 + (int)((uint32_t)(cb * -360960) & 0xffff0000u);
+            int b = yf + cb * 1858048;
+            r >>= 20; g >>= 20; b >>= 20;
+            d[0] = JpegDec::clamp8(r); d[1] = JpegDec::clamp8(g); d[2] = JpegDec::clamp8(b); d[3] = 255;
+        };
+        for (int i = 0; i < W; ++i) {
+            uint8_t* d = out + 4 * i;
+            if (nc == 1) { d[0] = d[1] = d[2] = row[0][i]; d[3] = 255; }
+            else if (nc == 3) {
+                if (is_rgb) { d[0] = row[0][i]; d[1] = row[1][i]; d[2] = row[2][i]; d[3] = 255; }
+                else ycc(d, row[0][i], row[1][i], row[2][i]);
+            } else if (z.adobe_transform == 0) {   // CMYK
+                const uint8_t k = row[3][i];
+                d[0] = jpeg_mul255(row[0][i], k); d[1] = jpeg_mul255(row[1][i], k); d[2] = jpeg_mul255(row[2][i], k); d[3] = 255;
+            } else if (z.adobe_transform == 2) {   // YCCK
+                ycc(d, row[0][i], row[1][i], row[2][i]);
+                const uint8_t k = row[3][i];
+                d[0] = jpeg_mul255((uint8_t)(255 - d[0]), k); d[1] = jpeg_mul255((uint8_t)(255 - d[1]), k); d[2] = jpeg_mul255((uint8_t)(255 - d[2]), k);
+            } else ycc(d, row[0][i], row[1][i], row[2][i]);   // four components without an Adobe tag: the fourth is ignored
+        }
+    }
     store_flipped(top, W, H, t);
     return true;
 }
 
 }  // namespace detail
 
-// Decodes an image file by content (PNG, BMP, PNM) or extension (TGA has no magic).  false + `why` if it cannot.
+// Decodes an image file by content, never by extension (like stbi_load).  false + `why` if it cannot.
+// Formats stb_image reads and this loader does not: GIF, PSD, PIC, Radiance HDR (such a map_Kd loads in the reference
+// and is "Error loading texture" / id -1 here).
 inline bool load_image(const std::string& path, Texture& t, std::string* why_out = nullptr) {
     std::vector<uint8_t> f;
     std::string why;
@@ -543,13 +1152,8 @@ inline bool load_image(const std::string& path, Texture& t, std::string* why_out
     else if (f.size() >= 2 && f[0] == 'B' && f[1] == 'M') ok = detail::load_bmp(f, t, why);
     else if (f.size() >= 2 && f[0] == 'P' && (f[1] == '5' || f[1] == '6')) ok = detail::load_pnm(f, t, why);
     else if (f.size() >= 3 && f[0] == 0xff && f[1] == 0xd8) ok = detail::load_jpeg(f, t, why);
-    else {
-        const size_t dot = path.rfind('.');
-        std::string ext = dot == std::string::npos ? "" : path.substr(dot + 1);
-        for (char& c : ext) c = (char)std::tolower((unsigned char)c);
-        if (ext == "tga") ok = detail::load_tga(f, t, why);
-        else why = "unknown image format";
-    }
+    else if (detail::tga_plausible(f)) ok = detail::load_tga(f, t, why);   // no magic number: tried last, like stb_image does
+    else why = "unknown image format";
     if (!ok && why.empty()) why = "not a valid image of its kind";
     if (why_out) *why_out = why;
     return ok;

@@ -76,6 +76,11 @@ public:
     CUDAMesh(const CUDAMesh&) = delete;
     CUDAMesh(CUDAMesh&& o) noexcept : _gas_handle(o._gas_handle) { o._gas_handle = 0; }
     CUDAMesh(rt3_context_t ctx, const Mesh& mesh) {
+        // the reference uploads whatever the loader produced and its closest-hit program reads normals[] / texcoords[] for every
+        // vertex (closehit_radiance.cu:71-75): a mesh whose .obj left some corner without vn / vt is out-of-bounds there (Q11)
+        for (unsigned k = 0; k < mesh.num_keys; ++k)
+            if (mesh.normals[k].size() != mesh.vertices[k].size() || mesh.texcoords[k].size() / 2 != mesh.vertices[k].size() / 3)
+                throw Exception("CUDAMesh: mesh has vertices without a normal or a texcoord (both are required, Q11)");
         std::vector<float> keys;
         for (unsigned k = 0; k < mesh.num_keys; ++k) keys.insert(keys.end(), mesh.vertices[k].begin(), mesh.vertices[k].end());
         RT3HOST_CHECK(rt3_mesh_create(ctx, keys.data(), (int)mesh.num_keys, (int)(mesh.vertices[0].size() / 3), mesh.indices.data(),

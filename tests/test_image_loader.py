@@ -402,8 +402,14 @@ def test_baseline_jpeg(exe, tmp_path):
         want = write_baseline_jpeg(p, img, **kw)
         got, err = decode(exe, p, tmp_path)
         assert got is not None, (tag, err)
+        # The decoder's exact bytes are pinned against the reference's stb_image in tests/test_loader_parity.py (integer
+        # IDCT, filtered chroma upsampling, fixed-point YCbCr).  `want` is a float model with replicated chroma: it only
+        # bounds the decode from the outside here - close where nothing is subsampled, the same picture elsewhere.
         diff = np.abs(got[..., :3].astype(np.int32) - want.astype(np.int32))
-        assert diff.max() <= 1 and diff.mean() < 0.02, (tag, diff.max(), diff.mean())   # float32 vs float64 IDCT: isolated +-1
+        if "sampling" not in kw:
+            assert diff.max() <= 4 and diff.mean() < 0.6, (tag, diff.max(), diff.mean())
+        else:
+            assert diff.mean() < 6, (tag, diff.mean())
         assert (got[..., 3] == 255).all()
         orig = img.astype(np.float64)
         if kw.get("grey"):
@@ -412,9 +418,9 @@ def test_baseline_jpeg(exe, tmp_path):
 
 
 def test_rejects_what_it_cannot_decode(exe, tmp_path):
-    p = str(tmp_path / "x.jpg"); open(p, "wb").write(b"\xff\xd8\xff\xc2" + struct.pack(">H", 17) + bytes(15) + b"\xff\xd9")
+    p = str(tmp_path / "x.jpg"); open(p, "wb").write(b"\xff\xd8\xff\xc9" + struct.pack(">H", 17) + bytes(15) + b"\xff\xd9")   # SOF9: arithmetic coding
     got, err = decode(exe, p, tmp_path)
-    assert got is None and "progressive" in err
+    assert got is None and "arithmetic" in err
     p = str(tmp_path / "y.jpg"); open(p, "wb").write(b"\xff\xd8\xff\xe0" + bytes(64))
     got, err = decode(exe, p, tmp_path)
     assert got is None
@@ -422,6 +428,22 @@ def test_rejects_what_it_cannot_decode(exe, tmp_path):
     p = str(tmp_path / "i.png"); write_png(p, rows, 2, 8, [0], interlace=2)
     got, err = decode(exe, p, tmp_path)
     assert got is None and "interlace" in err
+    # malformed headers must be refused before anything is indexed or allocated from them (bit depths 0 / 3 / 5 / 6 / 7,
+    # 16-bit palette, sub-byte RGB, absurd sizes)
+    for ctype, depth in ((0, 5), (0, 0), (3, 3), (0, 6), (3, 7), (3, 16), (2, 4), (6, 2), (4, 1)):
+        p = str(tmp_path / ("bad_%d_%d.png" % (ctype, depth)))
+        write_png(p, rows, ctype, 8, [0])
+        data = bytearray(open(p, "rb").read())
+        data[24] = depth; data[25] = ctype                             # IHDR depth / colour type (the CRC is not checked by the loader)
+        open(p, "wb").write(bytes(data))
+        got, err = decode(exe, p, tmp_path)
+        assert got is None and "bit depth" in err, (ctype, depth, err)
+    p = str(tmp_path / "huge.png"); write_png(p, rows, 2, 8, [0])
+    data = bytearray(open(p, "rb").read())
+    data[16:24] = struct.pack(">II", 60000, 60000)
+    open(p, "wb").write(bytes(data))
+    got, err = decode(exe, p, tmp_path)
+    assert got is None and "large" in err
     p = str(tmp_path / "t.png"); write_png(p, rows, 2, 8, [0])
     data = open(p, "rb").read()
     open(p, "wb").write(data[:len(data) // 2])

@@ -1,0 +1,154 @@
+"""N1 parity: this repo's loadOBJ (host/obj_loader.hpp + host/image_loader.hpp) returns the SAME Mesh / Texture lists as
+the reference's own loadOBJ (src/mesh.cpp:37-210 with its vendored tinyobjloader + stb_image), byte for byte.
+
+The goldens under tests/golden/loader/cases/*/ are dumps written by the reference's loader compiled where it lies
+(oracle/Makefile target `ref_loader`; generator tests/golden/loader/make_loader_goldens.py).  When /root/reference is
+present (the build container) the goldens are re-derived from it and a few hundred random .obj files are compared
+loader against loader; on a machine without the reference only the committed goldens are used."""
+import os
+import random
+import subprocess
+import sys
+
+import pytest
+
+import loader_dump
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = os.path.join(ROOT, "tests", "golden", "loader", "cases")
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden", "loader"))
+import make_loader_goldens as gen  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def own_dumper(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("own_loader") / "dump_own_loader")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "tools", "dump_own_loader.cpp")], check=True)
+    return exe
+
+
+@pytest.fixture(scope="module")
+def ref_dumper():
+    """the reference's loader, built from /root/reference where it lies; None on a machine without the reference"""
+    if not os.path.isdir("/root/reference/src"):
+        return None
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref_loader"], check=True, capture_output=True)
+    return gen.REF_DUMPER
+
+
+JOBS = gen.jobs()
+
+
+def test_fixture_inventory():
+    names = {j[0] for j in JOBS}
+    assert {"polygons", "groups", "syntax", "keyframes", "scenes", "mtl_textures", "textures_png", "textures_other", "textures_jpeg"} <= names
+    for case, golden, _ in JOBS:
+        assert os.path.exists(os.path.join(CASES, case, golden)), "golden missing: run tests/golden/loader/make_loader_goldens.py"
+    # what the goldens hold, so that an empty golden cannot pass for a match
+    meshes, tex = loader_dump.parse(os.path.join(CASES, "polygons", "golden.rt3l"))
+    assert len(meshes) == 2 and sum(m["nt"] for m in meshes) > 100
+    meshes, tex = loader_dump.parse(os.path.join(CASES, "textures_jpeg", "golden.rt3l"))
+    assert len(tex) >= 35 and len(meshes) >= len(tex)
+    meshes, tex = loader_dump.parse(os.path.join(CASES, "textures_png", "golden.rt3l"))
+    assert len(tex) == len(meshes) >= 20
+    meshes, tex = loader_dump.parse(os.path.join(CASES, "keyframes", "golden.rt3l"))
+    assert all(m["num_keys"] == 3 for m in meshes)
+
+
+@pytest.mark.parametrize("case,golden,paths", JOBS, ids=["%s/%s" % (j[0], j[1]) for j in JOBS])
+def test_own_loader_reproduces_the_reference_goldens(case, golden, paths, own_dumper, tmp_path):
+    out = str(tmp_path / "own.rt3l")
+    rc, err = gen.run(case, paths, own_dumper, out)
+    assert rc == 0, err
+    want = os.path.join(CASES, case, golden)
+    if open(out, "rb").read() != open(want, "rb").read():
+        pytest.fail("%s: %s" % (case, loader_dump.diff(want, out) or "dumps differ"))
+
+
+@pytest.mark.parametrize("case,golden,paths", JOBS, ids=["%s/%s" % (j[0], j[1]) for j in JOBS])
+def test_goldens_are_what_the_reference_loader_returns(case, golden, paths, ref_dumper, tmp_path):
+    if ref_dumper is None:
+        pytest.skip("/root/reference not present")
+    out = str(tmp_path / "ref.rt3l")
+    rc, err = gen.run(case, paths, ref_dumper, out)
+    assert rc == 0, err
+    assert open(out, "rb").read() == open(os.path.join(CASES, case, golden), "rb").read(), "committed golden is stale"
+
+
+# ---------------------------------------------------------------------------------------------- loader against loader
+def _num(r):
+    x = r.uniform(-10, 10)
+    return ["%.9g" % x, "%.17g" % x, "%d" % int(x), "%.3e" % x, ("%.12f" % x).rstrip("0"), "%+.5f" % x, "%.10E" % (x * 1e-3),
+            ("%.6f" % (x / 10)).replace("0.", ".", 1) if abs(x) < 10 else "%.4f" % x][r.randrange(8)]
+
+
+def _random_obj(r, path):
+    import math
+    base = os.path.splitext(path)[0]
+    eol = r.choice(["\n", "\r\n", "\n"])
+    nmat = r.randrange(1, 4)
+    with open(base + ".mtl", "w", newline="") as m:
+        for i in range(nmat):
+            m.write("newmtl m%d%s" % (i, eol))
+            for key, n, p in (("Kd", 3, 0.8), ("Ke", 3, 0.5), ("Pr", 1, 0.3), ("Ni", 1, 0.3), ("Tf", 3, 0.3), ("aniso", 1, 0.3)):
+                if r.random() < p:
+                    m.write("%s %s%s" % (key, " ".join(_num(r) for _ in range(n)), eol))
+            if r.random() < 0.2:
+                m.write("map_Kd -s 1 1 1 missing.png%s" % eol)
+    nv = r.randrange(6, 40)
+    L = ["mtllib %s.mtl" % os.path.basename(base)] + ["v %s %s %s" % (_num(r), _num(r), _num(r)) for _ in range(nv)]
+    nn, ntx = r.randrange(1, 6), r.randrange(1, 6)
+    L += ["vn %s %s %s" % (_num(r), _num(r), _num(r)) for _ in range(nn)] + ["vt %s %s" % (_num(r), _num(r)) for _ in range(ntx)] + ["usemtl m0"]
+    planar = r.random() < 0.5
+    for f in range(r.randrange(3, 25)):
+        q = r.random()
+        if q < 0.1:
+            L.append(r.choice(["o obj%d" % f, "g grp%d" % f, "g"]))
+        if q > 0.8:
+            L.append("usemtl m%d" % r.randrange(nmat))
+        if q > 0.95:
+            L += ["v %s %s %s" % (_num(r), _num(r), _num(r)) for _ in range(3)]
+            nv += 3
+        k = r.choice([3, 3, 4, 4, 5, 6, 7, 9])
+        style = r.randrange(4) if r.random() < 0.15 else 3
+        if planar and k > 4 and r.random() < 0.7:   # a planar, possibly concave polygon with its own vertices
+            ax, ids = r.randrange(3), []
+            for i in range(k):
+                a = 2 * math.pi * i / k
+                rad = r.uniform(0.3, 1.0) if r.random() < 0.5 else 1.0
+                p = [rad * math.cos(a), rad * math.sin(a)]
+                p.insert(ax, r.uniform(-0.01, 0.01) if r.random() < 0.3 else 0.5)
+                L.append("v %.9g %.9g %.9g" % tuple(p))
+                nv += 1
+                ids.append(nv)
+            if r.random() < 0.5:
+                ids.reverse()
+        else:
+            ids = [r.randrange(1, nv + 1) for _ in range(k)]
+        toks = []
+        for i in ids:
+            v = i if r.random() < 0.8 else i - nv - 1
+            t, n = r.randrange(1, ntx + 1), r.randrange(1, nn + 1)
+            if r.random() < 0.1:
+                t = t - ntx - 1
+            toks.append(["%d" % v, "%d/%d" % (v, t), "%d//%d" % (v, n), "%d/%d/%d" % (v, t, n)][style])
+        L.append("f " + r.choice([" ", "  ", "\t"]).join(toks) + r.choice(["", " ", ""]))
+    with open(path, "w", newline="") as f:
+        f.write(eol.join(L) + r.choice([eol, ""]))
+
+
+def test_random_obj_files_loader_against_loader(own_dumper, ref_dumper, tmp_path):
+    if ref_dumper is None:
+        pytest.skip("/root/reference not present")
+    compared = 0
+    for seed in range(250):
+        p = str(tmp_path / "fz.obj")
+        _random_obj(random.Random(seed), p)
+        a = subprocess.run([ref_dumper, str(tmp_path / "ref.bin"), p], capture_output=True)
+        b = subprocess.run([own_dumper, str(tmp_path / "own.bin"), p], capture_output=True)
+        assert (a.returncode == 0) == (b.returncode == 0), (seed, a.returncode, b.returncode, b.stderr[-200:])
+        if a.returncode == 0:
+            d = loader_dump.diff(str(tmp_path / "ref.bin"), str(tmp_path / "own.bin"))
+            assert d == "", (seed, d)
+            compared += 1
+    assert compared >= 200
