@@ -1045,6 +1045,7 @@ int rt3o_reset_stats(rt3o_scene* s) {
 }
 
 void rt3o_set_chain_sum(int on) { g_chain_sum = on != 0; }
+void rt3o_set_libm_sincos(int on) { g_libm_sincos = on != 0; }
 
 // ---------------------------------------------------------------- KAT hooks
 uint32_t rt3o_kat_tea4(uint32_t a, uint32_t b) { return tea4(a, b); }

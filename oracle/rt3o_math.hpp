@@ -87,11 +87,18 @@ static inline void sincos_2pi(float u, float& s, float& c) {
     }
 }
 
-// src/util/sampling.h:27-37 (with the sincos substitution above)
+// src/util/sampling.h:27-37 (with the sincos substitution above = deviation D1).  g_libm_sincos switches D1 OFF: phi =
+// 2 pi u2 and the C library's cosf / sinf, i.e. the reference's own text compiled for the host — the mode in which the
+// oracle is compared BIT FOR BIT with the reference's device programs run on the host shim (tests/test_reference_pins.py).
+inline bool g_libm_sincos = false;
 static inline f3 sample_cosine_hemisphere(float u1, float u2) {
     const float r = sqrtf(u1);
     float s, c;
-    sincos_2pi(u2, s, c);
+    if (g_libm_sincos) {
+        const float phi = 2.0f * 3.14159265358979323846f * u2;
+        c = cosf(phi);
+        s = sinf(phi);
+    } else sincos_2pi(u2, s, c);
     f3 p;
     p.x = r * c;
     p.y = r * s;
