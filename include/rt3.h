@@ -82,9 +82,14 @@ int rt3_set_option(rt3_context_t ctx, const char* key, int value); /* tuning swi
  * builds the BLAS (there: optixAccelBuild + compaction; here: GPU LBVH -> compressed BVH8).
  * verts [num_keys][nv][3]: num_keys > 1 = vertex-key (deformation) motion blur, keys spread evenly over ray
  * time [0,1] like the reference's motionOptions (cuda_mesh.h:82-88), per-vertex linear interpolation; idx [nt][3],
- * normals [nv][3], uvs [nv][2] (both required, like the reference, Q11). */
+ * normals [nv][3], uvs [nv][2].  The reference's own closest-hit program needs both (Q11); either may be NULL for the SDK's
+ * fallbacks (cuda/LocalGeometry.h:120-124,150-158): without normals N = the geometric normal, without texcoords UV = the
+ * barycentrics, in the shade stage and in rt3_get_local_geometry. */
 int rt3_mesh_create(rt3_context_t ctx, const float* verts, int num_keys, int nv, const int32_t* idx, int nt,
                     const float* normals, const float* uvs, rt3_handle_t* blas);
+/* optional vertex colours rgba [nv][4] of a triangle mesh (GeometryData::TriangleMesh::colors, cuda/LocalGeometry.h:99-110):
+ * interpolated into rt3_local_geometry::color; call before rt3_accel_build */
+int rt3_mesh_set_colors(rt3_context_t ctx, rt3_handle_t blas, const float* rgba);
 /* analytic spheres, center_radius [n][4] (cuda/GeometryData.h:83-87, test per cuda/sphere.cu:37-97) */
 int rt3_spheres_create(rt3_context_t ctx, const float* center_radius, int n, rt3_handle_t* blas);
 /* round curves.  cp_radius [ncp][4]; segment i uses control points seg_first_cp[i] .. seg_first_cp[i] + degree.
@@ -136,7 +141,7 @@ int rt3_trace_device(rt3_context_t ctx, const void* d_rays, int n, int any_hit, 
 /* The SDK's stage record (cuda/LocalGeometry.h:40-58, one texcoord set) for hits returned by rt3_trace: world-space P
  * (interpolated vertices, object -> world at the ray time), shading normal N and geometric normal Ng (world space,
  * unit length), UV, the object-space derivatives dndu/dndv/dpdu/dpdv as getLocalGeometry forms them
- * (LocalGeometry.h:126-160) and color = 1.  Spheres and curves (empty in the SDK): P = o + t d, N = Ng = surface
+ * (LocalGeometry.h:126-160) and color = the interpolated vertex colours (1 without them).  Spheres and curves (empty in the SDK): P = o + t d, N = Ng = surface
  * normal, UV = (0,0) / (u,0), zero derivatives.  Misses give an all-zero record. */
 typedef struct rt3_local_geometry {
     float P[3], N[3], Ng[3];

@@ -91,6 +91,8 @@ struct Lane {     /* the state of one OptiX thread */
     /* custom-primitive programs (cuda/sphere.cu): what optixReportIntersection received */
     bool reported = false; float rep_t = 0; unsigned int rep_kind = 0, rep_attr[8] = {0}; int rep_nattr = 0;
     void* sbt_override = nullptr; unsigned int prim_index = 0;
+    /* current instance transform, rows of the 3x4 object->world and world->object matrices (identity unless a harness sets them) */
+    float obj2world[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}, world2obj[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
 };
 extern Hooks hooks;
 extern thread_local Lane lane;
@@ -156,6 +158,18 @@ inline float optixGetRayTmax() { return rt3shim::lane.ray_tmax; }
 inline float optixGetRayTime() { return rt3shim::lane.ray_time; }
 inline float2 optixGetTriangleBarycentrics() { return make_float2(rt3shim::lane.hit.u, rt3shim::lane.hit.v); }
 template <class R, class... A> inline R optixDirectCall(unsigned int, A...) { return __direct_callable__test(); }
+
+/* object <-> world helpers used by cuda/LocalGeometry.h:95,110,119 — the arithmetic of the OptiX SDK's
+ * optix_device_impl_transformations.h: a point goes through the rows of object->world, a normal through the COLUMNS of
+ * world->object (inverse transpose), each a left-to-right sum */
+inline float3 optixTransformPointFromObjectToWorldSpace(float3 p) {
+    const float* m = rt3shim::lane.obj2world;
+    return make_float3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7], m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+}
+inline float3 optixTransformNormalFromObjectToWorldSpace(float3 n) {
+    const float* w = rt3shim::lane.world2obj;
+    return make_float3(w[0] * n.x + w[4] * n.y + w[8] * n.z, w[1] * n.x + w[5] * n.y + w[9] * n.z, w[2] * n.x + w[6] * n.y + w[10] * n.z);
+}
 
 /* custom-primitive intersection programs (cuda/sphere.cu:37-97) */
 template <class... A>

@@ -176,7 +176,8 @@ struct Blas {
     std::vector<f3> verts, normals;    // verts: [vkeys][nv] (vertex-key motion, cuda_mesh.h:85-88: keys spread over time [0,1])
     int vkeys = 1, nv = 0;
     int subdiv = 1;                    // curves of degree 2 / 3: linear sub-segments per user segment (hits translated at the API boundary)
-    std::vector<f2> uvs;
+    std::vector<f2> uvs;               // normals / uvs may be empty: the SDK's fallbacks (cuda/LocalGeometry.h:120-124,150-158)
+    std::vector<float> colors;         // optional vertex colours, 4 per vertex (LocalGeometry.h:99-110)
     std::vector<int32_t> idx;          // tris: 3 per prim
     std::vector<float> cr;             // spheres: 4 per prim; curves: control points 4 per cp
     std::vector<int32_t> seg;          // curves: first cp per segment
@@ -400,6 +401,22 @@ struct rt3o_scene {
     // "LocalGeometry" of the new shade stage: object-space N/uv per closehit_radiance.cu:66-74,
     // N moved to world space by the inverse-transpose (cuda/LocalGeometry.h:110,119) — exact
     // identity for the reference's identity instances.
+    // the three object-space vertices of a triangle at a ray time (vertex keys spread evenly over [0, 1], cuda_mesh.h:82-88)
+    static void tri_verts(const Blas& b, int prim, float time, f3& P0, f3& P1, f3& P2) {
+        const int i0 = b.idx[3 * prim], i1 = b.idx[3 * prim + 1], i2 = b.idx[3 * prim + 2];
+        if (b.vkeys <= 1) { P0 = b.verts[i0]; P1 = b.verts[i1]; P2 = b.verts[i2]; return; }
+        const float tc = fminf(fmaxf(time, 0.0f), 1.0f);
+        const float f = tc * (float)(b.vkeys - 1);
+        int ki = (int)floorf(f);
+        if (ki > b.vkeys - 2) ki = b.vkeys - 2;
+        const float al = f - (float)ki, w = 1.0f - al;
+        const f3* k0 = &b.verts[(size_t)ki * b.nv];
+        const f3* k1 = k0 + b.nv;
+        P0 = {w * k0[i0].x + al * k1[i0].x, w * k0[i0].y + al * k1[i0].y, w * k0[i0].z + al * k1[i0].z};
+        P1 = {w * k0[i1].x + al * k1[i1].x, w * k0[i1].y + al * k1[i1].y, w * k0[i1].z + al * k1[i1].z};
+        P2 = {w * k0[i2].x + al * k1[i2].x, w * k0[i2].y + al * k1[i2].y, w * k0[i2].z + al * k1[i2].z};
+    }
+
     void local_geometry(const Hit& h, f3 o, f3 d, float time, f3& N, f2& uv) const {
         const Instance& in = inst[h.inst];
         const Blas& b = *blas[in.blas];
@@ -407,9 +424,16 @@ struct rt3o_scene {
         if (b.type == PRIM_TRI) {
             const int i0 = b.idx[3 * h.prim], i1 = b.idx[3 * h.prim + 1], i2 = b.idx[3 * h.prim + 2];
             const float w0 = 1.0f - h.u - h.v;
-            n_obj = w0 * b.normals[i0] + h.u * b.normals[i1] + h.v * b.normals[i2];
-            uv.x = w0 * b.uvs[i0].x + h.u * b.uvs[i1].x + h.v * b.uvs[i2].x;
-            uv.y = w0 * b.uvs[i0].y + h.u * b.uvs[i1].y + h.v * b.uvs[i2].y;
+            if (!b.normals.empty()) n_obj = w0 * b.normals[i0] + h.u * b.normals[i1] + h.v * b.normals[i2];
+            else {  // no vertex normals: the geometric normal (cuda/LocalGeometry.h:120-124)
+                f3 P0, P1, P2;
+                tri_verts(b, h.prim, time, P0, P1, P2);
+                n_obj = cross(P1 - P0, P2 - P0);
+            }
+            if (!b.uvs.empty()) {
+                uv.x = w0 * b.uvs[i0].x + h.u * b.uvs[i1].x + h.v * b.uvs[i2].x;
+                uv.y = w0 * b.uvs[i0].y + h.u * b.uvs[i1].y + h.v * b.uvs[i2].y;
+            } else uv = {h.u, h.v};  // no texcoords: the barycentrics (LocalGeometry.h:150-152)
         } else {
             f3 oo, od;
             to_object(in, time, o, d, oo, od);
@@ -424,7 +448,7 @@ struct rt3o_scene {
                 f3 p1 = {b.cr[4 * a + 4], b.cr[4 * a + 5], b.cr[4 * a + 6]};
                 float r0 = b.cr[4 * a + 3], r1 = b.cr[4 * a + 7];
                 if (h.u == 0.0f) n_obj = ps - p0;
-                else if (h.u >= 1.0f) n_obj = ps - p1;
+                else if (h.u >= 1.0f) n_obj = ps - ((p1 - p0) + p0);  // the SDK rebuilds the end point from its pre-transformed coefficients (curve.h:389-394)
                 else {
                     f3 dd3 = p1 - p0;
                     float dr = r1 - r0;
@@ -459,54 +483,56 @@ struct rt3o_scene {
         const Blas& b = *blas[in.blas];
         f3 P, N, Ng, dndu{0, 0, 0}, dndv{0, 0, 0}, dpdu{0, 0, 0}, dpdv{0, 0, 0};
         f2 uv{0, 0};
+        float color[4] = {1.0f, 1.0f, 1.0f, 1.0f};
         if (b.type == PRIM_TRI) {
             const bool moving = in.nkeys > 0;
             Affine m{}, mi{};
             if (moving) { m = lerp_keys(in.keys.data(), in.nkeys, in.t0, in.t1, time); mi = invert_affine(m); }
             const int i0 = b.idx[3 * h.prim], i1 = b.idx[3 * h.prim + 1], i2 = b.idx[3 * h.prim + 2];
             f3 P0, P1, P2;
-            if (b.vkeys <= 1) {
-                P0 = b.verts[i0]; P1 = b.verts[i1]; P2 = b.verts[i2];
-            } else {
-                const float tc = fminf(fmaxf(time, 0.0f), 1.0f);
-                const float f = tc * (float)(b.vkeys - 1);
-                int ki = (int)floorf(f);
-                if (ki > b.vkeys - 2) ki = b.vkeys - 2;
-                const float al = f - (float)ki, w = 1.0f - al;
-                const f3* k0 = &b.verts[(size_t)ki * b.nv];
-                const f3* k1 = k0 + b.nv;
-                P0 = {w * k0[i0].x + al * k1[i0].x, w * k0[i0].y + al * k1[i0].y, w * k0[i0].z + al * k1[i0].z};
-                P1 = {w * k0[i1].x + al * k1[i1].x, w * k0[i1].y + al * k1[i1].y, w * k0[i1].z + al * k1[i1].z};
-                P2 = {w * k0[i2].x + al * k1[i2].x, w * k0[i2].y + al * k1[i2].y, w * k0[i2].z + al * k1[i2].z};
-            }
+            tri_verts(b, h.prim, time, P0, P1, P2);
             const float w0 = 1.0f - h.u - h.v;
             f3 p = w0 * P0 + h.u * P1 + h.v * P2;
             if (moving) p = xform_point(m, p);
             P = xform_point(in.stat, p);
+            if (!b.colors.empty())   // LocalGeometry.h:99-106
+                for (int k = 0; k < 4; k++) color[k] = w0 * b.colors[4 * i0 + k] + h.u * b.colors[4 * i1 + k] + h.v * b.colors[4 * i2 + k];
             f3 ng = cross(P1 - P0, P2 - P0);
-            const f3 N0 = b.normals[i0], N1 = b.normals[i1], N2 = b.normals[i2];
-            f3 n = w0 * N0 + h.u * N1 + h.v * N2;
-            if (moving) { ng = xform_normal_by_inverse(mi, ng); n = xform_normal_by_inverse(mi, n); }
+            if (moving) ng = xform_normal_by_inverse(mi, ng);
             Ng = normalize(xform_normal_by_inverse(in.stat_inv, ng));
-            N = normalize(xform_normal_by_inverse(in.stat_inv, n));
+            f3 N0, N1, N2;
+            if (!b.normals.empty()) {
+                N0 = b.normals[i0]; N1 = b.normals[i1]; N2 = b.normals[i2];
+                f3 n = w0 * N0 + h.u * N1 + h.v * N2;
+                if (moving) n = xform_normal_by_inverse(mi, n);
+                N = normalize(xform_normal_by_inverse(in.stat_inv, n));
+            } else N = N0 = N1 = N2 = Ng;   // LocalGeometry.h:120-124: the (world-space, unit) geometric normal stands in for all three
             const f3 dp1 = P0 - P2, dp2 = P1 - P2, dn1 = N0 - N2, dn2 = N1 - N2;
-            const f2 U0 = b.uvs[i0], U1 = b.uvs[i1], U2 = b.uvs[i2];
-            uv.x = w0 * U0.x + h.u * U1.x + h.v * U2.x;
-            uv.y = w0 * U0.y + h.u * U1.y + h.v * U2.y;
-            const float du1 = U0.x - U2.x, du2 = U1.x - U2.x, dv1 = U0.y - U2.y, dv2 = U1.y - U2.y;
-            const float det = du1 * dv2 - dv1 * du2;
-            const float invdet = 1.0f / det;
-            dpdu = (dv2 * dp1 - dv1 * dp2) * invdet;
-            dpdv = ((-du2) * dp1 + du1 * dp2) * invdet;
-            dndu = (dv2 * dn1 - dv1 * dn2) * invdet;
-            dndv = ((-du2) * dn1 + du1 * dn2) * invdet;
+            if (!b.uvs.empty()) {
+                const f2 U0 = b.uvs[i0], U1 = b.uvs[i1], U2 = b.uvs[i2];
+                uv.x = w0 * U0.x + h.u * U1.x + h.v * U2.x;
+                uv.y = w0 * U0.y + h.u * U1.y + h.v * U2.y;
+                const float du1 = U0.x - U2.x, du2 = U1.x - U2.x, dv1 = U0.y - U2.y, dv2 = U1.y - U2.y;
+                const float det = du1 * dv2 - dv1 * du2;
+                const float invdet = 1.0f / det;
+                dpdu = (dv2 * dp1 - dv1 * dp2) * invdet;
+                dpdv = ((-du2) * dp1 + du1 * dp2) * invdet;
+                dndu = (dv2 * dn1 - dv1 * dn2) * invdet;
+                dndv = ((-du2) * dn1 + du1 * dn2) * invdet;
+            } else {   // LocalGeometry.h:150-158
+                uv = {h.u, h.v};
+                dpdu = -dp1;
+                dpdv = -dp1 + dp2;
+                dndu = -dn1;
+                dndv = -dn1 + dn2;
+            }
         } else {
             local_geometry(h, o, d, time, N, uv);
             Ng = N;
             P = o + h.t * d;
         }
         const float v[27] = {P.x, P.y, P.z, N.x, N.y, N.z, Ng.x, Ng.y, Ng.z, uv.x, uv.y, dndu.x, dndu.y, dndu.z, dndv.x, dndv.y, dndv.z,
-                             dpdu.x, dpdu.y, dpdu.z, dpdv.x, dpdv.y, dpdv.z, 1.0f, 1.0f, 1.0f, 1.0f};
+                             dpdu.x, dpdu.y, dpdu.z, dpdv.x, dpdv.y, dpdv.z, color[0], color[1], color[2], color[3]};
         for (int k = 0; k < 27; k++) out[k] = v[k];
     }
 
@@ -571,8 +597,10 @@ struct rt3o_scene {
                 const f3 P = org + hit.t * dir;
                 if (in.emission.x != 0.0f || in.emission.y != 0.0f || in.emission.z != 0.0f) {
                     float wgt = 1.0f;
-                    if (depth > 0) {  // BSDF-sampled emitter hit: weight against the NEE strategy
-                        const Blas& b = *blas[in.blas];
+                    // BSDF-sampled emitter hit: weight against the NEE strategy where NEE can produce this point at all: the light
+                    // list holds object-space key-0 triangles (Q15), so only static meshes under identity instances qualify
+                    const Blas& b = *blas[in.blas];
+                    if (depth > 0 && b.type == PRIM_TRI && b.vkeys == 1 && in.identity) {
                         const f3 v0 = b.verts[b.idx[3 * hit.prim]], v1 = b.verts[b.idx[3 * hit.prim + 1]], v2 = b.verts[b.idx[3 * hit.prim + 2]];
                         const f3 nrm = cross(v1 - v0, v2 - v0);
                         const float area = 0.5f * length(nrm);
@@ -774,19 +802,26 @@ static int finish_blas(rt3o_scene* s, std::unique_ptr<Blas> b) {
 int rt3o_mesh_create(rt3o_scene* s, const float* verts, int num_keys, int nv, const int32_t* idx, int nt,
                      const float* normals, const float* uvs) {
     RT3O_TRY
-    if (!s || !verts || !idx || !normals || !uvs || nv <= 0 || nt <= 0 || num_keys < 1) { g_err = "mesh_create: bad argument"; return -1; }
+    if (!s || !verts || !idx || nv <= 0 || nt <= 0 || num_keys < 1) { g_err = "mesh_create: bad argument"; return -1; }
     for (int i = 0; i < 3 * nt; i++)
         if (idx[i] < 0 || idx[i] >= nv) { g_err = "mesh_create: index out of range"; return -1; }
     auto b = std::make_unique<Blas>();
     b->type = PRIM_TRI;
     b->nprims = nt;
     b->vkeys = num_keys; b->nv = nv;
-    b->verts.resize((size_t)nv * num_keys); b->normals.resize(nv); b->uvs.resize(nv);
+    b->verts.resize((size_t)nv * num_keys);
     std::memcpy(b->verts.data(), verts, sizeof(f3) * (size_t)nv * num_keys);  // [key][vertex]; normals / uvs: key 0 (create_sbt binds the buffer start)
-    std::memcpy(b->normals.data(), normals, sizeof(f3) * nv);
-    std::memcpy(b->uvs.data(), uvs, sizeof(f2) * nv);
+    if (normals) { b->normals.resize(nv); std::memcpy(b->normals.data(), normals, sizeof(f3) * nv); }
+    if (uvs) { b->uvs.resize(nv); std::memcpy(b->uvs.data(), uvs, sizeof(f2) * nv); }
     b->idx.assign(idx, idx + 3 * nt);
     return finish_blas(s, std::move(b));
+    RT3O_CATCH(-1)
+}
+int rt3o_mesh_set_colors(rt3o_scene* s, int blas, const float* rgba) {
+    RT3O_TRY
+    if (!s || !rgba || blas < 0 || blas >= (int)s->blas.size() || s->blas[blas]->type != PRIM_TRI) { g_err = "mesh_set_colors: bad argument"; return -1; }
+    s->blas[blas]->colors.assign(rgba, rgba + 4 * (size_t)s->blas[blas]->nv);
+    return 0;
     RT3O_CATCH(-1)
 }
 int rt3o_spheres_create(rt3o_scene* s, const float* cr, int n) {
@@ -807,6 +842,20 @@ int rt3o_spheres_create(rt3o_scene* s, const float* cr, int n) {
 #ifndef RT3_CURVE_SUBDIV
 #define RT3_CURVE_SUBDIV 8
 #endif
+// position4(u) of the SDK's Quadratic / CubicInterpolator initialised from uniform B-spline control points q[0..degree]
+// (cuda/curve.h:102-111,124-127,176-186,264-267), one component.  float4 / float in sutil/vec_math.h:735-739 is a
+// multiplication by the rounded reciprocal, and the sums associate left to right.
+static inline float bspline_component(int degree, float q0, float q1, float q2, float q3, float u) {
+    if (degree == 2) {
+        const float inv = 1.0f / 2.0f;
+        const float p0 = ((q0 - 2.0f * q1) + q2) * inv, p1 = (-2.0f * q0 + 2.0f * q1) * inv, p2 = (q0 + q1) * inv;
+        return (p0 * u + p1) * u + p2;
+    }
+    const float inv = 1.0f / 6.0f;
+    const float p0 = (((q0 * -1.0f + q1 * 3.0f) + q2 * -3.0f) + q3) * inv, p1 = ((q0 * 3.0f + q1 * -6.0f) + q2 * 3.0f) * inv,
+                p2 = (q0 * -3.0f + q2 * 3.0f) * inv, p3 = ((q0 * 1.0f + q1 * 4.0f) + q2 * 1.0f) * inv;
+    return ((p0 * u + p1) * u + p2) * u + p3;
+}
 static void tessellate_bspline(int degree, const float* cp, const int32_t* seg, int nseg, std::vector<float>& out_cp, std::vector<int32_t>& out_seg) {
     const int K = RT3_CURVE_SUBDIV;
     out_cp.resize((size_t)4 * nseg * (K + 1));
@@ -814,20 +863,8 @@ static void tessellate_bspline(int degree, const float* cp, const int32_t* seg, 
     for (int s = 0; s < nseg; s++) {
         const float* q = cp + 4 * (size_t)seg[s];
         for (int k = 0; k <= K; k++) {
-            const float u = (float)k / (float)K;
             float* o = &out_cp[4 * ((size_t)s * (K + 1) + (size_t)k)];
-            for (int c = 0; c < 4; c++) {
-                const float q0 = q[c], q1 = q[4 + c], q2 = q[8 + c];
-                if (degree == 2) {
-                    const float p0 = ((q0 - 2.0f * q1) + q2) / 2.0f, p1 = (-2.0f * q0 + 2.0f * q1) / 2.0f, p2 = (q0 + q1) / 2.0f;
-                    o[c] = (p0 * u + p1) * u + p2;
-                } else {
-                    const float q3 = q[12 + c];
-                    const float p0 = (((q0 * -1.0f + q1 * 3.0f) + q2 * -3.0f) + q3) / 6.0f, p1 = ((q0 * 3.0f + q1 * -6.0f) + q2 * 3.0f) / 6.0f,
-                                p2 = (q0 * -3.0f + q2 * 3.0f) / 6.0f, p3 = ((q0 * 1.0f + q1 * 4.0f) + q2 * 1.0f) / 6.0f;
-                    o[c] = ((p0 * u + p1) * u + p2) * u + p3;
-                }
-            }
+            for (int c = 0; c < 4; c++) o[c] = bspline_component(degree, q[c], q[4 + c], q[8 + c], degree == 3 ? q[12 + c] : 0.0f, (float)k / (float)K);
             if (k < K) out_seg[(size_t)s * K + (size_t)k] = s * (K + 1) + k;
         }
     }
@@ -1088,6 +1125,9 @@ void rt3o_kat_camera_uvw(const float e[3], const float l[3], const float u[3], f
     f3 U, V, W;
     camera_uvw({e[0], e[1], e[2]}, {l[0], l[1], l[2]}, {u[0], u[1], u[2]}, fovy, aspect, U, V, W);
     o[0] = U.x; o[1] = U.y; o[2] = U.z; o[3] = V.x; o[4] = V.y; o[5] = V.z; o[6] = W.x; o[7] = W.y; o[8] = W.z;
+}
+void rt3o_kat_bspline_position(int degree, const float* cp, float u, float out[4]) {
+    for (int c = 0; c < 4; c++) out[c] = bspline_component(degree, cp[c], cp[4 + c], cp[8 + c], degree == 3 ? cp[12 + c] : 0.0f, u);
 }
 void rt3o_kat_sincos_2pi(float u, float o[2]) { sincos_2pi(u, o[0], o[1]); }
 void rt3o_kat_invert_affine(const float m[12], float out[12]) {

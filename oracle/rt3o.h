@@ -18,7 +18,8 @@ typedef struct rt3o_scene rt3o_scene;
 rt3o_scene* rt3o_scene_create(void);
 void rt3o_scene_destroy(rt3o_scene*);
 int rt3o_mesh_create(rt3o_scene*, const float* verts, int num_keys, int nv, const int32_t* idx, int nt,
-                     const float* normals, const float* uvs);                 /* returns blas id or <0 */
+                     const float* normals, const float* uvs);                 /* returns blas id or <0; normals / uvs may be NULL (SDK fallbacks) */
+int rt3o_mesh_set_colors(rt3o_scene*, int blas, const float* rgba);          /* [nv][4] vertex colours, cuda/LocalGeometry.h:99-110 */
 int rt3o_spheres_create(rt3o_scene*, const float* center_radius, int n);
 int rt3o_curves_create(rt3o_scene*, int degree, const float* cp_radius, int ncp, const int32_t* seg_first_cp, int nseg);
 int rt3o_texture_create(rt3o_scene*, const uint8_t* rgba8, int w, int h, int address_mode, int filter_mode);
@@ -55,6 +56,7 @@ void rt3o_kat_light_sample(const void* light68, const float P[3], uint32_t* seed
 void rt3o_kat_make_color(const float c[3], uint8_t out[4]);
 void rt3o_kat_camera_uvw(const float eye[3], const float lookat[3], const float up[3], float fovy, float aspect, float out_uvw[9]);
 void rt3o_kat_sincos_2pi(float u, float out_sc[2]);
+void rt3o_kat_bspline_position(int degree, const float* cp /*[degree+1][4]*/, float u, float out[4]);  /* cuda/curve.h position4 of a B-spline segment */
 void rt3o_kat_invert_affine(const float m[12], float out[12]);
 int rt3o_kat_fetch_texture(rt3o_scene*, int tex, float u, float v, float out_rgb[3]);
 int rt3o_kat_sample_texture(rt3o_scene*, int instance_id, float u, float v, float out_rgb[3]);  /* with the instance's texcoord transform */  /* the shade stage's tex2D restatement */

@@ -26,7 +26,7 @@ LIB_PATH = os.path.join(_HERE, "librt3.so")
 
 RT3_SYMBOLS = [
     "rt3_context_create", "rt3_context_destroy", "rt3_sync", "rt3_last_error", "rt3_get_stream", "rt3_get_stats", "rt3_reset_stats", "rt3_get_debug_counters",
-    "rt3_set_option", "rt3_mesh_create", "rt3_spheres_create", "rt3_curves_create", "rt3_texture_create",
+    "rt3_set_option", "rt3_mesh_create", "rt3_mesh_set_colors", "rt3_spheres_create", "rt3_curves_create", "rt3_texture_create",
     "rt3_accel_append_instance", "rt3_accel_append_animated_instance", "rt3_accel_build", "rt3_scene_set_hitgroup",
     "rt3_scene_set_lights", "rt3_light_make", "rt3_camera_uvw", "rt3_launch_subframe", "rt3_trace", "rt3_trace_device", "rt3_get_local_geometry", "rt3_scene_set_texture_transform",
     "rt3_download_accum", "rt3_download_frame", "rt3_accum_device_ptr", "rt3_clear_accum", "rt3_finalize_accum",
@@ -119,12 +119,19 @@ class Context:
 
     # ---- geometry
     def mesh_create(self, verts, idx, normals, uvs):
-        v, n, t = _f32(verts), _f32(normals), _f32(uvs)  # verts [nv,3] or [keys,nv,3] (vertex-key motion)
+        v = _f32(verts)  # verts [nv,3] or [keys,nv,3] (vertex-key motion)
+        n = _f32(normals) if normals is not None else None   # None: the SDK's fallbacks (N = geometric normal / UV = barycentrics)
+        t = _f32(uvs) if uvs is not None else None
         i = np.ascontiguousarray(idx, dtype=np.int32)
         h = C.c_uint64()
         keys, nv = (v.shape[0], v.shape[1]) if v.ndim == 3 else (1, len(v))
-        self._chk(self.L.rt3_mesh_create(self.ctx, fptr(v), C.c_int(keys), C.c_int(nv), iptr(i), C.c_int(len(i)), fptr(n), fptr(t), C.byref(h)))
+        self._chk(self.L.rt3_mesh_create(self.ctx, fptr(v), C.c_int(keys), C.c_int(nv), iptr(i), C.c_int(len(i)), fptr(n) if n is not None else None,
+                                         fptr(t) if t is not None else None, C.byref(h)))
         return h.value
+
+    def mesh_set_colors(self, blas, rgba):
+        c = _f32(rgba)
+        self._chk(self.L.rt3_mesh_set_colors(self.ctx, C.c_uint64(blas), fptr(c)))
 
     def spheres_create(self, cr):
         c = _f32(cr)

@@ -17,7 +17,7 @@
 
 namespace rt3 {
 thread_local std::string g_last_error;
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};   // all contexts, any host thread
 }  // namespace rt3
 
 using namespace rt3;
@@ -27,7 +27,7 @@ namespace {
 struct Geometry {
     uint32_t type = PRIM_TRI, nprims = 0, vkeys = 1, nv = 0;
     uint32_t subdiv = 1;  // curves of degree 2 / 3: linear sub-segments per user segment (hit records are translated at the API boundary)
-    DevBuf<float> verts, normals, uvs;
+    DevBuf<float> verts, normals, uvs, colors;   // normals / uvs / colors stay empty when the caller has none (SDK fallbacks)
     DevBuf<int32_t> idx, seg;
     DevBuf<float4> cr;
     DevBuf<Node8> nodes;
@@ -110,7 +110,11 @@ struct rt3_context {
     float ms[6] = {0, 0, 0, 0, 0, 0};
     bool hitgroups_dirty = true;
 #ifndef RT3_EMULATE
+    // single-process multi-GPU reduce (rt3_allreduce_accum): this context's communicator, kept between calls, and the
+    // device list + rank it was created for; destroyed with the context
     void* nccl_comm = nullptr;
+    std::vector<int> nccl_devs;
+    int nccl_rank = -1;
 #endif
 
     TravScene trav_scene() {
@@ -263,6 +267,39 @@ static inline void use_device(rt3_context* c) {
     }                                                     \
     return RT3_OK;
 
+
+#ifndef RT3_EMULATE
+// NCCL is resolved at run time so that librt3.so has no link-time dependency on it
+struct NcclApi {
+    bool ok = false;
+    int (*initAll)(void**, int, const int*) = nullptr;
+    int (*allReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*groupStart)(void) = nullptr;
+    int (*groupEnd)(void) = nullptr;
+    int (*commDestroy)(void*) = nullptr;
+};
+static const NcclApi& nccl_api() {
+    static const NcclApi api = [] {
+        NcclApi a;
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return a;
+        a.initAll = (int (*)(void**, int, const int*))dlsym(lib, "ncclCommInitAll");
+        a.allReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        a.groupStart = (int (*)(void))dlsym(lib, "ncclGroupStart");
+        a.groupEnd = (int (*)(void))dlsym(lib, "ncclGroupEnd");
+        a.commDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+        a.ok = a.initAll && a.allReduce && a.groupStart && a.groupEnd && a.commDestroy;
+        return a;
+    }();
+    return api;
+}
+static void drop_nccl_comm(rt3_context* c) {
+    if (c->nccl_comm) { cudaSetDevice(c->device); nccl_api().commDestroy(c->nccl_comm); }
+    c->nccl_comm = nullptr; c->nccl_devs.clear(); c->nccl_rank = -1;
+}
+#endif
+
 extern "C" {
 
 const char* rt3_last_error(void) { return rt3::g_last_error.c_str(); }
@@ -305,6 +342,7 @@ void rt3_context_destroy(rt3_context_t c) {
     if (!c) return;
 #ifndef RT3_EMULATE
     cudaSetDevice(c->device);
+    drop_nccl_comm(c);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3); cudaStreamSynchronize(c->stream4);
     cudaStream_t s = c->stream, s2 = c->stream2, s3 = c->stream3, s4 = c->stream4;
@@ -356,7 +394,7 @@ int rt3_mesh_create(rt3_context_t c, const float* verts, int num_keys, int nv, c
                     const float* uvs, rt3_handle_t* blas) {
     RT3_API_BEGIN
     use_device(c);
-    RT3_REQUIRE(c && verts && idx && normals && uvs && blas, RT3_ERR_INVALID, "mesh_create: null argument (normals and uvs are required, Q11)");
+    RT3_REQUIRE(c && verts && idx && blas, RT3_ERR_INVALID, "mesh_create: null argument");
     RT3_REQUIRE(nv > 0 && nt > 0 && num_keys >= 1, RT3_ERR_INVALID, "mesh_create: empty mesh");
     for (size_t i = 0; i < 3 * (size_t)nt; i++) RT3_REQUIRE(idx[i] >= 0 && idx[i] < nv, RT3_ERR_INVALID, "mesh_create: index out of range");
     auto g = std::make_unique<Geometry>();
@@ -365,15 +403,26 @@ int rt3_mesh_create(rt3_context_t c, const float* verts, int num_keys, int nv, c
     g->nv = (uint32_t)nv;
     g->nprims = (uint32_t)nt;
     g->verts.alloc(3 * (size_t)nv * (size_t)num_keys);
-    g->normals.alloc(3 * (size_t)nv);
-    g->uvs.alloc(2 * (size_t)nv);
     g->idx.alloc(3 * (size_t)nt);
     h2d(g->verts.p, verts, g->verts.bytes(), c->stream);  // [key][vertex][3]
-    h2d(g->normals.p, normals, g->normals.bytes(), c->stream);
-    h2d(g->uvs.p, uvs, g->uvs.bytes(), c->stream);
+    if (normals) { g->normals.alloc(3 * (size_t)nv); h2d(g->normals.p, normals, g->normals.bytes(), c->stream); }
+    if (uvs) { g->uvs.alloc(2 * (size_t)nv); h2d(g->uvs.p, uvs, g->uvs.bytes(), c->stream); }
     h2d(g->idx.p, idx, g->idx.bytes(), c->stream);
     stream_sync(c->stream);  // host arrays are borrowed for the duration of the call only
     *blas = finish_geometry(c, std::move(g));
+    RT3_API_END
+}
+
+int rt3_mesh_set_colors(rt3_context_t c, rt3_handle_t blas, const float* rgba) {
+    RT3_API_BEGIN
+    use_device(c);
+    RT3_REQUIRE(c && rgba && blas >= 1 && blas <= c->geoms.size(), RT3_ERR_INVALID, "mesh_set_colors: bad argument");
+    Geometry& g = *c->geoms[(size_t)blas - 1];
+    RT3_REQUIRE(g.type == PRIM_TRI || g.type == PRIM_TRI_MOTION, RT3_ERR_INVALID, "mesh_set_colors: not a triangle mesh");
+    g.colors.alloc(4 * (size_t)g.nv);
+    h2d(g.colors.p, rgba, g.colors.bytes(), c->stream);
+    stream_sync(c->stream);
+    c->built = false;   // the device-side geometry table is rewritten by the next rt3_accel_build
     RT3_API_END
 }
 
@@ -400,30 +449,41 @@ int rt3_spheres_create(rt3_context_t c, const float* cr, int n, rt3_handle_t* bl
 #ifndef RT3_CURVE_SUBDIV
 #define RT3_CURVE_SUBDIV 8
 #endif
+// Polynomial coefficients (highest power first) of one component of a uniform B-spline segment, as the SDK's interpolators
+// form them: rows of the B-spline-to-power-basis matrix applied left to right, then scaled by the rounded reciprocal of the
+// common denominator (vec_math's float4 / float).
+static int bspline_coefficients(int degree, const float* q /* stride 4 */, float coef[4]) {
+    if (degree == 2) {
+        const float h = 1.0f / 2.0f;
+        coef[0] = ((q[0] - 2.0f * q[4]) + q[8]) * h;
+        coef[1] = (-2.0f * q[0] + 2.0f * q[4]) * h;
+        coef[2] = (q[0] + q[4]) * h;
+        return 3;
+    }
+    const float s = 1.0f / 6.0f;
+    coef[0] = (((q[0] * -1.0f + q[4] * 3.0f) + q[8] * -3.0f) + q[12]) * s;
+    coef[1] = ((q[0] * 3.0f + q[4] * -6.0f) + q[8] * 3.0f) * s;
+    coef[2] = (q[0] * -3.0f + q[8] * 3.0f) * s;
+    coef[3] = ((q[0] * 1.0f + q[4] * 4.0f) + q[8] * 1.0f) * s;
+    return 4;
+}
 static void tessellate_bspline(int degree, const float* cp, const int32_t* seg, int nseg, std::vector<float>& out_cp, std::vector<int32_t>& out_seg) {
     const int K = RT3_CURVE_SUBDIV;
     out_cp.resize((size_t)4 * nseg * (K + 1));
     out_seg.resize((size_t)nseg * K);
-    for (int s = 0; s < nseg; s++) {
-        const float* q = cp + 4 * (size_t)seg[s];
-        for (int k = 0; k <= K; k++) {
-            const float u = (float)k / (float)K;
-            float* o = &out_cp[4 * ((size_t)s * (K + 1) + (size_t)k)];
-            for (int c = 0; c < 4; c++) {
-                const float q0 = q[c], q1 = q[4 + c], q2 = q[8 + c];
-                if (degree == 2) {
-                    const float p0 = ((q0 - 2.0f * q1) + q2) / 2.0f, p1 = (-2.0f * q0 + 2.0f * q1) / 2.0f, p2 = (q0 + q1) / 2.0f;
-                    o[c] = (p0 * u + p1) * u + p2;
-                } else {
-                    const float q3 = q[12 + c];
-                    const float p0 = (((q0 * -1.0f + q1 * 3.0f) + q2 * -3.0f) + q3) / 6.0f, p1 = ((q0 * 3.0f + q1 * -6.0f) + q2 * 3.0f) / 6.0f,
-                                p2 = (q0 * -3.0f + q2 * 3.0f) / 6.0f, p3 = ((q0 * 1.0f + q1 * 4.0f) + q2 * 1.0f) / 6.0f;
-                    o[c] = ((p0 * u + p1) * u + p2) * u + p3;
-                }
+    for (int s = 0; s < nseg; s++)
+        for (int c = 0; c < 4; c++) {   // component by component: x, y, z, radius
+            float coef[4];
+            const int n = bspline_coefficients(degree, cp + 4 * (size_t)seg[s] + c, coef);
+            for (int k = 0; k <= K; k++) {
+                const float u = (float)k / (float)K;
+                float v = coef[0];
+                for (int j = 1; j < n; j++) v = v * u + coef[j];   // Horner
+                out_cp[4 * ((size_t)s * (K + 1) + (size_t)k) + (size_t)c] = v;
             }
-            if (k < K) out_seg[(size_t)s * K + (size_t)k] = s * (K + 1) + k;
         }
-    }
+    for (int s = 0; s < nseg; s++)
+        for (int k = 0; k < K; k++) out_seg[(size_t)s * K + (size_t)k] = s * (K + 1) + k;
 }
 static inline void curve_hit_to_internal(int K, int32_t& prim, float& u) {
     const float f = u * (float)K;
@@ -588,7 +648,7 @@ int rt3_accel_build(rt3_context_t c) {
     std::vector<BlasBounds> bb(ng + 1);
     for (size_t i = 0; i < ng; i++) {
         const Geometry& g = *c->geoms[i];
-        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p, g.vkeys, g.verts.p, g.nv, g.subdiv};
+        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p, g.vkeys, g.verts.p, g.nv, g.subdiv, g.colors.p};
         for (int k = 0; k < 3; k++) { bb[i].lo[k] = g.bvh.lo[k]; bb[i].hi[k] = g.bvh.hi[k]; }
     }
     bt[ng] = BlasDev{c->m_nodes_p, c->m_prims_p, PRIM_TRI, c->m_bvh.num_prims, nullptr, nullptr, nullptr, nullptr, nullptr, 1u, nullptr};
@@ -1058,32 +1118,31 @@ int rt3_allreduce_accum(rt3_context_t* ctxs, int n, uint32_t total_subframes) {
     throw Error(RT3_ERR_UNSUPPORTED, "allreduce_accum: not available in the kernel-logic simulator");
 #else
     if (n > 1) {
-        // NCCL is resolved at run time so that librt3.so has no link-time dependency on it
-        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-        RT3_REQUIRE(lib, RT3_ERR_NCCL, "allreduce_accum: libnccl.so.2 not found");
-        typedef int (*InitAll)(void**, int, const int*);
-        typedef int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
-        typedef int (*Group)(void);
-        typedef int (*Destroy)(void*);
-        InitAll initAll = (InitAll)dlsym(lib, "ncclCommInitAll");
-        AllReduce allReduce = (AllReduce)dlsym(lib, "ncclAllReduce");
-        Group gs = (Group)dlsym(lib, "ncclGroupStart"), ge = (Group)dlsym(lib, "ncclGroupEnd");
-        Destroy destroy = (Destroy)dlsym(lib, "ncclCommDestroy");
-        RT3_REQUIRE(initAll && allReduce && gs && ge && destroy, RT3_ERR_NCCL, "allreduce_accum: NCCL symbols missing");
-        std::vector<void*> comms(n);
+        const NcclApi& nccl = nccl_api();
+        RT3_REQUIRE(nccl.ok, RT3_ERR_NCCL, "allreduce_accum: libnccl.so.2 (ncclCommInitAll / ncclAllReduce / ncclGroupStart / ncclGroupEnd / ncclCommDestroy) not found");
         std::vector<int> devs(n);
         for (int i = 0; i < n; i++) { RT3_REQUIRE(ctxs[i] && ctxs[i]->accum.p, RT3_ERR_STATE, "allreduce_accum: context has no film"); devs[i] = ctxs[i]->device; }
-        RT3_REQUIRE(initAll(comms.data(), n, devs.data()) == 0, RT3_ERR_NCCL, "ncclCommInitAll failed");
-        RT3_REQUIRE(gs() == 0, RT3_ERR_NCCL, "ncclGroupStart failed");
-        for (int i = 0; i < n; i++) {
-            RT3_CUDA(cudaSetDevice(ctxs[i]->device));
-            const size_t count = 4ull * ctxs[i]->width * ctxs[i]->height;
-            RT3_REQUIRE(allReduce(ctxs[i]->accum.p, ctxs[i]->accum.p, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comms[i], ctxs[i]->stream) == 0, RT3_ERR_NCCL,
-                        "ncclAllReduce failed");
+        for (int i = 0; i < n; i++)
+            RT3_REQUIRE(ctxs[i]->width == ctxs[0]->width && ctxs[i]->height == ctxs[0]->height, RT3_ERR_STATE, "allreduce_accum: films differ in size");
+        // communicators are created once per (device list, rank) and live in the contexts
+        bool cached = true;
+        for (int i = 0; i < n; i++) cached = cached && ctxs[i]->nccl_comm && ctxs[i]->nccl_rank == i && ctxs[i]->nccl_devs == devs;
+        if (!cached) {
+            for (int i = 0; i < n; i++) drop_nccl_comm(ctxs[i]);
+            std::vector<void*> comms(n, nullptr);
+            RT3_REQUIRE(nccl.initAll(comms.data(), n, devs.data()) == 0, RT3_ERR_NCCL, "ncclCommInitAll failed");
+            for (int i = 0; i < n; i++) { ctxs[i]->nccl_comm = comms[i]; ctxs[i]->nccl_devs = devs; ctxs[i]->nccl_rank = i; }
         }
-        RT3_REQUIRE(ge() == 0, RT3_ERR_NCCL, "ncclGroupEnd failed");
-        for (int i = 0; i < n; i++) { RT3_CUDA(cudaSetDevice(ctxs[i]->device)); stream_sync(ctxs[i]->stream); destroy(comms[i]); }
+        RT3_REQUIRE(nccl.groupStart() == 0, RT3_ERR_NCCL, "ncclGroupStart failed");
+        int rc_all = 0;
+        for (int i = 0; i < n && rc_all == 0; i++) {
+            cudaSetDevice(ctxs[i]->device);
+            const size_t count = 4ull * ctxs[i]->width * ctxs[i]->height;
+            rc_all = nccl.allReduce(ctxs[i]->accum.p, ctxs[i]->accum.p, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, ctxs[i]->nccl_comm, ctxs[i]->stream);
+        }
+        const int rc_end = nccl.groupEnd();   // always closed, also after a failed call inside the group
+        RT3_REQUIRE(rc_all == 0 && rc_end == 0, RT3_ERR_NCCL, "ncclAllReduce failed");
+        for (int i = 0; i < n; i++) { RT3_CUDA(cudaSetDevice(ctxs[i]->device)); stream_sync(ctxs[i]->stream); }
     }
     for (int i = 0; i < n; i++) {
         RT3_CUDA(cudaSetDevice(ctxs[i]->device));

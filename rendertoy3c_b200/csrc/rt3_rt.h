@@ -8,6 +8,7 @@
 //     thread ids, device memory is host memory.  Test infrastructure for the GPU-less CI box only;
 //     it is never linked into librt3.so and is not reachable from the product API.
 #pragma once
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -28,7 +29,7 @@ struct Error : std::runtime_error {
 };
 
 extern thread_local std::string g_last_error;
-extern unsigned long long g_launch_count;  // kernels launched by this library (stats.kernel_launches)
+extern std::atomic<unsigned long long> g_launch_count;  // kernels launched by this library (stats.kernel_launches)
 inline void count_launch() { ++g_launch_count; }
 
 #define RT3_REQUIRE(cond, code, msg)                                         \

@@ -62,6 +62,7 @@ struct BlasDev {             // per geometry, device-resident table entry
     const float* verts;      // mesh [vkeys][nv][3] (corrected mode: area of BSDF-sampled emitter hits; rt3_get_local_geometry)
     uint32_t nv;             // vertices per key
     uint32_t subdiv;         // curves of degree 2 / 3: linear sub-segments per user segment (1 otherwise)
+    const float* colors;     // mesh, optional [nv][4] vertex colours (cuda/LocalGeometry.h:99-110); normals / uvs may be null too (SDK fallbacks)
 };
 
 struct InstanceDev {         // traversal record (64 B)

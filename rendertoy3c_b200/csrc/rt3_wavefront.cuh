@@ -480,6 +480,26 @@ RT3_HD float3 sample_texture(const TexDev& tx, const HitGroupDev& hg, float2 uv)
     return fetch_texture(tx, tu, tv);
 }
 
+// the three object-space vertices of a triangle at a ray time (vertex keys spread evenly over [0, 1], cuda_mesh.h:82-88), as in the traversal
+RT3_HD void triangle_vertices(const BlasDev* b, int i0, int i1, int i2, float time, float3& P0, float3& P1, float3& P2) {
+    if (b->vkeys <= 1u) {
+        P0 = ld3(b->verts + 3 * (size_t)i0); P1 = ld3(b->verts + 3 * (size_t)i1); P2 = ld3(b->verts + 3 * (size_t)i2);
+        return;
+    }
+    const float tc = fminf(fmaxf(time, 0.0f), 1.0f);
+    const float f = tc * (float)(b->vkeys - 1u);
+    int ki = (int)floorf(f);
+    if (ki > (int)b->vkeys - 2) ki = (int)b->vkeys - 2;
+    const float al = f - (float)ki, w = 1.0f - al;
+    const float* k0 = b->verts + 3 * (size_t)ki * b->nv;
+    const float* k1 = k0 + 3 * (size_t)b->nv;
+    const float3 a0 = ld3(k0 + 3 * (size_t)i0), a1 = ld3(k0 + 3 * (size_t)i1), a2 = ld3(k0 + 3 * (size_t)i2);
+    const float3 c0 = ld3(k1 + 3 * (size_t)i0), c1 = ld3(k1 + 3 * (size_t)i1), c2 = ld3(k1 + 3 * (size_t)i2);
+    P0 = v3(w * a0.x + al * c0.x, w * a0.y + al * c0.y, w * a0.z + al * c0.z);
+    P1 = v3(w * a1.x + al * c1.x, w * a1.y + al * c1.y, w * a1.z + al * c1.z);
+    P2 = v3(w * a2.x + al * c2.x, w * a2.y + al * c2.y, w * a2.z + al * c2.z);
+}
+
 RT3_HD LocalGeometry local_geometry(const TravScene& sc, const HitRec& h, float3 o, float3 d, float time) {
     LocalGeometry lg;
     const InstanceDev* in = sc.instances + h.inst;
@@ -489,9 +509,16 @@ RT3_HD LocalGeometry local_geometry(const TravScene& sc, const HitRec& h, float3
     if (b->type == PRIM_TRI || b->type == PRIM_TRI_MOTION) {  // closehit_radiance.cu:66-73 (key-0 normals / uvs: create_sbt binds the buffer start)
         const int i0 = b->idx[3 * (size_t)h.prim], i1 = b->idx[3 * (size_t)h.prim + 1], i2 = b->idx[3 * (size_t)h.prim + 2];
         const float w0 = 1.0f - h.u - h.v;
-        n_obj = add(add(mul(ld3(b->normals + 3 * (size_t)i0), w0), mul(ld3(b->normals + 3 * (size_t)i1), h.u)), mul(ld3(b->normals + 3 * (size_t)i2), h.v));
-        lg.UV.x = w0 * b->uvs[2 * (size_t)i0] + h.u * b->uvs[2 * (size_t)i1] + h.v * b->uvs[2 * (size_t)i2];
-        lg.UV.y = w0 * b->uvs[2 * (size_t)i0 + 1] + h.u * b->uvs[2 * (size_t)i1 + 1] + h.v * b->uvs[2 * (size_t)i2 + 1];
+        if (b->normals) n_obj = add(add(mul(ld3(b->normals + 3 * (size_t)i0), w0), mul(ld3(b->normals + 3 * (size_t)i1), h.u)), mul(ld3(b->normals + 3 * (size_t)i2), h.v));
+        else {  // the SDK's fallback (cuda/LocalGeometry.h:120-124): the geometric normal
+            float3 P0, P1, P2;
+            triangle_vertices(b, i0, i1, i2, time, P0, P1, P2);
+            n_obj = cross(sub(P1, P0), sub(P2, P0));
+        }
+        if (b->uvs) {
+            lg.UV.x = w0 * b->uvs[2 * (size_t)i0] + h.u * b->uvs[2 * (size_t)i1] + h.v * b->uvs[2 * (size_t)i2];
+            lg.UV.y = w0 * b->uvs[2 * (size_t)i0 + 1] + h.u * b->uvs[2 * (size_t)i1 + 1] + h.v * b->uvs[2 * (size_t)i2 + 1];
+        } else lg.UV = make_float2(h.u, h.v);  // LocalGeometry.h:150-152
     } else {
         float3 oo, od;
         instance_ray(sc, in, t1, time, o, d, oo, od);
@@ -503,7 +530,7 @@ RT3_HD LocalGeometry local_geometry(const TravScene& sc, const HitRec& h, float3
         } else {  // cuda/curve.h:382-425 surfaceNormal<LinearInterpolator>
             const float4 c0 = b->cr[b->seg[h.prim]], c1 = b->cr[b->seg[h.prim] + 1];
             if (h.u == 0.0f) n_obj = sub(ps, v3(c0));
-            else if (h.u >= 1.0f) n_obj = sub(ps, v3(c1));
+            else if (h.u >= 1.0f) n_obj = sub(ps, add(sub(v3(c1), v3(c0)), v3(c0)));  // end point rebuilt from the interpolator's coefficients, as the SDK does (curve.h:389-394)
             else {
                 const float3 dd3 = sub(v3(c1), v3(c0));
                 const float dr = c1.w - c0.w;
@@ -537,12 +564,13 @@ RT3_HD LocalGeometry local_geometry(const TravScene& sc, const HitRec& h, float3
 // object-space derivatives dpdu, dpdv, dndu, dndv exactly as the SDK forms them (not transformed, LocalGeometry.h:126-160).
 // Spheres and curves (left empty by the SDK, LocalGeometry.h:164-167) get P = o + t d, N = Ng = their D7 normal,
 // UV as in the shade stage and zero derivatives.
-struct LocalGeometryFull { float3 P, N, Ng; float2 UV; float3 dndu, dndv, dpdu, dpdv; };
+struct LocalGeometryFull { float3 P, N, Ng; float2 UV; float3 dndu, dndv, dpdu, dpdv; float4 color; };
 
 RT3_HD LocalGeometryFull local_geometry_full(const TravScene& sc, const HitRec& h, float3 o, float3 d, float time) {
     LocalGeometryFull lg;
     const float3 z = v3(0.0f, 0.0f, 0.0f);
     lg.P = z; lg.N = z; lg.Ng = z; lg.UV = make_float2(0.0f, 0.0f); lg.dndu = z; lg.dndv = z; lg.dpdu = z; lg.dpdv = z;
+    lg.color = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
     const InstanceDev* in = sc.instances + h.inst;
     const BlasDev* b = sc.blas + in->blas;
     const float t1 = sc.hitgroups[h.inst].t1;
@@ -554,44 +582,48 @@ RT3_HD LocalGeometryFull local_geometry_full(const TravScene& sc, const HitRec& 
     if (b->type == PRIM_TRI || b->type == PRIM_TRI_MOTION) {
         const int i0 = b->idx[3 * (size_t)h.prim], i1 = b->idx[3 * (size_t)h.prim + 1], i2 = b->idx[3 * (size_t)h.prim + 2];
         float3 P0, P1, P2;
-        if (b->vkeys <= 1u) {
-            P0 = ld3(b->verts + 3 * (size_t)i0); P1 = ld3(b->verts + 3 * (size_t)i1); P2 = ld3(b->verts + 3 * (size_t)i2);
-        } else {  // vertex keys at the ray time, as in the traversal
-            const float tc = fminf(fmaxf(time, 0.0f), 1.0f);
-            const float f = tc * (float)(b->vkeys - 1u);
-            int ki = (int)floorf(f);
-            if (ki > (int)b->vkeys - 2) ki = (int)b->vkeys - 2;
-            const float al = f - (float)ki, w = 1.0f - al;
-            const float* k0 = b->verts + 3 * (size_t)ki * b->nv;
-            const float* k1 = k0 + 3 * (size_t)b->nv;
-            const float3 a0 = ld3(k0 + 3 * (size_t)i0), a1 = ld3(k0 + 3 * (size_t)i1), a2 = ld3(k0 + 3 * (size_t)i2);
-            const float3 c0 = ld3(k1 + 3 * (size_t)i0), c1 = ld3(k1 + 3 * (size_t)i1), c2 = ld3(k1 + 3 * (size_t)i2);
-            P0 = v3(w * a0.x + al * c0.x, w * a0.y + al * c0.y, w * a0.z + al * c0.z);
-            P1 = v3(w * a1.x + al * c1.x, w * a1.y + al * c1.y, w * a1.z + al * c1.z);
-            P2 = v3(w * a2.x + al * c2.x, w * a2.y + al * c2.y, w * a2.z + al * c2.z);
-        }
+        triangle_vertices(b, i0, i1, i2, time, P0, P1, P2);
         const float w0 = 1.0f - h.u - h.v;
         float3 p = add(add(mul(P0, w0), mul(P1, h.u)), mul(P2, h.v));
         if (moving) p = xform_point(m, p);
         lg.P = xform_point(fs, p);
+        if (b->colors) {  // interpolated vertex colours, LocalGeometry.h:99-106
+            const float* c0 = b->colors + 4 * (size_t)i0, *c1 = b->colors + 4 * (size_t)i1, *c2 = b->colors + 4 * (size_t)i2;
+            lg.color = make_float4(w0 * c0[0] + h.u * c1[0] + h.v * c2[0], w0 * c0[1] + h.u * c1[1] + h.v * c2[1], w0 * c0[2] + h.u * c1[2] + h.v * c2[2],
+                                   w0 * c0[3] + h.u * c1[3] + h.v * c2[3]);
+        }
         float3 ng = cross(sub(P1, P0), sub(P2, P0));
-        const float3 N0 = ld3(b->normals + 3 * (size_t)i0), N1 = ld3(b->normals + 3 * (size_t)i1), N2 = ld3(b->normals + 3 * (size_t)i2);
-        float3 n = add(add(mul(N0, w0), mul(N1, h.u)), mul(N2, h.v));
-        if (moving) { ng = xform_normal_by_inverse(mi, ng); n = xform_normal_by_inverse(mi, n); }
+        if (moving) ng = xform_normal_by_inverse(mi, ng);
         lg.Ng = normalize(xform_normal_by_inverse(si, ng));
-        lg.N = normalize(xform_normal_by_inverse(si, n));
+        float3 N0, N1, N2;
+        if (b->normals) {
+            N0 = ld3(b->normals + 3 * (size_t)i0); N1 = ld3(b->normals + 3 * (size_t)i1); N2 = ld3(b->normals + 3 * (size_t)i2);
+            float3 n = add(add(mul(N0, w0), mul(N1, h.u)), mul(N2, h.v));
+            if (moving) n = xform_normal_by_inverse(mi, n);
+            lg.N = normalize(xform_normal_by_inverse(si, n));
+        } else {  // no vertex normals: the unit world-space geometric normal stands in for all three (LocalGeometry.h:120-124)
+            lg.N = lg.Ng; N0 = lg.Ng; N1 = lg.Ng; N2 = lg.Ng;
+        }
         const float3 dp1 = sub(P0, P2), dp2 = sub(P1, P2), dn1 = sub(N0, N2), dn2 = sub(N1, N2);
-        const float u0x = b->uvs[2 * (size_t)i0], u0y = b->uvs[2 * (size_t)i0 + 1], u1x = b->uvs[2 * (size_t)i1], u1y = b->uvs[2 * (size_t)i1 + 1],
-                    u2x = b->uvs[2 * (size_t)i2], u2y = b->uvs[2 * (size_t)i2 + 1];
-        lg.UV.x = w0 * u0x + h.u * u1x + h.v * u2x;
-        lg.UV.y = w0 * u0y + h.u * u1y + h.v * u2y;
-        const float du1 = u0x - u2x, du2 = u1x - u2x, dv1 = u0y - u2y, dv2 = u1y - u2y;
-        const float det = du1 * dv2 - dv1 * du2;
-        const float invdet = 1.0f / det;
-        lg.dpdu = mul(sub(mul(dp1, dv2), mul(dp2, dv1)), invdet);
-        lg.dpdv = mul(add(mul(dp1, -du2), mul(dp2, du1)), invdet);
-        lg.dndu = mul(sub(mul(dn1, dv2), mul(dn2, dv1)), invdet);
-        lg.dndv = mul(add(mul(dn1, -du2), mul(dn2, du1)), invdet);
+        if (b->uvs) {
+            const float u0x = b->uvs[2 * (size_t)i0], u0y = b->uvs[2 * (size_t)i0 + 1], u1x = b->uvs[2 * (size_t)i1], u1y = b->uvs[2 * (size_t)i1 + 1],
+                        u2x = b->uvs[2 * (size_t)i2], u2y = b->uvs[2 * (size_t)i2 + 1];
+            lg.UV.x = w0 * u0x + h.u * u1x + h.v * u2x;
+            lg.UV.y = w0 * u0y + h.u * u1y + h.v * u2y;
+            const float du1 = u0x - u2x, du2 = u1x - u2x, dv1 = u0y - u2y, dv2 = u1y - u2y;
+            const float det = du1 * dv2 - dv1 * du2;
+            const float invdet = 1.0f / det;
+            lg.dpdu = mul(sub(mul(dp1, dv2), mul(dp2, dv1)), invdet);
+            lg.dpdv = mul(add(mul(dp1, -du2), mul(dp2, du1)), invdet);
+            lg.dndu = mul(sub(mul(dn1, dv2), mul(dn2, dv1)), invdet);
+            lg.dndv = mul(add(mul(dn1, -du2), mul(dn2, du1)), invdet);
+        } else {  // no texcoords: the barycentrics and edge differences (LocalGeometry.h:150-158)
+            lg.UV = make_float2(h.u, h.v);
+            lg.dpdu = neg(dp1);
+            lg.dpdv = add(neg(dp1), dp2);
+            lg.dndu = neg(dn1);
+            lg.dndv = add(neg(dn1), dn2);
+        }
     } else {
         const LocalGeometry g = local_geometry(sc, h, o, d, time);
         lg.P = g.P; lg.N = g.N; lg.Ng = g.N; lg.UV = g.UV;
@@ -614,7 +646,7 @@ RT3_GLOBAL(k_local_geometry, TravScene sc, const float4* rays, const float4* hit
     r[9] = g.UV.x; r[10] = g.UV.y;
     r[11] = g.dndu.x; r[12] = g.dndu.y; r[13] = g.dndu.z; r[14] = g.dndv.x; r[15] = g.dndv.y; r[16] = g.dndv.z;
     r[17] = g.dpdu.x; r[18] = g.dpdu.y; r[19] = g.dpdu.z; r[20] = g.dpdv.x; r[21] = g.dpdv.y; r[22] = g.dpdv.z;
-    r[23] = 1.0f; r[24] = 1.0f; r[25] = 1.0f; r[26] = 1.0f;
+    r[23] = g.color.x; r[24] = g.color.y; r[25] = g.color.z; r[26] = g.color.w;
 }
 
 // rt3_trace output for degree-2 / -3 curves: the traversal reports linear sub-segments; the caller sees
@@ -795,8 +827,12 @@ RT3_HD void shade_slot_corrected(const FrameParams& f, const TravScene& sc, cons
             P = lg.P;
             if (hg.emission[0] != 0.0f || hg.emission[1] != 0.0f || hg.emission[2] != 0.0f) {
                 float wgt = 1.0f;
-                if (depth > 0u) {  // BSDF-sampled emitter hit: weight against the NEE strategy
-                    const BlasDev* b = sc.blas + sc.instances[h.inst].blas;
+                // BSDF-sampled emitter hit: weight against the NEE strategy — where NEE can produce this point at all.  The
+                // light list holds the OBJECT-space key-0 triangles of emissive meshes (buildLightSampler, src/wavefront.cpp:
+                // 257-275, Q15), so only static triangle meshes under an identity instance qualify; an emissive sphere, curve,
+                // deforming mesh or transformed instance is reached by BSDF sampling alone and keeps the full weight.
+                const BlasDev* b = sc.blas + sc.instances[h.inst].blas;
+                if (depth > 0u && b->type == PRIM_TRI && sc.instances[h.inst].identity == 1u) {
                     const float3 v0 = ld3(b->verts + 3 * (size_t)b->idx[3 * (size_t)h.prim]), v1 = ld3(b->verts + 3 * (size_t)b->idx[3 * (size_t)h.prim + 1]),
                                  v2 = ld3(b->verts + 3 * (size_t)b->idx[3 * (size_t)h.prim + 2]);
                     const float3 nrm = cross(sub(v1, v0), sub(v2, v0));

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <thread>
 
 #include "image_writer.hpp"
 #include "obj_loader.hpp"
@@ -25,16 +26,20 @@ int main(int argc, char** argv) {
     float eye[3] = {5, 5, 5}, lookat[3] = {0, 1, 0}, up[3] = {0, 1, 0}, fovy = 45.0f;  // initCameraState, wavefront.cpp:238-243
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
-        auto f3 = [&](float* v) { for (int k = 0; k < 3; ++k) v[k] = (float)std::atof(argv[++i]); };
-        if (a == "--scene") scene = argv[++i];
-        else if (a == "--key") key_files.push_back(argv[++i]);
-        else if (a == "--out") out = argv[++i];
-        else if (a == "--width") width = std::atoi(argv[++i]);
-        else if (a == "--height") height = std::atoi(argv[++i]);
-        else if (a == "--spp") spp = std::atoi(argv[++i]);
-        else if (a == "--spl") spl = std::atoi(argv[++i]);
-        else if (a == "--max-depth") max_depth = std::atoi(argv[++i]);
-        else if (a == "--gpus") gpus = std::atoi(argv[++i]);
+        auto value = [&]() -> const char* {   // the argument of option `a`
+            if (i + 1 >= argc) { std::fprintf(stderr, "option %s needs a value\n", a.c_str()); std::exit(2); }
+            return argv[++i];
+        };
+        auto f3 = [&](float* v) { for (int k = 0; k < 3; ++k) v[k] = (float)std::atof(value()); };
+        if (a == "--scene") scene = value();
+        else if (a == "--key") key_files.push_back(value());
+        else if (a == "--out") out = value();
+        else if (a == "--width") width = std::atoi(value());
+        else if (a == "--height") height = std::atoi(value());
+        else if (a == "--spp") spp = std::atoi(value());
+        else if (a == "--spl") spl = std::atoi(value());
+        else if (a == "--max-depth") max_depth = std::atoi(value());
+        else if (a == "--gpus") gpus = std::atoi(value());
         else if (a == "--decode-image" && i + 2 < argc) {  // utility: decode a texture file as loadOBJ would, dump w, h + RGBA8 (bottom row first)
             Texture t;
             std::string why;
@@ -47,15 +52,18 @@ int main(int argc, char** argv) {
             std::fclose(f);
             return 0;
         }
-        else if (a == "--mode") mode = std::atoi(argv[++i]);
-        else if (a == "--tonemap") tonemap = argv[++i];  // none | aces (the reference viewer's display curve; 8-bit outputs only)  // 0 reference-faithful, 1 corrected, 2 corrected + power light sampler
-        else if (a == "--fovy") fovy = (float)std::atof(argv[++i]);
+        else if (a == "--mode") mode = std::atoi(value());
+        else if (a == "--tonemap") tonemap = value();  // none | aces (the reference viewer's display curve; 8-bit outputs only)  // 0 reference-faithful, 1 corrected, 2 corrected + power light sampler
+        else if (a == "--fovy") fovy = (float)std::atof(value());
         else if (a == "--eye") f3(eye);
         else if (a == "--lookat") f3(lookat);
         else if (a == "--up") f3(up);
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     if (scene.empty()) { std::fprintf(stderr, "usage: wavefront --scene file.obj [options]\n"); return 2; }
+    if (width <= 0 || height <= 0 || spp <= 0 || spl <= 0 || gpus <= 0) { std::fprintf(stderr, "wavefront: width, height, spp, spl and gpus must be positive\n"); return 2; }
+    const int subframes = (spp + spl - 1) / spl;
+    if (gpus > subframes) gpus = subframes;   // a GPU without a subframe would have no film to reduce
     try {
         std::vector<Mesh> meshes;
         std::vector<Texture> textures;
@@ -74,13 +82,25 @@ int main(int argc, char** argv) {
         params.accum_mode = gpus > 1 ? 1 : 0;
         for (int k = 0; k < 3; ++k) params.eye[k] = eye[k];
         RT3HOST_CHECK(rt3_camera_uvw(eye, lookat, up, fovy, (float)width / (float)height, params.U, params.V, params.W));  // handleCameraUpdate
-        const int subframes = (spp + spl - 1) / spl;
         const auto t0 = std::chrono::steady_clock::now();
-        for (int sf = 0; sf < subframes; ++sf) {
-            params.subframe_index = (uint32_t)sf;
-            RT3HOST_CHECK(rt3_launch_subframe(ctx[(size_t)(sf % gpus)]->ctx(), &params));  // asynchronous: GPUs run concurrently
-        }
-        for (auto& c : ctx) RT3HOST_CHECK(rt3_sync(c->ctx()));
+        // GPU g renders subframes g, g + N, ... from its own host thread (one thread per context): a launch with unbounded
+        // depth waits for its queue counters every bounce, which must not hold up the other devices
+        std::vector<std::string> failures((size_t)gpus);
+        auto drive = [&](int g) {
+            try {
+                RenderSettings mine = params;
+                for (int sf = g; sf < subframes; sf += gpus) {
+                    mine.subframe_index = (uint32_t)sf;
+                    RT3HOST_CHECK(rt3_launch_subframe(ctx[(size_t)g]->ctx(), &mine));
+                }
+                RT3HOST_CHECK(rt3_sync(ctx[(size_t)g]->ctx()));
+            } catch (const std::exception& e) { failures[(size_t)g] = e.what(); }
+        };
+        std::vector<std::thread> workers;
+        for (int g = 1; g < gpus; ++g) workers.emplace_back(drive, g);
+        drive(0);
+        for (auto& w : workers) w.join();
+        for (const std::string& f : failures) if (!f.empty()) throw Exception(f);
         if (gpus > 1) {
             std::vector<rt3_context_t> raw;
             for (auto& c : ctx) raw.push_back(c->ctx());

@@ -26,6 +26,7 @@ class Geometry:
     seg: np.ndarray = None        # curves [nseg] i32 first control point
     degree: int = 1               # curves: 1 linear, 2 / 3 uniform B-spline (segment i uses control points seg[i] .. seg[i] + degree)
     vert_keys: np.ndarray = None  # mesh, optional [keys,nv,3]: vertex-key (deformation) motion; verts = key 0
+    colors: np.ndarray = None     # mesh, optional [nv,4] vertex colours (cuda/LocalGeometry.h:99-110); normals / uvs may be None too (SDK fallbacks)
 
     @property
     def nprims(self):
@@ -83,6 +84,8 @@ def replay(desc, be):
     for g in desc.geoms:
         if g.kind == "mesh":
             handles.append(be.mesh_create(g.verts if g.vert_keys is None else g.vert_keys, g.idx, g.normals, g.uvs))
+            if g.colors is not None:
+                be.mesh_set_colors(handles[-1], g.colors)
         elif g.kind == "spheres":
             handles.append(be.spheres_create(g.cr))
         else:
@@ -389,6 +392,24 @@ def splines(n_strands=40, width=80, height=48, spp=16, max_depth=4, seed=11):
     inst.append(Instance(len(geoms) - 1, diffuse=(0.6, 0.6, 0.6)))
     cam = Camera(eye=(0.0, 2.2, 5.0), lookat=(0.0, 0.6, 0.0), fovy=45.0)
     return SceneDesc("splines", geoms, inst, [], cam, width, height, spp, max_depth)
+
+
+def fallbacks(blob_n=10, width=80, height=48, spp=16, max_depth=5):
+    """the deforming scene with the SDK's optional vertex attributes exercised (cuda/LocalGeometry.h:99-124,150-158): the moving
+    blob has no normals and carries vertex colours, its static (transformed) copy has no texcoords, the floor has neither and
+    is textured, so its texture is addressed by the barycentrics"""
+    d = deforming(blob_n=blob_n, width=width, height=height, spp=spp, max_depth=max_depth)
+    rng = np.random.RandomState(17)
+    d.geoms[0].normals = None
+    d.geoms[0].colors = rng.rand(len(d.geoms[0].verts), 4).astype(np.float32)
+    d.geoms[1].uvs = None
+    d.geoms[1].colors = rng.rand(len(d.geoms[1].verts), 4).astype(np.float32)
+    d.geoms[3].normals = None
+    d.geoms[3].uvs = None
+    d.textures.append(Texture(value_noise_texture(32, 5, cells=8)))
+    d.instances[3].tex = 0
+    d.name = "fallbacks"
+    return d
 
 
 def by_name(name, **kw):

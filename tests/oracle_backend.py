@@ -36,7 +36,7 @@ def lib():
         L.rt3o_kat_rnd.restype = C.c_float
         L.rt3o_kat_tea4.restype = C.c_uint32
         L.rt3o_kat_tea4.argtypes = [C.c_uint32, C.c_uint32]
-        for name in ("rt3o_scene_destroy", "rt3o_mesh_create", "rt3o_spheres_create", "rt3o_curves_create", "rt3o_texture_create",
+        for name in ("rt3o_scene_destroy", "rt3o_mesh_create", "rt3o_mesh_set_colors", "rt3o_spheres_create", "rt3o_curves_create", "rt3o_texture_create",
                      "rt3o_accel_append_instance", "rt3o_accel_append_animated_instance", "rt3o_accel_build",
                      "rt3o_scene_set_hitgroup", "rt3o_scene_set_texture_transform", "rt3o_scene_set_lights", "rt3o_trace", "rt3o_get_local_geometry", "rt3o_launch_subframe",
                      "rt3o_download_accum", "rt3o_download_frame", "rt3o_get_stats", "rt3o_reset_stats", "rt3o_kat_fetch_texture", "rt3o_kat_sample_texture"):
@@ -75,10 +75,17 @@ class OracleScene:
         return rc
 
     def mesh_create(self, verts, idx, normals, uvs):
-        v, n, t = _f32(verts), _f32(normals), _f32(uvs)
+        v = _f32(verts)
+        n = _f32(normals) if normals is not None else None
+        t = _f32(uvs) if uvs is not None else None
         i = np.ascontiguousarray(idx, dtype=np.int32)
         keys, nv = (v.shape[0], v.shape[1]) if v.ndim == 3 else (1, len(v))
-        return self._chk(self.L.rt3o_mesh_create(self.s, fptr(v), C.c_int(keys), C.c_int(nv), iptr(i), C.c_int(len(i)), fptr(n), fptr(t)))
+        return self._chk(self.L.rt3o_mesh_create(self.s, fptr(v), C.c_int(keys), C.c_int(nv), iptr(i), C.c_int(len(i)), fptr(n) if n is not None else None,
+                                                 fptr(t) if t is not None else None))
+
+    def mesh_set_colors(self, blas, rgba):
+        c = _f32(rgba)
+        self._chk(self.L.rt3o_mesh_set_colors(self.s, C.c_int(blas), fptr(c)))
 
     def spheres_create(self, cr):
         c = _f32(cr)

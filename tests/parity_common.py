@@ -14,6 +14,7 @@ SMALL = {
     "motion": lambda: scenes.motion(n_inst=8, blob_n=8, n_spheres=10, n_curves=50, width=80, height=48),
     "deforming": lambda: scenes.deforming(blob_n=10, width=80, height=48),
     "splines": lambda: scenes.splines(),
+    "fallbacks": lambda: scenes.fallbacks(),
 }
 
 

@@ -99,3 +99,16 @@ def test_texcoord_transform_matches_oracle(emul_lib):
     with Context(0, lib_path=emul_lib) as e:
         o = build_pair(desc, e)
         check_render(e, o, desc, subframes=1)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_corrected_mode_with_emitters_nee_cannot_reach(emul_lib, mode):
+    """every instance of the motion scene emits — spheres, curves, animated and transformed meshes.  Their BSDF-sampled
+    hits keep the full weight (the light list only holds object-space triangles of identity meshes, Q15); none of them
+    may be looked up as a static triangle mesh (null vertex arrays on spheres / curves)"""
+    desc = SMALL["motion"]()
+    for k, inst in enumerate(desc.instances):
+        inst.emission = (0.5 + 0.25 * (k % 3), 0.4, 0.3)
+    with Context(0, lib_path=emul_lib) as e:
+        o = build_pair(desc, e)
+        check_render(e, o, desc, subframes=2, mode=mode)

@@ -15,7 +15,7 @@ HOST = os.path.join(ROOT, "rendertoy3c_b200", "host")
 
 
 def build_host(libdir, libname, out):
-    subprocess.run(["g++", "-O2", "-std=c++17", "-o", out, os.path.join(HOST, "wavefront.cpp"), "-L" + libdir, "-l:" + libname,
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", out, os.path.join(HOST, "wavefront.cpp"), "-L" + libdir, "-l:" + libname,
                     "-Wl,-rpath," + libdir], check=True)
     return out
 
