@@ -18,6 +18,17 @@ closes the job and is inside the timed region.
            write = 68 B/ray) / its CUDA-event time vs the measured HBM copy peak
   cpu_baseline: the scalar C++ oracle (oracle/, "port": the reference has no CPU renderer and its
            OptiX path cannot be built here) on all host cores, on a bounded sample of the same scene
+  configs (N=1): the other BASELINE configs, each measured in this run with its own context — C1 Cornell 512^2 depth 4,
+           C3 1000 instances x 100 k triangles + 1000 spheres, C4 64 two-key motion instances + spheres + 10 k curve segments:
+           Mrays/s, ms per subframe, stage times, rays by type
+  c5 (every N): BASELINE configs[4] — the C2 scene at 3840x2160, 128 subframes of 8 spl IN TOTAL split over the ranks (strong
+           scaling), render and reduce timed separately
+  roofline_issue: the bound the extend kernel is actually against — warp instructions issued per second vs SMs x 4 issue
+           slots x SM clock; instructions per ray come from the newest committed ncu capture, rays/s and clock from this run
+  traversal_counters: wide nodes and primitive tests per ray of one subframe, counted on the device in this run by the
+           -DRT3_STATS build of the same sources (rendertoy3c_b200/librt3_stats.so)
+  N>1 adds reduce_check (N subframes sample-partitioned + all-reduce vs the same N subframes on rank 0 alone) and cpp_host (the
+           single-process C++ host with --gpus N, i.e. rt3_allreduce_accum over NCCL)
 --impl reference: that CPU oracle as the reference arm (the reference itself is OptiX-only).
 """
 import argparse
@@ -48,6 +59,9 @@ def parse():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 / C5 records of the N=1 line")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 record (3840x2160, --c5-subframes subframes in total over all ranks)")
+    ap.add_argument("--c5-subframes", type=int, default=128, help="C5: subframes of 8 spl in total over all ranks (128 = 1024 spp)")
     return ap.parse_args()
 
 
@@ -182,7 +196,8 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": config_dict(args, args.gpus),
+        "data": "synthetic", "config": dict(config_dict(args, args.gpus), film_rendered_per_step="%dx%d" % (w, h), paths_rendered_per_step=w * h * SPL,
+                                             note="same scene, camera, depth and samples per pixel; the film is reduced so that a CPU step stays bounded (Mrays/s is per ray)"),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "samples_per_s": tot_samples / tot_s,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -208,11 +223,143 @@ def issue_evidence():
     blocks = [b for b in txt.split("=" * 100) if "k_traverse<0" in b]
     vals = {}
     for key in ("smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
-                "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"):
+                "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum"):
         v = [float(m.group(1)) for b in blocks for m in [re.search(re.escape(key) + r"\s+([0-9.]+)", b)] if m]
         if v:
             vals[key] = round(sum(v) / len(v), 2)
     return {"source": "profiles/" + os.path.basename(cand[-1]), "extend_launches_averaged": len(blocks), **vals}
+
+
+def issue_roofline(kernel_prefix, ext_ms_per_step, sm_mhz):
+    """The bound the traversal kernel is actually against: warp instructions issued per second vs SMs x 4 schedulers x
+    SM clock.  Instruction counts need ncu: they come from the newest committed launch list of this command that carries
+    smsp__inst_executed.sum (profiles/r*_launch_shares.json); the kernel time and the clock are this run's."""
+    import glob
+    sms, per_sm = 148, 4
+    clock_hz = (sm_mhz or 1965.0) * 1e6
+    peak = sms * per_sm * clock_hz
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_launch_shares.json")), reverse=True):
+        ks = json.load(open(path))["kernels"]
+        inst = sum(v.get("warp_inst", 0) for k, v in ks.items() if k.startswith(kernel_prefix))
+        if inst > 0 and ext_ms_per_step > 0:
+            ach = inst / (ext_ms_per_step * 1e-3)
+            return {"bound": "issue", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": ach / peak,
+                    "warp_instructions_per_step": inst, "instructions_source": "profiles/" + os.path.basename(path) + " (ncu smsp__inst_executed.sum, same command)",
+                    "kernel_ms_per_step": ext_ms_per_step, "sm_mhz": sm_mhz, "peak_is": "148 SMs x 4 issue slots x SM clock"}
+    ev = issue_evidence()
+    if not ev or "smsp__issue_active.avg.pct_of_peak_sustained_active" not in ev:
+        return None
+    frac = ev["smsp__issue_active.avg.pct_of_peak_sustained_active"] / 100.0
+    return {"bound": "issue", "achieved": frac * peak / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": frac, "source": ev["source"],
+            "note": "no committed launch list with instruction counts yet: fraction = issue-slot utilisation of the committed full capture", "peak_is": "148 SMs x 4 issue slots x SM clock"}
+
+
+def time_subframes(g, make, warmup, steps, stream, torch):
+    """device-timed render of `steps` subframes after `warmup`: (ms, stats of the timed region)"""
+    for i in range(warmup):
+        g.launch_subframe(make(i))
+    g.sync()
+    g.reset_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for i in range(steps):
+        g.launch_subframe(make(warmup + i))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), g.stats()
+
+
+def run_config(name, desc, local, torch, steps=3, warmup=2, spl=SPL, max_depth=None):
+    """one BASELINE config measured like the headline: own context, device-resident, CUDA events on the library's stream"""
+    from rendertoy3c_b200 import scenes
+    from rendertoy3c_b200.api import Context, make_settings
+    t0 = time.perf_counter()
+    g = Context(local)
+    scenes.replay(desc, g)
+    g.sync()
+    build_s = time.perf_counter() - t0
+    uvw = g.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, desc.width / desc.height)
+    stream = torch.cuda.ExternalStream(g.stream(), device=torch.device("cuda", local))
+    depth = desc.max_depth if max_depth is None else max_depth
+
+    def make(i):
+        return make_settings(desc, uvw, i, samples_per_launch=spl, max_depth=depth)
+
+    ms, st = time_subframes(g, make, warmup, steps, stream, torch)
+    rays = st["rays_primary"] + st["rays_bounce"] + st["rays_shadow"]
+    assert st["error_flags"] == 0, name + ": traversal stack overflow"
+    g.set_option("timing", 1)
+    g.reset_stats()
+    g.launch_subframe(make(warmup + steps))
+    g.sync()
+    s = g.stats()
+    g.set_option("timing", 0)
+    out = {"workload": desc.name, "instanced_primitives": int(desc.total_instanced_prims()), "width": desc.width, "height": desc.height, "samples_per_step": spl,
+           "max_depth": depth, "steps": steps, "warmup": warmup, "value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms / steps,
+           "samples_per_s": st["samples"] / (ms * 1e-3), "rays_per_step": {k: st["rays_" + k] // steps for k in ("primary", "bounce", "shadow")},
+           "stage_ms": {k: s[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_connect", "ms_resolve", "ms_total")},
+           "upload_and_build_s": build_s}
+    g.close()
+    return out
+
+
+def traversal_counters(desc, local):
+    """wide nodes visited and primitive tests per ray, counted on the device by the -DRT3_STATS build of the same sources
+    (one 960x540 x 8-spl subframe: the counters are 32 bit)"""
+    from rendertoy3c_b200 import scenes
+    from rendertoy3c_b200.api import Context, make_settings
+    lib = os.path.join(ROOT, "rendertoy3c_b200", "librt3_stats.so")
+    if not os.path.exists(lib):
+        return {"unavailable": "rendertoy3c_b200/librt3_stats.so not built"}
+    g = Context(local, lib_path=lib)
+    scenes.replay(desc, g)
+    w, h = 960, 540
+    uvw = g.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, w / h)
+    g.debug_counters()
+    g.reset_stats()
+    g.launch_subframe(make_settings(desc, uvw, 0, samples_per_launch=SPL, width=w, height=h, max_depth=desc.max_depth))
+    g.sync()
+    c = g.debug_counters()
+    st = g.stats()
+    g.close()
+    rays = max(1, int(c[5]))
+    return {"wide_nodes_per_ray": c[2] / rays, "primitive_tests_per_ray": c[3] / rays, "rounds_per_ray": c[4] / rays, "rays_counted": rays,
+            "rays_by_type": {k: st["rays_" + k] for k in ("primary", "bounce", "shadow")}, "film": "%dx%d x %d spl, all ray types of one subframe" % (w, h, SPL),
+            "library": "rendertoy3c_b200/librt3_stats.so (-DRT3_STATS build of the same sources; not the timed library)"}
+
+
+def cpp_host_run(n_gpus, local_root):
+    """the single-process C++ host (rendertoy3c_b200/host/wavefront.cpp) with --gpus N: loadOBJ, one context per GPU,
+    rt3_allreduce_accum (NCCL resolved with dlopen) — run once from rank 0 after the timed work"""
+    import tempfile
+    from rendertoy3c_b200 import scenes
+    exe = os.path.join(ROOT, "rendertoy3c_b200", "host", "wavefront")
+    if not os.path.exists(exe):
+        return {"unavailable": "rendertoy3c_b200/host/wavefront not built"}
+    d = tempfile.mkdtemp(prefix="rt3_host_")
+    desc = scenes.cornell(width=256, height=256)
+    obj = os.path.join(d, "cornell.obj")
+    scenes.write_obj(desc, obj)
+    c = desc.camera
+    res = {}
+    frames = {}
+    for n in (1, n_gpus):
+        out = os.path.join(d, "out_%d.ppm" % n)
+        cmd = [exe, "--scene", obj, "--width", "256", "--height", "256", "--spp", str(8 * max(8, n_gpus)), "--max-depth", "4", "--fovy", repr(c.fovy), "--gpus", str(n), "--out", out,
+               "--eye", *map(repr, c.eye), "--lookat", *map(repr, c.lookat), "--up", *map(repr, c.up)]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        if r.returncode != 0:
+            return {"failed": (r.stderr or r.stdout)[-400:], "gpus": n}
+        res["gpus_%d" % n] = json.loads(r.stdout.strip().splitlines()[-1])
+        with open(out, "rb") as f:
+            frames[n] = f.read()
+    import numpy as np
+    a = np.frombuffer(frames[1][-256 * 256 * 3:], dtype=np.uint8).astype(int)
+    b = np.frombuffer(frames[n_gpus][-256 * 256 * 3:], dtype=np.uint8).astype(int)
+    res["frame_max_lsb_vs_1gpu"] = int(np.abs(a - b).max())
+    res["what"] = "Cornell 256x256, %d spp through rt3_allreduce_accum on %d GPUs vs the same render on one GPU" % (8 * max(8, n_gpus), n_gpus)
+    return res
 
 
 def run_rt3(args):
@@ -229,14 +376,15 @@ def run_rt3(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; librt3 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
     K, Wm = args.steps, args.warmup
     desc = scenes.terrain(n=args.grid, width=args.width, height=args.height)
     g = Context(local)
     scenes.replay(desc, g)
     uvw = g.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, args.width / args.height)
-    stream = torch.cuda.ExternalStream(g.stream(), device=torch.device("cuda", local))
+    stream = torch.cuda.ExternalStream(g.stream(), device=dev)
     accum_mode = 1 if world > 1 else 0
 
     def settings(i):  # rank r renders subframes r, r+N, ...
@@ -247,13 +395,13 @@ def run_rt3(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def reduce_and_finalize(nsub):
+    def reduce_and_finalize(ctx, nsub_total):
         if world > 1:
-            ptr, n = g.accum_device_ptr()
-            t = torch.as_tensor(_CudaArray(ptr, n), device=torch.device("cuda", local))
+            ptr, n = ctx.accum_device_ptr()
+            t = torch.as_tensor(_CudaArray(ptr, n), device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             torch.cuda.synchronize()
-            g.finalize_accum(nsub * world)
+            ctx.finalize_accum(nsub_total)
 
     # ---- warm-up
     for i in range(Wm):
@@ -261,7 +409,7 @@ def run_rt3(args):
     g.sync()
     if world > 1:
         g.clear_accum()
-        reduce_and_finalize(1)
+        reduce_and_finalize(g, world)
         g.clear_accum()
     g.sync()
 
@@ -278,13 +426,14 @@ def run_rt3(args):
         g.launch_subframe(settings(Wm + i))
     if world > 1:
         g.sync()
-        reduce_and_finalize(K)
+        reduce_and_finalize(g, K * world)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     st = g.stats()
     launches = st["kernel_launches"] - l0
     rays = st["rays_primary"] + st["rays_bounce"] + st["rays_shadow"]
+    rays_by_type = {k: st["rays_" + k] for k in ("primary", "bounce", "shadow")}
     samples = st["samples"]
     assert st["error_flags"] == 0, "traversal stack overflow"
 
@@ -300,7 +449,7 @@ def run_rt3(args):
             g.download_frame_into(frame.data_ptr())
     if world > 1:
         g.sync()
-        reduce_and_finalize(K)
+        reduce_and_finalize(g, K * world)
         g.download_frame_into(frame.data_ptr())
     g.sync()
     barrier()
@@ -323,6 +472,81 @@ def run_rt3(args):
         stage = {k: s[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_connect", "ms_resolve", "ms_total")}
     g.set_option("timing", 0)
 
+    # ---- N > 1: the partitioned image equals the single-GPU image (fp32 summation order apart)
+    reduce_check = None
+    if world > 1:
+        g.clear_accum()
+        g.launch_subframe(make_settings(desc, uvw, rank, samples_per_launch=SPL, accum_mode=1, max_depth=8))     # subframe index = rank
+        g.sync()
+        reduce_and_finalize(g, world)
+        if rank == 0:
+            part_accum, part_frame = g.download_accum(), g.download_frame()
+            g.clear_accum()
+            for sf in range(world):
+                g.launch_subframe(make_settings(desc, uvw, sf, samples_per_launch=SPL, accum_mode=1, max_depth=8))
+            g.sync()
+            g.finalize_accum(world)
+            one_accum, one_frame = g.download_accum(), g.download_frame()
+            a, b = part_accum[..., :3].astype(np.float64), one_accum[..., :3].astype(np.float64)
+            reduce_check = {"max_rel_diff": float((np.abs(a - b) / np.maximum(np.abs(b), 1e-3)).max()), "frame_max_lsb": int(np.abs(part_frame.astype(int) - one_frame.astype(int)).max()),
+                            "bit_identical_pixels": float((part_accum.view(np.uint32) == one_accum.view(np.uint32)).all(axis=-1).mean()),
+                            "what": "%d subframes x %d spl at %dx%d: one per rank + NCCL sum + finalize, vs the same %d subframes on rank 0 alone" % (world, SPL, args.width, args.height, world)}
+        barrier()
+    g.close()
+
+    # ---- C5 as BASELINE names it: 3840x2160, 1024 spp = 128 subframes of 8 IN TOTAL, split over the ranks (strong scaling)
+    c5 = None
+    if not args.no_c5:
+        d5 = scenes.terrain(n=args.grid, width=3840, height=2160)
+        g5 = Context(local)
+        scenes.replay(d5, g5)
+        uvw5 = g5.camera_uvw(d5.camera.eye, d5.camera.lookat, d5.camera.up, d5.camera.fovy, 3840 / 2160)
+        stream5 = torch.cuda.ExternalStream(g5.stream(), device=dev)
+        total_sub = args.c5_subframes
+        mine = [sf for sf in range(total_sub) if sf % world == rank]
+        for sf in mine[:1]:
+            g5.launch_subframe(make_settings(d5, uvw5, sf, samples_per_launch=SPL, accum_mode=1, max_depth=8))
+        g5.sync()
+        if world > 1:
+            reduce_and_finalize(g5, world)
+        g5.clear_accum()
+        g5.reset_stats()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        barrier()
+        ev[0].record(stream5)
+        for sf in mine:
+            g5.launch_subframe(make_settings(d5, uvw5, sf, samples_per_launch=SPL, accum_mode=1, max_depth=8))
+        ev[1].record(stream5)
+        g5.sync()
+        if world > 1:
+            ptr, n = g5.accum_device_ptr()
+            t = torch.as_tensor(_CudaArray(ptr, n), device=dev)
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            r1.record()
+            torch.cuda.synchronize()
+            reduce_ms = r0.elapsed_time(r1)
+        else:
+            reduce_ms = 0.0
+        g5.finalize_accum(total_sub)
+        ev[2].record(stream5)
+        barrier()
+        render_ms = ev[0].elapsed_time(ev[1])
+        s5 = g5.stats()
+        r5 = s5["rays_primary"] + s5["rays_bounce"] + s5["rays_shadow"]
+        vals = torch.tensor([render_ms, reduce_ms], dtype=torch.float64, device="cuda")
+        cnt = torch.tensor([r5, s5["samples"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        total_ms = float(vals[0]) + float(vals[1])
+        c5 = {"workload": "C5: C2 scene at 3840x2160, %d subframes x %d spl = %d spp in total, split over %d GPU(s) (strong scaling)" % (total_sub, SPL, total_sub * SPL, world),
+              "subframes_total": total_sub, "subframes_per_gpu": len(mine), "render_ms_max_over_ranks": float(vals[0]), "reduce_ms_max_over_ranks": float(vals[1]),
+              "reduce_bytes": 3840 * 2160 * 16, "total_ms": total_ms, "value": float(cnt[0]) / (total_ms * 1e-3) / 1e6, "unit": UNIT,
+              "samples_per_s": float(cnt[1]) / (total_ms * 1e-3), "ms_per_subframe_per_gpu": float(vals[0]) / max(1, len(mine))}
+        g5.close()
+
     # ---- max over ranks / totals
     if world > 1:
         t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
@@ -331,6 +555,8 @@ def run_rt3(args):
         c = torch.tensor([rays, samples, rays2, launches], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         rays, samples, rays2, launches = (int(x) for x in c.tolist())
+        dist.barrier()
+        dist.destroy_process_group()
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -356,6 +582,7 @@ def run_rt3(args):
             "config": config_dict(args, world),
             "samples_per_s": samples / (ms * 1e-3),
             "rays_per_step": rays / K / world,
+            "rays_by_type_rank0": rays_by_type,
             "e2e": {"value": rays2 / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(RenderSettings),
                     "d2h_bytes_per_step": args.width * args.height * 4 if world == 1 else args.width * args.height * 4 // K,
                     "what": "rt3_launch_subframe(host settings) + rt3_download_frame(pinned host u8 frame) per step, wall clock"},
@@ -368,17 +595,32 @@ def run_rt3(args):
                          "kernel_share_of_step": ext_ms / tot_ms,
                          "connect_kernel_Mrays_s": con_rays / (con_ms * 1e-3) / 1e6 if con_ms > 0 else None,
                          "whole_path_achieved_GBs": BYTES_PER_RAY_PATH * rays / (ms * 1e-3) / 1e9,
-                         "note": "software BVH traversal is latency/issue bound, not HBM bound (SURVEY 8d): frac is expected to be small; "
-                                 "see profiles/ for issue-slot and L2 counters",
+                         "note": "HBM is the roofline of the queue traffic only: the kernel reads and writes its algorithmic bytes once (traffic ~ 1.0x) and is "
+                                 "bound by instruction issue, see roofline_issue",
                          "issue_bound_evidence": issue_evidence()},
+            "roofline_issue": issue_roofline("k_traverse<0", ext_ms / 2, (clk or {}).get("sm_mhz")),
             "stage_ms_last_step": stage,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(desc, gpu=g)
+        if reduce_check is not None:
+            out["reduce_check"] = reduce_check
+        if c5 is not None:
+            out["c5"] = c5
+        if world == 1:
+            out["traversal_counters"] = traversal_counters(desc, local)
+            if not args.no_configs:
+                cfg = {}
+                cfg["C1"] = run_config("C1", scenes.cornell(width=512, height=512), local, torch, steps=4, warmup=2)
+                cfg["C3"] = run_config("C3", scenes.instanced(width=1920, height=1080), local, torch)
+                cfg["C4"] = run_config("C4", scenes.motion(width=1920, height=1080), local, torch)
+                out["configs"] = cfg
+            if not args.no_cpu_baseline:
+                g2 = Context(local)
+                scenes.replay(desc, g2)
+                out["cpu_baseline"] = cpu_baseline(desc, gpu=g2)
+                g2.close()
+        else:
+            out["cpp_host"] = cpp_host_run(world, ROOT)
         print(json.dumps(out))
-    g.close()
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -1,5 +1,5 @@
 """Per-kernel time shares and DRAM bytes of the last complete subframe in an ncu launch list CSV
-(ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv).
+(ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum[,smsp__inst_executed.sum] --csv).
 usage: python tools/launch_shares.py launches.csv out.json"""
 import csv
 import json
@@ -22,13 +22,16 @@ tot = sum(d["gpu__time_duration.sum"] for d in sub)
 agg = {}
 for d in sub:
     name = d["k"].split("(")[0].replace("void ", "").replace("rt3::", "")
-    a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
+    a = agg.setdefault(name, [0, 0.0, 0.0, 0.0, 0.0])
     a[0] += 1
     a[1] += d["gpu__time_duration.sum"]
     a[2] += d.get("dram__bytes_read.sum", 0)
     a[3] += d.get("dram__bytes_write.sum", 0)
+    a[4] += d.get("smsp__inst_executed.sum", 0)
 out = {"source": sys.argv[1], "total_ms_under_ncu": tot / 1e6, "kernels": {}}
 for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
     print("%-28s launches %2d  %8.3f ms  share %5.1f%%  dram read %7.1f MB write %7.1f MB" % (k, a[0], a[1] / 1e6, 100 * a[1] / tot, a[2] / 1e6, a[3] / 1e6))
     out["kernels"][k] = {"launches": a[0], "ms": a[1] / 1e6, "share": a[1] / tot, "dram_read_MB": a[2] / 1e6, "dram_write_MB": a[3] / 1e6}
+    if a[4] > 0:
+        out["kernels"][k]["warp_inst"] = a[4]   # warp-level instructions of these launches (smsp__inst_executed.sum)
 json.dump(out, open(sys.argv[2], "w"), indent=1)
