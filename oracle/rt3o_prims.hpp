@@ -27,10 +27,14 @@ static inline RayShear make_shear(f3 d) {
     s.kx = s.kz + 1; if (s.kx == 3) s.kx = 0;
     s.ky = s.kx + 1; if (s.ky == 3) s.ky = 0;
     if (get(d, s.kz) < 0.0f) { int t = s.kx; s.kx = s.ky; s.ky = t; }
+    // one division: the reciprocal of the dominant component (clamped away from zero like the slab test's 1/d), Sx and Sy
+    // are products with it.  Every triangle of a ray sees the same constants, which is all watertightness needs.
+    const float eps = 8.271806e-25f;  // 2^-80
     float dz = get(d, s.kz);
-    s.Sx = get(d, s.kx) / dz;
-    s.Sy = get(d, s.ky) / dz;
+    if (!(fabsf(dz) > eps)) dz = copysignf(eps, dz);
     s.Sz = 1.0f / dz;
+    s.Sx = get(d, s.kx) * s.Sz;
+    s.Sy = get(d, s.ky) * s.Sz;
     return s;
 }
 

@@ -18,10 +18,8 @@
 #include "rt3_common.cuh"
 #include "rt3_rt.h"
 
-#ifdef RT3_EMULATE
 #include <algorithm>
 #include <vector>
-#endif
 
 namespace rt3 {
 
@@ -434,9 +432,81 @@ inline void sort_pairs(uint64_t* keys, uint32_t* vals, uint32_t n, Stream st) {
 #endif
 }
 
+// ------------------------------------------------------------------------------------ host SAH builder (small inputs)
+// The TLAS holds a few thousand instance boxes of very different sizes that overlap their neighbours: the case where a
+// Morton-order tree is at its worst (an instance visit costs a ray a transform, three divisions and a BLAS root).  For such
+// small inputs the binary tree is built on the host with the full-sweep surface-area heuristic (every split position along
+// every axis, primitives sorted by centroid), written in the SAME arrays the GPU hierarchy kernels produce — internal
+// nodes 0 .. n-2 (root 0), leaf of sorted position j at id n-1+j, [first, last] = the node's range of sorted positions —
+// and collapsed to the wide layout by the same kernel.  O(n log^2 n); ~1 ms for 1000 boxes.
+struct HostBvh2 {
+    std::vector<int> left, right, first, last;
+    std::vector<float4> nlo, nhi;   // [2n - 1]
+    std::vector<uint32_t> vals;     // sorted position -> primitive
+};
+inline void build_bvh2_sah_host(const std::vector<float4>& plo, const std::vector<float4>& phi, HostBvh2& t) {
+    const int n = (int)plo.size();
+    t.left.assign((size_t)n - 1, 0); t.right.assign((size_t)n - 1, 0); t.first.assign((size_t)n - 1, 0); t.last.assign((size_t)n - 1, 0);
+    t.nlo.assign((size_t)2 * n, make_float4(0, 0, 0, 0)); t.nhi.assign((size_t)2 * n, make_float4(0, 0, 0, 0));
+    t.vals.resize((size_t)n);
+    for (int i = 0; i < n; i++) t.vals[(size_t)i] = (uint32_t)i;
+    struct Box { float lo[3], hi[3]; };
+    auto grow = [&](Box& b, uint32_t p) {
+        const float l[3] = {plo[p].x, plo[p].y, plo[p].z}, h[3] = {phi[p].x, phi[p].y, phi[p].z};
+        for (int k = 0; k < 3; k++) { b.lo[k] = l[k] < b.lo[k] ? l[k] : b.lo[k]; b.hi[k] = h[k] > b.hi[k] ? h[k] : b.hi[k]; }
+    };
+    auto area = [](const Box& b) { const float e[3] = {b.hi[0] - b.lo[0], b.hi[1] - b.lo[1], b.hi[2] - b.lo[2]}; return e[0] * e[1] + e[1] * e[2] + e[2] * e[0]; };
+    const Box empty = {{3.4e38f, 3.4e38f, 3.4e38f}, {-3.4e38f, -3.4e38f, -3.4e38f}};
+    int next_internal = 0;
+    struct Job { int a, b, id; };
+    std::vector<Job> todo;
+    std::vector<float> right_area;
+    std::vector<uint32_t> best_order;
+    todo.push_back({0, n - 1, next_internal++});
+    while (!todo.empty()) {
+        const Job j = todo.back();
+        todo.pop_back();
+        const int cnt = j.b - j.a + 1;
+        float best_cost = 3.4e38f;
+        int best_split = -1;
+        for (int axis = 0; axis < 3; axis++) {
+            std::stable_sort(t.vals.begin() + j.a, t.vals.begin() + j.b + 1, [&](uint32_t p, uint32_t q) {
+                const float cp = axis == 0 ? plo[p].x + phi[p].x : (axis == 1 ? plo[p].y + phi[p].y : plo[p].z + phi[p].z);
+                const float cq = axis == 0 ? plo[q].x + phi[q].x : (axis == 1 ? plo[q].y + phi[q].y : plo[q].z + phi[q].z);
+                return cp < cq;
+            });
+            right_area.assign((size_t)cnt, 0.0f);
+            Box rb = empty;
+            for (int i = cnt - 1; i > 0; i--) { grow(rb, t.vals[(size_t)(j.a + i)]); right_area[(size_t)i] = area(rb); }
+            Box lb = empty;
+            for (int i = 0; i < cnt - 1; i++) {   // split after sorted element i
+                grow(lb, t.vals[(size_t)(j.a + i)]);
+                const float cost = area(lb) * (float)(i + 1) + right_area[(size_t)(i + 1)] * (float)(cnt - 1 - i);
+                if (cost < best_cost) { best_cost = cost; best_split = i; best_order.assign(t.vals.begin() + j.a, t.vals.begin() + j.b + 1); }
+            }
+        }
+        std::copy(best_order.begin(), best_order.end(), t.vals.begin() + j.a);
+        const int m = j.a + best_split;   // left = [a, m], right = [m + 1, b]
+        t.first[(size_t)j.id] = j.a; t.last[(size_t)j.id] = j.b;
+        const int lc = m == j.a ? n - 1 + j.a : next_internal++;
+        const int rc = m + 1 == j.b ? n - 1 + j.b : next_internal++;
+        t.left[(size_t)j.id] = lc; t.right[(size_t)j.id] = rc;
+        if (lc < n - 1) todo.push_back({j.a, m, lc});
+        if (rc < n - 1) todo.push_back({m + 1, j.b, rc});
+    }
+    // bounds: leaves from their primitive, internal nodes from their range (ids of children are larger than the parent's)
+    for (int p = 0; p < n; p++) { t.nlo[(size_t)(n - 1 + p)] = plo[t.vals[(size_t)p]]; t.nhi[(size_t)(n - 1 + p)] = phi[t.vals[(size_t)p]]; }
+    for (int id = n - 2; id >= 0; id--) {
+        const float4 a0 = t.nlo[(size_t)t.left[(size_t)id]], a1 = t.nhi[(size_t)t.left[(size_t)id]], c0 = t.nlo[(size_t)t.right[(size_t)id]], c1 = t.nhi[(size_t)t.right[(size_t)id]];
+        t.nlo[(size_t)id] = make_float4(fminf(a0.x, c0.x), fminf(a0.y, c0.y), fminf(a0.z, c0.z), 0.0f);
+        t.nhi[(size_t)id] = make_float4(fmaxf(a1.x, c1.x), fmaxf(a1.y, c1.y), fmaxf(a1.z, c1.z), 0.0f);
+    }
+}
+
 // Builds a BVH8 over n primitive boxes (device arrays).  Synchronises the stream (one-off build).
+// sah_host: the binary tree under the collapse comes from build_bvh2_sah_host (for small n: instance lists) instead of the LBVH.
 inline void build_bvh8(const float4* d_plo, const float4* d_phi, uint32_t n, Stream st, DevBuf<Node8>& out_nodes,
-                       DevBuf<uint32_t>& out_order, Bvh8& out) {
+                       DevBuf<uint32_t>& out_order, Bvh8& out, bool sah_host = false) {
     RT3_REQUIRE(n > 0, -1, "build_bvh8: no primitives");
     // the traversal kernels tag queued triangles as (lane << 27 | index): 2^27 primitives per acceleration structure
     RT3_REQUIRE(n < (1u << 27), -1, "build_bvh8: more than 134,217,727 primitives in one acceleration structure");
@@ -460,11 +530,29 @@ inline void build_bvh8(const float4* d_plo, const float4* d_phi, uint32_t n, Str
     h2d(bounds.p, init_bounds, sizeof(init_bounds), st);
     dev_memset(flags.p, 0, sizeof(uint32_t) * n, st);
     dev_memset(parent.p, 0xff, sizeof(int) * nn, st);
-    RT3_LAUNCH_1D(k_bvh_bounds, n, st, b);
-    RT3_LAUNCH_1D(k_bvh_morton, n, st, b);
-    sort_pairs(keys.p, vals.p, n, st);
-    if (n > 1) RT3_LAUNCH_1D(k_bvh_hierarchy, n - 1, st, b);
-    RT3_LAUNCH_1D(k_bvh_refit, n, st, b);
+    if (sah_host && n > 2) {
+        // small inputs (the TLAS): a full-sweep SAH binary tree built on the host, in the arrays the collapse reads
+        std::vector<float4> hlo(n), hhi(n);
+        d2h(hlo.data(), d_plo, sizeof(float4) * n, st);
+        d2h(hhi.data(), d_phi, sizeof(float4) * n, st);
+        stream_sync(st);
+        HostBvh2 t;
+        build_bvh2_sah_host(hlo, hhi, t);
+        h2d(vals.p, t.vals.data(), sizeof(uint32_t) * n, st);
+        h2d(nlo.p, t.nlo.data(), sizeof(float4) * nn, st);
+        h2d(nhi.p, t.nhi.data(), sizeof(float4) * nn, st);
+        h2d(left.p, t.left.data(), sizeof(int) * (n - 1), st);
+        h2d(right.p, t.right.data(), sizeof(int) * (n - 1), st);
+        h2d(first.p, t.first.data(), sizeof(int) * (n - 1), st);
+        h2d(last.p, t.last.data(), sizeof(int) * (n - 1), st);
+        stream_sync(st);
+    } else {
+        RT3_LAUNCH_1D(k_bvh_bounds, n, st, b);
+        RT3_LAUNCH_1D(k_bvh_morton, n, st, b);
+        sort_pairs(keys.p, vals.p, n, st);
+        if (n > 1) RT3_LAUNCH_1D(k_bvh_hierarchy, n - 1, st, b);
+        RT3_LAUNCH_1D(k_bvh_refit, n, st, b);
+    }
 
     // collapse, level by level
     const uint32_t init_counters[4] = {1u, 0u, 0u, 0u};  // node 0 = root

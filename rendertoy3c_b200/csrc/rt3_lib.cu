@@ -85,6 +85,7 @@ struct rt3_context {
     bool has_merged = false, single_level = false;
     bool has_subdiv_curves = false;  // some instance refers to a degree-2 / -3 curve geometry (set in rt3_accel_build)
     int opt_merge = 1;
+    int opt_tlas_sah = 1;   // TLAS binary tree from the host full-sweep SAH builder (small inputs) instead of the LBVH
     int opt_tlas_refine = 1;  // instance boxes from the BLAS root's grandchild boxes instead of its root box
     DevBuf<uint32_t> d_flags;  // [0] error flags, [1] max stack
     // film
@@ -382,6 +383,7 @@ int rt3_set_option(rt3_context_t c, const char* key, int value) {
     else if (k == "overlap") c->opt_overlap = value;
     else if (k == "persist_ctas_per_sm") c->opt_ctas_per_sm = value;
     else if (k == "merge_identity") { c->opt_merge = value; c->built = false; }
+    else if (k == "tlas_sah") { c->opt_tlas_sah = value; c->built = false; }
     else if (k == "l2_persist") { c->opt_l2_persist = value; c->built = false; }
     else if (k == "tlas_refine") { c->opt_tlas_refine = value; c->built = false; }
     else if (k == "sort_rays" || k == "sort_materials") { RT3_REQUIRE(value == 0, RT3_ERR_UNSUPPORTED, "set_option: sorting stages are not built yet"); }
@@ -696,7 +698,7 @@ int rt3_accel_build(rt3_context_t c) {
             d2d(slo.p + k, lo.p + sel[k], sizeof(float4), c->stream);
             d2d(shi.p + k, hi.p + sel[k], sizeof(float4), c->stream);
         }
-        build_bvh8(slo.p, shi.p, ns, c->stream, c->tlas_nodes, c->tlas_order, c->tlas);
+        build_bvh8(slo.p, shi.p, ns, c->stream, c->tlas_nodes, c->tlas_order, c->tlas, /*sah_host=*/c->opt_tlas_sah && ns <= (1u << 16));
         std::vector<uint32_t> order(ns);
         d2h(order.data(), c->tlas_order.p, sizeof(uint32_t) * ns, c->stream);
         stream_sync(c->stream);

@@ -130,7 +130,12 @@ RT3_HD void instance_ray(const TravScene& sc, const InstanceDev* in, float t1, f
 // ------------------------------------------------------------------------------------ primitive tests
 struct Shear { int kx, ky, kz; float Sx, Sy, Sz; };
 
-RT3_HD Shear make_shear(float3 d) {
+// Shear constants of the watertight test.  The reciprocal of the dominant component is the ONLY division: Sx, Sy are
+// products with it (the test stays watertight — every triangle of a ray sees the same constants), and it is the same
+// clamped reciprocal the slab test uses for that axis, so a ray set-up costs three divisions instead of six.
+#define RT3_DIR_EPS 8.271806e-25f  // 2^-80: keeps 1/d finite for axis-parallel rays
+RT3_HD float clamp_dir(float d) { return fabsf(d) > RT3_DIR_EPS ? d : copysignf(RT3_DIR_EPS, d); }
+RT3_HD Shear make_shear(float3 d, float3 idir) {  // idir = 1 / clamp_dir(d) per component
     Shear s;
     const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
     s.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
@@ -138,9 +143,9 @@ RT3_HD Shear make_shear(float3 d) {
     s.ky = s.kx + 1; if (s.ky == 3) s.ky = 0;
     const float dz = comp(d, s.kz);
     if (dz < 0.0f) { const int t = s.kx; s.kx = s.ky; s.ky = t; }
-    s.Sx = comp(d, s.kx) / dz;
-    s.Sy = comp(d, s.ky) / dz;
-    s.Sz = 1.0f / dz;
+    s.Sz = comp(idir, s.kz);
+    s.Sx = comp(d, s.kx) * s.Sz;
+    s.Sy = comp(d, s.ky) * s.Sz;
     return s;
 }
 
@@ -393,12 +398,9 @@ struct Trav {
             fr_set(FR_D_XY, dd.x, dd.y);
             fr_set(FR_DZ_TIME, dd.z, time);
         }
-        const float eps = 8.271806e-25f;  // 2^-80: keeps 1/d finite for axis-parallel rays
-        const float dx = fabsf(dd.x) > eps ? dd.x : copysignf(eps, dd.x);
-        const float dy = fabsf(dd.y) > eps ? dd.y : copysignf(eps, dd.y);
-        const float dz = fabsf(dd.z) > eps ? dd.z : copysignf(eps, dd.z);
+        const float dx = clamp_dir(dd.x), dy = clamp_dir(dd.y), dz = clamp_dir(dd.z);
         idir = v3(1.0f / dx, 1.0f / dy, 1.0f / dz);
-        const Shear s = make_shear(dd);
+        const Shear s = make_shear(dd, idir);
         Sx = s.Sx; Sy = s.Sy; Sz = s.Sz;
         inv = (dx >= 0.0f ? 1u : 0u) | (dy >= 0.0f ? 2u : 0u) | (dz >= 0.0f ? 4u : 0u) | ((uint32_t)s.kx << 8) | ((uint32_t)s.ky << 10) |
               ((uint32_t)s.kz << 12);

@@ -15,8 +15,11 @@ for r in rows[1:]:
 ids = sorted(byid)
 gen = [i for i in ids if "k_generate" in byid[i]["k"]]
 res = [i for i in ids if "k_resolve" in byid[i]["k"]]
-last_res = res[-1]
-last_gen = max(i for i in gen if i < last_res)
+# the last FULL-SIZE subframe: bench.py ends with smaller diagnostic subframes (the counted one of the -DRT3_STATS twin, the
+# CPU same-seed check); k_generate writes a fixed number of bytes per path, so its duration tells the size
+full = max(byid[i]["gpu__time_duration.sum"] for i in gen)
+last_gen = max(i for i in gen if byid[i]["gpu__time_duration.sum"] >= 0.8 * full and any(r > i for r in res))
+last_res = min(r for r in res if r > last_gen)
 sub = [byid[i] for i in ids if last_gen <= i <= last_res]
 tot = sum(d["gpu__time_duration.sum"] for d in sub)
 agg = {}

@@ -84,6 +84,13 @@ out["render_Mrays_s"] = rays / dt / 1e6
 out["render_Msamples_s"] = st["samples"] / dt / 1e6
 out["render_ms_per_subframe"] = dt / nsf * 1e3
 out["rays_per_sample"] = rays / st["samples"]
+if os.environ.get("RT3_LIB", "").endswith("_stats.so"):   # the -DRT3_STATS twin: device counters of one 960x540 subframe
+    g.debug_counters()
+    uvw2 = g.camera_uvw(d.camera.eye, d.camera.lookat, d.camera.up, d.camera.fovy, 960 / 540)
+    g.launch_subframe(make_settings(d, uvw2, 0, width=960, height=540))
+    g.sync()
+    c = g.debug_counters()
+    out["counters_per_ray"] = {"wide_nodes": c[2] / max(1, c[5]), "primitive_tests": c[3] / max(1, c[5]), "rounds": c[4] / max(1, c[5]), "rays": c[5]}
 print(json.dumps(out, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/perf_probe_%s.json" % scene, "w"), indent=1)
