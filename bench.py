@@ -301,12 +301,13 @@ def run_config(name, desc, local, torch, steps=3, warmup=2, spl=SPL, max_depth=N
            "stage_ms": {k: s[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_connect", "ms_resolve", "ms_total")},
            "upload_and_build_s": build_s}
     g.close()
+    out["traversal_counters"] = traversal_counters(desc, local)
     return out
 
 
 def traversal_counters(desc, local):
     """wide nodes visited and primitive tests per ray, counted on the device by the -DRT3_STATS build of the same sources
-    (one 960x540 x 8-spl subframe: the counters are 32 bit)"""
+    (one subframe of at most 960x540 x 8 spl: the counters are 32 bit)"""
     from rendertoy3c_b200 import scenes
     from rendertoy3c_b200.api import Context, make_settings
     lib = os.path.join(ROOT, "rendertoy3c_b200", "librt3_stats.so")
@@ -314,7 +315,7 @@ def traversal_counters(desc, local):
         return {"unavailable": "rendertoy3c_b200/librt3_stats.so not built"}
     g = Context(local, lib_path=lib)
     scenes.replay(desc, g)
-    w, h = 960, 540
+    w, h = (960, 540) if desc.width * desc.height > 960 * 540 else (desc.width, desc.height)
     uvw = g.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, w / h)
     g.debug_counters()
     g.reset_stats()
