@@ -92,10 +92,13 @@ int rt3_mesh_create(rt3_context_t ctx, const float* verts, int num_keys, int nv,
 int rt3_mesh_set_colors(rt3_context_t ctx, rt3_handle_t blas, const float* rgba);
 /* analytic spheres, center_radius [n][4] (cuda/GeometryData.h:83-87, test per cuda/sphere.cu:37-97) */
 int rt3_spheres_create(rt3_context_t ctx, const float* center_radius, int n, rt3_handle_t* blas);
-/* round curves.  cp_radius [ncp][4]; segment i uses control points seg_first_cp[i] .. seg_first_cp[i] + degree.
- * degree 1: linear segments (cuda/curve.h:38-80, cuda/GeometryData.h:127-133).  degree 2 / 3: uniform quadratic / cubic
- * B-spline segments, evaluated with the SDK's Quadratic / CubicInterpolator (cuda/curve.h:98-230) and realised as 8
- * round linear sub-segments each; hits report the segment and u in [0,1] along it. */
+/* round curves.  cp_radius [ncp][4]; `degree` selects the curve type (the round OptixPrimitiveTypes the SDK's cuda/curve.h
+ * evaluates): segment i uses control points seg_first_cp[i] .. + 1 (linear), + 2 (quadratic B-spline), + 3 (the cubic types).
+ * Linear segments are intersected directly (cuda/curve.h:38-80, cuda/GeometryData.h:127-133).  The other types are converted
+ * with the SDK's Quadratic / CubicInterpolator::initializeFrom{BSpline, Catrom, Bezier} (cuda/curve.h:98-243); rays are
+ * intersected with 8 round linear sub-segments per segment, and the shading normal is the SDK's surfaceNormal<> of the TRUE
+ * curve at the hit's parameter (cuda/curve.h:311-379; flat end caps at u = 0 / 1).  Hits report the segment and u in [0,1]. */
+enum { RT3_CURVE_LINEAR = 1, RT3_CURVE_QUADRATIC_BSPLINE = 2, RT3_CURVE_CUBIC_BSPLINE = 3, RT3_CURVE_CATMULLROM = 4, RT3_CURVE_BEZIER = 5 };
 int rt3_curves_create(rt3_context_t ctx, int degree, const float* cp_radius, int ncp, const int32_t* seg_first_cp,
                       int nseg, rt3_handle_t* blas);
 /* CUDATexture<uchar4>(w,h,data,address,filter) src/cuda/cuda_texture.h:46-75 */

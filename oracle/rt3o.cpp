@@ -16,6 +16,7 @@
 #include "rt3o.h"
 #include "rt3o_math.hpp"
 #include "rt3o_prims.hpp"
+#include "rt3o_curve.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -175,7 +176,8 @@ struct Blas {
     int type = PRIM_TRI;
     std::vector<f3> verts, normals;    // verts: [vkeys][nv] (vertex-key motion, cuda_mesh.h:85-88: keys spread over time [0,1])
     int vkeys = 1, nv = 0;
-    int subdiv = 1;                    // curves of degree 2 / 3: linear sub-segments per user segment (hits translated at the API boundary)
+    int subdiv = 1;                    // spline curves: linear sub-segments per user segment (hits translated at the API boundary)
+    std::vector<CurvePoly> poly;       // spline curves: the true curve of every USER segment (normals are taken from it, cuda/curve.h:311-379)
     std::vector<f2> uvs;               // normals / uvs may be empty: the SDK's fallbacks (cuda/LocalGeometry.h:120-124,150-158)
     std::vector<float> colors;         // optional vertex colours, 4 per vertex (LocalGeometry.h:99-110)
     std::vector<int32_t> idx;          // tris: 3 per prim
@@ -442,6 +444,11 @@ struct rt3o_scene {
                 f3 c = {b.cr[4 * h.prim], b.cr[4 * h.prim + 1], b.cr[4 * h.prim + 2]};
                 n_obj = (ps - c) / b.cr[4 * h.prim + 3];
                 uv = {0, 0};
+            } else if (b.subdiv > 1) {  // spline curve: the SDK's bona fide normal of the TRUE curve (cuda/curve.h:311-379) at the hit's curve parameter
+                const int K = b.subdiv, k = h.prim % K;
+                const float uu = ((float)k + h.u) / (float)K;
+                n_obj = curve_surface_normal_raw(b.poly[(size_t)(h.prim / K)], uu, ps);
+                uv = {uu, 0};
             } else {  // cuda/curve.h:382-425 surfaceNormal<LinearInterpolator>
                 int a = b.seg[h.prim];
                 f3 p0 = {b.cr[4 * a], b.cr[4 * a + 1], b.cr[4 * a + 2]};
@@ -842,29 +849,17 @@ int rt3o_spheres_create(rt3o_scene* s, const float* cr, int n) {
 #ifndef RT3_CURVE_SUBDIV
 #define RT3_CURVE_SUBDIV 8
 #endif
-// position4(u) of the SDK's Quadratic / CubicInterpolator initialised from uniform B-spline control points q[0..degree]
-// (cuda/curve.h:102-111,124-127,176-186,264-267), one component.  float4 / float in sutil/vec_math.h:735-739 is a
-// multiplication by the rounded reciprocal, and the sums associate left to right.
-static inline float bspline_component(int degree, float q0, float q1, float q2, float q3, float u) {
-    if (degree == 2) {
-        const float inv = 1.0f / 2.0f;
-        const float p0 = ((q0 - 2.0f * q1) + q2) * inv, p1 = (-2.0f * q0 + 2.0f * q1) * inv, p2 = (q0 + q1) * inv;
-        return (p0 * u + p1) * u + p2;
-    }
-    const float inv = 1.0f / 6.0f;
-    const float p0 = (((q0 * -1.0f + q1 * 3.0f) + q2 * -3.0f) + q3) * inv, p1 = ((q0 * 3.0f + q1 * -6.0f) + q2 * 3.0f) * inv,
-                p2 = (q0 * -3.0f + q2 * 3.0f) * inv, p3 = ((q0 * 1.0f + q1 * 4.0f) + q2 * 1.0f) * inv;
-    return ((p0 * u + p1) * u + p2) * u + p3;
-}
-static void tessellate_bspline(int degree, const float* cp, const int32_t* seg, int nseg, std::vector<float>& out_cp, std::vector<int32_t>& out_seg) {
+static void tessellate_curves(int basis, const float* cp, const int32_t* seg, int nseg, std::vector<float>& out_cp, std::vector<int32_t>& out_seg, std::vector<CurvePoly>& poly) {
     const int K = RT3_CURVE_SUBDIV;
     out_cp.resize((size_t)4 * nseg * (K + 1));
     out_seg.resize((size_t)nseg * K);
+    poly.resize((size_t)nseg);
     for (int s = 0; s < nseg; s++) {
-        const float* q = cp + 4 * (size_t)seg[s];
+        poly[(size_t)s] = curve_poly(basis, cp + 4 * (size_t)seg[s]);
         for (int k = 0; k <= K; k++) {
+            const f4 v = curve_position(poly[(size_t)s], (float)k / (float)K);
             float* o = &out_cp[4 * ((size_t)s * (K + 1) + (size_t)k)];
-            for (int c = 0; c < 4; c++) o[c] = bspline_component(degree, q[c], q[4 + c], q[8 + c], degree == 3 ? q[12 + c] : 0.0f, (float)k / (float)K);
+            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
             if (k < K) out_seg[(size_t)s * K + (size_t)k] = s * (K + 1) + k;
         }
     }
@@ -886,15 +881,15 @@ static inline void curve_hit_to_user(int K, int32_t& prim, float& u) {
 int rt3o_curves_create(rt3o_scene* s, int degree, const float* cp, int ncp, const int32_t* seg, int nseg) {
     RT3O_TRY
     if (!s || !cp || !seg || ncp < 2 || nseg <= 0) { g_err = "curves_create: bad argument"; return -1; }
-    if (degree < 1 || degree > 3) { g_err = "curves_create: degree must be 1, 2 or 3"; return -5; }
+    if (degree < CURVE_LINEAR || degree > CURVE_BEZIER) { g_err = "curves_create: basis must be 1 (linear), 2 / 3 (quadratic / cubic B-spline), 4 (Catmull-Rom) or 5 (Bezier)"; return -5; }
     for (int i = 0; i < nseg; i++)
-        if (seg[i] < 0 || seg[i] + degree >= ncp) { g_err = "curves_create: segment out of range"; return -1; }
+        if (seg[i] < 0 || seg[i] + curve_control_points(degree) > ncp) { g_err = "curves_create: segment out of range"; return -1; }
     auto b = std::make_unique<Blas>();
     b->type = PRIM_CURVE;
     std::vector<float> tcp;
     std::vector<int32_t> tseg;
     if (degree > 1) {
-        tessellate_bspline(degree, cp, seg, nseg, tcp, tseg);
+        tessellate_curves(degree, cp, seg, nseg, tcp, tseg, b->poly);
         cp = tcp.data(); ncp = (int)(tcp.size() / 4); seg = tseg.data(); nseg = (int)tseg.size();
         b->subdiv = RT3_CURVE_SUBDIV;
     }
@@ -1126,8 +1121,12 @@ void rt3o_kat_camera_uvw(const float e[3], const float l[3], const float u[3], f
     camera_uvw({e[0], e[1], e[2]}, {l[0], l[1], l[2]}, {u[0], u[1], u[2]}, fovy, aspect, U, V, W);
     o[0] = U.x; o[1] = U.y; o[2] = U.z; o[3] = V.x; o[4] = V.y; o[5] = V.z; o[6] = W.x; o[7] = W.y; o[8] = W.z;
 }
-void rt3o_kat_bspline_position(int degree, const float* cp, float u, float out[4]) {
-    for (int c = 0; c < 4; c++) out[c] = bspline_component(degree, cp[c], cp[4 + c], cp[8 + c], degree == 3 ? cp[12 + c] : 0.0f, u);
+void rt3o_kat_curve_eval(int basis, const float* cp, float u, float out[16]) {
+    const CurvePoly p = curve_poly(basis, cp);
+    const f4 a = curve_position(p, u), v = curve_velocity(p, u), c = curve_acceleration(p, u);
+    const f3 t = curve_tangent(p, u);
+    const float o[16] = {a.x, a.y, a.z, a.w, v.x, v.y, v.z, v.w, c.x, c.y, c.z, c.w, t.x, t.y, t.z, 0.0f};
+    for (int k = 0; k < 16; k++) out[k] = o[k];
 }
 void rt3o_kat_sincos_2pi(float u, float o[2]) { sincos_2pi(u, o[0], o[1]); }
 void rt3o_kat_invert_affine(const float m[12], float out[12]) {

@@ -56,7 +56,7 @@ void rt3o_kat_light_sample(const void* light68, const float P[3], uint32_t* seed
 void rt3o_kat_make_color(const float c[3], uint8_t out[4]);
 void rt3o_kat_camera_uvw(const float eye[3], const float lookat[3], const float up[3], float fovy, float aspect, float out_uvw[9]);
 void rt3o_kat_sincos_2pi(float u, float out_sc[2]);
-void rt3o_kat_bspline_position(int degree, const float* cp /*[degree+1][4]*/, float u, float out[4]);  /* cuda/curve.h position4 of a B-spline segment */
+void rt3o_kat_curve_eval(int basis, const float* cp, float u, float out[16]);  /* cuda/curve.h: position4, velocity4, acceleration4, curveTangent of one segment */
 void rt3o_kat_invert_affine(const float m[12], float out[12]);
 int rt3o_kat_fetch_texture(rt3o_scene*, int tex, float u, float v, float out_rgb[3]);
 int rt3o_kat_sample_texture(rt3o_scene*, int instance_id, float u, float v, float out_rgb[3]);  /* with the instance's texcoord transform */  /* the shade stage's tex2D restatement */

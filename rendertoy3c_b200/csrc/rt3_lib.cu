@@ -29,7 +29,8 @@ struct Geometry {
     uint32_t subdiv = 1;  // curves of degree 2 / 3: linear sub-segments per user segment (hit records are translated at the API boundary)
     DevBuf<float> verts, normals, uvs, colors;   // normals / uvs / colors stay empty when the caller has none (SDK fallbacks)
     DevBuf<int32_t> idx, seg;
-    DevBuf<float4> cr;
+    DevBuf<float4> cr, poly;   // poly: spline curves, 4 power-basis coefficients (float4: xyz + radius) per USER segment
+    uint32_t curve_cubic = 0;  // spline curves: 1 = cubic (its velocity nudges u = 0 / 1, curve.h:281-288)
     DevBuf<Node8> nodes;
     DevBuf<uint32_t> order;
     DevBuf<float4> prims;
@@ -451,41 +452,53 @@ int rt3_spheres_create(rt3_context_t c, const float* cr, int n, rt3_handle_t* bl
 #ifndef RT3_CURVE_SUBDIV
 #define RT3_CURVE_SUBDIV 8
 #endif
-// Polynomial coefficients (highest power first) of one component of a uniform B-spline segment, as the SDK's interpolators
-// form them: rows of the B-spline-to-power-basis matrix applied left to right, then scaled by the rounded reciprocal of the
-// common denominator (vec_math's float4 / float).
-static int bspline_coefficients(int degree, const float* q /* stride 4 */, float coef[4]) {
-    if (degree == 2) {
-        const float h = 1.0f / 2.0f;
-        coef[0] = ((q[0] - 2.0f * q[4]) + q[8]) * h;
-        coef[1] = (-2.0f * q[0] + 2.0f * q[4]) * h;
-        coef[2] = (q[0] + q[4]) * h;
-        return 3;
-    }
-    const float s = 1.0f / 6.0f;
-    coef[0] = (((q[0] * -1.0f + q[4] * 3.0f) + q[8] * -3.0f) + q[12]) * s;
-    coef[1] = ((q[0] * 3.0f + q[4] * -6.0f) + q[8] * 3.0f) * s;
-    coef[2] = (q[0] * -3.0f + q[8] * 3.0f) * s;
-    coef[3] = ((q[0] * 1.0f + q[4] * 4.0f) + q[8] * 1.0f) * s;
-    return 4;
+// Spline segments -> power-basis coefficients, table driven.  A row lists the terms (control point, factor) of one coefficient
+// in the order the SDK's interpolators add them (cuda/curve.h:43-47 linear, :102-110 quadratic B-spline, :176-186 cubic
+// B-spline, :209-219 Catmull-Rom, :233-243 Bezier); `div` is the common denominator, applied as a multiplication by its
+// rounded reciprocal like vec_math's float4 / float.  Coefficients are stored cubic-style, highest power first, with the
+// leading ones zero for lower degrees: the cubic Horner forms then evaluate to exactly the lower-degree ones.
+struct BasisRow { int n; int cp[4]; float f[4]; };
+struct BasisTable { int ncp; float div; BasisRow row[4]; };
+static const BasisTable& basis_table(int basis) {
+    static const BasisTable T[5] = {
+        /* linear      */ {2, 0.0f, {{0, {0}, {0}}, {0, {0}, {0}}, {2, {1, 0}, {1.0f, -1.0f}}, {1, {0}, {1.0f}}}},
+        /* quad bspl   */ {3, 2.0f, {{0, {0}, {0}}, {3, {0, 1, 2}, {1.0f, -2.0f, 1.0f}}, {2, {0, 1}, {-2.0f, 2.0f}}, {2, {0, 1}, {1.0f, 1.0f}}}},
+        /* cubic bspl  */ {4, 6.0f, {{4, {0, 1, 2, 3}, {-1.0f, 3.0f, -3.0f, 1.0f}}, {3, {0, 1, 2}, {3.0f, -6.0f, 3.0f}}, {2, {0, 2}, {-3.0f, 3.0f}}, {3, {0, 1, 2}, {1.0f, 4.0f, 1.0f}}}},
+        /* catmull-rom */ {4, 2.0f, {{4, {0, 1, 2, 3}, {-1.0f, 3.0f, -3.0f, 1.0f}}, {4, {0, 1, 2, 3}, {2.0f, -5.0f, 4.0f, -1.0f}}, {2, {0, 2}, {-1.0f, 1.0f}}, {1, {1}, {2.0f}}}},
+        /* bezier      */ {4, 0.0f, {{4, {0, 1, 2, 3}, {-1.0f, 3.0f, -3.0f, 1.0f}}, {3, {0, 1, 2}, {3.0f, -6.0f, 3.0f}}, {2, {0, 1}, {-3.0f, 3.0f}}, {1, {0}, {1.0f}}}},
+    };
+    return T[basis - 1];
 }
-static void tessellate_bspline(int degree, const float* cp, const int32_t* seg, int nseg, std::vector<float>& out_cp, std::vector<int32_t>& out_seg) {
+// coef[4][4]: coefficient j (u^(3-j)) x component (x, y, z, radius) of the segment whose first control point is q
+static void curve_coefficients(int basis, const float* q, float coef[4][4]) {
+    const BasisTable& t = basis_table(basis);
+    const float inv = t.div != 0.0f ? 1.0f / t.div : 1.0f;
+    for (int j = 0; j < 4; j++)
+        for (int c = 0; c < 4; c++) {
+            const BasisRow& r = t.row[j];
+            float v = 0.0f;
+            for (int k = 0; k < r.n; k++) {
+                const float term = q[4 * r.cp[k] + c] * r.f[k];
+                v = k == 0 ? term : v + term;
+            }
+            coef[j][c] = (r.n && t.div != 0.0f) ? v * inv : v;
+        }
+}
+static void tessellate_curves(int basis, const float* cp, const int32_t* seg, int nseg, std::vector<float>& out_cp, std::vector<int32_t>& out_seg, std::vector<float>& out_coef) {
     const int K = RT3_CURVE_SUBDIV;
     out_cp.resize((size_t)4 * nseg * (K + 1));
     out_seg.resize((size_t)nseg * K);
-    for (int s = 0; s < nseg; s++)
-        for (int c = 0; c < 4; c++) {   // component by component: x, y, z, radius
-            float coef[4];
-            const int n = bspline_coefficients(degree, cp + 4 * (size_t)seg[s] + c, coef);
-            for (int k = 0; k <= K; k++) {
-                const float u = (float)k / (float)K;
-                float v = coef[0];
-                for (int j = 1; j < n; j++) v = v * u + coef[j];   // Horner
-                out_cp[4 * ((size_t)s * (K + 1) + (size_t)k) + (size_t)c] = v;
-            }
+    out_coef.resize((size_t)16 * nseg);
+    for (int s = 0; s < nseg; s++) {
+        float coef[4][4];
+        curve_coefficients(basis, cp + 4 * (size_t)seg[s], coef);
+        memcpy(&out_coef[16 * (size_t)s], coef, sizeof(coef));
+        for (int k = 0; k <= K; k++) {
+            const float u = (float)k / (float)K;
+            for (int c = 0; c < 4; c++) out_cp[4 * ((size_t)s * (K + 1) + (size_t)k) + (size_t)c] = ((coef[0][c] * u + coef[1][c]) * u + coef[2][c]) * u + coef[3][c];   // Horner
+            if (k < K) out_seg[(size_t)s * K + (size_t)k] = s * (K + 1) + k;
         }
-    for (int s = 0; s < nseg; s++)
-        for (int k = 0; k < K; k++) out_seg[(size_t)s * K + (size_t)k] = s * (K + 1) + k;
+    }
 }
 static inline void curve_hit_to_internal(int K, int32_t& prim, float& u) {
     const float f = u * (float)K;
@@ -499,17 +512,21 @@ int rt3_curves_create(rt3_context_t c, int degree, const float* cp, int ncp, con
     RT3_API_BEGIN
     use_device(c);
     RT3_REQUIRE(c && cp && seg && blas && ncp >= 2 && nseg > 0, RT3_ERR_INVALID, "curves_create: bad argument");
-    RT3_REQUIRE(degree >= 1 && degree <= 3, RT3_ERR_UNSUPPORTED, "curves_create: degree must be 1 (linear), 2 or 3 (uniform B-spline)");
-    for (int i = 0; i < nseg; i++) RT3_REQUIRE(seg[i] >= 0 && seg[i] + degree < ncp, RT3_ERR_INVALID, "curves_create: segment out of range");
+    RT3_REQUIRE(degree >= RT3_CURVE_LINEAR && degree <= RT3_CURVE_BEZIER, RT3_ERR_UNSUPPORTED,
+                "curves_create: curve type must be 1 (linear), 2 / 3 (quadratic / cubic uniform B-spline), 4 (Catmull-Rom) or 5 (cubic Bezier)");
+    for (int i = 0; i < nseg; i++) RT3_REQUIRE(seg[i] >= 0 && seg[i] + basis_table(degree).ncp <= ncp, RT3_ERR_INVALID, "curves_create: segment out of range");
     auto g = std::make_unique<Geometry>();
     g->type = PRIM_CURVE;
-    std::vector<float> tcp;
+    std::vector<float> tcp, coef;
     std::vector<int32_t> tseg;
-    if (degree > 1) {
+    if (degree > RT3_CURVE_LINEAR) {
         RT3_REQUIRE((uint64_t)nseg * RT3_CURVE_SUBDIV < (1u << 27), RT3_ERR_INVALID, "curves_create: too many segments");
-        tessellate_bspline(degree, cp, seg, nseg, tcp, tseg);
+        tessellate_curves(degree, cp, seg, nseg, tcp, tseg, coef);
         cp = tcp.data(); ncp = (int)(tcp.size() / 4); seg = tseg.data(); nseg = (int)tseg.size();
         g->subdiv = RT3_CURVE_SUBDIV;
+        g->curve_cubic = degree >= RT3_CURVE_CUBIC_BSPLINE ? 1u : 0u;
+        g->poly.alloc(coef.size() / 4);   // the true curve of every user segment: normals are taken from it (cuda/curve.h:311-379)
+        h2d(g->poly.p, coef.data(), g->poly.bytes(), c->stream);
     }
     g->nprims = (uint32_t)nseg;
     g->cr.alloc(ncp);
@@ -650,7 +667,7 @@ int rt3_accel_build(rt3_context_t c) {
     std::vector<BlasBounds> bb(ng + 1);
     for (size_t i = 0; i < ng; i++) {
         const Geometry& g = *c->geoms[i];
-        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p, g.vkeys, g.verts.p, g.nv, g.subdiv, g.colors.p};
+        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p, g.vkeys, g.verts.p, g.nv, g.subdiv, g.colors.p, g.poly.p, g.curve_cubic};
         for (int k = 0; k < 3; k++) { bb[i].lo[k] = g.bvh.lo[k]; bb[i].hi[k] = g.bvh.hi[k]; }
     }
     bt[ng] = BlasDev{c->m_nodes_p, c->m_prims_p, PRIM_TRI, c->m_bvh.num_prims, nullptr, nullptr, nullptr, nullptr, nullptr, 1u, nullptr};

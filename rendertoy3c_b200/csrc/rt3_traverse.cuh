@@ -63,6 +63,8 @@ struct BlasDev {             // per geometry, device-resident table entry
     uint32_t nv;             // vertices per key
     uint32_t subdiv;         // curves of degree 2 / 3: linear sub-segments per user segment (1 otherwise)
     const float* colors;     // mesh, optional [nv][4] vertex colours (cuda/LocalGeometry.h:99-110); normals / uvs may be null too (SDK fallbacks)
+    const float4* poly;      // spline curves: power-basis coefficients c0 u^3 + c1 u^2 + c2 u + c3 of every USER segment (xyz + radius)
+    uint32_t curve_cubic;    // spline curves: 1 = cubic interpolator
 };
 
 struct InstanceDev {         // traversal record (64 B)

@@ -480,6 +480,31 @@ RT3_HD float3 sample_texture(const TexDev& tx, const HitGroupDev& hg, float2 uv)
     return fetch_texture(tx, tu, tv);
 }
 
+// Surface normal (not normalised) of a quadratic / cubic round curve segment given by its power-basis coefficients
+// c[0] u^3 + c[1] u^2 + c[2] u + c[3] (xyz + radius; c[0] = 0 for quadratics), at parameter u, for a point ps near the offset
+// surface — cuda/curve.h:311-379 with type = 2 (the bona fide normal): flat end caps at u = 0 / 1 (-+ velocity; the cubic
+// interpolator evaluates its velocity a hair inside, :281-288), else ps is projected onto the plane through the curve point
+// orthogonal to the tangent, dropped onto the surface, and the normal corrected for the radius derivative and the curvature.
+RT3_HD float3 spline_surface_normal(const float4* c, bool cubic, float u, float3 ps) {
+    const float4 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
+    if (u == 0.0f || u == 1.0f) {
+        const float ue = cubic ? (u == 0.0f ? 0.000001f : 0.999999f) : u;
+        const float3 vel = v3((3.0f * c0.x * ue + 2.0f * c1.x) * ue + c2.x, (3.0f * c0.y * ue + 2.0f * c1.y) * ue + c2.y, (3.0f * c0.z * ue + 2.0f * c1.z) * ue + c2.z);
+        return u == 0.0f ? neg(vel) : vel;
+    }
+    const float3 p = v3(((c0.x * u + c1.x) * u + c2.x) * u + c3.x, ((c0.y * u + c1.y) * u + c2.y) * u + c3.y, ((c0.z * u + c1.z) * u + c2.z) * u + c3.z);
+    const float r = ((c0.w * u + c1.w) * u + c2.w) * u + c3.w;
+    const float3 d = v3((3.0f * c0.x * u + 2.0f * c1.x) * u + c2.x, (3.0f * c0.y * u + 2.0f * c1.y) * u + c2.y, (3.0f * c0.z * u + 2.0f * c1.z) * u + c2.z);
+    const float dr = (3.0f * c0.w * u + 2.0f * c1.w) * u + c2.w;
+    const float3 acc = v3(6.0f * c0.x * u + 2.0f * c1.x, 6.0f * c0.y * u + 2.0f * c1.y, 6.0f * c0.z * u + 2.0f * c1.z);
+    float dd = dot(d, d);
+    float3 o1 = sub(ps, p);
+    o1 = sub(o1, mul(d, dot(o1, d) / dd));
+    o1 = mul(o1, r / length(o1));
+    dd -= dot(acc, o1);
+    return sub(mul(o1, dd), mul(d, dr * r));
+}
+
 // the three object-space vertices of a triangle at a ray time (vertex keys spread evenly over [0, 1], cuda_mesh.h:82-88), as in the traversal
 RT3_HD void triangle_vertices(const BlasDev* b, int i0, int i1, int i2, float time, float3& P0, float3& P1, float3& P2) {
     if (b->vkeys <= 1u) {
@@ -527,6 +552,11 @@ RT3_HD LocalGeometry local_geometry(const TravScene& sc, const HitRec& h, float3
             const float4 s = b->cr[h.prim];
             n_obj = divs(sub(ps, v3(s)), s.w);
             lg.UV = make_float2(0.0f, 0.0f);
+        } else if (b->subdiv > 1u) {  // spline curves: the SDK's surfaceNormal<> of the TRUE curve at the hit's parameter (cuda/curve.h:311-379)
+            const uint32_t K = b->subdiv, k = (uint32_t)h.prim % K;
+            const float uu = ((float)k + h.u) / (float)K;   // the hit was found on linear sub-segment k of its segment
+            n_obj = spline_surface_normal(b->poly + 4 * (size_t)((uint32_t)h.prim / K), b->curve_cubic != 0u, uu, ps);
+            lg.UV = make_float2(uu, 0.0f);
         } else {  // cuda/curve.h:382-425 surfaceNormal<LinearInterpolator>
             const float4 c0 = b->cr[b->seg[h.prim]], c1 = b->cr[b->seg[h.prim] + 1];
             if (h.u == 0.0f) n_obj = sub(ps, v3(c0));

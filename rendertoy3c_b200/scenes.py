@@ -24,7 +24,7 @@ class Geometry:
     uvs: np.ndarray = None        # mesh [nv,2]
     cr: np.ndarray = None         # spheres [n,4] / curves control points [ncp,4]
     seg: np.ndarray = None        # curves [nseg] i32 first control point
-    degree: int = 1               # curves: 1 linear, 2 / 3 uniform B-spline (segment i uses control points seg[i] .. seg[i] + degree)
+    degree: int = 1               # curves: 1 linear, 2 / 3 quadratic / cubic uniform B-spline, 4 Catmull-Rom, 5 cubic Bezier (rt3.h RT3_CURVE_*)
     vert_keys: np.ndarray = None  # mesh, optional [keys,nv,3]: vertex-key (deformation) motion; verts = key 0
     colors: np.ndarray = None     # mesh, optional [nv,4] vertex colours (cuda/LocalGeometry.h:99-110); normals / uvs may be None too (SDK fallbacks)
 
@@ -371,21 +371,23 @@ def deforming(blob_n=24, width=160, height=90, spp=16, max_depth=6, keys=3):
 
 
 def splines(n_strands=40, width=80, height=48, spp=16, max_depth=4, seed=11):
-    """degree-2 and degree-3 B-spline curve strands (random walks of control points, varying radius) over a lit floor"""
+    """spline curve strands of every type rt3_curves_create offers besides linear — quadratic and cubic B-spline, Catmull-Rom,
+    cubic Bezier (random walks of control points, varying radius) — over a lit floor"""
     rng = np.random.RandomState(seed)
     geoms, inst = [], []
-    for degree in (2, 3):
+    for degree in (2, 3, 4, 5):
         cps, segs = [], []
-        for _ in range(n_strands):
-            n = rng.randint(degree + 2, degree + 7)
+        ncp = 3 if degree == 2 else 4           # control points per segment
+        for _ in range(n_strands if degree < 4 else n_strands // 2):
+            n = rng.randint(ncp + 1, ncp + 6)
             p = np.cumsum(rng.randn(n, 3).astype(np.float32) * np.float32(0.35), axis=0) + (rng.rand(3).astype(np.float32) * 3 - 1.5) * np.array([1, 0.3, 1], np.float32)
             p[:, 1] = np.abs(p[:, 1]) + 0.2
             r = (0.03 + 0.05 * rng.rand(n)).astype(np.float32)
             base = sum(len(c) for c in cps)
             cps.append(np.concatenate([p, r[:, None]], axis=1))
-            segs.extend(range(base, base + n - degree))
+            segs.extend(range(base, base + n - ncp + 1))
         geoms.append(Geometry("curves", cr=np.concatenate(cps).astype(np.float32), seg=np.array(segs, np.int32), degree=degree))
-        inst.append(Instance(len(geoms) - 1, diffuse=(0.7, 0.5, 0.3) if degree == 2 else (0.3, 0.6, 0.7)))
+        inst.append(Instance(len(geoms) - 1, diffuse=[(0.7, 0.5, 0.3), (0.3, 0.6, 0.7), (0.5, 0.7, 0.3), (0.7, 0.3, 0.6)][degree - 2]))
     geoms.append(_quad_mesh([[[-3, 3.0, -3], [3, 3.0, -3], [3, 3.0, 3], [-3, 3.0, 3]]]))
     inst.append(Instance(len(geoms) - 1, diffuse=(0.8, 0.8, 0.8), emission=(7.0, 7.0, 6.5)))
     geoms.append(_quad_mesh([[[-5, 0, -5], [-5, 0, 5], [5, 0, 5], [5, 0, -5]]]))
