@@ -236,11 +236,122 @@ RT3_GLOBAL(k_bvh_refit, BuildArrays b) {
 }
 
 RT3_HD int bvh2_count(const BuildArrays& b, int id) { return id >= (int)b.n - 1 ? 1 : (b.last[id] - b.first[id] + 1); }
-RT3_HD int bvh2_first(const BuildArrays& b, int id) { return id >= (int)b.n - 1 ? id - ((int)b.n - 1) : b.first[id]; }
+// the (at most RT3_LEAF_MAX) sorted positions under a small subtree, left to right.  A walk instead of [first, last]: the
+// leaves of a PLOC subtree are not a contiguous range of the Morton order
+RT3_HD int bvh2_leaves(const BuildArrays& b, int id, int out[4]) {
+    const int n = (int)b.n;
+    int stack[8], sp = 0, cnt = 0;
+    stack[sp++] = id;
+    while (sp > 0 && cnt < 4) {
+        const int cur = stack[--sp];
+        if (cur >= n - 1) { out[cnt++] = cur - (n - 1); continue; }
+        if (sp < 7) { stack[sp++] = b.right[cur]; stack[sp++] = b.left[cur]; }
+    }
+    return cnt;
+}
 RT3_HD float bvh2_area(const BuildArrays& b, int id) {
     const float4 lo = b.nlo[id], hi = b.nhi[id];
     const float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
     return ex * ey + ey * ez + ez * ex;
+}
+
+// ------------------------------------------------------------------------------------ PLOC (SAH-quality binary tree)
+// Parallel locally-ordered clustering (Meister & Bittner 2018): the clusters — at first the primitives in Morton order —
+// each look RT3_PLOC_RADIUS neighbours to either side for the partner that gives the smallest merged surface area; mutual
+// nearest neighbours merge into a new node; the array is compacted and the round repeats until one cluster is left.
+// Agglomerative by surface area, so the tree approaches a full SAH build where the Morton-order tree (k_bvh_hierarchy)
+// splits at key-bit boundaries whatever they cut through.  Everything order dependent goes through prefix sums (no
+// atomics): the tree is the same run to run and in the kernel-logic simulator.  Internal node ids descend from n-2 so that
+// the last merge is node 0, the root, as the collapse expects; leaf of sorted position j is id n-1+j as before.
+#ifndef RT3_PLOC_RADIUS
+#define RT3_PLOC_RADIUS 16
+#endif
+struct PlocArrays {
+    const int* in;      // clusters of this round (node ids)
+    int* out;           // clusters of the next round
+    int* nn;            // nearest neighbour (index into `in`)
+    uint32_t* merge;    // 1: cluster i merges with nn[i] and i < nn[i]   -> after the scan: exclusive prefix
+    uint32_t* keep;     // 1: cluster i survives (as itself or as the merged node) -> after the scan: exclusive prefix
+    uint32_t* sums;     // [2][chunks] chunk totals, then their exclusive prefix
+    uint32_t count;     // clusters in `in`
+    int next_id;        // the first merge of this round gets next_id - 1
+};
+RT3_HD float ploc_union_area(const float4 a0, const float4 a1, const float4 c0, const float4 c1) {
+    const float ex = fmaxf(a1.x, c1.x) - fminf(a0.x, c0.x), ey = fmaxf(a1.y, c1.y) - fminf(a0.y, c0.y), ez = fmaxf(a1.z, c1.z) - fminf(a0.z, c0.z);
+    return ex * ey + ey * ez + ez * ex;
+}
+RT3_GLOBAL(k_ploc_leaves, BuildArrays b, int* clusters) {   // leaf boxes + the first cluster list
+    const uint32_t j = RT3_THREAD_ID();
+    if (j >= rt3_n_) return;
+    const int id = (int)b.n - 1 + (int)j;
+    const uint32_t prim = b.vals[j];
+    b.nlo[id] = b.plo[prim];
+    b.nhi[id] = b.phi[prim];
+    clusters[j] = id;
+}
+RT3_GLOBAL(k_ploc_nearest, BuildArrays b, PlocArrays p) {
+    const int i = (int)RT3_THREAD_ID();
+    if (i >= (int)p.count) return;
+    const float4 lo = b.nlo[p.in[i]], hi = b.nhi[p.in[i]];
+    const int from = i - RT3_PLOC_RADIUS < 0 ? 0 : i - RT3_PLOC_RADIUS, to = i + RT3_PLOC_RADIUS > (int)p.count - 1 ? (int)p.count - 1 : i + RT3_PLOC_RADIUS;
+    float best = 3.4e38f;
+    int bj = -1;
+    for (int j = from; j <= to; j++) {
+        if (j == i) continue;
+        const float a = ploc_union_area(lo, hi, b.nlo[p.in[j]], b.nhi[p.in[j]]);
+        if (a < best) { best = a; bj = j; }   // ties: the lower index
+    }
+    p.nn[i] = bj;
+}
+RT3_GLOBAL(k_ploc_flags, PlocArrays p) {
+    const int i = (int)RT3_THREAD_ID();
+    if (i >= (int)p.count) return;
+    const int j = p.nn[i];
+    const bool mutual = j >= 0 && p.nn[j] == i;
+    p.merge[i] = (mutual && i < j) ? 1u : 0u;
+    p.keep[i] = (mutual && i > j) ? 0u : 1u;
+}
+// exclusive prefix sums of merge[] and keep[] in three launches of independent threads (chunks of 256)
+RT3_GLOBAL(k_ploc_scan_chunks, PlocArrays p, uint32_t chunks) {
+    const uint32_t c = RT3_THREAD_ID();
+    if (c >= rt3_n_) return;
+    uint32_t m = 0, k = 0;
+    const uint32_t end = (c + 1) * 256u < p.count ? (c + 1) * 256u : p.count;
+    for (uint32_t i = c * 256u; i < end; i++) { m += p.merge[i]; k += p.keep[i]; }
+    p.sums[c] = m;
+    p.sums[chunks + c] = k;
+}
+RT3_GLOBAL(k_ploc_scan_sums, PlocArrays p, uint32_t chunks) {   // one thread; <= n / 256 entries
+    if (RT3_THREAD_ID() != 0) return;
+    uint32_t m = 0, k = 0;
+    for (uint32_t c = 0; c < chunks; c++) {
+        const uint32_t a = p.sums[c], d = p.sums[chunks + c];
+        p.sums[c] = m; p.sums[chunks + c] = k;
+        m += a; k += d;
+    }
+    p.sums[2 * chunks] = m;       // merges of this round
+    p.sums[2 * chunks + 1] = k;   // clusters of the next round
+}
+RT3_GLOBAL(k_ploc_merge, BuildArrays b, PlocArrays p, uint32_t chunks) {   // one thread per chunk: finishes the scan and applies it
+    const uint32_t c = RT3_THREAD_ID();
+    if (c >= rt3_n_) return;
+    uint32_t m = p.sums[c], k = p.sums[chunks + c];
+    const uint32_t end = (c + 1) * 256u < p.count ? (c + 1) * 256u : p.count;
+    for (uint32_t i = c * 256u; i < end; i++) {
+        const uint32_t is_merge = p.merge[i], is_keep = p.keep[i];
+        if (is_merge) {
+            const int id = p.next_id - 1 - (int)m, l = p.in[i], r = p.in[p.nn[i]];
+            const float4 a0 = b.nlo[l], a1 = b.nhi[l], c0 = b.nlo[r], c1 = b.nhi[r];
+            b.nlo[id] = make_float4(fminf(a0.x, c0.x), fminf(a0.y, c0.y), fminf(a0.z, c0.z), 0.0f);
+            b.nhi[id] = make_float4(fmaxf(a1.x, c1.x), fmaxf(a1.y, c1.y), fmaxf(a1.z, c1.z), 0.0f);
+            b.left[id] = l; b.right[id] = r;
+            b.parent[l] = id; b.parent[r] = id;
+            const int nl = l >= (int)b.n - 1 ? 1 : b.last[l] + 1, nr = r >= (int)b.n - 1 ? 1 : b.last[r] + 1;
+            b.first[id] = 0; b.last[id] = nl + nr - 1;   // only the COUNT of a PLOC subtree is meaningful (bvh2_count)
+            p.out[k] = id;
+        } else if (is_keep) p.out[k] = p.in[i];
+        m += is_merge; k += is_keep;
+    }
 }
 
 // smallest biased exponent E with p + RT3_QMAX * 2^(E-127) >= hi (checked in double)
@@ -362,8 +473,9 @@ RT3_GLOBAL(k_bvh_collapse, BuildArrays b) {
         } else {
             const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
             nd.meta[s] = (uint8_t)((unary << 5) | offset);
-            const int f = bvh2_first(b, id);
-            for (int k = 0; k < cnt; k++) b.prim_order[prim_base + offset + (uint32_t)k] = b.vals[f + k];
+            int pos[4];
+            bvh2_leaves(b, id, pos);
+            for (int k = 0; k < cnt; k++) b.prim_order[prim_base + offset + (uint32_t)k] = b.vals[pos[k]];
             offset += (uint32_t)cnt;
         }
         const float4 clo4 = b.nlo[id], chi4 = b.nhi[id];
@@ -506,7 +618,7 @@ inline void build_bvh2_sah_host(const std::vector<float4>& plo, const std::vecto
 // Builds a BVH8 over n primitive boxes (device arrays).  Synchronises the stream (one-off build).
 // sah_host: the binary tree under the collapse comes from build_bvh2_sah_host (for small n: instance lists) instead of the LBVH.
 inline void build_bvh8(const float4* d_plo, const float4* d_phi, uint32_t n, Stream st, DevBuf<Node8>& out_nodes,
-                       DevBuf<uint32_t>& out_order, Bvh8& out, bool sah_host = false) {
+                       DevBuf<uint32_t>& out_order, Bvh8& out, bool sah_host = false, bool ploc = false) {
     RT3_REQUIRE(n > 0, -1, "build_bvh8: no primitives");
     // the traversal kernels tag queued triangles as (lane << 27 | index): 2^27 primitives per acceleration structure
     RT3_REQUIRE(n < (1u << 27), -1, "build_bvh8: more than 134,217,727 primitives in one acceleration structure");
@@ -550,8 +662,36 @@ inline void build_bvh8(const float4* d_plo, const float4* d_phi, uint32_t n, Str
         RT3_LAUNCH_1D(k_bvh_bounds, n, st, b);
         RT3_LAUNCH_1D(k_bvh_morton, n, st, b);
         sort_pairs(keys.p, vals.p, n, st);
-        if (n > 1) RT3_LAUNCH_1D(k_bvh_hierarchy, n - 1, st, b);
-        RT3_LAUNCH_1D(k_bvh_refit, n, st, b);
+        if (ploc && n > 2) {
+            const uint32_t max_chunks = (n + 255) / 256;
+            DevBuf<int> ca(n), cb(n), nn(n);
+            DevBuf<uint32_t> fm(n), fk(n), sums(2 * (size_t)max_chunks + 2);
+            RT3_LAUNCH_1D(k_ploc_leaves, n, st, b, ca.p);
+            PlocArrays p;
+            p.in = ca.p; p.out = cb.p; p.nn = nn.p; p.merge = fm.p; p.keep = fk.p; p.sums = sums.p;
+            p.count = n; p.next_id = (int)n - 1;
+            int rounds = 0;
+            while (p.count > 1) {
+                const uint32_t chunks = (p.count + 255) / 256;
+                RT3_LAUNCH_1D(k_ploc_nearest, p.count, st, b, p);
+                RT3_LAUNCH_1D(k_ploc_flags, p.count, st, p);
+                RT3_LAUNCH_1D(k_ploc_scan_chunks, chunks, st, p, chunks);
+                RT3_LAUNCH_1D(k_ploc_scan_sums, 1, st, p, chunks);
+                RT3_LAUNCH_1D(k_ploc_merge, chunks, st, b, p, chunks);
+                uint32_t tot[2];
+                d2h(tot, sums.p + 2 * (size_t)chunks, sizeof(tot), st);
+                stream_sync(st);
+                RT3_REQUIRE(tot[0] > 0 && tot[1] == p.count - tot[0], -2, "build_bvh8: PLOC round made no progress");
+                p.next_id -= (int)tot[0];
+                p.count = tot[1];
+                const int* t = p.in; p.in = p.out; p.out = const_cast<int*>(t);
+                RT3_REQUIRE(++rounds < 4096, -2, "build_bvh8: PLOC did not converge");
+            }
+            RT3_REQUIRE(p.next_id == 0, -2, "build_bvh8: PLOC node count mismatch");
+        } else {
+            if (n > 1) RT3_LAUNCH_1D(k_bvh_hierarchy, n - 1, st, b);
+            RT3_LAUNCH_1D(k_bvh_refit, n, st, b);
+        }
     }
 
     // collapse, level by level

@@ -86,7 +86,8 @@ struct rt3_context {
     bool has_merged = false, single_level = false;
     bool has_subdiv_curves = false;  // some instance refers to a degree-2 / -3 curve geometry (set in rt3_accel_build)
     int opt_merge = 1;
-    int opt_tlas_sah = 1;   // TLAS binary tree from the host full-sweep SAH builder (small inputs) instead of the LBVH
+    int opt_tlas_sah = 1;
+    int opt_ploc = 1;       // BLAS binary tree by parallel locally-ordered clustering (SAH quality) instead of the Morton-order tree   // TLAS binary tree from the host full-sweep SAH builder (small inputs) instead of the LBVH
     int opt_tlas_refine = 1;  // instance boxes from the BLAS root's grandchild boxes instead of its root box
     DevBuf<uint32_t> d_flags;  // [0] error flags, [1] max stack
     // film
@@ -189,7 +190,7 @@ void ensure_blas(rt3_context* c, Geometry* g) {
     else if (g->type == PRIM_TRI_MOTION) RT3_LAUNCH_1D(k_tri_boxes_motion, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, g->vkeys, g->nv, lo.p, hi.p);
     else if (g->type == PRIM_SPHERE) RT3_LAUNCH_1D(k_sphere_boxes, g->nprims, c->stream, (const float4*)g->cr.p, lo.p, hi.p);
     else RT3_LAUNCH_1D(k_curve_boxes, g->nprims, c->stream, (const float4*)g->cr.p, (const int32_t*)g->seg.p, lo.p, hi.p);
-    build_bvh8(lo.p, hi.p, g->nprims, c->stream, g->nodes, g->order, g->bvh);
+    build_bvh8(lo.p, hi.p, g->nprims, c->stream, g->nodes, g->order, g->bvh, /*sah_host=*/false, /*ploc=*/c->opt_ploc != 0);
     g->prims.alloc(3 * (size_t)g->nprims * g->vkeys);
     if (g->type == PRIM_TRI_MOTION) RT3_LAUNCH_1D(k_pack_tris_motion, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, g->vkeys, g->nv, (const uint32_t*)g->order.p, g->prims.p);
     else if (g->type == PRIM_TRI) RT3_LAUNCH_1D(k_pack_tris, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, (const uint32_t*)g->order.p, g->prims.p);
@@ -385,6 +386,7 @@ int rt3_set_option(rt3_context_t c, const char* key, int value) {
     else if (k == "persist_ctas_per_sm") c->opt_ctas_per_sm = value;
     else if (k == "merge_identity") { c->opt_merge = value; c->built = false; }
     else if (k == "tlas_sah") { c->opt_tlas_sah = value; c->built = false; }
+    else if (k == "ploc") { c->opt_ploc = value; c->built = false; for (auto& g : c->geoms) g->has_blas = false; }
     else if (k == "l2_persist") { c->opt_l2_persist = value; c->built = false; }
     else if (k == "tlas_refine") { c->opt_tlas_refine = value; c->built = false; }
     else if (k == "sort_rays" || k == "sort_materials") { RT3_REQUIRE(value == 0, RT3_ERR_UNSUPPORTED, "set_option: sorting stages are not built yet"); }
@@ -637,7 +639,7 @@ int rt3_accel_build(rt3_context_t c) {
             const Geometry& g = *c->geoms[c->inst[r.inst].blas];
             RT3_LAUNCH_1D(k_tri_boxes, g.nprims, c->stream, (const float*)g.verts.p, (const int32_t*)g.idx.p, lo.p + r.first, hi.p + r.first);
         }
-        build_bvh8(lo.p, hi.p, total, c->stream, c->m_nodes, c->m_order, c->m_bvh);
+        build_bvh8(lo.p, hi.p, total, c->stream, c->m_nodes, c->m_order, c->m_bvh, /*sah_host=*/false, /*ploc=*/c->opt_ploc != 0);
         DevBuf<MergedRange> d_ranges(ranges.size());
         h2d(d_ranges.p, ranges.data(), sizeof(MergedRange) * ranges.size(), c->stream);
         c->m_prims.alloc(3 * (size_t)total);

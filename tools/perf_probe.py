@@ -27,6 +27,9 @@ else:
     d = scenes.motion(width=w, height=h)
 out["scene_gen_s"] = time.time() - t0
 g = Context(0)
+for kv in os.environ.get("OPTS", "").split(","):   # e.g. OPTS=ploc=0,tlas_sah=0
+    if kv:
+        g.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 t0 = time.time()
 scenes.replay(d, g)
 g.sync()
