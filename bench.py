@@ -193,7 +193,7 @@ def run_reference(args):
         tot_samples += sm
     v = tot_rays / tot_s / 1e6
     sample = "%dx%d px x %d spl subframe per step (same scene, camera, depth)" % (w, h, SPL)
-    print(json.dumps({
+    OUT.emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": dict(config_dict(args, args.gpus), film_rendered_per_step="%dx%d" % (w, h), paths_rendered_per_step=w * h * SPL,
@@ -621,11 +621,31 @@ def run_rt3(args):
                 g2.close()
         else:
             out["cpp_host"] = cpp_host_run(world, ROOT)
-        print(json.dumps(out))
+        OUT.emit(json.dumps(out))
+
+
+class QuietStdout:
+    """Everything libraries print to fd 1 while the bench runs (NCCL's version banner, ...) goes to stderr, so that stdout carries
+    exactly ONE line: the JSON record printed through emit()."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(text, flush=True)
+        os.dup2(2, 1)
+
+
+OUT = None
 
 
 if __name__ == "__main__":
     a = parse()
+    OUT = QuietStdout()
     if a.impl == "reference":
         run_reference(a)
     else:
