@@ -294,12 +294,18 @@ RT3_GLOBAL(k_ploc_nearest, BuildArrays b, PlocArrays p) {
     if (i >= (int)p.count) return;
     const float4 lo = b.nlo[p.in[i]], hi = b.nhi[p.in[i]];
     const int from = i - RT3_PLOC_RADIUS < 0 ? 0 : i - RT3_PLOC_RADIUS, to = i + RT3_PLOC_RADIUS > (int)p.count - 1 ? (int)p.count - 1 : i + RT3_PLOC_RADIUS;
+    // Ties are the rule on tessellated grids (every neighbour of a regular mesh gives the same merged area), and a one-sided
+    // tie-break ("the lower index") would chain i -> i-1 -> i-2 ... with ONE mutual pair per round.  The tie-break is therefore
+    // symmetric: among equal areas the partner with the smallest i XOR j, i.e. the one sharing the longest index prefix —
+    // whatever i prefers about j, j prefers about i, so tied neighbours pair up like the siblings of a binary heap.
     float best = 3.4e38f;
+    uint32_t best_x = 0xffffffffu;
     int bj = -1;
     for (int j = from; j <= to; j++) {
         if (j == i) continue;
         const float a = ploc_union_area(lo, hi, b.nlo[p.in[j]], b.nhi[p.in[j]]);
-        if (a < best) { best = a; bj = j; }   // ties: the lower index
+        const uint32_t x = (uint32_t)i ^ (uint32_t)j;
+        if (a < best || (a == best && x < best_x)) { best = a; best_x = x; bj = j; }
     }
     p.nn[i] = bj;
 }
@@ -688,6 +694,7 @@ inline void build_bvh8(const float4* d_plo, const float4* d_phi, uint32_t n, Str
                 RT3_REQUIRE(++rounds < 4096, -2, "build_bvh8: PLOC did not converge");
             }
             RT3_REQUIRE(p.next_id == 0, -2, "build_bvh8: PLOC node count mismatch");
+            if (getenv("RT3_BUILD_VERBOSE")) fprintf(stderr, "rt3 build: PLOC %u primitives, %d rounds\n", n, rounds);
         } else {
             if (n > 1) RT3_LAUNCH_1D(k_bvh_hierarchy, n - 1, st, b);
             RT3_LAUNCH_1D(k_bvh_refit, n, st, b);
