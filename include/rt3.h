@@ -56,8 +56,8 @@ typedef struct {
     uint64_t kernel_launches;                        /* number of librt3 kernels launched so far */
     float ms_generate, ms_extend, ms_shade, ms_connect, ms_resolve; /* CUDA-event time of the LAST subframe, per stage (0 if timing disabled) */
     float ms_total;
-    uint32_t max_stack_depth;                        /* traversal stack high-water mark (debug) */
-    uint32_t error_flags;                            /* bit0: traversal stack overflow */
+    uint32_t max_stack_depth;                        /* traversal stack high-water mark; recorded by diagnostic (-DRT3_STATS) builds only, 0 otherwise */
+    uint32_t error_flags;                            /* bit0: a traversal stack overflowed and dropped a subtree.  rt3_trace and rt3_download_* fail with RT3_ERR_STATE while it is set; rt3_reset_stats clears it */
 } rt3_stats;
 
 /* texture enums: identical values to CUDATexture<T>::AddressMode / FilterMode

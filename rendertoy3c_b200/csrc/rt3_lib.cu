@@ -87,7 +87,7 @@ struct rt3_context {
     bool has_subdiv_curves = false;  // some instance refers to a degree-2 / -3 curve geometry (set in rt3_accel_build)
     int opt_merge = 1;
     int opt_tlas_sah = 1;
-    int opt_ploc = 1;       // BLAS binary tree by parallel locally-ordered clustering (SAH quality) instead of the Morton-order tree   // TLAS binary tree from the host full-sweep SAH builder (small inputs) instead of the LBVH
+    int opt_ploc = 0;       // 1: BLAS binary tree by parallel locally-ordered clustering instead of the Morton-order tree (measured neutral on the tessellated BASELINE meshes)   // TLAS binary tree from the host full-sweep SAH builder (small inputs) instead of the LBVH
     int opt_tlas_refine = 1;  // instance boxes from the BLAS root's grandchild boxes instead of its root box
     DevBuf<uint32_t> d_flags;  // [0] error flags, [1] max stack
     // film
@@ -270,6 +270,16 @@ static inline void use_device(rt3_context* c) {
     }                                                     \
     return RT3_OK;
 
+
+// Device-side error word (bit 0: a traversal stack overflowed and dropped a subtree).  Read wherever the call synchronises
+// anyway, so that a wrong image or hit list is reported instead of returned silently.
+static void require_no_device_error(rt3_context* c, const char* where) {
+    uint32_t fl = 0;
+    d2h(&fl, c->d_flags.p, sizeof(fl), c->stream);
+    stream_sync(c->stream);
+    if (fl & 1u) throw Error(RT3_ERR_STATE, std::string(where) + ": a traversal stack overflowed (more than " + std::to_string(RT3_STACK_SIZE) +
+                                                " pending entries): results are incomplete; rt3_reset_stats clears the flag");
+}
 
 #ifndef RT3_EMULATE
 // NCCL is resolved at run time so that librt3.so has no link-time dependency on it
@@ -570,6 +580,7 @@ static int append_instance_impl(rt3_context_t c, rt3_handle_t blas, const float*
     memcpy(in.xform, xform, sizeof(in.xform));
     if (keys) {
         RT3_REQUIRE(nkeys >= 2 && t1 > t0, RT3_ERR_INVALID, "append_animated_instance: need >= 2 keys and t_end > t_begin");
+        RT3_REQUIRE(nkeys < 65536, RT3_ERR_INVALID, "append_animated_instance: at most 65535 keys (16-bit field of the instance record)");
         in.nkeys = (uint32_t)nkeys;
         in.keys.assign(keys, keys + 12 * (size_t)nkeys);
         in.t0 = t0; in.t1 = t1;
@@ -1013,7 +1024,7 @@ int rt3_trace(rt3_context_t c, const rt3_ray* rays, int n, int any_hit, rt3_hit*
     const int rc = rt3_trace_device(c, d_rays.p, n, any_hit, d_hits.p);
     if (rc != RT3_OK) return rc;
     d2h(hits, d_hits.p, sizeof(rt3_hit) * (size_t)n, c->stream);
-    stream_sync(c->stream);
+    require_no_device_error(c, "trace");
     RT3_API_END
 }
 
@@ -1060,7 +1071,7 @@ int rt3_download_accum(rt3_context_t c, float* rgba) {
     use_device(c);
     RT3_REQUIRE(c && rgba && c->accum.p, RT3_ERR_STATE, "download_accum: nothing rendered");
     d2h(rgba, c->accum.p, c->accum.bytes(), c->stream);
-    stream_sync(c->stream);
+    require_no_device_error(c, "download_accum");
     RT3_API_END
 }
 int rt3_download_frame(rt3_context_t c, uint8_t* rgba8) {
@@ -1068,7 +1079,7 @@ int rt3_download_frame(rt3_context_t c, uint8_t* rgba8) {
     use_device(c);
     RT3_REQUIRE(c && rgba8 && c->frame.p, RT3_ERR_STATE, "download_frame: nothing rendered");
     d2h(rgba8, c->frame.p, c->frame.bytes(), c->stream);
-    stream_sync(c->stream);
+    require_no_device_error(c, "download_frame");
     RT3_API_END
 }
 int rt3_accum_device_ptr(rt3_context_t c, void** p, uint64_t* n) {
@@ -1126,6 +1137,7 @@ int rt3_reset_stats(rt3_context_t c) {
     use_device(c);
     RT3_REQUIRE(c, RT3_ERR_INVALID, "reset_stats: null context");
     dev_memset(c->d_stats.p, 0, c->d_stats.bytes(), c->stream);
+    dev_memset(c->d_flags.p, 0, 2 * sizeof(uint32_t), c->stream);   // error word + stack high-water mark
     c->samples = 0;
     stream_sync(c->stream);
     RT3_API_END

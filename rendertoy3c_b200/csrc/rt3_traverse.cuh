@@ -44,6 +44,9 @@ enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2, PRIM_TRI_MOTION = 3 };  //
 #ifndef RT3_DEFER_PARTIAL
 #define RT3_DEFER_PARTIAL 1   // 1: a pass takes 32 pairs at most and leaves the rest queued (no near-empty second pass: +3-5 %)
 #endif
+#ifndef RT3_COOP_MIN
+#define RT3_COOP_MIN 0    // general kernel: redistribute a round's triangles only when the warp holds at least this many (0 = always when a lane has two)
+#endif
 #ifndef RT3_COOP
 #define RT3_COOP 1        // 1: warp-cooperative triangle phase (step_warp), 0: per-lane loop (step)
 #endif
@@ -455,7 +458,10 @@ struct Trav {
 
     RT3_HD void push(const TravScene& sc, uint2 e) {
         if (sp < RT3_STACK_SIZE) st_put(sp++, e);
-        else rt3_atomic_or(sc.error_flags, 1u);
+        else rt3_atomic_or(sc.error_flags, 1u);   // the subtree is lost: rt3_trace / rt3_download_* report it
+#if defined(RT3_STATS) && !defined(RT3_EMULATE)
+        if ((uint32_t)sp > *sc.max_stack) rt3_atomic_max(sc.max_stack, (uint32_t)sp);   // high-water mark, diagnostic builds
+#endif
     }
 
     RT3_HD bool in_range(float t) const { return t > tmin && (hprim < 0 ? t < tbest : t <= tbest); }
@@ -722,6 +728,16 @@ struct Trav {
                 atomicAdd(d + 9, tl); atomicAdd(d + 10, tt); atomicAdd(d + 11, bl);
             }
         }
+#endif
+#if RT3_COOP_MIN > 0
+        const uint32_t warp_total = __reduce_add_sync(0xffffffffu, cnt);
+        if (maxc > 1u && warp_total < RT3_COOP_MIN) {  // too few pairs to be worth the redistribution: each lane loops over its own
+            if (tri_lane) {
+                while (tg.y != 0u) {
+                    if (prim_step(sc)) { active = false; break; }
+                }
+            }
+        } else
 #endif
         if (maxc == 1u) {  // one triangle per lane at most: nothing to redistribute, test in place
             if (tri_lane) {

@@ -95,13 +95,16 @@ static void k_traverse(TraverseArgs a) {
 }
 #else
 #ifndef RT3_TRAV_MIN_BLOCKS
-#define RT3_TRAV_MIN_BLOCKS 8          // general kernel (TLAS, instances, all primitive types): 64 regs (9 CTAs = 56 regs: -7 % on C3/C4)
+#define RT3_TRAV_MIN_BLOCKS 7          // general kernel (TLAS, instances, all primitive types): 72 regs.  Measured (r02f, C3 / C4 Mrays/s): 5 CTAs 630 / 836, 6 670 / 876, 7 712 / 931, 8 (64 regs, 110 B spilled) 679 / 878, 9 -7 %
 #endif
 #ifndef RT3_TRAV_MIN_BLOCKS_SINGLE
 #define RT3_TRAV_MIN_BLOCKS_SINGLE 8   // single-level kernel (merged world BLAS only): 64 regs, no spills (9 CTAs = 56 regs spills 44 B: -5 %)
 #endif
 #ifndef RT3_REFILL_THRESHOLD
 #define RT3_REFILL_THRESHOLD 26
+#endif
+#ifndef RT3_REFILL_THRESHOLD_GENERAL
+#define RT3_REFILL_THRESHOLD_GENERAL RT3_REFILL_THRESHOLD
 #endif
 // Persistent threads with dynamic fetch: a warp keeps traversing until fewer than
 // RT3_REFILL_THRESHOLD lanes are busy, then refills the idle lanes from the queue with a single
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(RT3_TRAV_THREADS, SINGLE ? RT3_TRAV_MIN_BLOCKS
         }
         uint32_t busy = __ballot_sync(0xffffffffu, active);
         if (busy == 0u) break;
-        const uint32_t threshold = exhausted ? 1u : RT3_REFILL_THRESHOLD;
+        const uint32_t threshold = exhausted ? 1u : (SINGLE ? RT3_REFILL_THRESHOLD : RT3_REFILL_THRESHOLD_GENERAL);
         while (__popc(busy) >= threshold) {
 #if RT3_COOP
             const bool was = active;
