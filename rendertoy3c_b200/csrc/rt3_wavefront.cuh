@@ -104,7 +104,7 @@ static void k_traverse(TraverseArgs a) {
 #define RT3_REFILL_THRESHOLD 26
 #endif
 #ifndef RT3_REFILL_THRESHOLD_GENERAL
-#define RT3_REFILL_THRESHOLD_GENERAL RT3_REFILL_THRESHOLD
+#define RT3_REFILL_THRESHOLD_GENERAL 22   // two-level kernel: rounds are longer (entry, per-lane primitives), refilling earlier pays.  r02g, C3 / C4 Mrays/s: 16 713 / 961, 22 736 / 950, 26 727 / 920, 29 701 / 876
 #endif
 // Persistent threads with dynamic fetch: a warp keeps traversing until fewer than
 // RT3_REFILL_THRESHOLD lanes are busy, then refills the idle lanes from the queue with a single
