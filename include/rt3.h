@@ -74,7 +74,7 @@ const char* rt3_last_error(void);
 int rt3_get_stream(rt3_context_t ctx, void** cuda_stream); /* the cudaStream_t every launch of this context goes to (reference: state.stream, src/wavefront.cpp:302) */
 int rt3_get_stats(rt3_context_t ctx, rt3_stats* out);
 int rt3_reset_stats(rt3_context_t ctx);
-int rt3_get_debug_counters(rt3_context_t ctx, uint32_t out[16]); /* diagnostic builds (-DRT3_STATS): [2] wide nodes visited, [3] primitives tested, [4] rounds, [5] rays, [6..12] warp-round histogram, [12] = queue-full events (rt3_traverse.cuh); reads and clears */
+int rt3_get_debug_counters(rt3_context_t ctx, uint32_t out[16]); /* diagnostic builds (-DRT3_STATS): [2] wide nodes visited, [3] primitives tested, [4] rounds, [5] rays, [6..12] warp-round histogram, [12] = queue-full events, [13] = instance entries (rt3_traverse.cuh); reads and clears */
 int rt3_set_option(rt3_context_t ctx, const char* key, int value); /* tuning switches: "timing", "overlap" (0 = serial schedule, 1 = shadow rays of a bounce on a second stream beside the next extension (default), 2 = additionally two half-frame chains), "persist_ctas_per_sm", "merge_identity" (1 = single-level fast path for identity instances; call before rt3_accel_build) */
 
 /* ---- geometry (BLAS) ------------------------------------------------------------------- */

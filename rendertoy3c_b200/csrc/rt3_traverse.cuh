@@ -19,7 +19,9 @@
 namespace rt3 {
 
 enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2, PRIM_TRI_MOTION = 3 };  // 3: triangles with vertex keys (deformation blur)
+#ifndef RT3_STACK_SIZE
 #define RT3_STACK_SIZE 64
+#endif
 #ifndef RT3_COOP_CAP
 #define RT3_COOP_CAP 32   // (owner, triangle) pairs a warp shares per round
 #endif
@@ -374,7 +376,7 @@ struct Trav {
     int sp;
     uint32_t pend;     // triangles of this lane waiting in the warp's queue (step_warp_deferred)
 #ifdef RT3_STATS
-    uint32_t c_nodes, c_prims, c_rounds;  // diagnostic build only (tools/build_variant.sh -DRT3_STATS)
+    uint32_t c_nodes, c_prims, c_rounds, c_entries;  // diagnostic build only (-DRT3_STATS): wide nodes, primitive tests, rounds, instance entries
     uint32_t* dbg;
 #endif
     // the traversal stack (+ frame) is a separate per-thread array owned by the kernel: as a member its
@@ -430,7 +432,7 @@ struct Trav {
         dbg = sc.error_flags;
 #endif
 #ifdef RT3_STATS
-        c_nodes = c_prims = c_rounds = 0;
+        c_nodes = c_prims = c_rounds = c_entries = 0;
 #endif
         // single-level scenes (merged world BLAS only) never read the frame: skip its local-memory stores
         set_space(ro, rd, rtime, !SINGLE);
@@ -589,7 +591,14 @@ struct Trav {
         tg.y &= tg.y - 1u;
         const uint32_t pi = tg.x + (uint32_t)bit;
         if (!SINGLE && cur_inst < 0) {  // TLAS leaf: enter the instance
+#ifdef RT3_STATS
+            c_entries++;
+#endif
             const int inst = (int)rt3_ldg(sc.tlas_order + pi);
+            if (sp + 3 > RT3_STACK_SIZE) {  // no room for what has to come back (node group, leaf group, exit sentinel): skip the instance, report it
+                rt3_atomic_or(sc.error_flags, 1u);
+                return false;
+            }
             if (ng.y & 0xff000000u) push(sc, ng);
             if (tg.y) push(sc, tg);
             const InstanceDev* in = sc.instances + inst;
@@ -960,6 +969,7 @@ struct Trav {
         rt3_atomic_add(const_cast<uint32_t*>(dbg) + 2, c_nodes);
         rt3_atomic_add(const_cast<uint32_t*>(dbg) + 3, c_prims);
         rt3_atomic_add(const_cast<uint32_t*>(dbg) + 4, c_rounds);
+        rt3_atomic_add(const_cast<uint32_t*>(dbg) + 13, c_entries);
         rt3_atomic_add(const_cast<uint32_t*>(dbg) + 5, 1u);
 #endif
         HitRec h;

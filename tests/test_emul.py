@@ -112,3 +112,26 @@ def test_corrected_mode_with_emitters_nee_cannot_reach(emul_lib, mode):
     with Context(0, lib_path=emul_lib) as e:
         o = build_pair(desc, e)
         check_render(e, o, desc, subframes=2, mode=mode)
+
+
+def test_stack_overflow_is_reported(tmp_path):
+    """a traversal stack that overflows drops a subtree: rt3_trace and the download calls must say so instead of returning
+    an incomplete result (simulator built with a 2-entry stack; the product's holds 64)"""
+    import os
+    import subprocess
+    from rendertoy3c_b200.api import Rt3Error
+    from rendertoy3c_b200 import scenes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = str(tmp_path / "librt3_emul_smallstack.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-strict-aliasing", "-fPIC", "-shared", "-DRT3_EMULATE", "-DRT3_STACK_SIZE=2",
+                    "-x", "c++", os.path.join(root, "rendertoy3c_b200", "csrc", "rt3_lib.cu"), "-I/usr/local/cuda/include", "-o", lib], check=True)
+    desc = SMALL["instanced"]()
+    with Context(0, lib_path=lib) as e:
+        scenes.replay(desc, e)
+        uvw = e.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, 1.0)
+        rays = camera_rays(desc, uvw, 32, 32)
+        with pytest.raises(Rt3Error, match="stack overflowed"):
+            e.trace(rays)
+        assert e.stats()["error_flags"] & 1
+        e.reset_stats()
+        assert e.stats()["error_flags"] == 0

@@ -93,7 +93,7 @@ if os.environ.get("RT3_LIB", "").endswith("_stats.so"):   # the -DRT3_STATS twin
     g.launch_subframe(make_settings(d, uvw2, 0, width=960, height=540))
     g.sync()
     c = g.debug_counters()
-    out["counters_per_ray"] = {"wide_nodes": c[2] / max(1, c[5]), "primitive_tests": c[3] / max(1, c[5]), "rounds": c[4] / max(1, c[5]), "rays": c[5]}
+    out["counters_per_ray"] = {"wide_nodes": c[2] / max(1, c[5]), "primitive_tests": c[3] / max(1, c[5]), "rounds": c[4] / max(1, c[5]), "instance_entries": c[13] / max(1, c[5]), "rays": c[5]}
 print(json.dumps(out, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/perf_probe_%s.json" % scene, "w"), indent=1)
