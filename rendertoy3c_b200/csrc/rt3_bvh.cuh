@@ -110,6 +110,7 @@ struct BuildArrays {  // device pointers of one build
     uint32_t* counters;  // [0] nodes allocated, [1] prims allocated, [2] out-queue size
     int2* q_in;
     int2* q_out;
+    int leaf_max;        // primitives per leaf child, 1 .. RT3_LEAF_MAX
 };
 
 // ------------------------------------------------------------------------------------ kernels
@@ -390,7 +391,7 @@ RT3_GLOBAL(k_bvh_collapse, BuildArrays b) {
     // phase 1: open the largest-area child holding more than 3 primitives; phase 2: use free slots
     // to split the remaining multi-primitive leaves (tighter boxes at no extra nodes)
     for (int phase = 0; phase < 2; phase++) {
-        const int min_count = phase == 0 ? RT3_LEAF_MAX + 1 : 2;
+        const int min_count = phase == 0 ? b.leaf_max + 1 : 2;
         while (nch < 8) {
             int best = -1;
             float best_a = -1.0f;
@@ -439,7 +440,7 @@ RT3_GLOBAL(k_bvh_collapse, BuildArrays b) {
     for (int s = 0; s < 8; s++) {
         if (slot_child[s] < 0) continue;
         const int cnt = bvh2_count(b, ch[slot_child[s]]);
-        if (cnt > RT3_LEAF_MAX) imask |= 1u << s;
+        if (cnt > b.leaf_max) imask |= 1u << s;
         else nprims += (uint32_t)cnt;
     }
     const uint32_t nint = (uint32_t)rt3_popc(imask);
@@ -471,7 +472,7 @@ RT3_GLOBAL(k_bvh_collapse, BuildArrays b) {
         }
         const int id = ch[c];
         const int cnt = bvh2_count(b, id);
-        if (cnt > RT3_LEAF_MAX) {
+        if (cnt > b.leaf_max) {
             nd.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
             const uint32_t cw = child_base + (uint32_t)rt3_popc(imask & ((1u << s) - 1u));
             const uint32_t q = rt3_atomic_add(&b.counters[2], 1u);
@@ -624,7 +625,7 @@ inline void build_bvh2_sah_host(const std::vector<float4>& plo, const std::vecto
 // Builds a BVH8 over n primitive boxes (device arrays).  Synchronises the stream (one-off build).
 // sah_host: the binary tree under the collapse comes from build_bvh2_sah_host (for small n: instance lists) instead of the LBVH.
 inline void build_bvh8(const float4* d_plo, const float4* d_phi, uint32_t n, Stream st, DevBuf<Node8>& out_nodes,
-                       DevBuf<uint32_t>& out_order, Bvh8& out, bool sah_host = false, bool ploc = false) {
+                       DevBuf<uint32_t>& out_order, Bvh8& out, bool sah_host = false, bool ploc = false, int leaf_max = RT3_LEAF_MAX) {
     RT3_REQUIRE(n > 0, -1, "build_bvh8: no primitives");
     // the traversal kernels tag queued triangles as (lane << 27 | index): 2^27 primitives per acceleration structure
     RT3_REQUIRE(n < (1u << 27), -1, "build_bvh8: more than 134,217,727 primitives in one acceleration structure");
@@ -643,6 +644,7 @@ inline void build_bvh8(const float4* d_plo, const float4* d_phi, uint32_t n, Str
     b.nlo = nlo.p; b.nhi = nhi.p; b.left = left.p; b.right = right.p; b.parent = parent.p;
     b.first = first.p; b.last = last.p; b.flags = flags.p;
     b.nodes = nodes.p; b.prim_order = order.p; b.counters = counters.p; b.q_in = qa.p; b.q_out = qb.p;
+    b.leaf_max = leaf_max < 1 ? 1 : (leaf_max > RT3_LEAF_MAX ? RT3_LEAF_MAX : leaf_max);
 
     const uint32_t init_bounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     h2d(bounds.p, init_bounds, sizeof(init_bounds), st);

@@ -36,6 +36,7 @@ struct Geometry {
     DevBuf<float4> prims;
     Bvh8 bvh;
     bool has_blas = false;  // built lazily: meshes that are only used by merged (identity) instances never need one
+    float bsphere[4] = {0, 0, 0, -1};  // object-space bounding sphere (centre of the bounding box, radius to the farthest point), from the host arrays at creation
 };
 
 struct InstanceHost {
@@ -87,8 +88,11 @@ struct rt3_context {
     bool has_subdiv_curves = false;  // some instance refers to a degree-2 / -3 curve geometry (set in rt3_accel_build)
     int opt_merge = 1;
     int opt_tlas_sah = 1;
+    int opt_tlas_leaf = 3;      // instances per TLAS leaf child
+    int opt_bsphere_cull = 1;   // skip TLAS leaves whose instance bounding sphere the ray misses
     int opt_ploc = 0;       // 1: BLAS binary tree by parallel locally-ordered clustering instead of the Morton-order tree (measured neutral on the tessellated BASELINE meshes)   // TLAS binary tree from the host full-sweep SAH builder (small inputs) instead of the LBVH
     int opt_tlas_refine = 1;  // instance boxes from the BLAS root's grandchild boxes instead of its root box
+    DevBuf<float4> d_bsphere;  // [instance][2] world-space bounding spheres (TravScene::inst_bsphere)
     DevBuf<uint32_t> d_flags;  // [0] error flags, [1] max stack
     // film
     uint32_t width = 0, height = 0;
@@ -134,6 +138,7 @@ struct rt3_context {
         s.blas = d_blas.p;
         s.keys = d_keys.p;
         s.inst_fwd = d_static.p;
+        s.inst_bsphere = d_bsphere.p;
         s.error_flags = d_flags.p;
         s.max_stack = d_flags.p + 1;
         return s;
@@ -174,6 +179,44 @@ void upload_hitgroups(rt3_context* c) {
     h2d(c->d_hg.p, hg.data(), sizeof(HitGroupDev) * hg.size(), c->stream);
     stream_sync(c->stream);
     c->hitgroups_dirty = false;
+}
+
+// object-space bounding sphere of n points p[i] (stride floats apart) each with its own radius r[i] (or 0)
+static void bounding_sphere(const float* p, size_t stride, const float* r, size_t rstride, size_t n, float out[4]) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (size_t i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) {
+            const double rr = r ? (double)r[i * rstride] : 0.0, v = p[i * stride + k];
+            lo[k] = v - rr < lo[k] ? v - rr : lo[k];
+            hi[k] = v + rr > hi[k] ? v + rr : hi[k];
+        }
+    const double c[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+    double rad = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        const double dx = p[i * stride] - c[0], dy = p[i * stride + 1] - c[1], dz = p[i * stride + 2] - c[2];
+        const double d = std::sqrt(dx * dx + dy * dy + dz * dz) + (r ? (double)r[i * rstride] : 0.0);
+        rad = d > rad ? d : rad;
+    }
+    out[0] = (float)c[0]; out[1] = (float)c[1]; out[2] = (float)c[2];
+    out[3] = (float)(rad * (1.0 + 1e-5) + 1e-30);
+}
+// largest singular value of the 3x3 part of a row-major 3x4 matrix (power iteration on A^T A), rounded up
+static double spectral_norm(const float* m) {
+    double a[3][3] = {{m[0], m[1], m[2]}, {m[4], m[5], m[6]}, {m[8], m[9], m[10]}}, ata[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) ata[i][j] = a[0][i] * a[0][j] + a[1][i] * a[1][j] + a[2][i] * a[2][j];
+    double v[3] = {0.577, 0.577, 0.577}, lam = 0.0;
+    for (int it = 0; it < 64; it++) {
+        double w[3];
+        for (int i = 0; i < 3; i++) w[i] = ata[i][0] * v[0] + ata[i][1] * v[1] + ata[i][2] * v[2];
+        lam = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        if (lam < 1e-300) return 0.0;
+        for (int i = 0; i < 3; i++) v[i] = w[i] / lam;
+    }
+    // power iteration converges from below: bound it from above by the Frobenius norm where it has not converged
+    const double fro = std::sqrt(ata[0][0] + ata[1][1] + ata[2][2]);
+    const double s = std::sqrt(lam) * 1.001;
+    return s < fro ? s : fro;
 }
 
 uint64_t finish_geometry(rt3_context* c, std::unique_ptr<Geometry> g) {
@@ -396,6 +439,8 @@ int rt3_set_option(rt3_context_t c, const char* key, int value) {
     else if (k == "persist_ctas_per_sm") c->opt_ctas_per_sm = value;
     else if (k == "merge_identity") { c->opt_merge = value; c->built = false; }
     else if (k == "tlas_sah") { c->opt_tlas_sah = value; c->built = false; }
+    else if (k == "bsphere_cull") { c->opt_bsphere_cull = value; c->built = false; }
+    else if (k == "tlas_leaf") { c->opt_tlas_leaf = value; c->built = false; }
     else if (k == "ploc") { c->opt_ploc = value; c->built = false; for (auto& g : c->geoms) g->has_blas = false; }
     else if (k == "l2_persist") { c->opt_l2_persist = value; c->built = false; }
     else if (k == "tlas_refine") { c->opt_tlas_refine = value; c->built = false; }
@@ -419,6 +464,7 @@ int rt3_mesh_create(rt3_context_t c, const float* verts, int num_keys, int nv, c
     g->nprims = (uint32_t)nt;
     g->verts.alloc(3 * (size_t)nv * (size_t)num_keys);
     g->idx.alloc(3 * (size_t)nt);
+    bounding_sphere(verts, 3, nullptr, 0, (size_t)nv * (size_t)num_keys, g->bsphere);
     h2d(g->verts.p, verts, g->verts.bytes(), c->stream);  // [key][vertex][3]
     if (normals) { g->normals.alloc(3 * (size_t)nv); h2d(g->normals.p, normals, g->normals.bytes(), c->stream); }
     if (uvs) { g->uvs.alloc(2 * (size_t)nv); h2d(g->uvs.p, uvs, g->uvs.bytes(), c->stream); }
@@ -449,6 +495,7 @@ int rt3_spheres_create(rt3_context_t c, const float* cr, int n, rt3_handle_t* bl
     g->type = PRIM_SPHERE;
     g->nprims = (uint32_t)n;
     g->cr.alloc(n);
+    bounding_sphere(cr, 4, cr + 3, 4, (size_t)n, g->bsphere);
     h2d(g->cr.p, cr, g->cr.bytes(), c->stream);
     stream_sync(c->stream);
     *blas = finish_geometry(c, std::move(g));
@@ -541,6 +588,7 @@ int rt3_curves_create(rt3_context_t c, int degree, const float* cp, int ncp, con
         h2d(g->poly.p, coef.data(), g->poly.bytes(), c->stream);
     }
     g->nprims = (uint32_t)nseg;
+    bounding_sphere(cp, 4, cp + 3, 4, (size_t)ncp, g->bsphere);   // (tessellated) control points with their radii: every round segment lies in the hull of its end spheres
     g->cr.alloc(ncp);
     g->seg.alloc(nseg);
     h2d(g->cr.p, cp, g->cr.bytes(), c->stream);
@@ -714,6 +762,39 @@ int rt3_accel_build(rt3_context_t c) {
     h2d(c->d_static.p, stat.data(), sizeof(float) * stat.size(), c->stream);
     h2d(c->d_keys.p, keys.data(), sizeof(float) * keys.size(), c->stream);
     RT3_LAUNCH_1D(k_invert_static, ni + 1, c->stream, (const float*)c->d_static.p, c->d_inst.p);
+    {   // world-space bounding spheres of the instances (TravScene::inst_bsphere)
+        std::vector<float> bs(8 * (size_t)(ni + 1), 0.0f);
+        auto xform = [](const float* m, const double p[3], double out[3]) { for (int k = 0; k < 3; k++) out[k] = (double)m[4 * k] * p[0] + (double)m[4 * k + 1] * p[1] + (double)m[4 * k + 2] * p[2] + (double)m[4 * k + 3]; };
+        for (uint32_t i = 0; i <= ni; i++) {
+            float* o = &bs[8 * (size_t)i];
+            o[3] = -1.0f;
+            if (i == ni) continue;   // the merged pseudo-instance
+            const InstanceHost& in = c->inst[i];
+            const Geometry& g = *c->geoms[in.blas];
+            const bool identity = in.nkeys == 0 && memcmp(in.xform, ident, sizeof(ident)) == 0;
+            if (identity || in.nkeys > 2 || !c->opt_bsphere_cull || !(g.bsphere[3] >= 0.0f)) continue;
+            const double c0[3] = {g.bsphere[0], g.bsphere[1], g.bsphere[2]};
+            double w0[3], w1[3], t[3];
+            double scale = spectral_norm(in.xform);
+            if (in.nkeys == 2) {
+                xform(in.keys.data(), c0, t); xform(in.xform, t, w0);
+                xform(in.keys.data() + 12, c0, t); xform(in.xform, t, w1);
+                const double k0 = spectral_norm(in.keys.data()), k1 = spectral_norm(in.keys.data() + 12);
+                scale *= k0 > k1 ? k0 : k1;
+            } else {
+                xform(in.xform, c0, w0);
+                for (int k = 0; k < 3; k++) w1[k] = w0[k];
+            }
+            const double cn = std::sqrt(w0[0] * w0[0] + w0[1] * w0[1] + w0[2] * w0[2]) + std::sqrt(w1[0] * w1[0] + w1[1] * w1[1] + w1[2] * w1[2]);
+            o[0] = (float)w0[0]; o[1] = (float)w0[1]; o[2] = (float)w0[2];
+            o[3] = (float)((double)g.bsphere[3] * scale * (1.0 + 1e-4) + 1e-6 * cn + 1e-30);   // padded: float centres, float ray arithmetic
+            o[4] = (float)(w1[0] - w0[0]); o[5] = (float)(w1[1] - w0[1]); o[6] = (float)(w1[2] - w0[2]);
+            o[7] = in.nkeys == 2 ? 1.0f / (in.t1 - in.t0) : 0.0f;
+        }
+        c->d_bsphere.alloc(2 * (size_t)(ni + 1));
+        h2d(c->d_bsphere.p, bs.data(), sizeof(float) * bs.size(), c->stream);
+        stream_sync(c->stream);
+    }
     // ---- TLAS over the remaining instances (+ the merged pseudo-instance), unless the scene is single-level
     if (!c->single_level) {
         DevBuf<float4> lo(ni + 1), hi(ni + 1);
@@ -728,7 +809,7 @@ int rt3_accel_build(rt3_context_t c) {
             d2d(slo.p + k, lo.p + sel[k], sizeof(float4), c->stream);
             d2d(shi.p + k, hi.p + sel[k], sizeof(float4), c->stream);
         }
-        build_bvh8(slo.p, shi.p, ns, c->stream, c->tlas_nodes, c->tlas_order, c->tlas, /*sah_host=*/c->opt_tlas_sah && ns <= (1u << 16));
+        build_bvh8(slo.p, shi.p, ns, c->stream, c->tlas_nodes, c->tlas_order, c->tlas, /*sah_host=*/c->opt_tlas_sah && ns <= (1u << 16), /*ploc=*/false, /*leaf_max=*/c->opt_tlas_leaf);
         std::vector<uint32_t> order(ns);
         d2h(order.data(), c->tlas_order.p, sizeof(uint32_t) * ns, c->stream);
         stream_sync(c->stream);

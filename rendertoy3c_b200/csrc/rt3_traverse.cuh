@@ -46,6 +46,9 @@ enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2, PRIM_TRI_MOTION = 3 };  //
 #ifndef RT3_DEFER_PARTIAL
 #define RT3_DEFER_PARTIAL 1   // 1: a pass takes 32 pairs at most and leaves the rest queued (no near-empty second pass: +3-5 %)
 #endif
+#ifndef RT3_BSPHERE_TNEAR
+#define RT3_BSPHERE_TNEAR 0   // 1: instance bounding spheres also cull by entry distance against the closest hit so far (measured: entries per ray 3.38 -> 3.31 on C3, not worth a sqrt)
+#endif
 #ifndef RT3_COOP_MIN
 #define RT3_COOP_MIN 0    // general kernel: redistribute a round's triangles only when the warp holds at least this many (0 = always when a lane has two)
 #endif
@@ -102,6 +105,11 @@ struct TravScene {
     const BlasDev* blas;
     const float* keys;
     const float* inst_fwd;          // [instance][12] object -> world of the static instance transform (rt3_get_local_geometry)
+    // [instance][2] world-space bounding sphere of the instanced geometry: {centre at the first motion key, radius} {centre(last key) -
+    // centre(first key), 1 / (t1 - t0) or 0 when static}; radius < 0 = none (identity instances, more than two keys).  A TLAS leaf
+    // whose sphere the ray misses is not entered: the leaf box is the world AABB of a rotated object, and for compact objects about half
+    // of the rays through such a box miss the object's bounding sphere, while an entry costs a transform, three divisions and a BLAS root
+    const float4* inst_bsphere;
     uint32_t* error_flags;          // bit0 stack overflow
     uint32_t* max_stack;
     // single-level fast path: all identity, static triangle-mesh instances (every instance the
@@ -591,10 +599,31 @@ struct Trav {
         tg.y &= tg.y - 1u;
         const uint32_t pi = tg.x + (uint32_t)bit;
         if (!SINGLE && cur_inst < 0) {  // TLAS leaf: enter the instance
+            const int inst = (int)rt3_ldg(sc.tlas_order + pi);
+            {
+                const float4 b0 = rt3_ldg(sc.inst_bsphere + 2 * (size_t)inst);
+                if (b0.w >= 0.0f) {
+                    const float4 b1 = rt3_ldg(sc.inst_bsphere + 2 * (size_t)inst + 1);
+                    float3 c = v3(b0);
+                    if (b1.w != 0.0f) {  // two motion keys: the centre moves on a straight line (the transform is linear in the key weight)
+                        const float a = fminf(fmaxf((ray_time() - sc.instances[inst].t0) * b1.w, 0.0f), 1.0f);
+                        c = add(c, mul(v3(b1), a));
+                    }
+                    const float3 O = sub(o, c), D = cur_d();   // in the TLAS the current space is the world
+                    const float OO = dot(O, O), RR = b0.w * b0.w, bq = dot(O, D), cq = OO - RR;
+                    if (cq > 1e-5f * (OO + RR)) {                // origin safely outside
+                        const float aq = dot(D, D), disc = bq * bq - aq * cq;
+                        if (bq >= 0.0f || disc < -1e-5f * (bq * bq + aq * cq)) return false;   // pointing away, or passing by
+#if RT3_BSPHERE_TNEAR
+                        // entering the sphere beyond the closest hit so far (the leaf BOX was nearer, its corner is not the object)
+                        if (disc > 0.0f && (-bq - sqrtf(disc)) * (1.0f - 1e-5f) > tbest * aq) return false;
+#endif
+                    }
+                }
+            }
 #ifdef RT3_STATS
             c_entries++;
 #endif
-            const int inst = (int)rt3_ldg(sc.tlas_order + pi);
             if (sp + 3 > RT3_STACK_SIZE) {  // no room for what has to come back (node group, leaf group, exit sentinel): skip the instance, report it
                 rt3_atomic_or(sc.error_flags, 1u);
                 return false;
