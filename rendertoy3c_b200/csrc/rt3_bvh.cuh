@@ -111,6 +111,11 @@ struct BuildArrays {  // device pointers of one build
     int2* q_in;
     int2* q_out;
     int leaf_max;        // primitives per leaf child, 1 .. RT3_LEAF_MAX
+    // SAH-optimal collapse (k_bvh_dp): per BVH2 node the cost of representing its subtree with at most i = 1..7 children of a
+    // wide node, and the split that achieves it; null = greedy collapse
+    float* dp_cost;      // [2n-1][7]
+    uint8_t* dp_split;   // [2n-1][8]: [j-1] = slots given to the left child when the node is spread over j slots (0: j-1 slots are as good)
+    uint32_t* dp_flags;  // arrival counters of the bottom-up pass
 };
 
 // ------------------------------------------------------------------------------------ kernels
@@ -375,6 +380,93 @@ RT3_HD uint32_t quant_exponent(float p, float hi) {
     return E;
 }
 
+// ------------------------------------------------------------------------------------ SAH-optimal collapse (dynamic program)
+// Which descendants of a binary node become the (at most) 8 children of its wide node decides how many wide nodes a ray
+// visits.  After Ylitie, Karras & Laine 2017 (section 3.1): bottom-up over the binary tree, C(n, i) = the least SAH cost of
+// representing the subtree of n by at most i child slots —
+//     C(n, 1) = min( leaf: A(n) * P(n) * c_prim  if P(n) <= leaf_max,   wide node: D(n, 8) + A(n) * c_node )
+//     C(n, i) = min( D(n, i), C(n, i - 1) ),     D(n, j) = min over 0 < k < j of C(left, k) + C(right, j - k)
+// — and the collapse then follows the recorded splits instead of greedily opening the largest child.
+#define RT3_DP_CNODE 1.0f
+#ifndef RT3_DP_CPRIM
+#define RT3_DP_CPRIM 0.3f
+#endif
+RT3_HD void bvh_dp_node(const BuildArrays& b, int id) {
+    const int n = (int)b.n;
+    float* c = b.dp_cost + 7 * (size_t)id;
+    uint8_t* sp = b.dp_split + 8 * (size_t)id;
+    const float area = bvh2_area(b, id);
+    if (id >= n - 1) {  // a primitive
+        for (int i = 0; i < 7; i++) c[i] = area * RT3_DP_CPRIM;
+        for (int i = 0; i < 8; i++) sp[i] = 0;
+        return;
+    }
+    const float* cl = b.dp_cost + 7 * (size_t)b.left[id];
+    const float* cr = b.dp_cost + 7 * (size_t)b.right[id];
+    float dist[9];
+    uint8_t kbest[9];
+    for (int j = 2; j <= 8; j++) {
+        float best = 3.4e38f;
+        int bk = 1;
+        for (int k = 1; k < j; k++) {
+            if (k > 7 || j - k > 7) continue;
+            const float v = cl[k - 1] + cr[j - k - 1];
+            if (v < best) { best = v; bk = k; }
+        }
+        dist[j] = best;
+        kbest[j] = (uint8_t)bk;
+    }
+    const int cnt = bvh2_count(b, id);
+    const float c_leaf = cnt <= b.leaf_max ? area * (float)cnt * RT3_DP_CPRIM : 3.4e38f;
+    const float c_node = dist[8] + area * RT3_DP_CNODE;
+    c[0] = c_leaf < c_node ? c_leaf : c_node;
+    sp[0] = 0;
+    for (int i = 2; i <= 7; i++) {
+        if (dist[i] < c[i - 2]) { c[i - 1] = dist[i]; sp[i - 1] = kbest[i]; }
+        else { c[i - 1] = c[i - 2]; sp[i - 1] = 0; }
+    }
+    sp[7] = kbest[8];
+}
+RT3_GLOBAL(k_bvh_dp, BuildArrays b) {   // one thread per primitive, walking up; the second arrival at a node computes it
+    const uint32_t j = RT3_THREAD_ID();
+    if (j >= rt3_n_) return;
+    const int n = (int)b.n;
+    int id = n - 1 + (int)j;
+    bvh_dp_node(b, id);
+    if (n == 1) return;
+    int cur = b.parent[id];
+    while (cur >= 0) {
+        rt3_threadfence();
+        if (rt3_atomic_add(&b.dp_flags[cur], 1u) == 0u) return;
+        rt3_threadfence();
+        bvh_dp_node(b, cur);
+        cur = b.parent[cur];
+    }
+}
+// the children of the wide node rooted at binary node `root`, following the recorded splits
+RT3_HD int bvh_dp_children(const BuildArrays& b, int root, int ch[8]) {
+    const int n = (int)b.n;
+    int nch = 0;
+    int st_node[16], st_slots[16], sp = 0;
+    {   // the root of a wide node is opened by definition: its 8 slots go to its two binary children
+        const int k = b.dp_split[8 * (size_t)root + 7];
+        st_node[sp] = b.right[root]; st_slots[sp++] = 8 - k;
+        st_node[sp] = b.left[root]; st_slots[sp++] = k;
+    }
+    while (sp > 0) {
+        const int m = st_node[--sp];
+        int i = st_slots[sp];
+        if (m >= n - 1 || i <= 1) { ch[nch++] = m; continue; }
+        if (i > 7) i = 7;
+        int k = b.dp_split[8 * (size_t)m + (size_t)(i - 1)];
+        while (k == 0 && i > 1) { --i; k = i > 1 ? b.dp_split[8 * (size_t)m + (size_t)(i - 1)] : 0; }   // fewer slots are as good
+        if (i <= 1) { ch[nch++] = m; continue; }
+        st_node[sp] = b.right[m]; st_slots[sp++] = i - k;
+        st_node[sp] = b.left[m]; st_slots[sp++] = k;
+    }
+    return nch;
+}
+
 #ifndef RT3_LEAF_MAX
 #define RT3_LEAF_MAX 3  // primitives per leaf child (the meta byte holds a unary count of up to 3)
 #endif
@@ -388,6 +480,8 @@ RT3_GLOBAL(k_bvh_collapse, BuildArrays b) {
     int ch[8];
     int nch = 1;
     ch[0] = root;
+    if (b.dp_split != nullptr && root < n - 1) nch = bvh_dp_children(b, root, ch);
+    else
     // phase 1: open the largest-area child holding more than 3 primitives; phase 2: use free slots
     // to split the remaining multi-primitive leaves (tighter boxes at no extra nodes)
     for (int phase = 0; phase < 2; phase++) {
@@ -559,7 +653,7 @@ inline void sort_pairs(uint64_t* keys, uint32_t* vals, uint32_t n, Stream st) {
 // nodes 0 .. n-2 (root 0), leaf of sorted position j at id n-1+j, [first, last] = the node's range of sorted positions —
 // and collapsed to the wide layout by the same kernel.  O(n log^2 n); ~1 ms for 1000 boxes.
 struct HostBvh2 {
-    std::vector<int> left, right, first, last;
+    std::vector<int> left, right, first, last, parent;   // parent: [2n - 1], -1 at the root
     std::vector<float4> nlo, nhi;   // [2n - 1]
     std::vector<uint32_t> vals;     // sorted position -> primitive
 };
@@ -568,6 +662,7 @@ inline void build_bvh2_sah_host(const std::vector<float4>& plo, const std::vecto
     t.left.assign((size_t)n - 1, 0); t.right.assign((size_t)n - 1, 0); t.first.assign((size_t)n - 1, 0); t.last.assign((size_t)n - 1, 0);
     t.nlo.assign((size_t)2 * n, make_float4(0, 0, 0, 0)); t.nhi.assign((size_t)2 * n, make_float4(0, 0, 0, 0));
     t.vals.resize((size_t)n);
+    t.parent.assign((size_t)2 * n, -1);
     for (int i = 0; i < n; i++) t.vals[(size_t)i] = (uint32_t)i;
     struct Box { float lo[3], hi[3]; };
     auto grow = [&](Box& b, uint32_t p) {
@@ -610,6 +705,7 @@ inline void build_bvh2_sah_host(const std::vector<float4>& plo, const std::vecto
         const int lc = m == j.a ? n - 1 + j.a : next_internal++;
         const int rc = m + 1 == j.b ? n - 1 + j.b : next_internal++;
         t.left[(size_t)j.id] = lc; t.right[(size_t)j.id] = rc;
+        t.parent[(size_t)lc] = j.id; t.parent[(size_t)rc] = j.id;
         if (lc < n - 1) todo.push_back({j.a, m, lc});
         if (rc < n - 1) todo.push_back({m + 1, j.b, rc});
     }
@@ -625,7 +721,7 @@ inline void build_bvh2_sah_host(const std::vector<float4>& plo, const std::vecto
 // Builds a BVH8 over n primitive boxes (device arrays).  Synchronises the stream (one-off build).
 // sah_host: the binary tree under the collapse comes from build_bvh2_sah_host (for small n: instance lists) instead of the LBVH.
 inline void build_bvh8(const float4* d_plo, const float4* d_phi, uint32_t n, Stream st, DevBuf<Node8>& out_nodes,
-                       DevBuf<uint32_t>& out_order, Bvh8& out, bool sah_host = false, bool ploc = false, int leaf_max = RT3_LEAF_MAX) {
+                       DevBuf<uint32_t>& out_order, Bvh8& out, bool sah_host = false, bool ploc = false, int leaf_max = RT3_LEAF_MAX, bool sah_collapse = false) {
     RT3_REQUIRE(n > 0, -1, "build_bvh8: no primitives");
     // the traversal kernels tag queued triangles as (lane << 27 | index): 2^27 primitives per acceleration structure
     RT3_REQUIRE(n < (1u << 27), -1, "build_bvh8: more than 134,217,727 primitives in one acceleration structure");
@@ -665,6 +761,7 @@ inline void build_bvh8(const float4* d_plo, const float4* d_phi, uint32_t n, Str
         h2d(right.p, t.right.data(), sizeof(int) * (n - 1), st);
         h2d(first.p, t.first.data(), sizeof(int) * (n - 1), st);
         h2d(last.p, t.last.data(), sizeof(int) * (n - 1), st);
+        h2d(parent.p, t.parent.data(), sizeof(int) * (nn - 1), st);
         stream_sync(st);
     } else {
         RT3_LAUNCH_1D(k_bvh_bounds, n, st, b);
@@ -703,6 +800,16 @@ inline void build_bvh8(const float4* d_plo, const float4* d_phi, uint32_t n, Str
         }
     }
 
+    DevBuf<float> dp_cost;
+    DevBuf<uint8_t> dp_split;
+    DevBuf<uint32_t> dp_flags;
+    b.dp_cost = nullptr; b.dp_split = nullptr; b.dp_flags = nullptr;
+    if (sah_collapse && n > 8) {
+        dp_cost.alloc(7 * (size_t)nn); dp_split.alloc(8 * (size_t)nn); dp_flags.alloc(n);
+        dev_memset(dp_flags.p, 0, sizeof(uint32_t) * n, st);
+        b.dp_cost = dp_cost.p; b.dp_split = dp_split.p; b.dp_flags = dp_flags.p;
+        RT3_LAUNCH_1D(k_bvh_dp, n, st, b);
+    }
     // collapse, level by level
     const uint32_t init_counters[4] = {1u, 0u, 0u, 0u};  // node 0 = root
     h2d(counters.p, init_counters, sizeof(init_counters), st);

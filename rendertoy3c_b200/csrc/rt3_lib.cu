@@ -88,7 +88,8 @@ struct rt3_context {
     bool has_subdiv_curves = false;  // some instance refers to a degree-2 / -3 curve geometry (set in rt3_accel_build)
     int opt_merge = 1;
     int opt_tlas_sah = 1;
-    int opt_tlas_leaf = 3;      // instances per TLAS leaf child
+    int opt_tlas_leaf = 1;      // instances per TLAS leaf child (r02j, C3 / C4 Mrays/s: 3 -> 762 / 957, 2 -> 785 / 927, 1 -> 815 / 953: an own box per instance culls more entries than the extra TLAS nodes cost)
+    int opt_sah_collapse = 0;   // 1: binary -> wide collapse by the SAH dynamic program (k_bvh_dp) instead of greedy largest-area opening
     int opt_bsphere_cull = 1;   // skip TLAS leaves whose instance bounding sphere the ray misses
     int opt_ploc = 0;       // 1: BLAS binary tree by parallel locally-ordered clustering instead of the Morton-order tree (measured neutral on the tessellated BASELINE meshes)   // TLAS binary tree from the host full-sweep SAH builder (small inputs) instead of the LBVH
     int opt_tlas_refine = 1;  // instance boxes from the BLAS root's grandchild boxes instead of its root box
@@ -233,7 +234,7 @@ void ensure_blas(rt3_context* c, Geometry* g) {
     else if (g->type == PRIM_TRI_MOTION) RT3_LAUNCH_1D(k_tri_boxes_motion, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, g->vkeys, g->nv, lo.p, hi.p);
     else if (g->type == PRIM_SPHERE) RT3_LAUNCH_1D(k_sphere_boxes, g->nprims, c->stream, (const float4*)g->cr.p, lo.p, hi.p);
     else RT3_LAUNCH_1D(k_curve_boxes, g->nprims, c->stream, (const float4*)g->cr.p, (const int32_t*)g->seg.p, lo.p, hi.p);
-    build_bvh8(lo.p, hi.p, g->nprims, c->stream, g->nodes, g->order, g->bvh, /*sah_host=*/false, /*ploc=*/c->opt_ploc != 0);
+    build_bvh8(lo.p, hi.p, g->nprims, c->stream, g->nodes, g->order, g->bvh, /*sah_host=*/false, /*ploc=*/c->opt_ploc != 0, RT3_LEAF_MAX, /*sah_collapse=*/c->opt_sah_collapse != 0);
     g->prims.alloc(3 * (size_t)g->nprims * g->vkeys);
     if (g->type == PRIM_TRI_MOTION) RT3_LAUNCH_1D(k_pack_tris_motion, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, g->vkeys, g->nv, (const uint32_t*)g->order.p, g->prims.p);
     else if (g->type == PRIM_TRI) RT3_LAUNCH_1D(k_pack_tris, g->nprims, c->stream, (const float*)g->verts.p, (const int32_t*)g->idx.p, (const uint32_t*)g->order.p, g->prims.p);
@@ -441,6 +442,7 @@ int rt3_set_option(rt3_context_t c, const char* key, int value) {
     else if (k == "tlas_sah") { c->opt_tlas_sah = value; c->built = false; }
     else if (k == "bsphere_cull") { c->opt_bsphere_cull = value; c->built = false; }
     else if (k == "tlas_leaf") { c->opt_tlas_leaf = value; c->built = false; }
+    else if (k == "sah_collapse") { c->opt_sah_collapse = value; c->built = false; for (auto& g : c->geoms) g->has_blas = false; }
     else if (k == "ploc") { c->opt_ploc = value; c->built = false; for (auto& g : c->geoms) g->has_blas = false; }
     else if (k == "l2_persist") { c->opt_l2_persist = value; c->built = false; }
     else if (k == "tlas_refine") { c->opt_tlas_refine = value; c->built = false; }
@@ -698,7 +700,7 @@ int rt3_accel_build(rt3_context_t c) {
             const Geometry& g = *c->geoms[c->inst[r.inst].blas];
             RT3_LAUNCH_1D(k_tri_boxes, g.nprims, c->stream, (const float*)g.verts.p, (const int32_t*)g.idx.p, lo.p + r.first, hi.p + r.first);
         }
-        build_bvh8(lo.p, hi.p, total, c->stream, c->m_nodes, c->m_order, c->m_bvh, /*sah_host=*/false, /*ploc=*/c->opt_ploc != 0);
+        build_bvh8(lo.p, hi.p, total, c->stream, c->m_nodes, c->m_order, c->m_bvh, /*sah_host=*/false, /*ploc=*/c->opt_ploc != 0, RT3_LEAF_MAX, /*sah_collapse=*/c->opt_sah_collapse != 0);
         DevBuf<MergedRange> d_ranges(ranges.size());
         h2d(d_ranges.p, ranges.data(), sizeof(MergedRange) * ranges.size(), c->stream);
         c->m_prims.alloc(3 * (size_t)total);
@@ -809,7 +811,7 @@ int rt3_accel_build(rt3_context_t c) {
             d2d(slo.p + k, lo.p + sel[k], sizeof(float4), c->stream);
             d2d(shi.p + k, hi.p + sel[k], sizeof(float4), c->stream);
         }
-        build_bvh8(slo.p, shi.p, ns, c->stream, c->tlas_nodes, c->tlas_order, c->tlas, /*sah_host=*/c->opt_tlas_sah && ns <= (1u << 16), /*ploc=*/false, /*leaf_max=*/c->opt_tlas_leaf);
+        build_bvh8(slo.p, shi.p, ns, c->stream, c->tlas_nodes, c->tlas_order, c->tlas, /*sah_host=*/c->opt_tlas_sah && ns <= (1u << 16), /*ploc=*/false, /*leaf_max=*/c->opt_tlas_leaf, /*sah_collapse=*/c->opt_sah_collapse != 0);
         std::vector<uint32_t> order(ns);
         d2h(order.data(), c->tlas_order.p, sizeof(uint32_t) * ns, c->stream);
         stream_sync(c->stream);
