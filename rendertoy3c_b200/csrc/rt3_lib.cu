@@ -89,7 +89,7 @@ struct rt3_context {
     int opt_merge = 1;
     int opt_tlas_sah = 1;
     int opt_tlas_leaf = 1;      // instances per TLAS leaf child (r02j, C3 / C4 Mrays/s: 3 -> 762 / 957, 2 -> 785 / 927, 1 -> 815 / 953: an own box per instance culls more entries than the extra TLAS nodes cost)
-    int opt_sah_collapse = 0;   // 1: binary -> wide collapse by the SAH dynamic program (k_bvh_dp) instead of greedy largest-area opening
+    int opt_sah_collapse = 1;   // binary -> wide collapse by the SAH dynamic program (k_bvh_dp); 0 = greedy largest-area opening
     int opt_bsphere_cull = 1;   // skip TLAS leaves whose instance bounding sphere the ray misses
     int opt_ploc = 0;       // 1: BLAS binary tree by parallel locally-ordered clustering instead of the Morton-order tree (measured neutral on the tessellated BASELINE meshes)   // TLAS binary tree from the host full-sweep SAH builder (small inputs) instead of the LBVH
     int opt_tlas_refine = 1;  // instance boxes from the BLAS root's grandchild boxes instead of its root box
