@@ -49,6 +49,12 @@ enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2, PRIM_TRI_MOTION = 3 };  //
 #ifndef RT3_BSPHERE_TNEAR
 #define RT3_BSPHERE_TNEAR 0   // 1: instance bounding spheres also cull by entry distance against the closest hit so far (measured: entries per ray 3.38 -> 3.31 on C3, not worth a sqrt)
 #endif
+#ifndef RT3_TRI_BATCH
+#define RT3_TRI_BATCH 16    // general kernel: run the triangle phase only when the warp holds at least this many pending pairs (0 / 1 = every round)
+#endif
+#ifndef RT3_ENTRY_BATCH
+#define RT3_ENTRY_BATCH 6   // general kernel: run the entry / sphere / curve phase only when at least this many lanes want it (0 / 1 = every round)
+#endif
 #ifndef RT3_COOP_MIN
 #define RT3_COOP_MIN 0    // general kernel: redistribute a round's triangles only when the warp holds at least this many (0 = always when a lane has two)
 #endif
@@ -754,7 +760,21 @@ struct Trav {
             if (active && tg.y == 0u) node_step(sc);
         }
         // ---- cooperative triangle phase (warp-uniform control flow from here)
-        const bool tri_lane = active && tg.y != 0u && (SINGLE || (cur_inst >= 0 && ptype == PRIM_TRI));
+        bool tri_lane = active && tg.y != 0u && (SINGLE || (cur_inst >= 0 && ptype == PRIM_TRI));
+        const bool other_lane = !SINGLE && active && tg.y != 0u && !tri_lane;   // a TLAS leaf to enter, spheres, curves
+#if RT3_TRI_BATCH > 1 || RT3_ENTRY_BATCH > 1
+        // Minority phases run at a handful of lanes when every round serves whoever happens to need them.  A lane with
+        // pending primitives / a pending entry simply WAITS (it holds its place, does no node work) until enough lanes of
+        // the warp want the same phase — or until no lane could use the round for node work anyway.
+        const bool can_node = active && tg.y == 0u;   // will pop / step a node next round
+        const bool nobody_ready = __ballot_sync(0xffffffffu, can_node) == 0u;
+#endif
+#if RT3_TRI_BATCH > 1
+        if (!SINGLE) {
+            const uint32_t pending = __reduce_add_sync(0xffffffffu, tri_lane ? (uint32_t)__popc(tg.y) : 0u);
+            if (pending < RT3_TRI_BATCH && !nobody_ready) tri_lane = false;   // keep tg: the pairs wait in the lanes
+        }
+#endif
         const uint32_t cnt = tri_lane ? (uint32_t)__popc(tg.y) : 0u;
         const uint32_t maxc = __reduce_max_sync(0xffffffffu, cnt);
 #ifdef RT3_STATS
@@ -849,7 +869,12 @@ struct Trav {
         }
         }
         // ---- everything else that is pending: instance entry, spheres, curves (per lane)
-        if (!SINGLE && active && tg.y != 0u && !(cur_inst >= 0 && ptype == PRIM_TRI)) {
+#if RT3_ENTRY_BATCH > 1
+        const bool go_other = (uint32_t)__popc(__ballot_sync(0xffffffffu, other_lane)) >= RT3_ENTRY_BATCH || nobody_ready;
+#else
+        const bool go_other = true;
+#endif
+        if (other_lane && go_other) {
             while (tg.y != 0u) {
                 if (prim_step(sc)) { active = false; break; }
             }
