@@ -53,7 +53,7 @@ enum { PRIM_TRI = 0, PRIM_SPHERE = 1, PRIM_CURVE = 2, PRIM_TRI_MOTION = 3 };  //
 #define RT3_TRI_BATCH 16    // general kernel: run the triangle phase only when the warp holds at least this many pending pairs (0 / 1 = every round)
 #endif
 #ifndef RT3_ENTRY_BATCH
-#define RT3_ENTRY_BATCH 6   // general kernel: run the entry / sphere / curve phase only when at least this many lanes want it (0 / 1 = every round)
+#define RT3_ENTRY_BATCH 8   // general kernel: run the entry / sphere / curve phase only when at least this many lanes want it (0 / 1 = every round)
 #endif
 #ifndef RT3_COOP_MIN
 #define RT3_COOP_MIN 0    // general kernel: redistribute a round's triangles only when the warp holds at least this many (0 = always when a lane has two)
