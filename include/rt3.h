@@ -96,7 +96,8 @@ int rt3_spheres_create(rt3_context_t ctx, const float* center_radius, int n, rt3
  * evaluates): segment i uses control points seg_first_cp[i] .. + 1 (linear), + 2 (quadratic B-spline), + 3 (the cubic types).
  * Linear segments are intersected directly (cuda/curve.h:38-80, cuda/GeometryData.h:127-133).  The other types are converted
  * with the SDK's Quadratic / CubicInterpolator::initializeFrom{BSpline, Catrom, Bezier} (cuda/curve.h:98-243); rays are
- * intersected with 8 round linear sub-segments per segment, and the shading normal is the SDK's surfaceNormal<> of the TRUE
+ * intersected with K round linear pieces per segment — K adapts per segment (1..64) so that the pieces stay within 2 % of
+ * the segment's radius of the true curve — and the shading normal is the SDK's surfaceNormal<> of the TRUE
  * curve at the hit's parameter (cuda/curve.h:311-379; flat end caps at u = 0 / 1).  Hits report the segment and u in [0,1]. */
 enum { RT3_CURVE_LINEAR = 1, RT3_CURVE_QUADRATIC_BSPLINE = 2, RT3_CURVE_CUBIC_BSPLINE = 3, RT3_CURVE_CATMULLROM = 4, RT3_CURVE_BEZIER = 5 };
 int rt3_curves_create(rt3_context_t ctx, int degree, const float* cp_radius, int ncp, const int32_t* seg_first_cp,

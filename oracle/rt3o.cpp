@@ -176,7 +176,9 @@ struct Blas {
     int type = PRIM_TRI;
     std::vector<f3> verts, normals;    // verts: [vkeys][nv] (vertex-key motion, cuda_mesh.h:85-88: keys spread over time [0,1])
     int vkeys = 1, nv = 0;
-    int subdiv = 1;                    // spline curves: linear sub-segments per user segment (hits translated at the API boundary)
+    std::vector<int> sub_first;        // spline curves: first linear sub-segment of every USER segment (+ end); empty otherwise
+    std::vector<int> sub_seg;          // spline curves: user segment of every sub-segment (hits translated at the API boundary)
+    bool spline() const { return !sub_first.empty(); }
     std::vector<CurvePoly> poly;       // spline curves: the true curve of every USER segment (normals are taken from it, cuda/curve.h:311-379)
     std::vector<f2> uvs;               // normals / uvs may be empty: the SDK's fallbacks (cuda/LocalGeometry.h:120-124,150-158)
     std::vector<float> colors;         // optional vertex colours, 4 per vertex (LocalGeometry.h:99-110)
@@ -444,10 +446,10 @@ struct rt3o_scene {
                 f3 c = {b.cr[4 * h.prim], b.cr[4 * h.prim + 1], b.cr[4 * h.prim + 2]};
                 n_obj = (ps - c) / b.cr[4 * h.prim + 3];
                 uv = {0, 0};
-            } else if (b.subdiv > 1) {  // spline curve: the SDK's bona fide normal of the TRUE curve (cuda/curve.h:311-379) at the hit's curve parameter
-                const int K = b.subdiv, k = h.prim % K;
-                const float uu = ((float)k + h.u) / (float)K;
-                n_obj = curve_surface_normal_raw(b.poly[(size_t)(h.prim / K)], uu, ps);
+            } else if (b.spline()) {  // spline curve: the SDK's bona fide normal of the TRUE curve (cuda/curve.h:311-379) at the hit's curve parameter
+                const int sg = b.sub_seg[(size_t)h.prim], first = b.sub_first[(size_t)sg], K = b.sub_first[(size_t)sg + 1] - first;
+                const float uu = ((float)(h.prim - first) + h.u) / (float)K;
+                n_obj = curve_surface_normal_raw(b.poly[(size_t)sg], uu, ps);
                 uv = {uu, 0};
             } else {  // cuda/curve.h:382-425 surfaceNormal<LinearInterpolator>
                 int a = b.seg[h.prim];
@@ -841,41 +843,74 @@ int rt3o_spheres_create(rt3o_scene* s, const float* cr, int n) {
     return finish_blas(s, std::move(b));
     RT3O_CATCH(-1)
 }
-// Degree-2 / -3 round curves: each segment (uniform B-spline over control points [a, a + degree], the SDK's
-// Quadratic / CubicInterpolator::initializeFromBSpline + position4, cuda/curve.h:98-140,172-230) is realised as
-// RT3_CURVE_SUBDIV round linear sub-segments between the points P(k / RT3_CURVE_SUBDIV).  Inside the library the
-// sub-segments are ordinary linear-curve primitives; hit records are translated at the API boundary:
-// prim = sub / SUBDIV, u = (sub % SUBDIV + u_sub) / SUBDIV.
-#ifndef RT3_CURVE_SUBDIV
-#define RT3_CURVE_SUBDIV 8
+// Spline curves (quadratic / cubic B-spline, Catmull-Rom, Bezier: the SDK's interpolators, cuda/curve.h:98-243): every user
+// segment is intersected as K round linear sub-segments between the points P(k / K) of its TRUE polynomial; normals come
+// from the true curve (local_geometry).  K is chosen per segment from the polynomial itself: a chord over 1 / K of the
+// parameter range deviates from the curve by at most max|P''| / (8 K^2), and P'' is linear in u, so its maximum is at
+// u = 0 or 1.  K is the smallest count that keeps that bound — for the axis and for the radius — under RT3_CURVE_TOL
+// times the segment's largest radius (taken at u = 0, 1/2, 1), clamped to [1, RT3_CURVE_MAX_SUBDIV].  Inside the library the sub-segments are
+// ordinary linear-curve primitives; hit records are translated at the API boundary through sub_first / sub_seg:
+// prim = user segment, u = (k + u_sub) / K.
+#ifndef RT3_CURVE_TOL
+#define RT3_CURVE_TOL 0.02
 #endif
-static void tessellate_curves(int basis, const float* cp, const int32_t* seg, int nseg, std::vector<float>& out_cp, std::vector<int32_t>& out_seg, std::vector<CurvePoly>& poly) {
-    const int K = RT3_CURVE_SUBDIV;
-    out_cp.resize((size_t)4 * nseg * (K + 1));
-    out_seg.resize((size_t)nseg * K);
-    poly.resize((size_t)nseg);
+#ifndef RT3_CURVE_MAX_SUBDIV
+#define RT3_CURVE_MAX_SUBDIV 64
+#endif
+static int curve_pieces(const CurvePoly& p) {
+    double m_axis = 0.0, m_rad = 0.0;
+    for (int end = 0; end < 2; end++) {  // P''(u) = 6 c0 u + 2 c1
+        const double ax = 2.0 * (double)p.c[1].x + (end ? 6.0 * (double)p.c[0].x : 0.0);
+        const double ay = 2.0 * (double)p.c[1].y + (end ? 6.0 * (double)p.c[0].y : 0.0);
+        const double az = 2.0 * (double)p.c[1].z + (end ? 6.0 * (double)p.c[0].z : 0.0);
+        const double aw = 2.0 * (double)p.c[1].w + (end ? 6.0 * (double)p.c[0].w : 0.0);
+        m_axis = std::max(m_axis, std::sqrt(ax * ax + ay * ay + az * az));
+        m_rad = std::max(m_rad, std::fabs(aw));
+    }
+    const double r0 = (double)p.c[3].w;
+    const double r1 = (double)p.c[0].w + (double)p.c[1].w + (double)p.c[2].w + (double)p.c[3].w;
+    const double rh = 0.125 * (double)p.c[0].w + 0.25 * (double)p.c[1].w + 0.5 * (double)p.c[2].w + (double)p.c[3].w;
+    const double rref = std::max(r0, std::max(r1, rh));
+    if (!(rref > 0.0)) return 1;   // nothing to see
+    const double need = std::max(m_axis, m_rad) / (8.0 * RT3_CURVE_TOL * rref);   // K^2 >= need
+    if (!(need <= (double)RT3_CURVE_MAX_SUBDIV * RT3_CURVE_MAX_SUBDIV)) return RT3_CURVE_MAX_SUBDIV;
+    const int K = (int)std::ceil(std::sqrt(need));
+    return K < 1 ? 1 : (K > RT3_CURVE_MAX_SUBDIV ? RT3_CURVE_MAX_SUBDIV : K);
+}
+static void tessellate_curves(int basis, const float* cp, const int32_t* seg, int nseg, Blas& b, std::vector<float>& out_cp, std::vector<int32_t>& out_seg) {
+    b.poly.resize((size_t)nseg);
+    b.sub_first.assign((size_t)nseg + 1, 0);
     for (int s = 0; s < nseg; s++) {
-        poly[(size_t)s] = curve_poly(basis, cp + 4 * (size_t)seg[s]);
+        b.poly[(size_t)s] = curve_poly(basis, cp + 4 * (size_t)seg[s]);
+        b.sub_first[(size_t)s + 1] = b.sub_first[(size_t)s] + curve_pieces(b.poly[(size_t)s]);
+    }
+    const size_t nsub = (size_t)b.sub_first[(size_t)nseg];
+    out_cp.resize(4 * (nsub + (size_t)nseg));
+    out_seg.resize(nsub);
+    b.sub_seg.resize(nsub);
+    for (int s = 0; s < nseg; s++) {
+        const int first = b.sub_first[(size_t)s], K = b.sub_first[(size_t)s + 1] - first;
         for (int k = 0; k <= K; k++) {
-            const f4 v = curve_position(poly[(size_t)s], (float)k / (float)K);
-            float* o = &out_cp[4 * ((size_t)s * (K + 1) + (size_t)k)];
+            const f4 v = curve_position(b.poly[(size_t)s], (float)k / (float)K);
+            float* o = &out_cp[4 * ((size_t)first + (size_t)s + (size_t)k)];   // K + 1 points per segment
             o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-            if (k < K) out_seg[(size_t)s * K + (size_t)k] = s * (K + 1) + k;
+            if (k < K) { out_seg[(size_t)first + (size_t)k] = first + s + k; b.sub_seg[(size_t)first + (size_t)k] = s; }
         }
     }
 }
-static inline void curve_hit_to_internal(int K, int32_t& prim, float& u) {
+static inline void curve_hit_to_internal(const Blas& b, int32_t& prim, float& u) {
+    const int first = b.sub_first[(size_t)prim], K = b.sub_first[(size_t)prim + 1] - first;
     const float f = u * (float)K;
     int k = (int)f;
     k = k > K - 1 ? K - 1 : (k < 0 ? 0 : k);
     u = f - (float)k;
-    prim = prim * K + k;
+    prim = first + k;
 }
 
-static inline void curve_hit_to_user(int K, int32_t& prim, float& u) {
-    const int k = prim % K;
-    prim = prim / K;
-    u = ((float)k + u) / (float)K;
+static inline void curve_hit_to_user(const Blas& b, int32_t& prim, float& u) {
+    const int s = b.sub_seg[(size_t)prim], first = b.sub_first[(size_t)s], K = b.sub_first[(size_t)s + 1] - first;
+    u = ((float)(prim - first) + u) / (float)K;
+    prim = s;
 }
 
 int rt3o_curves_create(rt3o_scene* s, int degree, const float* cp, int ncp, const int32_t* seg, int nseg) {
@@ -889,9 +924,8 @@ int rt3o_curves_create(rt3o_scene* s, int degree, const float* cp, int ncp, cons
     std::vector<float> tcp;
     std::vector<int32_t> tseg;
     if (degree > 1) {
-        tessellate_curves(degree, cp, seg, nseg, tcp, tseg, b->poly);
+        tessellate_curves(degree, cp, seg, nseg, *b, tcp, tseg);
         cp = tcp.data(); ncp = (int)(tcp.size() / 4); seg = tseg.data(); nseg = (int)tseg.size();
-        b->subdiv = RT3_CURVE_SUBDIV;
     }
     b->nprims = nseg;
     b->cr.assign(cp, cp + 4 * ncp);
@@ -987,8 +1021,8 @@ int rt3o_trace(rt3o_scene* s, const rt3_ray* rays, int n, int any_hit, rt3_hit* 
         std::memset(&o, 0, sizeof(o));
         o.t = h.t; o.u = h.u; o.v = h.v; o.prim = h.prim; o.inst = h.inst;
         if (h.prim >= 0) {
-            const int K = s->blas[s->inst[h.inst].blas]->subdiv;
-            if (K > 1) curve_hit_to_user(K, o.prim, o.u);
+            const Blas& b = *s->blas[s->inst[h.inst].blas];
+            if (b.spline()) curve_hit_to_user(b, o.prim, o.u);
         }
     });
     return 0;
@@ -1004,11 +1038,14 @@ int rt3o_get_local_geometry(rt3o_scene* s, const rt3_ray* rays, const rt3_hit* h
         float* o = reinterpret_cast<float*>(out + i);
         if (hits[i].prim < 0) { for (int k = 0; k < 27; k++) o[k] = 0.0f; continue; }
         Hit h; h.t = hits[i].t; h.u = hits[i].u; h.v = hits[i].v; h.prim = hits[i].prim; h.inst = hits[i].inst;
-        const int K = s->blas[s->inst[h.inst].blas]->subdiv;
-        if (K > 1) curve_hit_to_internal(K, h.prim, h.u);
+        const Blas& b = *s->blas[s->inst[h.inst].blas];
+        if (b.spline()) {
+            if (h.prim >= (int)b.poly.size()) { g_err = "get_local_geometry: hit record does not belong to this scene"; return -1; }
+            curve_hit_to_internal(b, h.prim, h.u);
+        }
         const rt3_ray& r = rays[i];
         s->local_geometry_full(h, {r.o[0], r.o[1], r.o[2]}, {r.d[0], r.d[1], r.d[2]}, r.time, o);
-        if (K > 1) o[9] = hits[i].u;  // UV.x is the u along the user's segment, not along the sub-segment
+        if (b.spline()) o[9] = hits[i].u;  // UV.x is the u along the user's segment, not along the sub-segment
     }
     return 0;
     RT3O_CATCH(-1)

@@ -26,7 +26,10 @@ namespace {
 
 struct Geometry {
     uint32_t type = PRIM_TRI, nprims = 0, vkeys = 1, nv = 0;
-    uint32_t subdiv = 1;  // curves of degree 2 / 3: linear sub-segments per user segment (hit records are translated at the API boundary)
+    std::vector<uint32_t> sub_first;   // spline curves: first linear sub-segment of every USER segment (+ end); hit records are translated at the API boundary
+    DevBuf<uint32_t> sub;              // spline curves: (user segment, k | K << 16) per sub-segment
+    bool spline() const { return !sub_first.empty(); }
+    uint32_t user_prims() const { return spline() ? (uint32_t)sub_first.size() - 1u : nprims; }
     DevBuf<float> verts, normals, uvs, colors;   // normals / uvs / colors stay empty when the caller has none (SDK fallbacks)
     DevBuf<int32_t> idx, seg;
     DevBuf<float4> cr, poly;   // poly: spline curves, 4 power-basis coefficients (float4: xyz + radius) per USER segment
@@ -85,7 +88,7 @@ struct rt3_context {
     int opt_l2_persist = 0;  // measured: -5 % on C2 (the carve-out starves the streaming queue traffic), off by default
     Bvh8 m_bvh;
     bool has_merged = false, single_level = false;
-    bool has_subdiv_curves = false;  // some instance refers to a degree-2 / -3 curve geometry (set in rt3_accel_build)
+    bool has_subdiv_curves = false;  // some instance refers to a spline curve geometry (set in rt3_accel_build)
     int opt_merge = 1;
     int opt_tlas_sah = 1;
     int opt_tlas_leaf = 1;      // instances per TLAS leaf child (r02j, C3 / C4 Mrays/s: 3 -> 762 / 957, 2 -> 785 / 927, 1 -> 815 / 953: an own box per instance culls more entries than the extra TLAS nodes cost)
@@ -505,13 +508,19 @@ int rt3_spheres_create(rt3_context_t c, const float* cr, int n, rt3_handle_t* bl
 }
 
 
-// Degree-2 / -3 round curves: each segment (uniform B-spline over control points [a, a + degree], the SDK's
-// Quadratic / CubicInterpolator::initializeFromBSpline + position4, cuda/curve.h:98-140,172-230) is realised as
-// RT3_CURVE_SUBDIV round linear sub-segments between the points P(k / RT3_CURVE_SUBDIV).  Inside the library the
-// sub-segments are ordinary linear-curve primitives; hit records are translated at the API boundary:
-// prim = sub / SUBDIV, u = (sub % SUBDIV + u_sub) / SUBDIV.
-#ifndef RT3_CURVE_SUBDIV
-#define RT3_CURVE_SUBDIV 8
+// Spline curves (quadratic / cubic B-spline, Catmull-Rom, Bezier through the SDK's interpolators, cuda/curve.h:98-243):
+// every user segment is intersected as K round linear sub-segments between the points P(k / K) of its true polynomial, and
+// shaded with the SDK's surfaceNormal<> of that polynomial (k_shade / k_local_geometry).  K adapts to the segment: a chord
+// over 1 / K of the parameter range leaves the curve by at most max|P''| / (8 K^2), and P'' is linear in u, so the maximum
+// sits at u = 0 or 1.  K is the smallest count that keeps this bound — for the axis and for the radius — below RT3_CURVE_TOL
+// times the segment's largest radius (taken at u = 0, 1/2, 1), clamped to [1, RT3_CURVE_MAX_SUBDIV].  Inside the library the
+// sub-segments are ordinary linear-curve primitives; hit records are translated at the API boundary (Geometry::sub_first on
+// the host, BlasDev::sub on the device): prim = user segment, u = (k + u_sub) / K.
+#ifndef RT3_CURVE_TOL
+#define RT3_CURVE_TOL 0.02
+#endif
+#ifndef RT3_CURVE_MAX_SUBDIV
+#define RT3_CURVE_MAX_SUBDIV 64
 #endif
 // Spline segments -> power-basis coefficients, table driven.  A row lists the terms (control point, factor) of one coefficient
 // in the order the SDK's interpolators add them (cuda/curve.h:43-47 linear, :102-110 quadratic B-spline, :176-186 cubic
@@ -545,28 +554,61 @@ static void curve_coefficients(int basis, const float* q, float coef[4][4]) {
             coef[j][c] = (r.n && t.div != 0.0f) ? v * inv : v;
         }
 }
-static void tessellate_curves(int basis, const float* cp, const int32_t* seg, int nseg, std::vector<float>& out_cp, std::vector<int32_t>& out_seg, std::vector<float>& out_coef) {
-    const int K = RT3_CURVE_SUBDIV;
-    out_cp.resize((size_t)4 * nseg * (K + 1));
-    out_seg.resize((size_t)nseg * K);
+static int curve_pieces(const float coef[4][4]) {
+    double bend = 0.0;   // max |P''| over the segment, axis and radius
+    for (int end = 0; end < 2; end++) {
+        double acc[4];
+        for (int c = 0; c < 4; c++) acc[c] = 2.0 * (double)coef[1][c] + (end ? 6.0 * (double)coef[0][c] : 0.0);
+        bend = std::max(bend, std::max(std::sqrt(acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2]), std::fabs(acc[3])));
+    }
+    const double r0 = (double)coef[3][3];
+    const double r1 = (double)coef[0][3] + (double)coef[1][3] + (double)coef[2][3] + (double)coef[3][3];
+    const double rh = 0.125 * (double)coef[0][3] + 0.25 * (double)coef[1][3] + 0.5 * (double)coef[2][3] + (double)coef[3][3];
+    const double rref = std::max(r0, std::max(r1, rh));
+    if (!(rref > 0.0)) return 1;
+    const double need = bend / (8.0 * RT3_CURVE_TOL * rref);   // K^2 >= need
+    if (!(need <= (double)RT3_CURVE_MAX_SUBDIV * RT3_CURVE_MAX_SUBDIV)) return RT3_CURVE_MAX_SUBDIV;
+    const int K = (int)std::ceil(std::sqrt(need));
+    return K < 1 ? 1 : (K > RT3_CURVE_MAX_SUBDIV ? RT3_CURVE_MAX_SUBDIV : K);
+}
+// out_sub: (user segment, k | K << 16) per sub-segment; sub_first: first sub-segment of every user segment (+ end)
+static void tessellate_curves(int basis, const float* cp, const int32_t* seg, int nseg, std::vector<float>& out_cp, std::vector<int32_t>& out_seg,
+                              std::vector<float>& out_coef, std::vector<uint32_t>& out_sub, std::vector<uint32_t>& sub_first) {
     out_coef.resize((size_t)16 * nseg);
+    sub_first.assign((size_t)nseg + 1, 0u);
     for (int s = 0; s < nseg; s++) {
         float coef[4][4];
         curve_coefficients(basis, cp + 4 * (size_t)seg[s], coef);
         memcpy(&out_coef[16 * (size_t)s], coef, sizeof(coef));
-        for (int k = 0; k <= K; k++) {
+        sub_first[(size_t)s + 1] = sub_first[(size_t)s] + (uint32_t)curve_pieces(coef);
+        RT3_REQUIRE(sub_first[(size_t)s + 1] < (1u << 27), RT3_ERR_INVALID, "curves_create: too many segments");
+    }
+    const size_t nsub = sub_first[(size_t)nseg];
+    out_cp.resize(4 * (nsub + (size_t)nseg));
+    out_seg.resize(nsub);
+    out_sub.resize(2 * nsub);
+    for (int s = 0; s < nseg; s++) {
+        const float* coef = &out_coef[16 * (size_t)s];
+        const uint32_t first = sub_first[(size_t)s], K = sub_first[(size_t)s + 1] - first;
+        for (uint32_t k = 0; k <= K; k++) {
             const float u = (float)k / (float)K;
-            for (int c = 0; c < 4; c++) out_cp[4 * ((size_t)s * (K + 1) + (size_t)k) + (size_t)c] = ((coef[0][c] * u + coef[1][c]) * u + coef[2][c]) * u + coef[3][c];   // Horner
-            if (k < K) out_seg[(size_t)s * K + (size_t)k] = s * (K + 1) + k;
+            for (int c = 0; c < 4; c++) out_cp[4 * ((size_t)first + (size_t)s + k) + (size_t)c] = ((coef[c] * u + coef[4 + c]) * u + coef[8 + c]) * u + coef[12 + c];   // Horner
+            if (k < K) {
+                out_seg[(size_t)first + k] = (int32_t)(first + (uint32_t)s + k);   // K + 1 points per segment
+                out_sub[2 * ((size_t)first + k)] = (uint32_t)s;
+                out_sub[2 * ((size_t)first + k) + 1] = k | (K << 16);
+            }
         }
     }
 }
-static inline void curve_hit_to_internal(int K, int32_t& prim, float& u) {
+static inline void curve_hit_to_internal(const std::vector<uint32_t>& sub_first, int32_t& prim, float& u) {
+    const uint32_t first = sub_first[(size_t)prim];
+    const int K = (int)(sub_first[(size_t)prim + 1] - first);
     const float f = u * (float)K;
     int k = (int)f;
     k = k > K - 1 ? K - 1 : (k < 0 ? 0 : k);
     u = f - (float)k;
-    prim = prim * K + k;
+    prim = (int32_t)first + k;
 }
 
 int rt3_curves_create(rt3_context_t c, int degree, const float* cp, int ncp, const int32_t* seg, int nseg, rt3_handle_t* blas) {
@@ -580,11 +622,12 @@ int rt3_curves_create(rt3_context_t c, int degree, const float* cp, int ncp, con
     g->type = PRIM_CURVE;
     std::vector<float> tcp, coef;
     std::vector<int32_t> tseg;
+    std::vector<uint32_t> sub;
     if (degree > RT3_CURVE_LINEAR) {
-        RT3_REQUIRE((uint64_t)nseg * RT3_CURVE_SUBDIV < (1u << 27), RT3_ERR_INVALID, "curves_create: too many segments");
-        tessellate_curves(degree, cp, seg, nseg, tcp, tseg, coef);
+        tessellate_curves(degree, cp, seg, nseg, tcp, tseg, coef, sub, g->sub_first);
         cp = tcp.data(); ncp = (int)(tcp.size() / 4); seg = tseg.data(); nseg = (int)tseg.size();
-        g->subdiv = RT3_CURVE_SUBDIV;
+        g->sub.alloc(sub.size());
+        h2d(g->sub.p, sub.data(), g->sub.bytes(), c->stream);
         g->curve_cubic = degree >= RT3_CURVE_CUBIC_BSPLINE ? 1u : 0u;
         g->poly.alloc(coef.size() / 4);   // the true curve of every user segment: normals are taken from it (cuda/curve.h:311-379)
         h2d(g->poly.p, coef.data(), g->poly.bytes(), c->stream);
@@ -730,7 +773,7 @@ int rt3_accel_build(rt3_context_t c) {
     std::vector<BlasBounds> bb(ng + 1);
     for (size_t i = 0; i < ng; i++) {
         const Geometry& g = *c->geoms[i];
-        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p, g.vkeys, g.verts.p, g.nv, g.subdiv, g.colors.p, g.poly.p, g.curve_cubic};
+        bt[i] = BlasDev{g.nodes.p, g.prims.p, g.type, g.nprims, g.idx.p, g.normals.p, g.uvs.p, g.cr.p, g.seg.p, g.vkeys, g.verts.p, g.nv, g.sub.p, g.colors.p, g.poly.p, g.curve_cubic};
         for (int k = 0; k < 3; k++) { bb[i].lo[k] = g.bvh.lo[k]; bb[i].hi[k] = g.bvh.hi[k]; }
     }
     bt[ng] = BlasDev{c->m_nodes_p, c->m_prims_p, PRIM_TRI, c->m_bvh.num_prims, nullptr, nullptr, nullptr, nullptr, nullptr, 1u, nullptr};
@@ -822,7 +865,7 @@ int rt3_accel_build(rt3_context_t c) {
     c->hitgroups_dirty = true;
     upload_hitgroups(c);
     c->has_subdiv_curves = false;
-    for (const InstanceHost& in : c->inst) c->has_subdiv_curves = c->has_subdiv_curves || c->geoms[in.blas]->subdiv > 1;
+    for (const InstanceHost& in : c->inst) c->has_subdiv_curves = c->has_subdiv_curves || c->geoms[in.blas]->spline();
     c->built = true;
     RT3_API_END
 }
@@ -1090,7 +1133,7 @@ int rt3_trace_device(rt3_context_t c, const void* d_rays, int n, int any_hit, vo
     a.hit0 = (float4*)d_hits; a.hit_inst = nullptr; a.contrib = nullptr; a.result = nullptr; a.stat = nullptr; a.faithful = 0;
     if (any_hit) launch_traverse<TRAV_TRACE_ANY>(c, a, c->stream);
     else launch_traverse<TRAV_TRACE_CLOSEST>(c, a, c->stream);
-    // degree-2 / -3 curves: internal sub-segment hits -> (segment, u along the segment)
+    // spline curves: internal sub-segment hits -> (segment, u along the segment)
     if (c->has_subdiv_curves) RT3_LAUNCH_1D(k_curve_hits_to_user, (uint32_t)n, c->stream, a.scene, (float4*)d_hits);
     RT3_API_END
 }
@@ -1120,18 +1163,18 @@ int rt3_get_local_geometry(rt3_context_t c, const rt3_ray* rays, const rt3_hit* 
     RT3_REQUIRE(n >= 0 && (n == 0 || (rays && hits && out)), RT3_ERR_INVALID, "get_local_geometry: bad argument");
     for (int i = 0; i < n; i++)
         RT3_REQUIRE(hits[i].prim < 0 || (hits[i].inst >= 0 && (size_t)hits[i].inst < c->inst.size() &&
-                                        (uint32_t)hits[i].prim < c->geoms[c->inst[(size_t)hits[i].inst].blas]->nprims / c->geoms[c->inst[(size_t)hits[i].inst].blas]->subdiv),
+                                        (uint32_t)hits[i].prim < c->geoms[c->inst[(size_t)hits[i].inst].blas]->user_prims()),
                     RT3_ERR_INVALID, "get_local_geometry: hit record does not belong to this scene");
     if (n == 0) return RT3_OK;
     upload_hitgroups(c);
     std::vector<rt3_hit> internal;
     const rt3_hit* user_hits = hits;
-    if (c->has_subdiv_curves) {  // (segment, u) of a degree-2 / -3 curve -> its linear sub-segment
+    if (c->has_subdiv_curves) {  // (segment, u) of a spline curve -> its linear sub-segment
         internal.assign(hits, hits + n);
         for (int i = 0; i < n; i++)
             if (internal[(size_t)i].prim >= 0) {
-                const uint32_t K = c->geoms[c->inst[(size_t)internal[(size_t)i].inst].blas]->subdiv;
-                if (K > 1) curve_hit_to_internal((int)K, internal[(size_t)i].prim, internal[(size_t)i].u);
+                const Geometry& g = *c->geoms[c->inst[(size_t)internal[(size_t)i].inst].blas];
+                if (g.spline()) curve_hit_to_internal(g.sub_first, internal[(size_t)i].prim, internal[(size_t)i].u);
             }
         hits = internal.data();
     }
@@ -1144,7 +1187,7 @@ int rt3_get_local_geometry(rt3_context_t c, const rt3_ray* rays, const rt3_hit* 
     stream_sync(c->stream);
     if (c->has_subdiv_curves)  // UV.x is the u along the user's segment, not along the sub-segment
         for (int i = 0; i < n; i++)
-            if (user_hits[i].prim >= 0 && c->geoms[c->inst[(size_t)user_hits[i].inst].blas]->subdiv > 1) out[i].UV[0] = user_hits[i].u;
+            if (user_hits[i].prim >= 0 && c->geoms[c->inst[(size_t)user_hits[i].inst].blas]->spline()) out[i].UV[0] = user_hits[i].u;
     RT3_API_END
 }
 

@@ -75,7 +75,7 @@ struct BlasDev {             // per geometry, device-resident table entry
     uint32_t vkeys;          // PRIM_TRI_MOTION: vertex keys per triangle record (record = vkeys x 3 float4)
     const float* verts;      // mesh [vkeys][nv][3] (corrected mode: area of BSDF-sampled emitter hits; rt3_get_local_geometry)
     uint32_t nv;             // vertices per key
-    uint32_t subdiv;         // curves of degree 2 / 3: linear sub-segments per user segment (1 otherwise)
+    const uint32_t* sub;     // spline curves: (user segment, k | K << 16) of every linear sub-segment; null otherwise
     const float* colors;     // mesh, optional [nv][4] vertex colours (cuda/LocalGeometry.h:99-110); normals / uvs may be null too (SDK fallbacks)
     const float4* poly;      // spline curves: power-basis coefficients c0 u^3 + c1 u^2 + c2 u + c3 of every USER segment (xyz + radius)
     uint32_t curve_cubic;    // spline curves: 1 = cubic interpolator

@@ -555,10 +555,10 @@ RT3_HD LocalGeometry local_geometry(const TravScene& sc, const HitRec& h, float3
             const float4 s = b->cr[h.prim];
             n_obj = divs(sub(ps, v3(s)), s.w);
             lg.UV = make_float2(0.0f, 0.0f);
-        } else if (b->subdiv > 1u) {  // spline curves: the SDK's surfaceNormal<> of the TRUE curve at the hit's parameter (cuda/curve.h:311-379)
-            const uint32_t K = b->subdiv, k = (uint32_t)h.prim % K;
-            const float uu = ((float)k + h.u) / (float)K;   // the hit was found on linear sub-segment k of its segment
-            n_obj = spline_surface_normal(b->poly + 4 * (size_t)((uint32_t)h.prim / K), b->curve_cubic != 0u, uu, ps);
+        } else if (b->sub) {  // spline curves: the SDK's surfaceNormal<> of the TRUE curve at the hit's parameter (cuda/curve.h:311-379)
+            const uint32_t sg = b->sub[2 * (size_t)h.prim], kK = b->sub[2 * (size_t)h.prim + 1];
+            const float uu = ((float)(kK & 0xffffu) + h.u) / (float)(kK >> 16);   // the hit was found on linear sub-segment k of K of its segment
+            n_obj = spline_surface_normal(b->poly + 4 * (size_t)sg, b->curve_cubic != 0u, uu, ps);
             lg.UV = make_float2(uu, 0.0f);
         } else {  // cuda/curve.h:382-425 surfaceNormal<LinearInterpolator>
             const float4 c0 = b->cr[b->seg[h.prim]], c1 = b->cr[b->seg[h.prim] + 1];
@@ -682,8 +682,8 @@ RT3_GLOBAL(k_local_geometry, TravScene sc, const float4* rays, const float4* hit
     r[23] = g.color.x; r[24] = g.color.y; r[25] = g.color.z; r[26] = g.color.w;
 }
 
-// rt3_trace output for degree-2 / -3 curves: the traversal reports linear sub-segments; the caller sees
-// prim = segment, u = (sub-segment + u_sub) / subdiv
+// rt3_trace output for spline curves: the traversal reports linear sub-segments; the caller sees
+// prim = segment, u = (k + u_sub) / K for sub-segment k of the segment's K
 RT3_GLOBAL(k_curve_hits_to_user, TravScene sc, float4* hits) {
     const uint32_t i = RT3_THREAD_ID();
     if (i >= rt3_n_) return;
@@ -691,11 +691,11 @@ RT3_GLOBAL(k_curve_hits_to_user, TravScene sc, float4* hits) {
     const int prim = (int)rt3_f2u(h0.w);
     if (prim < 0) return;
     const int inst = (int)rt3_f2u(hits[2 * (size_t)i + 1].x);
-    const int K = (int)sc.blas[sc.instances[inst].blas].subdiv;
-    if (K <= 1) return;
-    const int k = prim % K;
-    h0.y = ((float)k + h0.y) / (float)K;
-    h0.w = rt3_u2f((uint32_t)(prim / K));
+    const uint32_t* sub = sc.blas[sc.instances[inst].blas].sub;
+    if (!sub) return;
+    const uint32_t kK = sub[2 * (size_t)prim + 1];
+    h0.y = ((float)(kK & 0xffffu) + h0.y) / (float)(kK >> 16);
+    h0.w = rt3_u2f(sub[2 * (size_t)prim]);
     hits[2 * (size_t)i] = h0;
 }
 

@@ -120,3 +120,58 @@ def check_golden(backend, name):
     assert hashlib.sha256(backend.download_accum().tobytes()).hexdigest() == gold["accum_sha256"]
     st = backend.stats()
     assert [st[k] for k in ("rays_primary", "rays_bounce", "rays_shadow")] == gold["rays"]
+
+
+def check_spline_tessellation(backend):
+    """Spline segments are intersected as K linear pieces, K chosen per segment so that the pieces stay within
+    RT3_CURVE_TOL (2 %) of the segment's radius of the true curve.  Property checked here, with the true Bezier curve
+    evaluated in float64: every hit point lies within 5 % of the radius of the true swept surface (chord deviation + radius
+    interpolation), on a hairpin that a fixed 8-piece split misses by more than that; and a straight spline segment
+    returns the hits of the linear curve with the same end points."""
+    from rendertoy3c_b200.scenes import Geometry, Instance, SceneDesc, Camera, replay
+    hairpin = np.array([[-1, 0, 0, 0.02], [-0.2, 2.6, 0, 0.03], [0.2, 2.6, 0, 0.03], [1, 0, 0, 0.02]], np.float32)
+    straight = np.array([[-1, -1, 0, 0.05], [-1 / 3, -1, 0, 0.05], [1 / 3, -1, 0, 0.05], [1, -1, 0, 0.05]], np.float32)
+    linear = np.array([[-1, -2, 0, 0.05], [1, -2, 0, 0.05]], np.float32)
+    geoms = [Geometry("curves", cr=hairpin, seg=np.array([0], np.int32), degree=5),
+             Geometry("curves", cr=straight, seg=np.array([0], np.int32), degree=5),
+             Geometry("curves", cr=linear, seg=np.array([0], np.int32), degree=1)]
+    desc = SceneDesc("spline_tess", geoms, [Instance(0), Instance(1), Instance(2)], [], Camera(eye=(0, 0, 5), lookat=(0, 0, 0), fovy=45.0), 8, 8, 1, 1)
+    replay(desc, backend)
+    # orthographic rays along -z over the hairpin
+    n = 160
+    xs, ys = np.meshgrid(np.linspace(-1.1, 1.1, n, dtype=np.float32), np.linspace(-0.1, 2.1, n, dtype=np.float32))
+    rays = np.zeros(n * n, dtype=RAY_DTYPE)
+    rays["o"] = np.stack([xs.ravel(), ys.ravel(), np.full(n * n, 3, np.float32)], axis=1)
+    rays["d"] = (0, 0, -1)
+    rays["tmin"], rays["tmax"] = 0.0, 1e16
+    h = backend.trace(rays)
+    sel = (h["prim"] >= 0) & (h["inst"] == 0) & (h["u"] > 0.01) & (h["u"] < 0.99)   # away from the (round) end caps
+    assert sel.sum() > 300
+    P = rays["o"][sel].astype(np.float64) + h["t"][sel, None].astype(np.float64) * rays["d"][sel].astype(np.float64)
+    u = np.linspace(0, 1, 4001)[:, None]
+    q = hairpin.astype(np.float64)
+    c = (1 - u) ** 3 * q[0] + 3 * u * (1 - u) ** 2 * q[1] + 3 * u * u * (1 - u) * q[2] + u ** 3 * q[3]      # [4001, 4]
+    err = np.empty(len(P))
+    for i in range(0, len(P), 256):
+        d = np.linalg.norm(P[i:i + 256, None, :] - c[None, :, :3], axis=2)                                   # [m, 4001]
+        err[i:i + 256] = np.abs(d - c[None, :, 3]).min(axis=1)
+    assert err.max() <= 0.05 * 0.03, "hit points leave the true curve's surface by %.3g radii" % (err.max() / 0.03)
+    # eight uniform pieces of this hairpin: chord deviation max|P''| / (8 * 64) — far outside the tolerance
+    bend = max(np.linalg.norm(6 * (q[2] - 2 * q[1] + q[0])[:3]), np.linalg.norm(6 * (q[3] - 2 * q[2] + q[1])[:3]))
+    assert bend / (8 * 64) > 0.05 * 0.03
+    # straight segment: one piece, same hits as the linear curve one unit below
+    ys2 = np.linspace(-1.06, -0.94, 64, dtype=np.float32)
+    xs2 = np.linspace(-1.02, 1.02, 64, dtype=np.float32)
+    gx, gy = np.meshgrid(xs2, ys2)
+    r2 = np.zeros(gx.size * 2, dtype=RAY_DTYPE)
+    r2["o"][:gx.size] = np.stack([gx.ravel(), gy.ravel(), np.full(gx.size, 3, np.float32)], axis=1)
+    r2["o"][gx.size:] = r2["o"][:gx.size] - np.array([0, 1, 0], np.float32)
+    r2["d"] = (0, 0, -1)
+    r2["tmin"], r2["tmax"] = 0.0, 1e16
+    h2 = backend.trace(r2)
+    a, b = h2[:gx.size], h2[gx.size:]
+    assert np.array_equal(a["prim"] >= 0, b["prim"] >= 0) and (a["prim"] >= 0).sum() > 100
+    hit = a["prim"] >= 0
+    assert np.all(a["inst"][hit] == 1) and np.all(b["inst"][hit] == 2)
+    np.testing.assert_allclose(a["t"][hit], b["t"][hit], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(a["u"][hit], b["u"][hit], rtol=0, atol=1e-5)

@@ -135,3 +135,10 @@ def test_stack_overflow_is_reported(tmp_path):
         assert e.stats()["error_flags"] & 1
         e.reset_stats()
         assert e.stats()["error_flags"] == 0
+
+
+def test_spline_tessellation_tolerance(emul_lib):
+    """adaptive split of spline segments: hits stay within the stated tolerance of the true curve (parity_common)"""
+    from parity_common import check_spline_tessellation
+    with Context(0, lib_path=emul_lib) as e:
+        check_spline_tessellation(e)

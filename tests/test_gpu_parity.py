@@ -169,3 +169,10 @@ def test_corrected_mode_with_emitters_nee_cannot_reach(product_lib, mode):
     with Context(0) as e:
         o = build_pair(desc, e)
         check_render(e, o, desc, subframes=2, mode=mode)
+
+
+def test_spline_tessellation_tolerance(product_lib):
+    """adaptive split of spline segments: hits stay within the stated tolerance of the true curve (parity_common)"""
+    from parity_common import check_spline_tessellation
+    with Context(0) as e:
+        check_spline_tessellation(e)

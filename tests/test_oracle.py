@@ -409,3 +409,9 @@ def test_bspline_curves_analytic():
     lg = o.get_local_geometry(rays, h)
     assert np.allclose(lg["N"][:3], [0, 1, 0], atol=1e-5) and np.allclose(lg["UV"][:3, 0], [0.5, 0.25, 0.25], atol=1e-5)
     assert np.allclose(lg["P"][:3, 1], [0.1, 0.1, 10.1], atol=1e-5)
+
+
+def test_spline_tessellation_tolerance():
+    """the oracle's adaptive split of spline segments keeps hits within the stated tolerance of the true curve"""
+    from parity_common import check_spline_tessellation
+    check_spline_tessellation(ob.OracleScene())
