@@ -7,6 +7,7 @@
 //   * PPM / PGM — binary P6 / P5, 8 or 16 bits per sample
 //   * JPEG — baseline, extended-sequential and progressive (Huffman, 8 bit); grey, YCbCr, RGB, CMYK / YCCK; integer
 //            sampling ratios; restart intervals; decoded with stb_image's arithmetic so that the bytes are the reference's
+//   * GIF (first image), Photoshop PSD (flattened RGB composite), Softimage PIC, Radiance HDR (tone-mapped to 8 bits as stbi_load does)
 // Arithmetic-coded / lossless JPEG are not supported (load_image returns false and says why), as in stb_image.
 #pragma once
 #include <cctype>
@@ -39,6 +40,7 @@ inline bool read_file(const std::string& path, std::vector<uint8_t>& out) {
 inline void store_flipped(const std::vector<uint8_t>& top, int w, int h, Texture& t) {
     t.width = w; t.height = h;
     t.pixel.resize((size_t)4 * w * h);
+    if (t.pixel.empty()) return;
     for (int y = 0; y < h; ++y) std::memcpy(&t.pixel[(size_t)4 * w * y], &top[(size_t)4 * w * (h - 1 - y)], (size_t)4 * w);
 }
 
@@ -517,6 +519,348 @@ inline bool load_pnm(const std::vector<uint8_t>& f, Texture& t, std::string& why
         d[0] = s[0]; d[1] = s[chan == 3 ? bytes : 0]; d[2] = s[chan == 3 ? 2 * bytes : 0]; d[3] = 255;
     }
     store_flipped(top, (int)w, (int)h, t);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------ GIF / PSD / PIC / Radiance HDR
+// The remaining formats stbi_load accepts (support/stb/stb_image.h v2.29), restated with its lenient reading rules so that
+// the same files — damaged ones included — give the same RGBA bytes: a read past the end of the file yields zero bytes.
+struct ByteCursor {
+    const uint8_t* p; size_t n, pos = 0;
+    explicit ByteCursor(const std::vector<uint8_t>& f) : p(f.data()), n(f.size()) {}
+    bool eof() const { return pos >= n; }
+    int u8() { return pos < n ? p[pos++] : 0; }
+    int u16le() { const int a = u8(); return a | (u8() << 8); }
+    int u16be() { const int a = u8(); return (a << 8) | u8(); }
+    uint32_t u32be() { const uint32_t a = (uint32_t)u16be(); return (a << 16) | (uint32_t)u16be(); }
+    void skip(long k) { pos = (k < 0 || (size_t)k > n - (pos < n ? pos : n)) ? n : pos + (size_t)k; }
+};
+// stb lets these four formats declare a width or height of zero (a texture without texels, refused later at upload)
+inline bool image_size_ok(long w, long h) { return w >= 0 && h >= 0 && w <= (1 << 24) && h <= (1 << 24) && (uint64_t)w * (uint64_t)h <= (1ull << 28); }
+
+// GIF87a / GIF89a, first image only (stb_image.h:6575-6947).  stb's choices, all visible in the texture: pixels of the
+// transparent index are not drawn (they stay 0,0,0,0); codes beyond the colour table are transparent; when the background
+// index is non-zero the pixels the first image does not cover get the background entry WITH RED AND BLUE EXCHANGED (stb
+// keeps its palettes as B,G,R,A and copies that entry unconverted, :6895-6903); interlaced rows in the 8/8/4/2 order; a
+// raster must start with a clear code; a data stream that ends early keeps what was drawn.
+inline bool load_gif(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
+    ByteCursor s(f);
+    if (s.u8() != 'G' || s.u8() != 'I' || s.u8() != 'F' || s.u8() != '8') return false;
+    const int version = s.u8();
+    if ((version != '7' && version != '9') || s.u8() != 'a') return false;
+    const int W = s.u16le(), H = s.u16le(), flags = s.u8(), bgindex = s.u8();
+    s.u8();   // aspect ratio
+    if (!image_size_ok(W, H)) { why = "bad GIF size"; return false; }
+    struct Rgba { uint8_t r, g, b, a; };
+    std::vector<Rgba> global(256, Rgba{0, 0, 0, 0}), local(256, Rgba{0, 0, 0, 0});
+    auto read_table = [&](std::vector<Rgba>& pal, int entries, int transparent) {
+        for (int i = 0; i < entries; ++i) {
+            pal[(size_t)i].r = (uint8_t)s.u8(); pal[(size_t)i].g = (uint8_t)s.u8(); pal[(size_t)i].b = (uint8_t)s.u8();
+            pal[(size_t)i].a = transparent == i ? 0 : 255;
+        }
+    };
+    if (flags & 0x80) read_table(global, 2 << (flags & 7), -1);
+    std::vector<uint8_t> top((size_t)4 * W * H, 0), drawn((size_t)W * H, 0);
+    int eflags = 0, transparent = -1;
+    for (;;) {
+        const int tag = s.u8();
+        if (tag == 0x21) {   // extension; only the graphic control block matters (transparent index)
+            const int ext = s.u8();
+            if (ext == 0xF9) {
+                const int len = s.u8();
+                if (len != 4) { s.skip(len); continue; }   // stb goes back to the tag loop here, without walking the sub-blocks
+                eflags = s.u8();
+                s.u16le();   // delay
+                if (transparent >= 0) global[(size_t)transparent].a = 255;
+                if (eflags & 1) { transparent = s.u8(); global[(size_t)transparent].a = 0; }
+                else { s.skip(1); transparent = -1; }
+            }
+            for (int len; (len = s.u8()) != 0;) s.skip(len);
+            continue;
+        }
+        if (tag != 0x2C) { why = tag == 0x3B ? "GIF without an image" : "corrupt GIF"; return false; }
+        break;
+    }
+    const int x0 = s.u16le(), y0 = s.u16le(), w = s.u16le(), h = s.u16le();
+    if (x0 + w > W || y0 + h > H) { why = "bad GIF image descriptor"; return false; }
+    const int lflags = s.u8();
+    // byte offsets into `top`, the way stb walks them
+    const long line = 4L * W, start_x = 4L * x0, start_y = (long)y0 * line, max_x = start_x + 4L * w, max_y = start_y + (long)h * line;
+    long cur_x = start_x, cur_y = w == 0 ? max_y : start_y, step = (lflags & 0x40) ? 8 * line : line;
+    int pass = (lflags & 0x40) ? 3 : 0;
+    const std::vector<Rgba>* table;
+    if (lflags & 0x80) { read_table(local, 2 << (lflags & 7), (eflags & 1) ? transparent : -1); table = &local; }
+    else if (flags & 0x80) table = &global;
+    else { why = "GIF without a colour table"; return false; }
+    auto put = [&](int index) {
+        if (cur_y >= max_y) return;
+        const size_t at = (size_t)(cur_x + cur_y);
+        drawn[at / 4] = 1;
+        const Rgba c = (*table)[(size_t)index];
+        if (c.a > 128) { top[at] = c.r; top[at + 1] = c.g; top[at + 2] = c.b; top[at + 3] = c.a; }
+        cur_x += 4;
+        if (cur_x >= max_x) {
+            cur_x = start_x;
+            cur_y += step;
+            while (cur_y >= max_y && pass > 0) { step = (1L << pass) * line; cur_y = start_y + (step >> 1); --pass; }
+        }
+    };
+    // LZW (variable code width, LSB first, data in sub-blocks)
+    const int min_bits = s.u8();
+    if (min_bits > 12) { why = "corrupt GIF"; return false; }
+    struct Code { int16_t prefix; uint8_t first, suffix; };
+    std::vector<Code> codes(8192);
+    const int clear = 1 << min_bits;
+    for (int i = 0; i < clear; ++i) codes[(size_t)i] = Code{-1, (uint8_t)i, (uint8_t)i};
+    int width = min_bits + 1, mask = (1 << width) - 1, avail = clear + 2, old = -1, have = 0, block = 0;
+    int32_t acc = 0;
+    bool seen_clear = false;
+    std::vector<uint8_t> chain;
+    for (;;) {
+        if (have < width) {
+            if (block == 0) { block = s.u8(); if (block == 0) break; }   // also where a truncated file ends
+            --block;
+            acc |= (int32_t)((uint32_t)s.u8() << have);
+            have += 8;
+            continue;
+        }
+        const int code = acc & mask;
+        acc >>= width; have -= width;
+        if (code == clear) { width = min_bits + 1; mask = (1 << width) - 1; avail = clear + 2; old = -1; seen_clear = true; continue; }
+        if (code == clear + 1) break;   // end of information (the trailing sub-blocks are of no interest here)
+        if (code > avail) { why = "corrupt GIF (illegal code)"; return false; }
+        if (!seen_clear) { why = "corrupt GIF (no clear code)"; return false; }
+        if (old >= 0) {
+            if (avail + 1 > 8192) { why = "corrupt GIF (too many codes)"; return false; }
+            Code& c = codes[(size_t)avail++];
+            c.prefix = (int16_t)old;
+            c.first = codes[(size_t)old].first;
+            c.suffix = code == avail ? c.first : codes[(size_t)code].first;
+        } else if (code == avail) { why = "corrupt GIF (illegal code)"; return false; }
+        chain.clear();
+        for (int k = code; k >= 0; k = codes[(size_t)k].prefix) chain.push_back(codes[(size_t)k].suffix);
+        for (size_t k = chain.size(); k-- > 0;) put(chain[k]);
+        if ((avail & mask) == 0 && avail <= 0x0FFF) { ++width; mask = (1 << width) - 1; }
+        old = code;
+    }
+    if (bgindex > 0) {
+        const Rgba bg = global[(size_t)bgindex];
+        for (size_t i = 0; i < drawn.size(); ++i)
+            if (!drawn[i]) { top[4 * i] = bg.b; top[4 * i + 1] = bg.g; top[4 * i + 2] = bg.r; top[4 * i + 3] = 255; }
+    }
+    store_flipped(top, W, H, t);
+    return true;
+}
+
+// Photoshop PSD, the flattened composite only (stb_image.h:6078-6326): version 1, RGB colour mode, 8 or 16 bits per
+// channel (the high byte is kept), raw or PackBits rows, channel planes R, G, B, A in that order (missing ones: 0, alpha
+// 255, extra ones ignored).  With four or more channels stb "removes the white matte": for 0 < a < 255 every colour byte
+// becomes c / a' + 255 (1 - 1 / a'), a' = a / 255, in float, truncated and reduced modulo 256.
+inline bool load_psd(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
+    ByteCursor s(f);
+    if (s.u32be() != 0x38425053u) return false;
+    if (s.u16be() != 1) { why = "unsupported PSD version"; return false; }
+    s.skip(6);
+    const int channels = s.u16be();
+    if (channels > 16) { why = "unsupported number of PSD channels"; return false; }
+    const uint32_t H = s.u32be(), W = s.u32be();
+    if (H > (1u << 24) || W > (1u << 24) || !image_size_ok((long)W, (long)H)) { why = "bad PSD size"; return false; }
+    const int depth = s.u16be();
+    if (depth != 8 && depth != 16) { why = "PSD bit depth is not 8 or 16"; return false; }
+    if (s.u16be() != 3) { why = "PSD is not in RGB colour mode"; return false; }
+    for (int k = 0; k < 3; ++k) s.skip((long)(int32_t)s.u32be());   // mode data, image resources, layer and mask information
+    const int compression = s.u16be();
+    if (compression > 1) { why = "unknown PSD compression"; return false; }
+    const size_t count = (size_t)W * H;
+    std::vector<uint8_t> top(4 * count);
+    if (compression) s.skip((long)H * channels * 2);   // byte counts of the packed rows
+    for (int ch = 0; ch < 4; ++ch) {
+        uint8_t* d = top.data() + ch;
+        if (ch >= channels) { for (size_t i = 0; i < count; ++i) d[4 * i] = ch == 3 ? 255 : 0; continue; }
+        if (!compression) {
+            for (size_t i = 0; i < count; ++i) d[4 * i] = (uint8_t)(depth == 16 ? s.u16be() >> 8 : s.u8());
+            continue;
+        }
+        // PackBits over the whole plane, bytes whatever the depth says (stb decodes packed 16-bit files this way too)
+        for (size_t done = 0; done < count;) {
+            int len = s.u8();
+            if (len == 128) continue;
+            const bool run = len > 128;
+            len = run ? 257 - len : len + 1;
+            if ((size_t)len > count - done) { why = "bad PSD RLE data"; return false; }
+            const int v = run ? s.u8() : 0;
+            for (int k = 0; k < len; ++k) d[4 * (done + (size_t)k)] = (uint8_t)(run ? v : s.u8());
+            done += (size_t)len;
+        }
+    }
+    if (channels >= 4)
+        for (size_t i = 0; i < count; ++i) {
+            uint8_t* px = &top[4 * i];
+            if (px[3] == 0 || px[3] == 255) continue;
+            const float a = px[3] / 255.0f, ra = 1.0f / a, inv_a = 255.0f * (1 - ra);
+            for (int c = 0; c < 3; ++c) px[c] = (uint8_t)(int32_t)(px[c] * ra + inv_a);
+        }
+    store_flipped(top, (int)W, (int)H, t);
+    return true;
+}
+
+// Softimage PIC (stb_image.h:6333-6536): up to ten 8-bit channel packets, each raw, run-length or mixed run-length coded,
+// applied row by row to a picture preset to 255.
+inline bool pic_plausible(const std::vector<uint8_t>& f) {
+    return f.size() >= 92 && f[0] == 0x53 && f[1] == 0x80 && f[2] == 0xF6 && f[3] == 0x34 && std::memcmp(&f[88], "PICT", 4) == 0;
+}
+inline bool load_pic(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
+    ByteCursor s(f);
+    s.skip(92);
+    const int W = s.u16be(), H = s.u16be();
+    if (s.eof() || !image_size_ok(W, H)) { why = "bad PIC header"; return false; }
+    s.skip(8);   // ratio, fields, pad
+    struct Packet { int type, channels; };
+    std::vector<Packet> packets;
+    for (int chained = 1; chained;) {
+        if (packets.size() == 10) { why = "PIC: too many packets"; return false; }
+        chained = s.u8();
+        const int size = s.u8();
+        Packet pk;
+        pk.type = s.u8(); pk.channels = s.u8();
+        packets.push_back(pk);
+        if (s.eof()) { why = "PIC file too short"; return false; }
+        if (size != 8) { why = "PIC packet is not 8 bits per channel"; return false; }
+    }
+    std::vector<uint8_t> top((size_t)4 * W * H, 255);
+    bool short_file = false;
+    auto read_value = [&](int channels, uint8_t* d) {   // 0x80 red, 0x40 green, 0x20 blue, 0x10 alpha
+        for (int i = 0; i < 4; ++i)
+            if (channels & (0x80 >> i)) {
+                if (s.eof()) { short_file = true; return; }
+                d[i] = (uint8_t)s.u8();
+            }
+    };
+    auto copy_value = [](int channels, uint8_t* d, const uint8_t* v) {
+        for (int i = 0; i < 4; ++i) if (channels & (0x80 >> i)) d[i] = v[i];
+    };
+    for (int y = 0; y < H; ++y)
+        for (const Packet& pk : packets) {
+            uint8_t* d = &top[(size_t)4 * W * y];
+            if (pk.type == 0) {
+                for (int x = 0; x < W && !short_file; ++x, d += 4) read_value(pk.channels, d);
+            } else if (pk.type == 1) {   // runs only; a run that overshoots the row is cut
+                for (int left = W; left > 0 && !short_file;) {
+                    int count = s.u8();
+                    if (s.eof()) { short_file = true; break; }
+                    if (count > left) count = (uint8_t)left;
+                    uint8_t v[4] = {0, 0, 0, 0};
+                    read_value(pk.channels, v);
+                    if (short_file) break;
+                    for (int i = 0; i < count; ++i, d += 4) copy_value(pk.channels, d, v);
+                    left -= count;
+                }
+            } else if (pk.type == 2) {   // runs and literal stretches
+                for (int left = W; left > 0 && !short_file;) {
+                    int count = s.u8();
+                    if (s.eof()) { short_file = true; break; }
+                    if (count >= 128) {
+                        count = count == 128 ? s.u16be() : count - 127;
+                        if (count > left) { why = "PIC scanline overrun"; return false; }
+                        uint8_t v[4] = {0, 0, 0, 0};
+                        read_value(pk.channels, v);
+                        if (short_file) break;
+                        for (int i = 0; i < count; ++i, d += 4) copy_value(pk.channels, d, v);
+                    } else {
+                        ++count;
+                        if (count > left) { why = "PIC scanline overrun"; return false; }
+                        for (int i = 0; i < count && !short_file; ++i, d += 4) read_value(pk.channels, d);
+                    }
+                    left -= count;
+                }
+            } else { why = "PIC packet has a bad compression type"; return false; }
+            if (short_file) { why = "PIC file too short"; return false; }
+        }
+    store_flipped(top, W, H, t);
+    return true;
+}
+
+// Radiance RGBE (stb_image.h:7086-7272) brought to 8 bits the way stbi_load does for an HDR file (:1883-1907): linear value
+// v = mantissa * 2^(exponent - 136), byte = (int)((float)pow(v, 1 / 2.2f) * 255 + 0.5f) clamped to 0..255, alpha 255.
+// Header: "#?RADIANCE" or "#?RGBE", a FORMAT=32-bit_rle_rgbe line, a blank line, "-Y h +X w".  Rows are new-style run-length
+// coded for widths 8..32767 (flat RGBE otherwise, or when the first row does not start with the 2 2 marker).
+inline bool hdr_plausible(const std::vector<uint8_t>& f) {
+    return (f.size() >= 11 && std::memcmp(f.data(), "#?RADIANCE\n", 11) == 0) || (f.size() >= 7 && std::memcmp(f.data(), "#?RGBE\n", 7) == 0);
+}
+inline bool load_hdr(const std::vector<uint8_t>& f, Texture& t, std::string& why) {
+    ByteCursor s(f);
+    auto line = [&]() {   // up to the next '\n'; at most 1022 characters are kept (a character that ends the file is dropped, as in stb)
+        std::string out;
+        char c = (char)s.u8();
+        while (!s.eof() && c != '\n') {
+            out.push_back(c);
+            if (out.size() == 1023) { while (!s.eof() && s.u8() != '\n') {} break; }
+            c = (char)s.u8();
+        }
+        return out;
+    };
+    line();   // the signature, checked by hdr_plausible
+    bool rle_rgbe = false;
+    for (;;) {
+        const std::string tok = line();
+        if (tok.empty()) break;
+        if (tok == "FORMAT=32-bit_rle_rgbe") rle_rgbe = true;
+    }
+    if (!rle_rgbe) { why = "unsupported HDR format"; return false; }
+    const std::string dims = line();
+    if (dims.compare(0, 3, "-Y ") != 0) { why = "unsupported HDR data layout"; return false; }
+    char* end = nullptr;
+    const long H = std::strtol(dims.c_str() + 3, &end, 10);
+    while (*end == ' ') ++end;
+    if (std::strncmp(end, "+X ", 3) != 0) { why = "unsupported HDR data layout"; return false; }
+    const long W = std::strtol(end + 3, nullptr, 10);
+    if (!image_size_ok(W, H)) { why = "bad HDR size"; return false; }
+    std::vector<uint8_t> rgbe((size_t)4 * W * H);
+    // flat pixels are read four bytes at a time into one buffer; where the file ends, the bytes it no longer supplies keep the
+    // previous pixel's values (stb's read leaves its buffer untouched there), so a cut file repeats its last pixel
+    uint8_t quad[4] = {0, 0, 0, 0};
+    auto flat_from = [&](size_t first) {
+        for (size_t i = first; i < (size_t)W * H; ++i) {
+            for (int k = 0; k < 4 && !s.eof(); ++k) quad[k] = (uint8_t)s.u8();
+            std::memcpy(&rgbe[4 * i], quad, 4);
+        }
+    };
+    if (W < 8 || W >= 32768) flat_from(0);
+    else
+        for (long y = 0; y < H; ++y) {
+            const int c1 = s.u8(), c2 = s.u8(), hi = s.u8();
+            if (c1 != 2 || c2 != 2 || (hi & 0x80)) {   // not run-length coded: these four bytes are the first pixel of a flat file
+                // (on a later row too: stb then starts the picture over, flat, from this point of the file)
+                quad[0] = (uint8_t)c1; quad[1] = (uint8_t)c2; quad[2] = (uint8_t)hi; quad[3] = (uint8_t)s.u8();
+                std::memcpy(&rgbe[0], quad, 4);
+                flat_from(1);
+                break;
+            }
+            if (((hi << 8) | s.u8()) != W) { why = "corrupt HDR (scanline length)"; return false; }
+            for (int k = 0; k < 4; ++k)
+                for (long i = 0; i < W;) {
+                    int count = s.u8();
+                    const bool run = count > 128;
+                    if (run) count -= 128;
+                    const int v = run ? s.u8() : 0;
+                    if (count == 0 || count > W - i) { why = "corrupt HDR (bad RLE data)"; return false; }
+                    for (int z = 0; z < count; ++z, ++i) rgbe[4 * ((size_t)y * W + (size_t)i) + (size_t)k] = (uint8_t)(run ? v : s.u8());
+                }
+        }
+    std::vector<uint8_t> top((size_t)4 * W * H);
+    const double gamma = (double)(1.0f / 2.2f);
+    for (size_t i = 0; i < (size_t)W * H; ++i) {
+        const uint8_t* in = &rgbe[4 * i];
+        const float scale = in[3] ? (float)std::ldexp(1.0f, in[3] - 136) : 0.0f;
+        for (int c = 0; c < 3; ++c) {
+            const float linear = in[3] ? in[c] * scale : 0.0f;
+            float z = (float)std::pow((double)(linear * 1.0f), gamma) * 255 + 0.5f;
+            z = z < 0 ? 0 : (z > 255 ? 255 : z);
+            top[4 * i + (size_t)c] = (uint8_t)(int)z;
+        }
+        top[4 * i + 3] = 255;
+    }
+    store_flipped(top, (int)W, (int)H, t);
     return true;
 }
 
@@ -1140,9 +1484,8 @@ inline bool load_jpeg(const std::vector<uint8_t>& f, Texture& t, std::string& wh
 
 }  // namespace detail
 
-// Decodes an image file by content, never by extension (like stbi_load).  false + `why` if it cannot.
-// Formats stb_image reads and this loader does not: GIF, PSD, PIC, Radiance HDR (such a map_Kd loads in the reference
-// and is "Error loading texture" / id -1 here).
+// Decodes an image file by content, never by extension, trying the formats in stbi_load's order (stb_image.h:1131-1187):
+// PNG, BMP, GIF, PSD, PIC, JPEG, PNM, Radiance HDR, and TGA — which has no magic number — last.  false + `why` if it cannot.
 inline bool load_image(const std::string& path, Texture& t, std::string* why_out = nullptr) {
     std::vector<uint8_t> f;
     std::string why;
@@ -1150,9 +1493,13 @@ inline bool load_image(const std::string& path, Texture& t, std::string* why_out
     if (!detail::read_file(path, f)) why = "cannot read file";
     else if (f.size() >= 8 && f[0] == 0x89 && f[1] == 'P') ok = detail::load_png(f, t, why);
     else if (f.size() >= 2 && f[0] == 'B' && f[1] == 'M') ok = detail::load_bmp(f, t, why);
-    else if (f.size() >= 2 && f[0] == 'P' && (f[1] == '5' || f[1] == '6')) ok = detail::load_pnm(f, t, why);
+    else if (f.size() >= 6 && std::memcmp(f.data(), "GIF8", 4) == 0 && (f[4] == '7' || f[4] == '9') && f[5] == 'a') ok = detail::load_gif(f, t, why);
+    else if (f.size() >= 4 && std::memcmp(f.data(), "8BPS", 4) == 0) ok = detail::load_psd(f, t, why);
+    else if (detail::pic_plausible(f)) ok = detail::load_pic(f, t, why);
     else if (f.size() >= 3 && f[0] == 0xff && f[1] == 0xd8) ok = detail::load_jpeg(f, t, why);
-    else if (detail::tga_plausible(f)) ok = detail::load_tga(f, t, why);   // no magic number: tried last, like stb_image does
+    else if (f.size() >= 2 && f[0] == 'P' && (f[1] == '5' || f[1] == '6')) ok = detail::load_pnm(f, t, why);
+    else if (detail::hdr_plausible(f)) ok = detail::load_hdr(f, t, why);
+    else if (detail::tga_plausible(f)) ok = detail::load_tga(f, t, why);
     else why = "unknown image format";
     if (!ok && why.empty()) why = "not a valid image of its kind";
     if (why_out) *why_out = why;

@@ -309,6 +309,252 @@ def case_textures_jpeg():
     return d, ["scene.obj"]
 
 
+# ------------------------------------------------------------------------------------------------ GIF / PSD / PIC / HDR, written by hand
+def gif_lzw(indices, min_bits):
+    """GIF flavour of LZW (clear code first, variable width, LSB first) cut into sub-blocks"""
+    clear, eoi = 1 << min_bits, (1 << min_bits) + 1
+    out, acc, nbits = bytearray(), 0, 0
+
+    def emit(code, width):
+        nonlocal acc, nbits
+        acc |= code << nbits
+        nbits += width
+        while nbits >= 8:
+            out.append(acc & 255)
+            acc >>= 8
+            nbits -= 8
+
+    table = {(i,): i for i in range(clear)}
+    width, nxt = min_bits + 1, eoi + 1
+    emit(clear, width)
+    cur = ()
+    for px in indices:
+        if cur + (px,) in table:
+            cur = cur + (px,)
+            continue
+        emit(table[cur], width)
+        if nxt < 4096:
+            table[cur + (px,)] = nxt
+            nxt += 1
+            if nxt - 1 == (1 << width) and width < 12:
+                width += 1
+        else:
+            emit(clear, width)
+            table = {(i,): i for i in range(clear)}
+            width, nxt = min_bits + 1, eoi + 1
+        cur = (px,)
+    if cur:
+        emit(table[cur], width)
+    emit(eoi, width)
+    if nbits:
+        out.append(acc & 255)
+    blocks = b"".join(bytes([len(out[i:i + 255])]) + bytes(out[i:i + 255]) for i in range(0, len(out), 255))
+    return bytes([min_bits]) + blocks + b"\0"
+
+
+def gif_file(W, H, palette, rect, indices, bg=0, transparent=None, interlace=False, local_palette=None, version=b"GIF89a", min_bits=None):
+    """one-image GIF: global `palette` ([n,3], n a power of two), image `rect` (x, y, w, h) of palette `indices` (row-major)"""
+    def table_bits(n):
+        return int(math.log2(n)) - 1
+    x, y, w, h = rect
+    out = bytearray(version + struct.pack("<HHBBB", W, H, (0x80 | table_bits(len(palette))) if palette is not None else 0, bg, 0))
+    if palette is not None:
+        out += np.asarray(palette, np.uint8).tobytes()
+    out += b"\x21\xfe\x05hello\x00"                                     # a comment extension
+    if transparent is not None:
+        out += b"\x21\xf9\x04" + struct.pack("<BHB", 1, 0, transparent) + b"\0"
+    rows = np.asarray(indices, np.uint8).reshape(h, w)
+    if interlace:
+        order = list(range(0, h, 8)) + list(range(4, h, 8)) + list(range(2, h, 4)) + list(range(1, h, 2))
+        rows = rows[order]
+    out += b"\x2c" + struct.pack("<HHHHB", x, y, w, h, (0x40 if interlace else 0) | ((0x80 | table_bits(len(local_palette))) if local_palette is not None else 0))
+    if local_palette is not None:
+        out += np.asarray(local_palette, np.uint8).tobytes()
+    ncol = len(local_palette) if local_palette is not None else len(palette)
+    out += gif_lzw(rows.ravel().tolist(), min_bits or max(2, int(math.log2(ncol))))
+    return bytes(out + b"\x3b")
+
+
+def packbits(row):
+    """PackBits of one row of bytes (runs of >= 3 equal bytes, literal stretches otherwise)"""
+    out, i, n = bytearray(), 0, len(row)
+    while i < n:
+        j = i
+        while j + 1 < n and row[j + 1] == row[i] and j - i < 127:
+            j += 1
+        if j - i >= 2:
+            out += bytes([257 - (j - i + 1), row[i]])
+            i = j + 1
+            continue
+        k = i
+        while k < n and k - i < 128 and not (k + 2 < n and row[k] == row[k + 1] == row[k + 2]):
+            k += 1
+        out += bytes([k - i - 1]) + bytes(row[i:k])
+        i = k
+    return bytes(out)
+
+
+def psd_file(planes, depth=8, rle=False):
+    """flattened RGB PSD: planes [channels, h, w] of uint8 (depth 8) or uint16 (depth 16)"""
+    c, h, w = planes.shape
+    out = bytearray(b"8BPS" + struct.pack(">H6xHIIHH", 1, c, h, w, depth, 3))
+    out += struct.pack(">I", 0) + struct.pack(">I", 6) + b"resrcs" + struct.pack(">I", 0)      # mode data, image resources, layers
+    out += struct.pack(">H", 1 if rle else 0)
+    if rle:
+        rows = [packbits(planes[ch, y].astype(">u2" if depth == 16 else np.uint8).tobytes()) for ch in range(c) for y in range(h)]
+        out += b"".join(struct.pack(">H", len(r)) for r in rows) + b"".join(rows)
+    else:
+        out += planes.astype(">u2" if depth == 16 else np.uint8).tobytes()
+    return bytes(out)
+
+
+def pic_file(w, h, packets, rows_coder):
+    """Softimage PIC: packets = [(type, channel mask)], rows_coder(y, packet index) -> bytes of that packet's row"""
+    out = bytearray(struct.pack(">If", 0x5380F634, 3.71) + b"rt3 loader fixture".ljust(80, b"\0") + b"PICT" + struct.pack(">HHfHH", w, h, 1.0, 3, 0))
+    for i, (typ, chan) in enumerate(packets):
+        out += bytes([1 if i + 1 < len(packets) else 0, 8, typ, chan])
+    for y in range(h):
+        for i in range(len(packets)):
+            out += rows_coder(y, i)
+    return bytes(out)
+
+
+def rgbe(rgb):
+    """float RGB [h, w, 3] -> Radiance RGBE bytes [h, w, 4]"""
+    m = rgb.max(axis=2)
+    e = np.where(m > 1e-32, np.floor(np.log2(np.maximum(m, 1e-38))) + 1, 0)
+    scale = np.where(m > 1e-32, 256.0 / np.exp2(e), 0)
+    out = np.zeros(rgb.shape[:2] + (4,), np.uint8)
+    out[..., :3] = np.clip(rgb * scale[..., None], 0, 255).astype(np.uint8)
+    out[..., 3] = np.where(m > 1e-32, e + 128, 0).astype(np.uint8)
+    return out
+
+
+def hdr_file(px, rle=True, signature=b"#?RADIANCE"):
+    h, w = px.shape[:2]
+    out = bytearray(signature + b"\n# made by hand\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=1.0\n\n-Y %d +X %d\n" % (h, w))
+    for y in range(h):
+        if not rle:
+            out += px[y].tobytes()
+            continue
+        out += bytes([2, 2, w >> 8, w & 255])
+        for k in range(4):
+            row, i = px[y, :, k].tolist(), 0
+            while i < w:
+                j = i
+                while j + 1 < w and row[j + 1] == row[i] and j - i < 126:
+                    j += 1
+                if j - i >= 2:
+                    out += bytes([128 + (j - i + 1), row[i]])
+                    i = j + 1
+                    continue
+                k2 = i
+                while k2 < w and k2 - i < 128 and not (k2 + 2 < w and row[k2] == row[k2 + 1] == row[k2 + 2]):
+                    k2 += 1
+                out += bytes([k2 - i]) + bytes(row[i:k2])
+                i = k2
+    return bytes(out)
+
+
+def case_textures_more():
+    d = case_dir("textures_more")
+    names = []
+
+    def put(fn, data):
+        open(os.path.join(d, fn), "wb").write(data)
+        names.append(fn)
+
+    rng = np.random.RandomState(77)
+    # ---- GIF
+    pal16 = rng.randint(0, 256, (16, 3))
+    w, h = 23, 17
+    smooth = ((np.add.outer(np.arange(h), np.arange(w)) // 3) % 16).astype(np.uint8)
+    noisy = rng.randint(0, 16, (h, w)).astype(np.uint8)
+    put("plain.gif", gif_file(w, h, pal16, (0, 0, w, h), smooth))
+    put("noisy87.gif", gif_file(w, h, pal16, (0, 0, w, h), noisy, version=b"GIF87a"))
+    put("interlaced.gif", gif_file(w, h, pal16, (0, 0, w, h), noisy, interlace=True))
+    put("transparent.gif", gif_file(w, h, pal16, (0, 0, w, h), smooth, transparent=5))
+    put("subrect_bg.gif", gif_file(w, h, pal16, (4, 3, 11, 9), noisy[:9, :11], bg=7))            # uncovered pixels: background entry, red / blue exchanged
+    put("subrect_bg0.gif", gif_file(w, h, pal16, (4, 3, 11, 9), noisy[:9, :11], bg=0))           # background index 0: uncovered pixels stay 0,0,0,0
+    put("local_palette.gif", gif_file(w, h, pal16, (0, 0, w, h), noisy % 8, local_palette=rng.randint(0, 256, (8, 3)), transparent=2))
+    put("only_local.gif", gif_file(w, h, None, (0, 0, w, h), noisy % 4, local_palette=rng.randint(0, 256, (4, 3))))
+    pal256 = rng.randint(0, 256, (256, 3))
+    big = rng.randint(0, 256, (90, 120)).astype(np.uint8)
+    put("big256.gif", gif_file(120, 90, pal256, (0, 0, 120, 90), big))                           # fills the code table: clear codes in mid-stream
+    put("beyond_table.gif", gif_file(w, h, pal16[:4], (0, 0, w, h), noisy % 8, min_bits=3))          # indices 4..7 have no palette entry: not drawn
+    whole = gif_file(w, h, pal16, (0, 0, w, h), noisy, bg=3)
+    put("cut.gif", whole[:len(whole) - 60])                                                      # data ends early: what was drawn stays, the rest is background
+    put("no_image.gif", gif_file(w, h, pal16, (0, 0, w, h), smooth)[:13 + 48] + b"\x3b")
+    try:
+        from PIL import Image
+        Image.fromarray(picture(31, 19, 3)).convert("P", palette=Image.ADAPTIVE, colors=64).save(os.path.join(d, "pil.gif"))
+        names.append("pil.gif")
+    except ImportError:
+        pass
+    # ---- PSD
+    rgb = picture(19, 11, 6).transpose(2, 0, 1)
+    alpha = picture(19, 11, 7)[..., 0][None]
+    alpha[0, :2] = 255
+    alpha[0, 2:4] = 0
+    put("rgb8.psd", psd_file(rgb))
+    put("rgba8.psd", psd_file(np.concatenate([rgb, alpha])))                                     # white matte removal
+    put("rgba8_rle.psd", psd_file(np.concatenate([rgb // 32 * 32, alpha // 64 * 64]), rle=True))
+    put("rgb16.psd", psd_file(rgb.astype(np.uint16) * 257 - 100, depth=16))
+    put("rgba16.psd", psd_file(np.concatenate([rgb, alpha]).astype(np.uint16) * 256 + 17, depth=16))
+    put("grey_as_rgb.psd", psd_file(rgb[:1]))                                                    # one channel in RGB mode: green and blue 0
+    put("five.psd", psd_file(np.concatenate([rgb, alpha, alpha // 2]), rle=True))                # a fifth channel is ignored
+    put("cmyk.psd", psd_file(rgb).replace(struct.pack(">HH", 8, 3), struct.pack(">HH", 8, 4), 1))  # refused
+    # ---- PIC
+    img = np.dstack([picture(21, 13, 8) // 16 * 16, picture(21, 13, 9)[..., :1]])
+    put("raw_rgb.pic", pic_file(21, 13, [(0, 0xE0)], lambda y, i: img[y, :, :3].tobytes()))
+
+    def mixed(vals):                                                                             # vals [n, k]: runs of equal pixels, literals otherwise
+        out, i, n = bytearray(), 0, len(vals)
+        while i < n:
+            j = i
+            while j + 1 < n and (vals[j + 1] == vals[i]).all() and j - i < 127:
+                j += 1
+            if j > i:
+                out += bytes([127 + (j - i + 1)]) + vals[i].tobytes()
+                i = j + 1
+            else:
+                k = i
+                while k < n and k - i < 128 and not (k + 1 < n and (vals[k] == vals[k + 1]).all()):
+                    k += 1
+                out += bytes([k - i - 1]) + vals[i:k].tobytes()
+                i = k
+        return bytes(out)
+
+    def pure(vals):
+        out, i, n = bytearray(), 0, len(vals)
+        while i < n:
+            j = i
+            while j + 1 < n and (vals[j + 1] == vals[i]).all() and j - i < 254:
+                j += 1
+            out += bytes([j - i + 1]) + vals[i].tobytes()
+            i = j + 1
+        return bytes(out)
+
+    put("mixed_rgb_pure_a.pic", pic_file(21, 13, [(2, 0xE0), (1, 0x10)], lambda y, i: mixed(img[y, :, :3]) if i == 0 else pure(img[y, :, 3:] // 64 * 64)))
+    put("long_run.pic", pic_file(300, 2, [(2, 0xE0)], lambda y, i: bytes([128]) + struct.pack(">H", 300) + bytes([10 * y + 1, 20, 30])))
+    put("green_only.pic", pic_file(21, 13, [(0, 0x40)], lambda y, i: img[y, :, 1].tobytes()))     # red / blue / alpha stay 255
+    put("overrun.pic", pic_file(21, 2, [(1, 0xE0)], lambda y, i: bytes([200, 1, 2, 3])))          # pure runs are cut at the row end
+    # ---- Radiance HDR
+    x = np.linspace(0, 1, 40)[None, :, None]
+    yv = np.linspace(0, 1, 12)[:, None, None]
+    lin = (np.array([0.02, 0.5, 3.0])[None, None, :] * (0.2 + x) * (0.3 + yv) * 2.0)
+    lin[3:5, 10:30] = 0.0
+    lin[6, :, :] = 1.0
+    px = rgbe(lin)
+    put("rle.hdr", hdr_file(px))
+    put("flat.hdr", hdr_file(px, rle=False))
+    put("narrow.hdr", hdr_file(px[:, :5]))                                                       # width < 8: always flat, whatever the bytes look like
+    put("rgbe_sig.hdr", hdr_file(px, signature=b"#?RGBE"))
+    put("xyze.hdr", hdr_file(px).replace(b"32-bit_rle_rgbe", b"32-bit_rle_xyze"))                 # refused
+    tri_scene(d, names)
+    return d, ["scene.obj"]
+
+
 def run(case, paths, dumper, out):
     d = os.path.join(CASES, case)
     r = subprocess.run([dumper, out] + [os.path.join(d, p) for p in paths], capture_output=True, text=True)
@@ -332,7 +578,7 @@ def jobs():
 
 
 if __name__ == "__main__":
-    for fn in (case_polygons, case_groups, case_syntax, case_keyframes, case_scenes, case_mtl_textures, case_textures_png, case_textures_other, case_textures_jpeg):
+    for fn in (case_polygons, case_groups, case_syntax, case_keyframes, case_scenes, case_mtl_textures, case_textures_png, case_textures_other, case_textures_jpeg, case_textures_more):
         fn()
     if not os.path.exists(REF_DUMPER):
         sys.exit("fixtures written; oracle/_ref/dump_ref_loader is missing (make -C oracle ref_loader): goldens NOT refreshed")

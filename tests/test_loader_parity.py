@@ -41,7 +41,7 @@ JOBS = gen.jobs()
 
 def test_fixture_inventory():
     names = {j[0] for j in JOBS}
-    assert {"polygons", "groups", "syntax", "keyframes", "scenes", "mtl_textures", "textures_png", "textures_other", "textures_jpeg"} <= names
+    assert {"polygons", "groups", "syntax", "keyframes", "scenes", "mtl_textures", "textures_png", "textures_other", "textures_jpeg", "textures_more"} <= names
     for case, golden, _ in JOBS:
         assert os.path.exists(os.path.join(CASES, case, golden)), "golden missing: run tests/golden/loader/make_loader_goldens.py"
     # what the goldens hold, so that an empty golden cannot pass for a match
@@ -53,6 +53,8 @@ def test_fixture_inventory():
     assert len(tex) == len(meshes) >= 20
     meshes, tex = loader_dump.parse(os.path.join(CASES, "keyframes", "golden.rt3l"))
     assert all(m["num_keys"] == 3 for m in meshes)
+    meshes, tex = loader_dump.parse(os.path.join(CASES, "textures_more", "golden.rt3l"))   # GIF / PSD / PIC / HDR; three files are refused
+    assert len(tex) >= 28 and len(meshes) == len(tex) + 3
 
 
 @pytest.mark.parametrize("case,golden,paths", JOBS, ids=["%s/%s" % (j[0], j[1]) for j in JOBS])
@@ -152,3 +154,41 @@ def test_random_obj_files_loader_against_loader(own_dumper, ref_dumper, tmp_path
             assert d == "", (seed, d)
             compared += 1
     assert compared >= 200
+
+
+def test_damaged_texture_files_loader_against_loader(own_dumper, ref_dumper, tmp_path):
+    """GIF / PSD / PIC / HDR fixtures with bytes overwritten, bits flipped or the tail cut off: both loaders must agree on
+    which files still load and on every texel of those that do (stb is lenient — reads past the end of a file yield zeros,
+    a cut flat HDR repeats its last pixel — and so is image_loader.hpp).  Formats whose stb decoder reads uninitialised
+    memory on damaged input (palettised BMP, raw TGA, JPEG with restart markers) are left out: there is nothing to agree on."""
+    if ref_dumper is None:
+        pytest.skip("/root/reference not present")
+    src = os.path.join(CASES, "textures_more")
+    files = [f for f in sorted(os.listdir(src)) if f.rsplit(".", 1)[-1] in ("gif", "psd", "pic", "hdr")]
+    assert len(files) >= 25
+    r = random.Random(2024)
+    loaded = 0
+    for it in range(300):
+        name = files[it % len(files)]
+        b = bytearray(open(os.path.join(src, name), "rb").read())
+        mode = r.randrange(3)
+        if mode == 0:
+            for _ in range(r.randrange(1, 4)):
+                b[r.randrange(len(b))] = r.randrange(256)
+        elif mode == 1:
+            b = b[:r.randrange(1, len(b))]
+        else:
+            b[r.randrange(len(b))] ^= 1 << r.randrange(8)
+        if name.endswith(".psd") and (b[14:18] != b"\0\0\0\x0b" or b[18:22] != b"\0\0\0\x13"):
+            continue   # a damaged size field can ask for more pixels than this loader accepts (2^28)
+        d = tmp_path / ("it%d" % it)
+        d.mkdir()
+        open(d / name, "wb").write(b)
+        gen.tri_scene(str(d), [name])
+        a = subprocess.run([ref_dumper, str(tmp_path / "ref.bin"), str(d / "scene.obj")], capture_output=True)
+        o = subprocess.run([own_dumper, str(tmp_path / "own.bin"), str(d / "scene.obj")], capture_output=True)
+        assert a.returncode == 0 and o.returncode == 0, (it, name, a.stderr[-200:], o.stderr[-200:])
+        same = open(tmp_path / "ref.bin", "rb").read() == open(tmp_path / "own.bin", "rb").read()
+        assert same, (it, name, mode, loader_dump.diff(str(tmp_path / "ref.bin"), str(tmp_path / "own.bin")))
+        loaded += b"Error loading texture" not in a.stderr
+    assert loaded >= 100
