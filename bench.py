@@ -299,7 +299,7 @@ def run_config(name, desc, local, torch, steps=3, warmup=2, spl=SPL, max_depth=N
            "max_depth": depth, "steps": steps, "warmup": warmup, "value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms / steps,
            "samples_per_s": st["samples"] / (ms * 1e-3), "rays_per_step": {k: st["rays_" + k] // steps for k in ("primary", "bounce", "shadow")},
            "stage_ms": {k: s[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_connect", "ms_resolve", "ms_total")},
-           "upload_and_build_s": build_s}
+           "upload_and_build_s": build_s, "flattened_instances": s["flattened_instances"], "traversal_passes": s["traversal_passes"]}
     g.close()
     out["traversal_counters"] = traversal_counters(desc, local)
     return out

@@ -31,6 +31,7 @@ namespace {
 
 thread_local std::string g_err;
 bool g_chain_sum = false;  // see render_pixel
+bool g_flatten = true;     // see rt3o_accel_build
 
 struct Box {
     f3 lo{3e38f, 3e38f, 3e38f}, hi{-3e38f, -3e38f, -3e38f};
@@ -132,9 +133,11 @@ struct Bvh2 {
         }
     }
 
-    // calls leaf(prim) for every primitive whose padded box the ray may touch within [tmin, *tfar]
+    // calls leaf(prim) for every primitive whose padded box the ray may touch within [tmin, *tfar].  `slack` (3 absolute
+    // distances) and `widen` loosen the test further for callers whose primitive test does not run on this ray (flattened
+    // instances: the boxes are object space, the triangles are tested in world space)
     template <class F>
-    bool traverse(f3 o, f3 d, float tmin, const float* tfar, F&& leaf) const {
+    bool traverse(f3 o, f3 d, float tmin, const float* tfar, F&& leaf, const float* slack = nullptr, float widen = 4e-7f) const {
         if (nodes.empty()) return false;
         f3 inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
         int stack[128];
@@ -146,13 +149,14 @@ struct Bvh2 {
             bool ok = true;
             for (int a = 0; a < 3 && ok; a++) {
                 float oa = get(o, a), da = get(d, a), lo = get(nd.box.lo, a), hi = get(nd.box.hi, a);
+                if (slack) { lo -= slack[a]; hi += slack[a]; }
                 if (da == 0.0f) { ok = (oa >= lo && oa <= hi); continue; }
                 float ia = get(inv, a);
                 float ta = (lo - oa) * ia, tb = (hi - oa) * ia;
                 if (ta > tb) std::swap(ta, tb);
                 // widen by a few ulps (robust slab test)
-                ta -= fabsf(ta) * 4e-7f;
-                tb += fabsf(tb) * 4e-7f;
+                ta -= fabsf(ta) * widen;
+                tb += fabsf(tb) * widen;
                 t0 = fmaxf(t0, ta);
                 t1 = fminf(t1, tb);
                 ok = t0 <= t1;
@@ -215,6 +219,8 @@ struct Instance {
     Affine stat, stat_inv;
     int nkeys = 0;
     bool identity = false;
+    bool flat = false;      // flattened (see rt3o_accel_build): its triangles are tested in WORLD space, vertices = stat * v
+    float flat_w[3] = {0, 0, 0};  // magnitude bound of the instance's world-space vertices per axis (padding of the object-space culling)
     std::vector<float> keys;
     float t0 = 0, t1 = 1;
     f3 emission{0, 0, 0}, diffuse{0.8f, 0.8f, 0.8f};
@@ -303,10 +309,13 @@ struct rt3o_scene {
             const Blas& b = *blas[in.blas];
             f3 oo, od;
             to_object(in, time, o, d, oo, od);
-            RayShear sh = make_shear(od);
+            RayShear sh = make_shear(in.flat ? d : od);
             auto visit_prim = [&](int p) -> bool {
                 float t, u, v;
-                if (!test_prim(b, p, oo, od, sh, tmin, tmax, time, t, u, v)) return false;
+                if (in.flat) {  // the world-space ray against the world-space triangle, exactly what the flattened BLAS of the product holds
+                    if (!hit_triangle(o, sh, xform_point(in.stat, b.verts[b.idx[3 * p]]), xform_point(in.stat, b.verts[b.idx[3 * p + 1]]),
+                                      xform_point(in.stat, b.verts[b.idx[3 * p + 2]]), tmin, tmax, t, u, v)) return false;
+                } else if (!test_prim(b, p, oo, od, sh, tmin, tmax, time, t, u, v)) return false;
                 if (better(t, ii, p, best)) {
                     best.t = t; best.u = u; best.v = v; best.prim = p; best.inst = ii;
                     tfar = t;
@@ -317,6 +326,17 @@ struct rt3o_scene {
                 for (int p = 0; p < b.nprims; p++)
                     if (visit_prim(p)) return true;
                 return false;
+            }
+            if (in.flat) {
+                // The BVH is the object-space one, walked by the object-space ray, but the hit decision is taken in world space:
+                // the culling must allow for the rounding of the ray transform and of the transformed vertices.  Both are a
+                // few 1e-7 of sum_j |minv_ij| (|world coordinate_j|) + |minv_i3| in object space; 1e-4 of it is taken.
+                float slack[3];
+                for (int i = 0; i < 3; i++) {
+                    const float* m = in.stat_inv.m + 4 * i;
+                    slack[i] = 1e-4f * (fabsf(m[0]) * (in.flat_w[0] + fabsf(o.x)) + fabsf(m[1]) * (in.flat_w[1] + fabsf(o.y)) + fabsf(m[2]) * (in.flat_w[2] + fabsf(o.z)) + fabsf(m[3]));
+                }
+                return b.bvh.traverse(oo, od, tmin, &tfar, visit_prim, slack, 1e-4f);
             }
             return b.bvh.traverse(oo, od, tmin, &tfar, visit_prim);
         };
@@ -976,6 +996,30 @@ int rt3o_accel_append_animated_instance(rt3o_scene* s, int blas, const float* ke
 int rt3o_accel_build(rt3o_scene* s) {
     RT3O_TRY
     if (!s || s->inst.empty()) { g_err = "accel_build: no instances"; return -4; }
+    // Flattening (rt3_accel_build of the product, "flatten"): static, transformed instances of plain triangle meshes are
+    // intersected in world space — vertices transformed once, x' = ((m0 x + m1 y) + m2 z) + m3 — instead of transforming every
+    // ray.  The hit records differ from the object-space ones in the last bits, so the oracle applies the same rule: all such
+    // instances if, together with the identity ones, they stay below 2^27 triangles; none otherwise.
+    {
+        uint64_t sum = 0;
+        for (Instance& in : s->inst) {
+            const Blas& b = *s->blas[in.blas];
+            in.flat = false;
+            if (in.nkeys == 0 && b.type == PRIM_TRI && b.vkeys == 1) sum += (uint64_t)b.nprims;
+        }
+        if (g_flatten && sum < (1ull << 27))
+            for (Instance& in : s->inst) {
+                const Blas& b = *s->blas[in.blas];
+                if (in.nkeys != 0 || in.identity || b.type != PRIM_TRI || b.vkeys != 1) continue;
+                in.flat = true;
+                const float bx = std::max(fabsf(b.bounds.lo.x), fabsf(b.bounds.hi.x)), by = std::max(fabsf(b.bounds.lo.y), fabsf(b.bounds.hi.y)),
+                            bz = std::max(fabsf(b.bounds.lo.z), fabsf(b.bounds.hi.z));
+                for (int i = 0; i < 3; i++) {
+                    const float* m = in.stat.m + 4 * i;
+                    in.flat_w[i] = fabsf(m[0]) * bx + fabsf(m[1]) * by + fabsf(m[2]) * bz + fabsf(m[3]);
+                }
+            }
+    }
     std::vector<Box> boxes(s->inst.size());
     for (size_t i = 0; i < s->inst.size(); i++) boxes[i] = s->instance_world_box(s->inst[i]);
     s->tlas.build(boxes);
@@ -1114,6 +1158,7 @@ int rt3o_reset_stats(rt3o_scene* s) {
 }
 
 void rt3o_set_chain_sum(int on) { g_chain_sum = on != 0; }
+void rt3o_set_flatten(int on) { g_flatten = on != 0; }
 void rt3o_set_libm_sincos(int on) { g_libm_sincos = on != 0; }
 
 // ---------------------------------------------------------------- KAT hooks

@@ -42,6 +42,10 @@ const char* rt3o_last_error(void);
 /* 1 = sum radiance in the reference's single running chain across the samples of a launch (raygen.cu:27,58-59);
  * 0 (default) = per-sample sums added in sample order, the association the wavefront kernels use */
 void rt3o_set_chain_sum(int on);
+/* 1 (default): static transformed triangle-mesh instances are intersected in world space, like the product's flattened
+ * merged BLAS ("flatten" option of rt3_set_option); 0: every non-identity instance transforms the ray.  Takes effect at the
+ * next rt3o_accel_build. */
+void rt3o_set_flatten(int on);
 /* 1 = deviation D1 off: the cosine sample uses cosf / sinf(2 pi u) of the C library like the reference's text compiled
  * for the host (src/util/sampling.h:27-37); 0 (default) = the explicit polynomial the kernels share */
 void rt3o_set_libm_sincos(int on);

@@ -28,7 +28,7 @@ class Stats(C.Structure):
         ("samples", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("ms_generate", C.c_float), ("ms_extend", C.c_float), ("ms_shade", C.c_float),
         ("ms_connect", C.c_float), ("ms_resolve", C.c_float), ("ms_total", C.c_float),
-        ("max_stack_depth", C.c_uint32), ("error_flags", C.c_uint32),
+        ("max_stack_depth", C.c_uint32), ("error_flags", C.c_uint32), ("flattened_instances", C.c_uint32), ("traversal_passes", C.c_uint32),
     ]
 
     def as_dict(self):

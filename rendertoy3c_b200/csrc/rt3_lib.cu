@@ -90,6 +90,10 @@ struct rt3_context {
     bool has_merged = false, single_level = false;
     bool has_subdiv_curves = false;  // some instance refers to a spline curve geometry (set in rt3_accel_build)
     int opt_merge = 1;
+    int opt_flatten = 1;   // static, transformed triangle-mesh instances join the merged world BLAS (vertices transformed once, at build)
+    int opt_split = 1;     // merged BLAS beside other instances: 0 = one TLAS over both, 2 = always two passes (single-level kernel, then the rest), 1 = two passes when the merged BLAS is large
+    bool split = false;
+    uint32_t flattened = 0;  // instances flattened by the last build
     int opt_tlas_sah = 1;
     int opt_tlas_leaf = 1;      // instances per TLAS leaf child (r02j, C3 / C4 Mrays/s: 3 -> 762 / 957, 2 -> 785 / 927, 1 -> 815 / 953: an own box per instance culls more entries than the extra TLAS nodes cost)
     int opt_sah_collapse = 1;   // binary -> wide collapse by the SAH dynamic program (k_bvh_dp); 0 = greedy largest-area opening
@@ -106,9 +110,9 @@ struct rt3_context {
     size_t pool_paths = 0;
     DevBuf<float4> ray[2][3], st[2][2], hit0, sh[4], result;
     DevBuf<int32_t> hit_inst;
-    DevBuf<uint32_t> counters;           // 2 chains x 4 x MAX_DEPTH_SLOTS
+    DevBuf<uint32_t> counters;           // 2 chains x 6 x MAX_DEPTH_SLOTS
     DevBuf<unsigned long long> d_stats;  // primary, bounce, shadow
-    DevBuf<uint32_t> trace_fetch;
+    DevBuf<uint32_t> trace_fetch;        // [2]: one work counter per pass
     // options / stats
     int opt_timing = 0;
     // connect(d) (shadow rays) and extend(d+1) (next bounce) are independent: connect runs on a second stream so that
@@ -128,7 +132,9 @@ struct rt3_context {
     int nccl_rank = -1;
 #endif
 
-    TravScene trav_scene() {
+    // merged_only: the scene as pass 1 of a split traversal sees it — the merged world BLAS and nothing else
+    TravScene trav_scene(bool merged_only = false) {
+        const bool single_level = this->single_level || merged_only;
         TravScene s;
         s.tlas_nodes = single_level ? m_nodes_p : tlas_nodes.p;
         s.tlas_order = tlas_order.p;
@@ -147,11 +153,12 @@ struct rt3_context {
         s.max_stack = d_flags.p + 1;
         return s;
     }
-    int trav_grid() const {
+    int trav_grid(bool single) const {
 #ifdef RT3_EMULATE
+        (void)single;
         return 1;
 #else
-        const int per_sm = opt_ctas_per_sm > 0 ? opt_ctas_per_sm : (single_level ? RT3_TRAV_MIN_BLOCKS_SINGLE : RT3_TRAV_MIN_BLOCKS);
+        const int per_sm = opt_ctas_per_sm > 0 ? opt_ctas_per_sm : (single ? RT3_TRAV_MIN_BLOCKS_SINGLE : RT3_TRAV_MIN_BLOCKS);
         return num_sms * per_sm;
 #endif
     }
@@ -159,19 +166,32 @@ struct rt3_context {
 
 namespace {
 
-template <int MODE>
-void launch_traverse(rt3_context* c, const TraverseArgs& a, Stream st) {
-    // single-level scenes (merged world BLAS only) run the lean instantiation
+template <int MODE, bool SINGLE>
+void launch_traverse_kernel(rt3_context* c, const TraverseArgs& a, Stream st) {
 #ifdef RT3_EMULATE
-    (void)st;
-    if (c->single_level) k_traverse<MODE, true>(a);
-    else k_traverse<MODE, false>(a);
+    (void)c; (void)st;
+    k_traverse<MODE, SINGLE>(a);
 #else
-    if (c->single_level) k_traverse<MODE, true><<<c->trav_grid(), RT3_TRAV_THREADS, 0, st>>>(a);
-    else k_traverse<MODE, false><<<c->trav_grid(), RT3_TRAV_THREADS, 0, st>>>(a);
+    k_traverse<MODE, SINGLE><<<c->trav_grid(SINGLE), RT3_TRAV_THREADS, 0, st>>>(a);
     RT3_CUDA(cudaGetLastError());
 #endif
     count_launch();
+}
+// fetch2: the work counter of the second launch of a split traversal (zeroed like a.fetch)
+template <int MODE>
+void launch_traverse(rt3_context* c, TraverseArgs a, uint32_t* fetch2, Stream st) {
+    a.pass = 0u;
+    if (c->single_level) launch_traverse_kernel<MODE, true>(c, a, st);   // merged world BLAS only: the lean instantiation
+    else if (c->split) {   // the bulk of the triangles with the lean kernel, then everything else, seeded with what that found
+        TraverseArgs p1 = a;
+        p1.scene = c->trav_scene(true);
+        p1.pass = 1u;
+        launch_traverse_kernel<MODE, true>(c, p1, st);
+        a.pass = 2u;
+        a.fetch = fetch2;
+        a.stat = nullptr;
+        launch_traverse_kernel<MODE, false>(c, a, st);
+    } else launch_traverse_kernel<MODE, false>(c, a, st);
 }
 
 void upload_hitgroups(rt3_context* c) {
@@ -388,9 +408,9 @@ int rt3_context_create(int device, rt3_context_t* out) {
     if (const char* e = getenv("RT3_OVERLAP")) c->opt_overlap = atoi(e);  // A/B switch for measurements; rt3_set_option("overlap", v) is the API
 #endif
     c->d_flags.alloc(16);  // [0] error flags, [1] max stack, [2..15] diagnostic counters (RT3_STATS builds)
-    c->counters.alloc(8 * MAX_DEPTH_SLOTS);  // two chains
+    c->counters.alloc(12 * MAX_DEPTH_SLOTS);  // two chains
     c->d_stats.alloc(4);
-    c->trace_fetch.alloc(1);
+    c->trace_fetch.alloc(2);
     dev_memset(c->d_flags.p, 0, c->d_flags.bytes(), c->stream);
     dev_memset(c->d_stats.p, 0, c->d_stats.bytes(), c->stream);
     stream_sync(c->stream);
@@ -442,6 +462,8 @@ int rt3_set_option(rt3_context_t c, const char* key, int value) {
     else if (k == "overlap") c->opt_overlap = value;
     else if (k == "persist_ctas_per_sm") c->opt_ctas_per_sm = value;
     else if (k == "merge_identity") { c->opt_merge = value; c->built = false; }
+    else if (k == "flatten") { c->opt_flatten = value; c->built = false; }
+    else if (k == "split") { c->opt_split = value; c->built = false; }
     else if (k == "tlas_sah") { c->opt_tlas_sah = value; c->built = false; }
     else if (k == "bsphere_cull") { c->opt_bsphere_cull = value; c->built = false; }
     else if (k == "tlas_leaf") { c->opt_tlas_leaf = value; c->built = false; }
@@ -710,24 +732,37 @@ int rt3_accel_build(rt3_context_t c) {
     const uint32_t ni = (uint32_t)c->inst.size();
     static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     // ---- which instances go into the merged world BLAS, which stay in the TLAS
+    // Identity instances (all the reference creates) always qualify.  Transformed static instances of plain triangle meshes
+    // are flattened into it as well ("flatten", default on): instancing saves memory the B200 has (48 B per triangle + nodes,
+    // ~100 B in all), and costs a ray transform, three divisions and a second BVH root per instance visit.  The merged BLAS is
+    // one acceleration structure and stays below the 2^27-primitive limit of build_bvh8: if flattening would exceed it, only
+    // the identity instances are merged; if those alone exceed it, nothing is.
     std::vector<uint32_t> merged, tl;
-    for (uint32_t i = 0; i < ni; i++) {
-        const InstanceHost& in = c->inst[i];
-        const bool identity = in.nkeys == 0 && memcmp(in.xform, ident, sizeof(ident)) == 0;
-        if (c->opt_merge && identity && c->geoms[in.blas]->type == PRIM_TRI) merged.push_back(i);
-        else tl.push_back(i);
-    }
-    {   // the merged BLAS is one acceleration structure: keep it below the 2^27-primitive limit of build_bvh8
+    auto select = [&](bool flatten) {
+        merged.clear(); tl.clear();
         uint64_t sum = 0;
-        for (uint32_t i : merged) sum += c->geoms[c->inst[i].blas]->nprims;
-        if (sum >= (1ull << 27)) {
-            merged.clear();
-            tl.clear();
-            for (uint32_t i = 0; i < ni; i++) tl.push_back(i);
+        for (uint32_t i = 0; i < ni; i++) {
+            const InstanceHost& in = c->inst[i];
+            const bool identity = in.nkeys == 0 && memcmp(in.xform, ident, sizeof(ident)) == 0;
+            if (c->opt_merge && in.nkeys == 0 && (identity || flatten) && c->geoms[in.blas]->type == PRIM_TRI) { merged.push_back(i); sum += c->geoms[in.blas]->nprims; }
+            else tl.push_back(i);
         }
+        return sum < (1ull << 27);
+    };
+    if (!(c->opt_flatten && select(true)) && !select(false)) {
+        merged.clear();
+        tl.clear();
+        for (uint32_t i = 0; i < ni; i++) tl.push_back(i);
     }
+    c->flattened = 0;
+    for (uint32_t i : merged) c->flattened += memcmp(c->inst[i].xform, ident, sizeof(ident)) != 0 ? 1u : 0u;
     c->has_merged = !merged.empty();
     c->single_level = c->has_merged && tl.empty();
+    {   // two passes pay when the merged BLAS carries real work; a floor quad beside animated instances does not
+        uint64_t sum = 0;
+        for (uint32_t i : merged) sum += c->geoms[c->inst[i].blas]->nprims;
+        c->split = c->has_merged && !tl.empty() && (c->opt_split >= 2 || (c->opt_split == 1 && sum >= 1024));
+    }
     for (uint32_t i : tl) ensure_blas(c, c->geoms[c->inst[i].blas].get());
     BlasBounds merged_bounds{};
     if (c->has_merged) {
@@ -735,17 +770,18 @@ int rt3_accel_build(rt3_context_t c) {
         uint32_t total = 0;
         for (uint32_t i : merged) {
             const Geometry& g = *c->geoms[c->inst[i].blas];
-            ranges.push_back(MergedRange{total, i, g.verts.p, g.idx.p});
+            MergedRange r{total, i, g.verts.p, g.idx.p, memcmp(c->inst[i].xform, ident, sizeof(ident)) != 0 ? 1u : 0u, {}};
+            memcpy(r.xf, c->inst[i].xform, sizeof(r.xf));
+            ranges.push_back(r);
             total += g.nprims;
         }
-        DevBuf<float4> lo(total), hi(total);
-        for (const MergedRange& r : ranges) {
-            const Geometry& g = *c->geoms[c->inst[r.inst].blas];
-            RT3_LAUNCH_1D(k_tri_boxes, g.nprims, c->stream, (const float*)g.verts.p, (const int32_t*)g.idx.p, lo.p + r.first, hi.p + r.first);
-        }
-        build_bvh8(lo.p, hi.p, total, c->stream, c->m_nodes, c->m_order, c->m_bvh, /*sah_host=*/false, /*ploc=*/c->opt_ploc != 0, RT3_LEAF_MAX, /*sah_collapse=*/c->opt_sah_collapse != 0);
         DevBuf<MergedRange> d_ranges(ranges.size());
         h2d(d_ranges.p, ranges.data(), sizeof(MergedRange) * ranges.size(), c->stream);
+        {
+            DevBuf<float4> lo(total), hi(total);
+            RT3_LAUNCH_1D(k_merged_boxes, total, c->stream, (const MergedRange*)d_ranges.p, (uint32_t)ranges.size(), lo.p, hi.p);
+            build_bvh8(lo.p, hi.p, total, c->stream, c->m_nodes, c->m_order, c->m_bvh, /*sah_host=*/false, /*ploc=*/c->opt_ploc != 0, RT3_LEAF_MAX, /*sah_collapse=*/c->opt_sah_collapse != 0);
+        }
         c->m_prims.alloc(3 * (size_t)total);
         c->m_map.alloc(total);
         RT3_LAUNCH_1D(k_pack_merged, total, c->stream, (const MergedRange*)d_ranges.p, (uint32_t)ranges.size(), (const uint32_t*)c->m_order.p, c->m_prims.p, c->m_map.p);
@@ -846,7 +882,7 @@ int rt3_accel_build(rt3_context_t c) {
         RT3_LAUNCH_1D(k_instance_boxes, ni + 1, c->stream, (const InstanceDev*)c->d_inst.p, (const float*)c->d_static.p, (const BlasBounds*)d_bb.p,
                       (const BlasDev*)c->d_blas.p, (const float*)c->d_keys.p, c->opt_tlas_refine, lo.p, hi.p);
         std::vector<uint32_t> sel(tl);
-        if (c->has_merged) sel.push_back(ni);
+        if (c->has_merged && !c->split) sel.push_back(ni);
         // gather the selected boxes, build, then translate the TLAS leaf order back to instance ids
         const uint32_t ns = (uint32_t)sel.size();
         DevBuf<float4> slo(ns), shi(ns);
@@ -998,7 +1034,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
     struct Chain {
         Stream main = 0, aux = 0;
         uint32_t base = 0, count = 0;
-        uint32_t* cnt = nullptr;   // [0,M): rays per depth  [M,2M): shadow rays per depth  [2M,3M): extend fetch  [3M,4M): connect fetch
+        uint32_t* cnt = nullptr;   // [0,M): rays per depth  [M,2M): shadow rays per depth  [2M,3M): extend fetch  [3M,4M): connect fetch  [4M,6M): the same for pass 2 of a split traversal
         int cur = 0, connect_pending = -1;
         Event* ev_shade = nullptr; Event* ev_connect = nullptr;
         Queues q;
@@ -1011,7 +1047,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
         const uint32_t half = (P / 2u) & ~31u;
         h.base = k == 0 ? 0u : half;
         h.count = nchains == 1 ? P : (k == 0 ? half : P - half);
-        h.cnt = c->counters.p + (size_t)k * 4 * M;
+        h.cnt = c->counters.p + (size_t)k * 6 * M;
         h.ev_shade = c->ev_shade[k]; h.ev_connect = c->ev_connect[k];
     }
     auto bind = [&](Chain& h, uint32_t depth) {
@@ -1055,7 +1091,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
             a.hit0 = h.q.hit0; a.hit_inst = h.q.hit_inst; a.contrib = nullptr; a.result = nullptr;
             a.stat = c->d_stats.p + (depth == 0 ? 0 : 1);
             a.faithful = 0;
-            launch_traverse<TRAV_EXTEND>(c, a, h.main);
+            launch_traverse<TRAV_EXTEND>(c, a, h.cnt + 4 * M + depth, h.main);
         }
         if (timing) event_record(e1, c->stream);
         for (int k = 0; k < nchains; k++) {
@@ -1084,7 +1120,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
             s.hit0 = nullptr; s.hit_inst = nullptr; s.contrib = h.q.sh3; s.result = h.q.result;
             s.stat = c->d_stats.p + 2;
             s.faithful = rs->mode == 0 ? 1u : 0u;
-            launch_traverse<TRAV_CONNECT>(c, s, overlap ? h.aux : h.main);
+            launch_traverse<TRAV_CONNECT>(c, s, h.cnt + 5 * M + depth, overlap ? h.aux : h.main);
             if (overlap) { event_record(h.ev_connect[depth & 1u], h.aux); h.connect_pending = (int)(depth & 1u); }
             h.cur ^= 1;
         }
@@ -1124,15 +1160,15 @@ int rt3_trace_device(rt3_context_t c, const void* d_rays, int n, int any_hit, vo
     RT3_REQUIRE(n >= 0 && (n == 0 || (d_rays && d_hits)), RT3_ERR_INVALID, "trace: bad argument");
     if (n == 0) return RT3_OK;
     upload_hitgroups(c);
-    dev_memset(c->trace_fetch.p, 0, sizeof(uint32_t), c->stream);
+    dev_memset(c->trace_fetch.p, 0, 2 * sizeof(uint32_t), c->stream);
     TraverseArgs a;
     a.scene = c->trav_scene();
     const float4* r = (const float4*)d_rays;
     a.rays = RayPlanes{r, r + 1, r + 2, 3u};
     a.count_ptr = nullptr; a.count = (uint32_t)n; a.fetch = c->trace_fetch.p;
     a.hit0 = (float4*)d_hits; a.hit_inst = nullptr; a.contrib = nullptr; a.result = nullptr; a.stat = nullptr; a.faithful = 0;
-    if (any_hit) launch_traverse<TRAV_TRACE_ANY>(c, a, c->stream);
-    else launch_traverse<TRAV_TRACE_CLOSEST>(c, a, c->stream);
+    if (any_hit) launch_traverse<TRAV_TRACE_ANY>(c, a, c->trace_fetch.p + 1, c->stream);
+    else launch_traverse<TRAV_TRACE_CLOSEST>(c, a, c->trace_fetch.p + 1, c->stream);
     // spline curves: internal sub-segment hits -> (segment, u along the segment)
     if (c->has_subdiv_curves) RT3_LAUNCH_1D(k_curve_hits_to_user, (uint32_t)n, c->stream, a.scene, (float4*)d_hits);
     RT3_API_END
@@ -1247,6 +1283,7 @@ int rt3_get_stats(rt3_context_t c, rt3_stats* st) {
     st->kernel_launches = g_launch_count;
     st->ms_generate = c->ms[0]; st->ms_extend = c->ms[1]; st->ms_shade = c->ms[2]; st->ms_connect = c->ms[3]; st->ms_resolve = c->ms[4]; st->ms_total = c->ms[5];
     st->error_flags = fl[0]; st->max_stack_depth = fl[1];
+    st->flattened_instances = c->flattened; st->traversal_passes = c->built && c->split ? 2u : 1u;
     RT3_API_END
 }
 int rt3_get_debug_counters(rt3_context_t c, uint32_t out[16]) {

@@ -38,16 +38,35 @@ struct TraverseArgs {
     float4* result;              // connect: per-path radiance
     unsigned long long* stat;    // ray counter to bump by count
     uint32_t faithful;           // connect: reproduce the reference's (Le*0)*last_att NaN propagation on occluded rays (mode 0)
+    // split scenes (a large merged world BLAS beside other instances) are traversed in two launches over the same rays:
+    // pass 1 = the single-level kernel on the merged BLAS, pass 2 = the general kernel on the TLAS of the remaining
+    // instances, seeded with pass 1's result (closest hit: t, ids for the tie rule; occlusion: nothing left to do).
+    // pass 1 of a connect launch leaves its verdict in the shadow ray itself (tmax = -1: occluded); 0 = the only pass
+    uint32_t pass;
 };
 
 enum { TRAV_EXTEND = 0, TRAV_CONNECT = 1, TRAV_TRACE_CLOSEST = 2, TRAV_TRACE_ANY = 3 };
 
 template <int MODE, bool SINGLE>
-RT3_HD void trav_begin(const TraverseArgs& a, uint32_t i, Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY), SINGLE>& tr) {
+RT3_HD bool trav_begin(const TraverseArgs& a, uint32_t i, Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY), SINGLE>& tr) {
     const float4 r0 = rt3_ldcs(&a.rays.r0[(size_t)i * a.rays.stride]);
     const float4 r1 = rt3_ldcs(&a.rays.r1[(size_t)i * a.rays.stride]);
     const float4 r2 = rt3_ldcs(&a.rays.r2[(size_t)i * a.rays.stride]);
     tr.init(a.scene, v3(r0), v3(r1), r0.w, r1.w, r2.x);
+    if (!SINGLE && a.pass == 2u) {  // what pass 1 found in the merged BLAS
+        if (MODE == TRAV_CONNECT) {
+            if (r1.w < 0.0f) { tr.hprim = 0; return false; }
+        } else {
+            const float4 h0 = MODE == TRAV_EXTEND ? a.hit0[i] : a.hit0[2 * (size_t)i];
+            const int hp = (int)rt3_f2u(h0.w);
+            if (hp >= 0) {
+                tr.tbest = h0.x; tr.hu = h0.y; tr.hv = h0.z; tr.hprim = hp;
+                tr.hinst = MODE == TRAV_EXTEND ? a.hit_inst[i] : (int)rt3_f2u(a.hit0[2 * (size_t)i + 1].x);
+                if (MODE == TRAV_TRACE_ANY) return false;
+            }
+        }
+    }
+    return true;
 }
 
 template <int MODE, bool SINGLE>
@@ -57,6 +76,10 @@ RT3_HD void trav_end(const TraverseArgs& a, uint32_t i, const Trav<(MODE == TRAV
         rt3_stcs(&a.hit0[i], make_float4(h.t, h.u, h.v, rt3_u2f((uint32_t)h.prim)));
         rt3_stcs(&a.hit_inst[i], h.inst);
     } else if (MODE == TRAV_CONNECT) {
+        if (SINGLE && a.pass == 1u) {  // the epilogue belongs to pass 2; an occluded ray is marked for it
+            if (h.prim >= 0) reinterpret_cast<float*>(const_cast<float4*>(&a.rays.r1[(size_t)i * a.rays.stride]))[3] = -1.0f;
+            return;
+        }
         const uint32_t path = rt3_f2u(a.rays.r2[(size_t)i * a.rays.stride].y);
         const float4 c = rt3_ldcs(&a.contrib[i]);
         if (h.prim < 0) {  // unoccluded: result += radiance * last_attenuation (raygen.cu:59)
@@ -86,9 +109,9 @@ static void k_traverse(TraverseArgs a) {
         Trav<(MODE == TRAV_CONNECT || MODE == TRAV_TRACE_ANY), SINGLE> tr;
         uint2 stack_mem[RT3_STACK_SIZE + FR_COUNT];
         tr.stack = stack_mem;
-        trav_begin<MODE, SINGLE>(a, i, tr);
         uint32_t hw = 0;
-        while (tr.step(a.scene)) { if ((uint32_t)tr.sp > hw) hw = (uint32_t)tr.sp; }
+        if (trav_begin<MODE, SINGLE>(a, i, tr))
+            while (tr.step(a.scene)) { if ((uint32_t)tr.sp > hw) hw = (uint32_t)tr.sp; }
         if (hw > *a.scene.max_stack) *a.scene.max_stack = hw;
         trav_end<MODE, SINGLE>(a, i, tr);
     }
@@ -141,8 +164,8 @@ __global__ void __launch_bounds__(RT3_TRAV_THREADS, SINGLE ? RT3_TRAV_MIN_BLOCKS
                 const uint32_t cand = base + __popc(idle & lt_mask);
                 if (cand < n) {
                     my = cand;
-                    trav_begin<MODE, SINGLE>(a, my, tr);
-                    active = true;
+                    active = trav_begin<MODE, SINGLE>(a, my, tr);
+                    if (!active) trav_end<MODE, SINGLE>(a, my, tr);   // settled by pass 1
                 }
             }
             if (base + nidle >= n) exhausted = true;
@@ -247,18 +270,36 @@ RT3_GLOBAL(k_pack_curves, const float4* cp, const int32_t* seg, const uint32_t* 
     out[3 * (size_t)j + 1] = cp[seg[p] + 1];
     out[3 * (size_t)j + 2] = make_float4(rt3_u2f(p), 0.0f, 0.0f, 0.0f);
 }
-// merged world BLAS: records of all identity static mesh instances, primitive id = merged index
-struct MergedRange { uint32_t first, inst; const float* verts; const int32_t* idx; };
+// merged world BLAS: records of the static triangle-mesh instances that are traversed without an instance transform —
+// identity instances as they are, the others ("flattened") with their vertices brought to world space once, here:
+// x' = ((m0 x + m1 y) + m2 z) + m3 per row, unfused (the oracle rebuilds the same vertices).  Primitive id = merged index.
+struct MergedRange { uint32_t first, inst; const float* verts; const int32_t* idx; uint32_t has_xf; float xf[12]; };
+RT3_HD float3 merged_vertex(const MergedRange& r, uint32_t p, int corner) {
+    const float3 v = ld3(r.verts + 3 * (size_t)r.idx[3 * (size_t)p + corner]);
+    if (!r.has_xf) return v;
+    const float* m = r.xf;
+    return v3(((m[0] * v.x + m[1] * v.y) + m[2] * v.z) + m[3], ((m[4] * v.x + m[5] * v.y) + m[6] * v.z) + m[7], ((m[8] * v.x + m[9] * v.y) + m[10] * v.z) + m[11]);
+}
+RT3_HD uint32_t merged_range_of(const MergedRange* ranges, uint32_t nranges, uint32_t g) {
+    uint32_t lo = 0, hi = nranges;  // last range with first <= g
+    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (ranges[mid].first <= g) lo = mid; else hi = mid; }
+    return lo;
+}
+RT3_GLOBAL(k_merged_boxes, const MergedRange* ranges, uint32_t nranges, float4* lo, float4* hi) {
+    const uint32_t g = RT3_THREAD_ID();
+    if (g >= rt3_n_) return;
+    const MergedRange& r = ranges[merged_range_of(ranges, nranges, g)];
+    const float3 a = merged_vertex(r, g - r.first, 0), b = merged_vertex(r, g - r.first, 1), c = merged_vertex(r, g - r.first, 2);
+    lo[g] = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.0f);
+    hi[g] = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.0f);
+}
 RT3_GLOBAL(k_pack_merged, const MergedRange* ranges, uint32_t nranges, const uint32_t* order, float4* out, uint2* map) {
     const uint32_t j = RT3_THREAD_ID();
     if (j >= rt3_n_) return;
     const uint32_t g = order[j];
-    uint32_t lo = 0, hi = nranges;  // last range with first <= g
-    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (ranges[mid].first <= g) lo = mid; else hi = mid; }
-    const MergedRange r = ranges[lo];
+    const MergedRange& r = ranges[merged_range_of(ranges, nranges, g)];
     const uint32_t p = g - r.first;
-    const float3 a = ld3(r.verts + 3 * (size_t)r.idx[3 * (size_t)p]), b = ld3(r.verts + 3 * (size_t)r.idx[3 * (size_t)p + 1]),
-                 c = ld3(r.verts + 3 * (size_t)r.idx[3 * (size_t)p + 2]);
+    const float3 a = merged_vertex(r, p, 0), b = merged_vertex(r, p, 1), c = merged_vertex(r, p, 2);
     out[3 * (size_t)j] = make_float4(a.x, a.y, a.z, rt3_u2f(g));
     out[3 * (size_t)j + 1] = make_float4(b.x, b.y, b.z, 0.0f);
     out[3 * (size_t)j + 2] = make_float4(c.x, c.y, c.z, 0.0f);

@@ -15,7 +15,7 @@ _LIB = os.path.join(_ROOT, "oracle", "_ref", "librt3o.so")
 
 def build_oracle():
     """(Re)build librt3o.so from oracle/*.cpp when missing or stale (g++ only, a few seconds)."""
-    srcs = [os.path.join(_ROOT, "oracle", f) for f in ("rt3o.cpp", "rt3o.h", "rt3o_math.hpp", "rt3o_prims.hpp")]
+    srcs = [os.path.join(_ROOT, "oracle", f) for f in ("rt3o.cpp", "rt3o.h", "rt3o_math.hpp", "rt3o_prims.hpp", "rt3o_curve.hpp")]
     srcs.append(os.path.join(_ROOT, "include", "rt3.h"))
     if os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in srcs):
         return _LIB
@@ -117,6 +117,12 @@ class OracleScene:
     def append_animated_instance(self, blas, keys, t_begin, t_end, static_xform):
         k, x = _f32(keys), _f32(static_xform)
         return self._chk(self.L.rt3o_accel_append_animated_instance(self.s, C.c_int(blas), fptr(k), C.c_int(len(k)), C.c_float(t_begin), C.c_float(t_end), fptr(x)))
+
+    def set_option(self, key, value):
+        """the build options that change results: "flatten" (process-wide in the oracle, read by accel_build); the kernels'
+        tuning switches ("split", "tlas_sah", ...) leave results alone and mean nothing here"""
+        if key == "flatten" or (key == "merge_identity" and not value):   # without the merged BLAS nothing is flattened
+            self.L.rt3o_set_flatten(C.c_int(int(value)))
 
     def accel_build(self):
         self._chk(self.L.rt3o_accel_build(self.s))

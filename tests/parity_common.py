@@ -93,9 +93,17 @@ def check_render(backend, oracle, desc, subframes=2, spl=8, width=None, height=N
     return ao
 
 
-def build_pair(desc, backend):
+def build_pair(desc, backend, options=None):
+    """the scene in the backend under test and in a fresh oracle; `options`: rt3_set_option switches applied to both before
+    the build (the oracle keeps the ones that change results — "flatten" — and is put back to its default afterwards)"""
     o = OracleScene()
-    scenes.replay(desc, o)
+    for k, v in (options or {}).items():
+        o.set_option(k, v)
+        backend.set_option(k, v)
+    try:
+        scenes.replay(desc, o)
+    finally:
+        o.set_option("flatten", 1)
     scenes.replay(desc, backend)
     return o
 

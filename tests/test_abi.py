@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(product_lib):
 def test_struct_sizes_match_header():
     assert C.sizeof(_abi.RenderSettings) == 4 * 4 + 12 * 4 + 2 * 4 + 3 * 4 + 4
     assert _abi.RAY_DTYPE.itemsize == 48 and _abi.HIT_DTYPE.itemsize == 32
-    assert C.sizeof(_abi.Stats) == 5 * 8 + 6 * 4 + 2 * 4
+    assert C.sizeof(_abi.Stats) == 5 * 8 + 6 * 4 + 4 * 4
 
 
 def test_product_has_no_oracle_or_emulation_inside(product_lib):

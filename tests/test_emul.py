@@ -142,3 +142,19 @@ def test_spline_tessellation_tolerance(emul_lib):
     from parity_common import check_spline_tessellation
     with Context(0, lib_path=emul_lib) as e:
         check_spline_tessellation(e)
+
+
+@pytest.mark.parametrize("options", [{"split": 2}, {"split": 0}, {"flatten": 0}, {"flatten": 0, "split": 2}, {"merge_identity": 0, "flatten": 0}],
+                         ids=lambda o: ",".join("%s=%d" % kv for kv in o.items()))
+@pytest.mark.parametrize("name", ["instanced", "motion", "deforming", "splines"])
+def test_flatten_and_split_variants_match_oracle(emul_lib, name, options):
+    """how static instances reach the kernels — flattened into the merged world BLAS or entered through the TLAS, in one
+    launch or two (single-level kernel, then the rest seeded with its result) — changes nothing the oracle can see;
+    `flatten` itself changes the hit arithmetic (world-space vertices) and is mirrored by the oracle"""
+    desc = SMALL[name]()
+    with Context(0, lib_path=emul_lib) as e:
+        o = build_pair(desc, e, options)
+        uvw = e.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, desc.width / desc.height)
+        rays = np.concatenate([camera_rays(desc, uvw, 40, 24), random_rays(desc, 1500, seed=5)])
+        check_trace(e, o, rays)
+        check_render(e, o, desc, subframes=1)

@@ -13,9 +13,11 @@ from rendertoy3c_b200.api import Context, camera_rays, make_settings
 pytestmark = pytest.mark.gpu
 
 
-def _fullsize(desc, n_rays, brute, width, height):
+def _fullsize(desc, n_rays, brute, width, height, options=None, expect=None):
     with Context(0) as g:
-        o = build_pair(desc, g)
+        o = build_pair(desc, g, options)
+        for k, v in (expect or {}).items():
+            assert g.stats()[k] == v, (k, g.stats()[k], v)
         uvw = o.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, width / height)
         rays = np.concatenate([camera_rays(desc, uvw, 256, 144), random_rays(desc, n_rays, 41)])
         ho = check_trace(g, o, rays, accel=1)
@@ -30,7 +32,13 @@ def test_c2_terrain_1m_triangles():
 
 
 def test_c3_thousand_instances_plus_spheres():
-    _fullsize(scenes.instanced(), 100000, 24, 320, 180)          # 1000 x 100,352-triangle BLAS + 1000 spheres
+    # 1000 x 100,352-triangle instances + 1000 spheres: the instances are flattened into one 100 M-triangle world BLAS (pass 1),
+    # the spheres stay behind a TLAS (pass 2)
+    _fullsize(scenes.instanced(), 100000, 24, 320, 180, expect={"flattened_instances": 1000, "traversal_passes": 2})
+
+
+def test_c3_thousand_instances_kept_as_instances():
+    _fullsize(scenes.instanced(), 100000, 24, 320, 180, options={"flatten": 0}, expect={"flattened_instances": 0})   # one BLAS, 1000 TLAS leaves
 
 
 def test_c4_motion_blur_tris_spheres_curves():

@@ -176,3 +176,18 @@ def test_spline_tessellation_tolerance(product_lib):
     from parity_common import check_spline_tessellation
     with Context(0) as e:
         check_spline_tessellation(e)
+
+
+@pytest.mark.parametrize("options", [{"split": 2}, {"split": 0}, {"flatten": 0}, {"flatten": 0, "split": 2}, {"merge_identity": 0, "flatten": 0}],
+                         ids=lambda o: ",".join("%s=%d" % kv for kv in o.items()))
+@pytest.mark.parametrize("name", ["instanced", "motion", "deforming", "splines"])
+def test_flatten_and_split_variants_match_oracle(product_lib, name, options):
+    """static instances flattened into the merged world BLAS or entered through the TLAS, traversed in one launch or two
+    (single-level kernel, then the rest seeded with its result): bit-identical to the oracle either way"""
+    desc = SMALL[name]()
+    with Context(0) as e:
+        o = build_pair(desc, e, options)
+        uvw = e.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, desc.width / desc.height)
+        rays = np.concatenate([camera_rays(desc, uvw, 40, 24), random_rays(desc, 1500, seed=5)])
+        check_trace(e, o, rays)
+        check_render(e, o, desc, subframes=1)

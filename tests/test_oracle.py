@@ -415,3 +415,37 @@ def test_spline_tessellation_tolerance():
     """the oracle's adaptive split of spline segments keeps hits within the stated tolerance of the true curve"""
     from parity_common import check_spline_tessellation
     check_spline_tessellation(ob.OracleScene())
+
+
+def test_flattened_instances_bvh_equals_bruteforce_far_from_the_origin():
+    """flattened instances are culled with the object-space BVH but tested in world space; the culling slack must cover the
+    rounding of the ray transform where it is worst — small, rotated, sheared copies far from the origin, and big ones"""
+    rng = np.random.RandomState(31)
+    blob = scenes.grid_mesh(24, 24, scenes._blob_pos)
+    inst, centres, radii = [], [], []
+    for k in range(10):
+        c = (rng.rand(3) - 0.5) * [2000.0, 600.0, 2000.0]
+        sc = [0.01, 0.05, 1.0, 40.0, 0.3][k % 5]
+        m = scenes.rigid(rng, 180.0, c, sc).reshape(3, 4)
+        if k % 2:   # anisotropic scale + shear
+            m[:, :3] = m[:, :3] @ np.array([[1.0, 0.4, 0.0], [0.0, 2.5, 0.0], [0.3, 0.0, 0.6]], np.float32)
+        inst.append(scenes.Instance(0, xform=m.reshape(12).astype(np.float32)))
+        centres.append(c)
+        radii.append(sc)
+    desc = scenes.SceneDesc("far_instances", [blob], inst, [], scenes.Camera(eye=(0, 0, 3000), lookat=(0, 0, 0), fovy=45.0), 8, 8, 1, 1)
+    o = ob.OracleScene()
+    scenes.replay(desc, o)
+    n = 20000
+    rays = np.zeros(n, dtype=RAY_DTYPE)
+    which = rng.randint(0, len(inst), n)
+    c = np.asarray(centres)[which]
+    r = np.asarray(radii)[which][:, None]
+    target = c + (rng.rand(n, 3) - 0.5) * 1.6 * r
+    origin = np.where(rng.rand(n, 1) < 0.5, c + rng.randn(n, 3) * 6.0 * r, (rng.rand(n, 3) - 0.5) * 3000.0)
+    rays["o"] = origin.astype(np.float32)
+    rays["d"] = (target - origin).astype(np.float32)
+    rays["tmin"], rays["tmax"] = 1e-4, 1e16
+    a, b = o.trace(rays, accel=0), o.trace(rays, accel=1)
+    assert (a["prim"] >= 0).mean() > 0.3
+    assert a.tobytes() == b.tobytes()
+    assert np.array_equal(o.trace(rays, any_hit=True, accel=0)["prim"] >= 0, o.trace(rays, any_hit=True, accel=1)["prim"] >= 0)
