@@ -324,8 +324,8 @@ def traversal_counters(desc, local):
     c = g.debug_counters()
     st = g.stats()
     g.close()
-    rays = max(1, int(c[5]))
-    return {"wide_nodes_per_ray": c[2] / rays, "primitive_tests_per_ray": c[3] / rays, "rounds_per_ray": c[4] / rays, "instance_entries_per_ray": c[13] / rays, "rays_counted": rays,
+    rays = max(1, int(c[5]) // max(1, st["traversal_passes"]))   # a split traversal finishes every ray twice (pass 1, pass 2)
+    return {"wide_nodes_per_ray": c[2] / rays, "primitive_tests_per_ray": c[3] / rays, "rounds_per_ray": c[4] / rays, "instance_entries_per_ray": c[13] / rays, "rays_counted": rays, "traversal_passes": st["traversal_passes"],
             "rays_by_type": {k: st["rays_" + k] for k in ("primary", "bounce", "shadow")}, "film": "%dx%d x %d spl, all ray types of one subframe" % (w, h, SPL),
             "library": "rendertoy3c_b200/librt3_stats.so (-DRT3_STATS build of the same sources; not the timed library)"}
 
