@@ -993,6 +993,15 @@ int rt3o_accel_append_animated_instance(rt3o_scene* s, int blas, const float* ke
     return add_instance(s, blas, static_xform, keys, nkeys, t_begin, t_end);
     RT3O_CATCH(-1)
 }
+// finite and not (numerically) singular: the same decision, in the same double arithmetic, as the product's rt3_accel_build
+static bool flattenable(const float* m) {
+    for (int k = 0; k < 12; k++) if (!std::isfinite(m[k])) return false;
+    const double det = (double)m[0] * ((double)m[5] * (double)m[10] - (double)m[6] * (double)m[9])
+                     - (double)m[1] * ((double)m[4] * (double)m[10] - (double)m[6] * (double)m[8])
+                     + (double)m[2] * ((double)m[4] * (double)m[9] - (double)m[5] * (double)m[8]);
+    return std::fabs(det) >= 1e-30;
+}
+
 int rt3o_accel_build(rt3o_scene* s) {
     RT3O_TRY
     if (!s || s->inst.empty()) { g_err = "accel_build: no instances"; return -4; }
@@ -1005,12 +1014,12 @@ int rt3o_accel_build(rt3o_scene* s) {
         for (Instance& in : s->inst) {
             const Blas& b = *s->blas[in.blas];
             in.flat = false;
-            if (in.nkeys == 0 && b.type == PRIM_TRI && b.vkeys == 1) sum += (uint64_t)b.nprims;
+            if (in.nkeys == 0 && b.type == PRIM_TRI && b.vkeys == 1 && (in.identity || flattenable(in.stat.m))) sum += (uint64_t)b.nprims;
         }
         if (g_flatten && sum < (1ull << 27))
             for (Instance& in : s->inst) {
                 const Blas& b = *s->blas[in.blas];
-                if (in.nkeys != 0 || in.identity || b.type != PRIM_TRI || b.vkeys != 1) continue;
+                if (in.nkeys != 0 || in.identity || b.type != PRIM_TRI || b.vkeys != 1 || !flattenable(in.stat.m)) continue;
                 in.flat = true;
                 const float bx = std::max(fabsf(b.bounds.lo.x), fabsf(b.bounds.hi.x)), by = std::max(fabsf(b.bounds.lo.y), fabsf(b.bounds.hi.y)),
                             bz = std::max(fabsf(b.bounds.lo.z), fabsf(b.bounds.hi.z));

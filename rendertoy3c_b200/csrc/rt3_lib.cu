@@ -724,6 +724,17 @@ int rt3_accel_append_animated_instance(rt3_context_t c, rt3_handle_t blas, const
     RT3_API_END
 }
 
+// a transform whose triangles may be intersected in world space: finite and not (numerically) singular — a collapsed instance
+// keeps its object-space semantics, where the inverse is what it is.  Evaluated in double from the float entries, in this
+// order, so that the oracle (rt3o_accel_build) takes the same decision
+static bool flattenable(const float* m) {
+    for (int k = 0; k < 12; k++) if (!std::isfinite(m[k])) return false;
+    const double det = (double)m[0] * ((double)m[5] * (double)m[10] - (double)m[6] * (double)m[9])
+                     - (double)m[1] * ((double)m[4] * (double)m[10] - (double)m[6] * (double)m[8])
+                     + (double)m[2] * ((double)m[4] * (double)m[9] - (double)m[5] * (double)m[8]);
+    return std::fabs(det) >= 1e-30;
+}
+
 int rt3_accel_build(rt3_context_t c) {
     RT3_API_BEGIN
     use_device(c);
@@ -744,7 +755,7 @@ int rt3_accel_build(rt3_context_t c) {
         for (uint32_t i = 0; i < ni; i++) {
             const InstanceHost& in = c->inst[i];
             const bool identity = in.nkeys == 0 && memcmp(in.xform, ident, sizeof(ident)) == 0;
-            if (c->opt_merge && in.nkeys == 0 && (identity || flatten) && c->geoms[in.blas]->type == PRIM_TRI) { merged.push_back(i); sum += c->geoms[in.blas]->nprims; }
+            if (c->opt_merge && in.nkeys == 0 && (identity || (flatten && flattenable(in.xform))) && c->geoms[in.blas]->type == PRIM_TRI) { merged.push_back(i); sum += c->geoms[in.blas]->nprims; }
             else tl.push_back(i);
         }
         return sum < (1ull << 27);

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from parity_common import SMALL, build_pair, check_render, check_trace, random_rays
+from rendertoy3c_b200 import scenes
 from rendertoy3c_b200.api import Context, camera_rays
 
 
@@ -158,3 +159,17 @@ def test_flatten_and_split_variants_match_oracle(emul_lib, name, options):
         rays = np.concatenate([camera_rays(desc, uvw, 40, 24), random_rays(desc, 1500, seed=5)])
         check_trace(e, o, rays)
         check_render(e, o, desc, subframes=1)
+
+
+def test_collapsed_instance_is_not_flattened(emul_lib):
+    """an instance whose transform is singular (a mesh squashed into a plane) or not finite keeps its object-space semantics in
+    the kernels and in the oracle alike; its neighbours are flattened as usual"""
+    desc = SMALL["instanced"]()
+    m = np.array(desc.instances[0].xform, np.float32).reshape(3, 4)
+    m[:, 2] = 0.0                      # rank 2
+    desc.instances[0].xform = m.reshape(12)
+    with Context(0, lib_path=emul_lib) as e:
+        o = build_pair(desc, e)
+        assert e.stats()["flattened_instances"] == sum(1 for i in desc.instances[1:] if desc.geoms[i.geom].kind == "mesh" and i.keys is None and not np.array_equal(np.asarray(i.xform, np.float32), scenes.IDENTITY))
+        uvw = e.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, desc.width / desc.height)
+        check_trace(e, o, np.concatenate([camera_rays(desc, uvw, 40, 24), random_rays(desc, 1500, seed=6)]))
