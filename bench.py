@@ -270,12 +270,14 @@ def time_subframes(g, make, warmup, steps, stream, torch):
     return e0.elapsed_time(e1), g.stats()
 
 
-def run_config(name, desc, local, torch, steps=3, warmup=2, spl=SPL, max_depth=None):
+def run_config(name, desc, local, torch, steps=3, warmup=2, spl=SPL, max_depth=None, options=None, counters=True):
     """one BASELINE config measured like the headline: own context, device-resident, CUDA events on the library's stream"""
     from rendertoy3c_b200 import scenes
     from rendertoy3c_b200.api import Context, make_settings
     t0 = time.perf_counter()
     g = Context(local)
+    for k, v in (options or {}).items():
+        g.set_option(k, v)
     scenes.replay(desc, g)
     g.sync()
     build_s = time.perf_counter() - t0
@@ -301,7 +303,10 @@ def run_config(name, desc, local, torch, steps=3, warmup=2, spl=SPL, max_depth=N
            "stage_ms": {k: s[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_connect", "ms_resolve", "ms_total")},
            "upload_and_build_s": build_s, "flattened_instances": s["flattened_instances"], "traversal_passes": s["traversal_passes"]}
     g.close()
-    out["traversal_counters"] = traversal_counters(desc, local)
+    if options:
+        out["options"] = options
+    if counters:
+        out["traversal_counters"] = traversal_counters(desc, local)
     return out
 
 
@@ -612,6 +617,8 @@ def run_rt3(args):
                 cfg = {}
                 cfg["C1"] = run_config("C1", scenes.cornell(width=512, height=512), local, torch, steps=4, warmup=2)
                 cfg["C3"] = run_config("C3", scenes.instanced(width=1920, height=1080), local, torch)
+                # the same scene with its 1000 instances kept as instances (one BLAS, 1000 TLAS leaves): the two-level path proper
+                cfg["C3_instances_kept"] = run_config("C3", scenes.instanced(width=1920, height=1080), local, torch, options={"flatten": 0}, counters=False)
                 cfg["C4"] = run_config("C4", scenes.motion(width=1920, height=1080), local, torch)
                 out["configs"] = cfg
             if not args.no_cpu_baseline:
