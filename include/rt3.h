@@ -57,7 +57,7 @@ typedef struct {
     float ms_generate, ms_extend, ms_shade, ms_connect, ms_resolve; /* CUDA-event time of the LAST subframe, per stage (0 if timing disabled) */
     float ms_total;
     uint32_t max_stack_depth;                        /* traversal stack high-water mark; recorded by diagnostic (-DRT3_STATS) builds only, 0 otherwise */
-    uint32_t error_flags;                            /* bit0: a traversal stack overflowed and dropped a subtree.  rt3_trace and rt3_download_* fail with RT3_ERR_STATE while it is set; rt3_reset_stats clears it */
+    uint32_t error_flags;                            /* bit0: a traversal stack overflowed and dropped a subtree: rt3_trace and rt3_download_* fail with RT3_ERR_STATE while it is set.  bit1: a launch with max_depth <= 0 (unbounded, like the reference) reached the 1022 bounces the library has slots for with paths still alive; they were ended there (informative).  rt3_reset_stats clears both */
     uint32_t flattened_instances;                    /* transformed static mesh instances the last rt3_accel_build merged into the world-space BLAS ("flatten") */
     uint32_t traversal_passes;                       /* launches per ray batch: 1, or 2 when the merged BLAS and the remaining instances are traversed one after the other ("split") */
 } rt3_stats;

@@ -93,6 +93,9 @@ struct rt3_context {
     int opt_flatten = 1;   // static, transformed triangle-mesh instances join the merged world BLAS (vertices transformed once, at build)
     int opt_split = 1;     // merged BLAS beside other instances: 0 = one TLAS over both, 2 = always two passes (single-level kernel, then the rest), 1 = two passes when the merged BLAS is large
     bool split = false;
+    uint32_t host_flags = 0;   // error_flags bits raised on the host (bit 1: an unbounded-depth launch ran out of depth slots)
+    DevBuf<float4> q_rays, q_hits;   // staging of rt3_trace / rt3_get_local_geometry (grown on demand, kept between calls)
+    DevBuf<float> q_out;
     uint32_t flattened = 0;  // instances flattened by the last build
     int opt_tlas_sah = 1;
     int opt_tlas_leaf = 1;      // instances per TLAS leaf child (r02j, C3 / C4 Mrays/s: 3 -> 762 / 957, 2 -> 785 / 927, 1 -> 815 / 953: an own box per instance culls more entries than the extra TLAS nodes cost)
@@ -1145,6 +1148,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
             d2h(&nnext, ch[0].q.n_next, sizeof(nnext), c->stream);
             stream_sync(c->stream);
             if (nnext == 0) break;
+            if (depth + 1 == depth_limit) c->host_flags |= 2u;   // paths still alive where the depth slots end: reported, not silent
         }
     }
     for (int k = 0; k < nchains; k++) {  // join: resolve (context stream) waits for every chain's last kernels
@@ -1192,7 +1196,9 @@ int rt3_trace(rt3_context_t c, const rt3_ray* rays, int n, int any_hit, rt3_hit*
     RT3_REQUIRE(c && c->built, RT3_ERR_STATE, "trace: rt3_accel_build has not been called");
     RT3_REQUIRE(n >= 0 && (n == 0 || (rays && hits)), RT3_ERR_INVALID, "trace: bad argument");
     if (n == 0) return RT3_OK;
-    DevBuf<float4> d_rays(3 * (size_t)n), d_hits(2 * (size_t)n);
+    c->q_rays.ensure(3 * (size_t)n);
+    c->q_hits.ensure(2 * (size_t)n);
+    DevBuf<float4>&d_rays = c->q_rays, &d_hits = c->q_hits;
     h2d(d_rays.p, rays, sizeof(rt3_ray) * (size_t)n, c->stream);
     const int rc = rt3_trace_device(c, d_rays.p, n, any_hit, d_hits.p);
     if (rc != RT3_OK) return rc;
@@ -1225,8 +1231,11 @@ int rt3_get_local_geometry(rt3_context_t c, const rt3_ray* rays, const rt3_hit* 
             }
         hits = internal.data();
     }
-    DevBuf<float4> d_rays(3 * (size_t)n), d_hits(2 * (size_t)n);
-    DevBuf<float> d_out(27 * (size_t)n);
+    c->q_rays.ensure(3 * (size_t)n);
+    c->q_hits.ensure(2 * (size_t)n);
+    c->q_out.ensure(27 * (size_t)n);
+    DevBuf<float4>&d_rays = c->q_rays, &d_hits = c->q_hits;
+    DevBuf<float>& d_out = c->q_out;
     h2d(d_rays.p, rays, sizeof(rt3_ray) * (size_t)n, c->stream);
     h2d(d_hits.p, hits, sizeof(rt3_hit) * (size_t)n, c->stream);
     RT3_LAUNCH_1D(k_local_geometry, (uint32_t)n, c->stream, c->trav_scene(), (const float4*)d_rays.p, (const float4*)d_hits.p, d_out.p);
@@ -1293,7 +1302,7 @@ int rt3_get_stats(rt3_context_t c, rt3_stats* st) {
     st->samples = c->samples;
     st->kernel_launches = g_launch_count;
     st->ms_generate = c->ms[0]; st->ms_extend = c->ms[1]; st->ms_shade = c->ms[2]; st->ms_connect = c->ms[3]; st->ms_resolve = c->ms[4]; st->ms_total = c->ms[5];
-    st->error_flags = fl[0]; st->max_stack_depth = fl[1];
+    st->error_flags = fl[0] | c->host_flags; st->max_stack_depth = fl[1];
     st->flattened_instances = c->flattened; st->traversal_passes = c->built && c->split ? 2u : 1u;
     RT3_API_END
 }
@@ -1312,6 +1321,7 @@ int rt3_reset_stats(rt3_context_t c) {
     RT3_REQUIRE(c, RT3_ERR_INVALID, "reset_stats: null context");
     dev_memset(c->d_stats.p, 0, c->d_stats.bytes(), c->stream);
     dev_memset(c->d_flags.p, 0, 2 * sizeof(uint32_t), c->stream);   // error word + stack high-water mark
+    c->host_flags = 0;
     c->samples = 0;
     stream_sync(c->stream);
     RT3_API_END

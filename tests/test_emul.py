@@ -7,7 +7,7 @@ import pytest
 
 from parity_common import SMALL, build_pair, check_render, check_trace, random_rays
 from rendertoy3c_b200 import scenes
-from rendertoy3c_b200.api import Context, camera_rays
+from rendertoy3c_b200.api import Context, camera_rays, make_settings
 
 
 @pytest.mark.parametrize("name", sorted(SMALL))
@@ -173,3 +173,27 @@ def test_collapsed_instance_is_not_flattened(emul_lib):
         assert e.stats()["flattened_instances"] == sum(1 for i in desc.instances[1:] if desc.geoms[i.geom].kind == "mesh" and i.keys is None and not np.array_equal(np.asarray(i.xform, np.float32), scenes.IDENTITY))
         uvw = e.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, desc.width / desc.height)
         check_trace(e, o, np.concatenate([camera_rays(desc, uvw, 40, 24), random_rays(desc, 1500, seed=6)]))
+
+
+def test_unbounded_depth_running_out_of_slots_is_reported(emul_lib):
+    """max_depth <= 0 means "until the path dies" (the reference has no bound); the library has 1022 depth slots.  Inside a
+    closed white box no path dies: the launch ends them at the last slot and says so in error_flags bit 1"""
+    s = 1.0
+    q = [[[-s, -s, -s], [s, -s, -s], [s, -s, s], [-s, -s, s]], [[-s, s, -s], [-s, s, s], [s, s, s], [s, s, -s]],
+         [[-s, -s, -s], [-s, -s, s], [-s, s, s], [-s, s, -s]], [[s, -s, -s], [s, s, -s], [s, s, s], [s, -s, s]],
+         [[-s, -s, -s], [-s, s, -s], [s, s, -s], [s, -s, -s]], [[-s, -s, s], [s, -s, s], [s, s, s], [-s, s, s]]]
+    box = scenes._quad_mesh(q)
+    lamp = scenes._quad_mesh([[[-0.2, 0.99, -0.2], [0.2, 0.99, -0.2], [0.2, 0.99, 0.2], [-0.2, 0.99, 0.2]]])
+    desc = scenes.SceneDesc("closed_box", [box, lamp], [scenes.Instance(0, diffuse=(1.0, 1.0, 1.0)), scenes.Instance(1, diffuse=(1.0, 1.0, 1.0), emission=(1.0, 1.0, 1.0))],
+                            [], scenes.Camera(eye=(0.0, 0.0, 0.5), lookat=(0.0, 0.0, -1.0), fovy=60.0), 8, 8, 1, 0)
+    with Context(0, lib_path=emul_lib) as e:
+        scenes.replay(desc, e)
+        uvw = e.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, 1.0)
+        e.launch_subframe(make_settings(desc, uvw, 0, samples_per_launch=1, max_depth=0))
+        e.sync()
+        st = e.stats()
+        assert st["error_flags"] & 2 and not st["error_flags"] & 1
+        assert st["rays_bounce"] > 1000
+        e.download_accum()          # informative only: the image is still handed out
+        e.reset_stats()
+        assert e.stats()["error_flags"] == 0

@@ -45,6 +45,15 @@ def test_c4_motion_blur_tris_spheres_curves():
     _fullsize(scenes.motion(), 100000, 48, 320, 180)             # 64 two-key instances, 256 moving spheres, 10k curve segments
 
 
+def test_c2_full_1080p_subframe_bit_identical():
+    """the headline workload as it is timed — 1,002,530 triangles, 1920x1080, 8 samples per pixel, depth 8: 16.6 M paths, ~41 M
+    rays — against the oracle on all host cores: every float of the accumulation buffer, every ray counter"""
+    desc = scenes.terrain()
+    with Context(0) as g:
+        o = build_pair(desc, g)
+        check_render(g, o, desc, subframes=1, width=1920, height=1080)
+
+
 def test_c2_full_film_properties():
     """1920x1080, 8 spl: same input twice -> identical bits; subframes {0,1} rendered as one context or as
     two sample partitions (SUM mode) agree; device ray counters add up."""
