@@ -673,6 +673,7 @@ inline bool load_psd(const std::vector<uint8_t>& f, Texture& t, std::string& why
     if (compression > 1) { why = "unknown PSD compression"; return false; }
     const size_t count = (size_t)W * H;
     std::vector<uint8_t> top(4 * count);
+    if (count == 0) { store_flipped(top, (int)W, (int)H, t); return true; }
     if (compression) s.skip((long)H * channels * 2);   // byte counts of the packed rows
     for (int ch = 0; ch < 4; ++ch) {
         uint8_t* d = top.data() + ch;
@@ -728,6 +729,7 @@ inline bool load_pic(const std::vector<uint8_t>& f, Texture& t, std::string& why
         if (size != 8) { why = "PIC packet is not 8 bits per channel"; return false; }
     }
     std::vector<uint8_t> top((size_t)4 * W * H, 255);
+    if (top.empty()) { store_flipped(top, W, H, t); return true; }   // no texels: the rows read nothing
     bool short_file = false;
     auto read_value = [&](int channels, uint8_t* d) {   // 0x80 red, 0x40 green, 0x20 blue, 0x10 alpha
         for (int i = 0; i < 4; ++i)
@@ -1228,23 +1230,28 @@ struct JpegDec {
         return true;
     }
 
+    // 32-bit arithmetic that wraps, as stb's int arithmetic does on the two's-complement machines it runs on: damaged files
+    // reach coefficients whose products leave the int range (valid ones never do), and the bytes should still be stb's
+    static int wadd(int a, int b) { return (int)((uint32_t)a + (uint32_t)b); }
+    static int wsub(int a, int b) { return (int)((uint32_t)a - (uint32_t)b); }
+    static int wmul(int a, int b) { return (int)((uint32_t)a * (uint32_t)b); }
     // 1-D pass of the integer inverse DCT on s[0..7]; returns the even part in x[] and the odd part in t[]
     static void idct_1d(const int s[8], int x[4], int t[4]) {
         int p2 = s[2], p3 = s[6];
-        int p1 = (p2 + p3) * 2217;
-        const int t2 = p1 + p3 * -7567, t3 = p1 + p2 * 3135;
+        int p1 = wmul(wadd(p2, p3), 2217);
+        const int t2 = wadd(p1, wmul(p3, -7567)), t3 = wadd(p1, wmul(p2, 3135));
         p2 = s[0]; p3 = s[4];
-        const int t0 = (p2 + p3) * 4096, t1 = (p2 - p3) * 4096;
-        x[0] = t0 + t3; x[3] = t0 - t3; x[1] = t1 + t2; x[2] = t1 - t2;
+        const int t0 = wmul(wadd(p2, p3), 4096), t1 = wmul(wsub(p2, p3), 4096);
+        x[0] = wadd(t0, t3); x[3] = wsub(t0, t3); x[1] = wadd(t1, t2); x[2] = wsub(t1, t2);
         int o0 = s[7], o1 = s[5], o2 = s[3], o3 = s[1];
-        p3 = o0 + o2;
-        int p4 = o1 + o3;
-        p1 = o0 + o3; p2 = o1 + o2;
-        const int p5 = (p3 + p4) * 4816;
-        o0 *= 1223; o1 *= 8410; o2 *= 12586; o3 *= 6149;
-        p1 = p5 + p1 * -3685; p2 = p5 + p2 * -10497;
-        p3 *= -8034; p4 *= -1597;
-        t[3] = o3 + p1 + p4; t[2] = o2 + p2 + p3; t[1] = o1 + p2 + p4; t[0] = o0 + p1 + p3;
+        p3 = wadd(o0, o2);
+        int p4 = wadd(o1, o3);
+        p1 = wadd(o0, o3); p2 = wadd(o1, o2);
+        const int p5 = wmul(wadd(p3, p4), 4816);
+        o0 = wmul(o0, 1223); o1 = wmul(o1, 8410); o2 = wmul(o2, 12586); o3 = wmul(o3, 6149);
+        p1 = wadd(p5, wmul(p1, -3685)); p2 = wadd(p5, wmul(p2, -10497));
+        p3 = wmul(p3, -8034); p4 = wmul(p4, -1597);
+        t[3] = wadd(wadd(o3, p1), p4); t[2] = wadd(wadd(o2, p2), p3); t[1] = wadd(wadd(o1, p2), p4); t[0] = wadd(wadd(o0, p1), p3);
     }
     static uint8_t clamp8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
     static void idct_block(uint8_t* out, int stride, const int16_t d[64]) {
@@ -1260,21 +1267,21 @@ struct JpegDec {
             const int s[8] = {c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56]};
             int x[4], t[4];
             idct_1d(s, x, t);
-            for (int q = 0; q < 4; ++q) x[q] += 512;
-            v[0] = (x[0] + t[3]) >> 10; v[56] = (x[0] - t[3]) >> 10;
-            v[8] = (x[1] + t[2]) >> 10; v[48] = (x[1] - t[2]) >> 10;
-            v[16] = (x[2] + t[1]) >> 10; v[40] = (x[2] - t[1]) >> 10;
-            v[24] = (x[3] + t[0]) >> 10; v[32] = (x[3] - t[0]) >> 10;
+            for (int q = 0; q < 4; ++q) x[q] = wadd(x[q], 512);
+            v[0] = wadd(x[0], t[3]) >> 10; v[56] = wsub(x[0], t[3]) >> 10;
+            v[8] = wadd(x[1], t[2]) >> 10; v[48] = wsub(x[1], t[2]) >> 10;
+            v[16] = wadd(x[2], t[1]) >> 10; v[40] = wsub(x[2], t[1]) >> 10;
+            v[24] = wadd(x[3], t[0]) >> 10; v[32] = wsub(x[3], t[0]) >> 10;
         }
         for (int i = 0; i < 8; ++i) {   // rows
             int x[4], t[4];
             idct_1d(val + 8 * i, x, t);
-            for (int q = 0; q < 4; ++q) x[q] += 65536 + (128 << 17);
+            for (int q = 0; q < 4; ++q) x[q] = wadd(x[q], 65536 + (128 << 17));
             uint8_t* o = out + (size_t)stride * i;
-            o[0] = clamp8((x[0] + t[3]) >> 17); o[7] = clamp8((x[0] - t[3]) >> 17);
-            o[1] = clamp8((x[1] + t[2]) >> 17); o[6] = clamp8((x[1] - t[2]) >> 17);
-            o[2] = clamp8((x[2] + t[1]) >> 17); o[5] = clamp8((x[2] - t[1]) >> 17);
-            o[3] = clamp8((x[3] + t[0]) >> 17); o[4] = clamp8((x[3] - t[0]) >> 17);
+            o[0] = clamp8(wadd(x[0], t[3]) >> 17); o[7] = clamp8(wsub(x[0], t[3]) >> 17);
+            o[1] = clamp8(wadd(x[1], t[2]) >> 17); o[6] = clamp8(wsub(x[1], t[2]) >> 17);
+            o[2] = clamp8(wadd(x[2], t[1]) >> 17); o[5] = clamp8(wsub(x[2], t[1]) >> 17);
+            o[3] = clamp8(wadd(x[3], t[0]) >> 17); o[4] = clamp8(wsub(x[3], t[0]) >> 17);
         }
     }
 
