@@ -50,10 +50,10 @@ inline void* dev_alloc(size_t bytes) {  // 256-byte aligned like cudaMalloc
     return p;
 }
 inline void dev_free(void* p) { free(p); }
-inline void h2d(void* d, const void* h, size_t n, Stream) { memcpy(d, h, n); }
-inline void d2h(void* h, const void* d, size_t n, Stream) { memcpy(h, d, n); }
-inline void d2d(void* d, const void* s, size_t n, Stream) { memcpy(d, s, n); }
-inline void dev_memset(void* d, int v, size_t n, Stream) { memset(d, v, n); }
+inline void h2d(void* d, const void* h, size_t n, Stream) { if (n) memcpy(d, h, n); }
+inline void d2h(void* h, const void* d, size_t n, Stream) { if (n) memcpy(h, d, n); }
+inline void d2d(void* d, const void* s, size_t n, Stream) { if (n) memcpy(d, s, n); }
+inline void dev_memset(void* d, int v, size_t n, Stream) { if (n) memset(d, v, n); }
 inline void stream_sync(Stream) {}
 inline void event_record(Event&, Stream) {}
 inline void stream_wait(Stream, Event&) {}
