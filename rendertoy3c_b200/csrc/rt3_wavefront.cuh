@@ -41,7 +41,8 @@ struct TraverseArgs {
     // split scenes (a large merged world BLAS beside other instances) are traversed in two launches over the same rays:
     // pass 1 = the single-level kernel on the merged BLAS, pass 2 = the general kernel on the TLAS of the remaining
     // instances, seeded with pass 1's result (closest hit: t, ids for the tie rule; occlusion: nothing left to do).
-    // pass 1 of a connect launch leaves its verdict in the shadow ray itself (tmax = -1: occluded); 0 = the only pass
+    // pass 1 of a connect launch leaves its verdict in the shadow ray itself (tmax = -infinity: occluded — a value no shadow ray
+    // has by itself: tmax = distance - 0.01 may well be negative, or NaN, but not that); 0 = the only pass
     uint32_t pass;
 };
 
@@ -55,7 +56,7 @@ RT3_HD bool trav_begin(const TraverseArgs& a, uint32_t i, Trav<(MODE == TRAV_CON
     tr.init(a.scene, v3(r0), v3(r1), r0.w, r1.w, r2.x);
     if (!SINGLE && a.pass == 2u) {  // what pass 1 found in the merged BLAS
         if (MODE == TRAV_CONNECT) {
-            if (r1.w < 0.0f) { tr.hprim = 0; return false; }
+            if (r1.w == rt3_u2f(0xff800000u)) { tr.hprim = 0; return false; }
         } else {
             const float4 h0 = MODE == TRAV_EXTEND ? a.hit0[i] : a.hit0[2 * (size_t)i];
             const int hp = (int)rt3_f2u(h0.w);
@@ -77,7 +78,7 @@ RT3_HD void trav_end(const TraverseArgs& a, uint32_t i, const Trav<(MODE == TRAV
         rt3_stcs(&a.hit_inst[i], h.inst);
     } else if (MODE == TRAV_CONNECT) {
         if (SINGLE && a.pass == 1u) {  // the epilogue belongs to pass 2; an occluded ray is marked for it
-            if (h.prim >= 0) reinterpret_cast<float*>(const_cast<float4*>(&a.rays.r1[(size_t)i * a.rays.stride]))[3] = -1.0f;
+            if (h.prim >= 0) reinterpret_cast<float*>(const_cast<float4*>(&a.rays.r1[(size_t)i * a.rays.stride]))[3] = rt3_u2f(0xff800000u);
             return;
         }
         const uint32_t path = rt3_f2u(a.rays.r2[(size_t)i * a.rays.stride].y);

@@ -183,3 +183,24 @@ def check_spline_tessellation(backend):
     assert np.all(a["inst"][hit] == 1) and np.all(b["inst"][hit] == 2)
     np.testing.assert_allclose(a["t"][hit], b["t"][hit], rtol=0, atol=1e-5)
     np.testing.assert_allclose(a["u"][hit], b["u"][hit], rtol=0, atol=1e-5)
+
+
+def millimetre_scene():
+    """the small instanced scene shrunk to a thousandth: every light is closer than the reference's fixed shadow-ray offsets
+    (tmin 0.001, tmax = distance - 0.01, closehit_radiance.cu:132-138), so EVERY shadow ray has a negative tmax — an empty
+    interval, nothing can occlude it.  (Found a marker collision in the two-pass traversal: "occluded in pass 1" used to be
+    written as a negative tmax.)"""
+    desc = SMALL["instanced"]()
+    s = np.float32(1e-3)
+    for g in desc.geoms:
+        if g.kind == "mesh":
+            g.verts = (g.verts * s).astype(np.float32)
+        else:
+            g.cr = (g.cr * s).astype(np.float32)
+    for i in desc.instances:
+        x = np.array(i.xform, np.float32)
+        x[[3, 7, 11]] *= s
+        i.xform = x
+    c = desc.camera
+    desc.camera = scenes.Camera(eye=tuple(np.float32(c.eye) * s), lookat=tuple(np.float32(c.lookat) * s), fovy=c.fovy)
+    return desc

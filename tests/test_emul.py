@@ -197,3 +197,13 @@ def test_unbounded_depth_running_out_of_slots_is_reported(emul_lib):
         e.download_accum()          # informative only: the image is still handed out
         e.reset_stats()
         assert e.stats()["error_flags"] == 0
+
+
+@pytest.mark.parametrize("split", [0, 2])
+def test_shadow_rays_with_negative_tmax(emul_lib, split):
+    from parity_common import millimetre_scene
+    desc = millimetre_scene()
+    with Context(0, lib_path=emul_lib) as e:
+        o = build_pair(desc, e, {"split": split})
+        check_render(e, o, desc, subframes=2)
+        assert e.stats()["rays_shadow"] > 100

@@ -191,3 +191,13 @@ def test_flatten_and_split_variants_match_oracle(product_lib, name, options):
         rays = np.concatenate([camera_rays(desc, uvw, 40, 24), random_rays(desc, 1500, seed=5)])
         check_trace(e, o, rays)
         check_render(e, o, desc, subframes=1)
+
+
+@pytest.mark.parametrize("split", [0, 2])
+def test_shadow_rays_with_negative_tmax(product_lib, split):
+    from parity_common import millimetre_scene
+    desc = millimetre_scene()
+    with Context(0) as e:
+        o = build_pair(desc, e, {"split": split})
+        check_render(e, o, desc, subframes=2)
+        assert e.stats()["rays_shadow"] > 100
