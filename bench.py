@@ -528,6 +528,7 @@ def run_rt3(args):
             ptr, n = g5.accum_device_ptr()
             t = torch.as_tensor(_CudaArray(ptr, n), device=dev)
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()   # the ranks finish rendering at slightly different times: that skew is already in max(render_ms), not reduce time
             r0.record()
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             r1.record()
