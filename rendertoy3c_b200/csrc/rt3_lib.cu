@@ -779,7 +779,7 @@ int rt3_accel_build(rt3_context_t c) {
     }
     for (uint32_t i : tl) ensure_blas(c, c->geoms[c->inst[i].blas].get());
     BlasBounds merged_bounds{};
-    if (c->has_merged) {
+    if (c->has_merged) try {
         std::vector<MergedRange> ranges;
         uint32_t total = 0;
         for (uint32_t i : merged) {
@@ -814,6 +814,11 @@ int rt3_accel_build(rt3_context_t c) {
             set_l2_window(c);
         }
         for (int k = 0; k < 3; k++) { merged_bounds.lo[k] = c->m_bvh.lo[k]; merged_bounds.hi[k] = c->m_bvh.hi[k]; }
+    } catch (const Error& e) {
+        if (c->flattened == 0) throw;
+        throw Error(e.code, std::string(e.what()) + " — while building the merged world BLAS with " + std::to_string(c->flattened) +
+                                " flattened instance(s) (about 350 B of device memory per instanced triangle at the peak of the build); "
+                                "rt3_set_option(ctx, \"flatten\", 0) keeps transformed instances as instances");
     } else {
         c->m_map.alloc(1);
     }
