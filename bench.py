@@ -444,7 +444,8 @@ def run_rt3(args):
     assert st["error_flags"] == 0, "traversal stack overflow"
 
     # ---- e2e: per step settings H2D (inside rt3_launch_subframe as kernel parameters) + frame D2H into pinned memory
-    frame = torch.empty((args.height, args.width, 4), dtype=torch.uint8).pin_memory()
+    frames = [torch.empty((args.height, args.width, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    frame = frames[0]
     g.clear_accum()
     g.reset_stats()
     barrier()
@@ -452,7 +453,7 @@ def run_rt3(args):
     for i in range(K):
         g.launch_subframe(settings(Wm + i))
         if world == 1:
-            g.download_frame_into(frame.data_ptr())
+            g.download_frame_async_into(frames[i & 1].data_ptr())   # the copy runs beside the next subframe; g.sync() below completes the last one
     if world > 1:
         g.sync()
         reduce_and_finalize(g, K * world)
@@ -592,7 +593,7 @@ def run_rt3(args):
             "rays_by_type_rank0": rays_by_type,
             "e2e": {"value": rays2 / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(RenderSettings),
                     "d2h_bytes_per_step": args.width * args.height * 4 if world == 1 else args.width * args.height * 4 // K,
-                    "what": "rt3_launch_subframe(host settings) + rt3_download_frame(pinned host u8 frame) per step, wall clock"},
+                    "what": "rt3_launch_subframe(host settings) + rt3_download_frame_async(pinned host u8 frame, two buffers in turn) per step, rt3_sync at the end, wall clock"},
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "rt3::k_traverse<0> (extend, closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -158,6 +158,10 @@ int rt3_get_local_geometry(rt3_context_t ctx, const rt3_ray* rays, const rt3_hit
 
 int rt3_download_accum(rt3_context_t ctx, float* rgba);   /* float4 accum_buffer [h][w][4]; row 0 = image bottom (Q19) */
 int rt3_download_frame(rt3_context_t ctx, uint8_t* rgba8);/* uchar4 frame_buffer, make_color cuda/helpers.h:57-66 */
+/* the same copy, asynchronous (the reference displays from a mapped GL buffer and never waits for a host copy, src/gui/display.cpp):
+ * returns at once; the frame of everything launched so far is copied to `rgba8_pinned` (page-locked host memory, valid until
+ * rt3_sync) on a copy stream beside the next subframe; rt3_sync completes it and fails like rt3_download_frame on a device error */
+int rt3_download_frame_async(rt3_context_t ctx, uint8_t* rgba8_pinned);
 int rt3_accum_device_ptr(rt3_context_t ctx, void** d_ptr, uint64_t* n_floats); /* for an external collective (torch.distributed / NCCL) */
 int rt3_clear_accum(rt3_context_t ctx);                  /* restart accumulation (reference: subframe_index = 0 on camera change, src/wavefront.cpp:193-201) */
 /* after an external SUM reduce in accum_mode 1: accum = sum / total_subframes, refresh the u8 frame */

@@ -29,7 +29,7 @@ RT3_SYMBOLS = [
     "rt3_set_option", "rt3_mesh_create", "rt3_mesh_set_colors", "rt3_spheres_create", "rt3_curves_create", "rt3_texture_create",
     "rt3_accel_append_instance", "rt3_accel_append_animated_instance", "rt3_accel_build", "rt3_scene_set_hitgroup",
     "rt3_scene_set_lights", "rt3_light_make", "rt3_camera_uvw", "rt3_launch_subframe", "rt3_trace", "rt3_trace_device", "rt3_get_local_geometry", "rt3_scene_set_texture_transform",
-    "rt3_download_accum", "rt3_download_frame", "rt3_accum_device_ptr", "rt3_clear_accum", "rt3_finalize_accum",
+    "rt3_download_accum", "rt3_download_frame", "rt3_download_frame_async", "rt3_accum_device_ptr", "rt3_clear_accum", "rt3_finalize_accum",
     "rt3_allreduce_accum",
 ]
 
@@ -248,6 +248,10 @@ class Context:
 
     def download_frame_into(self, host_ptr):
         self._chk(self.L.rt3_download_frame(self.ctx, C.c_void_p(host_ptr)))
+
+    def download_frame_async_into(self, pinned_host_ptr):
+        """rt3_download_frame_async: returns at once; sync() completes the copy"""
+        self._chk(self.L.rt3_download_frame_async(self.ctx, C.c_void_p(pinned_host_ptr)))
 
     def stats(self):
         st = Stats()

@@ -122,6 +122,9 @@ struct rt3_context {
     // the next extend fills the tail of its persistent CTAs; shade(d+1) waits for it (shadow queue + radiance RMW)
     int opt_overlap = 1;
     Stream stream2 = 0, stream3 = 0, stream4 = 0;   // aux of chain 0; main + aux of chain 1 ("overlap" >= 2)
+    Stream stream_copy = 0;                         // rt3_download_frame_async: the copy engine works beside the next subframe
+    Event ev_frame_ready, ev_frame_copied;
+    bool frame_copy_pending = false;
     Event ev_shade[2][2], ev_connect[2][2], ev_fork, ev_join;
     int opt_ctas_per_sm = 0;
     uint64_t samples = 0;
@@ -309,6 +312,7 @@ void ensure_pools(rt3_context* c, size_t paths) {
 
 void ensure_film(rt3_context* c, uint32_t w, uint32_t h) {
     if (c->width == w && c->height == h && c->accum.p) return;
+    if (c->frame_copy_pending) { stream_sync(c->stream_copy); c->frame_copy_pending = false; }   // the old frame is still being read
     c->width = w;
     c->height = h;
     c->accum.alloc((size_t)w * h);  // handleResize reallocates the accumulation buffer (src/wavefront.cpp:178-191)
@@ -408,6 +412,7 @@ int rt3_context_create(int device, rt3_context_t* out) {
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
+    RT3_CUDA(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
     if (const char* e = getenv("RT3_OVERLAP")) c->opt_overlap = atoi(e);  // A/B switch for measurements; rt3_set_option("overlap", v) is the API
 #endif
     c->d_flags.alloc(16);  // [0] error flags, [1] max stack, [2..15] diagnostic counters (RT3_STATS builds)
@@ -427,10 +432,10 @@ void rt3_context_destroy(rt3_context_t c) {
     cudaSetDevice(c->device);
     drop_nccl_comm(c);
     cudaStreamSynchronize(c->stream);
-    cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3); cudaStreamSynchronize(c->stream4);
-    cudaStream_t s = c->stream, s2 = c->stream2, s3 = c->stream3, s4 = c->stream4;
+    cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3); cudaStreamSynchronize(c->stream4); cudaStreamSynchronize(c->stream_copy);
+    cudaStream_t s = c->stream, s2 = c->stream2, s3 = c->stream3, s4 = c->stream4, s5 = c->stream_copy;
     delete c;
-    cudaStreamDestroy(s); cudaStreamDestroy(s2); cudaStreamDestroy(s3); cudaStreamDestroy(s4);
+    cudaStreamDestroy(s); cudaStreamDestroy(s2); cudaStreamDestroy(s3); cudaStreamDestroy(s4); cudaStreamDestroy(s5);
 #else
     delete c;
 #endif
@@ -441,6 +446,11 @@ int rt3_sync(rt3_context_t c) {
     use_device(c);
     RT3_REQUIRE(c, RT3_ERR_INVALID, "sync: null context");
     stream_sync(c->stream);
+    if (c->frame_copy_pending) {   // an asynchronous frame download: finished, and as trustworthy as a synchronous one
+        stream_sync(c->stream_copy);
+        c->frame_copy_pending = false;
+        require_no_device_error(c, "download_frame_async");
+    }
     RT3_API_END
 }
 
@@ -1162,6 +1172,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
         if (k > 0) { event_record(c->ev_join, h.main); stream_wait(c->stream, c->ev_join); }
     }
     if (timing) event_record(ev[2], c->stream);
+    if (c->frame_copy_pending) stream_wait(c->stream, c->ev_frame_copied);   // resolve overwrites the frame a pending download reads
     RT3_LAUNCH_1D(k_resolve, rs->width * rs->height, c->stream, f, (const float4*)c->result.p, c->accum.p, c->frame.p);
     if (timing) {
         event_record(ev[3], c->stream);
@@ -1269,6 +1280,19 @@ int rt3_download_frame(rt3_context_t c, uint8_t* rgba8) {
     require_no_device_error(c, "download_frame");
     RT3_API_END
 }
+// The frame of the subframes launched so far, copied on the context's copy stream: returns at once, the copy runs beside
+// whatever is launched next (the next subframe's resolve waits for it), rt3_sync completes it and reports device errors
+int rt3_download_frame_async(rt3_context_t c, uint8_t* rgba8_pinned) {
+    RT3_API_BEGIN
+    use_device(c);
+    RT3_REQUIRE(c && rgba8_pinned && c->frame.p, RT3_ERR_STATE, "download_frame_async: nothing rendered");
+    event_record(c->ev_frame_ready, c->stream);
+    stream_wait(c->stream_copy, c->ev_frame_ready);
+    d2h(rgba8_pinned, c->frame.p, c->frame.bytes(), c->stream_copy);
+    event_record(c->ev_frame_copied, c->stream_copy);
+    c->frame_copy_pending = true;
+    RT3_API_END
+}
 int rt3_accum_device_ptr(rt3_context_t c, void** p, uint64_t* n) {
     RT3_API_BEGIN
     use_device(c);
@@ -1289,6 +1313,7 @@ int rt3_finalize_accum(rt3_context_t c, uint32_t total_subframes) {
     RT3_API_BEGIN
     use_device(c);
     RT3_REQUIRE(c && c->accum.p && total_subframes > 0, RT3_ERR_STATE, "finalize_accum: nothing rendered");
+    if (c->frame_copy_pending) stream_wait(c->stream, c->ev_frame_copied);
     RT3_LAUNCH_1D(k_finalize, c->width * c->height, c->stream, c->accum.p, c->frame.p, 1.0f / (float)total_subframes);
     RT3_API_END
 }

@@ -204,3 +204,26 @@ def millimetre_scene():
     c = desc.camera
     desc.camera = scenes.Camera(eye=tuple(np.float32(c.eye) * s), lookat=tuple(np.float32(c.lookat) * s), fovy=c.fovy)
     return desc
+
+
+def check_async_frame_download(make_context):
+    """rt3_download_frame_async after every subframe (the copy overlaps the next subframe, whose resolve must wait for it)
+    returns the frames rt3_download_frame returns"""
+    desc = SMALL["cornell"]()
+    want, got = [], []
+    with make_context() as a, make_context() as b:
+        for c in (a, b):
+            scenes.replay(desc, c)
+        uvw = a.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, desc.width / desc.height)
+        for sf in range(4):
+            rs = make_settings(desc, uvw, sf)
+            a.launch_subframe(rs)
+            want.append(a.download_frame())
+            b.launch_subframe(rs)
+            buf = np.zeros((desc.height, desc.width, 4), dtype=np.uint8)
+            b.download_frame_async_into(buf.ctypes.data)
+            got.append(buf)
+        b.sync()
+    for sf in range(4):
+        assert np.array_equal(want[sf], got[sf]), "frame %d differs" % sf
+    assert not np.array_equal(got[0], got[3])

@@ -201,3 +201,8 @@ def test_shadow_rays_with_negative_tmax(product_lib, split):
         o = build_pair(desc, e, {"split": split})
         check_render(e, o, desc, subframes=2)
         assert e.stats()["rays_shadow"] > 100
+
+
+def test_async_frame_download(product_lib):
+    from parity_common import check_async_frame_download
+    check_async_frame_download(lambda: Context(0))
