@@ -211,6 +211,9 @@ class _CudaArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
+EXTEND_KERNELS = ("k_traverse<0", "k_extend_packets")   # the kernels of the extend stage, as the ncu launch list names them
+
+
 def issue_evidence():
     """Issue-slot utilisation of the extend launches from the newest committed full ncu capture of this command
     (profiles/r*_ncu_bench_traverse_full.txt): static evidence, not measured in this run."""
@@ -240,7 +243,7 @@ def issue_roofline(kernel_prefix, ext_ms_per_step, sm_mhz):
     peak = sms * per_sm * clock_hz
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_launch_shares.json")), reverse=True):
         ks = json.load(open(path))["kernels"]
-        inst = sum(v.get("warp_inst", 0) for k, v in ks.items() if k.startswith(kernel_prefix))
+        inst = sum(v.get("warp_inst", 0) for k, v in ks.items() if k.startswith(kernel_prefix))   # kernel_prefix: one prefix or a tuple of them
         if inst > 0 and ext_ms_per_step > 0:
             ach = inst / (ext_ms_per_step * 1e-3)
             return {"bound": "issue", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": ach / peak,
@@ -580,8 +583,9 @@ def run_rt3(args):
         cand = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_launch_shares.json")))  # newest committed capture
         shares = cand[-1] if cand else ""
         if shares and (args.grid, args.width, args.height) == (708, 1920, 1080):
-            k = json.load(open(shares))["kernels"].get("k_traverse<0, 1>")
-            if k:
+            ks = [v for n, v in json.load(open(shares))["kernels"].items() if n.startswith(EXTEND_KERNELS)]
+            if ks:
+                k = {f: sum(v[f] for v in ks) for f in ("dram_read_MB", "dram_write_MB", "launches")}
                 traffic = {"bytes_per_step": (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6, "launches_per_step": k["launches"],
                            "algorithmic_bytes_per_step": BYTES_PER_RAY_EXTEND * ext_rays / 2, "source": "profiles/%s (ncu dram__bytes_read/write.sum of this command)" % os.path.basename(shares)}
         out = {
@@ -596,7 +600,7 @@ def run_rt3(args):
                     "what": "rt3_launch_subframe(host settings) + rt3_download_frame_async(pinned host u8 frame, two buffers in turn) per step, rt3_sync at the end, wall clock"},
             "gpu_launches": launches,
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "rt3::k_traverse<0> (extend, closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "the extend stage: rt3::k_extend_packets (camera rays, depth 0) + rt3::k_traverse<0> (bounce rays), closest hit", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_ray": BYTES_PER_RAY_EXTEND,
                          "kernel_ms_per_step": ext_ms / 2, "kernel_Mrays_s": ext_rays / (ext_ms * 1e-3) / 1e6,
@@ -606,7 +610,7 @@ def run_rt3(args):
                          "note": "HBM is the roofline of the queue traffic only: the kernel reads and writes its algorithmic bytes once (traffic ~ 1.0x) and is "
                                  "bound by instruction issue, see roofline_issue",
                          "issue_bound_evidence": issue_evidence()},
-            "roofline_issue": issue_roofline("k_traverse<0", ext_ms / 2, (clk or {}).get("sm_mhz")),
+            "roofline_issue": issue_roofline(EXTEND_KERNELS, ext_ms / 2, (clk or {}).get("sm_mhz")),
             "stage_ms_last_step": stage,
         }
         if reduce_check is not None:

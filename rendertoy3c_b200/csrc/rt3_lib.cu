@@ -90,6 +90,7 @@ struct rt3_context {
     bool has_merged = false, single_level = false;
     bool has_subdiv_curves = false;  // some instance refers to a spline curve geometry (set in rt3_accel_build)
     int opt_merge = 1;
+    int opt_packets = 1;   // camera rays (depth 0) traverse the merged BLAS in packets of eight (k_extend_packets)
     int opt_flatten = 1;   // static, transformed triangle-mesh instances join the merged world BLAS (vertices transformed once, at build)
     int opt_split = 1;     // merged BLAS beside other instances: 0 = one TLAS over both, 2 = always two passes (single-level kernel, then the rest), 1 = two passes when the merged BLAS is large
     bool split = false;
@@ -183,16 +184,34 @@ void launch_traverse_kernel(rt3_context* c, const TraverseArgs& a, Stream st) {
 #endif
     count_launch();
 }
-// fetch2: the work counter of the second launch of a split traversal (zeroed like a.fetch)
+// camera rays (depth 0 of a subframe: `packet_rays` of them, known on the host) through the merged BLAS in packets of eight
+void launch_extend_packets(rt3_context* c, TraverseArgs a, uint32_t packet_rays, Stream st) {
+#ifdef RT3_EMULATE
+    (void)packet_rays; (void)st;
+    k_traverse<TRAV_EXTEND, true>(a);   // the simulator has no warps: the per-ray traversal returns the same hits
+#else
+    a.count_ptr = nullptr;
+    a.count = packet_rays;
+    k_extend_packets<<<(packet_rays + 127u) / 128u, 128, 0, st>>>(a);
+    RT3_CUDA(cudaGetLastError());
+#endif
+    count_launch();
+}
+// fetch2: the work counter of the second launch of a split traversal (zeroed like a.fetch); packet_rays > 0: the rays are the
+// camera rays of a subframe, that many
 template <int MODE>
-void launch_traverse(rt3_context* c, TraverseArgs a, uint32_t* fetch2, Stream st) {
+void launch_traverse(rt3_context* c, TraverseArgs a, uint32_t* fetch2, Stream st, uint32_t packet_rays = 0) {
     a.pass = 0u;
-    if (c->single_level) launch_traverse_kernel<MODE, true>(c, a, st);   // merged world BLAS only: the lean instantiation
-    else if (c->split) {   // the bulk of the triangles with the lean kernel, then everything else, seeded with what that found
+    const bool packets = MODE == TRAV_EXTEND && packet_rays > 0 && c->opt_packets;
+    if (c->single_level) {   // merged world BLAS only: the lean instantiation
+        if (packets) launch_extend_packets(c, a, packet_rays, st);
+        else launch_traverse_kernel<MODE, true>(c, a, st);
+    } else if (c->split) {   // the bulk of the triangles with the lean kernel, then everything else, seeded with what that found
         TraverseArgs p1 = a;
         p1.scene = c->trav_scene(true);
         p1.pass = 1u;
-        launch_traverse_kernel<MODE, true>(c, p1, st);
+        if (packets) launch_extend_packets(c, p1, packet_rays, st);
+        else launch_traverse_kernel<MODE, true>(c, p1, st);
         a.pass = 2u;
         a.fetch = fetch2;
         a.stat = nullptr;
@@ -413,6 +432,7 @@ int rt3_context_create(int device, rt3_context_t* out) {
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
+    if (const char* e = getenv("RT3_PACKETS")) c->opt_packets = atoi(e);
     if (const char* e = getenv("RT3_OVERLAP")) c->opt_overlap = atoi(e);  // A/B switch for measurements; rt3_set_option("overlap", v) is the API
 #endif
     c->d_flags.alloc(16);  // [0] error flags, [1] max stack, [2..15] diagnostic counters (RT3_STATS builds)
@@ -476,6 +496,7 @@ int rt3_set_option(rt3_context_t c, const char* key, int value) {
     else if (k == "persist_ctas_per_sm") c->opt_ctas_per_sm = value;
     else if (k == "merge_identity") { c->opt_merge = value; c->built = false; }
     else if (k == "flatten") { c->opt_flatten = value; c->built = false; }
+    else if (k == "packets") c->opt_packets = value;
     else if (k == "split") { c->opt_split = value; c->built = false; }
     else if (k == "tlas_sah") { c->opt_tlas_sah = value; c->built = false; }
     else if (k == "bsphere_cull") { c->opt_bsphere_cull = value; c->built = false; }
@@ -1120,7 +1141,7 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
             a.hit0 = h.q.hit0; a.hit_inst = h.q.hit_inst; a.contrib = nullptr; a.result = nullptr;
             a.stat = c->d_stats.p + (depth == 0 ? 0 : 1);
             a.faithful = 0;
-            launch_traverse<TRAV_EXTEND>(c, a, h.cnt + 4 * M + depth, h.main);
+            launch_traverse<TRAV_EXTEND>(c, a, h.cnt + 4 * M + depth, h.main, depth == 0 ? h.count : 0u);
         }
         if (timing) event_record(e1, c->stream);
         for (int k = 0; k < nchains; k++) {

@@ -599,6 +599,70 @@ struct Trav {
         }
     }
 
+#ifndef RT3_EMULATE
+    // ---------------------------------------------------------------------------------- primary-ray packets (k_extend_packets)
+    // Eight consecutive camera rays — the samples of one pixel in the pixel-major path order — leave the same origin in almost
+    // the same direction and walk the same nodes.  Here they walk them ONCE: the eight lanes of a group keep identical
+    // traversal state (node groups, stack) and share a node step, lane j testing child j of the wide node against the
+    // PACKET — the interval [ilo, ihi] of the group's 1/d per axis — instead of every lane testing all eight children for
+    // its own ray.  The packet test is a superset of every ray's own padded slab test (so is the packet's far bound, the
+    // largest tbest of the group), the triangles of every leaf reached are tested per lane with the ray's own watertight
+    // test, and the closest hit is an order-free choice: the result is the one the per-ray traversal finds, bit for bit.
+    // unbounded: bit k set = the group's directions straddle zero on axis k (no slab test on that axis).
+    __device__ __forceinline__ void node_step_packet(const TravScene& sc, uint32_t gmask, uint32_t gl, uint32_t oct, float3 ilo, float3 ihi, float3 iabs,
+                                                     uint32_t unbounded, float ptmin, float ptbest) {
+        const uint32_t hits = ng.y;
+        const int bit = 31 - __clz((int)hits);
+        ng.y &= ~(1u << bit);
+        if (ng.y & 0xff000000u) push(sc, ng);
+        const uint32_t slot = ((uint32_t)bit - 24u) ^ oct;
+        const uint32_t rel = (uint32_t)__popc(hits & 0xffu & ((1u << slot) - 1u));
+        const uint4* np = reinterpret_cast<const uint4*>(sc.tlas_nodes + (ng.x + rel));
+        const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+        const uint32_t m = __byte_perm(n1.z, n1.w, gl) & 0xffu;   // meta byte of child slot gl
+        uint32_t word = 0u;
+        if (m != 0u) {
+            const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
+            const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23), sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
+            const float lox = px + (float)(__byte_perm(n2.x, n2.y, gl) & 0xffu) * sx, loy = py + (float)(__byte_perm(n2.z, n2.w, gl) & 0xffu) * sy,
+                        loz = pz + (float)(__byte_perm(n3.x, n3.y, gl) & 0xffu) * sz;
+            const float hix = px + (float)(__byte_perm(n3.z, n3.w, gl) & 0xffu) * sx, hiy = py + (float)(__byte_perm(n4.x, n4.y, gl) & 0xffu) * sy,
+                        hiz = pz + (float)(__byte_perm(n4.z, n4.w, gl) & 0xffu) * sz;
+            float tn = ptmin, tf = ptbest;
+            if (!(unbounded & 1u)) {
+                const float pn = ((oct & 1u) ? lox : hix) - o.x, pf = ((oct & 1u) ? hix : lox) - o.x;
+                const float e = 4e-6f * (fabsf(o.x) + fabsf(px) + 256.0f * sx) * iabs.x;
+                tn = fmaxf(tn, fminf(pn * ilo.x, pn * ihi.x) - e);
+                tf = fminf(tf, fmaxf(pf * ilo.x, pf * ihi.x) + e);
+            }
+            if (!(unbounded & 2u)) {
+                const float pn = ((oct & 2u) ? loy : hiy) - o.y, pf = ((oct & 2u) ? hiy : loy) - o.y;
+                const float e = 4e-6f * (fabsf(o.y) + fabsf(py) + 256.0f * sy) * iabs.y;
+                tn = fmaxf(tn, fminf(pn * ilo.y, pn * ihi.y) - e);
+                tf = fminf(tf, fmaxf(pf * ilo.y, pf * ihi.y) + e);
+            }
+            if (!(unbounded & 4u)) {
+                const float pn = ((oct & 4u) ? loz : hiz) - o.z, pf = ((oct & 4u) ? hiz : loz) - o.z;
+                const float e = 4e-6f * (fabsf(o.z) + fabsf(pz) + 256.0f * sz) * iabs.z;
+                tn = fmaxf(tn, fminf(pn * ilo.z, pn * ihi.z) - e);
+                tf = fminf(tf, fmaxf(pf * ilo.z, pf * ihi.z) + e);
+            }
+            if (tn - 1e-5f * fabsf(tn) <= tf + 1e-5f * fabsf(tf)) {
+                const uint32_t inner = (m & (m << 1)) & 0x10u;   // 001sssss with sssss >= 24: bits 4 and 3 set
+                word = ((m >> 5) & 7u) << ((m ^ (inner ? oct : 0u)) & 0x1fu);
+            }
+        }
+        word |= __shfl_xor_sync(gmask, word, 1);
+        word |= __shfl_xor_sync(gmask, word, 2);
+        word |= __shfl_xor_sync(gmask, word, 4);
+        ng = make_uint2(n1.x, (word & 0xff000000u) | (n0.w >> 24));
+        tg = make_uint2(n1.y, word & 0x00ffffffu);
+#ifdef RT3_STATS
+        c_nodes++;
+#endif
+    }
+#endif
+
     // returns true when an any-hit ray is finished
     RT3_HD bool prim_step(const TravScene& sc) {
         const int bit = 31 - rt3_clz(tg.y & (0u - tg.y));  // lowest set bit

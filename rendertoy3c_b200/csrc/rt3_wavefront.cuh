@@ -194,6 +194,61 @@ __global__ void __launch_bounds__(RT3_TRAV_THREADS, SINGLE ? RT3_TRAV_MIN_BLOCKS
 }
 #endif
 
+#ifndef RT3_EMULATE
+// Extension rays of depth 0 in a single-level scene (or pass 1 of a split one): camera rays, eight consecutive ones per packet
+// (Trav::node_step_packet).  One thread per ray, 128 rays per CTA, no persistence: the packets of a launch cost about the same.
+__global__ void __launch_bounds__(128, 8) k_extend_packets(TraverseArgs a) {
+    const uint32_t n = a.count;
+    const uint32_t i = blockIdx.x * 128u + threadIdx.x;
+    if (a.stat && i == 0u) atomicAdd(a.stat, (unsigned long long)n);
+    const uint32_t lane = threadIdx.x & 31u, gl = lane & 7u, gmask = 0xffu << (lane & 24u);
+    const uint32_t ii = i < n ? i : n - 1u;   // a ragged last packet is filled with copies of the last ray (they are not written)
+    Trav<false, true> tr;
+    uint2 stack_mem[RT3_STACK_SIZE + FR_COUNT];
+    tr.stack = stack_mem;
+    trav_begin<TRAV_EXTEND, true>(a, ii, tr);
+    const float4 r1 = a.rays.r1[(size_t)ii * a.rays.stride];
+    // the packet: shared origin (all camera rays leave the eye; a group whose origins differ falls back to boxes of its own), 1/d interval
+    float dlx = r1.x, dhx = r1.x, dly = r1.y, dhy = r1.y, dlz = r1.z, dhz = r1.z;
+    bool same_o = true;
+#pragma unroll
+    for (int sft = 1; sft < 8; sft <<= 1) {
+        dlx = fminf(dlx, __shfl_xor_sync(0xffffffffu, dlx, sft)); dhx = fmaxf(dhx, __shfl_xor_sync(0xffffffffu, dhx, sft));
+        dly = fminf(dly, __shfl_xor_sync(0xffffffffu, dly, sft)); dhy = fmaxf(dhy, __shfl_xor_sync(0xffffffffu, dhy, sft));
+        dlz = fminf(dlz, __shfl_xor_sync(0xffffffffu, dlz, sft)); dhz = fmaxf(dhz, __shfl_xor_sync(0xffffffffu, dhz, sft));
+        same_o = same_o && __shfl_xor_sync(0xffffffffu, tr.o.x, sft) == tr.o.x && __shfl_xor_sync(0xffffffffu, tr.o.y, sft) == tr.o.y &&
+                 __shfl_xor_sync(0xffffffffu, tr.o.z, sft) == tr.o.z;
+    }
+    same_o = __all_sync(0xffffffffu, same_o) != 0;   // (checked per warp: one launch kind)
+    const float tiny = 1e-18f;
+    uint32_t unbounded = 0u;
+    float3 ilo, ihi, iabs;
+    if (dlx > tiny || dhx < -tiny) { ilo.x = 1.0f / dhx; ihi.x = 1.0f / dlx; } else { unbounded |= 1u; ilo.x = ihi.x = 0.0f; }
+    if (dly > tiny || dhy < -tiny) { ilo.y = 1.0f / dhy; ihi.y = 1.0f / dly; } else { unbounded |= 2u; ilo.y = ihi.y = 0.0f; }
+    if (dlz > tiny || dhz < -tiny) { ilo.z = 1.0f / dhz; ihi.z = 1.0f / dlz; } else { unbounded |= 4u; ilo.z = ihi.z = 0.0f; }
+    iabs = make_float3(fmaxf(fabsf(ilo.x), fabsf(ihi.x)), fmaxf(fabsf(ilo.y), fabsf(ihi.y)), fmaxf(fabsf(ilo.z), fabsf(ihi.z)));
+    const uint32_t oct = (dlx >= 0.0f ? 1u : 0u) | (dly >= 0.0f ? 2u : 0u) | (dlz >= 0.0f ? 4u : 0u);   // the group's front-to-back order
+    float ptmin = tr.tmin;   // the packet's near bound: the smallest tmin of the group (camera rays all have the same)
+#pragma unroll
+    for (int sft = 1; sft < 8; sft <<= 1) ptmin = fminf(ptmin, __shfl_xor_sync(0xffffffffu, ptmin, sft));
+    if (!same_o) {   // not a camera wave after all: every lane on its own (kept for safety; launch_subframe only sends depth 0 here)
+        while (tr.step(a.scene)) {}
+    } else {
+        for (;;) {
+            while (tr.tg.y != 0u) tr.prim_step(a.scene);
+            while (!(tr.ng.y & 0xff000000u) && tr.sp != 0) tr.ng = tr.st_get(--tr.sp);   // the stack holds node groups only
+            if (!(tr.ng.y & 0xff000000u)) break;
+            float ptbest = tr.tbest;
+            ptbest = fmaxf(ptbest, __shfl_xor_sync(gmask, ptbest, 1));
+            ptbest = fmaxf(ptbest, __shfl_xor_sync(gmask, ptbest, 2));
+            ptbest = fmaxf(ptbest, __shfl_xor_sync(gmask, ptbest, 4));
+            tr.node_step_packet(a.scene, gmask, gl, oct, ilo, ihi, iabs, unbounded, ptmin, ptbest);
+        }
+    }
+    if (i < n) trav_end<TRAV_EXTEND, true>(a, i, tr);
+}
+#endif
+
 // ------------------------------------------------------------------------------------ geometry packing / boxes
 RT3_GLOBAL(k_tri_boxes, const float* verts, const int32_t* idx, float4* lo, float4* hi) {
     const uint32_t p = RT3_THREAD_ID();
