@@ -90,7 +90,8 @@ struct rt3_context {
     bool has_merged = false, single_level = false;
     bool has_subdiv_curves = false;  // some instance refers to a spline curve geometry (set in rt3_accel_build)
     int opt_merge = 1;
-    int opt_packets = 1;   // camera rays (depth 0) traverse the merged BLAS in packets of eight (k_extend_packets)
+    int opt_packets = 1;   // camera rays (depth 0) traverse the merged BLAS in packets of eight (k_extend_packets): 1 = when the BLAS fits the L2, 2 = always
+    size_t l2_bytes = 0;
     int opt_flatten = 1;   // static, transformed triangle-mesh instances join the merged world BLAS (vertices transformed once, at build)
     int opt_split = 1;     // merged BLAS beside other instances: 0 = one TLAS over both, 2 = always two passes (single-level kernel, then the rest), 1 = two passes when the merged BLAS is large
     bool split = false;
@@ -202,7 +203,10 @@ void launch_extend_packets(rt3_context* c, TraverseArgs a, uint32_t packet_rays,
 template <int MODE>
 void launch_traverse(rt3_context* c, TraverseArgs a, uint32_t* fetch2, Stream st, uint32_t packet_rays = 0) {
     a.pass = 0u;
-    const bool packets = MODE == TRAV_EXTEND && packet_rays > 0 && c->opt_packets;
+    // packets put FOUR independent traversals into a warp where the per-ray kernel has thirty-two: fine while nodes come from L2,
+    // latency-bound once they come from DRAM (C3 flattened, 5.9 GB of nodes and triangles: 26.6 -> 159 ms) — only for a
+    // merged BLAS that fits the L2
+    const bool packets = MODE == TRAV_EXTEND && packet_rays > 0 && c->opt_packets && (c->opt_packets >= 2 || c->m_slab.bytes() <= c->l2_bytes);
     if (c->single_level) {   // merged world BLAS only: the lean instantiation
         if (packets) launch_extend_packets(c, a, packet_rays, st);
         else launch_traverse_kernel<MODE, true>(c, a, st);
@@ -427,6 +431,7 @@ int rt3_context_create(int device, rt3_context_t* out) {
     RT3_CUDA(cudaGetDeviceProperties(&prop, device));
     RT3_REQUIRE(prop.major >= 10, RT3_ERR_NO_DEVICE, "context_create: kernels are built for sm_100a only");
     c->num_sms = prop.multiProcessorCount;
+    c->l2_bytes = (size_t)prop.l2CacheSize;
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));

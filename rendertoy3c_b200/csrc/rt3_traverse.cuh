@@ -622,28 +622,31 @@ struct Trav {
         const uint32_t m = __byte_perm(n1.z, n1.w, gl) & 0xffu;   // meta byte of child slot gl
         uint32_t word = 0u;
         if (m != 0u) {
-            const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
+            // plane distances from the origin, formed like the per-ray test forms them — (p - o) first, then the quantised offset — so
+            // that their rounding is relative to the distance itself; the slack covers the per-ray test's own padding (4.8e-7 of
+            // |(p - o) / d| + 255 |scale / d|) and the rounding on both sides, a few times over
+            const float ox = __uint_as_float(n0.x) - o.x, oy = __uint_as_float(n0.y) - o.y, oz = __uint_as_float(n0.z) - o.z;
             const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23), sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
-            const float lox = px + (float)(__byte_perm(n2.x, n2.y, gl) & 0xffu) * sx, loy = py + (float)(__byte_perm(n2.z, n2.w, gl) & 0xffu) * sy,
-                        loz = pz + (float)(__byte_perm(n3.x, n3.y, gl) & 0xffu) * sz;
-            const float hix = px + (float)(__byte_perm(n3.z, n3.w, gl) & 0xffu) * sx, hiy = py + (float)(__byte_perm(n4.x, n4.y, gl) & 0xffu) * sy,
-                        hiz = pz + (float)(__byte_perm(n4.z, n4.w, gl) & 0xffu) * sz;
+            const float lox = fmaf((float)(__byte_perm(n2.x, n2.y, gl) & 0xffu), sx, ox), loy = fmaf((float)(__byte_perm(n2.z, n2.w, gl) & 0xffu), sy, oy),
+                        loz = fmaf((float)(__byte_perm(n3.x, n3.y, gl) & 0xffu), sz, oz);
+            const float hix = fmaf((float)(__byte_perm(n3.z, n3.w, gl) & 0xffu), sx, ox), hiy = fmaf((float)(__byte_perm(n4.x, n4.y, gl) & 0xffu), sy, oy),
+                        hiz = fmaf((float)(__byte_perm(n4.z, n4.w, gl) & 0xffu), sz, oz);
             float tn = ptmin, tf = ptbest;
             if (!(unbounded & 1u)) {
-                const float pn = ((oct & 1u) ? lox : hix) - o.x, pf = ((oct & 1u) ? hix : lox) - o.x;
-                const float e = 4e-6f * (fabsf(o.x) + fabsf(px) + 256.0f * sx) * iabs.x;
+                const float pn = (oct & 1u) ? lox : hix, pf = (oct & 1u) ? hix : lox;
+                const float e = 3e-6f * (fabsf(ox) + 512.0f * sx) * iabs.x;
                 tn = fmaxf(tn, fminf(pn * ilo.x, pn * ihi.x) - e);
                 tf = fminf(tf, fmaxf(pf * ilo.x, pf * ihi.x) + e);
             }
             if (!(unbounded & 2u)) {
-                const float pn = ((oct & 2u) ? loy : hiy) - o.y, pf = ((oct & 2u) ? hiy : loy) - o.y;
-                const float e = 4e-6f * (fabsf(o.y) + fabsf(py) + 256.0f * sy) * iabs.y;
+                const float pn = (oct & 2u) ? loy : hiy, pf = (oct & 2u) ? hiy : loy;
+                const float e = 3e-6f * (fabsf(oy) + 512.0f * sy) * iabs.y;
                 tn = fmaxf(tn, fminf(pn * ilo.y, pn * ihi.y) - e);
                 tf = fminf(tf, fmaxf(pf * ilo.y, pf * ihi.y) + e);
             }
             if (!(unbounded & 4u)) {
-                const float pn = ((oct & 4u) ? loz : hiz) - o.z, pf = ((oct & 4u) ? hiz : loz) - o.z;
-                const float e = 4e-6f * (fabsf(o.z) + fabsf(pz) + 256.0f * sz) * iabs.z;
+                const float pn = (oct & 4u) ? loz : hiz, pf = (oct & 4u) ? hiz : loz;
+                const float e = 3e-6f * (fabsf(oz) + 512.0f * sz) * iabs.z;
                 tn = fmaxf(tn, fminf(pn * ilo.z, pn * ihi.z) - e);
                 tf = fminf(tf, fmaxf(pf * ilo.z, pf * ihi.z) + e);
             }
