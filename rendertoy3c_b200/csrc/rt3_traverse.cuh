@@ -608,7 +608,8 @@ struct Trav {
     // its own ray.  The packet test is a superset of every ray's own padded slab test (so is the packet's far bound, the
     // largest tbest of the group), the triangles of every leaf reached are tested per lane with the ray's own watertight
     // test, and the closest hit is an order-free choice: the result is the one the per-ray traversal finds, bit for bit.
-    // unbounded: bit k set = the group's directions straddle zero on axis k (no slab test on that axis).
+    // unbounded: bit k set = the group's directions straddle zero on axis k; ilo = 1 / (most negative d), ihi = 1 / (most positive d)
+    // there, and the axis only bounds the entry distance.
     __device__ __forceinline__ void node_step_packet(const TravScene& sc, uint32_t gmask, uint32_t gl, uint32_t oct, float3 ilo, float3 ihi, float3 iabs,
                                                      uint32_t unbounded, float ptmin, float ptbest) {
         const uint32_t hits = ng.y;
@@ -632,23 +633,41 @@ struct Trav {
             const float hix = fmaf((float)(__byte_perm(n3.z, n3.w, gl) & 0xffu), sx, ox), hiy = fmaf((float)(__byte_perm(n4.x, n4.y, gl) & 0xffu), sy, oy),
                         hiz = fmaf((float)(__byte_perm(n4.z, n4.w, gl) & 0xffu), sz, oz);
             float tn = ptmin, tf = ptbest;
-            if (!(unbounded & 1u)) {
-                const float pn = (oct & 1u) ? lox : hix, pf = (oct & 1u) ? hix : lox;
+            {
                 const float e = 3e-6f * (fabsf(ox) + 512.0f * sx) * iabs.x;
-                tn = fmaxf(tn, fminf(pn * ilo.x, pn * ihi.x) - e);
-                tf = fminf(tf, fmaxf(pf * ilo.x, pf * ihi.x) + e);
+                if (!(unbounded & 1u)) {
+                    const float pn = (oct & 1u) ? lox : hix, pf = (oct & 1u) ? hix : lox;
+                    tn = fmaxf(tn, fminf(pn * ilo.x, pn * ihi.x) - e);
+                    tf = fminf(tf, fmaxf(pf * ilo.x, pf * ihi.x) + e);
+                } else {   // directions of both signs: the beam [o + t dlo, o + t dhi] reaches a box beside the origin only from some t on
+                    const float k = 3e-6f * (fabsf(ox) + 512.0f * sx);
+                    if (lox > 0.0f) tn = fmaxf(tn, lox * ihi.x - k * ihi.x);
+                    if (hix < 0.0f) tn = fmaxf(tn, hix * ilo.x + k * ilo.x);
+                }
             }
-            if (!(unbounded & 2u)) {
-                const float pn = (oct & 2u) ? loy : hiy, pf = (oct & 2u) ? hiy : loy;
+            {
                 const float e = 3e-6f * (fabsf(oy) + 512.0f * sy) * iabs.y;
-                tn = fmaxf(tn, fminf(pn * ilo.y, pn * ihi.y) - e);
-                tf = fminf(tf, fmaxf(pf * ilo.y, pf * ihi.y) + e);
+                if (!(unbounded & 2u)) {
+                    const float pn = (oct & 2u) ? loy : hiy, pf = (oct & 2u) ? hiy : loy;
+                    tn = fmaxf(tn, fminf(pn * ilo.y, pn * ihi.y) - e);
+                    tf = fminf(tf, fmaxf(pf * ilo.y, pf * ihi.y) + e);
+                } else {   // directions of both signs: the beam [o + t dlo, o + t dhi] reaches a box beside the origin only from some t on
+                    const float k = 3e-6f * (fabsf(oy) + 512.0f * sy);
+                    if (loy > 0.0f) tn = fmaxf(tn, loy * ihi.y - k * ihi.y);
+                    if (hiy < 0.0f) tn = fmaxf(tn, hiy * ilo.y + k * ilo.y);
+                }
             }
-            if (!(unbounded & 4u)) {
-                const float pn = (oct & 4u) ? loz : hiz, pf = (oct & 4u) ? hiz : loz;
+            {
                 const float e = 3e-6f * (fabsf(oz) + 512.0f * sz) * iabs.z;
-                tn = fmaxf(tn, fminf(pn * ilo.z, pn * ihi.z) - e);
-                tf = fminf(tf, fmaxf(pf * ilo.z, pf * ihi.z) + e);
+                if (!(unbounded & 4u)) {
+                    const float pn = (oct & 4u) ? loz : hiz, pf = (oct & 4u) ? hiz : loz;
+                    tn = fmaxf(tn, fminf(pn * ilo.z, pn * ihi.z) - e);
+                    tf = fminf(tf, fmaxf(pf * ilo.z, pf * ihi.z) + e);
+                } else {   // directions of both signs: the beam [o + t dlo, o + t dhi] reaches a box beside the origin only from some t on
+                    const float k = 3e-6f * (fabsf(oz) + 512.0f * sz);
+                    if (loz > 0.0f) tn = fmaxf(tn, loz * ihi.z - k * ihi.z);
+                    if (hiz < 0.0f) tn = fmaxf(tn, hiz * ilo.z + k * ilo.z);
+                }
             }
             if (tn - 1e-5f * fabsf(tn) <= tf + 1e-5f * fabsf(tf)) {
                 const uint32_t inner = (m & (m << 1)) & 0x10u;   // 001sssss with sssss >= 24: bits 4 and 3 set

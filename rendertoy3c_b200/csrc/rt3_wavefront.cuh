@@ -220,12 +220,12 @@ __global__ void __launch_bounds__(128, 8) k_extend_packets(TraverseArgs a) {
                  __shfl_xor_sync(0xffffffffu, tr.o.z, sft) == tr.o.z;
     }
     same_o = __all_sync(0xffffffffu, same_o) != 0;   // (checked per warp: one launch kind)
-    const float tiny = 1e-18f;
+    // per axis: directions of one sign -> the interval of 1/d; of both signs (or zero) -> 1 / the extreme of either sign
     uint32_t unbounded = 0u;
     float3 ilo, ihi, iabs;
-    if (dlx > tiny || dhx < -tiny) { ilo.x = 1.0f / dhx; ihi.x = 1.0f / dlx; } else { unbounded |= 1u; ilo.x = ihi.x = 0.0f; }
-    if (dly > tiny || dhy < -tiny) { ilo.y = 1.0f / dhy; ihi.y = 1.0f / dly; } else { unbounded |= 2u; ilo.y = ihi.y = 0.0f; }
-    if (dlz > tiny || dhz < -tiny) { ilo.z = 1.0f / dhz; ihi.z = 1.0f / dlz; } else { unbounded |= 4u; ilo.z = ihi.z = 0.0f; }
+    if (dlx > 0.0f || dhx < 0.0f) { ilo.x = 1.0f / clamp_dir(dhx); ihi.x = 1.0f / clamp_dir(dlx); } else { unbounded |= 1u; ilo.x = 1.0f / fminf(dlx, -RT3_DIR_EPS); ihi.x = 1.0f / fmaxf(dhx, RT3_DIR_EPS); }
+    if (dly > 0.0f || dhy < 0.0f) { ilo.y = 1.0f / clamp_dir(dhy); ihi.y = 1.0f / clamp_dir(dly); } else { unbounded |= 2u; ilo.y = 1.0f / fminf(dly, -RT3_DIR_EPS); ihi.y = 1.0f / fmaxf(dhy, RT3_DIR_EPS); }
+    if (dlz > 0.0f || dhz < 0.0f) { ilo.z = 1.0f / clamp_dir(dhz); ihi.z = 1.0f / clamp_dir(dlz); } else { unbounded |= 4u; ilo.z = 1.0f / fminf(dlz, -RT3_DIR_EPS); ihi.z = 1.0f / fmaxf(dhz, RT3_DIR_EPS); }
     iabs = make_float3(fmaxf(fabsf(ilo.x), fabsf(ihi.x)), fmaxf(fabsf(ilo.y), fabsf(ihi.y)), fmaxf(fabsf(ilo.z), fabsf(ihi.z)));
     const uint32_t oct = (dlx >= 0.0f ? 1u : 0u) | (dly >= 0.0f ? 2u : 0u) | (dlz >= 0.0f ? 4u : 0u);   // the group's front-to-back order
     float ptmin = tr.tmin;   // the packet's near bound: the smallest tmin of the group (camera rays all have the same)

@@ -206,3 +206,16 @@ def test_shadow_rays_with_negative_tmax(product_lib, split):
 def test_async_frame_download(product_lib):
     from parity_common import check_async_frame_download
     check_async_frame_download(lambda: Context(0))
+
+
+def test_camera_ray_packets_with_axis_parallel_view(product_lib):
+    """camera rays are traversed in packets of eight whose direction interval is tested against the boxes; looking straight down
+    an axis puts zero inside that interval on two axes for the packets around the image centre (and on one axis along the
+    centre row and column) — the hits must still be the per-ray ones, bit for bit"""
+    desc = scenes.terrain(n=120, width=96, height=64, tex_size=64)
+    for eye, look in (((0.0, 0.5, 16.0), (0.0, 0.5, 0.0)), ((0.0, 14.0, 0.0), (0.0, 0.0, 1e-3)), ((16.0, 2.0, 0.0), (0.0, 2.0, 0.0))):
+        desc.camera = scenes.Camera(eye=eye, lookat=look, fovy=40.0)
+        for packets in (1, 0):
+            with Context(0) as e:
+                o = build_pair(desc, e, {"packets": packets})
+                check_render(e, o, desc, subframes=2)
