@@ -223,7 +223,7 @@ def issue_evidence():
     if not cand:
         return None
     txt = open(cand[-1]).read()
-    blocks = [b for b in txt.split("=" * 100) if "k_traverse<0" in b]
+    blocks = [b for b in txt.split("=" * 100) if any(k in b for k in EXTEND_KERNELS)]
     vals = {}
     for key in ("smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
                 "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum"):
