@@ -203,10 +203,12 @@ void launch_extend_packets(rt3_context* c, TraverseArgs a, uint32_t packet_rays,
 template <int MODE>
 void launch_traverse(rt3_context* c, TraverseArgs a, uint32_t* fetch2, Stream st, uint32_t packet_rays = 0) {
     a.pass = 0u;
-    // packets put FOUR independent traversals into a warp where the per-ray kernel has thirty-two: fine while nodes come from L2,
-    // latency-bound once they come from DRAM (C3 flattened, 5.9 GB of nodes and triangles: 26.6 -> 159 ms) — only for a
-    // merged BLAS that fits the L2
-    const bool packets = MODE == TRAV_EXTEND && packet_rays > 0 && c->opt_packets && (c->opt_packets >= 2 || c->m_slab.bytes() <= c->l2_bytes);
+    // packets put FOUR independent traversals into a warp where the per-ray kernel has thirty-two: fine while most nodes come from
+    // L2, latency-bound once they come from DRAM.  Measured (C2's terrain at growing size, Mrays/s without -> with packets): 1.0 M
+    // triangles / 64 MB 2656 -> 2861, 1.5 M 2561 -> 2742, 2 M / 128 MB 2506 -> 2664, 3.9 M / 250 MB 2370 -> 2472, 8 M / 512 MB
+    // 2235 -> 2265, 15.7 M / 1 GB 2101 -> 2047; C3 flattened (100 M / 5.9 GB, many silhouettes) 1326 -> 287.  Used up to four times
+    // the L2 ("packets" = 2: always)
+    const bool packets = MODE == TRAV_EXTEND && packet_rays > 0 && c->opt_packets && (c->opt_packets >= 2 || c->m_slab.bytes() <= 4 * c->l2_bytes);
     if (c->single_level) {   // merged world BLAS only: the lean instantiation
         if (packets) launch_extend_packets(c, a, packet_rays, st);
         else launch_traverse_kernel<MODE, true>(c, a, st);
