@@ -112,10 +112,21 @@ struct rt3_context {
     DevBuf<float4> accum;
     DevBuf<uchar4> frame;
     // wavefront pools
-    size_t pool_paths = 0;
-    DevBuf<float4> ray[2][3], st[2][2], hit0, sh[4], result;
-    DevBuf<int32_t> hit_inst;
-    DevBuf<uint32_t> counters;           // 2 chains x 6 x MAX_DEPTH_SLOTS
+    // Two sets ("slots") of them: consecutive subframes alternate between the slots and between two pairs of streams, so that
+    // the head of subframe k + 1 (generate, the camera-ray packets) fills the GPU while the last bounces of subframe k — a dozen
+    // launches over the few paths still alive — drain ("pipeline").  Only the resolves, which update the film in subframe
+    // order, stay on the context's stream.  Slot 1 is allocated when it is first used.
+    struct Pools {
+        size_t paths = 0;
+        DevBuf<float4> ray[2][3], st[2][2], hit0, sh[4], result;
+        DevBuf<int32_t> hit_inst;
+        DevBuf<uint32_t> counters;       // 2 chains x 6 x MAX_DEPTH_SLOTS
+        Event done;                      // recorded on the context's stream behind the resolve of the subframe that used the slot
+    } pool[2];
+    Stream pipe_stream[2][2] = {{0, 0}, {0, 0}};   // [slot][main, aux]
+    Event ev_pipe_join[2];
+    int pipe_slot = 0;
+    int opt_pipeline = 1;
     DevBuf<unsigned long long> d_stats;  // primary, bounce, shadow
     DevBuf<uint32_t> trace_fetch;        // [2]: one work counter per pass
     // options / stats
@@ -230,6 +241,7 @@ void upload_hitgroups(rt3_context* c) {
     std::vector<HitGroupDev> hg(c->inst.size() + 1);  // + the merged pseudo-instance (never shaded)
     for (size_t i = 0; i < c->inst.size(); i++) hg[i] = c->inst[i].hg;
     hg[c->inst.size()] = HitGroupDev{{0, 0, 0}, {0, 0, 0}, -1, 1.0f, {1, 1}, {0, 1}, {0, 0}, 0u, 0u};
+    stream_sync(c->stream);   // subframes in flight on the pipeline's streams still read the old records
     c->d_hg.ensure(hg.size());
     h2d(c->d_hg.p, hg.data(), sizeof(HitGroupDev) * hg.size(), c->stream);
     stream_sync(c->stream);
@@ -322,17 +334,23 @@ void set_l2_window(rt3_context* c) {
 #endif
 }
 
-void ensure_pools(rt3_context* c, size_t paths) {
-    if (paths <= c->pool_paths) return;
-    for (int b = 0; b < 2; b++) {
-        for (int k = 0; k < 3; k++) c->ray[b][k].alloc(paths);
-        for (int k = 0; k < 2; k++) c->st[b][k].alloc(paths);
+void ensure_pools(rt3_context* c, int slot, size_t paths) {
+    rt3_context::Pools& p = c->pool[slot];
+    if (!p.counters.p) {
+        p.counters.alloc(12 * MAX_DEPTH_SLOTS);  // two chains
+        dev_memset(p.counters.p, 0, p.counters.bytes(), c->stream);
     }
-    c->hit0.alloc(paths);
-    c->hit_inst.alloc(paths);
-    for (int k = 0; k < 4; k++) c->sh[k].alloc(paths);
-    c->result.alloc(paths);
-    c->pool_paths = paths;
+    if (paths <= p.paths) return;
+    stream_sync(c->stream);   // every subframe in flight ends in a resolve on this stream
+    for (int b = 0; b < 2; b++) {
+        for (int k = 0; k < 3; k++) p.ray[b][k].alloc(paths);
+        for (int k = 0; k < 2; k++) p.st[b][k].alloc(paths);
+    }
+    p.hit0.alloc(paths);
+    p.hit_inst.alloc(paths);
+    for (int k = 0; k < 4; k++) p.sh[k].alloc(paths);
+    p.result.alloc(paths);
+    p.paths = paths;
 }
 
 void ensure_film(rt3_context* c, uint32_t w, uint32_t h) {
@@ -439,11 +457,13 @@ int rt3_context_create(int device, rt3_context_t* out) {
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
+    for (int sl = 0; sl < 2; sl++)
+        for (int k = 0; k < 2; k++) RT3_CUDA(cudaStreamCreateWithFlags(&c->pipe_stream[sl][k], cudaStreamNonBlocking));
+    if (const char* e = getenv("RT3_PIPELINE")) c->opt_pipeline = atoi(e);
     if (const char* e = getenv("RT3_PACKETS")) c->opt_packets = atoi(e);
     if (const char* e = getenv("RT3_OVERLAP")) c->opt_overlap = atoi(e);  // A/B switch for measurements; rt3_set_option("overlap", v) is the API
 #endif
     c->d_flags.alloc(16);  // [0] error flags, [1] max stack, [2..15] diagnostic counters (RT3_STATS builds)
-    c->counters.alloc(12 * MAX_DEPTH_SLOTS);  // two chains
     c->d_stats.alloc(4);
     c->trace_fetch.alloc(2);
     dev_memset(c->d_flags.p, 0, c->d_flags.bytes(), c->stream);
@@ -461,8 +481,11 @@ void rt3_context_destroy(rt3_context_t c) {
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3); cudaStreamSynchronize(c->stream4); cudaStreamSynchronize(c->stream_copy);
     cudaStream_t s = c->stream, s2 = c->stream2, s3 = c->stream3, s4 = c->stream4, s5 = c->stream_copy;
+    cudaStream_t ps[4] = {c->pipe_stream[0][0], c->pipe_stream[0][1], c->pipe_stream[1][0], c->pipe_stream[1][1]};
+    for (cudaStream_t q : ps) cudaStreamSynchronize(q);
     delete c;
     cudaStreamDestroy(s); cudaStreamDestroy(s2); cudaStreamDestroy(s3); cudaStreamDestroy(s4); cudaStreamDestroy(s5);
+    for (cudaStream_t q : ps) cudaStreamDestroy(q);
 #else
     delete c;
 #endif
@@ -504,6 +527,7 @@ int rt3_set_option(rt3_context_t c, const char* key, int value) {
     else if (k == "merge_identity") { c->opt_merge = value; c->built = false; }
     else if (k == "flatten") { c->opt_flatten = value; c->built = false; }
     else if (k == "packets") c->opt_packets = value;
+    else if (k == "pipeline") c->opt_pipeline = value;
     else if (k == "split") { c->opt_split = value; c->built = false; }
     else if (k == "tlas_sah") { c->opt_tlas_sah = value; c->built = false; }
     else if (k == "bsphere_cull") { c->opt_bsphere_cull = value; c->built = false; }
@@ -1061,7 +1085,6 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
     const uint32_t P = (uint32_t)paths64;
     upload_hitgroups(c);
     ensure_film(c, rs->width, rs->height);
-    ensure_pools(c, P);
 
     FrameParams f;
     f.width = rs->width; f.height = rs->height; f.spl = rs->samples_per_launch; f.subframe = rs->subframe_index;
@@ -1088,6 +1111,13 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
     // halves issued as two independent chains on their own stream pairs, so that there is always another chain's
     // kernel to fill a tail.  Paths are independent and `result` is indexed by path id: the image is unchanged.
     const int nchains = (overlap && c->opt_overlap >= 2 && P >= (1u << 20)) ? 2 : 1;
+    // consecutive subframes alternate between two slots (pools + streams) unless something in this launch needs the host
+    const bool pipelined = overlap && nchains == 1 && c->opt_pipeline != 0;
+    const int slot = pipelined ? (c->pipe_slot ^= 1) : 0;
+    ensure_pools(c, slot, P);
+    rt3_context::Pools& pool = c->pool[slot];
+    const Stream s_main = pipelined ? c->pipe_stream[slot][0] : c->stream, s_aux = pipelined ? c->pipe_stream[slot][1] : c->stream2;
+    if (pipelined && event_recorded(pool.done)) stream_wait(s_main, pool.done);   // the slot's previous subframe has been resolved
     struct Chain {
         Stream main = 0, aux = 0;
         uint32_t base = 0, count = 0;
@@ -1096,27 +1126,27 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
         Event* ev_shade = nullptr; Event* ev_connect = nullptr;
         Queues q;
     } ch[2];
-    dev_memset(c->counters.p, 0, c->counters.bytes(), c->stream);
+    dev_memset(pool.counters.p, 0, pool.counters.bytes(), s_main);
     for (int k = 0; k < nchains; k++) {
         Chain& h = ch[k];
-        h.main = k == 0 ? c->stream : c->stream3;
-        h.aux = k == 0 ? c->stream2 : c->stream4;
+        h.main = k == 0 ? s_main : c->stream3;
+        h.aux = k == 0 ? s_aux : c->stream4;
         const uint32_t half = (P / 2u) & ~31u;
         h.base = k == 0 ? 0u : half;
         h.count = nchains == 1 ? P : (k == 0 ? half : P - half);
-        h.cnt = c->counters.p + (size_t)k * 6 * M;
-        h.ev_shade = c->ev_shade[k]; h.ev_connect = c->ev_connect[k];
+        h.cnt = pool.counters.p + (size_t)k * 6 * M;
+        h.ev_shade = c->ev_shade[pipelined ? slot : k]; h.ev_connect = c->ev_connect[pipelined ? slot : k];
     }
     auto bind = [&](Chain& h, uint32_t depth) {
         Queues& q = h.q;
         const size_t o = h.base;
-        q.ray0 = c->ray[h.cur][0].p + o; q.ray1 = c->ray[h.cur][1].p + o; q.ray2 = c->ray[h.cur][2].p + o;
-        q.st0 = c->st[h.cur][0].p + o; q.st1 = c->st[h.cur][1].p + o;
-        q.nray0 = c->ray[h.cur ^ 1][0].p + o; q.nray1 = c->ray[h.cur ^ 1][1].p + o; q.nray2 = c->ray[h.cur ^ 1][2].p + o;
-        q.nst0 = c->st[h.cur ^ 1][0].p + o; q.nst1 = c->st[h.cur ^ 1][1].p + o;
-        q.hit0 = c->hit0.p + o; q.hit_inst = c->hit_inst.p + o;
-        q.sh0 = c->sh[0].p + o; q.sh1 = c->sh[1].p + o; q.sh2 = c->sh[2].p + o; q.sh3 = c->sh[3].p + o;
-        q.result = c->result.p;
+        q.ray0 = pool.ray[h.cur][0].p + o; q.ray1 = pool.ray[h.cur][1].p + o; q.ray2 = pool.ray[h.cur][2].p + o;
+        q.st0 = pool.st[h.cur][0].p + o; q.st1 = pool.st[h.cur][1].p + o;
+        q.nray0 = pool.ray[h.cur ^ 1][0].p + o; q.nray1 = pool.ray[h.cur ^ 1][1].p + o; q.nray2 = pool.ray[h.cur ^ 1][2].p + o;
+        q.nst0 = pool.st[h.cur ^ 1][0].p + o; q.nst1 = pool.st[h.cur ^ 1][1].p + o;
+        q.hit0 = pool.hit0.p + o; q.hit_inst = pool.hit_inst.p + o;
+        q.sh0 = pool.sh[0].p + o; q.sh1 = pool.sh[1].p + o; q.sh2 = pool.sh[2].p + o; q.sh3 = pool.sh[3].p + o;
+        q.result = pool.result.p;
         q.n_cur = h.cnt + depth; q.n_next = h.cnt + depth + 1; q.n_shadow = h.cnt + M + depth;
     };
 
@@ -1199,9 +1229,11 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
         if (overlap && h.connect_pending >= 0) stream_wait(c->stream, h.ev_connect[h.connect_pending]);
         if (k > 0) { event_record(c->ev_join, h.main); stream_wait(c->stream, c->ev_join); }
     }
+    if (pipelined) { event_record(c->ev_pipe_join[slot], s_main); stream_wait(c->stream, c->ev_pipe_join[slot]); }
     if (timing) event_record(ev[2], c->stream);
     if (c->frame_copy_pending) stream_wait(c->stream, c->ev_frame_copied);   // resolve overwrites the frame a pending download reads
-    RT3_LAUNCH_1D(k_resolve, rs->width * rs->height, c->stream, f, (const float4*)c->result.p, c->accum.p, c->frame.p);
+    RT3_LAUNCH_1D(k_resolve, rs->width * rs->height, c->stream, f, (const float4*)pool.result.p, c->accum.p, c->frame.p);
+    event_record(pool.done, c->stream);   // (whatever stream this subframe ran on: a later pipelined one may take the slot)
     if (timing) {
         event_record(ev[3], c->stream);
         stream_sync(c->stream);
@@ -1377,6 +1409,7 @@ int rt3_reset_stats(rt3_context_t c) {
     RT3_API_BEGIN
     use_device(c);
     RT3_REQUIRE(c, RT3_ERR_INVALID, "reset_stats: null context");
+    stream_sync(c->stream);   // subframes in flight still count
     dev_memset(c->d_stats.p, 0, c->d_stats.bytes(), c->stream);
     dev_memset(c->d_flags.p, 0, 2 * sizeof(uint32_t), c->stream);   // error word + stack high-water mark
     c->host_flags = 0;

@@ -56,6 +56,7 @@ inline void d2d(void* d, const void* s, size_t n, Stream) { if (n) memcpy(d, s, 
 inline void dev_memset(void* d, int v, size_t n, Stream) { if (n) memset(d, v, n); }
 inline void stream_sync(Stream) {}
 inline void event_record(Event&, Stream) {}
+inline bool event_recorded(const Event&) { return false; }
 inline void stream_wait(Stream, Event&) {}
 inline float event_ms(Event&, Event&) { return 0.0f; }
 
@@ -93,6 +94,7 @@ inline void d2d(void* d, const void* s_, size_t n, Stream s) { if (n) RT3_CUDA(c
 inline void dev_memset(void* d, int v, size_t n, Stream s) { if (n) RT3_CUDA(cudaMemsetAsync(d, v, n, s)); }
 inline void stream_sync(Stream s) { RT3_CUDA(cudaStreamSynchronize(s)); }
 inline void event_record(Event& e, Stream s) { if (!e.e) RT3_CUDA(cudaEventCreate(&e.e)); RT3_CUDA(cudaEventRecord(e.e, s)); }
+inline bool event_recorded(const Event& e) { return e.e != nullptr; }
 inline void stream_wait(Stream s, Event& e) { RT3_CUDA(cudaStreamWaitEvent(s, e.e, 0)); }  // e must have been recorded
 inline float event_ms(Event& a, Event& b) { float ms = 0; RT3_CUDA(cudaEventElapsedTime(&ms, a.e, b.e)); return ms; }
 

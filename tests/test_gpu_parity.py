@@ -219,3 +219,25 @@ def test_camera_ray_packets_with_axis_parallel_view(product_lib):
             with Context(0) as e:
                 o = build_pair(desc, e, {"packets": packets})
                 check_render(e, o, desc, subframes=2)
+
+
+@pytest.mark.parametrize("name", ["cornell", "terrain", "instanced"])
+def test_many_subframes_in_flight(product_lib, name):
+    """consecutive subframes overlap on the GPU (two pool slots, alternating stream pairs; only the resolves stay in order):
+    eight of them launched back to back, the running-mean film compared with the oracle's bit for bit — with and without
+    the pipeline, and with a stats / frame read in the middle"""
+    desc = SMALL[name]()
+    for pipeline in (1, 0):
+        with Context(0) as e:
+            o = build_pair(desc, e, {"pipeline": pipeline})
+            check_render(e, o, desc, subframes=8)
+            uvw = e.camera_uvw(desc.camera.eye, desc.camera.lookat, desc.camera.up, desc.camera.fovy, desc.width / desc.height)
+            from rendertoy3c_b200.api import make_settings
+            frames = []
+            for sf in range(5):
+                e.launch_subframe(make_settings(desc, uvw, sf))
+                if sf == 2:
+                    frames.append(e.download_frame())
+                    assert e.stats()["error_flags"] == 0
+            frames.append(e.download_frame())
+            assert not np.array_equal(frames[0], frames[1])
