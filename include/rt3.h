@@ -77,7 +77,7 @@ int rt3_get_stream(rt3_context_t ctx, void** cuda_stream); /* the cudaStream_t e
 int rt3_get_stats(rt3_context_t ctx, rt3_stats* out);
 int rt3_reset_stats(rt3_context_t ctx);
 int rt3_get_debug_counters(rt3_context_t ctx, uint32_t out[16]); /* diagnostic builds (-DRT3_STATS): [2] wide nodes visited, [3] primitives tested, [4] rounds, [5] rays, [6..12] warp-round histogram, [12] = queue-full events, [13] = instance entries (rt3_traverse.cuh); reads and clears */
-int rt3_set_option(rt3_context_t ctx, const char* key, int value); /* tuning switches: "timing", "overlap" (0 = serial schedule, 1 = shadow rays of a bounce on a second stream beside the next extension (default), 2 = additionally two half-frame chains), "persist_ctas_per_sm", "merge_identity" (1 = single-level fast path for identity instances; call before rt3_accel_build), "flatten" (1, default: static transformed instances of plain triangle meshes are merged into the same world-space BLAS, vertices transformed at build — ~100 B of device memory per instanced triangle instead of a ray transform per visit; hit records then carry world-space arithmetic; needs merge_identity; not applied when the merged BLAS would exceed 2^27 triangles), "packets" (1, default: the camera rays of a subframe — depth 0 — traverse the merged BLAS in packets of eight consecutive rays, the eight lanes sharing one traversal and one wide-node test per step, when that BLAS is at most four times the L2 cache; 2 = whatever its size; 0 = never; results identical), "split" (merged BLAS beside other instances: 1, default = two launches per batch when the merged BLAS holds >= 1024 triangles — the single-level kernel, then the general kernel on the rest seeded with its result; 0 = never, 2 = always; results identical) */
+int rt3_set_option(rt3_context_t ctx, const char* key, int value); /* tuning switches: "timing", "overlap" (0 = serial schedule, 1 = shadow rays of a bounce on a second stream beside the next extension (default), 2 = additionally two half-frame chains), "persist_ctas_per_sm", "merge_identity" (1 = single-level fast path for identity instances; call before rt3_accel_build), "flatten" (1, default: static transformed instances of plain triangle meshes are merged into the same world-space BLAS, vertices transformed at build — ~100 B of device memory per instanced triangle instead of a ray transform per visit; hit records then carry world-space arithmetic; needs merge_identity; not applied when the merged BLAS would exceed 2^27 triangles), "pipeline" (1, default: consecutive rt3_launch_subframe calls overlap on the GPU — three sets of queue pools and stream pairs take turns, so the head of the next subframe fills the GPU while the last bounces of the previous ones drain; only the resolves, which update the film in subframe order, stay on the context's stream; 0 = one subframe at a time; results identical, device memory for the pools x 3), "packets" (1, default: the camera rays of a subframe — depth 0 — traverse the merged BLAS in packets of eight consecutive rays, the eight lanes sharing one traversal and one wide-node test per step, when that BLAS is at most four times the L2 cache; 2 = whatever its size; 0 = never; results identical), "split" (merged BLAS beside other instances: 1, default = two launches per batch when the merged BLAS holds >= 1024 triangles — the single-level kernel, then the general kernel on the rest seeded with its result; 0 = never, 2 = always; results identical) */
 
 /* ---- geometry (BLAS) ------------------------------------------------------------------- */
 /* CUDAMesh(ctx, mesh) src/cuda/cuda_mesh.h:33-155: uploads vertex/index/normal/uv arrays and

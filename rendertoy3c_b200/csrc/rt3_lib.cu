@@ -54,6 +54,9 @@ struct InstanceHost {
 struct TextureObj { DevBuf<uchar4> px; int w = 0, h = 0, addr = 0, filt = 0; };
 
 constexpr uint32_t MAX_DEPTH_SLOTS = 1024;
+#ifndef RT3_PIPE_SLOTS
+#define RT3_PIPE_SLOTS 3   // subframes in flight (pool sets); measured on C2: 1 -> 2863, 2 -> 2953, 3 -> see DESIGN
+#endif
 
 }  // namespace
 
@@ -112,19 +115,19 @@ struct rt3_context {
     DevBuf<float4> accum;
     DevBuf<uchar4> frame;
     // wavefront pools
-    // Two sets ("slots") of them: consecutive subframes alternate between the slots and between two pairs of streams, so that
+    // RT3_PIPE_SLOTS sets ("slots") of them: consecutive subframes rotate through the slots, each with its own pair of streams, so that
     // the head of subframe k + 1 (generate, the camera-ray packets) fills the GPU while the last bounces of subframe k — a dozen
     // launches over the few paths still alive — drain ("pipeline").  Only the resolves, which update the film in subframe
-    // order, stay on the context's stream.  Slot 1 is allocated when it is first used.
+    // order, stay on the context's stream.  The slots are allocated together, at the first pipelined launch.
     struct Pools {
         size_t paths = 0;
         DevBuf<float4> ray[2][3], st[2][2], hit0, sh[4], result;
         DevBuf<int32_t> hit_inst;
         DevBuf<uint32_t> counters;       // 2 chains x 6 x MAX_DEPTH_SLOTS
         Event done;                      // recorded on the context's stream behind the resolve of the subframe that used the slot
-    } pool[2];
-    Stream pipe_stream[2][2] = {{0, 0}, {0, 0}};   // [slot][main, aux]
-    Event ev_pipe_join[2];
+    } pool[RT3_PIPE_SLOTS];
+    Stream pipe_stream[RT3_PIPE_SLOTS][2] = {};   // [slot][main, aux]
+    Event ev_pipe_join[RT3_PIPE_SLOTS];
     int pipe_slot = 0;
     int opt_pipeline = 1;
     DevBuf<unsigned long long> d_stats;  // primary, bounce, shadow
@@ -138,7 +141,7 @@ struct rt3_context {
     Stream stream_copy = 0;                         // rt3_download_frame_async: the copy engine works beside the next subframe
     Event ev_frame_ready, ev_frame_copied;
     bool frame_copy_pending = false;
-    Event ev_shade[2][2], ev_connect[2][2], ev_fork, ev_join;
+    Event ev_shade[RT3_PIPE_SLOTS][2], ev_connect[RT3_PIPE_SLOTS][2], ev_fork, ev_join;   // [chain, or slot when pipelined][depth parity]
     int opt_ctas_per_sm = 0;
     uint64_t samples = 0;
     float ms[6] = {0, 0, 0, 0, 0, 0};
@@ -457,7 +460,7 @@ int rt3_context_create(int device, rt3_context_t* out) {
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
     RT3_CUDA(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
-    for (int sl = 0; sl < 2; sl++)
+    for (int sl = 0; sl < RT3_PIPE_SLOTS; sl++)
         for (int k = 0; k < 2; k++) RT3_CUDA(cudaStreamCreateWithFlags(&c->pipe_stream[sl][k], cudaStreamNonBlocking));
     if (const char* e = getenv("RT3_PIPELINE")) c->opt_pipeline = atoi(e);
     if (const char* e = getenv("RT3_PACKETS")) c->opt_packets = atoi(e);
@@ -481,7 +484,8 @@ void rt3_context_destroy(rt3_context_t c) {
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3); cudaStreamSynchronize(c->stream4); cudaStreamSynchronize(c->stream_copy);
     cudaStream_t s = c->stream, s2 = c->stream2, s3 = c->stream3, s4 = c->stream4, s5 = c->stream_copy;
-    cudaStream_t ps[4] = {c->pipe_stream[0][0], c->pipe_stream[0][1], c->pipe_stream[1][0], c->pipe_stream[1][1]};
+    cudaStream_t ps[2 * RT3_PIPE_SLOTS];
+    for (int sl = 0; sl < RT3_PIPE_SLOTS; sl++) { ps[2 * sl] = c->pipe_stream[sl][0]; ps[2 * sl + 1] = c->pipe_stream[sl][1]; }
     for (cudaStream_t q : ps) cudaStreamSynchronize(q);
     delete c;
     cudaStreamDestroy(s); cudaStreamDestroy(s2); cudaStreamDestroy(s3); cudaStreamDestroy(s4); cudaStreamDestroy(s5);
@@ -1113,8 +1117,9 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
     const int nchains = (overlap && c->opt_overlap >= 2 && P >= (1u << 20)) ? 2 : 1;
     // consecutive subframes alternate between two slots (pools + streams) unless something in this launch needs the host
     const bool pipelined = overlap && nchains == 1 && c->opt_pipeline != 0;
-    const int slot = pipelined ? (c->pipe_slot ^= 1) : 0;
-    ensure_pools(c, slot, P);
+    const int slot = pipelined ? (c->pipe_slot = (c->pipe_slot + 1) % RT3_PIPE_SLOTS) : 0;
+    if (pipelined) for (int sl = 0; sl < RT3_PIPE_SLOTS; sl++) ensure_pools(c, sl, P);   // all at once: no allocation in the middle of a sequence
+    else ensure_pools(c, slot, P);
     rt3_context::Pools& pool = c->pool[slot];
     const Stream s_main = pipelined ? c->pipe_stream[slot][0] : c->stream, s_aux = pipelined ? c->pipe_stream[slot][1] : c->stream2;
     if (pipelined && event_recorded(pool.done)) stream_wait(s_main, pool.done);   // the slot's previous subframe has been resolved
