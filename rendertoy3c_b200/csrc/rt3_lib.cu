@@ -463,6 +463,7 @@ int rt3_context_create(int device, rt3_context_t* out) {
     for (int sl = 0; sl < RT3_PIPE_SLOTS; sl++)
         for (int k = 0; k < 2; k++) RT3_CUDA(cudaStreamCreateWithFlags(&c->pipe_stream[sl][k], cudaStreamNonBlocking));
     if (const char* e = getenv("RT3_PIPELINE")) c->opt_pipeline = atoi(e);
+    if (const char* e = getenv("RT3_CTAS")) c->opt_ctas_per_sm = atoi(e);
     if (const char* e = getenv("RT3_PACKETS")) c->opt_packets = atoi(e);
     if (const char* e = getenv("RT3_OVERLAP")) c->opt_overlap = atoi(e);  // A/B switch for measurements; rt3_set_option("overlap", v) is the API
 #endif
