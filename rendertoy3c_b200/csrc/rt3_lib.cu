@@ -54,6 +54,11 @@ struct InstanceHost {
 struct TextureObj { DevBuf<uchar4> px; int w = 0, h = 0, addr = 0, filt = 0; };
 
 constexpr uint32_t MAX_DEPTH_SLOTS = 1024;
+#ifndef RT3_TRAV_BLOCKS_SINGLE_SHARED
+// persistent CTAs per SM of the single-level kernel while other subframes are in flight: a smaller grid leaves room for their
+// kernels (8 / 7 / 6 / 5 / 4 / 3: 2977 / 2983 / 2995 / 3010 / 3011 / 2903 Mrays/s on C2); alone on the GPU the kernel keeps its 8
+#define RT3_TRAV_BLOCKS_SINGLE_SHARED 5
+#endif
 #ifndef RT3_PIPE_SLOTS
 #define RT3_PIPE_SLOTS 3   // subframes in flight (pool sets); measured on C2: 1 -> 2863, 2 -> 2953, 3 -> see DESIGN
 #endif
@@ -129,6 +134,7 @@ struct rt3_context {
     Stream pipe_stream[RT3_PIPE_SLOTS][2] = {};   // [slot][main, aux]
     Event ev_pipe_join[RT3_PIPE_SLOTS];
     int pipe_slot = 0;
+    bool shared_gpu = false;   // this subframe is launched while earlier ones are still running: see RT3_TRAV_BLOCKS_SINGLE_SHARED
     int opt_pipeline = 1;
     DevBuf<unsigned long long> d_stats;  // primary, bounce, shadow
     DevBuf<uint32_t> trace_fetch;        // [2]: one work counter per pass
@@ -180,7 +186,7 @@ struct rt3_context {
         (void)single;
         return 1;
 #else
-        const int per_sm = opt_ctas_per_sm > 0 ? opt_ctas_per_sm : (single ? RT3_TRAV_MIN_BLOCKS_SINGLE : RT3_TRAV_MIN_BLOCKS);
+        const int per_sm = opt_ctas_per_sm > 0 ? opt_ctas_per_sm : (single ? (shared_gpu ? RT3_TRAV_BLOCKS_SINGLE_SHARED : RT3_TRAV_MIN_BLOCKS_SINGLE) : RT3_TRAV_MIN_BLOCKS);
         return num_sms * per_sm;
 #endif
     }
@@ -1124,6 +1130,12 @@ int rt3_launch_subframe(rt3_context_t c, const rt3_render_settings* rs) {
     rt3_context::Pools& pool = c->pool[slot];
     const Stream s_main = pipelined ? c->pipe_stream[slot][0] : c->stream, s_aux = pipelined ? c->pipe_stream[slot][1] : c->stream2;
     if (pipelined && event_recorded(pool.done)) stream_wait(s_main, pool.done);   // the slot's previous subframe has been resolved
+    c->shared_gpu = false;
+#ifndef RT3_EMULATE
+    if (pipelined)   // is an earlier subframe still running?  (a caller that synchronises after every subframe never sees one)
+        for (int sl = 0; sl < RT3_PIPE_SLOTS; sl++)
+            if (sl != slot && event_recorded(c->pool[sl].done) && cudaEventQuery(c->pool[sl].done.e) == cudaErrorNotReady) c->shared_gpu = true;
+#endif
     struct Chain {
         Stream main = 0, aux = 0;
         uint32_t base = 0, count = 0;
